@@ -1,0 +1,288 @@
+/*
+ * pop.h — C ABI of libpop.so, the B200-native per-replan hot path of a
+ * spatio-temporal-occupancy (SOGM) swarm planner.
+ *
+ * This is the drop-in boundary: plain C, plain pointers and sizes, no C++/torch
+ * types.  Every entry point names the reference interface it replaces
+ * (paths relative to the reference tree, file:line).  A handle owns N_local
+ * agents' SOGM grids, A* pools and QP workspaces on ONE GPU; it stands where
+ * N_local `FakeBaselinePlanner`/`BaselinePlanner` objects stood
+ * (plan_manager/src/baseline_fake.cpp:18-51, plan_manager/src/baseline.cpp:15-43).
+ *
+ * Conventions
+ *   - every function returns 0 on success, <0 on error (POP_E_*);
+ *     pop_last_error() gives the text.  Per-agent outcomes mirror the reference
+ *     enums (ASTAR_RET, bool replan, int -1/0/1 occupancy).
+ *   - all pointer arguments are HOST pointers unless the name ends in _dev.
+ *     Calls enqueue on the handle's stream and return after the results are in
+ *     the caller's buffers (they synchronise the stream) unless documented async.
+ *   - there is NO CPU fallback: if no CUDA device is usable pop_create() fails
+ *     with POP_E_NO_DEVICE.
+ */
+#ifndef POP_H_
+#define POP_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define POP_ABI_VERSION 1
+
+/* error codes */
+enum {
+  POP_OK            = 0,
+  POP_E_INVALID     = -1, /* bad argument / config */
+  POP_E_NO_DEVICE   = -2, /* no usable CUDA device (never falls back to CPU) */
+  POP_E_CUDA        = -3, /* CUDA runtime error, see pop_last_error */
+  POP_E_CAPACITY    = -4, /* a caller-provided buffer or an internal pool is too small */
+  POP_E_STATE       = -5, /* call order violated (e.g. query before first map update) */
+  POP_E_UNSUPPORTED = -6
+};
+
+/* cell storage of the SOGM */
+enum { POP_CELL_F32 = 0, POP_CELL_U8 = 1 };
+/* collision-kernel shape: FakeParticleRiskVoxel/MapBase build a single z layer
+ * (plan_env/src/fake_particle_risk_voxel.cpp:37-46, map.cpp:54-62); RiskBase a cube
+ * (plan_env/src/risk_base.cpp:31-39). */
+enum { POP_KERNEL_DISC_Z0 = 0, POP_KERNEL_CUBE = 1 };
+/* query variant: FAKE returns -1 outside [ground,ceiling] and compares the
+ * region sum with risk_threshold (fake_particle_risk_voxel.cpp:309-330); RISKBASE returns 1
+ * and compares with risk_threshold_region - t*decay (risk_base.cpp:228-250). */
+enum { POP_QUERY_FAKE = 0, POP_QUERY_RISKBASE = 1 };
+
+/* ASTAR_RET (path_searching/include/path_searching/dyn_a_star.h:15) */
+enum {
+  POP_ASTAR_NO_PATH = 0, POP_ASTAR_INIT_ERR = 1, POP_ASTAR_SEARCH_ERR = 2,
+  POP_ASTAR_REACH_HORIZON = 3, POP_ASTAR_REACH_END = 4, POP_ASTAR_NEAR_END = 5
+};
+
+/* replan outcome per agent (bool replan() in the reference, plus the stage that failed) */
+enum {
+  POP_REPLAN_OK = 0,
+  POP_REPLAN_FAIL_ASTAR = 1,       /* baseline_fake.cpp:286-289 */
+  POP_REPLAN_FAIL_CORRIDOR = 2,    /* :375-391 */
+  POP_REPLAN_FAIL_QP = 3,          /* :427-432 */
+  POP_REPLAN_FAIL_SEPARATION = 4   /* :441-446 */
+};
+
+#define POP_MAX_PIECES 12   /* trajectory_piece_max_size, baseline_fake.h:67 */
+#define POP_MAX_BODY   64   /* body particles per agent (27..36 in the reference configs) */
+#define POP_MAX_PATH   16   /* samples returned by getPathWithVel */
+#define POP_MAX_FACES  48   /* faces kept per corridor polytope */
+
+/* One ground-truth obstacle, plan_env/include/plan_env/fake_particle_risk_voxel.h:31-44.
+ * type 3 = vertical cylinder; other types are skipped by this build. */
+typedef struct pop_cylinder {
+  int32_t type;
+  int32_t _pad;
+  double  x, y, z;
+  double  w, h;
+  double  vx, vy;
+  double  qw, qx, qy, qz;
+} pop_cylinder;
+
+/* Fixed-size trajectory record, the unit of the per-cycle allgather.  Derived from
+ * traj_utils/msg/BezierTraj.msg:1-9; `duration` is float32 on the wire (msg:8), so peers
+ * evaluate with float-rounded piece durations. 1536 bytes. */
+typedef struct pop_traj_record {
+  int32_t drone_id;
+  int32_t traj_id;
+  int32_t n_pieces;      /* 0 = no trajectory published yet */
+  int32_t valid;
+  double  start_time;
+  float   duration[POP_MAX_PIECES];
+  double  cpts[POP_MAX_PIECES * 5 * 3];
+  double  _pad[3];
+} pop_traj_record;
+
+/* All run-time parameters.  The reference spreads them over compile-time #defines
+ * (plan_env/include/plan_env/map_parameters.h:5-24) and ROS params (map.cpp:15-40,
+ * fake_risk_hybrid_a_star.cpp:62-82, baseline_fake.h:84-113, particles.cpp:28-34). */
+typedef struct pop_config {
+  int32_t abi_version;            /* = POP_ABI_VERSION */
+  /* --- grid --- */
+  int32_t nx, ny, nz;             /* MAP_LENGTH/WIDTH/HEIGHT_VOXEL_NUM */
+  int32_t nt;                     /* PREDICTION_TIMES */
+  float   resolution;             /* VOXEL_RESOLUTION */
+  float   time_resolution;        /* map/time_resolution */
+  float   risk_threshold;         /* map/risk_threshold_voxel */
+  float   clearance;              /* map/clearance */
+  float   ground_height;          /* map/ground_height */
+  float   ceiling_height;         /* map/ceiling_height */
+  float   risk_threshold_region;  /* map/risk_threshold_region       (RISKBASE) */
+  float   risk_region_decay;      /* map/risk_threshold_region_decay (RISKBASE) */
+  float   risk_voxel_decay;       /* map/risk_threshold_voxel_decay  (RISKBASE) */
+  int32_t kernel_shape;           /* POP_KERNEL_* */
+  int32_t query_variant;          /* POP_QUERY_* */
+  int32_t cell_dtype;             /* POP_CELL_* */
+  /* --- swarm --- */
+  int32_t n_agents_local;         /* agents owned by this handle (this GPU) */
+  int32_t n_agents_total;         /* swarm size over all ranks */
+  int32_t agent_id_base;          /* global id of local agent 0 */
+  double  drone_size[3];          /* swarm/drone_size_{x,y,z} */
+  float   replan_risk_rate;       /* swarm/replan_risk_rate (only 0 supported) */
+  int32_t num_resample;           /* swarm/num_resample */
+  /* --- hybrid A* (search/...) --- */
+  double  max_tau, max_vel, max_acc, w_time, horizon, lambda_heu;
+  double  resolution_astar, time_resolution_astar;
+  int32_t allocate_num, check_num, tolerance;
+  int32_t _pad0;
+  /* --- corridor + optimiser (planner/..., corridor/..., optimizer/...) --- */
+  double  corridor_tau, init_range, shrink_size;
+  double  opt_max_vel, opt_max_acc;
+  /* --- capacities --- */
+  int32_t max_cloud_points;       /* world cloud capacity */
+  int32_t max_cylinders;
+  int32_t max_obstacle_points;    /* per corridor segment (reference reserves 2000) */
+  /* --- QP (OSQP settings used by traj_opt/include/iosqp.hpp:87-89 + library defaults) --- */
+  int32_t osqp_max_iter;          /* 4000 */
+  int32_t osqp_adaptive_rho_interval; /* fixed interval replacing OSQP's wall-clock rule */
+  int32_t osqp_check_termination; /* 25 */
+  double  osqp_eps_abs, osqp_eps_rel;
+} pop_config;
+
+typedef struct pop_handle pop_handle;
+
+/* ---- lifetime ------------------------------------------------------------------------ */
+/* stream: a cudaStream_t cast to void* on which all work is enqueued (NULL → own stream).
+ * Replaces FakeBaselinePlanner::init (baseline_fake.cpp:18-51). */
+int         pop_create(const pop_config* cfg, int device, void* stream, pop_handle** out);
+int         pop_destroy(pop_handle* h);
+const char* pop_last_error(const pop_handle* h);
+int         pop_abi_version(void);
+int         pop_sync(pop_handle* h);
+/* fill *cfg with the reference's simulator defaults (plan_manager/config/sim_fake.yaml) */
+void        pop_default_config(pop_config* cfg);
+
+/* ---- map inputs ------------------------------------------------------------------------ */
+/* World point cloud shared by all local agents: what arrives on "map/cloud"
+ * (fake_particle_risk_voxel.cpp:50, updateMap :80-104). pts = n x (x,y,z) float32. */
+int pop_set_world_cloud(pop_handle* h, const float* pts, int n);
+/* Ground-truth obstacle states: "map/state" (groundTruthStateCallback :244-264). */
+int pop_set_cylinders(pop_handle* h, const pop_cylinder* cyl, int n);
+/* Map centre per local agent: MapBase::pose_ set by odom/pose callbacks (map.cpp:139-168).
+ * poses = n_agents_local x 3 float32. */
+int pop_set_poses(pop_handle* h, const float* poses);
+/* Body particle offsets per GLOBAL agent: ParticleATC::particles_buffer_
+ * (particles.cpp:62-87, 90-110). offs = n_agents_total x POP_MAX_BODY x 3 doubles,
+ * counts = n_agents_total. */
+int pop_set_body_particles(pop_handle* h, const double* offs, const int32_t* counts);
+/* Peer trajectories as last received: ParticleATC::swarm_trajs_ (particles.cpp:131-191).
+ * recs = n_agents_total records indexed by global drone id. */
+int pop_set_trajectories(pop_handle* h, const pop_traj_record* recs);
+
+/* ---- K1f + K5: SOGM update ------------------------------------------------------------- */
+/* FakeParticleRiskVoxel::updateMap for every local agent (fake_particle_risk_voxel.cpp:80-222):
+ * clear, slice 0 from the cloud, future slices from the owning cylinder's velocity, then
+ * peer-trajectory particles (addParticlesToRiskMap :291-301). t_map = last_update_time_. */
+int pop_map_update_gt(pop_handle* h, double t_map);
+
+/* getClearOcccupancy(pos, int t) (fake_particle_risk_voxel.cpp:309-330 / risk_base.cpp:228-250)
+ * pos = n x 3 doubles (world), t_idx = n slice indices, out = n results in {-1,0,1}. */
+int pop_map_query(pop_handle* h, int agent, const double* pos, const int32_t* t_idx, int n,
+                  int8_t* out);
+/* getClearOcccupancy(pos, double dt) (:343-348 / risk_base.cpp:256-260). */
+int pop_map_query_dt(pop_handle* h, int agent, const double* pos, const double* dt, int n,
+                     int8_t* out);
+/* MapBase::getObstaclePoints(points, t_start, t_end, lc, hc) (map.cpp:463-531; RiskBase
+ * variant risk_base.cpp:295-337). out = cap x 3 doubles in the reference's emission order
+ * (z, y, x, slice); *n_out = number the reference would have emitted (may exceed cap →
+ * POP_E_CAPACITY with the first cap points written). */
+int pop_map_obstacle_points(pop_handle* h, int agent, double t_start, double t_end,
+                            const double lc[3], const double hc[3], double* out, int cap,
+                            int* n_out);
+/* addParticlesToRiskMap(pts, risks, t_index) (fake_particle_risk_voxel.cpp:291-301):
+ * pts are already map-frame (pose subtracted) doubles. */
+int pop_map_add_particles(pop_handle* h, int agent, const double* pts, const float* risks, int n,
+                          int t_index);
+/* Parity/debug: the grid in the reference's [VOXEL_NUM][PREDICTION_TIMES] float layout
+ * (plan_env/include/plan_env/map.h:52). out = nx*ny*nz*nt floats. */
+int pop_map_download(pop_handle* h, int agent, float* out);
+
+/* ---- K2: kinodynamic hybrid A* -------------------------------------------------------- */
+/* FakeRiskHybridAstar::reset + search(+retry with init=false) + getPathWithVel(corridor_tau)
+ * for n = n_agents_local agents (fake_risk_hybrid_a_star.cpp:85-107,114-421,663-694;
+ * call site baseline_fake.cpp:268-296).
+ *   start   n x 9  (pos, vel, acc)        goal n x 3
+ *   t_start n      (traj_start_time - map time)
+ *   out_ret n      ASTAR_RET of the search whose path is returned
+ *   out_path n x POP_MAX_PATH x 6 (pos, vel per sample), out_len n samples
+ *   out_stats n x 4 (optional, may be NULL): iterations, nodes used, retried, reserved */
+int pop_astar_search_batch(pop_handle* h, const double* start, const double* goal,
+                           const double* t_start, int32_t* out_ret, double* out_path,
+                           int32_t* out_len, int32_t* out_stats);
+
+/* ---- K3: safe flight corridors --------------------------------------------------------- */
+/* Corridor stage of replan (baseline_fake.cpp:296-411): per path segment obstacle points →
+ * firi::firi (plan_manager/include/sfc_gen/firi.hpp:238-365) → ShrinkCorridor → validity,
+ * adjacency and goal-reachability LPs (traj_utils/include/traj_utils/sdlp.hpp:708-785).
+ *   path/len as returned by pop_astar_search_batch, start n x 9, traj_start_time n (absolute)
+ *   out_hpoly n x POP_MAX_PIECES x POP_MAX_FACES x 4, out_rows n x POP_MAX_PIECES,
+ *   out_npoly n (0 = corridor stage failed), out_goal n x 6 (local goal pos, vel) */
+int pop_corridor_batch(pop_handle* h, const double* path, const int32_t* len, const double* start,
+                       const double* traj_start_time, double* out_hpoly, int32_t* out_rows,
+                       int32_t* out_npoly, double* out_goal);
+
+/* ---- K4: corridor-constrained Bézier QP ------------------------------------------------ */
+/* BezierOpt::setup + optimize + getOptCtrlPtsMat for a batch (traj_opt/src/bezier_optimizer.cpp:
+ * 27-285 → traj_opt/include/iosqp.hpp:40-115 → OSQP).
+ *   n_pieces n; init/goal n x 9 (rows pos;vel;acc); dur n x POP_MAX_PIECES;
+ *   hpoly n x POP_MAX_PIECES x POP_MAX_FACES x 4 with rows n x POP_MAX_PIECES;
+ *   out_cpts n x POP_MAX_PIECES x 5 x 3; out_status n OSQP status_val (1 solved,
+ *   2 solved inaccurate, -2 max iter, -3 primal infeasible, -4 dual infeasible);
+ *   out_iters n ADMM iterations (may be NULL). */
+int pop_qp_solve_batch(pop_handle* h, int n, const int32_t* n_pieces, const double* init,
+                       const double* goal, const double* dur, const double* hpoly,
+                       const int32_t* rows, double vmax, double amax, double* out_cpts,
+                       int32_t* out_status, int32_t* out_iters);
+
+/* ---- K6: post-optimisation separation check ------------------------------------------- */
+/* ParticleATC::isSafeAfterOpt (particles.cpp:223-283) → separator::Separator::solveModel
+ * (utils/separator/src/separator_glpk.cpp:73-246): for every local agent, its new control
+ * points against every active peer's remaining control points; out_safe n (1 safe). */
+int pop_separation_check_batch(pop_handle* h, const int32_t* n_pieces, const double* cpts,
+                               double t_now, int8_t* out_safe);
+
+/* ---- whole cycle ------------------------------------------------------------------------ */
+typedef struct pop_cycle_io {
+  /* inputs (host): */
+  const double* start;      /* n_local x 9 */
+  const double* goal;       /* n_local x 3 */
+  const float*  poses;      /* n_local x 3 map centres */
+  double        t_map;      /* map stamp of this cycle */
+  double        t_plan;     /* traj_start_time of this cycle */
+  /* outputs (host): */
+  int32_t*         status;  /* n_local POP_REPLAN_* */
+  pop_traj_record* traj;    /* n_local records (valid=1 where status==OK) */
+} pop_cycle_io;
+
+/* One replan cycle for all local agents = FakeBaselinePlanner::replan x N
+ * (baseline_fake.cpp:253-453) preceded by the map update it reads.  Host inputs are copied
+ * in, results copied out (this is the call `e2e` in bench.py times). */
+int pop_replan_cycle(pop_handle* h, const pop_cycle_io* io);
+/* Same cycle with inputs already resident on the device (uploaded by the previous
+ * pop_replan_cycle/pop_set_* calls); nothing is copied to the host. Async. */
+int pop_replan_cycle_resident(pop_handle* h, double t_map, double t_plan);
+/* Device buffers for the per-cycle trajectory allgather ("/broadcast_traj",
+ * plan_manager/src/fake_plan_manager.cpp:364-399 → particles.cpp:131-191):
+ * *send_dev = n_agents_local records produced by the last cycle,
+ * *recv_dev = n_agents_total records consumed by the next map update. */
+int pop_traj_buffers(pop_handle* h, void** send_dev, void** recv_dev);
+
+/* ---- measurement ------------------------------------------------------------------------ */
+enum { POP_STAGE_VOXEL_UPDATE = 0, POP_STAGE_PEERS = 1, POP_STAGE_ASTAR = 2, POP_STAGE_CORRIDOR = 3,
+       POP_STAGE_QP = 4, POP_STAGE_SEPARATION = 5, POP_STAGE_COUNT = 8 };
+/* Enable CUDA-event bracketing of every stage on the handle's stream. */
+int pop_profile_enable(pop_handle* h, int on);
+/* Accumulated milliseconds and launch counts per stage since the last reset. */
+int pop_profile_read(pop_handle* h, float* ms /*[POP_STAGE_COUNT]*/,
+                     int64_t* launches /*[POP_STAGE_COUNT]*/, int reset);
+/* total kernels launched by this handle since creation */
+int64_t pop_kernel_launches(const pop_handle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* POP_H_ */

@@ -1,0 +1,181 @@
+// o_map.cpp — oracle: SOGM grid, ground-truth update, occupancy queries (TEST INFRASTRUCTURE).
+// Follows plan_env/src/fake_particle_risk_voxel.cpp, plan_env/src/risk_base.cpp,
+// plan_env/src/map.cpp and plan_env/include/plan_env/map.h of the reference.
+#include <algorithm>
+
+#include "oracle.hpp"
+
+namespace orc {
+
+// fake_particle_risk_voxel.cpp:27-46 (Fake) / risk_base.cpp:25-39 (RiskBase)
+void Grid::init(const pop_config& c) {
+  nx = c.nx; ny = c.ny; nz = c.nz; nt = c.nt;
+  res = c.resolution;
+  dt = c.time_resolution;
+  rx = nx / 2 * res;  // integer half, then fp32 multiply
+  ry = ny / 2 * res;
+  rz = nz / 2 * res;
+  risk_threshold = c.risk_threshold;
+  clearance = c.clearance;
+  ground = c.ground_height;
+  ceiling = c.ceiling_height;
+  thr_region = c.risk_threshold_region;
+  decay_region = c.risk_region_decay;
+  decay_voxel = c.risk_voxel_decay;
+  query_variant = c.query_variant;
+  kernel_shape = c.kernel_shape;
+  inf_step = clearance / res;  // fp32 divide, truncation (0.45f/0.15f -> 2)
+  kernel.clear();
+  for (int x = -inf_step; x <= inf_step; x++)
+    for (int y = -inf_step; y <= inf_step; y++) {
+      if (kernel_shape == POP_KERNEL_DISC_Z0) {
+        // `for (int z = -0.3; z <= 0.3; z++)` collapses to z = 0
+        kernel.push_back(V3i{x, y, 0});
+      } else {
+        for (int z = -inf_step; z <= inf_step; z++) kernel.push_back(V3i{x, y, z});
+      }
+    }
+  pose = V3f{0.f, 0.f, 0.f};
+  t_map = 0.0;
+  risk.assign(static_cast<size_t>(V()) * nt, 0.f);
+}
+
+// fake_particle_risk_voxel.cpp:80-170
+void gt_update(Grid& g, const float* cloud, int n, const pop_cylinder* cyl, int ncyl,
+               double t_map) {
+  g.t_map = t_map;
+  const int V = g.V(), T = g.nt;
+  // PassThrough x, y, z (:88-104): keep finite points with field in [pose-range, pose+range]
+  const float xl = g.pose.x - g.rx, xh = g.pose.x + g.rx;
+  const float yl = g.pose.y - g.ry, yh = g.pose.y + g.ry;
+  const float zl = g.pose.z - g.rz, zh = g.pose.z + g.rz;
+
+  std::vector<float> tmp(static_cast<size_t>(V) * T, 0.0F);  // :106-107
+  for (int i = 0; i < n; i++) {
+    const float px = cloud[3 * i], py = cloud[3 * i + 1], pz = cloud[3 * i + 2];
+    if (!std::isfinite(px) || !std::isfinite(py) || !std::isfinite(pz)) continue;
+    if (px < xl || px > xh) continue;
+    if (py < yl || py > yh) continue;
+    if (pz < zl || pz > zh) continue;
+    V3f pt{px - g.pose.x, py - g.pose.y, pz - g.pose.z};  // :111
+    if (g.in_range(pt)) {
+      // fp32 rounding of (p + range) / res can reach nx (ny, nz) for points a hair inside the
+      // border; the reference then writes the linear index as is (bleeding into the next
+      // row/layer, out of bounds past the last layer — UB). Kept, minus the out-of-bounds write.
+      const int idx = g.index(pt);
+      if (idx >= 0 && idx < V) tmp[static_cast<size_t>(idx) * T + 0] = 1.0F;
+    }
+  }
+  std::vector<int> obs;  // :118-125
+  for (int i = 0; i < V; i++)
+    if (tmp[static_cast<size_t>(i) * T] > g.risk_threshold) obs.push_back(i);
+
+  for (int i : obs) {  // :127-162
+    V3f pt = g.voxel_position(i);
+    V3f vel{0, 0, 0};
+    for (int c = 0; c < ncyl; c++) {
+      if (cyl[c].type == 3) {
+        V3f pc{static_cast<float>(cyl[c].x), static_cast<float>(cyl[c].y), pt.z};
+        float dx = pt.x - pc.x, dy = pt.y - pc.y, dz = pt.z - pc.z;
+        float dist = std::sqrt(dx * dx + dy * dy + dz * dz);
+        if (dist <= cyl[c].w + g.clearance) {  // evaluated in double
+          vel = V3f{static_cast<float>(cyl[c].vx), static_cast<float>(cyl[c].vy), 0.0F};
+          break;
+        }
+      }
+      // type 2 (ring obstacles) and unknown types are not produced by this repo's inputs
+    }
+    for (int k = 1; k < T; k++) {
+      const float kf = static_cast<float>(k);
+      V3f pp{(pt.x + vel.x * g.dt * kf) - g.pose.x, (pt.y + vel.y * g.dt * kf) - g.pose.y,
+             (pt.z + vel.z * g.dt * kf) - g.pose.z};
+      if (g.in_range(pp)) {
+        const int idx = g.index(pp);
+        if (idx >= 0 && idx < V) tmp[static_cast<size_t>(idx) * T + k] = 1.0F;
+      }
+    }
+  }
+  g.risk.swap(tmp);  // :164-170
+}
+
+// fake_particle_risk_voxel.cpp:291-301
+void add_particles(Grid& g, const V3d* pts, const float* risks, int n, int t_index) {
+  for (int i = 0; i < n; i++) {
+    V3f p{static_cast<float>(pts[i].x), static_cast<float>(pts[i].y), static_cast<float>(pts[i].z)};
+    if (!g.in_range(p)) continue;
+    const int idx = g.index(p);
+    if (idx < 0 || idx >= g.V()) continue;  // see gt_update
+    g.at(idx, t_index) += risks[i];
+  }
+}
+
+// fake_particle_risk_voxel.cpp:309-330 / risk_base.cpp:228-250
+int query(const Grid& g, V3d pos, int t) {
+  if (g.query_variant == POP_QUERY_FAKE) {
+    if (pos.z < g.ground || pos.z > g.ceiling) return -1;
+  } else {
+    if (pos.z < g.ground) return 1;
+    if (pos.z > g.ceiling) return 1;
+  }
+  V3f pf{static_cast<float>(pos.x) - g.pose.x, static_cast<float>(pos.y) - g.pose.y,
+         static_cast<float>(pos.z) - g.pose.z};
+  V3i pi = g.rel_index(pf);
+  if (!g.in_range(pi)) return -1;
+  float sum = 0.0;
+  const float thr = g.query_variant == POP_QUERY_FAKE ? g.risk_threshold
+                                                      : g.thr_region - t * g.decay_region;
+  for (const V3i& k : g.kernel) {
+    V3i p{pi.x + k.x, pi.y + k.y, pi.z + k.z};
+    if (!g.in_range(p)) continue;
+    sum += g.at(g.index(p), t);
+    if (sum > thr) return 1;
+  }
+  return 0;
+}
+
+// fake_particle_risk_voxel.cpp:343-348 / risk_base.cpp:256-260
+int query_dt(const Grid& g, V3d pos, double dt) {
+  int tf = std::floor(dt / g.dt);
+  tf = tf > (g.nt - 1) ? g.nt - 1 : tf;
+  return query(g, pos, tf);
+}
+
+// map.cpp:463-531 (Fake inherits MapBase's) / risk_base.cpp:295-337.
+// Deviation: the reference clamps slice indices to PREDICTION_TIMES and reads
+// one slice past the end; here they are clamped to nt-1.
+void obstacle_points(const Grid& g, double t_start, double t_end, V3d lc, V3d hc,
+                     std::vector<V3d>& out) {
+  const double t0 = g.t_map;
+  int idx_start = std::floor((t_start - t0) / g.dt);
+  int idx_end = std::ceil((t_end - t0) / g.dt);
+  idx_start = idx_start < 0 ? 0 : idx_start;
+  idx_start = idx_start > g.nt - 1 ? g.nt - 1 : idx_start;
+  idx_end = idx_end > g.nt - 1 ? g.nt - 1 : idx_end;
+  idx_end = idx_end < 0 ? 0 : idx_end;
+
+  int lx = (lc.x - g.pose.x + g.rx) / g.res;  // double arithmetic, truncation
+  int ly = (lc.y - g.pose.y + g.ry) / g.res;
+  int lz = (lc.z - g.pose.z + g.rz) / g.res;
+  int hx = (hc.x - g.pose.x + g.rx) / g.res;
+  int hy = (hc.y - g.pose.y + g.ry) / g.res;
+  int hz = (hc.z - g.pose.z + g.rz) / g.res;
+  hx = std::min(hx, g.nx - 1); hy = std::min(hy, g.ny - 1); hz = std::min(hz, g.nz - 1);
+  lx = std::max(lx, 0); ly = std::max(ly, 0); lz = std::max(lz, 0);
+
+  for (int z = lz; z <= hz; z++)
+    for (int y = ly; y <= hy; y++)
+      for (int x = lx; x <= hx; x++) {
+        int i = x + y * g.nx + z * g.nx * g.ny;
+        for (int j = idx_start; j <= idx_end; j++) {
+          const float thr = g.query_variant == POP_QUERY_FAKE
+                                ? g.risk_threshold
+                                : g.risk_threshold - g.decay_voxel * j;
+          if (g.at(i, j) > thr) {
+            V3f p = g.voxel_position(i);
+            out.push_back(V3d{p.x, p.y, p.z});
+          }
+        }
+      }
+}
+
+}  // namespace orc

@@ -1,0 +1,235 @@
+"""Host side of the drop-in: Python mirror of the reference's map / planner interfaces over
+the C ABI of libpop.so.
+
+`PopEngine` owns one `pop_handle` (= N local agents on one GPU) and stands where N
+`FakeBaselinePlanner` objects stood (plan_manager/src/baseline_fake.cpp:18-51).
+`AgentMap` keeps the method names and return conventions of `FakeParticleRiskVoxel` /
+`MapBase` (plan_env/include/plan_env/fake_particle_risk_voxel.h:49-91,
+plan_env/include/plan_env/map.h:93-146) so parity tests read like reference call sites.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import (POP_MAX_BODY, POP_MAX_FACES, POP_MAX_PATH, POP_MAX_PIECES, POP_STAGE_COUNT,
+                   STAGE_NAMES, TRAJ_DTYPE, PopConfig, PopCylinder, PopError, PopTrajRecord, as_ptr)
+
+
+def _f64(a, shape=None):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    if shape is not None:
+        a = a.reshape(shape)
+    return a
+
+
+class PopEngine:
+    def __init__(self, cfg: PopConfig, device: int = 0, stream: int | None = None):
+        self.lib = _lib.load()
+        self.cfg = cfg.copy()
+        self._h = C.c_void_p()
+        rc = self.lib.pop_create(C.byref(self.cfg), device, C.c_void_p(stream or 0), C.byref(self._h))
+        if rc != 0:
+            self._h = C.c_void_p()
+            raise PopError(rc, "pop_create failed (no CUDA device → NO_DEVICE; there is no CPU fallback)")
+        self.n_local = cfg.n_agents_local
+        self.n_total = cfg.n_agents_total
+
+    # -- plumbing ----------------------------------------------------------------------------
+    def _check(self, rc: int):
+        if rc != 0:
+            raise PopError(rc, self.lib.pop_last_error(self._h).decode())
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self.lib.pop_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def sync(self):
+        self._check(self.lib.pop_sync(self._h))
+
+    # -- inputs --------------------------------------------------------------------------------
+    def set_world_cloud(self, pts: np.ndarray):
+        pts = np.ascontiguousarray(pts, dtype=np.float32).reshape(-1, 3)
+        self._check(self.lib.pop_set_world_cloud(self._h, as_ptr(pts, C.c_float), len(pts)))
+
+    def set_cylinders(self, cyl: np.ndarray):
+        cyl = np.ascontiguousarray(cyl, dtype=_lib.CYL_DTYPE)
+        self._check(self.lib.pop_set_cylinders(self._h, cyl.ctypes.data_as(C.POINTER(PopCylinder)), len(cyl)))
+
+    def set_poses(self, poses: np.ndarray):
+        poses = np.ascontiguousarray(poses, dtype=np.float32).reshape(self.n_local, 3)
+        self._check(self.lib.pop_set_poses(self._h, as_ptr(poses, C.c_float)))
+        self._poses = poses.copy()
+
+    def set_body_particles(self, offs: np.ndarray, counts: np.ndarray):
+        offs = _f64(offs, (self.n_total, POP_MAX_BODY, 3))
+        counts = np.ascontiguousarray(counts, dtype=np.int32)
+        self._check(self.lib.pop_set_body_particles(self._h, as_ptr(offs, C.c_double), as_ptr(counts, C.c_int32)))
+
+    def set_trajectories(self, recs: np.ndarray):
+        recs = np.ascontiguousarray(recs, dtype=TRAJ_DTYPE)
+        assert len(recs) == self.n_total
+        self._check(self.lib.pop_set_trajectories(self._h, recs.ctypes.data_as(C.POINTER(PopTrajRecord))))
+
+    # -- map -----------------------------------------------------------------------------------
+    def map_update_gt(self, t_map: float):
+        """FakeParticleRiskVoxel::updateMap for every local agent (K1f + K5)."""
+        self._check(self.lib.pop_map_update_gt(self._h, float(t_map)))
+        self._t_map = float(t_map)
+
+    def agent_map(self, agent: int) -> "AgentMap":
+        return AgentMap(self, agent)
+
+    # -- planning stages -----------------------------------------------------------------------
+    def astar_search_batch(self, start, goal, t_start):
+        n = self.n_local
+        start, goal, t_start = _f64(start, (n, 9)), _f64(goal, (n, 3)), _f64(t_start, (n,))
+        ret = np.zeros(n, np.int32)
+        path = np.zeros((n, POP_MAX_PATH, 6))
+        ln = np.zeros(n, np.int32)
+        stats = np.zeros((n, 4), np.int32)
+        self._check(self.lib.pop_astar_search_batch(self._h, as_ptr(start, C.c_double), as_ptr(goal, C.c_double),
+                                                    as_ptr(t_start, C.c_double), as_ptr(ret, C.c_int32),
+                                                    as_ptr(path, C.c_double), as_ptr(ln, C.c_int32),
+                                                    as_ptr(stats, C.c_int32)))
+        return ret, path, ln, stats
+
+    def corridor_batch(self, path, ln, start, traj_start_time):
+        n = self.n_local
+        path, start = _f64(path, (n, POP_MAX_PATH, 6)), _f64(start, (n, 9))
+        ln = np.ascontiguousarray(ln, np.int32)
+        tst = _f64(traj_start_time, (n,))
+        hpoly = np.zeros((n, POP_MAX_PIECES, POP_MAX_FACES, 4))
+        rows = np.zeros((n, POP_MAX_PIECES), np.int32)
+        npoly = np.zeros(n, np.int32)
+        goal = np.zeros((n, 6))
+        self._check(self.lib.pop_corridor_batch(self._h, as_ptr(path, C.c_double), as_ptr(ln, C.c_int32),
+                                                as_ptr(start, C.c_double), as_ptr(tst, C.c_double),
+                                                as_ptr(hpoly, C.c_double), as_ptr(rows, C.c_int32),
+                                                as_ptr(npoly, C.c_int32), as_ptr(goal, C.c_double)))
+        return hpoly, rows, npoly, goal
+
+    def qp_solve_batch(self, n_pieces, init, goal, dur, hpoly, rows, vmax, amax):
+        n_pieces = np.ascontiguousarray(n_pieces, np.int32)
+        n = len(n_pieces)
+        init, goal = _f64(init, (n, 9)), _f64(goal, (n, 9))
+        dur = _f64(dur, (n, POP_MAX_PIECES))
+        hpoly = _f64(hpoly, (n, POP_MAX_PIECES, POP_MAX_FACES, 4))
+        rows = np.ascontiguousarray(rows, np.int32).reshape(n, POP_MAX_PIECES)
+        cpts = np.zeros((n, POP_MAX_PIECES * 5, 3))
+        status = np.zeros(n, np.int32)
+        iters = np.zeros(n, np.int32)
+        self._check(self.lib.pop_qp_solve_batch(self._h, n, as_ptr(n_pieces, C.c_int32), as_ptr(init, C.c_double),
+                                                as_ptr(goal, C.c_double), as_ptr(dur, C.c_double),
+                                                as_ptr(hpoly, C.c_double), as_ptr(rows, C.c_int32),
+                                                float(vmax), float(amax), as_ptr(cpts, C.c_double),
+                                                as_ptr(status, C.c_int32), as_ptr(iters, C.c_int32)))
+        return cpts, status, iters
+
+    def separation_check_batch(self, n_pieces, cpts, t_now):
+        n = self.n_local
+        n_pieces = np.ascontiguousarray(n_pieces, np.int32)
+        cpts = _f64(cpts, (n, POP_MAX_PIECES * 5, 3))
+        safe = np.zeros(n, np.int8)
+        self._check(self.lib.pop_separation_check_batch(self._h, as_ptr(n_pieces, C.c_int32), as_ptr(cpts, C.c_double),
+                                                        float(t_now), as_ptr(safe, C.c_int8)))
+        return safe
+
+    def replan_cycle(self, start, goal, poses, t_map, t_plan):
+        """One full cycle with HOST inputs/outputs (map update → A* → corridor → QP → separation)."""
+        n = self.n_local
+        start, goal = _f64(start, (n, 9)), _f64(goal, (n, 3))
+        poses = np.ascontiguousarray(poses, np.float32).reshape(n, 3)
+        status = np.zeros(n, np.int32)
+        traj = np.zeros(n, TRAJ_DTYPE)
+        io = _lib.PopCycleIO(as_ptr(start, C.c_double), as_ptr(goal, C.c_double), as_ptr(poses, C.c_float),
+                             float(t_map), float(t_plan), as_ptr(status, C.c_int32),
+                             traj.ctypes.data_as(C.POINTER(PopTrajRecord)))
+        self._check(self.lib.pop_replan_cycle(self._h, C.byref(io)))
+        self._poses = poses.copy()
+        self._t_map = float(t_map)
+        return status, traj
+
+    def replan_cycle_resident(self, t_map, t_plan):
+        self._check(self.lib.pop_replan_cycle_resident(self._h, float(t_map), float(t_plan)))
+
+    def traj_buffers(self):
+        s, r = C.c_void_p(), C.c_void_p()
+        self._check(self.lib.pop_traj_buffers(self._h, C.byref(s), C.byref(r)))
+        return s.value, r.value
+
+    # -- measurement -----------------------------------------------------------------------------
+    def profile_enable(self, on: bool = True):
+        self._check(self.lib.pop_profile_enable(self._h, int(on)))
+
+    def profile_read(self, reset: bool = True):
+        ms = np.zeros(POP_STAGE_COUNT, np.float32)
+        ln = np.zeros(POP_STAGE_COUNT, np.int64)
+        self._check(self.lib.pop_profile_read(self._h, as_ptr(ms, C.c_float), as_ptr(ln, C.c_int64), int(reset)))
+        return ({STAGE_NAMES[i]: float(ms[i]) for i in range(6)},
+                {STAGE_NAMES[i]: int(ln[i]) for i in range(6)})
+
+    def kernel_launches(self) -> int:
+        return int(self.lib.pop_kernel_launches(self._h))
+
+
+class AgentMap:
+    """One agent's SOGM with the reference's method names (FakeParticleRiskVoxel / MapBase)."""
+
+    def __init__(self, eng: PopEngine, agent: int):
+        self.eng, self.agent = eng, agent
+
+    def getMapCenter(self) -> np.ndarray:
+        return self.eng._poses[self.agent].copy()
+
+    def getMapTime(self) -> float:
+        return self.eng._t_map
+
+    def getClearOcccupancy(self, pos, t=0):
+        """int t → slice index; float t → seconds after the map stamp. 0 free, 1 occupied, -1 out."""
+        pos = _f64(pos).reshape(-1, 3)
+        n = len(pos)
+        out = np.zeros(n, np.int8)
+        e = self.eng
+        if np.issubdtype(np.asarray(t).dtype, np.integer):
+            tt = np.ascontiguousarray(np.broadcast_to(np.asarray(t, np.int32), (n,)))
+            e._check(e.lib.pop_map_query(e._h, self.agent, as_ptr(pos, C.c_double), as_ptr(tt, C.c_int32), n,
+                                         as_ptr(out, C.c_int8)))
+        else:
+            tt = np.ascontiguousarray(np.broadcast_to(np.asarray(t, np.float64), (n,)))
+            e._check(e.lib.pop_map_query_dt(e._h, self.agent, as_ptr(pos, C.c_double), as_ptr(tt, C.c_double), n,
+                                            as_ptr(out, C.c_int8)))
+        return out
+
+    def getObstaclePoints(self, t_start, t_end, lower_corner, higher_corner, cap=None):
+        e = self.eng
+        cap = cap or e.cfg.max_obstacle_points
+        lc, hc = _f64(lower_corner, (3,)), _f64(higher_corner, (3,))
+        out = np.zeros((cap, 3))
+        n = C.c_int(0)
+        e._check(e.lib.pop_map_obstacle_points(e._h, self.agent, float(t_start), float(t_end), as_ptr(lc, C.c_double),
+                                               as_ptr(hc, C.c_double), as_ptr(out, C.c_double), cap, C.byref(n)))
+        return out[:n.value].copy()
+
+    def addParticlesToRiskMap(self, pts, risks, t_index: int):
+        pts = _f64(pts).reshape(-1, 3)
+        risks = np.ascontiguousarray(risks, np.float32)
+        e = self.eng
+        e._check(e.lib.pop_map_add_particles(e._h, self.agent, as_ptr(pts, C.c_double), as_ptr(risks, C.c_float),
+                                             len(pts), int(t_index)))
+
+    def risk_maps(self) -> np.ndarray:
+        """risk_maps_[VOXEL_NUM][PREDICTION_TIMES] as float32 (plan_env/include/plan_env/map.h:52)."""
+        e = self.eng
+        out = np.zeros((e.cfg.nx * e.cfg.ny * e.cfg.nz, e.cfg.nt), np.float32)
+        e._check(e.lib.pop_map_download(e._h, self.agent, as_ptr(out, C.c_float)))
+        return out

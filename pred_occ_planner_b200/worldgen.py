@@ -1,0 +1,134 @@
+"""Seeded synthetic inputs for the replan hot path (no dataset, no network).
+
+The obstacle model follows the reference simulator's ground-truth publisher:
+`MovingCylinder` (uav_simulator/map_generator/include/map_generator/moving_cylinder.h:56-124)
+— centre snapped to grid centres, solid disc fill at `res_gen` pitch from z=-0.15 m up, a
++0.01 m offset on every point, per-obstacle constant velocity — and the marker fields the
+planner-side map reads (plan_env/src/fake_particle_risk_voxel.cpp:244-264: `w` is the
+DIAMETER, `vx, vy` in m/s).  Everything is derived from numpy's Philox generator.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+
+from ._lib import CYL_DTYPE, POP_MAX_BODY, POP_MAX_PIECES, TRAJ_DTYPE
+
+
+def _rng(seed: int) -> np.random.Generator:
+    return np.random.Generator(np.random.Philox(seed))
+
+
+def make_world(seed: int, arena=(30.0, 30.0, 5.0), n_static=0, n_moving=40, v_max=1.0,
+               w_range=(0.5, 1.0), height=4.0, res_gen=0.1):
+    """Returns (cloud float32 [n,3], cylinders CYL_DTYPE [n_static+n_moving])."""
+    rng = _rng(seed)
+    ax, ay = arena[0] / 2 - 1.0, arena[1] / 2 - 1.0
+    n = n_static + n_moving
+    cyl = np.zeros(n, dtype=CYL_DTYPE)
+    clouds = []
+    for i in range(n):
+        x = rng.uniform(-ax, ax)
+        y = rng.uniform(-ay, ay)
+        w = rng.uniform(*w_range)
+        vx, vy = (rng.uniform(-v_max, v_max), rng.uniform(-v_max, v_max)) if i >= n_static else (0.0, 0.0)
+        x = math.floor(x / res_gen) * res_gen + res_gen / 2.0
+        y = math.floor(y / res_gen) * res_gen + res_gen / 2.0
+        height_num = math.ceil(height / res_gen)
+        wid_num = math.ceil(w / res_gen)
+        r0 = int(-wid_num / 2.0)  # C truncation toward zero
+        rs = np.arange(r0, math.ceil(wid_num / 2.0 - 1e-12))
+        rr, ss = np.meshgrid(rs, rs, indexing="ij")
+        keep = (rr * rr + ss * ss) <= (wid_num * wid_num / 4.0)
+        rr, ss = rr[keep], ss[keep]
+        ts = np.arange(-2, height_num)
+        px = np.repeat(x + (rr + 0.5) * res_gen + 1e-2, len(ts))
+        py = np.repeat(y + (ss + 0.5) * res_gen + 1e-2, len(ts))
+        pz = np.tile((ts + 0.5) * res_gen + 1e-2, len(rr))
+        pts = np.stack([px, py, pz], axis=1)
+        pts = np.concatenate([[[x, y, height]], pts], axis=0)
+        clouds.append(pts.astype(np.float32))
+        cyl[i] = (3, 0, x, y, 0.0, w, height, vx, vy, 1.0, 0.0, 0.0, 0.0)
+    cloud = np.concatenate(clouds, axis=0) if clouds else np.zeros((0, 3), np.float32)
+    return np.ascontiguousarray(cloud), cyl
+
+
+def circle_agents(n: int, radius: float, z: float = 1.0):
+    """Agents on a circle heading to their antipodes: (start [n,9] pos/vel/acc, goal [n,3])."""
+    ang = 2 * np.pi * np.arange(n) / n
+    start = np.zeros((n, 9))
+    start[:, 0] = radius * np.cos(ang)
+    start[:, 1] = radius * np.sin(ang)
+    start[:, 2] = z
+    goal = np.stack([-start[:, 0], -start[:, 1], np.full(n, z)], axis=1)
+    return start, np.ascontiguousarray(goal)
+
+
+def lattice_agents(n: int, arena=(50.0, 50.0), z: float = 1.0, seed: int = 0):
+    """Agents on a square lattice with shuffled goals (BASELINE config 3 style)."""
+    side = int(math.ceil(math.sqrt(n)))
+    xs = np.linspace(-arena[0] / 2 + 2, arena[0] / 2 - 2, side)
+    ys = np.linspace(-arena[1] / 2 + 2, arena[1] / 2 - 2, side)
+    gx, gy = np.meshgrid(xs, ys, indexing="ij")
+    p = np.stack([gx.ravel(), gy.ravel()], axis=1)[:n]
+    start = np.zeros((n, 9))
+    start[:, :2] = p
+    start[:, 2] = z
+    perm = _rng(seed).permutation(n)
+    goal = np.concatenate([p[perm], np.full((n, 1), z)], axis=1)
+    return start, np.ascontiguousarray(goal)
+
+
+def ego_particles(size) -> np.ndarray:
+    """ParticleATC::initEgoParticles (traj_coordinator/src/particles.cpp:62-75): body cube
+    sampled every 0.15 m with the reference's accumulating double loop."""
+    out = []
+    step = 0.15
+    x = -size[0] / 2
+    while x <= size[0] / 2:
+        y = -size[1] / 2
+        while y <= size[1] / 2:
+            z = -size[2] / 2
+            while z <= size[2] / 2:
+                out.append((x, y, z))
+                z += step
+            y += step
+        x += step
+    return np.array(out, dtype=np.float64).reshape(-1, 3)
+
+
+def body_table(n_total: int, size, ego_id: int | None = None):
+    """particles_buffer_ as every agent sees it: its own offsets exact, peers' offsets rounded
+    through float32 (`geometry_msgs/Point32`, particles.cpp:90-123)."""
+    p = ego_particles(size)
+    if len(p) > POP_MAX_BODY:
+        raise ValueError("too many body particles")
+    offs = np.zeros((n_total, POP_MAX_BODY, 3))
+    offs[:, :len(p)] = p.astype(np.float32).astype(np.float64)
+    if ego_id is not None:
+        offs[ego_id, :len(p)] = p
+    counts = np.full(n_total, len(p), dtype=np.int32)
+    return offs, counts
+
+
+def straight_trajs(start_pos: np.ndarray, goal: np.ndarray, t_start: float, speed: float,
+                   n_pieces: int, piece_dur: float) -> np.ndarray:
+    """Constant-velocity Bézier trajectories towards each goal, as TRAJ_DTYPE records."""
+    n = len(start_pos)
+    rec = np.zeros(n, dtype=TRAJ_DTYPE)
+    for i in range(n):
+        d = goal[i] - start_pos[i]
+        nrm = np.linalg.norm(d)
+        v = d / nrm * speed if nrm > 1e-9 else np.zeros(3)
+        rec["drone_id"][i] = i
+        rec["traj_id"][i] = 1
+        rec["n_pieces"][i] = n_pieces
+        rec["valid"][i] = 1
+        rec["start_time"][i] = t_start
+        for p in range(n_pieces):
+            rec["duration"][i, p] = piece_dur
+            p0 = start_pos[i] + v * piece_dur * p
+            for k in range(5):
+                rec["cpts"][i, p * 5 + k] = p0 + v * piece_dur * k / 4.0
+    return rec

@@ -1,0 +1,144 @@
+"""ctypes binding of oracle/liboracle.so — the CPU restatement used as the parity checker.
+Only tests, __graft_entry__.smoke() and bench.py's CPU-baseline legs import this."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+LIB = os.path.join(ORACLE_DIR, "liboracle.so")
+
+_lib = None
+
+
+def build():
+    subprocess.run(["make", "-C", ORACLE_DIR, "-s"], check=True)
+
+
+def load():
+    global _lib
+    if _lib is not None:
+        return _lib
+    srcs = [os.path.join(ORACLE_DIR, f) for f in os.listdir(ORACLE_DIR) if f.endswith((".cpp", ".hpp"))]
+    srcs.append(os.path.join(ROOT, "include", "pop.h"))
+    if not os.path.exists(LIB) or any(os.path.getmtime(s) > os.path.getmtime(LIB) for s in srcs):
+        build()
+    lib = C.CDLL(LIB)
+    lib.orc_map_create.restype = C.c_void_p
+    lib.orc_bezier_max_rate.restype = C.c_double
+    _lib = OracleLib(lib)
+    return _lib
+
+
+def _p(a, t):
+    return a.ctypes.data_as(C.POINTER(t))
+
+
+class OracleMap:
+    """orc::Grid — restatement of FakeParticleRiskVoxel / RiskBase map state and queries."""
+
+    def __init__(self, lib, cfg):
+        self.lib, self.cfg = lib, cfg
+        self.h = C.c_void_p(lib.orc_map_create(C.byref(cfg)))
+
+    def __del__(self):
+        try:
+            self.lib.orc_map_destroy(self.h)
+        except Exception:
+            pass
+
+    def set_pose(self, p):
+        p = np.ascontiguousarray(p, np.float32)
+        self.lib.orc_map_set_pose(self.h, _p(p, C.c_float))
+
+    def kernel_size(self):
+        return self.lib.orc_map_kernel_size(self.h)
+
+    def update_gt(self, cloud, cyl, t_map):
+        cloud = np.ascontiguousarray(cloud, np.float32).reshape(-1, 3)
+        cyl = np.ascontiguousarray(cyl)
+        self.lib.orc_map_update_gt(self.h, _p(cloud, C.c_float), len(cloud), C.c_void_p(cyl.ctypes.data), len(cyl),
+                                   C.c_double(t_map))
+
+    def add_other_agents(self, offs, counts, recs, ego_id):
+        offs = np.ascontiguousarray(offs, np.float64)
+        counts = np.ascontiguousarray(counts, np.int32)
+        recs = np.ascontiguousarray(recs)
+        self.lib.orc_map_add_other_agents(self.h, _p(offs, C.c_double), _p(counts, C.c_int32),
+                                          C.c_void_p(recs.ctypes.data), int(ego_id))
+
+    def add_particles(self, pts, risks, t):
+        pts = np.ascontiguousarray(pts, np.float64).reshape(-1, 3)
+        risks = np.ascontiguousarray(risks, np.float32)
+        self.lib.orc_map_add_particles(self.h, _p(pts, C.c_double), _p(risks, C.c_float), len(pts), int(t))
+
+    def query(self, pos, t):
+        pos = np.ascontiguousarray(pos, np.float64).reshape(-1, 3)
+        n = len(pos)
+        out = np.zeros(n, np.int8)
+        if np.issubdtype(np.asarray(t).dtype, np.integer):
+            tt = np.ascontiguousarray(np.broadcast_to(np.asarray(t, np.int32), (n,)))
+            self.lib.orc_map_query(self.h, _p(pos, C.c_double), _p(tt, C.c_int32), n, _p(out, C.c_int8))
+        else:
+            tt = np.ascontiguousarray(np.broadcast_to(np.asarray(t, np.float64), (n,)))
+            self.lib.orc_map_query_dt(self.h, _p(pos, C.c_double), _p(tt, C.c_double), n, _p(out, C.c_int8))
+        return out
+
+    def obstacle_points(self, t0, t1, lc, hc, cap=200000):
+        lc = np.ascontiguousarray(lc, np.float64)
+        hc = np.ascontiguousarray(hc, np.float64)
+        out = np.zeros((cap, 3))
+        n = self.lib.orc_map_obstacle_points(self.h, C.c_double(t0), C.c_double(t1), _p(lc, C.c_double),
+                                             _p(hc, C.c_double), _p(out, C.c_double), cap)
+        assert n <= cap
+        return out[:n].copy()
+
+    def risk_maps(self):
+        c = self.cfg
+        out = np.zeros((c.nx * c.ny * c.nz, c.nt), np.float32)
+        self.lib.orc_map_download(self.h, _p(out, C.c_float))
+        return out
+
+
+class OracleLib:
+    def __init__(self, lib):
+        self.lib = lib
+
+    def map(self, cfg) -> OracleMap:
+        return OracleMap(self.lib, cfg)
+
+    def ego_particles(self, size):
+        size = np.ascontiguousarray(size, np.float64)
+        out = np.zeros((256, 3))
+        n = self.lib.orc_ego_particles(_p(size, C.c_double), _p(out, C.c_double), 256)
+        return out[:n].copy()
+
+    def bezier_eval(self, dur, cpts, t, deriv=0):
+        dur = np.ascontiguousarray(dur, np.float64)
+        cpts = np.ascontiguousarray(cpts, np.float64).reshape(-1, 3)
+        t = np.ascontiguousarray(np.atleast_1d(t), np.float64)
+        out = np.zeros((len(t), 3))
+        self.lib.orc_bezier_eval(_p(dur, C.c_double), len(dur), _p(cpts, C.c_double), _p(t, C.c_double), len(t),
+                                 int(deriv), _p(out, C.c_double))
+        return out
+
+    def piece_eval(self, cpts, t0, tf, t, deriv=0):
+        cpts = np.ascontiguousarray(cpts, np.float64).reshape(5, 3)
+        out = np.zeros(3)
+        self.lib.orc_piece_eval(_p(cpts, C.c_double), C.c_double(t0), C.c_double(tf), C.c_double(t), int(deriv),
+                                _p(out, C.c_double))
+        return out
+
+    def bezier_max_rate(self, dur, cpts, order):
+        dur = np.ascontiguousarray(dur, np.float64)
+        cpts = np.ascontiguousarray(cpts, np.float64).reshape(-1, 3)
+        return self.lib.orc_bezier_max_rate(_p(dur, C.c_double), len(dur), _p(cpts, C.c_double), int(order))
+
+    def bernstein_coeff(self):
+        out = np.zeros(25)
+        self.lib.orc_bernstein_coeff(_p(out, C.c_double))
+        return out.reshape(5, 5)

@@ -102,4 +102,17 @@ double orc_bezier_max_rate(const double* dur, int M, const double* cpts, int ord
 }
 void orc_bernstein_coeff(double* out25) { std::copy(kBernsteinA, kBernsteinA + 25, out25); }
 
+
+// Hybrid A*: returns ASTAR_RET; path = n x 6 samples of getPathWithVel(corridor_tau)
+int orc_astar(void* h, const double* start9, const double* goal3, double t_start, double* out_path,
+              int cap, int* out_len, int* out_stats) {
+  OrcMap* m = static_cast<OrcMap*>(h);
+  AstarResult r = astar_replan(m->grid, m->cfg, start9, goal3, t_start, 0);
+  int n = static_cast<int>(r.path.size() / 6);
+  *out_len = n;
+  for (int i = 0; i < std::min(n, cap) * 6; i++) out_path[i] = r.path[i];
+  if (out_stats) { out_stats[0] = r.iters; out_stats[1] = r.nodes; out_stats[2] = r.retried; out_stats[3] = 0; }
+  return r.ret;
+}
+
 }  // extern "C"

@@ -121,6 +121,7 @@ int query(const Grid& g, V3d pos, int t) {
          static_cast<float>(pos.z) - g.pose.z};
   V3i pi = g.rel_index(pf);
   if (!g.in_range(pi)) return -1;
+  if (t < 0 || t >= g.nt) return -1;  // the reference would index risk_maps_ out of bounds
   float sum = 0.0;
   const float thr = g.query_variant == POP_QUERY_FAKE ? g.risk_threshold
                                                       : g.thr_region - t * g.decay_region;

@@ -229,7 +229,6 @@ __global__ void k_query(PopGeom g, const uint8_t* __restrict__ ag, const float* 
   } else {
     t = t_idx[i];
   }
-  if (t < 0 || t >= g.nt) { out[i] = -1; return; }  // the reference would read out of bounds
   out[i] = static_cast<int8_t>(
       geom_query<C>(g, ag, pose[0], pose[1], pose[2], pos[3 * i], pos[3 * i + 1], pos[3 * i + 2], t));
 }

@@ -97,6 +97,7 @@ __device__ __forceinline__ int geom_query(const PopGeom& g, const uint8_t* grid,
   const int iy = geom_axis_index(fy, g.ry, g.res);
   const int iz = geom_axis_index(fz, g.rz, g.res);
   if (!geom_in_range_i(g, ix, iy, iz)) return -1;
+  if (t < 0 || t >= g.nt) return -1;  // the reference would index risk_maps_ out of bounds
   const float thr = g.query_variant == POP_QUERY_FAKE
                         ? g.risk_threshold
                         : __fsub_rn(g.thr_region, __fmul_rn(static_cast<float>(t), g.decay_region));

@@ -104,3 +104,14 @@ int popk_obstacle_points(pop_handle* h, int agent, double t_start, double t_end,
 int popk_add_particles(pop_handle* h, int agent, const double* d_pts, const float* d_risks, int n,
                        int t_index);
 int popk_download(pop_handle* h, int agent, float* d_out);
+
+// planning stage launchers -------------------------------------------------------------------------
+int popk_astar_alloc(pop_handle* h);
+void popk_astar_free(pop_handle* h);
+int popk_astar_run(pop_handle* h);   // inputs resident in the A* device buffers
+double* popk_astar_path_dev(pop_handle* h);
+int* popk_astar_len_dev(pop_handle* h);
+int* popk_astar_ret_dev(pop_handle* h);
+double* popk_astar_start_dev(pop_handle* h);
+double* popk_astar_goal_dev(pop_handle* h);
+double* popk_astar_tstart_dev(pop_handle* h);

@@ -97,6 +97,16 @@ class OracleMap:
         assert n <= cap
         return out[:n].copy()
 
+    def astar(self, start9, goal3, t_start, cap=64):
+        start9 = np.ascontiguousarray(start9, np.float64).reshape(9)
+        goal3 = np.ascontiguousarray(goal3, np.float64).reshape(3)
+        path = np.zeros((cap, 6))
+        ln = C.c_int(0)
+        stats = np.zeros(4, np.int32)
+        ret = self.lib.orc_astar(self.h, _p(start9, C.c_double), _p(goal3, C.c_double), C.c_double(t_start),
+                                 _p(path, C.c_double), cap, C.byref(ln), _p(stats, C.c_int32))
+        return ret, path[:ln.value].copy(), stats
+
     def risk_maps(self):
         c = self.cfg
         out = np.zeros((c.nx * c.ny * c.nz, c.nt), np.float32)

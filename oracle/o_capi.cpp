@@ -115,4 +115,88 @@ int orc_astar(void* h, const double* start9, const double* goal3, double t_start
   return r.ret;
 }
 
+
+// sdlp::linprog<d>
+double orc_linprog(int d, const double* c, const double* A, const double* b, int m, double* x, uint64_t seed) {
+  uint64_t s = seed;
+  return linprog(d, c, A, b, m, x, &s);
+}
+
+// firi::firi on explicit inputs; returns rows (0 when firi returned false)
+int orc_firi(const double* bd24, const double* pc, int n, const double* a, const double* b, int iterations,
+             uint64_t seed, double* out_h, int cap_rows) {
+  std::vector<V3d> pts(n);
+  for (int i = 0; i < n; i++) pts[i] = V3d{pc[3 * i], pc[3 * i + 1], pc[3 * i + 2]};
+  Poly poly;
+  double r[3] = {1, 1, 1};
+  uint64_t s = seed;
+  bool ok = firi(bd24, pts, V3d{a[0], a[1], a[2]}, V3d{b[0], b[1], b[2]}, poly, r, iterations, &s);
+  if (!ok) return 0;
+  int rows = poly.rows();
+  for (int i = 0; i < std::min(rows, cap_rows) * 4; i++) out_h[i] = poly.h[i];
+  return rows;
+}
+
+// corridor stage; out_hpoly = POP_MAX_PIECES x POP_MAX_FACES x 4; returns number of corridors
+int orc_corridor(void* h, const double* path, int n, const double* start9, double traj_start_time,
+                 double* out_hpoly, int32_t* out_rows, double* out_goal) {
+  OrcMap* m = static_cast<OrcMap*>(h);
+  std::vector<double> pv(path, path + static_cast<size_t>(n) * 6);
+  CorridorResult r = corridor_stage(m->grid, m->cfg, pv, start9, traj_start_time);
+  if (!r.ok) return 0;
+  int np = static_cast<int>(r.polys.size());
+  for (int i = 0; i < std::min(np, POP_MAX_PIECES); i++) {
+    int rows = r.polys[i].rows();
+    out_rows[i] = rows;
+    for (int k = 0; k < std::min(rows, POP_MAX_FACES) * 4; k++)
+      out_hpoly[(static_cast<size_t>(i) * POP_MAX_FACES) * 4 + k] = r.polys[i].h[k];
+  }
+  for (int k = 0; k < 6; k++) out_goal[k] = r.goal[k];
+  return np;
+}
+
+
+static std::vector<Poly> polys_from(const double* hpoly, const int32_t* rows, int M) {
+  std::vector<Poly> polys(M);
+  for (int i = 0; i < M; i++)
+    polys[i].h.assign(hpoly + static_cast<size_t>(i) * POP_MAX_FACES * 4,
+                      hpoly + static_cast<size_t>(i) * POP_MAX_FACES * 4 + static_cast<size_t>(rows[i]) * 4);
+  return polys;
+}
+
+// BezierOpt::setup: returns m (rows); A (m x n), l, u, Q (n x n) written when non-null
+int orc_qp_setup(int M, const double* init9, const double* goal9, const double* dur, const double* hpoly,
+                 const int32_t* rows, double vmax, double amax, double* outQ, double* outA, double* outl,
+                 double* outu) {
+  QpProblem p;
+  qp_setup(p, init9, goal9, std::vector<double>(dur, dur + M), polys_from(hpoly, rows, M), vmax, amax);
+  if (outQ) std::copy(p.Q.begin(), p.Q.end(), outQ);
+  if (outA) std::copy(p.A.begin(), p.A.end(), outA);
+  if (outl) std::copy(p.l.begin(), p.l.end(), outl);
+  if (outu) std::copy(p.u.begin(), p.u.end(), outu);
+  return p.m;
+}
+
+// BezierOpt::setup + optimize: returns OSQP status_val; out_cpts = 5M x 3
+int orc_qp_solve(const pop_config* cfg, int M, const double* init9, const double* goal9, const double* dur,
+                 const double* hpoly, const int32_t* rows, double vmax, double amax, double* out_cpts,
+                 int* out_iters) {
+  QpProblem p;
+  qp_setup(p, init9, goal9, std::vector<double>(dur, dur + M), polys_from(hpoly, rows, M), vmax, amax);
+  OsqpSettings S;
+  S.eps_abs = cfg->osqp_eps_abs; S.eps_rel = cfg->osqp_eps_rel; S.max_iter = cfg->osqp_max_iter;
+  S.check_termination = cfg->osqp_check_termination; S.adaptive_rho_interval = cfg->osqp_adaptive_rho_interval;
+  OsqpResult r = osqp_solve(p, S);
+  for (int i = 0; i < p.n; i++) out_cpts[i] = r.x[i];
+  if (out_iters) *out_iters = r.iters;
+  return r.status;
+}
+
+int orc_separable(const double* A, int na, const double* B, int nb) {
+  std::vector<V3d> a(na), b(nb);
+  for (int i = 0; i < na; i++) a[i] = V3d{A[3 * i], A[3 * i + 1], A[3 * i + 2]};
+  for (int i = 0; i < nb; i++) b[i] = V3d{B[3 * i], B[3 * i + 1], B[3 * i + 2]};
+  return separable(a, b) ? 1 : 0;
+}
+
 }  // extern "C"

@@ -39,6 +39,8 @@ struct PopProfile {
 };
 
 struct AstarDev;   // k_astar.cu
+struct CorridorDev;  // k_corridor.cu
+struct QpDev;      // k_qp.cu
 struct PlanDev;    // corridor + QP workspaces
 
 struct pop_handle {
@@ -74,6 +76,8 @@ struct pop_handle {
   void* d_scratch = nullptr; size_t d_scratch_bytes = 0;
 
   AstarDev* astar = nullptr;
+  CorridorDev* corridor = nullptr;
+  QpDev* qp = nullptr;
   PlanDev* plan = nullptr;
   PopProfile prof;
 };
@@ -115,3 +119,13 @@ int* popk_astar_ret_dev(pop_handle* h);
 double* popk_astar_start_dev(pop_handle* h);
 double* popk_astar_goal_dev(pop_handle* h);
 double* popk_astar_tstart_dev(pop_handle* h);
+
+int popk_corridor_alloc(pop_handle* h);
+void popk_corridor_free(pop_handle* h);
+int popk_corridor_run(pop_handle* h, const double* d_path, const int* d_len, const double* d_start);
+int popk_corridor_check_err(pop_handle* h);
+double* popk_corridor_hpoly_dev(pop_handle* h);
+int* popk_corridor_rows_dev(pop_handle* h);
+int* popk_corridor_npoly_dev(pop_handle* h);
+double* popk_corridor_goal_dev(pop_handle* h);
+double* popk_corridor_tst_dev(pop_handle* h);

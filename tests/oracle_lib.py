@@ -107,6 +107,18 @@ class OracleMap:
                                  _p(path, C.c_double), cap, C.byref(ln), _p(stats, C.c_int32))
         return ret, path[:ln.value].copy(), stats
 
+    def corridor(self, path, start9, traj_start_time):
+        from pred_occ_planner_b200 import POP_MAX_FACES, POP_MAX_PIECES
+        path = np.ascontiguousarray(path, np.float64).reshape(-1, 6)
+        start9 = np.ascontiguousarray(start9, np.float64).reshape(9)
+        hp = np.zeros((POP_MAX_PIECES, POP_MAX_FACES, 4))
+        rows = np.zeros(POP_MAX_PIECES, np.int32)
+        goal = np.zeros(6)
+        n = self.lib.orc_corridor(self.h, _p(path, C.c_double), len(path), _p(start9, C.c_double),
+                                  C.c_double(traj_start_time), _p(hp, C.c_double), _p(rows, C.c_int32),
+                                  _p(goal, C.c_double))
+        return n, hp, rows, goal
+
     def risk_maps(self):
         c = self.cfg
         out = np.zeros((c.nx * c.ny * c.nz, c.nt), np.float32)
@@ -126,6 +138,72 @@ class OracleLib:
         out = np.zeros((256, 3))
         n = self.lib.orc_ego_particles(_p(size, C.c_double), _p(out, C.c_double), 256)
         return out[:n].copy()
+
+    def linprog(self, c, A, b, seed=1):
+        c = np.ascontiguousarray(c, np.float64)
+        A = np.ascontiguousarray(A, np.float64).reshape(-1, len(c))
+        b = np.ascontiguousarray(b, np.float64)
+        x = np.zeros(len(c))
+        self.lib.orc_linprog.restype = C.c_double
+        v = self.lib.orc_linprog(len(c), _p(c, C.c_double), _p(A, C.c_double), _p(b, C.c_double), len(b),
+                                 _p(x, C.c_double), C.c_uint64(seed))
+        return v, x
+
+    def firi(self, bd, pc, a, b, iterations=2, seed=1, cap=256):
+        bd = np.ascontiguousarray(bd, np.float64).reshape(6, 4)
+        pc = np.ascontiguousarray(pc, np.float64).reshape(-1, 3)
+        a = np.ascontiguousarray(a, np.float64)
+        b = np.ascontiguousarray(b, np.float64)
+        out = np.zeros((cap, 4))
+        rows = self.lib.orc_firi(_p(bd, C.c_double), _p(pc, C.c_double), len(pc), _p(a, C.c_double),
+                                 _p(b, C.c_double), int(iterations), C.c_uint64(seed), _p(out, C.c_double), cap)
+        return out[:rows].copy()
+
+    @staticmethod
+    def pack_polys(polys):
+        from pred_occ_planner_b200 import POP_MAX_FACES, POP_MAX_PIECES
+        hp = np.zeros((POP_MAX_PIECES, POP_MAX_FACES, 4))
+        rows = np.zeros(POP_MAX_PIECES, np.int32)
+        for i, h in enumerate(polys):
+            h = np.asarray(h, np.float64).reshape(-1, 4)
+            hp[i, :len(h)] = h
+            rows[i] = len(h)
+        return hp, rows
+
+    def qp_setup(self, init, goal, dur, polys, vmax=3.0, amax=3.0):
+        M = len(dur)
+        hp, rows = self.pack_polys(polys)
+        init = np.ascontiguousarray(init, np.float64).reshape(9)
+        goal = np.ascontiguousarray(goal, np.float64).reshape(9)
+        dur = np.ascontiguousarray(dur, np.float64)
+        n = 15 * M
+        args = (M, _p(init, C.c_double), _p(goal, C.c_double), _p(dur, C.c_double), _p(hp, C.c_double),
+                _p(rows, C.c_int32), C.c_double(vmax), C.c_double(amax))
+        m = self.lib.orc_qp_setup(*args, None, None, None, None)
+        Q, A, l, u = np.zeros((n, n)), np.zeros((m, n)), np.zeros(m), np.zeros(m)
+        self.lib.orc_qp_setup(*args, _p(Q, C.c_double), _p(A, C.c_double), _p(l, C.c_double), _p(u, C.c_double))
+        return Q, A, l, u
+
+    def qp_solve(self, cfg, init, goal, dur, polys=None, vmax=3.0, amax=3.0, hp=None, rows=None):
+        M = len(dur)
+        if hp is None:
+            hp, rows = self.pack_polys(polys)
+        hp = np.ascontiguousarray(hp, np.float64)
+        rows = np.ascontiguousarray(rows, np.int32)
+        init = np.ascontiguousarray(init, np.float64).reshape(9)
+        goal = np.ascontiguousarray(goal, np.float64).reshape(9)
+        dur = np.ascontiguousarray(dur, np.float64)
+        cpts = np.zeros((5 * M, 3))
+        iters = C.c_int(0)
+        st = self.lib.orc_qp_solve(C.byref(cfg), M, _p(init, C.c_double), _p(goal, C.c_double), _p(dur, C.c_double),
+                                   _p(hp, C.c_double), _p(rows, C.c_int32), C.c_double(vmax), C.c_double(amax),
+                                   _p(cpts, C.c_double), C.byref(iters))
+        return st, cpts, iters.value
+
+    def separable(self, A, B):
+        A = np.ascontiguousarray(A, np.float64).reshape(-1, 3)
+        B = np.ascontiguousarray(B, np.float64).reshape(-1, 3)
+        return bool(self.lib.orc_separable(_p(A, C.c_double), len(A), _p(B, C.c_double), len(B)))
 
     def bezier_eval(self, dur, cpts, t, deriv=0):
         dur = np.ascontiguousarray(dur, np.float64)

@@ -51,17 +51,19 @@ __device__ __forceinline__ int seg_count_or_emit(const PopGeom& g, const uint8_t
   const int bx = s.hx - s.lx + 1, by = s.hy - s.ly + 1;
   const int x = s.lx + v % bx, y = s.ly + (v / bx) % by, z = s.lz + v / (bx * by);
   const size_t i = static_cast<size_t>(x) + static_cast<size_t>(y) * g.nx + static_cast<size_t>(z) * g.nx * g.ny;
-  int c = 0;
+  // The reference emits the voxel once per slice above threshold (duplicates adjacent in its
+  // order).  Duplicates cannot change FIRI's output — an identical point is eliminated by the face
+  // its first copy generates — so each voxel is emitted once.
   for (int j = s.j0; j <= s.j1; j++) {
     const float thr = g.query_variant == POP_QUERY_FAKE
                           ? g.risk_threshold
                           : __fsub_rn(g.risk_threshold, __fmul_rn(g.decay_voxel, static_cast<float>(j)));
     if (Cell<C>::load(ag, static_cast<size_t>(j) * g.V + i) > thr) {
-      if (out && base + c < cap) out[base + c] = static_cast<int>(i);
-      c++;
+      if (out && base < cap) out[base] = static_cast<int>(i);
+      return 1;
     }
   }
-  return c;
+  return 0;
 }
 
 template <typename C>

@@ -127,7 +127,7 @@ void pop_default_config(pop_config* c) {
   c->opt_max_vel = 2.0; c->opt_max_acc = 6.0;
   c->max_cloud_points = 1 << 18;
   c->max_cylinders = 256;
-  c->max_obstacle_points = 8192;
+  c->max_obstacle_points = 16384;
   c->osqp_max_iter = 4000;
   c->osqp_adaptive_rho_interval = 25;
   c->osqp_check_termination = 25;

@@ -129,3 +129,14 @@ int* popk_corridor_rows_dev(pop_handle* h);
 int* popk_corridor_npoly_dev(pop_handle* h);
 double* popk_corridor_goal_dev(pop_handle* h);
 double* popk_corridor_tst_dev(pop_handle* h);
+
+int popk_qp_alloc(pop_handle* h, int n_agents);
+void popk_qp_free(pop_handle* h);
+int popk_qp_run(pop_handle* h, int n_agents, const double* d_hpoly, const int* d_rows, double vmax, double amax);
+int* popk_qp_npieces_dev(pop_handle* h);
+double* popk_qp_init_dev(pop_handle* h);
+double* popk_qp_goal_dev(pop_handle* h);
+double* popk_qp_dur_dev(pop_handle* h);
+double* popk_qp_cpts_dev(pop_handle* h);
+int* popk_qp_status_dev(pop_handle* h);
+int* popk_qp_iters_dev(pop_handle* h);

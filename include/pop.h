@@ -265,6 +265,12 @@ int pop_replan_cycle(pop_handle* h, const pop_cycle_io* io);
 /* Same cycle with inputs already resident on the device (uploaded by the previous
  * pop_replan_cycle/pop_set_* calls); nothing is copied to the host. Async. */
 int pop_replan_cycle_resident(pop_handle* h, double t_map, double t_plan);
+/* Results of the last enqueued cycle (synchronises): status n_local POP_REPLAN_*, traj n_local
+ * records (either may be NULL). */
+int pop_cycle_results(pop_handle* h, int32_t* status, pop_traj_record* traj);
+/* Single-rank stand-in for the allgather: copies this handle's freshly published records into
+ * its own receive buffer at [agent_id_base, agent_id_base + n_agents_local). Async. */
+int pop_traj_publish_local(pop_handle* h);
 /* Device buffers for the per-cycle trajectory allgather ("/broadcast_traj",
  * plan_manager/src/fake_plan_manager.cpp:364-399 → particles.cpp:131-191):
  * *send_dev = n_agents_local records produced by the last cycle,

@@ -199,4 +199,68 @@ int orc_separable(const double* A, int na, const double* B, int nb) {
   return separable(a, b) ? 1 : 0;
 }
 
+
+// one replan for the agent owning this map (map already updated, peers included);
+// offs/counts/recs may be null (single agent)
+int orc_replan(void* h, const double* offs, const int32_t* counts, const pop_traj_record* recs, int ego_id,
+               const double* start9, const double* goal3, double t_plan, pop_traj_record* out, int* stats) {
+  OrcMap* m = static_cast<OrcMap*>(h);
+  pop_config c = m->cfg;
+  c.agent_id_base = ego_id;  // LP shuffle seed base = global agent id
+  if (recs) {
+    Swarm s = make_swarm(m->cfg, offs, counts, recs);
+    return replan(m->grid, c, &s, ego_id, start9, goal3, t_plan, out, stats);
+  }
+  return replan(m->grid, c, nullptr, ego_id, start9, goal3, t_plan, out, stats);
+}
+
+int orc_safe_after_opt(const pop_config* cfg, const double* offs, const int32_t* counts,
+                       const pop_traj_record* recs, int ego_id, const double* cpts, int M, double t0) {
+  Swarm s = make_swarm(*cfg, offs, counts, recs);
+  std::vector<double> x(cpts, cpts + 15 * M);
+  return safe_after_opt(s, ego_id, x, M, t0) ? 1 : 0;
+}
+
+// multi-threaded batch used by bench.py's CPU-baseline legs: full cycle (map update incl. peers +
+// replan) for agents [a0, a1) of a swarm sharing one world; returns seconds of wall time
+double orc_cycle_batch(const pop_config* cfg, int a0, int a1, int n_threads, const float* cloud, int n_cloud,
+                       const pop_cylinder* cyl, int n_cyl, const float* poses, const double* offs,
+                       const int32_t* counts, const pop_traj_record* recs, const double* start, const double* goal,
+                       double t_map, double t_plan, int32_t* status_out);
+
 }  // extern "C"
+
+#include <atomic>
+#include <chrono>
+#include <thread>
+
+extern "C" double orc_cycle_batch(const pop_config* cfg, int a0, int a1, int n_threads, const float* cloud,
+                                  int n_cloud, const pop_cylinder* cyl, int n_cyl, const float* poses,
+                                  const double* offs, const int32_t* counts, const pop_traj_record* recs,
+                                  const double* start, const double* goal, double t_map, double t_plan,
+                                  int32_t* status_out) {
+  const auto t0 = std::chrono::steady_clock::now();
+  std::atomic<int> next(a0);
+  Swarm swarm;
+  if (recs) swarm = make_swarm(*cfg, offs, counts, recs);
+  auto worker = [&]() {
+    Grid g;
+    g.init(*cfg);
+    for (;;) {
+      const int a = next.fetch_add(1);
+      if (a >= a1) break;
+      const int local = a - cfg->agent_id_base;
+      g.pose = V3f{poses[3 * local], poses[3 * local + 1], poses[3 * local + 2]};
+      gt_update(g, cloud, n_cloud, cyl, n_cyl, t_map);
+      if (recs) add_other_agents(g, swarm, a);
+      pop_config c = *cfg;
+      c.agent_id_base = a;
+      status_out[local] = replan(g, c, recs ? &swarm : nullptr, a, start + 9 * local, goal + 3 * local, t_plan,
+                                 nullptr, nullptr);
+    }
+  };
+  std::vector<std::thread> th;
+  for (int i = 0; i < std::max(1, n_threads); i++) th.emplace_back(worker);
+  for (auto& t : th) t.join();
+  return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+}

@@ -1,0 +1,67 @@
+// o_replan.cpp — oracle: one replan cycle for one agent (TEST INFRASTRUCTURE).
+// Follows FakeBaselinePlanner::replan (plan_manager/src/baseline_fake.cpp:253-453) and
+// ParticleATC::isSafeAfterOpt (traj_coordinator/src/particles.cpp:223-283); the trajectory record
+// is what FiniteStateMachineFake::publishTrajectory broadcasts
+// (plan_manager/src/fake_plan_manager.cpp:364-399; durations narrowed to float32 by
+// traj_utils/msg/BezierTraj.msg:8).
+#include "oracle.hpp"
+
+namespace orc {
+
+// isSafeAfterOpt: ego control points vs every active peer's remaining control points
+bool safe_after_opt(const Swarm& s, int ego_id, const std::vector<double>& cpts, int M, double t0) {
+  std::vector<V3d> A;
+  for (int i = 0; i < 5 * M; i++) A.push_back(V3d{cpts[i * 3], cpts[i * 3 + 1], cpts[i * 3 + 2]});
+  for (int id = 0; id < s.n_agents; id++) {
+    const pop_traj_record& r = s.trajs[id];
+    if (id == ego_id || r.n_pieces <= 0) continue;
+    double t_end = r.start_time;
+    for (int i = 0; i < r.n_pieces; i++) t_end += r.duration[i];
+    if (r.start_time < t0 && t0 < t_end) {
+      double rem = t0 - r.start_time;  // locatePiece
+      int piece = r.n_pieces - 1;
+      for (int i = 0; i < r.n_pieces; i++) {
+        rem -= static_cast<double>(r.duration[i]);
+        if (rem < 0) { piece = i; break; }
+      }
+      std::vector<V3d> B;
+      for (int i = piece * 5; i < r.n_pieces * 5; i++) B.push_back(V3d{r.cpts[i * 3], r.cpts[i * 3 + 1], r.cpts[i * 3 + 2]});
+      if (!separable(A, B)) return false;
+    }
+  }
+  return true;
+}
+
+// returns POP_REPLAN_*; fills `out` on success
+int replan(const Grid& g, const pop_config& c, const Swarm* swarm, int ego_id, const double start[9],
+           const double goal[3], double t_plan, pop_traj_record* out, int* stats) {
+  AstarResult ar = astar_replan(g, c, start, goal, t_plan - g.t_map, 0);
+  if (stats) { stats[0] = ar.ret; stats[1] = ar.iters; stats[2] = 0; stats[3] = 0; }
+  if (ar.ret == POP_ASTAR_NO_PATH || ar.path.empty()) return POP_REPLAN_FAIL_ASTAR;
+  CorridorResult cr = corridor_stage(g, c, ar.path, start, t_plan);
+  if (!cr.ok || cr.polys.empty()) return POP_REPLAN_FAIL_CORRIDOR;
+  const int M = static_cast<int>(cr.polys.size());
+  if (stats) stats[2] = M;
+  double fin[9] = {cr.goal[0], cr.goal[1], cr.goal[2], cr.goal[3], cr.goal[4], cr.goal[5], 0, 0, 0};
+  QpProblem qp;
+  qp_setup(qp, start, fin, std::vector<double>(M, c.corridor_tau), cr.polys, c.opt_max_vel, c.opt_max_acc);
+  OsqpSettings S;
+  S.eps_abs = c.osqp_eps_abs; S.eps_rel = c.osqp_eps_rel; S.max_iter = c.osqp_max_iter;
+  S.check_termination = c.osqp_check_termination; S.adaptive_rho_interval = c.osqp_adaptive_rho_interval;
+  OsqpResult qr = osqp_solve(qp, S);
+  if (stats) stats[3] = qr.iters;
+  if (!(qr.status == 1 || qr.status == 2)) return POP_REPLAN_FAIL_QP;
+  if (swarm && !safe_after_opt(*swarm, ego_id, qr.x, M, t_plan)) return POP_REPLAN_FAIL_SEPARATION;
+  if (out) {
+    std::memset(out, 0, sizeof(*out));
+    out->drone_id = ego_id;
+    out->n_pieces = M;
+    out->valid = 1;
+    out->start_time = t_plan;
+    for (int i = 0; i < M; i++) out->duration[i] = static_cast<float>(c.corridor_tau);
+    for (int i = 0; i < 15 * M; i++) out->cpts[i] = qr.x[i];
+  }
+  return POP_REPLAN_OK;
+}
+
+}  // namespace orc

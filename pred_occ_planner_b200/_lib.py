@@ -130,6 +130,8 @@ SYMBOLS = [
     ("pop_separation_check_batch", _I, [_VP, _PI32, _PD, _D, _PI8]),
     ("pop_replan_cycle", _I, [_VP, C.POINTER(PopCycleIO)]),
     ("pop_replan_cycle_resident", _I, [_VP, _D, _D]),
+    ("pop_cycle_results", _I, [_VP, _PI32, C.POINTER(PopTrajRecord)]),
+    ("pop_traj_publish_local", _I, [_VP]),
     ("pop_traj_buffers", _I, [_VP, C.POINTER(_VP), C.POINTER(_VP)]),
     ("pop_profile_enable", _I, [_VP, _I]),
     ("pop_profile_read", _I, [_VP, _PF, C.POINTER(C.c_int64), _I]),

@@ -1,0 +1,283 @@
+// k_cycle.cu — K6 separation check and the fused replan cycle (stage glue, trajectory records).
+//
+// Cycle = FakeBaselinePlanner::replan for every local agent (plan_manager/src/baseline_fake.cpp:
+// 253-453) preceded by the map update it reads: SOGM update + peer projection → hybrid A* →
+// corridors → QP → ParticleATC::isSafeAfterOpt (traj_coordinator/src/particles.cpp:223-283, LP of
+// utils/separator/src/separator_glpk.cpp:73-246) → trajectory record as broadcast by
+// FiniteStateMachineFake::publishTrajectory (plan_manager/src/fake_plan_manager.cpp:364-399).
+// Everything stays on the device between stages; the host only enqueues kernels.
+#include "pop_internal.h"
+#include "pop_lp.cuh"
+
+namespace {
+
+constexpr int kSepRows = 2 * POP_MAX_PIECES * 5 + 8;  // ego pts + peer pts + box
+constexpr int kSepDoubles = 5 * kSepRows + poplp::work_doubles(kSepRows, 4);
+constexpr int kSepInts = poplp::work_ints(kSepRows);
+constexpr int kSepWarps = 148 * 8;
+
+// one warp (lane 0) per (ego, peer) pair, grid-stride over pairs
+__global__ void __launch_bounds__(128) k_separate(int n_local, int n_total, int id_base, double t0,
+                                                  const int* __restrict__ n_pieces, const int* __restrict__ qp_status,
+                                                  const double* __restrict__ cpts,
+                                                  const pop_traj_record* __restrict__ trajs, double* __restrict__ wd,
+                                                  int* __restrict__ wi, int* __restrict__ safe) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if ((threadIdx.x & 31) != 0) return;
+  const int total_warps = (gridDim.x * blockDim.x) >> 5;
+  double* rowsM = wd + static_cast<size_t>(warp) * kSepDoubles;
+  double* rhs = rowsM + 4 * kSepRows;
+  double* lpw = rhs + kSepRows;
+  int* lpi = wi + static_cast<size_t>(warp) * kSepInts;
+  for (long long pair = warp; pair < static_cast<long long>(n_local) * n_total; pair += total_warps) {
+    const int a = static_cast<int>(pair / n_total), i = static_cast<int>(pair % n_total);
+    if (i == id_base + a) continue;
+    const int M = n_pieces[a];
+    const int st = qp_status[a];
+    if (M <= 0 || !(st == 1 || st == 2)) continue;
+    const pop_traj_record& r = trajs[i];
+    if (r.n_pieces <= 0 || r.n_pieces > POP_MAX_PIECES) continue;
+    double t_end = r.start_time;
+    for (int k = 0; k < r.n_pieces; k++) t_end += r.duration[k];
+    if (!(r.start_time < t0 && t0 < t_end)) continue;
+    double rem = t0 - r.start_time;  // Bezier::locatePiece
+    int piece = r.n_pieces - 1;
+    for (int k = 0; k < r.n_pieces; k++) {
+      rem -= static_cast<double>(r.duration[k]);
+      if (rem < 0) { piece = k; break; }
+    }
+    const double* A = cpts + static_cast<size_t>(a) * POP_MAX_PIECES * 15;
+    const int na = 5 * M, nb = (r.n_pieces - piece) * 5;
+    const double* B = r.cpts + piece * 15;
+    // axis-aligned gap: an LP with margin 1 inside |n|,|d| <= 1e4 is feasible for any gap > 2e-4
+    double amin[3] = {1e300, 1e300, 1e300}, amax[3] = {-1e300, -1e300, -1e300};
+    double bmin[3] = {1e300, 1e300, 1e300}, bmax[3] = {-1e300, -1e300, -1e300};
+    for (int k = 0; k < na; k++) for (int q = 0; q < 3; q++) { amin[q] = fmin(amin[q], A[k * 3 + q]); amax[q] = fmax(amax[q], A[k * 3 + q]); }
+    for (int k = 0; k < nb; k++) for (int q = 0; q < 3; q++) { bmin[q] = fmin(bmin[q], B[k * 3 + q]); bmax[q] = fmax(bmax[q], B[k * 3 + q]); }
+    bool far = false;
+    for (int q = 0; q < 3; q++) if (bmin[q] - amax[q] > 1e-2 || amin[q] - bmax[q] > 1e-2) far = true;
+    if (far) continue;
+    int rr = 0;
+    for (int k = 0; k < na; k++) { for (int q = 0; q < 3; q++) rowsM[rr * 4 + q] = -A[k * 3 + q]; rowsM[rr * 4 + 3] = -1.0; rhs[rr] = -1.0; rr++; }
+    for (int k = 0; k < nb; k++) { for (int q = 0; q < 3; q++) rowsM[rr * 4 + q] = B[k * 3 + q]; rowsM[rr * 4 + 3] = 1.0; rhs[rr] = -1.0; rr++; }
+    for (int k = 0; k < 4; k++) {
+      for (int q = 0; q < 4; q++) { rowsM[rr * 4 + q] = q == k ? 1.0 : 0.0; rowsM[(rr + 1) * 4 + q] = q == k ? -1.0 : 0.0; }
+      rhs[rr] = 1e4; rhs[rr + 1] = 1e4;
+      rr += 2;
+    }
+    const double c[4] = {0, 0, 0, 0};
+    double x[4];
+    unsigned long long rng = 0x5eed5eedull + static_cast<unsigned long long>(na) * 131 + nb;
+    const double v = poplp::linprog<4>(c, rowsM, 4, rhs, 1, rr, x, &rng, lpw, lpi);
+    if (isinf(v)) atomicExch(&safe[a], 0);
+  }
+}
+
+__global__ void k_fill_times(int n, double t_rel, double t_abs, double* tstart, double* tst, int* safe) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  tstart[i] = t_rel;
+  tst[i] = t_abs;
+  safe[i] = 1;
+}
+
+// QP inputs from the A* / corridor outputs (baseline_fake.cpp:393-427)
+__global__ void k_prepare_qp(int n, double tau, const double* __restrict__ start, const int* __restrict__ ret,
+                             const int* __restrict__ npoly, const double* __restrict__ cgoal,
+                             int* __restrict__ n_pieces, double* __restrict__ init, double* __restrict__ goal,
+                             double* __restrict__ dur) {
+  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= n) return;
+  const int M = ret[a] == POP_ASTAR_NO_PATH ? 0 : npoly[a];
+  n_pieces[a] = M;
+  for (int k = 0; k < 9; k++) init[a * 9 + k] = start[a * 9 + k];
+  for (int k = 0; k < 6; k++) goal[a * 9 + k] = cgoal[a * 6 + k];
+  for (int k = 6; k < 9; k++) goal[a * 9 + k] = 0.0;
+  for (int k = 0; k < POP_MAX_PIECES; k++) dur[a * POP_MAX_PIECES + k] = k < M ? tau : 0.0;
+}
+
+__global__ void k_finalize(int n, int id_base, double t_plan, double tau, const int* __restrict__ ret,
+                           const int* __restrict__ npoly, const int* __restrict__ qp_status,
+                           const int* __restrict__ safe, const double* __restrict__ cpts,
+                           int* __restrict__ status, pop_traj_record* __restrict__ send, int* __restrict__ traj_ids) {
+  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= n) return;
+  int st = POP_REPLAN_OK;
+  if (ret[a] == POP_ASTAR_NO_PATH || ret[a] == POP_ASTAR_SEARCH_ERR) st = POP_REPLAN_FAIL_ASTAR;
+  else if (npoly[a] <= 0) st = POP_REPLAN_FAIL_CORRIDOR;
+  else if (!(qp_status[a] == 1 || qp_status[a] == 2)) st = POP_REPLAN_FAIL_QP;
+  else if (!safe[a]) st = POP_REPLAN_FAIL_SEPARATION;
+  status[a] = st;
+  if (st != POP_REPLAN_OK) return;  // nothing is published; peers keep the previous trajectory
+  pop_traj_record& r = send[a];
+  const int M = npoly[a];
+  r.drone_id = id_base + a;
+  r.traj_id = ++traj_ids[a];
+  r.n_pieces = M;
+  r.valid = 1;
+  r.start_time = t_plan;
+  for (int k = 0; k < POP_MAX_PIECES; k++) r.duration[k] = k < M ? static_cast<float>(tau) : 0.f;
+  const double* c = cpts + static_cast<size_t>(a) * POP_MAX_PIECES * 15;
+  for (int k = 0; k < POP_MAX_PIECES * 15; k++) r.cpts[k] = k < 15 * M ? c[k] : 0.0;
+}
+
+}  // namespace
+
+struct PlanDev {
+  double* sep_wd = nullptr;
+  int* sep_wi = nullptr;
+  int* safe = nullptr;      // [n_local]
+  int* status = nullptr;    // [n_local]
+  int* traj_ids = nullptr;  // [n_local]
+  int* sep_np = nullptr;    // staging for pop_separation_check_batch
+  int* sep_st = nullptr;
+  double* sep_cpts = nullptr;
+};
+
+static int plan_alloc(pop_handle* h) {
+  if (h->plan) return POP_OK;
+  PlanDev* d = new PlanDev();
+  h->plan = d;
+  const int nl = h->cfg.n_agents_local;
+  bool ok = true;
+  ok &= cudaMalloc(&d->sep_wd, sizeof(double) * kSepDoubles * kSepWarps) == cudaSuccess;
+  ok &= cudaMalloc(&d->sep_wi, sizeof(int) * kSepInts * kSepWarps) == cudaSuccess;
+  ok &= cudaMalloc(&d->safe, sizeof(int) * nl) == cudaSuccess;
+  ok &= cudaMalloc(&d->status, sizeof(int) * nl) == cudaSuccess;
+  ok &= cudaMalloc(&d->traj_ids, sizeof(int) * nl) == cudaSuccess;
+  ok &= cudaMalloc(&d->sep_np, sizeof(int) * nl) == cudaSuccess;
+  ok &= cudaMalloc(&d->sep_st, sizeof(int) * nl) == cudaSuccess;
+  ok &= cudaMalloc(&d->sep_cpts, sizeof(double) * POP_MAX_PIECES * 15 * nl) == cudaSuccess;
+  if (!ok) { cudaGetLastError(); return pop_fail(h, POP_E_CUDA, "cycle workspace allocation failed"); }
+  POP_CUDA(h, cudaMemsetAsync(d->traj_ids, 0, sizeof(int) * nl, h->stream));
+  POP_CUDA(h, cudaMemsetAsync(d->status, 0, sizeof(int) * nl, h->stream));
+  return POP_OK;
+}
+
+void pop_plan_free(pop_handle* h) {
+  popk_astar_free(h);
+  popk_corridor_free(h);
+  popk_qp_free(h);
+  PlanDev* d = h->plan;
+  if (!d) return;
+  void* ptrs[] = {d->sep_wd, d->sep_wi, d->safe, d->status, d->traj_ids, d->sep_np, d->sep_st, d->sep_cpts};
+  for (void* p : ptrs) if (p) cudaFree(p);
+  delete d;
+  h->plan = nullptr;
+}
+
+static int run_separation(pop_handle* h, double t_now, const int* d_np, const int* d_st, const double* d_cpts) {
+  PlanDev* d = h->plan;
+  pop_prof_begin(h, POP_STAGE_SEPARATION);
+  int launches = 0;
+  if (h->have_traj && h->cfg.n_agents_total > 1) {
+    k_separate<<<kSepWarps / 4, 128, 0, h->stream>>>(h->cfg.n_agents_local, h->cfg.n_agents_total, h->cfg.agent_id_base,
+                                                     t_now, d_np, d_st, d_cpts, h->d_traj_all, d->sep_wd, d->sep_wi,
+                                                     d->safe);
+    POP_LAUNCH_CHECK(h);
+    launches = 1;
+  }
+  pop_prof_end(h, POP_STAGE_SEPARATION, launches);
+  return POP_OK;
+}
+
+// the whole cycle on the stream; inputs (cloud, cylinders, poses, peers, start, goal) resident
+static int cycle_enqueue(pop_handle* h, double t_map, double t_plan) {
+  int rc;
+  if ((rc = popk_astar_alloc(h))) return rc;
+  if ((rc = popk_corridor_alloc(h))) return rc;
+  if ((rc = popk_qp_alloc(h, h->cfg.n_agents_local))) return rc;
+  if ((rc = plan_alloc(h))) return rc;
+  PlanDev* d = h->plan;
+  const pop_config& c = h->cfg;
+  const int nl = c.n_agents_local;
+  h->t_map = t_map;
+  if ((rc = popk_voxel_update(h))) return rc;
+  if ((rc = popk_peer_project(h))) return rc;
+  h->map_ready = true;
+  k_fill_times<<<(nl + 127) / 128, 128, 0, h->stream>>>(nl, t_plan - t_map, t_plan, popk_astar_tstart_dev(h),
+                                                       popk_corridor_tst_dev(h), d->safe);
+  POP_LAUNCH_CHECK(h);
+  if ((rc = popk_astar_run(h))) return rc;
+  if ((rc = popk_corridor_run(h, popk_astar_path_dev(h), popk_astar_len_dev(h), popk_astar_start_dev(h)))) return rc;
+  k_prepare_qp<<<(nl + 127) / 128, 128, 0, h->stream>>>(nl, c.corridor_tau, popk_astar_start_dev(h),
+                                                       popk_astar_ret_dev(h), popk_corridor_npoly_dev(h),
+                                                       popk_corridor_goal_dev(h), popk_qp_npieces_dev(h),
+                                                       popk_qp_init_dev(h), popk_qp_goal_dev(h), popk_qp_dur_dev(h));
+  POP_LAUNCH_CHECK(h);
+  if ((rc = popk_qp_run(h, nl, popk_corridor_hpoly_dev(h), popk_corridor_rows_dev(h), c.opt_max_vel, c.opt_max_acc))) return rc;
+  if ((rc = run_separation(h, t_plan, popk_qp_npieces_dev(h), popk_qp_status_dev(h), popk_qp_cpts_dev(h)))) return rc;
+  k_finalize<<<(nl + 127) / 128, 128, 0, h->stream>>>(nl, c.agent_id_base, t_plan, c.corridor_tau, popk_astar_ret_dev(h),
+                                                     popk_qp_npieces_dev(h), popk_qp_status_dev(h), d->safe,
+                                                     popk_qp_cpts_dev(h), d->status, h->d_traj_send, d->traj_ids);
+  POP_LAUNCH_CHECK(h);
+  h->n_launches += 3;
+  return POP_OK;
+}
+
+extern "C" {
+
+int pop_separation_check_batch(pop_handle* h, const int32_t* n_pieces, const double* cpts, double t_now,
+                               int8_t* out_safe) {
+  if (!h || !n_pieces || !cpts || !out_safe) return POP_E_INVALID;
+  int rc = plan_alloc(h);
+  if (rc) return rc;
+  PlanDev* d = h->plan;
+  const int nl = h->cfg.n_agents_local;
+  std::vector<int> ones(nl, 1);
+  for (int i = 0; i < nl; i++) if (n_pieces[i] < 0 || n_pieces[i] > POP_MAX_PIECES) return POP_E_INVALID;
+  POP_CUDA(h, cudaMemcpyAsync(d->sep_np, n_pieces, sizeof(int) * nl, cudaMemcpyHostToDevice, h->stream));
+  POP_CUDA(h, cudaMemcpyAsync(d->sep_st, ones.data(), sizeof(int) * nl, cudaMemcpyHostToDevice, h->stream));
+  POP_CUDA(h, cudaMemcpyAsync(d->safe, ones.data(), sizeof(int) * nl, cudaMemcpyHostToDevice, h->stream));
+  POP_CUDA(h, cudaMemcpyAsync(d->sep_cpts, cpts, sizeof(double) * POP_MAX_PIECES * 15 * nl, cudaMemcpyHostToDevice, h->stream));
+  rc = run_separation(h, t_now, d->sep_np, d->sep_st, d->sep_cpts);
+  if (rc) return rc;
+  std::vector<int> safe(nl);
+  POP_CUDA(h, cudaMemcpyAsync(safe.data(), d->safe, sizeof(int) * nl, cudaMemcpyDeviceToHost, h->stream));
+  POP_CUDA(h, cudaStreamSynchronize(h->stream));
+  for (int i = 0; i < nl; i++) out_safe[i] = static_cast<int8_t>(safe[i]);
+  return POP_OK;
+}
+
+int pop_replan_cycle_resident(pop_handle* h, double t_map, double t_plan) {
+  if (!h) return POP_E_INVALID;
+  if (!h->astar) return pop_fail(h, POP_E_STATE, "no resident inputs: call pop_replan_cycle (or pop_astar_search_batch) once first");
+  return cycle_enqueue(h, t_map, t_plan);
+}
+
+int pop_replan_cycle(pop_handle* h, const pop_cycle_io* io) {
+  if (!h || !io || !io->start || !io->goal || !io->poses || !io->status || !io->traj) return POP_E_INVALID;
+  int rc;
+  if ((rc = popk_astar_alloc(h))) return rc;
+  if ((rc = plan_alloc(h))) return rc;
+  const int nl = h->cfg.n_agents_local;
+  POP_CUDA(h, cudaMemcpyAsync(h->d_poses, io->poses, sizeof(float) * 3 * nl, cudaMemcpyHostToDevice, h->stream));
+  POP_CUDA(h, cudaMemcpyAsync(popk_astar_start_dev(h), io->start, sizeof(double) * 9 * nl, cudaMemcpyHostToDevice, h->stream));
+  POP_CUDA(h, cudaMemcpyAsync(popk_astar_goal_dev(h), io->goal, sizeof(double) * 3 * nl, cudaMemcpyHostToDevice, h->stream));
+  if ((rc = cycle_enqueue(h, io->t_map, io->t_plan))) return rc;
+  POP_CUDA(h, cudaMemcpyAsync(io->status, h->plan->status, sizeof(int) * nl, cudaMemcpyDeviceToHost, h->stream));
+  POP_CUDA(h, cudaMemcpyAsync(io->traj, h->d_traj_send, sizeof(pop_traj_record) * nl, cudaMemcpyDeviceToHost, h->stream));
+  POP_CUDA(h, cudaStreamSynchronize(h->stream));
+  for (int i = 0; i < nl; i++) if (io->status[i] != POP_REPLAN_OK) io->traj[i].valid = 0;
+  return popk_corridor_check_err(h);
+}
+
+}  // extern "C"
+
+extern "C" int pop_cycle_results(pop_handle* h, int32_t* status, pop_traj_record* traj) {
+  if (!h) return POP_E_INVALID;
+  if (!h->plan) return pop_fail(h, POP_E_STATE, "no cycle has run yet");
+  const int nl = h->cfg.n_agents_local;
+  if (status) POP_CUDA(h, cudaMemcpyAsync(status, h->plan->status, sizeof(int) * nl, cudaMemcpyDeviceToHost, h->stream));
+  if (traj) POP_CUDA(h, cudaMemcpyAsync(traj, h->d_traj_send, sizeof(pop_traj_record) * nl, cudaMemcpyDeviceToHost, h->stream));
+  POP_CUDA(h, cudaStreamSynchronize(h->stream));
+  return popk_corridor_check_err(h);
+}
+
+extern "C" int pop_traj_publish_local(pop_handle* h) {
+  if (!h) return POP_E_INVALID;
+  POP_CUDA(h, cudaMemcpyAsync(h->d_traj_all + h->cfg.agent_id_base, h->d_traj_send,
+                              sizeof(pop_traj_record) * h->cfg.n_agents_local, cudaMemcpyDeviceToDevice, h->stream));
+  h->have_traj = true;
+  return POP_OK;
+}

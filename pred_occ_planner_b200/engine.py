@@ -162,6 +162,16 @@ class PopEngine:
     def replan_cycle_resident(self, t_map, t_plan):
         self._check(self.lib.pop_replan_cycle_resident(self._h, float(t_map), float(t_plan)))
 
+    def cycle_results(self):
+        status = np.zeros(self.n_local, np.int32)
+        traj = np.zeros(self.n_local, TRAJ_DTYPE)
+        self._check(self.lib.pop_cycle_results(self._h, as_ptr(status, C.c_int32),
+                                               traj.ctypes.data_as(C.POINTER(PopTrajRecord))))
+        return status, traj
+
+    def traj_publish_local(self):
+        self._check(self.lib.pop_traj_publish_local(self._h))
+
     def traj_buffers(self):
         s, r = C.c_void_p(), C.c_void_p()
         self._check(self.lib.pop_traj_buffers(self._h, C.byref(s), C.byref(r)))

@@ -1,0 +1,119 @@
+"""End-to-end parity of the fused replan cycle (SOGM update + peers → A* → corridors → QP →
+separation → trajectory record) against the oracle, through pop_replan_cycle (host buffers).
+Trajectory coefficients within 1e-4 relative, replan status identical."""
+import numpy as np
+import pytest
+
+import pred_occ_planner_b200 as p
+from tests import cases, oracle_cycle
+
+pytestmark = pytest.mark.gpu
+
+
+def _oracle_cycle(oracle, cfg, cloud, cyl, poses, swarm, start, goal, t_map, t_plan):
+    out = []
+    for a in range(cfg.n_agents_local):
+        gid = cfg.agent_id_base + a
+        m = oracle.map(cfg)
+        m.set_pose(poses[a])
+        m.update_gt(cloud, cyl, t_map)
+        if swarm is not None:
+            m.add_other_agents(swarm[0], swarm[1], swarm[2], gid)
+        out.append(oracle_cycle.replan(m, swarm, gid, start[a], goal[a], t_plan))
+    return out
+
+
+def _compare(status, traj, ref):
+    bad = []
+    for a, (st, rec, stats) in enumerate(ref):
+        ok = st == status[a]
+        if ok and st == 0:
+            M = int(rec["n_pieces"])
+            ok = traj["n_pieces"][a] == M and traj["valid"][a] == 1 and traj["start_time"][a] == rec["start_time"]
+            if ok:
+                g, r = traj["cpts"][a][:5 * M], rec["cpts"][:5 * M]
+                ok = np.abs(g - r).max() <= 1e-4 * max(1.0, np.abs(r).max())
+                ok = ok and np.array_equal(traj["duration"][a][:M], rec["duration"][:M])
+        if not ok:
+            bad.append((a, int(st), int(status[a]), stats.tolist()))
+    return bad
+
+
+def test_single_agent_c1(oracle):
+    cfg = cases.cfg_c1(p.POP_CELL_U8)
+    cloud, cyl = cases.world_c1()
+    start = np.zeros((1, 9))
+    start[0, :3] = [-4, 0, 1.0]
+    goal = np.array([[4.0, 0, 1.0]])
+    poses = start[:, :3].astype(np.float32)
+    eng = p.PopEngine(cfg)
+    eng.set_world_cloud(cloud)
+    eng.set_cylinders(cyl)
+    status, traj = eng.replan_cycle(start, goal, poses, 10.0, 10.02)
+    ref = _oracle_cycle(oracle, cfg, cloud, cyl, poses, None, start, goal, 10.0, 10.02)
+    assert not _compare(status, traj, ref)
+    assert status[0] == 0 and traj["n_pieces"][0] >= 2
+    # resident re-run of the same cycle gives the same answer
+    eng.replan_cycle_resident(10.0, 10.02)
+    st2, tr2 = eng.cycle_results()
+    assert np.array_equal(st2, status) and np.array_equal(tr2["cpts"], traj["cpts"])
+
+
+def test_swarm_two_cycles_with_peers(oracle):
+    n = 12
+    cfg = cases.cfg_small_c2(p.POP_CELL_U8, n_local=n, n_total=n, nx=160, ny=160, nz=30, nt=20)
+    cloud, cyl = cases.world_moving(21, (16.0, 16.0, 3.0), 6, 12)
+    start, goal = p.worldgen.circle_agents(n, 5.0)
+    poses = start[:, :3].astype(np.float32)
+    body = p.worldgen.body_table(n, [0.4, 0.4, 0.45])
+    eng = p.PopEngine(cfg)
+    eng.set_world_cloud(cloud)
+    eng.set_cylinders(cyl)
+    eng.set_body_particles(*body)
+    eng.set_trajectories(np.zeros(n, p.TRAJ_DTYPE))   # nobody has published yet
+    # cycle 1: no peers known
+    st1, tr1 = eng.replan_cycle(start, goal, poses, 20.0, 20.02)
+    swarm0 = (body[0], body[1], np.zeros(n, p.TRAJ_DTYPE))
+    ref1 = _oracle_cycle(oracle, cfg, cloud, cyl, poses, swarm0, start, goal, 20.0, 20.02)
+    assert not _compare(st1, tr1, ref1)
+    assert (st1 == 0).sum() >= n // 2
+    # exchange (single rank: local publish), then cycle 2 sees every peer's cycle-1 trajectory
+    eng.traj_publish_local()
+    recs = np.zeros(n, p.TRAJ_DTYPE)
+    for a in range(n):
+        if st1[a] == 0:
+            recs[a] = tr1[a]
+    start2 = start.copy()
+    for a in range(n):   # advance along the planned trajectory by 0.1 s (state handed to the next replan)
+        if st1[a] == 0:
+            M = int(tr1["n_pieces"][a])
+            dur = tr1["duration"][a][:M].astype(np.float64)
+            for d in range(3):
+                start2[a, 3 * d:3 * d + 3] = oracle.bezier_eval(dur, tr1["cpts"][a][:5 * M], [0.1], d)[0]
+    poses2 = start2[:, :3].astype(np.float32)
+    st2, tr2 = eng.replan_cycle(start2, goal, poses2, 20.1, 20.12)
+    ref2 = _oracle_cycle(oracle, cfg, cloud, cyl, poses2, (body[0], body[1], recs), start2, goal, 20.1, 20.12)
+    assert not _compare(st2, tr2, ref2)
+    assert (st2 == 0).sum() >= n // 3
+
+
+def test_separation_check(oracle):
+    n = 6
+    cfg = cases.cfg_c1(p.POP_CELL_U8, n_local=n, n_total=n)
+    eng = p.PopEngine(cfg)
+    body = p.worldgen.body_table(n, [0.4, 0.4, 0.45])
+    # peers fly straight lines; ego trajectories either cross them or stay clear
+    sp = np.array([[0, 0, 1.0], [0, 0.5, 1.0], [3, 3, 1.0], [-3, 0, 1.0], [0, -3, 1.2], [2, -2, 0.8]])
+    gp = np.array([[2, 0, 1.0], [2, 0.5, 1.0], [3, 0, 1.0], [3, 0, 1.0], [0, 3, 1.2], [-2, 2, 0.8]])
+    recs = p.worldgen.straight_trajs(sp, gp, 4.9, 1.0, 6, 0.3)
+    recs["n_pieces"][5] = 0
+    eng.set_body_particles(*body)
+    eng.set_trajectories(recs)
+    ego = p.worldgen.straight_trajs(sp[::-1].copy(), gp[::-1].copy(), 5.0, 1.0, 4, 0.3)
+    cpts = np.zeros((n, p.POP_MAX_PIECES * 5, 3))
+    cpts[:, :20] = ego["cpts"][:, :20]
+    npieces = np.full(n, 4, np.int32)
+    safe = eng.separation_check_batch(npieces, cpts, 5.0)
+    want = [oracle_cycle.safe_after_opt(cfg, (body[0], body[1], recs), a, cpts[a, :20], 4, 5.0) for a in range(n)]
+    assert safe.astype(bool).tolist() == want
+    assert any(want) and not all(want)

@@ -49,6 +49,8 @@ struct QpDev {
   int* csc_idx = nullptr;     // [agent][kMaxRows*6]  → row*6+slot
   double* Pblk = nullptr;     // [agent][POP_MAX_PIECES][225]
   double* E = nullptr;        // [agent][kMaxRows]
+  double* lo = nullptr;       // [agent][kMaxRows] scaled lower bounds
+  double* up = nullptr;       // [agent][kMaxRows] scaled upper bounds
   double* dy = nullptr;       // [agent][kMaxRows]
   double* Kb = nullptr;       // [agent][kMaxN][kBand] banded lower factor
   double* QM = nullptr;       // [225] jerk cost block
@@ -87,11 +89,20 @@ __device__ double block_sum(double v, double* red) {
   return r;
 }
 
+// Shared-memory row capacity: rows beyond it make the solve report status -20 (the host turns
+// that into POP_E_CAPACITY). 1536 rows = 233 corridor faces over 12 pieces.
+constexpr int kRowCap = 1536;
+// Packed lower-triangular inverse Cholesky factor; row i starts at a bank offset of i mod 16
+// doubles so that both traversals (row-per-thread forward, column-per-thread backward) are
+// bank-conflict free.
+constexpr int kLinvCap = kMaxN * (kMaxN + 1) / 2 + 16 * kMaxN;
+
 struct Smem {
   double x[kMaxN], xp[kMaxN], xt[kMaxN], rhs[kMaxN], tn[kMaxN], D[kMaxN];
-  double Linv[POP_MAX_PIECES][225], G[POP_MAX_PIECES][225], H[POP_MAX_PIECES][225];
-  double z[kMaxRows], y[kMaxRows], l[kMaxRows], u[kMaxRows];
-  signed char type[kMaxRows];
+  double Linv[kLinvCap];
+  int row_off[kMaxN];
+  double z[kRowCap], y[kRowCap], w[kRowCap];   // w = rho z - y
+  signed char type[kRowCap];
   double red[kT / 32];
   int face_off[POP_MAX_PIECES + 1];
   double t[POP_MAX_PIECES];
@@ -230,87 +241,49 @@ __device__ void factorize(Smem& S, const int* ell_col, const double* ell_val, co
     }
     __syncthreads();
   }
-  // Linv_i = inverse of the diagonal block L_ii (lower triangular 15x15); thread per (block, column)
-  for (int e = tid; e < M * 15; e += kT) {
-    const int b = e / 15, c = e % 15;
-    double colv[15];
-    for (int r = 0; r < 15; r++) {
+  // Linv = L^-1 (dense lower triangular, packed rows): thread per column, forward substitution on
+  // the banded factor; previously computed entries of the same column are read back from smem
+  for (int c = tid; c < n; c += kT) {
+    for (int r = c; r < n; r++) {
       double s = r == c ? 1.0 : 0.0;
-      for (int k = c; k < r; k++) s -= Kb[(15 * b + k) * kBand + (r - k)] * colv[k];
-      colv[r] = r < c ? 0.0 : s / Kb[(15 * b + r) * kBand];
+      const int k0 = max(c, r - 15);
+      for (int k = k0; k < r; k++) s -= Kb[k * kBand + (r - k)] * S.Linv[S.row_off[k] + c];
+      S.Linv[S.row_off[r] + c] = s / Kb[r * kBand];
     }
-    for (int r = 0; r < 15; r++) S.Linv[b][r * 15 + c] = colv[r];
-  }
-  __syncthreads();
-  // G_i = Linv_i * Lo_i (Lo_i = L block (i, i-1)),  H_i = Linv_i' * Lo_{i+1}'
-  for (int e = tid; e < M * 225; e += kT) {
-    const int b = e / 225, r = (e % 225) / 15, c = e % 15;
-    double g = 0.0, hh = 0.0;
-    if (b >= 1) {
-      for (int k = 0; k < 15; k++) {
-        const int gr = 15 * b + k, gc = 15 * (b - 1) + c, dd = gr - gc;
-        const double lo = dd <= 15 ? Kb[gc * kBand + dd] : 0.0;
-        g += S.Linv[b][r * 15 + k] * lo;
-      }
-    }
-    if (b + 1 < M) {
-      for (int k = 0; k < 15; k++) {
-        // (Linv_b')[r][k] = Linv_b[k][r];  (Lo_{b+1}')[k][c] = L[15(b+1)+c][15b+k]
-        const int gr = 15 * (b + 1) + c, gc = 15 * b + k, dd = gr - gc;
-        const double lo = dd <= 15 ? Kb[gc * kBand + dd] : 0.0;
-        hh += S.Linv[b][k * 15 + r] * lo;
-      }
-    }
-    S.G[b][r * 15 + c] = g;
-    S.H[b][r * 15 + c] = hh;
   }
   __syncthreads();
 }
 
-// solve K xt = rhs with the block recurrences; result in S.xt (uses S.tn as scratch)
+// solve K xt = rhs:  y = L^-1 rhs,  xt = L^-T y  (two triangular mat-vecs from shared memory)
 __device__ void kkt_solve(Smem& S) {
-  const int n = S.n, M = S.M, tid = threadIdx.x;
-  // u_i = Linv_i b_i
+  const int n = S.n, tid = threadIdx.x;
   if (tid < n) {
-    const int b = tid / 15, r = tid % 15;
-    double s = 0;
-    for (int k = 0; k <= r; k++) s += S.Linv[b][r * 15 + k] * S.rhs[15 * b + k];
-    S.tn[tid] = s;
+    const double* row = S.Linv + S.row_off[tid];
+    double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+    int j = 0;
+    for (; j + 3 <= tid; j += 4) {
+      a0 += row[j] * S.rhs[j];
+      a1 += row[j + 1] * S.rhs[j + 1];
+      a2 += row[j + 2] * S.rhs[j + 2];
+      a3 += row[j + 3] * S.rhs[j + 3];
+    }
+    for (; j <= tid; j++) a0 += row[j] * S.rhs[j];
+    S.tn[tid] = (a0 + a1) + (a2 + a3);
   }
   __syncthreads();
-  // y_i = u_i - G_i y_{i-1}
-  const int row = tid >> 4, cc = tid & 15;
-  for (int b = 1; b < M; b++) {
-    double pr = 0.0;
-    if (row < 15 && cc < 15) pr = S.G[b][row * 15 + cc] * S.tn[15 * (b - 1) + cc];
-    pr += __shfl_xor_sync(0xffffffffu, pr, 8);
-    pr += __shfl_xor_sync(0xffffffffu, pr, 4);
-    pr += __shfl_xor_sync(0xffffffffu, pr, 2);
-    pr += __shfl_xor_sync(0xffffffffu, pr, 1);
-    __syncthreads();
-    if (row < 15 && cc == 0) S.tn[15 * b + row] -= pr;
-    __syncthreads();
-  }
-  // w_i = Linv_i' y_i
   if (tid < n) {
-    const int b = tid / 15, r = tid % 15;
-    double s = 0;
-    for (int k = r; k < 15; k++) s += S.Linv[b][k * 15 + r] * S.tn[15 * b + k];
-    S.xt[tid] = s;
+    double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+    int i = tid;
+    for (; i + 3 < n; i += 4) {
+      a0 += S.Linv[S.row_off[i] + tid] * S.tn[i];
+      a1 += S.Linv[S.row_off[i + 1] + tid] * S.tn[i + 1];
+      a2 += S.Linv[S.row_off[i + 2] + tid] * S.tn[i + 2];
+      a3 += S.Linv[S.row_off[i + 3] + tid] * S.tn[i + 3];
+    }
+    for (; i < n; i++) a0 += S.Linv[S.row_off[i] + tid] * S.tn[i];
+    S.xt[tid] = (a0 + a1) + (a2 + a3);
   }
   __syncthreads();
-  // x_i = w_i - H_i x_{i+1}
-  for (int b = M - 2; b >= 0; b--) {
-    double pr = 0.0;
-    if (row < 15 && cc < 15) pr = S.H[b][row * 15 + cc] * S.xt[15 * (b + 1) + cc];
-    pr += __shfl_xor_sync(0xffffffffu, pr, 8);
-    pr += __shfl_xor_sync(0xffffffffu, pr, 4);
-    pr += __shfl_xor_sync(0xffffffffu, pr, 2);
-    pr += __shfl_xor_sync(0xffffffffu, pr, 1);
-    __syncthreads();
-    if (row < 15 && cc == 0) S.xt[15 * b + row] -= pr;
-    __syncthreads();
-  }
 }
 
 __global__ void __launch_bounds__(kT, 1) k_qp_admm(QpDev Dv, QpParams P, const double* __restrict__ hpoly_all,
@@ -335,9 +308,17 @@ __global__ void __launch_bounds__(kT, 1) k_qp_admm(QpDev Dv, QpParams P, const d
   double* E = Dv.E + static_cast<size_t>(a) * kMaxRows;
   double* dyv = Dv.dy + static_cast<size_t>(a) * kMaxRows;
   double* Kb = Dv.Kb + static_cast<size_t>(a) * kMaxN * kBand;
+  double* lov = Dv.lo + static_cast<size_t>(a) * kMaxRows;
+  double* upv = Dv.up + static_cast<size_t>(a) * kMaxRows;
 
   if (tid == 0) {
     S.M = M; S.n = 15 * M;
+    int off = 0;
+    for (int i = 0; i < 15 * M; i++) {
+      while ((off & 15) != (i & 15)) off++;
+      S.row_off[i] = off;
+      off += i + 1;
+    }
     S.face_off[0] = 0;
     for (int i = 0; i < M; i++) {
       int r = rows[i];
@@ -350,6 +331,10 @@ __global__ void __launch_bounds__(kT, 1) k_qp_admm(QpDev Dv, QpParams P, const d
   }
   __syncthreads();
   const int n = S.n, m = S.m;
+  if (m > kRowCap) {
+    if (tid == 0) { Dv.status[a] = -20; Dv.iters[a] = 0; }
+    return;
+  }
 
   // ---- assembly ----
   for (int r = tid; r < m; r += kT) {
@@ -357,9 +342,9 @@ __global__ void __launch_bounds__(kT, 1) k_qp_admm(QpDev Dv, QpParams P, const d
     double val[kEll], lo, up;
     build_row(S, r, init, goal, hpoly, rows, P, col, val, &lo, &up);
     for (int k = 0; k < kEll; k++) { ell_col[r * kEll + k] = col[k]; ell_val[r * kEll + k] = val[k]; }
-    S.l[r] = fmax(lo, -OSQP_INFTY);
-    S.u[r] = fmin(up, OSQP_INFTY);
-    S.z[r] = 0.0; S.y[r] = 0.0;
+    lov[r] = fmax(lo, -OSQP_INFTY);
+    upv[r] = fmin(up, OSQP_INFTY);
+    S.z[r] = 0.0; S.y[r] = 0.0; S.w[r] = 0.0;
     E[r] = 1.0;
   }
   for (int e = tid; e < M * 225; e += kT) Pblk[e] = Dv.QM[e % 225];
@@ -435,11 +420,11 @@ __global__ void __launch_bounds__(kT, 1) k_qp_admm(QpDev Dv, QpParams P, const d
   }
   // scaled bounds and constraint types (set_rho_vec)
   for (int r = tid; r < m; r += kT) {
-    S.l[r] *= E[r];
-    S.u[r] *= E[r];
+    lov[r] *= E[r];
+    upv[r] *= E[r];
     signed char ty;
-    if (S.l[r] < -OSQP_INFTY * MIN_SCALING && S.u[r] > OSQP_INFTY * MIN_SCALING) ty = -1;
-    else if (S.u[r] - S.l[r] < RHO_TOL) ty = 1;
+    if (lov[r] < -OSQP_INFTY * MIN_SCALING && upv[r] > OSQP_INFTY * MIN_SCALING) ty = -1;
+    else if (upv[r] - lov[r] < RHO_TOL) ty = 1;
     else ty = 0;
     S.type[r] = ty;
   }
@@ -504,15 +489,15 @@ __global__ void __launch_bounds__(kT, 1) k_qp_admm(QpDev Dv, QpParams P, const d
     double v_nd = 0, v_lhs = 0;
     for (int r = tid; r < m; r += kT) {
       double d = dyv[r];
-      if (S.u[r] > OSQP_INFTY * MIN_SCALING) {
-        if (S.l[r] < -OSQP_INFTY * MIN_SCALING) d = 0.0;
+      if (upv[r] > OSQP_INFTY * MIN_SCALING) {
+        if (lov[r] < -OSQP_INFTY * MIN_SCALING) d = 0.0;
         else d = fmin(d, 0.0);
-      } else if (S.l[r] < -OSQP_INFTY * MIN_SCALING) {
+      } else if (lov[r] < -OSQP_INFTY * MIN_SCALING) {
         d = fmax(d, 0.0);
       }
       dyv[r] = d;
       v_nd = fmax(v_nd, fabs(E[r] * d));
-      v_lhs += S.u[r] * fmax(d, 0.0) + S.l[r] * fmin(d, 0.0);
+      v_lhs += upv[r] * fmax(d, 0.0) + lov[r] * fmin(d, 0.0);
     }
     const double nd = block_max(v_nd, S.red);
     const double lhs = block_sum(v_lhs, S.red);
@@ -544,15 +529,30 @@ __global__ void __launch_bounds__(kT, 1) k_qp_admm(QpDev Dv, QpParams P, const d
   };
 
   for (iter = 1; iter <= P.max_iter; iter++) {
-    // x_prev <- x ; rhs = sigma x_prev - q + A'(rho z - y)
-    if (tid < n) {
-      S.xp[tid] = S.x[tid];
-      double s = 0;
-      for (int q = csc_ptr[tid]; q < csc_ptr[tid + 1]; q++) {
-        const int idx = csc_idx[q], r = idx / kEll;
-        s += ell_val[idx] * (rho_of(r) * S.z[r] - S.y[r]);
+    // x_prev <- x ; rhs = sigma x_prev - q + A' w with w = rho z - y.  Half-warp per column, lanes
+    // stride its entries, fixed shuffle tree (deterministic order).
+    {
+      const int grp = tid >> 4, ln = tid & 15;
+      for (int j0 = 0; j0 < n; j0 += kT / 16) {
+        const int j = j0 + grp;
+        double s = 0.0;
+        if (j < n) {
+          const int q1 = csc_ptr[j + 1];
+          for (int q = csc_ptr[j] + ln; q < q1; q += 16) {
+            const int idx = csc_idx[q];
+            s += ell_val[idx] * S.w[idx / kEll];
+          }
+        }
+        s += __shfl_xor_sync(0xffffffffu, s, 8);
+        s += __shfl_xor_sync(0xffffffffu, s, 4);
+        s += __shfl_xor_sync(0xffffffffu, s, 2);
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        if (j < n && ln == 0) {
+          const double xv = S.x[j];
+          S.xp[j] = xv;
+          S.rhs[j] = (SIGMA * xv - 0.0) + s;
+        }
       }
-      S.rhs[tid] = (SIGMA * S.x[tid] - 0.0) + s;
     }
     __syncthreads();
     kkt_solve(S);
@@ -563,10 +563,11 @@ __global__ void __launch_bounds__(kT, 1) k_qp_admm(QpDev Dv, QpParams P, const d
       const double rho = rho_of(r), zp = S.z[r], yv = S.y[r];
       const double mix = ALPHA * zt + (1.0 - ALPHA) * zp;
       const double v = mix + (1. / rho) * yv;
-      const double zn = fmin(fmax(v, S.l[r]), S.u[r]);
+      const double zn = fmin(fmax(v, lov[r]), upv[r]);
       const double d = rho * (mix - zn);
       S.z[r] = zn;
       S.y[r] = yv + d;
+      S.w[r] = rho * zn - (yv + d);
       if (store_dy) dyv[r] = d;
     }
     if (tid < n) S.x[tid] = ALPHA * S.xt[tid] + (1.0 - ALPHA) * S.xp[tid];
@@ -588,6 +589,7 @@ __global__ void __launch_bounds__(kT, 1) k_qp_admm(QpDev Dv, QpParams P, const d
         __syncthreads();
         if (tid == 0) S.rho = rho_new;
         __syncthreads();
+        for (int r = tid; r < m; r += kT) S.w[r] = rho_of(r) * S.z[r] - S.y[r];
         factorize(S, ell_col, ell_val, csc_ptr, csc_idx, Pblk, Kb);
       }
     }
@@ -641,6 +643,8 @@ int popk_qp_alloc(pop_handle* h, int n_agents) {
   ok &= cudaMalloc(&d->Pblk, na * POP_MAX_PIECES * 225 * sizeof(double)) == cudaSuccess;
   ok &= cudaMalloc(&d->E, na * kMaxRows * sizeof(double)) == cudaSuccess;
   ok &= cudaMalloc(&d->dy, na * kMaxRows * sizeof(double)) == cudaSuccess;
+  ok &= cudaMalloc(&d->lo, na * kMaxRows * sizeof(double)) == cudaSuccess;
+  ok &= cudaMalloc(&d->up, na * kMaxRows * sizeof(double)) == cudaSuccess;
   ok &= cudaMalloc(&d->Kb, na * kMaxN * kBand * sizeof(double)) == cudaSuccess;
   ok &= cudaMalloc(&d->QM, 225 * sizeof(double)) == cudaSuccess;
   ok &= cudaMalloc(&d->cpts, na * POP_MAX_PIECES * 15 * sizeof(double)) == cudaSuccess;
@@ -660,7 +664,7 @@ void popk_qp_free(pop_handle* h) {
   QpDev* d = h->qp;
   if (!d) return;
   void* ptrs[] = {d->n_pieces, d->init, d->goal, d->dur, d->ell_col, d->ell_val, d->csc_ptr, d->csc_idx, d->Pblk,
-                  d->E, d->dy, d->Kb, d->QM, d->cpts, d->status, d->iters};
+                  d->E, d->dy, d->lo, d->up, d->Kb, d->QM, d->cpts, d->status, d->iters};
   for (void* p : ptrs) if (p) cudaFree(p);
   delete d;
   h->qp = nullptr;
@@ -722,5 +726,8 @@ extern "C" int pop_qp_solve_batch(pop_handle* h, int n, const int32_t* n_pieces,
   POP_CUDA(h, cudaMemcpyAsync(out_status, d->status, sizeof(int) * n, cudaMemcpyDeviceToHost, h->stream));
   if (out_iters) POP_CUDA(h, cudaMemcpyAsync(out_iters, d->iters, sizeof(int) * n, cudaMemcpyDeviceToHost, h->stream));
   POP_CUDA(h, cudaStreamSynchronize(h->stream));
+  for (int i = 0; i < n; i++)
+    if (out_status[i] == -20)
+      return pop_fail(h, POP_E_CAPACITY, "problem %d has more than %d constraint rows (shared-memory capacity)", i, kRowCap);
   return POP_OK;
 }

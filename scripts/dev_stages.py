@@ -1,0 +1,29 @@
+"""Dev helper: run the c2 batch stage by stage through the C ABI and print per-stage statistics."""
+import os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import pred_occ_planner_b200 as p
+import bench
+
+n = int(os.environ.get("N_AGENTS", "64"))
+cfg, cloud, cyl, start, goal, body = bench.workload(n, n, 0)
+eng = p.PopEngine(cfg)
+eng.set_world_cloud(cloud); eng.set_cylinders(cyl); eng.set_body_particles(*body)
+eng.set_trajectories(np.zeros(n, p.TRAJ_DTYPE))
+poses = start[:, :3].astype(np.float32)
+st, tr = eng.replan_cycle(start, goal, poses, 100.0, 100.02)
+eng.traj_publish_local()
+eng.set_poses(poses)
+eng.map_update_gt(100.1)
+ret, path, ln, stats = eng.astar_search_batch(start, goal, np.full(n, 0.02))
+print("astar ret", np.bincount(ret, minlength=6), "iters", stats[:, 0].min(), np.median(stats[:, 0]), stats[:, 0].max(),
+      "nodes max", stats[:, 1].max(), "len", np.bincount(ln.clip(0)))
+hp, rows, npoly, lgoal = eng.corridor_batch(path, ln, start, np.full(n, 100.12))
+print("npoly", np.bincount(npoly), "rows mean", rows[rows > 0].mean(), "max", rows.max())
+fin = np.zeros((n, 9)); fin[:, :6] = lgoal
+dur = np.zeros((n, p.POP_MAX_PIECES))
+for a in range(n): dur[a, :npoly[a]] = cfg.corridor_tau
+eng.profile_enable(True)
+cpts, status, iters = eng.qp_solve_batch(npoly, start, fin, dur, hp, rows, cfg.opt_max_vel, cfg.opt_max_acc)
+ms, _ = eng.profile_read(True)
+print("qp status", {int(s): int((status == s).sum()) for s in np.unique(status)}, "iters", np.sort(iters), "ms", ms["qp"])

@@ -19,7 +19,7 @@
 
 namespace {
 
-constexpr int kT = 256;                       // threads per CTA
+constexpr int kT = 512;                       // threads per CTA
 constexpr int kMaxN = 15 * POP_MAX_PIECES;    // 180 variables
 constexpr int kMaxRows = 9 * (POP_MAX_PIECES + 1) + 21 * POP_MAX_PIECES + 5 * POP_MAX_PIECES * POP_MAX_FACES;
 constexpr int kEll = 6;
@@ -51,7 +51,6 @@ struct QpDev {
   double* E = nullptr;        // [agent][kMaxRows]
   double* lo = nullptr;       // [agent][kMaxRows] scaled lower bounds
   double* up = nullptr;       // [agent][kMaxRows] scaled upper bounds
-  double* dy = nullptr;       // [agent][kMaxRows]
   double* Kb = nullptr;       // [agent][kMaxN][kBand] banded lower factor
   double* QM = nullptr;       // [225] jerk cost block
   // outputs
@@ -68,15 +67,57 @@ __device__ __forceinline__ double limit_scaling(double v) {
   return v;
 }
 
-// block-wide max of a per-thread value (all threads receive the result)
+// Row capacity: every thread owns up to kSlots rows (row = slot*kT + tid) whose coefficients,
+// bounds, z and y live in REGISTERS for the whole solve; more rows (or a problem that does not fit
+// the shared-memory plan below) make the solve report status -20 (host: POP_E_CAPACITY).
+constexpr int kSlots = 3;
+constexpr int kRowCap = kT * kSlots;
+constexpr int kMaxStruct = 9 * (POP_MAX_PIECES + 1) + 21 * POP_MAX_PIECES;  // 369 structured rows < kT
+constexpr int kSmemBytes = 232448;   // 227 KB opt-in maximum per CTA on sm_100a
+constexpr int kRedN = 12;
+
+// Shared-memory plan.  Fixed header, then per problem (n variables, ms structured rows, m rows):
+//   Linv  n(n+1)/2 doubles  packed lower-triangular inverse Cholesky factor (row i at i(i+1)/2)
+//   pst   6*ms doubles      products val*w of the structured rows, [row][slot]
+//   psf   3*(m-ms) doubles  products val*w of the safety rows, [row][xyz]; within a piece the 15
+//                           columns of face j are the 15 consecutive doubles at 15*j
+//   cidx  6*ms u16          column lists of the structured rows (indices into pst)
+//   type  m s8              constraint type per row (-1 loose, 0 inequality, 1 equality)
+struct Smem {
+  double x[kMaxN], xp[kMaxN], xt[kMaxN], rhs[kMaxN], tn[kMaxN], D[kMaxN];
+  double red[(kT / 32) * kRedN];
+  double t[POP_MAX_PIECES];
+  double rho, c_scale;
+  double rho_v[3], rinv_v[3];   // indexed by type+1: loose, inequality, equality
+  int face_off[POP_MAX_PIECES + 1];
+  int M, n, m, ms, status, fail;
+  unsigned short cptr[kMaxN + 2];
+};
+constexpr int kHdrBytes = (sizeof(Smem) + 15) / 16 * 16;
+
+// block-wide max of N per-thread values at once (all threads receive the results)
+template <int N>
+__device__ void block_max_n(double (&v)[N], double* red) {
+#pragma unroll
+  for (int k = 0; k < N; k++)
+    for (int o = 16; o > 0; o >>= 1) v[k] = fmax(v[k], __shfl_xor_sync(0xffffffffu, v[k], o));
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+    for (int k = 0; k < N; k++) red[(threadIdx.x >> 5) * N + k] = v[k];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < N; k++) {
+    double r = red[k];
+    for (int w = 1; w < kT / 32; w++) r = fmax(r, red[w * N + k]);
+    v[k] = r;
+  }
+}
 __device__ double block_max(double v, double* red) {
-  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
-  __syncthreads();
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
-  __syncthreads();
-  double r = red[0];
-  for (int w = 1; w < kT / 32; w++) r = fmax(r, red[w]);
-  return r;
+  double a[1] = {v};
+  block_max_n<1>(a, red);
+  return a[0];
 }
 // deterministic block-wide sum (fixed tree)
 __device__ double block_sum(double v, double* red) {
@@ -88,27 +129,6 @@ __device__ double block_sum(double v, double* red) {
   for (int w = 0; w < kT / 32; w++) r += red[w];
   return r;
 }
-
-// Shared-memory row capacity: rows beyond it make the solve report status -20 (the host turns
-// that into POP_E_CAPACITY). 1536 rows = 233 corridor faces over 12 pieces.
-constexpr int kRowCap = 1536;
-// Packed lower-triangular inverse Cholesky factor; row i starts at a bank offset of i mod 16
-// doubles so that both traversals (row-per-thread forward, column-per-thread backward) are
-// bank-conflict free.
-constexpr int kLinvCap = kMaxN * (kMaxN + 1) / 2 + 16 * kMaxN;
-
-struct Smem {
-  double x[kMaxN], xp[kMaxN], xt[kMaxN], rhs[kMaxN], tn[kMaxN], D[kMaxN];
-  double Linv[kLinvCap];
-  int row_off[kMaxN];
-  double z[kRowCap], y[kRowCap], w[kRowCap];   // w = rho z - y
-  signed char type[kRowCap];
-  double red[kT / 32];
-  int face_off[POP_MAX_PIECES + 1];
-  double t[POP_MAX_PIECES];
-  int M, n, m, status, fail;
-  double rho, c_scale;
-};
 
 // ---- row construction (bezier_optimizer.cpp:133-260); entries ascending in column -----------------
 __device__ void build_row(const Smem& S, int r, const double* init, const double* goal, const double* hpoly,
@@ -198,11 +218,11 @@ __device__ __forceinline__ double row_dot(const int* col, const double* val, con
   return s;
 }
 
-// K = P + sigma I + A' diag(rho) A in banded-lower storage Kb[c][d] = K[c+d][c], then banded
-// Cholesky in place and the block recurrence matrices Linv/G/H.
-__device__ void factorize(Smem& S, const int* ell_col, const double* ell_val, const int* csc_ptr, const int* csc_idx,
-                          const double* Pblk, double* Kb) {
-  const int n = S.n, M = S.M;
+// K = P + sigma I + A' diag(rho) A in banded-lower storage Kb[c][d] = K[c+d][c], banded Cholesky
+// in place, then Linv = L^-1 (dense lower triangular, packed rows) into shared memory.
+__device__ void factorize(Smem& S, double* Linv, const signed char* type, const int* ell_col, const double* ell_val,
+                          const int* csc_ptr, const int* csc_idx, const double* Pblk, double* Kb) {
+  const int n = S.n;
   const int tid = threadIdx.x;
   for (int e = tid; e < n * kBand; e += kT) {
     const int c = e / kBand, d = e % kBand, r = c + d;
@@ -215,7 +235,7 @@ __device__ void factorize(Smem& S, const int* ell_col, const double* ell_val, co
         const int* rc = ell_col + row * kEll;
         for (int k = 0; k < kEll; k++)
           if (rc[k] == c) {
-            const double rho = S.type[row] == 1 ? RHO_EQ * S.rho : (S.type[row] == 0 ? S.rho : RHO_MIN);
+            const double rho = S.rho_v[type[row] + 1];
             v += (rho * ell_val[idx]) * ell_val[row * kEll + k];
             break;
           }
@@ -241,49 +261,96 @@ __device__ void factorize(Smem& S, const int* ell_col, const double* ell_val, co
     }
     __syncthreads();
   }
-  // Linv = L^-1 (dense lower triangular, packed rows): thread per column, forward substitution on
-  // the banded factor; previously computed entries of the same column are read back from smem
+  // thread per column: forward substitution on the banded factor; previously computed entries of
+  // the same column are read back from shared memory
   for (int c = tid; c < n; c += kT) {
     for (int r = c; r < n; r++) {
       double s = r == c ? 1.0 : 0.0;
       const int k0 = max(c, r - 15);
-      for (int k = k0; k < r; k++) s -= Kb[k * kBand + (r - k)] * S.Linv[S.row_off[k] + c];
-      S.Linv[S.row_off[r] + c] = s / Kb[r * kBand];
+      for (int k = k0; k < r; k++) s -= Kb[k * kBand + (r - k)] * Linv[k * (k + 1) / 2 + c];
+      Linv[r * (r + 1) / 2 + c] = s / Kb[r * kBand];
     }
   }
   __syncthreads();
 }
 
-// solve K xt = rhs:  y = L^-1 rhs,  xt = L^-T y  (two triangular mat-vecs from shared memory)
-__device__ void kkt_solve(Smem& S) {
+// solve K xt = rhs:  tn = L^-1 rhs,  xt = L^-T tn.  Rows (columns) i and n-1-i are paired so every
+// pair has n+1 products; L lanes (4 or 8, consecutive threads of one warp) split a pair and
+// combine with shuffles.  FMA is fine here: the oracle solves the same system by another route.
+__device__ __forceinline__ void kkt_solve(Smem& S, const double* __restrict__ Linv, int L) {
   const int n = S.n, tid = threadIdx.x;
-  if (tid < n) {
-    const double* row = S.Linv + S.row_off[tid];
-    double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
-    int j = 0;
-    for (; j + 3 <= tid; j += 4) {
-      a0 += row[j] * S.rhs[j];
-      a1 += row[j + 1] * S.rhs[j + 1];
-      a2 += row[j + 2] * S.rhs[j + 2];
-      a3 += row[j + 3] * S.rhs[j + 3];
+  const int l = tid & (L - 1), p = L == 8 ? tid >> 3 : tid >> 2;
+  const int P = (n + 1) >> 1;
+  const int i1 = p, i2 = n - 1 - p;
+  const bool act = p < P, two = act && i2 != i1;
+  double a1 = 0, a2 = 0, b1 = 0, b2 = 0;
+  if (act) {
+    const double* r1 = Linv + i1 * (i1 + 1) / 2;
+    int j = l;
+    for (; j + L <= i1; j += 2 * L) { a1 = fma(r1[j], S.rhs[j], a1); b1 = fma(r1[j + L], S.rhs[j + L], b1); }
+    if (j <= i1) a1 = fma(r1[j], S.rhs[j], a1);
+    if (two) {
+      const double* r2 = Linv + i2 * (i2 + 1) / 2;
+      j = l;
+      for (; j + L <= i2; j += 2 * L) { a2 = fma(r2[j], S.rhs[j], a2); b2 = fma(r2[j + L], S.rhs[j + L], b2); }
+      if (j <= i2) a2 = fma(r2[j], S.rhs[j], a2);
     }
-    for (; j <= tid; j++) a0 += row[j] * S.rhs[j];
-    S.tn[tid] = (a0 + a1) + (a2 + a3);
   }
+  a1 += b1; a2 += b2;
+  for (int o = L >> 1; o > 0; o >>= 1) {
+    a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+    a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+  }
+  if (act && l == 0) { S.tn[i1] = a1; if (two) S.tn[i2] = a2; }
   __syncthreads();
-  if (tid < n) {
-    double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
-    int i = tid;
-    for (; i + 3 < n; i += 4) {
-      a0 += S.Linv[S.row_off[i] + tid] * S.tn[i];
-      a1 += S.Linv[S.row_off[i + 1] + tid] * S.tn[i + 1];
-      a2 += S.Linv[S.row_off[i + 2] + tid] * S.tn[i + 2];
-      a3 += S.Linv[S.row_off[i + 3] + tid] * S.tn[i + 3];
+  a1 = a2 = b1 = b2 = 0;
+  if (act) {
+    int i = i1 + l;
+    for (; i + L < n; i += 2 * L) {
+      a1 = fma(Linv[i * (i + 1) / 2 + i1], S.tn[i], a1);
+      b1 = fma(Linv[(i + L) * (i + L + 1) / 2 + i1], S.tn[i + L], b1);
     }
-    for (; i < n; i++) a0 += S.Linv[S.row_off[i] + tid] * S.tn[i];
-    S.xt[tid] = (a0 + a1) + (a2 + a3);
+    if (i < n) a1 = fma(Linv[i * (i + 1) / 2 + i1], S.tn[i], a1);
+    if (two) {
+      i = i2 + l;
+      for (; i + L < n; i += 2 * L) {
+        a2 = fma(Linv[i * (i + 1) / 2 + i2], S.tn[i], a2);
+        b2 = fma(Linv[(i + L) * (i + L + 1) / 2 + i2], S.tn[i + L], b2);
+      }
+      if (i < n) a2 = fma(Linv[i * (i + 1) / 2 + i2], S.tn[i], a2);
+    }
   }
+  a1 += b1; a2 += b2;
+  for (int o = L >> 1; o > 0; o >>= 1) {
+    a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+    a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+  }
+  if (act && l == 0) { S.xt[i1] = a1; if (two) S.xt[i2] = a2; }
   __syncthreads();
+}
+
+// (A' u)_c from the products u-weighted rows left in pst/psf: G lanes (2 or 4) per column, the
+// safety rows of the column's piece strided over the lanes, the structured rows on the last lane;
+// fixed order, shuffle tree.  Every thread of the CTA calls this; lane 0 of column c < n gets the sum.
+__device__ __forceinline__ double gather_col(const Smem& S, const double* __restrict__ pst,
+                                             const double* __restrict__ psf,
+                                             const unsigned short* __restrict__ cidx, int G) {
+  const int tid = threadIdx.x;
+  const int lane = tid & (G - 1), c = G == 4 ? tid >> 2 : tid >> 1;
+  double s0 = 0, s1 = 0;
+  if (c < S.n) {
+    const int i = c / 15, cc = c - 15 * i;
+    const int f0 = S.face_off[i], F = S.face_off[i + 1] - f0;
+    const double* base = psf + 15 * f0 + cc;
+    int j = lane;
+    for (; j + G < F; j += 2 * G) { s0 += base[15 * j]; s1 += base[15 * (j + G)]; }
+    if (j < F) s0 += base[15 * j];
+    if (lane == G - 1)
+      for (int q = S.cptr[c]; q < S.cptr[c + 1]; q++) s1 += pst[cidx[q]];
+  }
+  double s = s0 + s1;
+  for (int o = G >> 1; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  return s;
 }
 
 __global__ void __launch_bounds__(kT, 1) k_qp_admm(QpDev Dv, QpParams P, const double* __restrict__ hpoly_all,
@@ -306,19 +373,12 @@ __global__ void __launch_bounds__(kT, 1) k_qp_admm(QpDev Dv, QpParams P, const d
   int* csc_idx = Dv.csc_idx + static_cast<size_t>(a) * kMaxRows * kEll;
   double* Pblk = Dv.Pblk + static_cast<size_t>(a) * POP_MAX_PIECES * 225;
   double* E = Dv.E + static_cast<size_t>(a) * kMaxRows;
-  double* dyv = Dv.dy + static_cast<size_t>(a) * kMaxRows;
   double* Kb = Dv.Kb + static_cast<size_t>(a) * kMaxN * kBand;
   double* lov = Dv.lo + static_cast<size_t>(a) * kMaxRows;
   double* upv = Dv.up + static_cast<size_t>(a) * kMaxRows;
 
   if (tid == 0) {
     S.M = M; S.n = 15 * M;
-    int off = 0;
-    for (int i = 0; i < 15 * M; i++) {
-      while ((off & 15) != (i & 15)) off++;
-      S.row_off[i] = off;
-      off += i + 1;
-    }
     S.face_off[0] = 0;
     for (int i = 0; i < M; i++) {
       int r = rows[i];
@@ -326,15 +386,25 @@ __global__ void __launch_bounds__(kT, 1) k_qp_admm(QpDev Dv, QpParams P, const d
       S.face_off[i + 1] = S.face_off[i] + r;
       S.t[i] = Dv.dur[a * POP_MAX_PIECES + i];
     }
-    S.m = 9 * (M + 1) + 21 * M + 5 * S.face_off[M];
+    S.ms = 9 * (M + 1) + 21 * M;
+    S.m = S.ms + 5 * S.face_off[M];
     S.status = 0; S.fail = 0; S.rho = RHO0; S.c_scale = 1.0;
+    S.rho_v[0] = RHO_MIN; S.rho_v[1] = RHO0; S.rho_v[2] = RHO_EQ * RHO0;
+    for (int k = 0; k < 3; k++) S.rinv_v[k] = 1. / S.rho_v[k];
   }
   __syncthreads();
-  const int n = S.n, m = S.m;
-  if (m > kRowCap) {
+  const int n = S.n, m = S.m, ms = S.ms;
+  const size_t dyn_bytes = sizeof(double) * (static_cast<size_t>(n) * (n + 1) / 2 + 6 * ms + 3 * (m - ms)) +
+                           sizeof(unsigned short) * 6 * ms + m;
+  if (m > kRowCap || kHdrBytes + dyn_bytes > kSmemBytes) {
     if (tid == 0) { Dv.status[a] = -20; Dv.iters[a] = 0; }
     return;
   }
+  double* Linv = reinterpret_cast<double*>(smem_raw + kHdrBytes);
+  double* pst = Linv + n * (n + 1) / 2;
+  double* psf = pst + 6 * ms;
+  unsigned short* cidx = reinterpret_cast<unsigned short*>(psf + 3 * (m - ms));
+  signed char* type = reinterpret_cast<signed char*>(cidx + 6 * ms);
 
   // ---- assembly ----
   for (int r = tid; r < m; r += kT) {
@@ -344,7 +414,6 @@ __global__ void __launch_bounds__(kT, 1) k_qp_admm(QpDev Dv, QpParams P, const d
     for (int k = 0; k < kEll; k++) { ell_col[r * kEll + k] = col[k]; ell_val[r * kEll + k] = val[k]; }
     lov[r] = fmax(lo, -OSQP_INFTY);
     upv[r] = fmin(up, OSQP_INFTY);
-    S.z[r] = 0.0; S.y[r] = 0.0; S.w[r] = 0.0;
     E[r] = 1.0;
   }
   for (int e = tid; e < M * 225; e += kT) Pblk[e] = Dv.QM[e % 225];
@@ -426,101 +495,188 @@ __global__ void __launch_bounds__(kT, 1) k_qp_admm(QpDev Dv, QpParams P, const d
     if (lov[r] < -OSQP_INFTY * MIN_SCALING && upv[r] > OSQP_INFTY * MIN_SCALING) ty = -1;
     else if (upv[r] - lov[r] < RHO_TOL) ty = 1;
     else ty = 0;
-    S.type[r] = ty;
+    type[r] = ty;
+  }
+  // column lists of the structured rows (they lead every column's ascending-row list)
+  if (tid < n) {
+    int cnt = 0;
+    for (int q = csc_ptr[tid]; q < csc_ptr[tid + 1] && csc_idx[q] < ms * kEll; q++) cnt++;
+    S.tn[tid] = cnt;
   }
   __syncthreads();
-  factorize(S, ell_col, ell_val, csc_ptr, csc_idx, Pblk, Kb);
+  if (tid == 0) { int run = 0; S.cptr[0] = 0; for (int j = 0; j < n; j++) { run += static_cast<int>(S.tn[j]); S.cptr[j + 1] = static_cast<unsigned short>(run); } }
+  __syncthreads();
+  if (tid < n) {
+    int w = S.cptr[tid];
+    for (int q = csc_ptr[tid]; q < csc_ptr[tid + 1] && csc_idx[q] < ms * kEll; q++) cidx[w++] = static_cast<unsigned short>(csc_idx[q]);
+  }
+  __syncthreads();
+  factorize(S, Linv, type, ell_col, ell_val, csc_ptr, csc_idx, Pblk, Kb);
   if (S.fail) {
     if (tid == 0) { Dv.status[a] = -7; Dv.iters[a] = 0; }
     return;
   }
   const double cinv = 1.0 / S.c_scale;
 
+  // ---- per-thread row state in registers ----
+  // slot 0 (row tid): structured or safety, 6 coefficients with packed 8-bit columns
+  double v0[kEll], z0 = 0, y0 = 0, lo0 = 0, up0 = 0;
+  unsigned long long c0 = 0;
+  int ty0 = 0;
+  const bool has0 = tid < m, struct0 = tid < ms;
+#pragma unroll
+  for (int k = 0; k < kEll; k++) v0[k] = 0.0;
+  if (has0) {
+#pragma unroll
+    for (int k = 0; k < kEll; k++) {
+      const int c = ell_col[tid * kEll + k];
+      if (c >= 0) { v0[k] = ell_val[tid * kEll + k]; c0 |= static_cast<unsigned long long>(c) << (8 * k); }
+    }
+    lo0 = lov[tid]; up0 = upv[tid]; ty0 = type[tid];
+  }
+  // slots 1.. (rows s*kT + tid): safety rows only — 3 coefficients on consecutive columns, lower
+  // bound -OSQP_INFTY*E (never active), type 0
+  double vs[kSlots - 1][3], zs[kSlots - 1], ys[kSlots - 1], ups[kSlots - 1];
+  int bs[kSlots - 1];
+#pragma unroll
+  for (int s = 0; s < kSlots - 1; s++) {
+    const int r = (s + 1) * kT + tid;
+    zs[s] = ys[s] = 0.0; ups[s] = 0.0; bs[s] = 0;
+    vs[s][0] = vs[s][1] = vs[s][2] = 0.0;
+    if (r < m) {
+      bs[s] = ell_col[r * kEll];
+      vs[s][0] = ell_val[r * kEll]; vs[s][1] = ell_val[r * kEll + 1]; vs[s][2] = ell_val[r * kEll + 2];
+      ups[s] = upv[r];
+    }
+  }
+#define COL0(k) static_cast<int>((c0 >> (8 * (k))) & 0xffull)
+  auto dot0 = [&](const double* x) {
+    double s = 0;
+#pragma unroll
+    for (int k = 0; k < kEll; k++) s += v0[k] * x[COL0(k)];
+    return s;
+  };
+  auto dots = [&](int s, const double* x) {
+    return (vs[s][0] * x[bs[s]] + vs[s][1] * x[bs[s] + 1]) + vs[s][2] * x[bs[s] + 2];
+  };
+  // leave u-weighted coefficients in pst/psf for gather_col; sel: 0 → w = rho z - y, 1 → y, 2 → dy
+  auto write_p = [&](int sel, const double (&dy)[kSlots]) {
+    if (has0) {
+      const double u = sel == 0 ? S.rho_v[ty0 + 1] * z0 - y0 : (sel == 1 ? y0 : dy[0]);
+      if (struct0) {
+#pragma unroll
+        for (int k = 0; k < kEll; k++) pst[tid * kEll + k] = v0[k] * u;
+      } else {
+#pragma unroll
+        for (int k = 0; k < 3; k++) psf[(tid - ms) * 3 + k] = v0[k] * u;
+      }
+    }
+#pragma unroll
+    for (int s = 0; s < kSlots - 1; s++) {
+      const int r = (s + 1) * kT + tid;
+      if (r < m) {
+        const double u = sel == 0 ? S.rho_v[1] * zs[s] - ys[s] : (sel == 1 ? ys[s] : dy[s + 1]);
+#pragma unroll
+        for (int k = 0; k < 3; k++) psf[(r - ms) * 3 + k] = vs[s][k] * u;
+      }
+    }
+  };
+
+  const int G = 4 * n <= kT ? 4 : 2;          // lanes per column in gather_col
+  const int L = 4 * (n + 1) <= kT ? 8 : 4;    // lanes per row pair in kkt_solve
+  const int gc = G == 4 ? tid >> 2 : tid >> 1;  // this thread's gather column
+  const bool gl0 = (tid & (G - 1)) == 0 && gc < n;
+
   // ---- ADMM ----
   int iter, status = 0;
   bool can_check = false;
   double pri_res = 0, dua_res = 0;
-  auto rho_of = [&](int r) { return S.type[r] == 1 ? RHO_EQ * S.rho : (S.type[r] == 0 ? S.rho : RHO_MIN); };
-
-  // residuals + norms needed by check_termination / compute_rho_estimate.  Outputs (all threads):
   double nz = 0, nAx = 0, nAty = 0, nPx = 0, rp_scaled = 0, rd_scaled = 0, nz_un = 0, nd_un = 0;
-  auto update_info = [&]() {
-    double v_pri = 0, v_rp = 0, v_z = 0, v_ax = 0, v_ez = 0, v_eax = 0;
-    for (int r = tid; r < m; r += kT) {
-      const double ax = row_dot(ell_col + r * kEll, ell_val + r * kEll, S.x);
-      const double res = ax - S.z[r];
-      const double einv = 1.0 / E[r];
-      v_pri = fmax(v_pri, fabs(einv * res));
-      v_rp = fmax(v_rp, fabs(res));
-      v_z = fmax(v_z, fabs(S.z[r]));
-      v_ax = fmax(v_ax, fabs(ax));
-      v_ez = fmax(v_ez, fabs(einv * S.z[r]));
-      v_eax = fmax(v_eax, fabs(einv * ax));
-    }
-    double v_dua = 0, v_rd = 0, v_aty = 0, v_px = 0, v_daty = 0, v_dpx = 0;
-    if (tid < n) {
-      const int b = tid / 15, rr = tid % 15;
+
+  // residuals + norms needed by check_termination / compute_rho_estimate (all threads get them).
+  // Leaves val*y in pst/psf: the caller restores val*w before the next iteration.
+  auto update_info = [&](const double (&dy)[kSlots]) {
+    double mx[kRedN];
+#pragma unroll
+    for (int k = 0; k < kRedN; k++) mx[k] = 0.0;
+    auto row_norms = [&](double ax, double z, double Er) {
+      const double res = ax - z;
+      const double einv = 1.0 / Er;
+      mx[0] = fmax(mx[0], fabs(einv * res));
+      mx[1] = fmax(mx[1], fabs(res));
+      mx[2] = fmax(mx[2], fabs(z));
+      mx[3] = fmax(mx[3], fabs(ax));
+      mx[4] = fmax(mx[4], fabs(einv * z));
+      mx[5] = fmax(mx[5], fabs(einv * ax));
+    };
+    if (has0) row_norms(dot0(S.x), z0, E[tid]);
+#pragma unroll
+    for (int s = 0; s < kSlots - 1; s++)
+      if ((s + 1) * kT + tid < m) row_norms(dots(s, S.x), zs[s], E[(s + 1) * kT + tid]);
+    write_p(1, dy);
+    __syncthreads();
+    const double aty = gather_col(S, pst, psf, cidx, G);
+    if (gl0) {
+      const int b = gc / 15, rr = gc % 15;
       double px = 0;
       for (int k = 0; k < 15; k++) px += Pblk[b * 225 + rr * 15 + k] * S.x[15 * b + k];
-      double aty = 0;
-      for (int q = csc_ptr[tid]; q < csc_ptr[tid + 1]; q++) { const int idx = csc_idx[q]; aty += ell_val[idx] * S.y[idx / kEll]; }
       const double res = (0.0 + px) + aty;
-      const double dinv = 1.0 / S.D[tid];
-      v_dua = fabs(dinv * res); v_rd = fabs(res); v_aty = fabs(aty); v_px = fabs(px);
-      v_daty = fabs(dinv * aty); v_dpx = fabs(dinv * px);
+      const double dinv = 1.0 / S.D[gc];
+      mx[6] = fabs(dinv * res); mx[7] = fabs(res); mx[8] = fabs(aty); mx[9] = fabs(px);
+      mx[10] = fabs(dinv * aty); mx[11] = fabs(dinv * px);
     }
-    pri_res = block_max(v_pri, S.red);
-    rp_scaled = block_max(v_rp, S.red);
-    nz = block_max(v_z, S.red);
-    nAx = block_max(v_ax, S.red);
-    const double ez = block_max(v_ez, S.red), eax = block_max(v_eax, S.red);
-    dua_res = cinv * block_max(v_dua, S.red);
-    rd_scaled = block_max(v_rd, S.red);
-    nAty = block_max(v_aty, S.red);
-    nPx = block_max(v_px, S.red);
-    const double daty = block_max(v_daty, S.red), dpx = block_max(v_dpx, S.red);
+    block_max_n<kRedN>(mx, S.red);
+    pri_res = mx[0]; rp_scaled = mx[1]; nz = mx[2]; nAx = mx[3];
+    dua_res = cinv * mx[6]; rd_scaled = mx[7]; nAty = mx[8]; nPx = mx[9];
     // unscaled norms for the tolerance computation (compute_pri_tol / compute_dua_tol)
-    nz_un = fmax(ez, eax);
-    nd_un = cinv * fmax(fmax(0.0, daty), dpx);
+    nz_un = fmax(mx[4], mx[5]);
+    nd_un = cinv * fmax(fmax(0.0, mx[10]), mx[11]);
   };
 
-  auto primal_infeasible = [&](double eps) -> bool {
-    // is_primal_infeasible: delta_y projected on the polar of the recession cone, stored in dyv
+  auto primal_infeasible = [&](double eps, double (&dy)[kSlots]) -> bool {
+    // is_primal_infeasible: delta_y projected on the polar of the recession cone (kept in place)
     double v_nd = 0, v_lhs = 0;
-    for (int r = tid; r < m; r += kT) {
-      double d = dyv[r];
-      if (upv[r] > OSQP_INFTY * MIN_SCALING) {
-        if (lov[r] < -OSQP_INFTY * MIN_SCALING) d = 0.0;
+    if (has0) {
+      double d = dy[0];
+      if (up0 > OSQP_INFTY * MIN_SCALING) {
+        if (lo0 < -OSQP_INFTY * MIN_SCALING) d = 0.0;
         else d = fmin(d, 0.0);
-      } else if (lov[r] < -OSQP_INFTY * MIN_SCALING) {
+      } else if (lo0 < -OSQP_INFTY * MIN_SCALING) {
         d = fmax(d, 0.0);
       }
-      dyv[r] = d;
-      v_nd = fmax(v_nd, fabs(E[r] * d));
-      v_lhs += upv[r] * fmax(d, 0.0) + lov[r] * fmin(d, 0.0);
+      dy[0] = d;
+      v_nd = fabs(E[tid] * d);
+      v_lhs = up0 * fmax(d, 0.0) + lo0 * fmin(d, 0.0);
     }
+#pragma unroll
+    for (int s = 0; s < kSlots - 1; s++)
+      if ((s + 1) * kT + tid < m) {   // up finite, lo = -OSQP_INFTY*E: project on d >= 0
+        const double d = fmax(dy[s + 1], 0.0);
+        dy[s + 1] = d;
+        v_nd = fmax(v_nd, fabs(E[(s + 1) * kT + tid] * d));
+        v_lhs += ups[s] * d;
+      }
     const double nd = block_max(v_nd, S.red);
     const double lhs = block_sum(v_lhs, S.red);
     if (nd > eps && lhs < -eps * nd) {
-      double v = 0;
-      if (tid < n) {
-        double s = 0;
-        for (int q = csc_ptr[tid]; q < csc_ptr[tid + 1]; q++) { const int idx = csc_idx[q]; s += ell_val[idx] * dyv[idx / kEll]; }
-        v = fabs((1.0 / S.D[tid]) * s);
-      }
+      __syncthreads();
+      write_p(2, dy);
+      __syncthreads();
+      const double s = gather_col(S, pst, psf, cidx, G);
+      const double v = gl0 ? fabs((1.0 / S.D[gc]) * s) : 0.0;
       const double nrm = block_max(v, S.red);
       return nrm < eps * nd;
     }
     return false;
   };
-  auto check_termination = [&](bool approximate) -> bool {
+  auto check_termination = [&](bool approximate, double (&dy)[kSlots]) -> bool {
     double eps_abs = P.eps_abs, eps_rel = P.eps_rel, eps_pi = P.eps_prim_inf;
     if (approximate) { eps_abs *= 10; eps_rel *= 10; eps_pi *= 10; }
     if (pri_res > OSQP_INFTY || dua_res > OSQP_INFTY) { status = -7; return true; }
     bool prim_ok = false, dual_ok = false, prim_inf = false;
     const double eps_prim = eps_abs + eps_rel * nz_un;
     if (pri_res < eps_prim) prim_ok = true;
-    else prim_inf = primal_infeasible(eps_pi);
+    else prim_inf = primal_infeasible(eps_pi, dy);
     const double eps_dual = eps_abs + eps_rel * nd_un;
     if (dua_res < eps_dual) dual_ok = true;
     if (prim_ok && dual_ok) { status = approximate ? 2 : 1; return true; }
@@ -528,80 +684,106 @@ __global__ void __launch_bounds__(kT, 1) k_qp_admm(QpDev Dv, QpParams P, const d
     return false;
   };
 
+  {
+    const double dy[kSlots] = {0, 0, 0};
+    write_p(0, dy);
+  }
+  __syncthreads();
   for (iter = 1; iter <= P.max_iter; iter++) {
-    // x_prev <- x ; rhs = sigma x_prev - q + A' w with w = rho z - y.  Half-warp per column, lanes
-    // stride its entries, fixed shuffle tree (deterministic order).
+    // x_prev <- x ; rhs = sigma x_prev - q + A' w with w = rho z - y
     {
-      const int grp = tid >> 4, ln = tid & 15;
-      for (int j0 = 0; j0 < n; j0 += kT / 16) {
-        const int j = j0 + grp;
-        double s = 0.0;
-        if (j < n) {
-          const int q1 = csc_ptr[j + 1];
-          for (int q = csc_ptr[j] + ln; q < q1; q += 16) {
-            const int idx = csc_idx[q];
-            s += ell_val[idx] * S.w[idx / kEll];
-          }
-        }
-        s += __shfl_xor_sync(0xffffffffu, s, 8);
-        s += __shfl_xor_sync(0xffffffffu, s, 4);
-        s += __shfl_xor_sync(0xffffffffu, s, 2);
-        s += __shfl_xor_sync(0xffffffffu, s, 1);
-        if (j < n && ln == 0) {
-          const double xv = S.x[j];
-          S.xp[j] = xv;
-          S.rhs[j] = (SIGMA * xv - 0.0) + s;
-        }
+      const double s = gather_col(S, pst, psf, cidx, G);
+      if (gl0) {
+        const double xv = S.x[gc];
+        S.xp[gc] = xv;
+        S.rhs[gc] = (SIGMA * xv - 0.0) + s;
       }
     }
     __syncthreads();
-    kkt_solve(S);
-    __syncthreads();
-    const bool store_dy = P.check_interval && (iter % P.check_interval == 0);
-    for (int r = tid; r < m; r += kT) {
-      const double zt = row_dot(ell_col + r * kEll, ell_val + r * kEll, S.xt);
-      const double rho = rho_of(r), zp = S.z[r], yv = S.y[r];
-      const double mix = ALPHA * zt + (1.0 - ALPHA) * zp;
-      const double v = mix + (1. / rho) * yv;
-      const double zn = fmin(fmax(v, lov[r]), upv[r]);
-      const double d = rho * (mix - zn);
-      S.z[r] = zn;
-      S.y[r] = yv + d;
-      S.w[r] = rho * zn - (yv + d);
-      if (store_dy) dyv[r] = d;
+    kkt_solve(S, Linv, L);
+    // z, y updates of the rows this thread owns; leave val*w for the next gather
+    double dy[kSlots] = {0, 0, 0};   // delta_y of this iteration (is_primal_infeasible)
+    {
+      const double rho_in = S.rho_v[1], rinv_in = S.rinv_v[1];
+      if (has0) {
+        const double zt = dot0(S.xt);
+        const double rho = S.rho_v[ty0 + 1], rinv = S.rinv_v[ty0 + 1];
+        const double mix = ALPHA * zt + (1.0 - ALPHA) * z0;
+        const double v = mix + rinv * y0;
+        const double zn = fmin(fmax(v, lo0), up0);
+        const double d = rho * (mix - zn);
+        z0 = zn; y0 = y0 + d; dy[0] = d;
+        const double w = rho * zn - y0;
+        if (struct0) {
+#pragma unroll
+          for (int k = 0; k < kEll; k++) pst[tid * kEll + k] = v0[k] * w;
+        } else {
+#pragma unroll
+          for (int k = 0; k < 3; k++) psf[(tid - ms) * 3 + k] = v0[k] * w;
+        }
+      }
+#pragma unroll
+      for (int s = 0; s < kSlots - 1; s++) {
+        const int r = (s + 1) * kT + tid;
+        if (r < m) {
+          const double zt = dots(s, S.xt);
+          const double mix = ALPHA * zt + (1.0 - ALPHA) * zs[s];
+          const double v = mix + rinv_in * ys[s];
+          const double zn = fmin(v, ups[s]);
+          const double d = rho_in * (mix - zn);
+          zs[s] = zn; ys[s] = ys[s] + d; dy[s + 1] = d;
+          const double w = rho_in * zn - ys[s];
+#pragma unroll
+          for (int k = 0; k < 3; k++) psf[(r - ms) * 3 + k] = vs[s][k] * w;
+        }
+      }
     }
     if (tid < n) S.x[tid] = ALPHA * S.xt[tid] + (1.0 - ALPHA) * S.xp[tid];
     __syncthreads();
+    const bool last = iter == P.max_iter;
     can_check = P.check_interval && (iter % P.check_interval == 0);
     bool info = false;
-    if (can_check) {
-      update_info();
+    if (can_check || last) {
+      update_info(dy);
       info = true;
-      if (check_termination(false)) break;
+      if (check_termination(false, dy)) break;
+      if (last) {   // osqp_solve's closing test with relaxed tolerances, else max-iter
+        if (!check_termination(true, dy)) status = -2;
+        break;
+      }
     }
+    bool refactor = false;
     if (P.adaptive_interval && (iter % P.adaptive_interval == 0)) {
-      if (!info) update_info();
+      if (!info) { update_info(dy); info = true; }
       double pr = rp_scaled / (fmax(nz, nAx) + 1e-10);
       double dr = rd_scaled / (fmax(fmax(0.0, nAty), nPx) + 1e-10);
       double rho_new = S.rho * sqrt(pr / (dr + 1e-10));
       rho_new = fmin(fmax(rho_new, RHO_MIN), RHO_MAX);
       if (rho_new > S.rho * ADAPT_TOL || rho_new < S.rho / ADAPT_TOL) {
         __syncthreads();
-        if (tid == 0) S.rho = rho_new;
+        if (tid == 0) {
+          S.rho = rho_new;
+          S.rho_v[1] = rho_new; S.rho_v[2] = RHO_EQ * rho_new;
+          S.rinv_v[1] = 1. / S.rho_v[1]; S.rinv_v[2] = 1. / S.rho_v[2];
+        }
         __syncthreads();
-        for (int r = tid; r < m; r += kT) S.w[r] = rho_of(r) * S.z[r] - S.y[r];
-        factorize(S, ell_col, ell_val, csc_ptr, csc_idx, Pblk, Kb);
+        refactor = true;
       }
     }
+    if (info) {   // pst/psf hold val*y (or val*dy): restore val*w (with the new rho, if it changed)
+      __syncthreads();
+      write_p(0, dy);
+      if (refactor) factorize(S, Linv, type, ell_col, ell_val, csc_ptr, csc_idx, Pblk, Kb);
+      __syncthreads();
+    }
   }
-  if (status == 0 && !can_check) { update_info(); check_termination(false); }
-  if (status == 0) { if (!check_termination(true)) status = -2; }
   __syncthreads();
   if (tid < n) Dv.cpts[static_cast<size_t>(a) * POP_MAX_PIECES * 15 + tid] = S.D[tid] * S.x[tid];
   if (tid == 0) {
     Dv.status[a] = status;
     Dv.iters[a] = iter < P.max_iter ? iter : P.max_iter;
   }
+#undef COL0
 }
 
 }  // namespace
@@ -642,7 +824,6 @@ int popk_qp_alloc(pop_handle* h, int n_agents) {
   ok &= cudaMalloc(&d->csc_idx, na * kMaxRows * kEll * sizeof(int)) == cudaSuccess;
   ok &= cudaMalloc(&d->Pblk, na * POP_MAX_PIECES * 225 * sizeof(double)) == cudaSuccess;
   ok &= cudaMalloc(&d->E, na * kMaxRows * sizeof(double)) == cudaSuccess;
-  ok &= cudaMalloc(&d->dy, na * kMaxRows * sizeof(double)) == cudaSuccess;
   ok &= cudaMalloc(&d->lo, na * kMaxRows * sizeof(double)) == cudaSuccess;
   ok &= cudaMalloc(&d->up, na * kMaxRows * sizeof(double)) == cudaSuccess;
   ok &= cudaMalloc(&d->Kb, na * kMaxN * kBand * sizeof(double)) == cudaSuccess;
@@ -656,7 +837,7 @@ int popk_qp_alloc(pop_handle* h, int n_agents) {
   POP_CUDA(h, cudaMemcpyAsync(d->QM, QM, sizeof(QM), cudaMemcpyHostToDevice, h->stream));
   POP_CUDA(h, cudaMemsetAsync(d->cpts, 0, na * POP_MAX_PIECES * 15 * sizeof(double), h->stream));
   POP_CUDA(h, cudaStreamSynchronize(h->stream));
-  POP_CUDA(h, cudaFuncSetAttribute(k_qp_admm, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(Smem))));
+  POP_CUDA(h, cudaFuncSetAttribute(k_qp_admm, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
   return POP_OK;
 }
 
@@ -664,7 +845,7 @@ void popk_qp_free(pop_handle* h) {
   QpDev* d = h->qp;
   if (!d) return;
   void* ptrs[] = {d->n_pieces, d->init, d->goal, d->dur, d->ell_col, d->ell_val, d->csc_ptr, d->csc_idx, d->Pblk,
-                  d->E, d->dy, d->lo, d->up, d->Kb, d->QM, d->cpts, d->status, d->iters};
+                  d->E, d->lo, d->up, d->Kb, d->QM, d->cpts, d->status, d->iters};
   for (void* p : ptrs) if (p) cudaFree(p);
   delete d;
   h->qp = nullptr;
@@ -680,7 +861,7 @@ int popk_qp_run(pop_handle* h, int n_agents, const double* d_hpoly, const int* d
   P.eps_abs = c.osqp_eps_abs; P.eps_rel = c.osqp_eps_rel; P.eps_prim_inf = 1e-4;
   P.vmax = vmax; P.amax = amax;
   pop_prof_begin(h, POP_STAGE_QP);
-  k_qp_admm<<<n_agents, kT, sizeof(Smem), h->stream>>>(*d, P, d_hpoly, d_rows);
+  k_qp_admm<<<n_agents, kT, kSmemBytes, h->stream>>>(*d, P, d_hpoly, d_rows);
   POP_LAUNCH_CHECK(h);
   pop_prof_end(h, POP_STAGE_QP, 1);
   return POP_OK;
@@ -728,6 +909,6 @@ extern "C" int pop_qp_solve_batch(pop_handle* h, int n, const int32_t* n_pieces,
   POP_CUDA(h, cudaStreamSynchronize(h->stream));
   for (int i = 0; i < n; i++)
     if (out_status[i] == -20)
-      return pop_fail(h, POP_E_CAPACITY, "problem %d has more than %d constraint rows (shared-memory capacity)", i, kRowCap);
+      return pop_fail(h, POP_E_CAPACITY, "problem %d exceeds the %d-row / shared-memory capacity of the QP kernel", i, kRowCap);
   return POP_OK;
 }

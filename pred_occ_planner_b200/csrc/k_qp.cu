@@ -19,7 +19,7 @@
 
 namespace {
 
-constexpr int kT = 512;                       // threads per CTA
+constexpr int kT = 384;                       // threads per CTA
 constexpr int kMaxN = 15 * POP_MAX_PIECES;    // 180 variables
 constexpr int kMaxRows = 9 * (POP_MAX_PIECES + 1) + 21 * POP_MAX_PIECES + 5 * POP_MAX_PIECES * POP_MAX_FACES;
 constexpr int kEll = 6;
@@ -70,21 +70,22 @@ __device__ __forceinline__ double limit_scaling(double v) {
 // Row capacity: every thread owns up to kSlots rows (row = slot*kT + tid) whose coefficients,
 // bounds, z and y live in REGISTERS for the whole solve; more rows (or a problem that does not fit
 // the shared-memory plan below) make the solve report status -20 (host: POP_E_CAPACITY).
-constexpr int kSlots = 3;
+constexpr int kSlots = 4;
 constexpr int kRowCap = kT * kSlots;
 constexpr int kMaxStruct = 9 * (POP_MAX_PIECES + 1) + 21 * POP_MAX_PIECES;  // 369 structured rows < kT
 constexpr int kSmemBytes = 232448;   // 227 KB opt-in maximum per CTA on sm_100a
 constexpr int kRedN = 12;
 
 // Shared-memory plan.  Fixed header, then per problem (n variables, ms structured rows, m rows):
-//   Linv  n(n+1)/2 doubles  packed lower-triangular inverse Cholesky factor (row i at i(i+1)/2)
+//   Linv  ~n(n+1)/2 doubles packed lower-triangular inverse Cholesky factor, rows padded to an
+//                           even length (row i at linv_off(i)) so that 16-byte loads stay aligned
 //   pst   6*ms doubles      products val*w of the structured rows, [row][slot]
 //   psf   3*(m-ms) doubles  products val*w of the safety rows, [row][xyz]; within a piece the 15
 //                           columns of face j are the 15 consecutive doubles at 15*j
 //   cidx  6*ms u16          column lists of the structured rows (indices into pst)
 //   type  m s8              constraint type per row (-1 loose, 0 inequality, 1 equality)
 struct Smem {
-  double x[kMaxN], xp[kMaxN], xt[kMaxN], rhs[kMaxN], tn[kMaxN], D[kMaxN];
+  double x[kMaxN + 2], xp[kMaxN + 2], xt[kMaxN + 2], rhs[kMaxN + 2], tn[kMaxN + 2], D[kMaxN + 2];
   double red[(kT / 32) * kRedN];
   double t[POP_MAX_PIECES];
   double rho, c_scale;
@@ -218,6 +219,13 @@ __device__ __forceinline__ double row_dot(const int* col, const double* val, con
   return s;
 }
 
+// Packed storage of the lower-triangular L^-1: rows 2q and 2q+1 both take 2q+2 doubles (row 2q
+// ends with one zero pad), so every row starts on a 16-byte boundary.
+__device__ __forceinline__ int linv_off(int i) {
+  const int q = i >> 1;
+  return (i & 1) ? 2 * (q + 1) * (q + 1) : 2 * q * (q + 1);
+}
+
 // K = P + sigma I + A' diag(rho) A in banded-lower storage Kb[c][d] = K[c+d][c], banded Cholesky
 // in place, then Linv = L^-1 (dense lower triangular, packed rows) into shared memory.
 __device__ void factorize(Smem& S, double* Linv, const signed char* type, const int* ell_col, const double* ell_val,
@@ -267,65 +275,127 @@ __device__ void factorize(Smem& S, double* Linv, const signed char* type, const 
     for (int r = c; r < n; r++) {
       double s = r == c ? 1.0 : 0.0;
       const int k0 = max(c, r - 15);
-      for (int k = k0; k < r; k++) s -= Kb[k * kBand + (r - k)] * Linv[k * (k + 1) / 2 + c];
-      Linv[r * (r + 1) / 2 + c] = s / Kb[r * kBand];
+      for (int k = k0; k < r; k++) s -= Kb[k * kBand + (r - k)] * Linv[linv_off(k) + c];
+      Linv[linv_off(r) + c] = s / Kb[r * kBand];
     }
   }
   __syncthreads();
 }
 
-// solve K xt = rhs:  tn = L^-1 rhs,  xt = L^-T tn.  Rows (columns) i and n-1-i are paired so every
-// pair has n+1 products; L lanes (4 or 8, consecutive threads of one warp) split a pair and
-// combine with shuffles.  FMA is fine here: the oracle solves the same system by another route.
-__device__ __forceinline__ void kkt_solve(Smem& S, const double* __restrict__ Linv, int L) {
+// solve K xt = rhs:  tn = L^-1 rhs,  xt = L^-T tn, then x = alpha xt + (1-alpha) x_prev.
+// Both triangular mat-vecs run on groups of 8 lanes with 16-byte shared-memory loads:
+//   forward:  a group owns row blocks {2b, 2b+1} for b = g and b = NB-1-g (balanced), lanes stride
+//             the 2-column chunks, each rhs chunk load feeds both rows;
+//   backward: a group owns column pairs {2b, 2b+1} for the same two b, lanes stride the rows, one
+//             load brings L^-1[i][2b..2b+1].
+// FMA is fine here: the oracle solves the same system by another route.
+__device__ __forceinline__ void kkt_solve(Smem& S, const double* __restrict__ Linv) {
   const int n = S.n, tid = threadIdx.x;
-  const int l = tid & (L - 1), p = L == 8 ? tid >> 3 : tid >> 2;
-  const int P = (n + 1) >> 1;
-  const int i1 = p, i2 = n - 1 - p;
-  const bool act = p < P, two = act && i2 != i1;
-  double a1 = 0, a2 = 0, b1 = 0, b2 = 0;
+  const int l = tid & 7, g = tid >> 3;
+  const int NB = (n + 1) >> 1;
+  const int b1 = g, b2 = NB - 1 - g;
+  const bool act = b1 <= b2, two = b1 < b2;
+  const double2* rhs2 = reinterpret_cast<const double2*>(S.rhs);
+  double s00 = 0, s01 = 0, s10 = 0, s11 = 0;   // rows 2b1, 2b1+1, 2b2, 2b2+1
   if (act) {
-    const double* r1 = Linv + i1 * (i1 + 1) / 2;
-    int j = l;
-    for (; j + L <= i1; j += 2 * L) { a1 = fma(r1[j], S.rhs[j], a1); b1 = fma(r1[j + L], S.rhs[j + L], b1); }
-    if (j <= i1) a1 = fma(r1[j], S.rhs[j], a1);
-    if (two) {
-      const double* r2 = Linv + i2 * (i2 + 1) / 2;
-      j = l;
-      for (; j + L <= i2; j += 2 * L) { a2 = fma(r2[j], S.rhs[j], a2); b2 = fma(r2[j + L], S.rhs[j + L], b2); }
-      if (j <= i2) a2 = fma(r2[j], S.rhs[j], a2);
-    }
-  }
-  a1 += b1; a2 += b2;
-  for (int o = L >> 1; o > 0; o >>= 1) {
-    a1 += __shfl_xor_sync(0xffffffffu, a1, o);
-    a2 += __shfl_xor_sync(0xffffffffu, a2, o);
-  }
-  if (act && l == 0) { S.tn[i1] = a1; if (two) S.tn[i2] = a2; }
-  __syncthreads();
-  a1 = a2 = b1 = b2 = 0;
-  if (act) {
-    int i = i1 + l;
-    for (; i + L < n; i += 2 * L) {
-      a1 = fma(Linv[i * (i + 1) / 2 + i1], S.tn[i], a1);
-      b1 = fma(Linv[(i + L) * (i + L + 1) / 2 + i1], S.tn[i + L], b1);
-    }
-    if (i < n) a1 = fma(Linv[i * (i + 1) / 2 + i1], S.tn[i], a1);
-    if (two) {
-      i = i2 + l;
-      for (; i + L < n; i += 2 * L) {
-        a2 = fma(Linv[i * (i + 1) / 2 + i2], S.tn[i], a2);
-        b2 = fma(Linv[(i + L) * (i + L + 1) / 2 + i2], S.tn[i + L], b2);
+    {
+      const double2* r0 = reinterpret_cast<const double2*>(Linv + linv_off(2 * b1));
+      const double2* r1 = reinterpret_cast<const double2*>(Linv + linv_off(2 * b1 + 1));
+      double e0 = 0, e1 = 0;
+      for (int k = l; k <= b1; k += 8) {
+        const double2 x = rhs2[k], u = r0[k], v = r1[k];
+        s00 = fma(u.x, x.x, s00); e0 = fma(u.y, x.y, e0);
+        s01 = fma(v.x, x.x, s01); e1 = fma(v.y, x.y, e1);
       }
-      if (i < n) a2 = fma(Linv[i * (i + 1) / 2 + i2], S.tn[i], a2);
+      s00 += e0; s01 += e1;
+    }
+    if (two) {
+      const double2* r0 = reinterpret_cast<const double2*>(Linv + linv_off(2 * b2));
+      const double2* r1 = reinterpret_cast<const double2*>(Linv + linv_off(2 * b2 + 1));
+      double e0 = 0, e1 = 0;
+      for (int k = l; k <= b2; k += 8) {
+        const double2 x = rhs2[k], u = r0[k], v = r1[k];
+        s10 = fma(u.x, x.x, s10); e0 = fma(u.y, x.y, e0);
+        s11 = fma(v.x, x.x, s11); e1 = fma(v.y, x.y, e1);
+      }
+      s10 += e0; s11 += e1;
     }
   }
-  a1 += b1; a2 += b2;
-  for (int o = L >> 1; o > 0; o >>= 1) {
-    a1 += __shfl_xor_sync(0xffffffffu, a1, o);
-    a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+#pragma unroll
+  for (int o = 4; o > 0; o >>= 1) {
+    s00 += __shfl_xor_sync(0xffffffffu, s00, o);
+    s01 += __shfl_xor_sync(0xffffffffu, s01, o);
+    s10 += __shfl_xor_sync(0xffffffffu, s10, o);
+    s11 += __shfl_xor_sync(0xffffffffu, s11, o);
   }
-  if (act && l == 0) { S.xt[i1] = a1; if (two) S.xt[i2] = a2; }
+  if (act && l == 0) {
+    S.tn[2 * b1] = s00;
+    if (2 * b1 + 1 < n) S.tn[2 * b1 + 1] = s01;
+    if (two) { S.tn[2 * b2] = s10; if (2 * b2 + 1 < n) S.tn[2 * b2 + 1] = s11; }
+  }
+  __syncthreads();
+  s00 = s01 = s10 = s11 = 0;
+  if (act) {
+    {
+      const int c0 = 2 * b1;
+      int i = c0 + l, off = linv_off(i) + c0;
+      double e0 = 0, e1 = 0;
+      for (; i + 8 < n; i += 16) {
+        const double2 u = *reinterpret_cast<const double2*>(Linv + off);
+        const double t = S.tn[i];
+        off += 8 * i + 40;
+        const double2 v = *reinterpret_cast<const double2*>(Linv + off);
+        const double t2 = S.tn[i + 8];
+        off += 8 * (i + 8) + 40;
+        s00 = fma(u.x, t, s00); s01 = fma(u.y, t, s01);
+        e0 = fma(v.x, t2, e0); e1 = fma(v.y, t2, e1);
+      }
+      if (i < n) {
+        const double2 u = *reinterpret_cast<const double2*>(Linv + off);
+        const double t = S.tn[i];
+        s00 = fma(u.x, t, s00); s01 = fma(u.y, t, s01);
+      }
+      s00 += e0; s01 += e1;
+    }
+    if (two) {
+      const int c0 = 2 * b2;
+      int i = c0 + l, off = linv_off(i) + c0;
+      double e0 = 0, e1 = 0;
+      for (; i + 8 < n; i += 16) {
+        const double2 u = *reinterpret_cast<const double2*>(Linv + off);
+        const double t = S.tn[i];
+        off += 8 * i + 40;
+        const double2 v = *reinterpret_cast<const double2*>(Linv + off);
+        const double t2 = S.tn[i + 8];
+        off += 8 * (i + 8) + 40;
+        s10 = fma(u.x, t, s10); s11 = fma(u.y, t, s11);
+        e0 = fma(v.x, t2, e0); e1 = fma(v.y, t2, e1);
+      }
+      if (i < n) {
+        const double2 u = *reinterpret_cast<const double2*>(Linv + off);
+        const double t = S.tn[i];
+        s10 = fma(u.x, t, s10); s11 = fma(u.y, t, s11);
+      }
+      s10 += e0; s11 += e1;
+    }
+  }
+#pragma unroll
+  for (int o = 4; o > 0; o >>= 1) {
+    s00 += __shfl_xor_sync(0xffffffffu, s00, o);
+    s01 += __shfl_xor_sync(0xffffffffu, s01, o);
+    s10 += __shfl_xor_sync(0xffffffffu, s10, o);
+    s11 += __shfl_xor_sync(0xffffffffu, s11, o);
+  }
+  if (act && l == 0) {
+    int c = 2 * b1;
+    S.xt[c] = s00; S.x[c] = ALPHA * s00 + (1.0 - ALPHA) * S.xp[c];
+    if (c + 1 < n) { S.xt[c + 1] = s01; S.x[c + 1] = ALPHA * s01 + (1.0 - ALPHA) * S.xp[c + 1]; }
+    if (two) {
+      c = 2 * b2;
+      S.xt[c] = s10; S.x[c] = ALPHA * s10 + (1.0 - ALPHA) * S.xp[c];
+      if (c + 1 < n) { S.xt[c + 1] = s11; S.x[c + 1] = ALPHA * s11 + (1.0 - ALPHA) * S.xp[c + 1]; }
+    }
+  }
   __syncthreads();
 }
 
@@ -394,14 +464,15 @@ __global__ void __launch_bounds__(kT, 1) k_qp_admm(QpDev Dv, QpParams P, const d
   }
   __syncthreads();
   const int n = S.n, m = S.m, ms = S.ms;
-  const size_t dyn_bytes = sizeof(double) * (static_cast<size_t>(n) * (n + 1) / 2 + 6 * ms + 3 * (m - ms)) +
+  const int linv_len = linv_off((n + 1) & ~1);
+  const size_t dyn_bytes = sizeof(double) * (static_cast<size_t>(linv_len) + 6 * ms + 3 * (m - ms)) +
                            sizeof(unsigned short) * 6 * ms + m;
   if (m > kRowCap || kHdrBytes + dyn_bytes > kSmemBytes) {
     if (tid == 0) { Dv.status[a] = -20; Dv.iters[a] = 0; }
     return;
   }
   double* Linv = reinterpret_cast<double*>(smem_raw + kHdrBytes);
-  double* pst = Linv + n * (n + 1) / 2;
+  double* pst = Linv + linv_len;
   double* psf = pst + 6 * ms;
   unsigned short* cidx = reinterpret_cast<unsigned short*>(psf + 3 * (m - ms));
   signed char* type = reinterpret_cast<signed char*>(cidx + 6 * ms);
@@ -417,7 +488,8 @@ __global__ void __launch_bounds__(kT, 1) k_qp_admm(QpDev Dv, QpParams P, const d
     E[r] = 1.0;
   }
   for (int e = tid; e < M * 225; e += kT) Pblk[e] = Dv.QM[e % 225];
-  if (tid < n) { S.D[tid] = 1.0; S.x[tid] = 0.0; }
+  for (int e = tid; e < linv_len; e += kT) Linv[e] = 0.0;   // row pads stay zero
+  if (tid < kMaxN + 2) { S.D[tid] = 1.0; S.x[tid] = 0.0; S.xp[tid] = 0.0; S.xt[tid] = 0.0; S.rhs[tid] = 0.0; S.tn[tid] = 0.0; }
   __syncthreads();
   // column index: entries of column j in ascending row order
   if (tid == 0) csc_ptr[0] = 0;
@@ -583,7 +655,6 @@ __global__ void __launch_bounds__(kT, 1) k_qp_admm(QpDev Dv, QpParams P, const d
   };
 
   const int G = 4 * n <= kT ? 4 : 2;          // lanes per column in gather_col
-  const int L = 4 * (n + 1) <= kT ? 8 : 4;    // lanes per row pair in kkt_solve
   const int gc = G == 4 ? tid >> 2 : tid >> 1;  // this thread's gather column
   const bool gl0 = (tid & (G - 1)) == 0 && gc < n;
 
@@ -685,11 +756,11 @@ __global__ void __launch_bounds__(kT, 1) k_qp_admm(QpDev Dv, QpParams P, const d
   };
 
   {
-    const double dy[kSlots] = {0, 0, 0};
+    const double dy[kSlots] = {0, 0, 0, 0};
     write_p(0, dy);
   }
   __syncthreads();
-  for (iter = 1; iter <= P.max_iter; iter++) {
+  auto admm_iter = [&](double (&dy)[kSlots]) {
     // x_prev <- x ; rhs = sigma x_prev - q + A' w with w = rho z - y
     {
       const double s = gather_col(S, pst, psf, cidx, G);
@@ -700,9 +771,8 @@ __global__ void __launch_bounds__(kT, 1) k_qp_admm(QpDev Dv, QpParams P, const d
       }
     }
     __syncthreads();
-    kkt_solve(S, Linv, L);
+    kkt_solve(S, Linv);
     // z, y updates of the rows this thread owns; leave val*w for the next gather
-    double dy[kSlots] = {0, 0, 0};   // delta_y of this iteration (is_primal_infeasible)
     {
       const double rho_in = S.rho_v[1], rinv_in = S.rinv_v[1];
       if (has0) {
@@ -738,9 +808,23 @@ __global__ void __launch_bounds__(kT, 1) k_qp_admm(QpDev Dv, QpParams P, const d
         }
       }
     }
-    if (tid < n) S.x[tid] = ALPHA * S.xt[tid] + (1.0 - ALPHA) * S.xp[tid];
     __syncthreads();
-    const bool last = iter == P.max_iter;
+  };
+  // Hot iterations run in a tight inner loop up to the next event (termination test, rho
+  // adaptation, last iteration); only the event iteration keeps its delta_y.
+  iter = 0;
+  while (true) {
+    int next = P.max_iter;
+    if (P.check_interval) next = min(next, (iter / P.check_interval + 1) * P.check_interval);
+    if (P.adaptive_interval) next = min(next, (iter / P.adaptive_interval + 1) * P.adaptive_interval);
+    for (; iter + 1 < next; iter++) {
+      double scratch[kSlots];
+      admm_iter(scratch);
+    }
+    double dy[kSlots] = {0, 0, 0, 0};   // delta_y of this iteration (is_primal_infeasible)
+    admm_iter(dy);
+    iter++;
+    const bool last = iter >= P.max_iter;
     can_check = P.check_interval && (iter % P.check_interval == 0);
     bool info = false;
     if (can_check || last) {

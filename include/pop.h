@@ -285,6 +285,10 @@ int pop_profile_enable(pop_handle* h, int on);
 /* Accumulated milliseconds and launch counts per stage since the last reset. */
 int pop_profile_read(pop_handle* h, float* ms /*[POP_STAGE_COUNT]*/,
                      int64_t* launches /*[POP_STAGE_COUNT]*/, int reset);
+/* SM cycles the last QP launch spent per problem: out = n x 8 int64 {assembly+scaling+first
+ * factorisation, all factorisations, ADMM loop, number of factorisations, and (builds with
+ * -DPOP_QP_PHASE_PROF only) gather, KKT solve, row update inside the loop, reserved}. */
+int pop_qp_profile(pop_handle* h, int n, int64_t* out);
 /* total kernels launched by this handle since creation */
 int64_t pop_kernel_launches(const pop_handle* h);
 

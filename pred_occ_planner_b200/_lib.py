@@ -135,6 +135,7 @@ SYMBOLS = [
     ("pop_traj_buffers", _I, [_VP, C.POINTER(_VP), C.POINTER(_VP)]),
     ("pop_profile_enable", _I, [_VP, _I]),
     ("pop_profile_read", _I, [_VP, _PF, C.POINTER(C.c_int64), _I]),
+    ("pop_qp_profile", _I, [_VP, _I, C.POINTER(C.c_int64)]),
     ("pop_kernel_launches", C.c_int64, [_VP]),
 ]
 

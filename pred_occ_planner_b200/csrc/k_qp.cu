@@ -9,10 +9,21 @@
 // traj_opt/include/iosqp.hpp:40-115 with eps_abs = eps_rel = 1e-3 and default settings —
 // Ruiz equilibration, per-row rho, alpha = 1.6 relaxation, termination test every 25
 // iterations, residual-balancing rho updates at a fixed interval.  The KKT solve is done on the
-// reduced SPD matrix P + sigma I + A' diag(rho) A, which for this problem is block-tridiagonal
-// with 15x15 blocks (continuity rows couple neighbouring pieces only): banded Cholesky once per
-// rho, then block forward/backward recurrences with pre-multiplied inverse blocks, all in
-// shared memory.  Inner products and inf-norms use warp shuffles + one shared-memory stage.
+// reduced SPD matrix K = P + sigma I + A' diag(rho) A, banded with half bandwidth 15
+// (continuity rows couple neighbouring pieces only).
+//
+// How one ADMM iteration runs on the SM (all operands on chip, nothing touches L2/HBM):
+//   * every thread owns up to kSlots constraint rows for the whole solve: coefficients, bounds,
+//     z and y live in REGISTERS; after the z/y update the thread leaves coefficient * w
+//     (w = rho z - y) at the row's slots of a column-ordered product array in shared memory;
+//   * A'w is then a contiguous sum per column (kG lanes per column + shuffle);
+//   * K^-1 is applied as L^-T (L^-1 rhs) with the dense inverse Cholesky factor held in
+//     REGISTERS as 6x6 tiles, one tile per thread (n <= 150; larger problems stream the packed
+//     factor from shared memory with 16-byte loads): tile x vector products, partial sums
+//     exchanged through shared memory, four barriers;
+//   * the factor itself (once per rho): banded K assembled in shared memory, warp-synchronous
+//     banded Cholesky, then one thread per column of L^-1 by forward substitution with the last
+//     15 entries in a register window.
 #include <cfloat>
 
 #include "pop_internal.h"
@@ -42,21 +53,23 @@ struct QpDev {
   double* init = nullptr;     // [agent][9]
   double* goal = nullptr;     // [agent][9]
   double* dur = nullptr;      // [agent][POP_MAX_PIECES]
-  // workspaces per agent
+  // workspaces per agent (set-up only; the iteration never reads them)
   int* ell_col = nullptr;     // [agent][kMaxRows][6]
   double* ell_val = nullptr;  // [agent][kMaxRows][6]
   int* csc_ptr = nullptr;     // [agent][kMaxN+1]
   int* csc_idx = nullptr;     // [agent][kMaxRows*6]  → row*6+slot
+  unsigned short* dst = nullptr;  // [agent][kMaxRows*6] position of (row,slot) in column order
   double* Pblk = nullptr;     // [agent][POP_MAX_PIECES][225]
   double* E = nullptr;        // [agent][kMaxRows]
   double* lo = nullptr;       // [agent][kMaxRows] scaled lower bounds
   double* up = nullptr;       // [agent][kMaxRows] scaled upper bounds
-  double* Kb = nullptr;       // [agent][kMaxN][kBand] banded lower factor
   double* QM = nullptr;       // [225] jerk cost block
   // outputs
   double* cpts = nullptr;     // [agent][POP_MAX_PIECES*5][3]
   int* status = nullptr;      // [agent]
   int* iters = nullptr;       // [agent]
+  long long* prof = nullptr;  // [agent][8] SM cycles: setup, factorisations, ADMM loop, #factorisations,
+                              //            and inside the loop: gather, KKT solve, row update, (unused)
 };
 
 namespace {
@@ -67,32 +80,42 @@ __device__ __forceinline__ double limit_scaling(double v) {
   return v;
 }
 
-// Row capacity: every thread owns up to kSlots rows (row = slot*kT + tid) whose coefficients,
-// bounds, z and y live in REGISTERS for the whole solve; more rows (or a problem that does not fit
-// the shared-memory plan below) make the solve report status -20 (host: POP_E_CAPACITY).
-constexpr int kSlots = 4;
-constexpr int kRowCap = kT * kSlots;
+// Row capacity: every thread owns up to kSlots rows (row = slot*kT + tid); more rows (or a
+// problem that does not fit the shared-memory plan below) make the solve report status -20
+// (host: POP_E_CAPACITY).
+constexpr int kSlotsMax = 4;            // shared-memory factor path; the register-tile path owns 3
+constexpr int kRowCap = kT * kSlotsMax;
 constexpr int kMaxStruct = 9 * (POP_MAX_PIECES + 1) + 21 * POP_MAX_PIECES;  // 369 structured rows < kT
 constexpr int kSmemBytes = 232448;   // 227 KB opt-in maximum per CTA on sm_100a
 constexpr int kRedN = 12;
+constexpr int kVec = kMaxN + 6;      // vectors padded so 6-wide tile loads stay in bounds
+constexpr int kTileNB = 25;          // register-tile path: n <= 150 → <= 325 tiles of 6x6
+// Shared memory of the register-tile variant: header + partial sums (150 x 28 + 26 x 150) + Kb + products
+// + types for n <= 150, m <= 3 kT.  Leaving the rest of the 256 KB to L1 keeps the set-up arrays
+// and the few spilled row constants close.
+constexpr int kSmemTiles = 150 * 1024;
 
-// Shared-memory plan.  Fixed header, then per problem (n variables, ms structured rows, m rows):
+// Shared-memory plan.  Fixed header, then per problem (n variables, m rows, nnz non-zeros of A):
 //   Linv  ~n(n+1)/2 doubles packed lower-triangular inverse Cholesky factor, rows padded to an
-//                           even length (row i at linv_off(i)) so that 16-byte loads stay aligned
-//   pst   6*ms doubles      products val*w of the structured rows, [row][slot]
-//   psf   3*(m-ms) doubles  products val*w of the safety rows, [row][xyz]; within a piece the 15
-//                           columns of face j are the 15 consecutive doubles at 15*j
-//   cidx  6*ms u16          column lists of the structured rows (indices into pst)
+//                           even length (row i at linv_off(i)); on the register-tile path it is
+//                           only a staging area and the iteration reuses it for partial sums
+//   Kb    16 n doubles      banded K / its Cholesky factor, Kb[c][d] = K[c+d][c]
+//   pc    <= nnz+16n+2      coefficient * u products in column order; column c starts at cptr[c],
+//                           padded so that start = 2c (mod 16): the two lanes per column of a
+//                           warp's gather then hit all 16 eight-byte bank pairs evenly; the
+//                           last slot absorbs the stores of unused row slots
 //   type  m s8              constraint type per row (-1 loose, 0 inequality, 1 equality)
 struct Smem {
-  double x[kMaxN + 2], xp[kMaxN + 2], xt[kMaxN + 2], rhs[kMaxN + 2], tn[kMaxN + 2], D[kMaxN + 2];
+  double x[kVec], xp[kVec], xt[kVec], rhs[kVec], tn[kVec], D[kVec], rd[kVec];
   double red[(kT / 32) * kRedN];
   double t[POP_MAX_PIECES];
   double rho, c_scale;
   double rho_v[3], rinv_v[3];   // indexed by type+1: loose, inequality, equality
   int face_off[POP_MAX_PIECES + 1];
-  int M, n, m, ms, status, fail;
-  unsigned short cptr[kMaxN + 2];
+  int M, n, m, ms, nnz, status, fail;
+  unsigned short cptr[kMaxN + 2];   // start of column c in pc (padded: start = 2c mod 16)
+  unsigned short clen[kMaxN + 2];   // entries of column c
+  int pc_len;
 };
 constexpr int kHdrBytes = (sizeof(Smem) + 15) / 16 * 16;
 
@@ -226,11 +249,25 @@ __device__ __forceinline__ int linv_off(int i) {
   return (i & 1) ? 2 * (q + 1) * (q + 1) : 2 * q * (q + 1);
 }
 
-// K = P + sigma I + A' diag(rho) A in banded-lower storage Kb[c][d] = K[c+d][c], banded Cholesky
-// in place, then Linv = L^-1 (dense lower triangular, packed rows) into shared memory.
-__device__ void factorize(Smem& S, double* Linv, const signed char* type, const int* ell_col, const double* ell_val,
-                          const int* csc_ptr, const int* csc_idx, const double* Pblk, double* Kb) {
-  const int n = S.n;
+struct TileId { int rb, cb, NB, NBp; bool act; };
+
+// K = P + sigma I + A' diag(rho) A → banded Cholesky → L^-1, all in shared memory.
+//   1. thread per band entry: P block + safety rows (same control point only) + structured rows
+//      through the column lists; coefficients are read from the set-up arrays in global memory
+//      (L2), a few dozen independent loads per entry;
+//   2. warp 0: right-looking banded Cholesky, one pivot per step (sqrt, scale the column, rank-1
+//      update of the 15x15 trailing window), __syncwarp between the three sub-steps;
+//   3. thread per column c of L^-1: forward substitution x_r = (e_c - sum_k L[r][k] x_k) / L[r][r]
+//      with the last 15 x in a rotating register window; all columns walk r together so the
+//      factor rows are shared-memory broadcasts.  TILES: every 6 rows the block of L^-1 is
+//      handed through a 6 x 6NB staging buffer to the threads whose register tile it fills;
+//      otherwise the rows go to the packed factor in shared memory.
+template <bool TILES, int NT>
+__device__ void factorize(Smem& S, double* __restrict__ Linv, double (&T)[NT], const TileId& ti, double* __restrict__ Kb,
+                          const signed char* __restrict__ type, const int* __restrict__ ell_col,
+                          const double* __restrict__ ell_val, const int* __restrict__ csc_ptr,
+                          const int* __restrict__ csc_idx, const double* __restrict__ Pblk) {
+  const int n = S.n, ms = S.ms;
   const int tid = threadIdx.x;
   for (int e = tid; e < n * kBand; e += kT) {
     const int c = e / kBand, d = e % kBand, r = c + d;
@@ -238,8 +275,18 @@ __device__ void factorize(Smem& S, double* Linv, const signed char* type, const 
     if (r < n) {
       if (r / 15 == c / 15) v = Pblk[(c / 15) * 225 + (r % 15) * 15 + (c % 15)];
       if (d == 0) v += SIGMA;
-      for (int q = csc_ptr[r]; q < csc_ptr[r + 1]; q++) {   // rows containing column r, ascending
+      // rows containing column r in ascending order: structured rows first, then (only when r
+      // and c belong to the same control point) the safety rows of that piece
+      const int q0 = csc_ptr[r], q1 = csc_ptr[r + 1];
+      const bool same_pt = r / 3 == c / 3;
+      for (int q = q0; q < q1; q++) {
         const int idx = csc_idx[q], row = idx / kEll;
+        if (row >= ms) {
+          if (!same_pt) break;
+          const double rho = S.rho_v[type[row] + 1];
+          v += (rho * ell_val[idx]) * ell_val[idx - (r - c)];   // slots of a safety row are x,y,z
+          continue;
+        }
         const int* rc = ell_col + row * kEll;
         for (int k = 0; k < kEll; k++)
           if (rc[k] == c) {
@@ -252,43 +299,168 @@ __device__ void factorize(Smem& S, double* Linv, const signed char* type, const 
     Kb[e] = v;
   }
   __syncthreads();
-  // banded Cholesky, column by column
-  for (int j = 0; j < n; j++) {
-    if (tid == 0) {
-      double d = Kb[j * kBand];
-      for (int k = max(0, j - 15); k < j; k++) { const double l = Kb[k * kBand + (j - k)]; d -= l * l; }
-      if (!(d > 0.0)) S.fail = 1;
-      Kb[j * kBand] = sqrt(d);
+  if (tid < 32) {
+    const int lane = tid;
+    int udi[4], udk[4];   // trailing-window entries of this lane: (di, dk), 1 <= dk <= di <= 15
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const int e = lane + 32 * u;
+      int di = 1, base = 0;
+      while (base + di <= e) { base += di; di++; }
+      udi[u] = e < 120 ? di : 0;
+      udk[u] = e - base + 1;
     }
-    __syncthreads();
-    if (tid >= 1 && tid <= 15 && j + tid < n) {
-      const int i = j + tid;
-      double s = Kb[j * kBand + tid];
-      for (int k = max(0, i - 15); k < j; k++) s -= Kb[k * kBand + (i - k)] * Kb[k * kBand + (j - k)];
-      Kb[j * kBand + tid] = s / Kb[j * kBand];
+    for (int j = 0; j < n; j++) {
+      // pivot
+      const double dj = Kb[j * kBand];
+      if (!(dj > 0.0)) { if (lane == 0) S.fail = 1; }
+      const double lj = sqrt(dj > 0.0 ? dj : 1.0);
+      const double inv = 1.0 / lj;
+      __syncwarp();
+      if (lane == 0) { Kb[j * kBand] = lj; S.rd[j] = inv; }
+      if (lane >= 1 && lane < kBand && j + lane < n) Kb[j * kBand + lane] = Kb[j * kBand + lane] / lj;
+      __syncwarp();
+      // trailing update: a[i][k] -= l[i][j] l[k][j] for j < k <= i <= j+15 (120 entries, 4 per lane)
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const int di = udi[u], dk = udk[u];
+        if (di > 0 && j + di < n) Kb[(j + dk) * kBand + (di - dk)] -= Kb[j * kBand + di] * Kb[j * kBand + dk];
+      }
+      __syncwarp();
     }
-    __syncthreads();
   }
-  // thread per column: forward substitution on the banded factor; previously computed entries of
-  // the same column are read back from shared memory
-  for (int c = tid; c < n; c += kT) {
-    for (int r = c; r < n; r++) {
-      double s = r == c ? 1.0 : 0.0;
-      const int k0 = max(c, r - 15);
-      for (int k = k0; k < r; k++) s -= Kb[k * kBand + (r - k)] * Linv[linv_off(k) + c];
-      Linv[linv_off(r) + c] = s / Kb[r * kBand];
+  __syncthreads();
+  {
+    const int c = tid;
+    const int nst = 6 * ti.NB;   // staging row length (TILES)
+    double w[15];   // w[k] = x_{r-1-k}
+#pragma unroll
+    for (int k = 0; k < 15; k++) w[k] = 0.0;
+    const int r_end = TILES ? nst : n;
+    for (int r = 0; r < r_end; r++) {
+      double xr = 0.0;
+      if (c < n && r < n && r >= c) {
+        // L[r][r-1-k] = Kb[(r-1-k)*16 + (k+1)]; entries before the column start multiply w = 0
+        double s0 = r == c ? 1.0 : 0.0, s1 = 0.0;
+#pragma unroll
+        for (int k = 0; k < 15; k += 2) {
+          s0 -= Kb[max(r - 1 - k, 0) * kBand + (k + 1)] * w[k];
+          if (k + 1 < 15) s1 -= Kb[max(r - 2 - k, 0) * kBand + (k + 2)] * w[k + 1];
+        }
+        xr = (s0 + s1) * S.rd[r];
+      }
+#pragma unroll
+      for (int k = 14; k > 0; k--) w[k] = w[k - 1];
+      w[0] = xr;
+      if constexpr (TILES) {
+        if (c < nst) Linv[(r % 6) * nst + c] = xr;
+        if (r % 6 == 5) {
+          __syncthreads();
+          if (ti.act && ti.rb == r / 6) {
+#pragma unroll
+            for (int rr = 0; rr < 6; rr++)
+#pragma unroll
+              for (int cc = 0; cc < 6; cc++) T[rr * 6 + cc] = Linv[rr * nst + 6 * ti.cb + cc];
+          }
+          __syncthreads();
+        }
+      } else {
+        if (c < n && r < n && r >= c) Linv[linv_off(r) + c] = xr;
+      }
     }
   }
   __syncthreads();
 }
 
-// solve K xt = rhs:  tn = L^-1 rhs,  xt = L^-T tn, then x = alpha xt + (1-alpha) x_prev.
+// ---- K^-1 application, register-tile path (n <= 150) -----------------------------------------
+// Thread t < NB(NB+1)/2 holds the 6x6 tile (rb, cb) of L^-1 (NB = ceil(n/6), cb <= rb).
+//   forward:  part[6 rb + r][cb] = tile[r][:] . rhs[6 cb ..],  tn[i] = sum_cb part[i][cb]
+//   backward: part[rb][6 cb + c] = tile[:][c] . tn[6 rb ..],   xt[j] = sum_rb part[rb][j]
+// then x = alpha xt + (1 - alpha) x_prev.  FMA is fine here: bit parity of this solve with a CPU
+// factorisation is not attainable anyway.
+template <int NT>
+__device__ __forceinline__ void kkt_tiles(Smem& S, const double (&T)[NT], const TileId& ti,
+                                          double* __restrict__ part1, double* __restrict__ part2) {
+  // part1 [6NB][NBp] (NBp even, = 2 mod 4, >= NB) and part2 [NBq][6NB] (NBq = even >= NB) are zero
+  // outside the tiles' entries, so the reductions add whole rows / columns without any masking:
+  // two lanes per output, half a row (column) each, independent loads, one shuffle.
+  const int n = S.n, tid = threadIdx.x;
+  const int NB6 = 6 * ti.NB;
+  if (ti.act) {
+    const double2* xr = reinterpret_cast<const double2*>(S.rhs + 6 * ti.cb);
+    const double2 x01 = xr[0], x23 = xr[1], x45 = xr[2];
+    double* out = part1 + (6 * ti.rb) * ti.NBp + ti.cb;
+#pragma unroll
+    for (int r = 0; r < 6; r++) {
+      double s = T[r * 6] * x01.x;
+      s = fma(T[r * 6 + 1], x01.y, s);
+      s = fma(T[r * 6 + 2], x23.x, s);
+      s = fma(T[r * 6 + 3], x23.y, s);
+      s = fma(T[r * 6 + 4], x45.x, s);
+      s = fma(T[r * 6 + 5], x45.y, s);
+      out[r * ti.NBp] = s;
+    }
+  }
+  __syncthreads();
+  {
+    // NBp/2 (odd) 16-byte loads per row: lane 0 takes the first (NBp/2+1)/2, lane 1 the rest
+    const int i = tid >> 1, half = tid & 1, c0n = ((ti.NBp >> 1) + 1) >> 1;
+    const int cnt = half ? (ti.NBp >> 1) - c0n : c0n;
+    double a = 0, b = 0;
+    if (i < n) {
+      const double2* pr = reinterpret_cast<const double2*>(part1 + i * ti.NBp) + half * c0n;
+#pragma unroll 4
+      for (int k = 0; k < cnt; k++) { const double2 v = pr[k]; a += v.x; b += v.y; }
+    }
+    double sum = a + b;
+    sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+    if (i < n && half == 0) S.tn[i] = sum;
+  }
+  __syncthreads();
+  if (ti.act) {
+    const double2* tr = reinterpret_cast<const double2*>(S.tn + 6 * ti.rb);
+    const double2 t01 = tr[0], t23 = tr[1], t45 = tr[2];
+    double o[6];
+#pragma unroll
+    for (int c = 0; c < 6; c++) {
+      double s = T[c] * t01.x;
+      s = fma(T[6 + c], t01.y, s);
+      s = fma(T[12 + c], t23.x, s);
+      s = fma(T[18 + c], t23.y, s);
+      s = fma(T[24 + c], t45.x, s);
+      s = fma(T[30 + c], t45.y, s);
+      o[c] = s;
+    }
+    double2* out = reinterpret_cast<double2*>(part2 + ti.rb * NB6 + 6 * ti.cb);
+    out[0] = make_double2(o[0], o[1]); out[1] = make_double2(o[2], o[3]); out[2] = make_double2(o[4], o[5]);
+  }
+  __syncthreads();
+  {
+    const int j = tid >> 1, half = tid & 1, cnt = (ti.NB + 1) >> 1;   // rows of part2 per lane
+    double a = 0, b = 0;
+    if (j < n) {
+      const double* pc = part2 + half * cnt * NB6 + j;
+      int k = 0;
+#pragma unroll 4
+      for (; k + 1 < cnt; k += 2) { a += pc[k * NB6]; b += pc[(k + 1) * NB6]; }
+      if (k < cnt) a += pc[k * NB6];
+    }
+    double xt = a + b;
+    xt += __shfl_xor_sync(0xffffffffu, xt, 1);
+    if (j < n && half == 0) {
+      S.xt[j] = xt;
+      S.x[j] = ALPHA * xt + (1.0 - ALPHA) * S.xp[j];
+    }
+  }
+  __syncthreads();
+}
+
+// ---- K^-1 application, shared-memory path (n > 150) -------------------------------------------
 // Both triangular mat-vecs run on groups of 8 lanes with 16-byte shared-memory loads:
 //   forward:  a group owns row blocks {2b, 2b+1} for b = g and b = NB-1-g (balanced), lanes stride
 //             the 2-column chunks, each rhs chunk load feeds both rows;
 //   backward: a group owns column pairs {2b, 2b+1} for the same two b, lanes stride the rows, one
 //             load brings L^-1[i][2b..2b+1].
-// FMA is fine here: the oracle solves the same system by another route.
 __device__ __forceinline__ void kkt_solve(Smem& S, const double* __restrict__ Linv) {
   const int n = S.n, tid = threadIdx.x;
   const int l = tid & 7, g = tid >> 3;
@@ -399,38 +571,37 @@ __device__ __forceinline__ void kkt_solve(Smem& S, const double* __restrict__ Li
   __syncthreads();
 }
 
-// (A' u)_c from the products u-weighted rows left in pst/psf: G lanes (2 or 4) per column, the
-// safety rows of the column's piece strided over the lanes, the structured rows on the last lane;
-// fixed order, shuffle tree.  Every thread of the CTA calls this; lane 0 of column c < n gets the sum.
-__device__ __forceinline__ double gather_col(const Smem& S, const double* __restrict__ pst,
-                                             const double* __restrict__ psf,
-                                             const unsigned short* __restrict__ cidx, int G) {
-  const int tid = threadIdx.x;
-  const int lane = tid & (G - 1), c = G == 4 ? tid >> 2 : tid >> 1;
+// (A' u)_c = sum of the column-c segment of pc: 2 lanes per column (n <= 180 → 360 threads),
+// the lane's first entry and entry count stay in registers; fixed order, one shuffle.  Every
+// thread of the CTA calls this; the even lane of column c < n gets the sum.
+__device__ __forceinline__ double gather_col(const double* __restrict__ pq, int cnt) {
   double s0 = 0, s1 = 0;
-  if (c < S.n) {
-    const int i = c / 15, cc = c - 15 * i;
-    const int f0 = S.face_off[i], F = S.face_off[i + 1] - f0;
-    const double* base = psf + 15 * f0 + cc;
-    int j = lane;
-    for (; j + G < F; j += 2 * G) { s0 += base[15 * j]; s1 += base[15 * (j + G)]; }
-    if (j < F) s0 += base[15 * j];
-    if (lane == G - 1)
-      for (int q = S.cptr[c]; q < S.cptr[c + 1]; q++) s1 += pst[cidx[q]];
-  }
+  int k = 0;
+#pragma unroll 4
+  for (; k + 1 < cnt; k += 2) { s0 += pq[2 * k]; s1 += pq[2 * k + 2]; }
+  if (k < cnt) s0 += pq[2 * k];
   double s = s0 + s1;
-  for (int o = G >> 1; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  s += __shfl_xor_sync(0xffffffffu, s, 1);
   return s;
 }
 
+// TILES = true: problems with n <= 150 and m <= 3 kT rows (L^-1 in registers, 3 row slots per
+// thread); TILES = false: the rest (L^-1 streamed from shared memory, 4 row slots).  Both variants
+// are launched over the whole batch; each CTA returns at once if the problem is not its kind.
+template <bool TILES>
 __global__ void __launch_bounds__(kT, 1) k_qp_admm(QpDev Dv, QpParams P, const double* __restrict__ hpoly_all,
                                                    const int* __restrict__ rows_all) {
+  constexpr int kSlots = TILES ? 3 : 4;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Smem& S = *reinterpret_cast<Smem*>(smem_raw);
   const int a = blockIdx.x, tid = threadIdx.x;
+  const long long clk0 = clock64();
+  long long clk_fact = 0;
+  int n_fact = 0;
   const int M = Dv.n_pieces[a];
+  long long clk_g = 0, clk_k = 0, clk_r = 0;
   if (M <= 0 || M > POP_MAX_PIECES) {
-    if (tid == 0) { Dv.status[a] = 0; Dv.iters[a] = 0; }
+    if (TILES && tid == 0) { Dv.status[a] = 0; Dv.iters[a] = 0; }
     return;
   }
   const double* init = Dv.init + a * 9;
@@ -441,9 +612,9 @@ __global__ void __launch_bounds__(kT, 1) k_qp_admm(QpDev Dv, QpParams P, const d
   double* ell_val = Dv.ell_val + static_cast<size_t>(a) * kMaxRows * kEll;
   int* csc_ptr = Dv.csc_ptr + static_cast<size_t>(a) * (kMaxN + 1);
   int* csc_idx = Dv.csc_idx + static_cast<size_t>(a) * kMaxRows * kEll;
+  unsigned short* dstv = Dv.dst + static_cast<size_t>(a) * kMaxRows * kEll;
   double* Pblk = Dv.Pblk + static_cast<size_t>(a) * POP_MAX_PIECES * 225;
   double* E = Dv.E + static_cast<size_t>(a) * kMaxRows;
-  double* Kb = Dv.Kb + static_cast<size_t>(a) * kMaxN * kBand;
   double* lov = Dv.lo + static_cast<size_t>(a) * kMaxRows;
   double* upv = Dv.up + static_cast<size_t>(a) * kMaxRows;
 
@@ -458,24 +629,29 @@ __global__ void __launch_bounds__(kT, 1) k_qp_admm(QpDev Dv, QpParams P, const d
     }
     S.ms = 9 * (M + 1) + 21 * M;
     S.m = S.ms + 5 * S.face_off[M];
+    // non-zeros of A: pos 2 + vel 4 + acc 6 per join and dimension (1 + 2 + 3 at each end), velocity
+    // boxes 2, acceleration boxes 3, safety rows 3
+    S.nnz = 87 * M + 15 * S.face_off[M];   // 36 per join/end pair + 24 + 27 box entries per piece
     S.status = 0; S.fail = 0; S.rho = RHO0; S.c_scale = 1.0;
     S.rho_v[0] = RHO_MIN; S.rho_v[1] = RHO0; S.rho_v[2] = RHO_EQ * RHO0;
     for (int k = 0; k < 3; k++) S.rinv_v[k] = 1. / S.rho_v[k];
   }
   __syncthreads();
-  const int n = S.n, m = S.m, ms = S.ms;
-  const int linv_len = linv_off((n + 1) & ~1);
-  const size_t dyn_bytes = sizeof(double) * (static_cast<size_t>(linv_len) + 6 * ms + 3 * (m - ms)) +
-                           sizeof(unsigned short) * 6 * ms + m;
-  if (m > kRowCap || kHdrBytes + dyn_bytes > kSmemBytes) {
+  const int n = S.n, m = S.m, ms = S.ms, nnz = S.nnz;
+  if (((n + 5) / 6 <= kTileNB && m <= 3 * kT) != TILES) return;   // the other variant's problem
+  const int NBt = (n + 5) / 6;
+  // TILES: staging rows (6 x 6NB) / partial sums (6NB x NBp) instead of the packed factor
+  const int part1_len = 6 * NBt * (((NBt + 1) & ~1) + 4), part2_len = ((NBt + 1) & ~1) * 6 * NBt;
+  const int linv_len = TILES ? max(36 * NBt, part1_len + part2_len) : linv_off((n + 1) & ~1);
+  const size_t dyn_bytes = sizeof(double) * (static_cast<size_t>(linv_len) + n * kBand + nnz + 16 * n + 2) + m + 16;
+  if (m > kRowCap || kHdrBytes + dyn_bytes > (TILES ? kSmemTiles : kSmemBytes)) {
     if (tid == 0) { Dv.status[a] = -20; Dv.iters[a] = 0; }
     return;
   }
   double* Linv = reinterpret_cast<double*>(smem_raw + kHdrBytes);
-  double* pst = Linv + linv_len;
-  double* psf = pst + 6 * ms;
-  unsigned short* cidx = reinterpret_cast<unsigned short*>(psf + 3 * (m - ms));
-  signed char* type = reinterpret_cast<signed char*>(cidx + 6 * ms);
+  double* Kb = Linv + linv_len;
+  double* pc = Kb + n * kBand;
+  signed char* type = reinterpret_cast<signed char*>(pc + nnz + 16 * n + 2);
 
   // ---- assembly ----
   for (int r = tid; r < m; r += kT) {
@@ -489,7 +665,7 @@ __global__ void __launch_bounds__(kT, 1) k_qp_admm(QpDev Dv, QpParams P, const d
   }
   for (int e = tid; e < M * 225; e += kT) Pblk[e] = Dv.QM[e % 225];
   for (int e = tid; e < linv_len; e += kT) Linv[e] = 0.0;   // row pads stay zero
-  if (tid < kMaxN + 2) { S.D[tid] = 1.0; S.x[tid] = 0.0; S.xp[tid] = 0.0; S.xt[tid] = 0.0; S.rhs[tid] = 0.0; S.tn[tid] = 0.0; }
+  if (tid < kVec) { S.D[tid] = 1.0; S.x[tid] = 0.0; S.xp[tid] = 0.0; S.xt[tid] = 0.0; S.rhs[tid] = 0.0; S.tn[tid] = 0.0; S.rd[tid] = 0.0; }
   __syncthreads();
   // column index: entries of column j in ascending row order
   if (tid == 0) csc_ptr[0] = 0;
@@ -500,14 +676,32 @@ __global__ void __launch_bounds__(kT, 1) k_qp_admm(QpDev Dv, QpParams P, const d
     S.tn[tid] = cnt;
   }
   __syncthreads();
-  if (tid == 0) { int run = 0; for (int j = 0; j < n; j++) { run += static_cast<int>(S.tn[j]); csc_ptr[j + 1] = run; } }
-  __syncthreads();
-  if (tid < n) {
-    int w = csc_ptr[tid];
-    for (int r = 0; r < m; r++)
-      for (int k = 0; k < kEll; k++) if (ell_col[r * kEll + k] == tid) csc_idx[w++] = r * kEll + k;
+  if (tid == 0) {
+    int run = 0, prun = 0;
+    for (int j = 0; j < n; j++) {
+      const int len = static_cast<int>(S.tn[j]);
+      while ((prun & 15) != ((2 * j) & 15)) prun++;
+      S.cptr[j] = static_cast<unsigned short>(prun);
+      S.clen[j] = static_cast<unsigned short>(len);
+      prun += len;
+      run += len;
+      csc_ptr[j + 1] = run;
+    }
+    S.pc_len = prun;
+    if (run != nnz || prun > nnz + 16 * n) S.fail = 2;
   }
   __syncthreads();
+  if (tid < n) {
+    int w = csc_ptr[tid], pw = S.cptr[tid];
+    for (int r = 0; r < m; r++)
+      for (int k = 0; k < kEll; k++)
+        if (ell_col[r * kEll + k] == tid) { dstv[r * kEll + k] = static_cast<unsigned short>(pw++); csc_idx[w++] = r * kEll + k; }
+  }
+  __syncthreads();
+  if (S.fail) {
+    if (tid == 0) { Dv.status[a] = -21; Dv.iters[a] = 0; }
+    return;
+  }
 
   // ---- Ruiz equilibration (osqp scale_data, scaling = 10) ----
   for (int it = 0; it < P.scaling_iters; it++) {
@@ -559,6 +753,7 @@ __global__ void __launch_bounds__(kT, 1) k_qp_admm(QpDev Dv, QpParams P, const d
     for (int e = tid; e < M * 225; e += kT) Pblk[e] *= ct;
     __syncthreads();
   }
+  if (tid < kVec) { S.rhs[tid] = 0.0; S.tn[tid] = 0.0; }   // scratch use above; pads must be zero
   // scaled bounds and constraint types (set_rho_vec)
   for (int r = tid; r < m; r += kT) {
     lov[r] *= E[r];
@@ -569,21 +764,35 @@ __global__ void __launch_bounds__(kT, 1) k_qp_admm(QpDev Dv, QpParams P, const d
     else ty = 0;
     type[r] = ty;
   }
-  // column lists of the structured rows (they lead every column's ascending-row list)
-  if (tid < n) {
-    int cnt = 0;
-    for (int q = csc_ptr[tid]; q < csc_ptr[tid + 1] && csc_idx[q] < ms * kEll; q++) cnt++;
-    S.tn[tid] = cnt;
+  __syncthreads();
+
+  // ---- register tile of L^-1 (n <= 150) ----
+  TileId ti;
+  ti.NB = (n + 5) / 6;
+  ti.NBp = ((ti.NB + 1) & ~1) | 2;   // even, = 2 (mod 4): row stride is an odd number of 16-byte units
+  if (ti.NBp < ti.NB) ti.NBp += 4;
+  constexpr bool tiles = TILES;
+  ti.rb = 0; ti.cb = 0;
+  {
+    int rb = static_cast<int>((sqrtf(8.0f * tid + 1.0f) - 1.0f) * 0.5f);
+    while ((rb + 1) * (rb + 2) / 2 <= tid) rb++;
+    while (rb * (rb + 1) / 2 > tid) rb--;
+    ti.rb = rb; ti.cb = tid - rb * (rb + 1) / 2;
   }
-  __syncthreads();
-  if (tid == 0) { int run = 0; S.cptr[0] = 0; for (int j = 0; j < n; j++) { run += static_cast<int>(S.tn[j]); S.cptr[j + 1] = static_cast<unsigned short>(run); } }
-  __syncthreads();
-  if (tid < n) {
-    int w = S.cptr[tid];
-    for (int q = csc_ptr[tid]; q < csc_ptr[tid + 1] && csc_idx[q] < ms * kEll; q++) cidx[w++] = static_cast<unsigned short>(csc_idx[q]);
-  }
-  __syncthreads();
-  factorize(S, Linv, type, ell_col, ell_val, csc_ptr, csc_idx, Pblk, Kb);
+  ti.act = tiles && ti.rb < ti.NB;
+  double T[TILES ? 36 : 1];
+#pragma unroll
+  for (int k = 0; k < (TILES ? 36 : 1); k++) T[k] = 0.0;
+  auto refactor = [&]() {
+    const long long c0k = clock64();
+    factorize<TILES>(S, Linv, T, ti, Kb, type, ell_col, ell_val, csc_ptr, csc_idx, Pblk);
+    if constexpr (TILES) {   // the staging area becomes the partial-sum buffers: zero outside the tiles
+      for (int e = tid; e < linv_len; e += kT) Linv[e] = 0.0;
+      __syncthreads();
+    }
+    clk_fact += clock64() - c0k; n_fact++;
+  };
+  refactor();
   if (S.fail) {
     if (tid == 0) { Dv.status[a] = -7; Dv.iters[a] = 0; }
     return;
@@ -591,37 +800,54 @@ __global__ void __launch_bounds__(kT, 1) k_qp_admm(QpDev Dv, QpParams P, const d
   const double cinv = 1.0 / S.c_scale;
 
   // ---- per-thread row state in registers ----
-  // slot 0 (row tid): structured or safety, 6 coefficients with packed 8-bit columns
-  double v0[kEll], z0 = 0, y0 = 0, lo0 = 0, up0 = 0;
+  // slot 0 (row tid): structured or safety, 6 coefficients with packed 8-bit columns and 16-bit
+  // product slots; unused slots point at the scratch entry pc[nnz] with zero coefficients
+  double v0[kEll], z0 = 0, y0 = 0, lo0 = -OSQP_INFTY, up0 = OSQP_INFTY;
   unsigned long long c0 = 0;
+  unsigned d0[3];
   int ty0 = 0;
-  const bool has0 = tid < m, struct0 = tid < ms;
+  const bool has0 = tid < m;
+  {
+    unsigned short ds[kEll];
 #pragma unroll
-  for (int k = 0; k < kEll; k++) v0[k] = 0.0;
-  if (has0) {
+    for (int k = 0; k < kEll; k++) { v0[k] = 0.0; ds[k] = static_cast<unsigned short>(S.pc_len); }
+    if (has0) {
 #pragma unroll
-    for (int k = 0; k < kEll; k++) {
-      const int c = ell_col[tid * kEll + k];
-      if (c >= 0) { v0[k] = ell_val[tid * kEll + k]; c0 |= static_cast<unsigned long long>(c) << (8 * k); }
+      for (int k = 0; k < kEll; k++) {
+        const int c = ell_col[tid * kEll + k];
+        if (c >= 0) {
+          v0[k] = ell_val[tid * kEll + k];
+          c0 |= static_cast<unsigned long long>(c) << (8 * k);
+          ds[k] = dstv[tid * kEll + k];
+        }
+      }
+      lo0 = lov[tid]; up0 = upv[tid]; ty0 = type[tid];
     }
-    lo0 = lov[tid]; up0 = upv[tid]; ty0 = type[tid];
+#pragma unroll
+    for (int k = 0; k < 3; k++) d0[k] = ds[2 * k] | (static_cast<unsigned>(ds[2 * k + 1]) << 16);
   }
   // slots 1.. (rows s*kT + tid): safety rows only — 3 coefficients on consecutive columns, lower
   // bound -OSQP_INFTY*E (never active), type 0
   double vs[kSlots - 1][3], zs[kSlots - 1], ys[kSlots - 1], ups[kSlots - 1];
   int bs[kSlots - 1];
+  unsigned long long dss[kSlots - 1];
 #pragma unroll
   for (int s = 0; s < kSlots - 1; s++) {
     const int r = (s + 1) * kT + tid;
-    zs[s] = ys[s] = 0.0; ups[s] = 0.0; bs[s] = 0;
+    zs[s] = ys[s] = 0.0; ups[s] = OSQP_INFTY; bs[s] = 0;
     vs[s][0] = vs[s][1] = vs[s][2] = 0.0;
+    dss[s] = static_cast<unsigned long long>(S.pc_len) * 0x000100010001ull;
     if (r < m) {
       bs[s] = ell_col[r * kEll];
       vs[s][0] = ell_val[r * kEll]; vs[s][1] = ell_val[r * kEll + 1]; vs[s][2] = ell_val[r * kEll + 2];
       ups[s] = upv[r];
+      dss[s] = static_cast<unsigned long long>(dstv[r * kEll]) | (static_cast<unsigned long long>(dstv[r * kEll + 1]) << 16) |
+               (static_cast<unsigned long long>(dstv[r * kEll + 2]) << 32);
     }
   }
 #define COL0(k) static_cast<int>((c0 >> (8 * (k))) & 0xffull)
+#define DST0(k) static_cast<int>((d0[(k) >> 1] >> (16 * ((k) & 1))) & 0xffffu)
+#define DSTS(s, k) static_cast<int>((dss[s] >> (16 * (k))) & 0xffffull)
   auto dot0 = [&](const double* x) {
     double s = 0;
 #pragma unroll
@@ -631,32 +857,27 @@ __global__ void __launch_bounds__(kT, 1) k_qp_admm(QpDev Dv, QpParams P, const d
   auto dots = [&](int s, const double* x) {
     return (vs[s][0] * x[bs[s]] + vs[s][1] * x[bs[s] + 1]) + vs[s][2] * x[bs[s] + 2];
   };
-  // leave u-weighted coefficients in pst/psf for gather_col; sel: 0 → w = rho z - y, 1 → y, 2 → dy
+  auto put0 = [&](double u) {
+#pragma unroll
+    for (int k = 0; k < kEll; k++) pc[DST0(k)] = v0[k] * u;
+  };
+  auto puts = [&](int s, double u) {
+#pragma unroll
+    for (int k = 0; k < 3; k++) pc[DSTS(s, k)] = vs[s][k] * u;
+  };
+  // leave u-weighted coefficients in pc for gather_col; sel: 0 → w = rho z - y, 1 → y, 2 → dy
   auto write_p = [&](int sel, const double (&dy)[kSlots]) {
-    if (has0) {
-      const double u = sel == 0 ? S.rho_v[ty0 + 1] * z0 - y0 : (sel == 1 ? y0 : dy[0]);
-      if (struct0) {
+    put0(sel == 0 ? S.rho_v[ty0 + 1] * z0 - y0 : (sel == 1 ? y0 : dy[0]));
 #pragma unroll
-        for (int k = 0; k < kEll; k++) pst[tid * kEll + k] = v0[k] * u;
-      } else {
-#pragma unroll
-        for (int k = 0; k < 3; k++) psf[(tid - ms) * 3 + k] = v0[k] * u;
-      }
-    }
-#pragma unroll
-    for (int s = 0; s < kSlots - 1; s++) {
-      const int r = (s + 1) * kT + tid;
-      if (r < m) {
-        const double u = sel == 0 ? S.rho_v[1] * zs[s] - ys[s] : (sel == 1 ? ys[s] : dy[s + 1]);
-#pragma unroll
-        for (int k = 0; k < 3; k++) psf[(r - ms) * 3 + k] = vs[s][k] * u;
-      }
-    }
+    for (int s = 0; s < kSlots - 1; s++)
+      if ((s + 1) * kT < m) puts(s, sel == 0 ? S.rho_v[1] * zs[s] - ys[s] : (sel == 1 ? ys[s] : dy[s + 1]));
   };
 
-  const int G = 4 * n <= kT ? 4 : 2;          // lanes per column in gather_col
-  const int gc = G == 4 ? tid >> 2 : tid >> 1;  // this thread's gather column
-  const bool gl0 = (tid & (G - 1)) == 0 && gc < n;
+  const int gc = tid >> 1;                    // this thread's gather column
+  const bool gl0 = (tid & 1) == 0 && gc < n;
+  // entries cptr[gc] + lane, +2, ... of the column: first entry and count of this lane
+  const double* gq = pc + (gc < n ? S.cptr[gc] + (tid & 1) : 0);
+  const int gcnt = gc < n ? (S.clen[gc] + 1 - (tid & 1)) >> 1 : 0;
 
   // ---- ADMM ----
   int iter, status = 0;
@@ -665,7 +886,7 @@ __global__ void __launch_bounds__(kT, 1) k_qp_admm(QpDev Dv, QpParams P, const d
   double nz = 0, nAx = 0, nAty = 0, nPx = 0, rp_scaled = 0, rd_scaled = 0, nz_un = 0, nd_un = 0;
 
   // residuals + norms needed by check_termination / compute_rho_estimate (all threads get them).
-  // Leaves val*y in pst/psf: the caller restores val*w before the next iteration.
+  // Leaves val*y in pc: the caller restores val*w before the next iteration.
   auto update_info = [&](const double (&dy)[kSlots]) {
     double mx[kRedN];
 #pragma unroll
@@ -686,7 +907,7 @@ __global__ void __launch_bounds__(kT, 1) k_qp_admm(QpDev Dv, QpParams P, const d
       if ((s + 1) * kT + tid < m) row_norms(dots(s, S.x), zs[s], E[(s + 1) * kT + tid]);
     write_p(1, dy);
     __syncthreads();
-    const double aty = gather_col(S, pst, psf, cidx, G);
+    const double aty = gather_col(gq, gcnt);
     if (gl0) {
       const int b = gc / 15, rr = gc % 15;
       double px = 0;
@@ -733,7 +954,7 @@ __global__ void __launch_bounds__(kT, 1) k_qp_admm(QpDev Dv, QpParams P, const d
       __syncthreads();
       write_p(2, dy);
       __syncthreads();
-      const double s = gather_col(S, pst, psf, cidx, G);
+      const double s = gather_col(gq, gcnt);
       const double v = gl0 ? fabs((1.0 / S.D[gc]) * s) : 0.0;
       const double nrm = block_max(v, S.red);
       return nrm < eps * nd;
@@ -756,14 +977,17 @@ __global__ void __launch_bounds__(kT, 1) k_qp_admm(QpDev Dv, QpParams P, const d
   };
 
   {
-    const double dy[kSlots] = {0, 0, 0, 0};
+    const double dy[kSlots] = {0};
     write_p(0, dy);
   }
   __syncthreads();
   auto admm_iter = [&](double (&dy)[kSlots]) {
+#ifdef POP_QP_PHASE_PROF
+    const long long t0 = clock64();
+#endif
     // x_prev <- x ; rhs = sigma x_prev - q + A' w with w = rho z - y
     {
-      const double s = gather_col(S, pst, psf, cidx, G);
+      const double s = gather_col(gq, gcnt);
       if (gl0) {
         const double xv = S.x[gc];
         S.xp[gc] = xv;
@@ -771,48 +995,51 @@ __global__ void __launch_bounds__(kT, 1) k_qp_admm(QpDev Dv, QpParams P, const d
       }
     }
     __syncthreads();
-    kkt_solve(S, Linv);
-    // z, y updates of the rows this thread owns; leave val*w for the next gather
+#ifdef POP_QP_PHASE_PROF
+    const long long t1 = clock64();
+#endif
+    if constexpr (TILES) kkt_tiles(S, T, ti, Linv, Linv + part1_len);
+    else kkt_solve(S, Linv);
+#ifdef POP_QP_PHASE_PROF
+    const long long t2 = clock64();
+#endif
+    // z, y updates of the rows this thread owns (branch-free: unused slots carry zero
+    // coefficients and write to the scratch entry); leave val*w for the next gather
     {
       const double rho_in = S.rho_v[1], rinv_in = S.rinv_v[1];
-      if (has0) {
-        const double zt = dot0(S.xt);
-        const double rho = S.rho_v[ty0 + 1], rinv = S.rinv_v[ty0 + 1];
-        const double mix = ALPHA * zt + (1.0 - ALPHA) * z0;
+      const double rho = S.rho_v[ty0 + 1], rinv = S.rinv_v[ty0 + 1];
+      double zt[kSlots];
+      zt[0] = dot0(S.xt);
+#pragma unroll
+      for (int s = 0; s < kSlots - 1; s++) zt[s + 1] = (s + 1) * kT < m ? dots(s, S.xt) : 0.0;
+      {
+        const double mix = ALPHA * zt[0] + (1.0 - ALPHA) * z0;
         const double v = mix + rinv * y0;
         const double zn = fmin(fmax(v, lo0), up0);
         const double d = rho * (mix - zn);
         z0 = zn; y0 = y0 + d; dy[0] = d;
-        const double w = rho * zn - y0;
-        if (struct0) {
-#pragma unroll
-          for (int k = 0; k < kEll; k++) pst[tid * kEll + k] = v0[k] * w;
-        } else {
-#pragma unroll
-          for (int k = 0; k < 3; k++) psf[(tid - ms) * 3 + k] = v0[k] * w;
-        }
+        put0(rho * zn - y0);
       }
 #pragma unroll
       for (int s = 0; s < kSlots - 1; s++) {
-        const int r = (s + 1) * kT + tid;
-        if (r < m) {
-          const double zt = dots(s, S.xt);
-          const double mix = ALPHA * zt + (1.0 - ALPHA) * zs[s];
-          const double v = mix + rinv_in * ys[s];
-          const double zn = fmin(v, ups[s]);
-          const double d = rho_in * (mix - zn);
-          zs[s] = zn; ys[s] = ys[s] + d; dy[s + 1] = d;
-          const double w = rho_in * zn - ys[s];
-#pragma unroll
-          for (int k = 0; k < 3; k++) psf[(r - ms) * 3 + k] = vs[s][k] * w;
-        }
+        if ((s + 1) * kT >= m) continue;   // uniform: no row of this problem lives in the slot
+        const double mix = ALPHA * zt[s + 1] + (1.0 - ALPHA) * zs[s];
+        const double v = mix + rinv_in * ys[s];
+        const double zn = fmin(v, ups[s]);
+        const double d = rho_in * (mix - zn);
+        zs[s] = zn; ys[s] = ys[s] + d; dy[s + 1] = d;
+        puts(s, rho_in * zn - ys[s]);
       }
     }
     __syncthreads();
+#ifdef POP_QP_PHASE_PROF
+    clk_g += t1 - t0; clk_k += t2 - t1; clk_r += clock64() - t2;
+#endif
   };
   // Hot iterations run in a tight inner loop up to the next event (termination test, rho
   // adaptation, last iteration); only the event iteration keeps its delta_y.
   iter = 0;
+  const long long clk_loop = clock64();
   while (true) {
     int next = P.max_iter;
     if (P.check_interval) next = min(next, (iter / P.check_interval + 1) * P.check_interval);
@@ -821,7 +1048,7 @@ __global__ void __launch_bounds__(kT, 1) k_qp_admm(QpDev Dv, QpParams P, const d
       double scratch[kSlots];
       admm_iter(scratch);
     }
-    double dy[kSlots] = {0, 0, 0, 0};   // delta_y of this iteration (is_primal_infeasible)
+    double dy[kSlots] = {0};   // delta_y of this iteration (is_primal_infeasible)
     admm_iter(dy);
     iter++;
     const bool last = iter >= P.max_iter;
@@ -836,7 +1063,7 @@ __global__ void __launch_bounds__(kT, 1) k_qp_admm(QpDev Dv, QpParams P, const d
         break;
       }
     }
-    bool refactor = false;
+    bool new_rho = false;
     if (P.adaptive_interval && (iter % P.adaptive_interval == 0)) {
       if (!info) { update_info(dy); info = true; }
       double pr = rp_scaled / (fmax(nz, nAx) + 1e-10);
@@ -851,13 +1078,13 @@ __global__ void __launch_bounds__(kT, 1) k_qp_admm(QpDev Dv, QpParams P, const d
           S.rinv_v[1] = 1. / S.rho_v[1]; S.rinv_v[2] = 1. / S.rho_v[2];
         }
         __syncthreads();
-        refactor = true;
+        new_rho = true;
       }
     }
-    if (info) {   // pst/psf hold val*y (or val*dy): restore val*w (with the new rho, if it changed)
+    if (info) {   // pc holds val*y (or val*dy): restore val*w (with the new rho, if it changed)
       __syncthreads();
+      if (new_rho) refactor();
       write_p(0, dy);
-      if (refactor) factorize(S, Linv, type, ell_col, ell_val, csc_ptr, csc_idx, Pblk, Kb);
       __syncthreads();
     }
   }
@@ -866,8 +1093,16 @@ __global__ void __launch_bounds__(kT, 1) k_qp_admm(QpDev Dv, QpParams P, const d
   if (tid == 0) {
     Dv.status[a] = status;
     Dv.iters[a] = iter < P.max_iter ? iter : P.max_iter;
+    const long long now = clock64();
+    Dv.prof[a * 8 + 0] = clk_loop - clk0;   // assembly, scaling, first factorisation, register load
+    Dv.prof[a * 8 + 1] = clk_fact;
+    Dv.prof[a * 8 + 2] = now - clk_loop;
+    Dv.prof[a * 8 + 3] = n_fact;
+    Dv.prof[a * 8 + 4] = clk_g; Dv.prof[a * 8 + 5] = clk_k; Dv.prof[a * 8 + 6] = clk_r;
   }
 #undef COL0
+#undef DST0
+#undef DSTS
 }
 
 }  // namespace
@@ -910,18 +1145,20 @@ int popk_qp_alloc(pop_handle* h, int n_agents) {
   ok &= cudaMalloc(&d->E, na * kMaxRows * sizeof(double)) == cudaSuccess;
   ok &= cudaMalloc(&d->lo, na * kMaxRows * sizeof(double)) == cudaSuccess;
   ok &= cudaMalloc(&d->up, na * kMaxRows * sizeof(double)) == cudaSuccess;
-  ok &= cudaMalloc(&d->Kb, na * kMaxN * kBand * sizeof(double)) == cudaSuccess;
+  ok &= cudaMalloc(&d->dst, na * kMaxRows * kEll * sizeof(unsigned short)) == cudaSuccess;
   ok &= cudaMalloc(&d->QM, 225 * sizeof(double)) == cudaSuccess;
   ok &= cudaMalloc(&d->cpts, na * POP_MAX_PIECES * 15 * sizeof(double)) == cudaSuccess;
   ok &= cudaMalloc(&d->status, na * sizeof(int)) == cudaSuccess;
   ok &= cudaMalloc(&d->iters, na * sizeof(int)) == cudaSuccess;
+  ok &= cudaMalloc(&d->prof, na * 8 * sizeof(long long)) == cudaSuccess;
   if (!ok) { cudaGetLastError(); return pop_fail(h, POP_E_CUDA, "QP workspace allocation failed"); }
   double QM[225];
   host_jerk_block(QM);
   POP_CUDA(h, cudaMemcpyAsync(d->QM, QM, sizeof(QM), cudaMemcpyHostToDevice, h->stream));
   POP_CUDA(h, cudaMemsetAsync(d->cpts, 0, na * POP_MAX_PIECES * 15 * sizeof(double), h->stream));
   POP_CUDA(h, cudaStreamSynchronize(h->stream));
-  POP_CUDA(h, cudaFuncSetAttribute(k_qp_admm, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+  POP_CUDA(h, cudaFuncSetAttribute(k_qp_admm<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTiles));
+  POP_CUDA(h, cudaFuncSetAttribute(k_qp_admm<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
   return POP_OK;
 }
 
@@ -929,7 +1166,7 @@ void popk_qp_free(pop_handle* h) {
   QpDev* d = h->qp;
   if (!d) return;
   void* ptrs[] = {d->n_pieces, d->init, d->goal, d->dur, d->ell_col, d->ell_val, d->csc_ptr, d->csc_idx, d->Pblk,
-                  d->E, d->lo, d->up, d->Kb, d->QM, d->cpts, d->status, d->iters};
+                  d->E, d->lo, d->up, d->dst, d->QM, d->cpts, d->status, d->iters, d->prof};
   for (void* p : ptrs) if (p) cudaFree(p);
   delete d;
   h->qp = nullptr;
@@ -945,9 +1182,11 @@ int popk_qp_run(pop_handle* h, int n_agents, const double* d_hpoly, const int* d
   P.eps_abs = c.osqp_eps_abs; P.eps_rel = c.osqp_eps_rel; P.eps_prim_inf = 1e-4;
   P.vmax = vmax; P.amax = amax;
   pop_prof_begin(h, POP_STAGE_QP);
-  k_qp_admm<<<n_agents, kT, kSmemBytes, h->stream>>>(*d, P, d_hpoly, d_rows);
+  k_qp_admm<true><<<n_agents, kT, kSmemTiles, h->stream>>>(*d, P, d_hpoly, d_rows);
   POP_LAUNCH_CHECK(h);
-  pop_prof_end(h, POP_STAGE_QP, 1);
+  k_qp_admm<false><<<n_agents, kT, kSmemBytes, h->stream>>>(*d, P, d_hpoly, d_rows);
+  POP_LAUNCH_CHECK(h);
+  pop_prof_end(h, POP_STAGE_QP, 2);
   return POP_OK;
 }
 
@@ -994,5 +1233,15 @@ extern "C" int pop_qp_solve_batch(pop_handle* h, int n, const int32_t* n_pieces,
   for (int i = 0; i < n; i++)
     if (out_status[i] == -20)
       return pop_fail(h, POP_E_CAPACITY, "problem %d exceeds the %d-row / shared-memory capacity of the QP kernel", i, kRowCap);
+  return POP_OK;
+}
+
+// Measurement hook: SM cycles the last QP launch spent per problem in {setup, factorisations, ADMM
+// loop} and the number of factorisations; out = n x 8 int64.
+extern "C" int pop_qp_profile(pop_handle* h, int n, int64_t* out) {
+  if (!h || !out || n <= 0) return POP_E_INVALID;
+  if (!h->qp || n > h->qp->cap_agents) return pop_fail(h, POP_E_STATE, "no QP launch to report on");
+  POP_CUDA(h, cudaMemcpyAsync(out, h->qp->prof, sizeof(long long) * 8 * n, cudaMemcpyDeviceToHost, h->stream));
+  POP_CUDA(h, cudaStreamSynchronize(h->stream));
   return POP_OK;
 }

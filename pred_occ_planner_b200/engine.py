@@ -188,6 +188,11 @@ class PopEngine:
         return ({STAGE_NAMES[i]: float(ms[i]) for i in range(6)},
                 {STAGE_NAMES[i]: int(ln[i]) for i in range(6)})
 
+    def qp_profile(self, n: int) -> np.ndarray:
+        out = np.zeros((n, 8), np.int64)
+        self._check(self.lib.pop_qp_profile(self._h, n, as_ptr(out, C.c_int64)))
+        return out
+
     def kernel_launches(self) -> int:
         return int(self.lib.pop_kernel_launches(self._h))
 

@@ -27,3 +27,11 @@ eng.profile_enable(True)
 cpts, status, iters = eng.qp_solve_batch(npoly, start, fin, dur, hp, rows, cfg.opt_max_vel, cfg.opt_max_acc)
 ms, _ = eng.profile_read(True)
 print("qp status", {int(s): int((status == s).sum()) for s in np.unique(status)}, "iters", np.sort(iters), "ms", ms["qp"])
+prof = eng.qp_profile(n)
+order = np.argsort(iters)
+print("qp cycles per agent: iters | setup | factor total | loop | nfact | loop/iter | gather/it kkt/it rows/it")
+for a in order[-10:]:
+    it = max(1, int(iters[a]))
+    print(int(iters[a]), int(prof[a, 0]), int(prof[a, 1]), int(prof[a, 2]), int(prof[a, 3]), int(prof[a, 2] / it),
+          int(prof[a, 4] / it), int(prof[a, 5] / it), int(prof[a, 6] / it))
+print("median setup", np.median(prof[:, 0]), "median cycles per factorisation", np.median(prof[:, 1] / np.maximum(prof[:, 3], 1)))

@@ -27,7 +27,7 @@ def test_reference_fixture(oracle):
     dur[:3] = FIX_T
     cpts, status, iters = eng.qp_solve_batch([3], [FIX_START], [FIX_END], [dur], [hp], [rows], 3.0, 3.0)
     st, X, it = oracle.qp_solve(cfg, FIX_START, FIX_END, FIX_T, FIX_POLYS)
-    assert status[0] == st == 1
+    assert status[0] == st and st in (1, 2)   # optimize() == true (bezier_optimizer.cpp:279)
     assert iters[0] == it
     assert _close(cpts[0, :15], X)
     # the reference's assertions on the solution (boundary conditions within 1e-3)

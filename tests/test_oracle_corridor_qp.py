@@ -5,6 +5,9 @@ traj_opt/test/test_bezier_opt.cpp:47-221 (matrix shapes, solved status, boundary
 1e-3, C1/C2 continuity) and the separable 4-vs-5 point instance of
 utils/separator/src/test_separator.cpp:20-32.  LP/FIRI have no reference tests: checked against
 scipy's HiGHS and through geometric invariants."""
+import json
+import os
+
 import numpy as np
 import pytest
 
@@ -16,10 +19,13 @@ def _cube(lo, hi):
     return [[-1, 0, 0, lo], [1, 0, 0, -hi], [0, -1, 0, lo], [0, 1, 0, -hi], [0, 0, -1, lo], [0, 0, 1, -hi]]
 
 
-FIX_POLYS = [_cube(0, 3), _cube(2, 6), _cube(5, 9)]
-FIX_START = [1, 0, 1, 0, 0, 0, 0, 0, 0]
-FIX_END = [8, 9, 8, 0.5, 1, 0, 0, 0, 0]
-FIX_T = [2.0, 4.0, 2.0]
+# the reference's own QP fixture (traj_opt/test/test_bezier_opt.cpp:59-99), parsed from its source
+# into tests/golden/reference_kats.json by scripts/make_golden.py
+_KAT = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_kats.json")))["bezier_opt"]
+FIX_POLYS = _KAT["polys"]
+FIX_START = _KAT["start"]
+FIX_END = _KAT["end"]
+FIX_T = _KAT["t"]
 
 
 def test_lp_matches_highs(oracle):

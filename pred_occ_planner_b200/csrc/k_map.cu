@@ -317,6 +317,264 @@ __global__ void k_download(PopGeom g, const uint8_t* __restrict__ ag, float* __r
 // =============================================================================================
 // launchers
 // =============================================================================================
+// =============================================================================================
+// K1f (tiled)  u8 grids whose z-layer (nx*ny bytes) fits in shared memory.
+//
+// Every SOGM byte is written exactly once, by a TMA bulk store of a finished tile; nothing is
+// read back and no partial-sector read-modify-write reaches L2/HBM:
+//   1. k_vox_count / k_vox_scan / k_vox_fill: counting sort of the cloud points of every agent
+//      by destination z-layer — one list for slice 0 (voxel of pt - pose) and one for the future
+//      slices (voxel corner + owner cylinder id; the z of pt + v*dt*k - pose does not depend on
+//      k because vz = 0, but is recomputed in fp32 exactly as the reference does, so it may differ
+//      from the slice-0 layer by rounding and gets its own list);
+//   2. k_vox_tiles: persistent CTAs walk the (agent, slice, z-layer) units; a unit zeroes its
+//      nx*ny-byte tile in shared memory, scatters the layer's entries displaced by v*dt*k
+//      (same fp32 operation order as fake_particle_risk_voxel.cpp:127-162), and hands the tile
+//      to cp.async.bulk (shared → global).  Two CTAs per SM alternate between building and draining.
+// Duplicate points in a voxel are idempotent stores of 1, so the per-voxel compaction of the
+// scatter path is not needed.  Algorithmic bytes: V*T written once + N_pts*12 read per agent.
+// =============================================================================================
+struct VoxDev {
+  int cap = 0, nl = 0, nz = 0;
+  int* cnt = nullptr;            // [agent][2][nz]   entries per layer (list 0: slice 0, list 1: future)
+  int* off = nullptr;            // [agent][2][nz+1] exclusive prefix
+  int* cur = nullptr;            // [agent][2][nz]   fill cursors
+  unsigned* ent0 = nullptr;      // [agent][cap]     iy*nx + ix of the slice-0 voxel
+  unsigned long long* entf = nullptr;  // [agent][cap] ix | iy<<16 | owner<<32 (owner 0xffff: static)
+};
+
+// slice-0 voxel of a cloud point as the reference computes it, or false
+__device__ __forceinline__ bool vox_point(const PopGeom& g, const float* __restrict__ cloud, int i, float posex,
+                                          float posey, float posez, int* ix, int* iy, int* iz) {
+  const float px = cloud[3 * i], py = cloud[3 * i + 1], pz = cloud[3 * i + 2];
+  if (!isfinite(px) || !isfinite(py) || !isfinite(pz)) return false;
+  if (px < __fsub_rn(posex, g.rx) || px > __fadd_rn(posex, g.rx)) return false;
+  if (py < __fsub_rn(posey, g.ry) || py > __fadd_rn(posey, g.ry)) return false;
+  if (pz < __fsub_rn(posez, g.rz) || pz > __fadd_rn(posez, g.rz)) return false;
+  const float x = __fsub_rn(px, posex), y = __fsub_rn(py, posey), z = __fsub_rn(pz, posez);
+  if (!geom_in_range_f(g, x, y, z)) return false;
+  *ix = geom_axis_index(x, g.rx, g.res);
+  *iy = geom_axis_index(y, g.ry, g.res);
+  *iz = geom_axis_index(z, g.rz, g.res);
+  return geom_in_range_i(g, *ix, *iy, *iz);
+}
+// z-layer of the future slices of the voxel in layer iz: voxel of (corner_z + 0*dt*k) - pose_z
+__device__ __forceinline__ int vox_future_layer(const PopGeom& g, int iz, float posez) {
+  const float ptz = geom_axis_position(iz, g.rz, g.res, posez);
+  const float qz = __fsub_rn(__fadd_rn(ptz, __fmul_rn(__fmul_rn(0.0f, g.dt), 1.0f)), posez);
+  if (!(qz > -g.rz && qz < g.rz)) return -1;
+  const int l = geom_axis_index(qz, g.rz, g.res);
+  return (l >= 0 && l < g.nz) ? l : -1;
+}
+
+__global__ void __launch_bounds__(256) k_vox_count(PopGeom g, const float* __restrict__ cloud, int n_cloud,
+                                                   const float* __restrict__ poses, int* __restrict__ cnt) {
+  const int a = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_cloud) return;
+  const float posez = poses[3 * a + 2];
+  int ix, iy, iz;
+  if (!vox_point(g, cloud, i, poses[3 * a], poses[3 * a + 1], posez, &ix, &iy, &iz)) return;
+  atomicAdd(&cnt[(a * 2 + 0) * g.nz + iz], 1);
+  if (1.0f > g.risk_threshold) {   // tmp[i][0] > risk_threshold_ (fake_particle_risk_voxel.cpp:121)
+    const int lf = vox_future_layer(g, iz, posez);
+    if (lf >= 0) atomicAdd(&cnt[(a * 2 + 1) * g.nz + lf], 1);
+  }
+}
+
+__global__ void k_vox_scan(int n_lists, int nz, int cap, const int* __restrict__ cnt, int* __restrict__ off,
+                           int* __restrict__ cur) {
+  // one thread per (agent, list): nz <= a few hundred
+  const int l = blockIdx.x * blockDim.x + threadIdx.x;
+  if (l >= n_lists) return;
+  int run = 0;
+  for (int z = 0; z < nz; z++) {
+    off[l * (nz + 1) + z] = run;
+    cur[l * nz + z] = 0;
+    run += cnt[l * nz + z];
+  }
+  off[l * (nz + 1) + nz] = run < cap ? run : cap;
+}
+
+__global__ void __launch_bounds__(256) k_vox_fill(PopGeom g, const float* __restrict__ cloud, int n_cloud,
+                                                  const float* __restrict__ poses,
+                                                  const PopCylDev* __restrict__ cyl, int n_cyl,
+                                                  const int* __restrict__ off, int* __restrict__ cur,
+                                                  unsigned* __restrict__ ent0,
+                                                  unsigned long long* __restrict__ entf, int cap) {
+  extern __shared__ PopCylDev scyl[];
+  for (int c = threadIdx.x; c < n_cyl; c += blockDim.x) scyl[c] = cyl[c];
+  __syncthreads();
+  const int a = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_cloud) return;
+  const float posex = poses[3 * a], posey = poses[3 * a + 1], posez = poses[3 * a + 2];
+  int ix, iy, iz;
+  if (!vox_point(g, cloud, i, posex, posey, posez, &ix, &iy, &iz)) return;
+  {
+    const int l = a * 2 + 0;
+    const int pos = off[l * (g.nz + 1) + iz] + atomicAdd(&cur[l * g.nz + iz], 1);
+    if (pos < cap) ent0[static_cast<size_t>(a) * cap + pos] = static_cast<unsigned>(iy * g.nx + ix);
+  }
+  if (!(1.0f > g.risk_threshold)) return;
+  const int lf = vox_future_layer(g, iz, posez);
+  if (lf < 0) return;
+  // owner: first type-3 cylinder with |corner - axis| <= w + clearance (compared in double)
+  const float ptx = geom_axis_position(ix, g.rx, g.res, posex);
+  const float pty = geom_axis_position(iy, g.ry, g.res, posey);
+  const float ptz = geom_axis_position(iz, g.rz, g.res, posez);
+  unsigned owner = 0xffffu;
+  for (int c = 0; c < n_cyl; c++) {
+    if (scyl[c].type != 3) continue;
+    const float dx = __fsub_rn(ptx, scyl[c].x), dy = __fsub_rn(pty, scyl[c].y);
+    const float dz = __fsub_rn(ptz, ptz);
+    const float dist = __fsqrt_rn(
+        __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
+    if (static_cast<double>(dist) <= __dadd_rn(scyl[c].w, static_cast<double>(g.clearance))) {
+      owner = static_cast<unsigned>(c);
+      break;
+    }
+  }
+  const int l = a * 2 + 1;
+  const int pos = off[l * (g.nz + 1) + lf] + atomicAdd(&cur[l * g.nz + lf], 1);
+  if (pos < cap)
+    entf[static_cast<size_t>(a) * cap + pos] = static_cast<unsigned long long>(ix) |
+                                               (static_cast<unsigned long long>(iy) << 16) |
+                                               (static_cast<unsigned long long>(owner) << 32);
+}
+
+constexpr int kTileThreads = 256;
+constexpr int kTileChunk = 32 * 1024;   // bytes per bulk store
+
+__global__ void __launch_bounds__(kTileThreads, 2) k_vox_tiles(PopGeom g, uint8_t* __restrict__ grid, int n_agents,
+                                                               const float* __restrict__ poses,
+                                                               const PopCylDev* __restrict__ cyl, int n_cyl,
+                                                               const int* __restrict__ off,
+                                                               const unsigned* __restrict__ ent0,
+                                                               const unsigned long long* __restrict__ entf,
+                                                               int cap) {
+  extern __shared__ __align__(128) uint8_t tile[];
+  const int layer = g.nx * g.ny;                      // bytes, multiple of 16
+  float2* svel = reinterpret_cast<float2*>(tile + ((layer + 127) & ~127));   // cylinder velocities
+  for (int c = threadIdx.x; c < n_cyl; c += blockDim.x) svel[c] = make_float2(cyl[c].vx, cyl[c].vy);
+  const unsigned smem = static_cast<unsigned>(__cvta_generic_to_shared(tile));
+  const long long units = static_cast<long long>(n_agents) * g.nt * g.nz;
+  for (long long u = blockIdx.x; u < units; u += gridDim.x) {
+    const int iz = static_cast<int>(u % g.nz);
+    const int k = static_cast<int>((u / g.nz) % g.nt);
+    const int a = static_cast<int>(u / (static_cast<long long>(g.nz) * g.nt));
+    // the previous unit's bulk stores must have finished READING the tile before it is rebuilt
+    if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    __syncthreads();
+    for (int i = threadIdx.x * 16; i < layer; i += kTileThreads * 16)
+      *reinterpret_cast<uint4*>(tile + i) = make_uint4(0, 0, 0, 0);
+    __syncthreads();
+    const int list = k == 0 ? 0 : 1;
+    const int* o = off + (a * 2 + list) * (g.nz + 1);
+    const int e0 = o[iz], e1 = o[iz + 1];
+    if (k == 0) {
+      const unsigned* e = ent0 + static_cast<size_t>(a) * cap;
+      for (int q = e0 + threadIdx.x; q < e1; q += kTileThreads) tile[e[q]] = 1;
+    } else {
+      const unsigned long long* e = entf + static_cast<size_t>(a) * cap;
+      const float posex = poses[3 * a], posey = poses[3 * a + 1];
+      const float kf = static_cast<float>(k);
+      for (int q = e0 + threadIdx.x; q < e1; q += kTileThreads) {
+        const unsigned long long v = e[q];
+        const int ix = static_cast<int>(v & 0xffffu), iy = static_cast<int>((v >> 16) & 0xffffu);
+        const unsigned owner = static_cast<unsigned>(v >> 32) & 0xffffu;
+        float vx = 0.f, vy = 0.f;
+        if (owner != 0xffffu) { const float2 w = svel[owner]; vx = w.x; vy = w.y; }
+        const float ptx = geom_axis_position(ix, g.rx, g.res, posex);
+        const float pty = geom_axis_position(iy, g.ry, g.res, posey);
+        const float qx = __fsub_rn(__fadd_rn(ptx, __fmul_rn(__fmul_rn(vx, g.dt), kf)), posex);
+        const float qy = __fsub_rn(__fadd_rn(pty, __fmul_rn(__fmul_rn(vy, g.dt), kf)), posey);
+        if (!(qx > -g.rx && qx < g.rx && qy > -g.ry && qy < g.ry)) continue;
+        const int jx = geom_axis_index(qx, g.rx, g.res), jy = geom_axis_index(qy, g.ry, g.res);
+        if (jx < 0 || jx >= g.nx || jy < 0 || jy >= g.ny) continue;
+        tile[jy * g.nx + jx] = 1;
+      }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      uint8_t* dst = grid + a * g.agent_stride + (static_cast<size_t>(k) * g.nz + iz) * layer;
+      for (int b = 0; b < layer; b += kTileChunk) {
+        const unsigned n = layer - b < kTileChunk ? layer - b : kTileChunk;
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst + b),
+                     "r"(smem + b), "r"(n)
+                     : "memory");
+      }
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+  }
+  if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
+void popk_vox_free(pop_handle* h) {
+  VoxDev* d = h->vox;
+  if (!d) return;
+  void* ptrs[] = {d->cnt, d->off, d->cur, d->ent0, d->entf};
+  for (void* p : ptrs) if (p) cudaFree(p);
+  delete d;
+  h->vox = nullptr;
+}
+
+// the tiled path applies to u8 grids whose layer fits in shared memory next to a second CTA
+static bool vox_tiles_ok(const pop_handle* h) {
+  const PopGeom& g = h->geom;
+  const char* e = getenv("POP_VOXEL_MODE");   // "tiles" (default) | "scatter"
+  if (e && e[0] == 's') return false;
+  const int layer = g.nx * g.ny;
+  return h->cfg.cell_dtype == POP_CELL_U8 && layer % 16 == 0 && layer <= 110 * 1024 && g.nx < 65536 &&
+         g.ny < 65536 && h->cfg.max_cylinders < 0xffff;
+}
+
+static int vox_update_tiles(pop_handle* h, int sms, int* launches) {
+  const PopGeom& g = h->geom;
+  const int nl = h->cfg.n_agents_local, cap = h->cfg.max_cloud_points;
+  if (!h->vox) {
+    VoxDev* d = new VoxDev();
+    h->vox = d;
+    d->cap = cap; d->nl = nl; d->nz = g.nz;
+    bool ok = true;
+    ok &= cudaMalloc(&d->cnt, sizeof(int) * nl * 2 * g.nz) == cudaSuccess;
+    ok &= cudaMalloc(&d->off, sizeof(int) * nl * 2 * (g.nz + 1)) == cudaSuccess;
+    ok &= cudaMalloc(&d->cur, sizeof(int) * nl * 2 * g.nz) == cudaSuccess;
+    ok &= cudaMalloc(&d->ent0, sizeof(unsigned) * static_cast<size_t>(nl) * cap) == cudaSuccess;
+    ok &= cudaMalloc(&d->entf, sizeof(unsigned long long) * static_cast<size_t>(nl) * cap) == cudaSuccess;
+    if (!ok) { cudaGetLastError(); return pop_fail(h, POP_E_CUDA, "voxel-update entry lists allocation failed"); }
+    const int layer = g.nx * g.ny;
+    const int smem = ((layer + 127) & ~127) + static_cast<int>(sizeof(float2)) * (h->cfg.max_cylinders + 1);
+    POP_CUDA(h, cudaFuncSetAttribute(k_vox_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  }
+  VoxDev* d = h->vox;
+  const int layer = g.nx * g.ny;
+  const int smem = ((layer + 127) & ~127) + static_cast<int>(sizeof(float2)) * (h->cfg.max_cylinders + 1);
+  POP_CUDA(h, cudaMemsetAsync(d->cnt, 0, sizeof(int) * nl * 2 * g.nz, h->stream));
+  if (h->n_cloud > 0) {
+    dim3 grid((h->n_cloud + 255) / 256, nl);
+    k_vox_count<<<grid, 256, 0, h->stream>>>(g, h->d_cloud, h->n_cloud, h->d_poses, d->cnt);
+    POP_LAUNCH_CHECK(h);
+    (*launches)++;
+  }
+  k_vox_scan<<<(nl * 2 + 63) / 64, 64, 0, h->stream>>>(nl * 2, g.nz, cap, d->cnt, d->off, d->cur);
+  POP_LAUNCH_CHECK(h);
+  (*launches)++;
+  if (h->n_cloud > 0) {
+    dim3 grid((h->n_cloud + 255) / 256, nl);
+    const size_t sm = sizeof(PopCylDev) * (h->n_cyl > 0 ? h->n_cyl : 1);
+    k_vox_fill<<<grid, 256, sm, h->stream>>>(g, h->d_cloud, h->n_cloud, h->d_poses, h->d_cyl, h->n_cyl, d->off,
+                                             d->cur, d->ent0, d->entf, cap);
+    POP_LAUNCH_CHECK(h);
+    (*launches)++;
+  }
+  const int ctas = smem <= 110 * 1024 ? 2 * sms : sms;
+  k_vox_tiles<<<ctas, kTileThreads, smem, h->stream>>>(g, h->d_grid, nl, h->d_poses, h->d_cyl, h->n_cyl, d->off,
+                                                       d->ent0, d->entf, cap);
+  POP_LAUNCH_CHECK(h);
+  (*launches)++;
+  return POP_OK;
+}
+
 static int clear_mode() {
   static int mode = -1;
   if (mode < 0) {
@@ -336,6 +594,12 @@ int popk_voxel_update(pop_handle* h) {
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
   pop_prof_begin(h, POP_STAGE_VOXEL_UPDATE);
   int launches = 0;
+  if (vox_tiles_ok(h)) {
+    const int rc = vox_update_tiles(h, sms, &launches);
+    if (rc) return rc;
+    pop_prof_end(h, POP_STAGE_VOXEL_UPDATE, launches);
+    return POP_OK;
+  }
   POP_CUDA(h, cudaMemsetAsync(h->d_occ_count, 0, sizeof(int) * nl, h->stream));
   const int mode = clear_mode();
   if (mode == 0) {

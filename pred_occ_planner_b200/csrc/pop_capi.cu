@@ -190,6 +190,7 @@ int pop_destroy(pop_handle* h) {
   if (!h) return POP_OK;
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
+  popk_vox_free(h);
   void* ptrs[] = {h->d_grid, h->d_cloud, h->d_cyl, h->d_poses, h->d_occ_list, h->d_occ_count, h->d_body,
                   h->d_body_count, h->d_traj_all, h->d_traj_send, h->d_peer_pos, h->d_peer_valid,
                   h->d_scratch};

@@ -38,6 +38,7 @@ struct PopProfile {
   std::vector<cudaEvent_t> pool;
 };
 
+struct VoxDev;     // k_map.cu: per-layer entry lists of the tiled voxel update
 struct AstarDev;   // k_astar.cu
 struct CorridorDev;  // k_corridor.cu
 struct QpDev;      // k_qp.cu
@@ -75,6 +76,7 @@ struct pop_handle {
   void* h_pinned = nullptr; size_t h_pinned_bytes = 0;
   void* d_scratch = nullptr; size_t d_scratch_bytes = 0;
 
+  VoxDev* vox = nullptr;
   AstarDev* astar = nullptr;
   CorridorDev* corridor = nullptr;
   QpDev* qp = nullptr;
@@ -100,6 +102,7 @@ void pop_prof_end(pop_handle* h, int stage, int n_launches);
 
 // map stage launchers (k_map.cu) ---------------------------------------------------------------
 int popk_voxel_update(pop_handle* h);        // clear + slice 0 + future slices (K1f)
+void popk_vox_free(pop_handle* h);
 int popk_peer_project(pop_handle* h);        // peer trajectories → particles → grid (K5)
 int popk_query(pop_handle* h, int agent, const double* d_pos, const int32_t* d_t,
                const double* d_dt, int n, int8_t* d_out);

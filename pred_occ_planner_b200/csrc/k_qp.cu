@@ -336,6 +336,10 @@ __device__ void factorize(Smem& S, double* __restrict__ Linv, double (&T)[NT], c
     double w[15];   // w[k] = x_{r-1-k}
 #pragma unroll
     for (int k = 0; k < 15; k++) w[k] = 0.0;
+    if constexpr (TILES) {
+#pragma unroll
+      for (int k = 0; k < NT; k++) T[k] = 0.0;
+    }
     const int r_end = TILES ? nst : n;
     for (int r = 0; r < r_end; r++) {
       double xr = 0.0;
@@ -353,14 +357,24 @@ __device__ void factorize(Smem& S, double* __restrict__ Linv, double (&T)[NT], c
       for (int k = 14; k > 0; k--) w[k] = w[k - 1];
       w[0] = xr;
       if constexpr (TILES) {
+        // K^-1 = L^-T L^-1 = sum over rows r of (row r of L^-1)' (row r of L^-1): every staged block
+        // of 6 rows adds its outer products to the register tile (rb, cb) it reaches (6b >= 6rb)
         if (c < nst) Linv[(r % 6) * nst + c] = xr;
         if (r % 6 == 5) {
           __syncthreads();
-          if (ti.act && ti.rb == r / 6) {
+          if (ti.act && ti.rb <= r / 6) {
 #pragma unroll
-            for (int rr = 0; rr < 6; rr++)
+            for (int rr = 0; rr < 6; rr++) {
+              const double2* pa = reinterpret_cast<const double2*>(Linv + rr * nst + 6 * ti.rb);
+              const double2* pb = reinterpret_cast<const double2*>(Linv + rr * nst + 6 * ti.cb);
+              const double2 a01 = pa[0], a23 = pa[1], a45 = pa[2], b01 = pb[0], b23 = pb[1], b45 = pb[2];
+              const double av[6] = {a01.x, a01.y, a23.x, a23.y, a45.x, a45.y};
+              const double bv[6] = {b01.x, b01.y, b23.x, b23.y, b45.x, b45.y};
 #pragma unroll
-              for (int cc = 0; cc < 6; cc++) T[rr * 6 + cc] = Linv[rr * nst + 6 * ti.cb + cc];
+              for (int i = 0; i < 6; i++)
+#pragma unroll
+                for (int j = 0; j < 6; j++) T[i * 6 + j] = fma(av[i], bv[j], T[i * 6 + j]);
+            }
           }
           __syncthreads();
         }
@@ -373,83 +387,68 @@ __device__ void factorize(Smem& S, double* __restrict__ Linv, double (&T)[NT], c
 }
 
 // ---- K^-1 application, register-tile path (n <= 150) -----------------------------------------
-// Thread t < NB(NB+1)/2 holds the 6x6 tile (rb, cb) of L^-1 (NB = ceil(n/6), cb <= rb).
-//   forward:  part[6 rb + r][cb] = tile[r][:] . rhs[6 cb ..],  tn[i] = sum_cb part[i][cb]
-//   backward: part[rb][6 cb + c] = tile[:][c] . tn[6 rb ..],   xt[j] = sum_rb part[rb][j]
-// then x = alpha xt + (1 - alpha) x_prev.  FMA is fine here: bit parity of this solve with a CPU
-// factorisation is not attainable anyway.
+// Thread t < NB(NB+1)/2 holds the 6x6 tile (rb, cb), cb <= rb, of the SYMMETRIC K^-1 (NB = ceil(n/6))
+// and uses it for both triangles in one pass:
+//   partA[6 rb + i][cb] = tile[i][:] . rhs[6 cb ..]        (row side)
+//   partB[6 cb + j][rb] = tile[:][j] . rhs[6 rb ..]        (column side, off-diagonal tiles only)
+//   xt[i] = sum_cb partA[i][cb] + sum_rb partB[i][rb]      (two lanes per output, one per side)
+// then x = alpha xt + (1 - alpha) x_prev.  partA and partB, both [6NB][NBp], are zero outside the
+// entries the tiles write, so the sums run over whole rows / columns without masking.  FMA is
+// fine here: bit parity of this solve with a CPU factorisation is not attainable anyway.
 template <int NT>
 __device__ __forceinline__ void kkt_tiles(Smem& S, const double (&T)[NT], const TileId& ti,
-                                          double* __restrict__ part1, double* __restrict__ part2) {
-  // part1 [6NB][NBp] (NBp even, = 2 mod 4, >= NB) and part2 [NBq][6NB] (NBq = even >= NB) are zero
-  // outside the tiles' entries, so the reductions add whole rows / columns without any masking:
-  // two lanes per output, half a row (column) each, independent loads, one shuffle.
+                                          double* __restrict__ partA, double* __restrict__ partB) {
   const int n = S.n, tid = threadIdx.x;
-  const int NB6 = 6 * ti.NB;
   if (ti.act) {
-    const double2* xr = reinterpret_cast<const double2*>(S.rhs + 6 * ti.cb);
-    const double2 x01 = xr[0], x23 = xr[1], x45 = xr[2];
-    double* out = part1 + (6 * ti.rb) * ti.NBp + ti.cb;
+    const double2* xc = reinterpret_cast<const double2*>(S.rhs + 6 * ti.cb);
+    const double2* xr = reinterpret_cast<const double2*>(S.rhs + 6 * ti.rb);
+    const double2 c01 = xc[0], c23 = xc[1], c45 = xc[2];
+    double* outA = partA + (6 * ti.rb) * ti.NBp + ti.cb;
 #pragma unroll
-    for (int r = 0; r < 6; r++) {
-      double s = T[r * 6] * x01.x;
-      s = fma(T[r * 6 + 1], x01.y, s);
-      s = fma(T[r * 6 + 2], x23.x, s);
-      s = fma(T[r * 6 + 3], x23.y, s);
-      s = fma(T[r * 6 + 4], x45.x, s);
-      s = fma(T[r * 6 + 5], x45.y, s);
-      out[r * ti.NBp] = s;
+    for (int i = 0; i < 6; i++) {
+      double s = T[i * 6] * c01.x;
+      s = fma(T[i * 6 + 1], c01.y, s);
+      s = fma(T[i * 6 + 2], c23.x, s);
+      s = fma(T[i * 6 + 3], c23.y, s);
+      s = fma(T[i * 6 + 4], c45.x, s);
+      s = fma(T[i * 6 + 5], c45.y, s);
+      outA[i * ti.NBp] = s;
+    }
+    if (ti.rb != ti.cb) {
+      const double2 r01 = xr[0], r23 = xr[1], r45 = xr[2];
+      double o[6];
+#pragma unroll
+      for (int j = 0; j < 6; j++) {
+        double s = T[j] * r01.x;
+        s = fma(T[6 + j], r01.y, s);
+        s = fma(T[12 + j], r23.x, s);
+        s = fma(T[18 + j], r23.y, s);
+        s = fma(T[24 + j], r45.x, s);
+        s = fma(T[30 + j], r45.y, s);
+        o[j] = s;
+      }
+      double* outB = partB + (6 * ti.cb) * ti.NBp + ti.rb;
+#pragma unroll
+      for (int j = 0; j < 6; j++) outB[j * ti.NBp] = o[j];
     }
   }
   __syncthreads();
   {
-    // NBp/2 (odd) 16-byte loads per row: lane 0 takes the first (NBp/2+1)/2, lane 1 the rest
-    const int i = tid >> 1, half = tid & 1, c0n = ((ti.NBp >> 1) + 1) >> 1;
-    const int cnt = half ? (ti.NBp >> 1) - c0n : c0n;
+    // both sides keep the same [output][NBp] layout, so the two lanes of an output run the same
+    // instruction stream (no divergence): NBp/2 16-byte loads each
+    const int i = tid >> 1, side = tid & 1;
     double a = 0, b = 0;
     if (i < n) {
-      const double2* pr = reinterpret_cast<const double2*>(part1 + i * ti.NBp) + half * c0n;
+      const double2* pr = reinterpret_cast<const double2*>((side ? partB : partA) + i * ti.NBp);
+      const int cnt = ti.NBp >> 1;
 #pragma unroll 4
       for (int k = 0; k < cnt; k++) { const double2 v = pr[k]; a += v.x; b += v.y; }
     }
-    double sum = a + b;
-    sum += __shfl_xor_sync(0xffffffffu, sum, 1);
-    if (i < n && half == 0) S.tn[i] = sum;
-  }
-  __syncthreads();
-  if (ti.act) {
-    const double2* tr = reinterpret_cast<const double2*>(S.tn + 6 * ti.rb);
-    const double2 t01 = tr[0], t23 = tr[1], t45 = tr[2];
-    double o[6];
-#pragma unroll
-    for (int c = 0; c < 6; c++) {
-      double s = T[c] * t01.x;
-      s = fma(T[6 + c], t01.y, s);
-      s = fma(T[12 + c], t23.x, s);
-      s = fma(T[18 + c], t23.y, s);
-      s = fma(T[24 + c], t45.x, s);
-      s = fma(T[30 + c], t45.y, s);
-      o[c] = s;
-    }
-    double2* out = reinterpret_cast<double2*>(part2 + ti.rb * NB6 + 6 * ti.cb);
-    out[0] = make_double2(o[0], o[1]); out[1] = make_double2(o[2], o[3]); out[2] = make_double2(o[4], o[5]);
-  }
-  __syncthreads();
-  {
-    const int j = tid >> 1, half = tid & 1, cnt = (ti.NB + 1) >> 1;   // rows of part2 per lane
-    double a = 0, b = 0;
-    if (j < n) {
-      const double* pc = part2 + half * cnt * NB6 + j;
-      int k = 0;
-#pragma unroll 4
-      for (; k + 1 < cnt; k += 2) { a += pc[k * NB6]; b += pc[(k + 1) * NB6]; }
-      if (k < cnt) a += pc[k * NB6];
-    }
     double xt = a + b;
     xt += __shfl_xor_sync(0xffffffffu, xt, 1);
-    if (j < n && half == 0) {
-      S.xt[j] = xt;
-      S.x[j] = ALPHA * xt + (1.0 - ALPHA) * S.xp[j];
+    if (i < n && side == 0) {
+      S.xt[i] = xt;
+      S.x[i] = ALPHA * xt + (1.0 - ALPHA) * S.xp[i];
     }
   }
   __syncthreads();
@@ -641,7 +640,7 @@ __global__ void __launch_bounds__(kT, 1) k_qp_admm(QpDev Dv, QpParams P, const d
   if (((n + 5) / 6 <= kTileNB && m <= 3 * kT) != TILES) return;   // the other variant's problem
   const int NBt = (n + 5) / 6;
   // TILES: staging rows (6 x 6NB) / partial sums (6NB x NBp) instead of the packed factor
-  const int part1_len = 6 * NBt * (((NBt + 1) & ~1) + 4), part2_len = ((NBt + 1) & ~1) * 6 * NBt;
+  const int part1_len = 6 * NBt * (((NBt + 1) & ~1) + 4), part2_len = part1_len;
   const int linv_len = TILES ? max(36 * NBt, part1_len + part2_len) : linv_off((n + 1) & ~1);
   const size_t dyn_bytes = sizeof(double) * (static_cast<size_t>(linv_len) + n * kBand + nnz + 16 * n + 2) + m + 16;
   if (m > kRowCap || kHdrBytes + dyn_bytes > (TILES ? kSmemTiles : kSmemBytes)) {

@@ -318,29 +318,32 @@ __global__ void k_download(PopGeom g, const uint8_t* __restrict__ ag, float* __r
 // launchers
 // =============================================================================================
 // =============================================================================================
-// K1f (tiled)  u8 grids whose z-layer (nx*ny bytes) fits in shared memory.
+// K1f (tiled)  u8 grids: every SOGM byte is written exactly once, by a TMA bulk store of a
+// finished shared-memory tile; nothing is read back and no partial-sector read-modify-write
+// reaches L2/HBM.
 //
-// Every SOGM byte is written exactly once, by a TMA bulk store of a finished tile; nothing is
-// read back and no partial-sector read-modify-write reaches L2/HBM:
-//   1. k_vox_count / k_vox_scan / k_vox_fill: counting sort of the cloud points of every agent
-//      by destination z-layer — one list for slice 0 (voxel of pt - pose) and one for the future
-//      slices (voxel corner + owner cylinder id; the z of pt + v*dt*k - pose does not depend on
-//      k because vz = 0, but is recomputed in fp32 exactly as the reference does, so it may differ
-//      from the slice-0 layer by rounding and gets its own list);
-//   2. k_vox_tiles: persistent CTAs walk the (agent, slice, z-layer) units; a unit zeroes its
-//      nx*ny-byte tile in shared memory, scatters the layer's entries displaced by v*dt*k
-//      (same fp32 operation order as fake_particle_risk_voxel.cpp:127-162), and hands the tile
-//      to cp.async.bulk (shared → global).  Two CTAs per SM alternate between building and draining.
+// A tile is a band of H rows of one z-layer of one slice of one agent (nx*H bytes <= 96 KB, so
+// two CTAs per SM alternate between building and draining; at BASELINE config 2 a band is the
+// whole 300x300 layer).
+//   1. k_vox_count / k_vox_scan / k_vox_fill: counting sort of every agent's cloud points by
+//      (z-layer, band) — one list for slice 0 (voxel of pt - pose, keyed by its own row) and one
+//      for the future slices (voxel corner + owner cylinder id, keyed by the SOURCE row).  The z
+//      of pt + v*dt*k - pose does not depend on k (vz = 0) but is recomputed in fp32 exactly as the
+//      reference does, so it may differ from the slice-0 layer by rounding.
+//   2. k_vox_tiles: persistent CTAs walk the (agent, slice, layer, band) units; a unit zeroes its
+//      tile, scatters the entries of the source bands within reach of the largest |vy|*dt*k
+//      displaced by v*dt*k (same fp32 operation order as fake_particle_risk_voxel.cpp:127-162),
+//      and hands the tile to cp.async.bulk (shared → global).
 // Duplicate points in a voxel are idempotent stores of 1, so the per-voxel compaction of the
 // scatter path is not needed.  Algorithmic bytes: V*T written once + N_pts*12 read per agent.
 // =============================================================================================
 struct VoxDev {
-  int cap = 0, nl = 0, nz = 0;
-  int* cnt = nullptr;            // [agent][2][nz]   entries per layer (list 0: slice 0, list 1: future)
-  int* off = nullptr;            // [agent][2][nz+1] exclusive prefix
-  int* cur = nullptr;            // [agent][2][nz]   fill cursors
-  unsigned* ent0 = nullptr;      // [agent][cap]     iy*nx + ix of the slice-0 voxel
-  unsigned long long* entf = nullptr;  // [agent][cap] ix | iy<<16 | owner<<32 (owner 0xffff: static)
+  int cap = 0, nl = 0, nkeys = 0, H = 0, nbands = 0;
+  int* cnt = nullptr;            // [agent][2][nkeys]   entries per (layer, band); list 0: slice 0, 1: future
+  int* off = nullptr;            // [agent][2][nkeys+1] exclusive prefix
+  int* cur = nullptr;            // [agent][2][nkeys]   fill cursors
+  unsigned* ent0 = nullptr;      // [agent][cap]        iy*nx + ix of the slice-0 voxel
+  unsigned long long* entf = nullptr;  // [agent][cap]  ix | iy<<16 | owner<<32 (owner 0xffff: static)
 };
 
 // slice-0 voxel of a cloud point as the reference computes it, or false
@@ -367,36 +370,50 @@ __device__ __forceinline__ int vox_future_layer(const PopGeom& g, int iz, float 
   return (l >= 0 && l < g.nz) ? l : -1;
 }
 
-__global__ void __launch_bounds__(256) k_vox_count(PopGeom g, const float* __restrict__ cloud, int n_cloud,
-                                                   const float* __restrict__ poses, int* __restrict__ cnt) {
+__global__ void __launch_bounds__(256) k_vox_count(PopGeom g, int H, int nbands, const float* __restrict__ cloud,
+                                                   int n_cloud, const float* __restrict__ poses,
+                                                   int* __restrict__ cnt) {
   const int a = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_cloud) return;
   const float posez = poses[3 * a + 2];
+  const int nkeys = g.nz * nbands;
   int ix, iy, iz;
   if (!vox_point(g, cloud, i, poses[3 * a], poses[3 * a + 1], posez, &ix, &iy, &iz)) return;
-  atomicAdd(&cnt[(a * 2 + 0) * g.nz + iz], 1);
+  const int band = iy / H;
+  atomicAdd(&cnt[(a * 2 + 0) * nkeys + iz * nbands + band], 1);
   if (1.0f > g.risk_threshold) {   // tmp[i][0] > risk_threshold_ (fake_particle_risk_voxel.cpp:121)
     const int lf = vox_future_layer(g, iz, posez);
-    if (lf >= 0) atomicAdd(&cnt[(a * 2 + 1) * g.nz + lf], 1);
+    if (lf >= 0) atomicAdd(&cnt[(a * 2 + 1) * nkeys + lf * nbands + band], 1);
   }
 }
 
-__global__ void k_vox_scan(int n_lists, int nz, int cap, const int* __restrict__ cnt, int* __restrict__ off,
-                           int* __restrict__ cur) {
-  // one thread per (agent, list): nz <= a few hundred
-  const int l = blockIdx.x * blockDim.x + threadIdx.x;
-  if (l >= n_lists) return;
-  int run = 0;
-  for (int z = 0; z < nz; z++) {
-    off[l * (nz + 1) + z] = run;
-    cur[l * nz + z] = 0;
-    run += cnt[l * nz + z];
+// exclusive prefix over the keys of one (agent, list) per CTA
+__global__ void __launch_bounds__(256) k_vox_scan(int nkeys, int cap, const int* __restrict__ cnt,
+                                                  int* __restrict__ off, int* __restrict__ cur) {
+  __shared__ int part[256];
+  const int l = blockIdx.x, tid = threadIdx.x;
+  const int per = (nkeys + 255) / 256;
+  const int k0 = tid * per, k1 = min(nkeys, k0 + per);
+  int s = 0;
+  for (int k = k0; k < k1; k++) s += cnt[l * nkeys + k];
+  part[tid] = s;
+  __syncthreads();
+  if (tid == 0) {
+    int run = 0;
+    for (int t = 0; t < 256; t++) { const int v = part[t]; part[t] = run; run += v; }
+    off[l * (nkeys + 1) + nkeys] = run < cap ? run : cap;
   }
-  off[l * (nz + 1) + nz] = run < cap ? run : cap;
+  __syncthreads();
+  int run = part[tid];
+  for (int k = k0; k < k1; k++) {
+    off[l * (nkeys + 1) + k] = run < cap ? run : cap;
+    cur[l * nkeys + k] = 0;
+    run += cnt[l * nkeys + k];
+  }
 }
 
-__global__ void __launch_bounds__(256) k_vox_fill(PopGeom g, const float* __restrict__ cloud, int n_cloud,
-                                                  const float* __restrict__ poses,
+__global__ void __launch_bounds__(256) k_vox_fill(PopGeom g, int H, int nbands, const float* __restrict__ cloud,
+                                                  int n_cloud, const float* __restrict__ poses,
                                                   const PopCylDev* __restrict__ cyl, int n_cyl,
                                                   const int* __restrict__ off, int* __restrict__ cur,
                                                   unsigned* __restrict__ ent0,
@@ -407,11 +424,13 @@ __global__ void __launch_bounds__(256) k_vox_fill(PopGeom g, const float* __rest
   const int a = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_cloud) return;
   const float posex = poses[3 * a], posey = poses[3 * a + 1], posez = poses[3 * a + 2];
+  const int nkeys = g.nz * nbands;
   int ix, iy, iz;
   if (!vox_point(g, cloud, i, posex, posey, posez, &ix, &iy, &iz)) return;
+  const int band = iy / H;
   {
-    const int l = a * 2 + 0;
-    const int pos = off[l * (g.nz + 1) + iz] + atomicAdd(&cur[l * g.nz + iz], 1);
+    const int l = a * 2 + 0, key = iz * nbands + band;
+    const int pos = off[l * (nkeys + 1) + key] + atomicAdd(&cur[l * nkeys + key], 1);
     if (pos < cap) ent0[static_cast<size_t>(a) * cap + pos] = static_cast<unsigned>(iy * g.nx + ix);
   }
   if (!(1.0f > g.risk_threshold)) return;
@@ -433,8 +452,8 @@ __global__ void __launch_bounds__(256) k_vox_fill(PopGeom g, const float* __rest
       break;
     }
   }
-  const int l = a * 2 + 1;
-  const int pos = off[l * (g.nz + 1) + lf] + atomicAdd(&cur[l * g.nz + lf], 1);
+  const int l = a * 2 + 1, key = lf * nbands + band;
+  const int pos = off[l * (nkeys + 1) + key] + atomicAdd(&cur[l * nkeys + key], 1);
   if (pos < cap)
     entf[static_cast<size_t>(a) * cap + pos] = static_cast<unsigned long long>(ix) |
                                                (static_cast<unsigned long long>(iy) << 16) |
@@ -443,8 +462,10 @@ __global__ void __launch_bounds__(256) k_vox_fill(PopGeom g, const float* __rest
 
 constexpr int kTileThreads = 256;
 constexpr int kTileChunk = 32 * 1024;   // bytes per bulk store
+constexpr int kTileMax = 96 * 1024;     // tile bytes: two CTAs per SM
 
-__global__ void __launch_bounds__(kTileThreads, 2) k_vox_tiles(PopGeom g, uint8_t* __restrict__ grid, int n_agents,
+__global__ void __launch_bounds__(kTileThreads, 2) k_vox_tiles(PopGeom g, int H, int nbands, float reach_per_slice,
+                                                               uint8_t* __restrict__ grid, int n_agents,
                                                                const float* __restrict__ poses,
                                                                const PopCylDev* __restrict__ cyl, int n_cyl,
                                                                const int* __restrict__ off,
@@ -452,28 +473,35 @@ __global__ void __launch_bounds__(kTileThreads, 2) k_vox_tiles(PopGeom g, uint8_
                                                                const unsigned long long* __restrict__ entf,
                                                                int cap) {
   extern __shared__ __align__(128) uint8_t tile[];
-  const int layer = g.nx * g.ny;                      // bytes, multiple of 16
-  float2* svel = reinterpret_cast<float2*>(tile + ((layer + 127) & ~127));   // cylinder velocities
+  const int tile_max = ((g.nx * H + 127) & ~127);
+  float2* svel = reinterpret_cast<float2*>(tile + tile_max);   // cylinder velocities
   for (int c = threadIdx.x; c < n_cyl; c += blockDim.x) svel[c] = make_float2(cyl[c].vx, cyl[c].vy);
   const unsigned smem = static_cast<unsigned>(__cvta_generic_to_shared(tile));
-  const long long units = static_cast<long long>(n_agents) * g.nt * g.nz;
+  const int nkeys = g.nz * nbands;
+  const long long units = static_cast<long long>(n_agents) * g.nt * nkeys;
   for (long long u = blockIdx.x; u < units; u += gridDim.x) {
-    const int iz = static_cast<int>(u % g.nz);
-    const int k = static_cast<int>((u / g.nz) % g.nt);
-    const int a = static_cast<int>(u / (static_cast<long long>(g.nz) * g.nt));
+    const int band = static_cast<int>(u % nbands);
+    const int iz = static_cast<int>((u / nbands) % g.nz);
+    const int k = static_cast<int>((u / nkeys) % g.nt);
+    const int a = static_cast<int>(u / (static_cast<long long>(nkeys) * g.nt));
+    const int y0 = band * H, rows = min(H, g.ny - y0), bytes = rows * g.nx;
     // the previous unit's bulk stores must have finished READING the tile before it is rebuilt
     if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     __syncthreads();
-    for (int i = threadIdx.x * 16; i < layer; i += kTileThreads * 16)
+    for (int i = threadIdx.x * 16; i < bytes; i += kTileThreads * 16)
       *reinterpret_cast<uint4*>(tile + i) = make_uint4(0, 0, 0, 0);
     __syncthreads();
-    const int list = k == 0 ? 0 : 1;
-    const int* o = off + (a * 2 + list) * (g.nz + 1);
-    const int e0 = o[iz], e1 = o[iz + 1];
     if (k == 0) {
+      const int* o = off + (a * 2 + 0) * (nkeys + 1) + iz * nbands + band;
       const unsigned* e = ent0 + static_cast<size_t>(a) * cap;
-      for (int q = e0 + threadIdx.x; q < e1; q += kTileThreads) tile[e[q]] = 1;
+      const int e1 = o[1], base = y0 * g.nx;
+      for (int q = o[0] + threadIdx.x; q < e1; q += kTileThreads) tile[e[q] - base] = 1;
     } else {
+      // source bands whose voxels can land in this band after k slices
+      const int r = static_cast<int>((reach_per_slice * static_cast<float>(k) + 2.0f) / static_cast<float>(H)) + 1;
+      const int b0 = max(0, band - r), b1 = min(nbands - 1, band + r);
+      const int* o = off + (a * 2 + 1) * (nkeys + 1) + iz * nbands;
+      const int e0 = o[b0], e1 = o[b1 + 1];   // the keys of one layer are consecutive
       const unsigned long long* e = entf + static_cast<size_t>(a) * cap;
       const float posex = poses[3 * a], posey = poses[3 * a + 1];
       const float kf = static_cast<float>(k);
@@ -488,17 +516,17 @@ __global__ void __launch_bounds__(kTileThreads, 2) k_vox_tiles(PopGeom g, uint8_
         const float qx = __fsub_rn(__fadd_rn(ptx, __fmul_rn(__fmul_rn(vx, g.dt), kf)), posex);
         const float qy = __fsub_rn(__fadd_rn(pty, __fmul_rn(__fmul_rn(vy, g.dt), kf)), posey);
         if (!(qx > -g.rx && qx < g.rx && qy > -g.ry && qy < g.ry)) continue;
-        const int jx = geom_axis_index(qx, g.rx, g.res), jy = geom_axis_index(qy, g.ry, g.res);
-        if (jx < 0 || jx >= g.nx || jy < 0 || jy >= g.ny) continue;
+        const int jx = geom_axis_index(qx, g.rx, g.res), jy = geom_axis_index(qy, g.ry, g.res) - y0;
+        if (jx < 0 || jx >= g.nx || jy < 0 || jy >= rows) continue;
         tile[jy * g.nx + jx] = 1;
       }
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
     if (threadIdx.x == 0) {
-      uint8_t* dst = grid + a * g.agent_stride + (static_cast<size_t>(k) * g.nz + iz) * layer;
-      for (int b = 0; b < layer; b += kTileChunk) {
-        const unsigned n = layer - b < kTileChunk ? layer - b : kTileChunk;
+      uint8_t* dst = grid + a * g.agent_stride + ((static_cast<size_t>(k) * g.nz + iz) * g.ny + y0) * g.nx;
+      for (int b = 0; b < bytes; b += kTileChunk) {
+        const unsigned n = bytes - b < kTileChunk ? bytes - b : kTileChunk;
         asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst + b),
                      "r"(smem + b), "r"(n)
                      : "memory");
@@ -518,58 +546,67 @@ void popk_vox_free(pop_handle* h) {
   h->vox = nullptr;
 }
 
-// the tiled path applies to u8 grids whose layer fits in shared memory next to a second CTA
+// band height: the largest H with nx*H <= kTileMax whose tiles start and end on 16-byte boundaries
+// (bulk-copy alignment); 0 if the grid cannot be tiled that way
+static int vox_band_rows(const PopGeom& g) {
+  if (static_cast<long long>(g.nx) * g.ny <= kTileMax) return (g.nx * g.ny) % 16 == 0 ? g.ny : 0;
+  int step = 1;
+  while ((g.nx * step) % 16) step++;        // <= 16
+  if ((static_cast<long long>(g.nx) * g.ny) % 16) return 0;   // layer starts must stay aligned too
+  const int H = (kTileMax / g.nx) / step * step;
+  return H > 0 ? H : 0;
+}
+
+// the tiled path applies to u8 grids (the scatter kernels cover f32 cells and unaligned shapes)
 static bool vox_tiles_ok(const pop_handle* h) {
   const PopGeom& g = h->geom;
   const char* e = getenv("POP_VOXEL_MODE");   // "tiles" (default) | "scatter"
   if (e && e[0] == 's') return false;
-  const int layer = g.nx * g.ny;
-  return h->cfg.cell_dtype == POP_CELL_U8 && layer % 16 == 0 && layer <= 110 * 1024 && g.nx < 65536 &&
-         g.ny < 65536 && h->cfg.max_cylinders < 0xffff;
+  return h->cfg.cell_dtype == POP_CELL_U8 && vox_band_rows(g) > 0 && g.nx < 65536 && g.ny < 65536 &&
+         h->cfg.max_cylinders < 0xffff;
 }
 
 static int vox_update_tiles(pop_handle* h, int sms, int* launches) {
   const PopGeom& g = h->geom;
   const int nl = h->cfg.n_agents_local, cap = h->cfg.max_cloud_points;
+  const int H = vox_band_rows(g), nbands = (g.ny + H - 1) / H, nkeys = g.nz * nbands;
+  const int smem = ((g.nx * H + 127) & ~127) + static_cast<int>(sizeof(float2)) * (h->cfg.max_cylinders + 1);
   if (!h->vox) {
     VoxDev* d = new VoxDev();
     h->vox = d;
-    d->cap = cap; d->nl = nl; d->nz = g.nz;
+    d->cap = cap; d->nl = nl; d->nkeys = nkeys; d->H = H; d->nbands = nbands;
     bool ok = true;
-    ok &= cudaMalloc(&d->cnt, sizeof(int) * nl * 2 * g.nz) == cudaSuccess;
-    ok &= cudaMalloc(&d->off, sizeof(int) * nl * 2 * (g.nz + 1)) == cudaSuccess;
-    ok &= cudaMalloc(&d->cur, sizeof(int) * nl * 2 * g.nz) == cudaSuccess;
+    ok &= cudaMalloc(&d->cnt, sizeof(int) * nl * 2 * nkeys) == cudaSuccess;
+    ok &= cudaMalloc(&d->off, sizeof(int) * nl * 2 * (nkeys + 1)) == cudaSuccess;
+    ok &= cudaMalloc(&d->cur, sizeof(int) * nl * 2 * nkeys) == cudaSuccess;
     ok &= cudaMalloc(&d->ent0, sizeof(unsigned) * static_cast<size_t>(nl) * cap) == cudaSuccess;
     ok &= cudaMalloc(&d->entf, sizeof(unsigned long long) * static_cast<size_t>(nl) * cap) == cudaSuccess;
     if (!ok) { cudaGetLastError(); return pop_fail(h, POP_E_CUDA, "voxel-update entry lists allocation failed"); }
-    const int layer = g.nx * g.ny;
-    const int smem = ((layer + 127) & ~127) + static_cast<int>(sizeof(float2)) * (h->cfg.max_cylinders + 1);
     POP_CUDA(h, cudaFuncSetAttribute(k_vox_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   }
   VoxDev* d = h->vox;
-  const int layer = g.nx * g.ny;
-  const int smem = ((layer + 127) & ~127) + static_cast<int>(sizeof(float2)) * (h->cfg.max_cylinders + 1);
-  POP_CUDA(h, cudaMemsetAsync(d->cnt, 0, sizeof(int) * nl * 2 * g.nz, h->stream));
+  POP_CUDA(h, cudaMemsetAsync(d->cnt, 0, sizeof(int) * nl * 2 * nkeys, h->stream));
   if (h->n_cloud > 0) {
     dim3 grid((h->n_cloud + 255) / 256, nl);
-    k_vox_count<<<grid, 256, 0, h->stream>>>(g, h->d_cloud, h->n_cloud, h->d_poses, d->cnt);
+    k_vox_count<<<grid, 256, 0, h->stream>>>(g, H, nbands, h->d_cloud, h->n_cloud, h->d_poses, d->cnt);
     POP_LAUNCH_CHECK(h);
     (*launches)++;
   }
-  k_vox_scan<<<(nl * 2 + 63) / 64, 64, 0, h->stream>>>(nl * 2, g.nz, cap, d->cnt, d->off, d->cur);
+  k_vox_scan<<<nl * 2, 256, 0, h->stream>>>(nkeys, cap, d->cnt, d->off, d->cur);
   POP_LAUNCH_CHECK(h);
   (*launches)++;
   if (h->n_cloud > 0) {
     dim3 grid((h->n_cloud + 255) / 256, nl);
     const size_t sm = sizeof(PopCylDev) * (h->n_cyl > 0 ? h->n_cyl : 1);
-    k_vox_fill<<<grid, 256, sm, h->stream>>>(g, h->d_cloud, h->n_cloud, h->d_poses, h->d_cyl, h->n_cyl, d->off,
-                                             d->cur, d->ent0, d->entf, cap);
+    k_vox_fill<<<grid, 256, sm, h->stream>>>(g, H, nbands, h->d_cloud, h->n_cloud, h->d_poses, h->d_cyl, h->n_cyl,
+                                             d->off, d->cur, d->ent0, d->entf, cap);
     POP_LAUNCH_CHECK(h);
     (*launches)++;
   }
-  const int ctas = smem <= 110 * 1024 ? 2 * sms : sms;
-  k_vox_tiles<<<ctas, kTileThreads, smem, h->stream>>>(g, h->d_grid, nl, h->d_poses, h->d_cyl, h->n_cyl, d->off,
-                                                       d->ent0, d->entf, cap);
+  // rows a voxel can move per slice: |vy|*dt/res (the kernel adds a 2-row rounding margin)
+  const float reach = h->max_abs_vy * g.dt / g.res;
+  k_vox_tiles<<<2 * sms, kTileThreads, smem, h->stream>>>(g, H, nbands, reach, h->d_grid, nl, h->d_poses, h->d_cyl,
+                                                         h->n_cyl, d->off, d->ent0, d->entf, cap);
   POP_LAUNCH_CHECK(h);
   (*launches)++;
   return POP_OK;

@@ -226,6 +226,7 @@ int pop_set_cylinders(pop_handle* h, const pop_cylinder* cyl, int n) {
   if (!h || n < 0 || (n > 0 && !cyl)) return POP_E_INVALID;
   if (n > h->cfg.max_cylinders) return pop_fail(h, POP_E_CAPACITY, "%d cylinders exceed max_cylinders=%d", n, h->cfg.max_cylinders);
   std::vector<PopCylDev> v(n);
+  float max_vy = 0.f;
   for (int i = 0; i < n; i++) {
     // casts of fake_particle_risk_voxel.cpp:133,137: Vector3f(cyl.x, cyl.y, .), Vector3f(cyl.vx, cyl.vy, 0)
     v[i].x = static_cast<float>(cyl[i].x);
@@ -235,7 +236,9 @@ int pop_set_cylinders(pop_handle* h, const pop_cylinder* cyl, int n) {
     v[i].w = cyl[i].w;
     v[i].type = cyl[i].type;
     v[i]._pad = 0;
+    if (v[i].type == 3 && std::fabs(v[i].vy) > max_vy) max_vy = std::fabs(v[i].vy);
   }
+  h->max_abs_vy = max_vy;
   if (n > 0) POP_CUDA(h, cudaMemcpyAsync(h->d_cyl, v.data(), sizeof(PopCylDev) * n, cudaMemcpyHostToDevice, h->stream));
   POP_CUDA(h, cudaStreamSynchronize(h->stream));
   h->n_cyl = n;

@@ -61,6 +61,7 @@ struct pop_handle {
   int n_cloud = 0;
   PopCylDev* d_cyl = nullptr;
   int n_cyl = 0;
+  float max_abs_vy = 0.f;         // largest |vy| of the type-3 cylinders (tile reach of the voxel update)
   float* d_poses = nullptr;       // n_local x 3
   int* d_occ_list = nullptr;      // n_local x max_cloud_points voxel indices of slice 0
   int* d_occ_count = nullptr;     // n_local

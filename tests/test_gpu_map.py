@@ -221,3 +221,32 @@ def test_full_size_c2_tiled_equals_scatter_path(monkeypatch):
     eng.set_world_cloud(np.zeros((0, 3), np.float32))
     eng.map_update_gt(1.1)
     assert not eng.agent_map(0).risk_maps().any()
+
+
+def test_banded_tiles_equal_scatter_path(monkeypatch):
+    """A layer larger than one shared-memory tile (400x400 B → two bands of rows): fast cylinders carry
+    voxels across the band boundary over the 20 slices; the banded tile build must still equal the
+    scatter kernels byte for byte."""
+    n = 3
+    cfg = cases.cfg_small_c2(p.POP_CELL_U8, n_local=n, n_total=n, nx=400, ny=400, nz=8, nt=20)
+    cloud, cyl = worldgen_fast(5, (40.0, 40.0, 0.8), 60)
+    poses = np.array([[0.3, -0.2, 0.2], [7.0, 5.0, 0.3], [-15.0, 12.0, 0.1]], np.float32)
+    eng = p.PopEngine(cfg)
+    eng.set_world_cloud(cloud)
+    eng.set_cylinders(cyl)
+    eng.set_poses(poses)
+    monkeypatch.setenv("POP_VOXEL_MODE", "tiles")
+    eng.map_update_gt(3.0)
+    tiled = [eng.agent_map(a).risk_maps() for a in range(n)]
+    monkeypatch.setenv("POP_VOXEL_MODE", "scatter")
+    eng.map_update_gt(3.0)
+    moved = 0
+    for a in range(n):
+        ref = eng.agent_map(a).risk_maps()
+        assert np.array_equal(tiled[a], ref), f"agent {a}"
+        moved += int(np.count_nonzero(ref[:, 19] != ref[:, 0]))
+    assert moved > 1000   # the world really moved
+
+
+def worldgen_fast(seed, arena, n_moving):
+    return p.worldgen.make_world(seed, arena=arena, n_static=4, n_moving=n_moving, v_max=3.0, height=0.6)

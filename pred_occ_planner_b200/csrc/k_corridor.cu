@@ -163,14 +163,20 @@ __device__ __forceinline__ bool smoothed_l1(double mu, double x, double& f, doub
   return true;
 }
 
-// costMVIE (firi.hpp:73-142); A = M x 3 row-major
-__device__ double cost_mvie(const double* A, int M, double smooth_eps, double penalty, const double* x, double* grad) {
+// costMVIE (firi.hpp:73-142); A = M x 3 row-major.  Warp-cooperative: every lane evaluates the faces
+// lane, lane+32 (square root, divisions, smoothed penalty — the expensive part), leaves the face's
+// ten contributions in shared memory, and lanes 0..9 then add one quantity each over the faces IN
+// FACE ORDER, so the sums round exactly like the sequential loop (an inactive face contributes +0.0,
+// which never changes a sum that started at +0.0).  All lanes hold the same x and receive the same
+// cost and gradient.
+constexpr int kTerms = 10;
+__device__ double cost_mvie(const double* A, int M, double smooth_eps, double penalty, const double* x, double* grad,
+                            double (*terms)[kTerms]) {
+  const int lane = threadIdx.x & 31;
   const double* p = x; const double* rtd = x + 3; const double* cde = x + 6;
-  double gdp[3] = {0, 0, 0}, gdrtd[3] = {0, 0, 0}, gdcde[3] = {0, 0, 0};
-  double cost = 0;
   const double L00 = rtd[0] * rtd[0] + DBL_EPSILON, L10 = cde[0], L11 = rtd[1] * rtd[1] + DBL_EPSILON,
                L20 = cde[2], L21 = cde[1], L22 = rtd[2] * rtd[2] + DBL_EPSILON;
-  for (int i = 0; i < M; ++i) {
+  for (int i = lane; i < M; i += 32) {
     const double* a = A + i * 3;
     const double al0 = (a[0] * L00 + a[1] * L10) + a[2] * L20;
     const double al1 = (a[0] * 0.0 + a[1] * L11) + a[2] * L21;
@@ -179,15 +185,29 @@ __device__ double cost_mvie(const double* A, int M, double smooth_eps, double pe
     const double adj0 = al0 / nrm, adj1 = al1 / nrm, adj2 = al2 / nrm;
     const double viol = (nrm + ((a[0] * p[0] + a[1] * p[1]) + a[2] * p[2])) - 1.0;
     double c, dc;
+    double* t = terms[i];
     if (smoothed_l1(smooth_eps, viol, c, dc)) {
-      cost += c;
       const double v0 = dc * a[0], v1 = dc * a[1], v2 = dc * a[2];
-      gdp[0] += v0; gdp[1] += v1; gdp[2] += v2;
-      gdrtd[0] += adj0 * v0; gdrtd[1] += adj1 * v1; gdrtd[2] += adj2 * v2;
-      gdcde[0] += adj0 * v1;
-      gdcde[1] += adj1 * v2;
-      gdcde[2] += adj0 * v2;
+      t[0] = c; t[1] = v0; t[2] = v1; t[3] = v2;
+      t[4] = adj0 * v0; t[5] = adj1 * v1; t[6] = adj2 * v2;
+      t[7] = adj0 * v1; t[8] = adj1 * v2; t[9] = adj0 * v2;
+    } else {
+#pragma unroll
+      for (int q = 0; q < kTerms; q++) t[q] = 0.0;
     }
+  }
+  __syncwarp();
+  double acc = 0;
+  if (lane < kTerms)
+    for (int i = 0; i < M; ++i) acc += terms[i][lane];
+  __syncwarp();
+  double cost = __shfl_sync(0xffffffffu, acc, 0);
+  double gdp[3], gdrtd[3], gdcde[3];
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    gdp[k] = __shfl_sync(0xffffffffu, acc, 1 + k);
+    gdrtd[k] = __shfl_sync(0xffffffffu, acc, 4 + k);
+    gdcde[k] = __shfl_sync(0xffffffffu, acc, 7 + k);
   }
   cost *= penalty;
   for (int k = 0; k < 3; k++) { gdp[k] *= penalty; gdrtd[k] *= penalty; gdcde[k] *= penalty; }
@@ -211,8 +231,10 @@ __device__ __forceinline__ double maxabs9(const double* a) {
 }
 
 // line_search_lewisoverton (lbfgs.hpp:96-190)
+// Run by ALL lanes of the warp with identical arguments (uniform control flow).
 __device__ int line_search(const double* A, int M, double* x, double& f, double* g, double& stp, const double* s,
-                           const double* xp, const double* gp, double stpmin, double stpmax) {
+                           const double* xp, const double* gp, double stpmin, double stpmax,
+                           double (*terms)[kTerms]) {
   const double f_dec = 1.0e-4, s_curv = 0.9, machine_prec = 1.0e-16;
   const int max_ls = 64;
   int count = 0;
@@ -224,7 +246,7 @@ __device__ int line_search(const double* A, int M, double* x, double& f, double*
   const double finit = f, dgtest = f_dec * dginit, dstest = s_curv * dginit;
   while (true) {
     for (int i = 0; i < N9; i++) x[i] = xp[i] + stp * s[i];
-    f = cost_mvie(A, M, 1.0e-2, 1.0e+3, x, g);
+    f = cost_mvie(A, M, 1.0e-2, 1.0e+3, x, g, terms);
     ++count;
     if (isinf(f) || isnan(f)) return -3;
     if (f > finit + stp * dgtest) {
@@ -248,8 +270,10 @@ __device__ int line_search(const double* A, int M, double* x, double& f, double*
 }
 
 // lbfgs_optimize (lbfgs.hpp:192-430) with mem_size 18, past 3, delta 1e-7, g_epsilon 0,
-// min_step 1e-32 (firi.hpp:191-199); lm = 2*9*18 + 2*18 doubles of scratch
-__device__ int lbfgs9(const double* A, int M, double* x, double* lm) {
+// min_step 1e-32 (firi.hpp:191-199); lm = 2*9*18 + 2*18 doubles of per-warp shared memory.
+// Run by ALL lanes of the warp with identical arguments: the scalar algorithm is replicated, only
+// the cost evaluation is split over the lanes.
+__device__ int lbfgs9(const double* A, int M, double* x, double* lm, double (*terms)[kTerms]) {
   const int m = kMem, past = 3;
   const double delta = 1.0e-7, g_epsilon = 0.0, min_step = 1.0e-32, max_step = 1.0e+20, cautious = 1.0e-6;
   double* lm_s = lm;
@@ -258,7 +282,7 @@ __device__ int lbfgs9(const double* A, int M, double* x, double* lm) {
   double* lm_alpha = lm_ys + kMem;
   double xp[N9], g[N9], gp[N9], d[N9], pf[3];
   int ret = 0, k = 1, end = 0, bound = 0;
-  double fx = cost_mvie(A, M, 1.0e-2, 1.0e+3, x, g);
+  double fx = cost_mvie(A, M, 1.0e-2, 1.0e+3, x, g, terms);
   pf[0] = fx;
   for (int i = 0; i < N9; i++) d[i] = -g[i];
   double gnorm = maxabs9(g), xnorm = maxabs9(x);
@@ -266,7 +290,7 @@ __device__ int lbfgs9(const double* A, int M, double* x, double* lm) {
   double step = 1.0 / sqrt(dot9(d, d));
   while (true) {
     for (int i = 0; i < N9; i++) { xp[i] = x[i]; gp[i] = g[i]; }
-    const int ls = line_search(A, M, x, fx, g, step, d, xp, gp, min_step, max_step);
+    const int ls = line_search(A, M, x, fx, g, step, d, xp, gp, min_step, max_step, terms);
     if (ls < 0) {
       for (int i = 0; i < N9; i++) { x[i] = xp[i]; g[i] = gp[i]; }
       ret = ls;
@@ -283,6 +307,7 @@ __device__ int lbfgs9(const double* A, int M, double* x, double* lm) {
     double* sc = lm_s + end * N9;
     double* yc = lm_y + end * N9;
     for (int i = 0; i < N9; i++) { sc[i] = x[i] - xp[i]; yc[i] = g[i] - gp[i]; }
+    __syncwarp();
     const double ys = dot9(yc, sc), yy = dot9(yc, yc);
     lm_ys[end] = ys;
     for (int i = 0; i < N9; i++) d[i] = -g[i];
@@ -380,9 +405,10 @@ constexpr int kScrLp = kScrLm + 2 * N9 * kMem + 2 * kMem;
 constexpr int kScrDoubles = kScrLp + poplp::work_doubles(kLpRows, 4);
 constexpr int kScrInts = poplp::work_ints(kLpRows);
 
-// maxVolInsEllipsoid (firi.hpp:146-236); hPoly = M x 4
-__device__ bool max_vol_ins_ellipsoid(const double* hPoly, int M, double* R, double* p, double* r,
-                                      unsigned long long* rng, double* scr, int* scri) {
+// maxVolInsEllipsoid (firi.hpp:146-236); hPoly = M x 4.  Three steps: mvie_prepare (lane 0: deepest
+// point by LP, normalised faces A3, Cholesky start point), lbfgs9 (whole warp), mvie_finish (lane 0).
+__device__ bool mvie_prepare(const double* hPoly, int M, const double* R, const double* p, const double* r,
+                             unsigned long long* rng, double* scr, int* scri, double* x, double* interior) {
   double* Alp = scr + kScrAlp;
   double* blp = scr + kScrBlp;
   double* A3 = scr + kScrA3;
@@ -397,7 +423,7 @@ __device__ bool max_vol_ins_ellipsoid(const double* hPoly, int M, double* R, dou
   double xlp[4];
   const double maxdepth = -poplp::linprog<4>(clp, Alp, 4, blp, 1, M, xlp, rng, scr + kScrLp, scri);
   if (!(maxdepth > 0.0) || isinf(maxdepth)) return false;
-  const double interior[3] = {xlp[0], xlp[1], xlp[2]};
+  for (int k = 0; k < 3; k++) interior[k] = xlp[k];
   for (int i = 0; i < M; i++) {
     const double* a = Alp + i * 4;
     const double den = blp[i] - ((a[0] * interior[0] + a[1] * interior[1]) + a[2] * interior[2]);
@@ -413,11 +439,13 @@ __device__ bool max_vol_ins_ellipsoid(const double* hPoly, int M, double* R, dou
       Q[i * 3 + j] = s;
     }
   chol3(Q, L);
-  double x[9];
   for (int k = 0; k < 3; k++) x[k] = p[k] - interior[k];
   x[3] = sqrt(L[0]); x[4] = sqrt(L[4]); x[5] = sqrt(L[8]);
   x[6] = L[3]; x[7] = L[7]; x[8] = L[6];
-  const int ret = lbfgs9(A3, M, x, scr + kScrLm);
+  return true;
+}
+
+__device__ void mvie_finish(const double* x, const double* interior, double* R, double* p, double* r) {
   for (int k = 0; k < 3; k++) p[k] = x[k] + interior[k];
   const double Lf[9] = {x[3] * x[3], 0, 0, x[6], x[4] * x[4], 0, x[8], x[7], x[5] * x[5]};
   double U[9], S[3];
@@ -429,7 +457,6 @@ __device__ bool max_vol_ins_ellipsoid(const double* hPoly, int M, double* R, dou
     for (int k = 0; k < 9; k++) R[k] = U[k];
     for (int k = 0; k < 3; k++) r[k] = S[k];
   }
-  return ret >= 0;
 }
 
 // checkCorridorValidity (baseline_fake.cpp:191-204) on m rows of (h0,h1,h2,h3)
@@ -452,6 +479,10 @@ struct FiriWarp {           // shared memory per warp
   double fH[POP_MAX_FACES][4];
   double hP[POP_MAX_FACES][4];
   double R[9], p[3], r[3];
+  double lm[2 * N9 * kMem + 2 * kMem];   // L-BFGS memory of the MVIE step
+  double terms[POP_MAX_FACES][kTerms];   // per-face cost / gradient contributions
+  double x9[N9], interior[3];
+  int mvie_ok;
 };
 
 __device__ __forceinline__ void voxel_pos(const PopGeom& g, const float* pose, int idx, double* out) {
@@ -650,12 +681,21 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_corridor_firi(
       if (loop == 1) break;
       if (lane == 0) {
         unsigned long long rng = lp_seed(seed_base, si, 0);
-        double Rl[9], pl[3], rl[3];
-        for (int k = 0; k < 9; k++) Rl[k] = W.R[k];
-        for (int k = 0; k < 3; k++) { pl[k] = W.p[k]; rl[k] = W.r[k]; }
-        max_vol_ins_ellipsoid(&W.hP[0][0], nH, Rl, pl, rl, &rng, scr, scri);
-        for (int k = 0; k < 9; k++) W.R[k] = Rl[k];
-        for (int k = 0; k < 3; k++) { W.p[k] = pl[k]; W.r[k] = rl[k]; }
+        W.mvie_ok = mvie_prepare(&W.hP[0][0], nH, W.R, W.p, W.r, &rng, scr, scri, W.x9, W.interior) ? 1 : 0;
+      }
+      __syncwarp();
+      if (W.mvie_ok) {   // uniform: the whole warp runs the 9-variable L-BFGS, lanes share the face loop
+        __threadfence_block();
+        double x9[N9];
+        for (int k = 0; k < N9; k++) x9[k] = W.x9[k];
+        lbfgs9(scr + kScrA3, nH, x9, W.lm, W.terms);
+        __syncwarp();
+        if (lane == 0) {
+          double Rl[9], pl[3], rl[3];
+          mvie_finish(x9, W.interior, Rl, pl, rl);
+          for (int k = 0; k < 9; k++) W.R[k] = Rl[k];
+          for (int k = 0; k < 3; k++) { W.p[k] = pl[k]; W.r[k] = rl[k]; }
+        }
       }
       __syncwarp();
     }

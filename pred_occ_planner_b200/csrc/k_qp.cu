@@ -30,7 +30,8 @@
 
 namespace {
 
-constexpr int kT = 384;                       // threads per CTA
+constexpr int kT = 384;                       // threads per CTA, shared-memory factor variant (and upper bound)
+constexpr int kTt = 384;                      // threads per CTA, register-tile variant (11 warps would be allocated like 12)
 constexpr int kMaxN = 15 * POP_MAX_PIECES;    // 180 variables
 constexpr int kMaxRows = 9 * (POP_MAX_PIECES + 1) + 21 * POP_MAX_PIECES + 5 * POP_MAX_PIECES * POP_MAX_FACES;
 constexpr int kEll = 6;
@@ -93,7 +94,7 @@ constexpr int kTileNB = 25;          // register-tile path: n <= 150 → <= 325 
 // Shared memory of the register-tile variant: header + partial sums (150 x 28 + 26 x 150) + Kb + products
 // + types for n <= 150, m <= 3 kT.  Leaving the rest of the 256 KB to L1 keeps the set-up arrays
 // and the few spilled row constants close.
-constexpr int kSmemTiles = 150 * 1024;
+constexpr int kSmemTiles = 136 * 1024;
 
 // Shared-memory plan.  Fixed header, then per problem (n variables, m rows, nnz non-zeros of A):
 //   Linv  ~n(n+1)/2 doubles packed lower-triangular inverse Cholesky factor, rows padded to an
@@ -115,28 +116,41 @@ struct Smem {
   int M, n, m, ms, nnz, status, fail;
   unsigned short cptr[kMaxN + 2];   // start of column c in pc (padded: start = 2c mod 16)
   unsigned short clen[kMaxN + 2];   // entries of column c
-  int pc_len;
+  int pc_len, max_clen;
 };
 constexpr int kHdrBytes = (sizeof(Smem) + 15) / 16 * 16;
 
-// block-wide max of N per-thread values at once (all threads receive the results)
+// warp-wide max of a NON-NEGATIVE double: such values order like their 64-bit patterns, so two
+// 32-bit REDUX instructions (high words, then low words among the lanes holding the top high word)
+// replace five shuffle + max rounds
+__device__ __forceinline__ double warp_max_nonneg(double v) {
+  const unsigned hi = static_cast<unsigned>(__double2hiint(v)), lo = static_cast<unsigned>(__double2loint(v));
+  const unsigned mh = __reduce_max_sync(0xffffffffu, hi);
+  const unsigned ml = __reduce_max_sync(0xffffffffu, hi == mh ? lo : 0u);
+  return __hiloint2double(static_cast<int>(mh), static_cast<int>(ml));
+}
+
+// block-wide max of N per-thread NON-NEGATIVE values at once (all threads receive the results):
+// REDUX inside the warps, one shared-memory stage reduced by the first N lanes of warp 0
 template <int N>
 __device__ void block_max_n(double (&v)[N], double* red) {
+  const int nw = blockDim.x >> 5, w = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #pragma unroll
-  for (int k = 0; k < N; k++)
-    for (int o = 16; o > 0; o >>= 1) v[k] = fmax(v[k], __shfl_xor_sync(0xffffffffu, v[k], o));
+  for (int k = 0; k < N; k++) v[k] = warp_max_nonneg(v[k]);
   __syncthreads();
-  if ((threadIdx.x & 31) == 0) {
+  if (lane == 0) {
 #pragma unroll
-    for (int k = 0; k < N; k++) red[(threadIdx.x >> 5) * N + k] = v[k];
+    for (int k = 0; k < N; k++) red[w * N + k] = v[k];
+  }
+  __syncthreads();
+  if (w == 0 && lane < N) {
+    double r = red[lane];
+    for (int q = 1; q < nw; q++) r = fmax(r, red[q * N + lane]);
+    red[lane] = r;
   }
   __syncthreads();
 #pragma unroll
-  for (int k = 0; k < N; k++) {
-    double r = red[k];
-    for (int w = 1; w < kT / 32; w++) r = fmax(r, red[w * N + k]);
-    v[k] = r;
-  }
+  for (int k = 0; k < N; k++) v[k] = red[k];
 }
 __device__ double block_max(double v, double* red) {
   double a[1] = {v};
@@ -150,7 +164,7 @@ __device__ double block_sum(double v, double* red) {
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
   __syncthreads();
   double r = 0;
-  for (int w = 0; w < kT / 32; w++) r += red[w];
+  for (int w = 0; w < (blockDim.x >> 5); w++) r += red[w];
   return r;
 }
 
@@ -269,7 +283,7 @@ __device__ void factorize(Smem& S, double* __restrict__ Linv, double (&T)[NT], c
                           const int* __restrict__ csc_idx, const double* __restrict__ Pblk) {
   const int n = S.n, ms = S.ms;
   const int tid = threadIdx.x;
-  for (int e = tid; e < n * kBand; e += kT) {
+  for (int e = tid; e < n * kBand; e += blockDim.x) {
     const int c = e / kBand, d = e % kBand, r = c + d;
     double v = 0.0;
     if (r < n) {
@@ -573,13 +587,19 @@ __device__ __forceinline__ void kkt_solve(Smem& S, const double* __restrict__ Li
 // (A' u)_c = sum of the column-c segment of pc: 2 lanes per column (n <= 180 → 360 threads),
 // the lane's first entry and entry count stay in registers; fixed order, one shuffle.  Every
 // thread of the CTA calls this; the even lane of column c < n gets the sum.
-__device__ __forceinline__ double gather_col(const double* __restrict__ pq, int cnt) {
-  double s0 = 0, s1 = 0;
-  int k = 0;
-#pragma unroll 4
-  for (; k + 1 < cnt; k += 2) { s0 += pq[2 * k]; s1 += pq[2 * k + 2]; }
-  if (k < cnt) s0 += pq[2 * k];
-  double s = s0 + s1;
+// `trips` is the CTA-wide maximum entry count rounded up to 4, so the loop is uniform and fully
+// pipelined (4 independent loads per trip); entries past the lane's own count are read (they belong
+// to the next column or the padded tail of pc) and masked to +0.0.
+__device__ __forceinline__ double gather_col(const double* __restrict__ pq, int cnt, int trips) {
+  double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+  for (int k = 0; k < trips; k += 4) {
+    const double v0 = pq[2 * k], v1 = pq[2 * k + 2], v2 = pq[2 * k + 4], v3 = pq[2 * k + 6];
+    s0 += k < cnt ? v0 : 0.0;
+    s1 += k + 1 < cnt ? v1 : 0.0;
+    s2 += k + 2 < cnt ? v2 : 0.0;
+    s3 += k + 3 < cnt ? v3 : 0.0;
+  }
+  double s = (s0 + s1) + (s2 + s3);
   s += __shfl_xor_sync(0xffffffffu, s, 1);
   return s;
 }
@@ -588,9 +608,10 @@ __device__ __forceinline__ double gather_col(const double* __restrict__ pq, int 
 // thread); TILES = false: the rest (L^-1 streamed from shared memory, 4 row slots).  Both variants
 // are launched over the whole batch; each CTA returns at once if the problem is not its kind.
 template <bool TILES>
-__global__ void __launch_bounds__(kT, 1) k_qp_admm(QpDev Dv, QpParams P, const double* __restrict__ hpoly_all,
+__global__ void __launch_bounds__(TILES ? kTt : kT, 1) k_qp_admm(QpDev Dv, QpParams P, const double* __restrict__ hpoly_all,
                                                    const int* __restrict__ rows_all) {
   constexpr int kSlots = TILES ? 3 : 4;
+  constexpr int KT = TILES ? kTt : kT;   // threads of this variant
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Smem& S = *reinterpret_cast<Smem*>(smem_raw);
   const int a = blockIdx.x, tid = threadIdx.x;
@@ -598,7 +619,7 @@ __global__ void __launch_bounds__(kT, 1) k_qp_admm(QpDev Dv, QpParams P, const d
   long long clk_fact = 0;
   int n_fact = 0;
   const int M = Dv.n_pieces[a];
-  long long clk_g = 0, clk_k = 0, clk_r = 0;
+  long long clk_g = 0, clk_k = 0, clk_r = 0, clk_e = 0, clk_e1 = 0, clk_e2 = 0;
   if (M <= 0 || M > POP_MAX_PIECES) {
     if (TILES && tid == 0) { Dv.status[a] = 0; Dv.iters[a] = 0; }
     return;
@@ -637,23 +658,31 @@ __global__ void __launch_bounds__(kT, 1) k_qp_admm(QpDev Dv, QpParams P, const d
   }
   __syncthreads();
   const int n = S.n, m = S.m, ms = S.ms, nnz = S.nnz;
-  if (((n + 5) / 6 <= kTileNB && m <= 3 * kT) != TILES) return;   // the other variant's problem
+  if (((n + 5) / 6 <= kTileNB && m <= 3 * kTt) != TILES) return;   // the other variant's problem
   const int NBt = (n + 5) / 6;
   // TILES: staging rows (6 x 6NB) / partial sums (6NB x NBp) instead of the packed factor
-  const int part1_len = 6 * NBt * (((NBt + 1) & ~1) + 4), part2_len = part1_len;
-  const int linv_len = TILES ? max(36 * NBt, part1_len + part2_len) : linv_off((n + 1) & ~1);
-  const size_t dyn_bytes = sizeof(double) * (static_cast<size_t>(linv_len) + n * kBand + nnz + 16 * n + 2) + m + 16;
+  int NBpt = ((NBt + 1) & ~1) | 2;
+  if (NBpt < NBt) NBpt += 4;
+  const int part1_len = 6 * NBt * NBpt, part2_len = part1_len;
+  // TILES: [staging 36 NB | Kb 16 n] during a factorisation, [partA | partB] during the iterations
+  const int linv_len = TILES ? max(36 * NBt + n * kBand, part1_len + part2_len) : linv_off((n + 1) & ~1);
+  const size_t dyn_bytes = sizeof(double) * (static_cast<size_t>(linv_len) + (TILES ? 0 : n * kBand) + nnz + 16 * n + 2 + 128) +
+                           ((m + 15) & ~15) + 16 + (TILES ? sizeof(double) * 2 * static_cast<size_t>(m) : 0);
   if (m > kRowCap || kHdrBytes + dyn_bytes > (TILES ? kSmemTiles : kSmemBytes)) {
     if (tid == 0) { Dv.status[a] = -20; Dv.iters[a] = 0; }
     return;
   }
   double* Linv = reinterpret_cast<double*>(smem_raw + kHdrBytes);
-  double* Kb = Linv + linv_len;
-  double* pc = Kb + n * kBand;
-  signed char* type = reinterpret_cast<signed char*>(pc + nnz + 16 * n + 2);
+  double* Kb = TILES ? Linv + 36 * NBt : Linv + linv_len;
+  double* pc = TILES ? Linv + linv_len : Kb + n * kBand;
+  signed char* type = reinterpret_cast<signed char*>(pc + nnz + 16 * n + 2 + 128);
+  // tile variant: row scalings and their reciprocals stay in shared memory for
+  // the termination / rho-adaptation events (the other variant reads them from global memory)
+  double* Es = reinterpret_cast<double*>(type + ((m + 15) & ~15));
+  double* Eis = Es + m;
 
   // ---- assembly ----
-  for (int r = tid; r < m; r += kT) {
+  for (int r = tid; r < m; r += KT) {
     int col[kEll];
     double val[kEll], lo, up;
     build_row(S, r, init, goal, hpoly, rows, P, col, val, &lo, &up);
@@ -662,8 +691,9 @@ __global__ void __launch_bounds__(kT, 1) k_qp_admm(QpDev Dv, QpParams P, const d
     upv[r] = fmin(up, OSQP_INFTY);
     E[r] = 1.0;
   }
-  for (int e = tid; e < M * 225; e += kT) Pblk[e] = Dv.QM[e % 225];
-  for (int e = tid; e < linv_len; e += kT) Linv[e] = 0.0;   // row pads stay zero
+  for (int e = tid; e < M * 225; e += KT) Pblk[e] = Dv.QM[e % 225];
+  for (int e = tid; e < linv_len; e += KT) Linv[e] = 0.0;   // row pads stay zero
+  for (int e = tid; e < nnz + 16 * n + 2 + 128; e += KT) pc[e] = 0.0;   // pads are read (masked) by gather_col: keep them finite
   if (tid < kVec) { S.D[tid] = 1.0; S.x[tid] = 0.0; S.xp[tid] = 0.0; S.xt[tid] = 0.0; S.rhs[tid] = 0.0; S.tn[tid] = 0.0; S.rd[tid] = 0.0; }
   __syncthreads();
   // column index: entries of column j in ascending row order
@@ -687,6 +717,9 @@ __global__ void __launch_bounds__(kT, 1) k_qp_admm(QpDev Dv, QpParams P, const d
       csc_ptr[j + 1] = run;
     }
     S.pc_len = prun;
+    int mx = 0;
+    for (int j = 0; j < n; j++) mx = max(mx, static_cast<int>(S.clen[j]));
+    S.max_clen = mx;
     if (run != nnz || prun > nnz + 16 * n) S.fail = 2;
   }
   __syncthreads();
@@ -714,7 +747,7 @@ __global__ void __launch_bounds__(kT, 1) k_qp_admm(QpDev Dv, QpParams P, const d
       S.tn[tid] = dt;
     }
     __syncthreads();
-    for (int r = tid; r < m; r += kT) {
+    for (int r = tid; r < m; r += KT) {
       double rm = 0;
       for (int k = 0; k < kEll; k++) if (ell_col[r * kEll + k] >= 0) rm = fmax(rm, fabs(ell_val[r * kEll + k]));
       const double et = 1.0 / sqrt(limit_scaling(rm));
@@ -724,7 +757,7 @@ __global__ void __launch_bounds__(kT, 1) k_qp_admm(QpDev Dv, QpParams P, const d
       }
       E[r] *= et;
     }
-    for (int e = tid; e < M * 225; e += kT) {
+    for (int e = tid; e < M * 225; e += KT) {
       const int b = e / 225, r = (e % 225) / 15, c = e % 15;
       Pblk[e] = (S.tn[15 * b + r] * Pblk[e]) * S.tn[15 * b + c];
     }
@@ -749,12 +782,12 @@ __global__ void __launch_bounds__(kT, 1) k_qp_admm(QpDev Dv, QpParams P, const d
     }
     __syncthreads();
     const double ct = S.rhs[0];
-    for (int e = tid; e < M * 225; e += kT) Pblk[e] *= ct;
+    for (int e = tid; e < M * 225; e += KT) Pblk[e] *= ct;
     __syncthreads();
   }
   if (tid < kVec) { S.rhs[tid] = 0.0; S.tn[tid] = 0.0; }   // scratch use above; pads must be zero
   // scaled bounds and constraint types (set_rho_vec)
-  for (int r = tid; r < m; r += kT) {
+  for (int r = tid; r < m; r += KT) {
     lov[r] *= E[r];
     upv[r] *= E[r];
     signed char ty;
@@ -762,6 +795,7 @@ __global__ void __launch_bounds__(kT, 1) k_qp_admm(QpDev Dv, QpParams P, const d
     else if (upv[r] - lov[r] < RHO_TOL) ty = 1;
     else ty = 0;
     type[r] = ty;
+    if constexpr (TILES) { Es[r] = E[r]; Eis[r] = 1.0 / E[r]; }
   }
   __syncthreads();
 
@@ -786,7 +820,7 @@ __global__ void __launch_bounds__(kT, 1) k_qp_admm(QpDev Dv, QpParams P, const d
     const long long c0k = clock64();
     factorize<TILES>(S, Linv, T, ti, Kb, type, ell_col, ell_val, csc_ptr, csc_idx, Pblk);
     if constexpr (TILES) {   // the staging area becomes the partial-sum buffers: zero outside the tiles
-      for (int e = tid; e < linv_len; e += kT) Linv[e] = 0.0;
+      for (int e = tid; e < linv_len; e += KT) Linv[e] = 0.0;
       __syncthreads();
     }
     clk_fact += clock64() - c0k; n_fact++;
@@ -825,14 +859,14 @@ __global__ void __launch_bounds__(kT, 1) k_qp_admm(QpDev Dv, QpParams P, const d
 #pragma unroll
     for (int k = 0; k < 3; k++) d0[k] = ds[2 * k] | (static_cast<unsigned>(ds[2 * k + 1]) << 16);
   }
-  // slots 1.. (rows s*kT + tid): safety rows only — 3 coefficients on consecutive columns, lower
+  // slots 1.. (rows s*KT + tid): safety rows only — 3 coefficients on consecutive columns, lower
   // bound -OSQP_INFTY*E (never active), type 0
   double vs[kSlots - 1][3], zs[kSlots - 1], ys[kSlots - 1], ups[kSlots - 1];
   int bs[kSlots - 1];
   unsigned long long dss[kSlots - 1];
 #pragma unroll
   for (int s = 0; s < kSlots - 1; s++) {
-    const int r = (s + 1) * kT + tid;
+    const int r = (s + 1) * KT + tid;
     zs[s] = ys[s] = 0.0; ups[s] = OSQP_INFTY; bs[s] = 0;
     vs[s][0] = vs[s][1] = vs[s][2] = 0.0;
     dss[s] = static_cast<unsigned long long>(S.pc_len) * 0x000100010001ull;
@@ -869,7 +903,7 @@ __global__ void __launch_bounds__(kT, 1) k_qp_admm(QpDev Dv, QpParams P, const d
     put0(sel == 0 ? S.rho_v[ty0 + 1] * z0 - y0 : (sel == 1 ? y0 : dy[0]));
 #pragma unroll
     for (int s = 0; s < kSlots - 1; s++)
-      if ((s + 1) * kT < m) puts(s, sel == 0 ? S.rho_v[1] * zs[s] - ys[s] : (sel == 1 ? ys[s] : dy[s + 1]));
+      if ((s + 1) * KT < m) puts(s, sel == 0 ? S.rho_v[1] * zs[s] - ys[s] : (sel == 1 ? ys[s] : dy[s + 1]));
   };
 
   const int gc = tid >> 1;                    // this thread's gather column
@@ -877,6 +911,7 @@ __global__ void __launch_bounds__(kT, 1) k_qp_admm(QpDev Dv, QpParams P, const d
   // entries cptr[gc] + lane, +2, ... of the column: first entry and count of this lane
   const double* gq = pc + (gc < n ? S.cptr[gc] + (tid & 1) : 0);
   const int gcnt = gc < n ? (S.clen[gc] + 1 - (tid & 1)) >> 1 : 0;
+  const int gtrips = (((S.max_clen + 1) >> 1) + 3) & ~3;   // uniform trip count of gather_col
 
   // ---- ADMM ----
   int iter, status = 0;
@@ -890,9 +925,9 @@ __global__ void __launch_bounds__(kT, 1) k_qp_admm(QpDev Dv, QpParams P, const d
     double mx[kRedN];
 #pragma unroll
     for (int k = 0; k < kRedN; k++) mx[k] = 0.0;
-    auto row_norms = [&](double ax, double z, double Er) {
+    auto row_norms = [&](double ax, double z, int r) {
       const double res = ax - z;
-      const double einv = 1.0 / Er;
+      const double einv = TILES ? Eis[r] : 1.0 / E[r];
       mx[0] = fmax(mx[0], fabs(einv * res));
       mx[1] = fmax(mx[1], fabs(res));
       mx[2] = fmax(mx[2], fabs(z));
@@ -900,17 +935,19 @@ __global__ void __launch_bounds__(kT, 1) k_qp_admm(QpDev Dv, QpParams P, const d
       mx[4] = fmax(mx[4], fabs(einv * z));
       mx[5] = fmax(mx[5], fabs(einv * ax));
     };
-    if (has0) row_norms(dot0(S.x), z0, E[tid]);
+    if (has0) row_norms(dot0(S.x), z0, tid);
 #pragma unroll
     for (int s = 0; s < kSlots - 1; s++)
-      if ((s + 1) * kT + tid < m) row_norms(dots(s, S.x), zs[s], E[(s + 1) * kT + tid]);
+      if ((s + 1) * KT + tid < m) row_norms(dots(s, S.x), zs[s], (s + 1) * KT + tid);
     write_p(1, dy);
     __syncthreads();
-    const double aty = gather_col(gq, gcnt);
+    const double aty = gather_col(gq, gcnt, gtrips);
     if (gl0) {
       const int b = gc / 15, rr = gc % 15;
       double px = 0;
-      for (int k = 0; k < 15; k++) px += Pblk[b * 225 + rr * 15 + k] * S.x[15 * b + k];
+      const double* Pb = Pblk + b * 225 + rr * 15;
+#pragma unroll
+      for (int k = 0; k < 15; k++) px += Pb[k] * S.x[15 * b + k];
       const double res = (0.0 + px) + aty;
       const double dinv = 1.0 / S.D[gc];
       mx[6] = fabs(dinv * res); mx[7] = fabs(res); mx[8] = fabs(aty); mx[9] = fabs(px);
@@ -936,15 +973,15 @@ __global__ void __launch_bounds__(kT, 1) k_qp_admm(QpDev Dv, QpParams P, const d
         d = fmax(d, 0.0);
       }
       dy[0] = d;
-      v_nd = fabs(E[tid] * d);
+      v_nd = fabs((TILES ? Es[tid] : E[tid]) * d);
       v_lhs = up0 * fmax(d, 0.0) + lo0 * fmin(d, 0.0);
     }
 #pragma unroll
     for (int s = 0; s < kSlots - 1; s++)
-      if ((s + 1) * kT + tid < m) {   // up finite, lo = -OSQP_INFTY*E: project on d >= 0
+      if ((s + 1) * KT + tid < m) {   // up finite, lo = -OSQP_INFTY*E: project on d >= 0
         const double d = fmax(dy[s + 1], 0.0);
         dy[s + 1] = d;
-        v_nd = fmax(v_nd, fabs(E[(s + 1) * kT + tid] * d));
+        v_nd = fmax(v_nd, fabs((TILES ? Es[(s + 1) * KT + tid] : E[(s + 1) * KT + tid]) * d));
         v_lhs += ups[s] * d;
       }
     const double nd = block_max(v_nd, S.red);
@@ -953,7 +990,7 @@ __global__ void __launch_bounds__(kT, 1) k_qp_admm(QpDev Dv, QpParams P, const d
       __syncthreads();
       write_p(2, dy);
       __syncthreads();
-      const double s = gather_col(gq, gcnt);
+      const double s = gather_col(gq, gcnt, gtrips);
       const double v = gl0 ? fabs((1.0 / S.D[gc]) * s) : 0.0;
       const double nrm = block_max(v, S.red);
       return nrm < eps * nd;
@@ -986,7 +1023,7 @@ __global__ void __launch_bounds__(kT, 1) k_qp_admm(QpDev Dv, QpParams P, const d
 #endif
     // x_prev <- x ; rhs = sigma x_prev - q + A' w with w = rho z - y
     {
-      const double s = gather_col(gq, gcnt);
+      const double s = gather_col(gq, gcnt, gtrips);
       if (gl0) {
         const double xv = S.x[gc];
         S.xp[gc] = xv;
@@ -1010,7 +1047,7 @@ __global__ void __launch_bounds__(kT, 1) k_qp_admm(QpDev Dv, QpParams P, const d
       double zt[kSlots];
       zt[0] = dot0(S.xt);
 #pragma unroll
-      for (int s = 0; s < kSlots - 1; s++) zt[s + 1] = (s + 1) * kT < m ? dots(s, S.xt) : 0.0;
+      for (int s = 0; s < kSlots - 1; s++) zt[s + 1] = (s + 1) * KT < m ? dots(s, S.xt) : 0.0;
       {
         const double mix = ALPHA * zt[0] + (1.0 - ALPHA) * z0;
         const double v = mix + rinv * y0;
@@ -1021,7 +1058,7 @@ __global__ void __launch_bounds__(kT, 1) k_qp_admm(QpDev Dv, QpParams P, const d
       }
 #pragma unroll
       for (int s = 0; s < kSlots - 1; s++) {
-        if ((s + 1) * kT >= m) continue;   // uniform: no row of this problem lives in the slot
+        if ((s + 1) * KT >= m) continue;   // uniform: no row of this problem lives in the slot
         const double mix = ALPHA * zt[s + 1] + (1.0 - ALPHA) * zs[s];
         const double v = mix + rinv_in * ys[s];
         const double zn = fmin(v, ups[s]);
@@ -1050,13 +1087,23 @@ __global__ void __launch_bounds__(kT, 1) k_qp_admm(QpDev Dv, QpParams P, const d
     double dy[kSlots] = {0};   // delta_y of this iteration (is_primal_infeasible)
     admm_iter(dy);
     iter++;
+#ifdef POP_QP_PHASE_PROF
+    const long long te0 = clock64();
+    long long te1 = te0, te2 = te0;
+#endif
     const bool last = iter >= P.max_iter;
     can_check = P.check_interval && (iter % P.check_interval == 0);
     bool info = false;
     if (can_check || last) {
       update_info(dy);
+#ifdef POP_QP_PHASE_PROF
+      te1 = clock64();
+#endif
       info = true;
       if (check_termination(false, dy)) break;
+#ifdef POP_QP_PHASE_PROF
+      te2 = clock64();
+#endif
       if (last) {   // osqp_solve's closing test with relaxed tolerances, else max-iter
         if (!check_termination(true, dy)) status = -2;
         break;
@@ -1086,6 +1133,9 @@ __global__ void __launch_bounds__(kT, 1) k_qp_admm(QpDev Dv, QpParams P, const d
       write_p(0, dy);
       __syncthreads();
     }
+#ifdef POP_QP_PHASE_PROF
+    clk_e += clock64() - te0; clk_e1 += te1 - te0; clk_e2 += te2 - te1;
+#endif
   }
   __syncthreads();
   if (tid < n) Dv.cpts[static_cast<size_t>(a) * POP_MAX_PIECES * 15 + tid] = S.D[tid] * S.x[tid];
@@ -1098,6 +1148,7 @@ __global__ void __launch_bounds__(kT, 1) k_qp_admm(QpDev Dv, QpParams P, const d
     Dv.prof[a * 8 + 2] = now - clk_loop;
     Dv.prof[a * 8 + 3] = n_fact;
     Dv.prof[a * 8 + 4] = clk_g; Dv.prof[a * 8 + 5] = clk_k; Dv.prof[a * 8 + 6] = clk_r;
+    Dv.prof[a * 8 + 7] = clk_e; Dv.prof[a * 8 + 0] = clk_e1; Dv.prof[a * 8 + 1] = clk_e2;   // PHASE_PROF builds only
   }
 #undef COL0
 #undef DST0
@@ -1181,7 +1232,7 @@ int popk_qp_run(pop_handle* h, int n_agents, const double* d_hpoly, const int* d
   P.eps_abs = c.osqp_eps_abs; P.eps_rel = c.osqp_eps_rel; P.eps_prim_inf = 1e-4;
   P.vmax = vmax; P.amax = amax;
   pop_prof_begin(h, POP_STAGE_QP);
-  k_qp_admm<true><<<n_agents, kT, kSmemTiles, h->stream>>>(*d, P, d_hpoly, d_rows);
+  k_qp_admm<true><<<n_agents, kTt, kSmemTiles, h->stream>>>(*d, P, d_hpoly, d_rows);
   POP_LAUNCH_CHECK(h);
   k_qp_admm<false><<<n_agents, kT, kSmemBytes, h->stream>>>(*d, P, d_hpoly, d_rows);
   POP_LAUNCH_CHECK(h);

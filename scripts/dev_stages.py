@@ -33,5 +33,5 @@ print("qp cycles per agent: iters | setup | factor total | loop | nfact | loop/i
 for a in order[-10:]:
     it = max(1, int(iters[a]))
     print(int(iters[a]), int(prof[a, 0]), int(prof[a, 1]), int(prof[a, 2]), int(prof[a, 3]), int(prof[a, 2] / it),
-          int(prof[a, 4] / it), int(prof[a, 5] / it), int(prof[a, 6] / it))
+          int(prof[a, 4] / it), int(prof[a, 5] / it), int(prof[a, 6] / it), '| events total', int(prof[a, 7]), 'per event', int(prof[a, 7] / max(1, it // 25)), 'update_info', int(prof[a, 0] / max(1, it // 25)), 'check', int(prof[a, 1] / max(1, it // 25)))
 print("median setup", np.median(prof[:, 0]), "median cycles per factorisation", np.median(prof[:, 1] / np.maximum(prof[:, 3], 1)))

@@ -280,7 +280,10 @@ int pop_traj_buffers(pop_handle* h, void** send_dev, void** recv_dev);
 /* ---- measurement ------------------------------------------------------------------------ */
 enum { POP_STAGE_VOXEL_UPDATE = 0, POP_STAGE_PEERS = 1, POP_STAGE_ASTAR = 2, POP_STAGE_CORRIDOR = 3,
        POP_STAGE_QP = 4, POP_STAGE_SEPARATION = 5, POP_STAGE_COUNT = 8 };
-/* Enable CUDA-event bracketing of every stage on the handle's stream. */
+/* CUDA-event bracketing of the stages on the handle's stream.  on = 1: every stage (the planning
+ * stages then run one after the other over the whole batch, so the per-stage times mean something);
+ * on = 2: the map stages only (voxel update, peers) — the planning stages stay pipelined over agent
+ * groups on side streams, as they are with profiling off; on = 0: off. */
 int pop_profile_enable(pop_handle* h, int on);
 /* Accumulated milliseconds and launch counts per stage since the last reset. */
 int pop_profile_read(pop_handle* h, float* ms /*[POP_STAGE_COUNT]*/,

@@ -55,6 +55,11 @@ CYL_DTYPE = np.dtype([("type", "<i4"), ("_pad", "<i4"), ("x", "<f8"), ("y", "<f8
 assert CYL_DTYPE.itemsize == C.sizeof(PopCylinder)
 
 
+# the planning stages are pipelined over up to 32 side streams: ask for that many hardware work
+# queues before any CUDA context exists (a value chosen by the application wins)
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
+
 class PopConfig(C.Structure):
     _fields_ = [
         ("abi_version", C.c_int32),

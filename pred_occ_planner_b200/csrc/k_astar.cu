@@ -235,7 +235,7 @@ struct Prim {  // per-primitive scratch in shared memory
 template <typename C>
 __global__ void __launch_bounds__(kThreads) k_astar(PopGeom g, AstarParams P, AstarDev D,
                                                     const uint8_t* __restrict__ grid,
-                                                    const float* __restrict__ poses) {
+                                                    const float* __restrict__ poses, int a0) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* f = reinterpret_cast<double*>(smem_raw);            // [cap]
   int* heap = reinterpret_cast<int*>(f + P.cap);              // [cap]
@@ -247,7 +247,7 @@ __global__ void __launch_bounds__(kThreads) k_astar(PopGeom g, AstarParams P, As
   __shared__ unsigned s_gen;
   __shared__ int s_wrap;
 
-  const int a = blockIdx.x;
+  const int a = blockIdx.x + a0;
   const int tid = threadIdx.x;
   const uint8_t* ag = grid + a * g.agent_stride;
   const float* pose = poses + 3 * a;
@@ -626,7 +626,7 @@ void popk_astar_free(pop_handle* h) {
 }
 
 // device-resident search: inputs already in astar->d_start/d_goal/d_tstart
-int popk_astar_run(pop_handle* h) {
+int popk_astar_run(pop_handle* h, cudaStream_t st, int a0, int na) {
   AstarDev* d = h->astar;
   const pop_config& c = h->cfg;
   AstarParams P;
@@ -641,9 +641,9 @@ int popk_astar_run(pop_handle* h) {
   const size_t smem = static_cast<size_t>(d->cap) * 12 + 16;
   pop_prof_begin(h, POP_STAGE_ASTAR);
   if (c.cell_dtype == POP_CELL_U8)
-    k_astar<uint8_t><<<d->n_agents, kThreads, smem, h->stream>>>(h->geom, P, *d, h->d_grid, h->d_poses);
+    k_astar<uint8_t><<<na, kThreads, smem, st>>>(h->geom, P, *d, h->d_grid, h->d_poses, a0);
   else
-    k_astar<float><<<d->n_agents, kThreads, smem, h->stream>>>(h->geom, P, *d, h->d_grid, h->d_poses);
+    k_astar<float><<<na, kThreads, smem, st>>>(h->geom, P, *d, h->d_grid, h->d_poses, a0);
   POP_LAUNCH_CHECK(h);
   pop_prof_end(h, POP_STAGE_ASTAR, 1);
   return POP_OK;
@@ -668,7 +668,7 @@ extern "C" int pop_astar_search_batch(pop_handle* h, const double* start, const 
   POP_CUDA(h, cudaMemcpyAsync(d->d_start, start, sizeof(double) * 9 * n, cudaMemcpyHostToDevice, h->stream));
   POP_CUDA(h, cudaMemcpyAsync(d->d_goal, goal, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, h->stream));
   POP_CUDA(h, cudaMemcpyAsync(d->d_tstart, t_start, sizeof(double) * n, cudaMemcpyHostToDevice, h->stream));
-  rc = popk_astar_run(h);
+  rc = popk_astar_run(h, h->stream, 0, h->astar->n_agents);
   if (rc) return rc;
   POP_CUDA(h, cudaMemcpyAsync(out_ret, d->d_ret, sizeof(int) * n, cudaMemcpyDeviceToHost, h->stream));
   POP_CUDA(h, cudaMemcpyAsync(out_len, d->d_len, sizeof(int) * n, cudaMemcpyDeviceToHost, h->stream));

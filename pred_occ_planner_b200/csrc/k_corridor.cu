@@ -74,11 +74,12 @@ __global__ void __launch_bounds__(256) k_corridor_points(PopGeom g, const uint8_
                                                          const double* __restrict__ start,
                                                          const double* __restrict__ tst, double tau,
                                                          double init_range, SegInfo* __restrict__ segs,
-                                                         int* __restrict__ pts, int cap) {
+                                                         int* __restrict__ pts, int cap, int seg0) {
   __shared__ SegInfo s;
   __shared__ int warp_sums[8];
   __shared__ int total_s;
-  const int a = blockIdx.x / POP_MAX_PIECES, i = blockIdx.x % POP_MAX_PIECES;
+  const int bid = blockIdx.x + seg0;   // global segment index
+  const int a = bid / POP_MAX_PIECES, i = bid % POP_MAX_PIECES;
   const int n = len[a];
   const float* pose = poses + 3 * a;
   if (threadIdx.x == 0) {
@@ -118,11 +119,11 @@ __global__ void __launch_bounds__(256) k_corridor_points(PopGeom g, const uint8_
   }
   __syncthreads();
   if (!s.active) {
-    if (threadIdx.x == 0) segs[blockIdx.x] = s;
+    if (threadIdx.x == 0) segs[bid] = s;
     return;
   }
   const uint8_t* ag = grid + a * g.agent_stride;
-  int* out = pts + static_cast<size_t>(blockIdx.x) * cap;
+  int* out = pts + static_cast<size_t>(bid) * cap;
   const int bx = s.hx - s.lx + 1, by = s.hy - s.ly + 1, bz = s.hz - s.lz + 1;
   const int nvox = (bx > 0 && by > 0 && bz > 0) ? bx * by * bz : 0;
   const int per = (nvox + blockDim.x - 1) / blockDim.x;
@@ -147,7 +148,7 @@ __global__ void __launch_bounds__(256) k_corridor_points(PopGeom g, const uint8_
   for (int v = v0; v < v1; v++) base += seg_count_or_emit<C>(g, ag, s, v, out, base, cap);
   if (threadIdx.x == 0) {
     s.n_pts = total_s;
-    segs[blockIdx.x] = s;
+    segs[bid] = s;
   }
 }
 
@@ -496,11 +497,11 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_corridor_firi(
     PopGeom g, const float* __restrict__ poses, const SegInfo* __restrict__ segs, const int* __restrict__ pts,
     int cap, double shrink_size, int id_base, double* __restrict__ distRs_all, double* __restrict__ tang_all,
     uint8_t* __restrict__ flags_all, double* __restrict__ scr_all, int* __restrict__ scri_all,
-    double* __restrict__ out_h, int* __restrict__ out_rows, int* __restrict__ out_valid, int n_segs,
+    double* __restrict__ out_h, int* __restrict__ out_rows, int* __restrict__ out_valid, int seg0, int n_segs,
     int* __restrict__ err_flag) {
   __shared__ FiriWarp sw[kWarpsPerBlock];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int seg = blockIdx.x * kWarpsPerBlock + warp;
+  const int seg = seg0 + blockIdx.x * kWarpsPerBlock + warp;   // n_segs = end of this launch's range
   if (seg >= n_segs) return;
   const SegInfo& S = segs[seg];
   const int a = seg / POP_MAX_PIECES, si = seg % POP_MAX_PIECES;
@@ -727,8 +728,8 @@ __global__ void k_corridor_finish(const double* __restrict__ path, const int* __
                                   const double* __restrict__ start, int id_base, const double* __restrict__ seg_h,
                                   const int* __restrict__ seg_rows, const int* __restrict__ seg_valid,
                                   double* __restrict__ scr_all, int* __restrict__ scri_all,
-                                  int* __restrict__ out_npoly, double* __restrict__ out_goal, int n_agents) {
-  const int a = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+                                  int* __restrict__ out_npoly, double* __restrict__ out_goal, int a0, int n_agents) {
+  const int a = a0 + blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);   // n_agents = end of the range
   if (a >= n_agents || (threadIdx.x & 31) != 0) return;
   // reuse segment 0's scratch of this agent: holds up to kLpRows rows of LP workspace
   double* scr = scr_all + static_cast<size_t>(a) * POP_MAX_PIECES * kScrDoubles;
@@ -872,27 +873,28 @@ void popk_corridor_free(pop_handle* h) {
 }
 
 // path/len/start device-resident; traj_start_time in corridor->tst
-int popk_corridor_run(pop_handle* h, const double* d_path, const int* d_len, const double* d_start) {
+int popk_corridor_run(pop_handle* h, const double* d_path, const int* d_len, const double* d_start, cudaStream_t st,
+                      int a0, int na) {
   CorridorDev* d = h->corridor;
   const pop_config& c = h->cfg;
-  const int ns = d->n_agents * POP_MAX_PIECES;
+  const int ns = na * POP_MAX_PIECES, seg0 = a0 * POP_MAX_PIECES;
   pop_prof_begin(h, POP_STAGE_CORRIDOR);
   if (c.cell_dtype == POP_CELL_U8)
-    k_corridor_points<uint8_t><<<ns, 256, 0, h->stream>>>(h->geom, h->d_grid, h->d_poses, h->t_map, d_path, d_len,
+    k_corridor_points<uint8_t><<<ns, 256, 0, st>>>(h->geom, h->d_grid, h->d_poses, h->t_map, d_path, d_len,
                                                           d_start, d->tst, c.corridor_tau, c.init_range, d->segs,
-                                                          d->pts, d->cap);
+                                                          d->pts, d->cap, seg0);
   else
-    k_corridor_points<float><<<ns, 256, 0, h->stream>>>(h->geom, h->d_grid, h->d_poses, h->t_map, d_path, d_len,
+    k_corridor_points<float><<<ns, 256, 0, st>>>(h->geom, h->d_grid, h->d_poses, h->t_map, d_path, d_len,
                                                         d_start, d->tst, c.corridor_tau, c.init_range, d->segs,
-                                                        d->pts, d->cap);
+                                                        d->pts, d->cap, seg0);
   POP_LAUNCH_CHECK(h);
-  k_corridor_firi<<<(ns + kWarpsPerBlock - 1) / kWarpsPerBlock, kWarpsPerBlock * 32, 0, h->stream>>>(
+  k_corridor_firi<<<(ns + kWarpsPerBlock - 1) / kWarpsPerBlock, kWarpsPerBlock * 32, 0, st>>>(
       h->geom, h->d_poses, d->segs, d->pts, d->cap, c.shrink_size, c.agent_id_base, d->distRs, d->tang, d->flags,
-      d->scr, d->scri, d->seg_h, d->seg_rows, d->seg_valid, ns, d->err);
+      d->scr, d->scri, d->seg_h, d->seg_rows, d->seg_valid, seg0, seg0 + ns, d->err);
   POP_LAUNCH_CHECK(h);
-  k_corridor_finish<<<(d->n_agents + 3) / 4, 128, 0, h->stream>>>(d_path, d_len, d_start, c.agent_id_base, d->seg_h,
+  k_corridor_finish<<<(na + 3) / 4, 128, 0, st>>>(d_path, d_len, d_start, c.agent_id_base, d->seg_h,
                                                                  d->seg_rows, d->seg_valid, d->scr, d->scri, d->npoly,
-                                                                 d->goal, d->n_agents);
+                                                                 d->goal, a0, a0 + na);
   POP_LAUNCH_CHECK(h);
   pop_prof_end(h, POP_STAGE_CORRIDOR, 3);
   return POP_OK;
@@ -938,7 +940,7 @@ extern "C" int pop_corridor_batch(pop_handle* h, const double* path, const int32
   POP_CUDA(h, cudaMemcpyAsync(d_start, start, bstart, cudaMemcpyHostToDevice, h->stream));
   POP_CUDA(h, cudaMemcpyAsync(d_len, len, blen, cudaMemcpyHostToDevice, h->stream));
   POP_CUDA(h, cudaMemcpyAsync(d->tst, traj_start_time, sizeof(double) * n, cudaMemcpyHostToDevice, h->stream));
-  rc = popk_corridor_run(h, d_path, d_len, d_start);
+  rc = popk_corridor_run(h, d_path, d_len, d_start, h->stream, 0, h->corridor->n_agents);
   if (rc) return rc;
   const size_t ns = static_cast<size_t>(n) * POP_MAX_PIECES;
   POP_CUDA(h, cudaMemcpyAsync(out_hpoly, d->seg_h, ns * POP_MAX_FACES * 4 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));

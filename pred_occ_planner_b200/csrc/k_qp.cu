@@ -609,12 +609,12 @@ __device__ __forceinline__ double gather_col(const double* __restrict__ pq, int 
 // are launched over the whole batch; each CTA returns at once if the problem is not its kind.
 template <bool TILES>
 __global__ void __launch_bounds__(TILES ? kTt : kT, 1) k_qp_admm(QpDev Dv, QpParams P, const double* __restrict__ hpoly_all,
-                                                   const int* __restrict__ rows_all) {
+                                                                 const int* __restrict__ rows_all, int a0) {
   constexpr int kSlots = TILES ? 3 : 4;
   constexpr int KT = TILES ? kTt : kT;   // threads of this variant
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Smem& S = *reinterpret_cast<Smem*>(smem_raw);
-  const int a = blockIdx.x, tid = threadIdx.x;
+  const int a = blockIdx.x + a0, tid = threadIdx.x;
   const long long clk0 = clock64();
   long long clk_fact = 0;
   int n_fact = 0;
@@ -1223,7 +1223,9 @@ void popk_qp_free(pop_handle* h) {
 }
 
 // inputs resident in qp->{n_pieces, init, goal, dur}; corridors at d_hpoly / d_rows
-int popk_qp_run(pop_handle* h, int n_agents, const double* d_hpoly, const int* d_rows, double vmax, double amax) {
+int popk_qp_run(pop_handle* h, int n_agents, const double* d_hpoly, const int* d_rows, double vmax, double amax,
+                cudaStream_t st, int a0) {
+  if (!st) st = h->stream;
   QpDev* d = h->qp;
   const pop_config& c = h->cfg;
   QpParams P;
@@ -1232,10 +1234,13 @@ int popk_qp_run(pop_handle* h, int n_agents, const double* d_hpoly, const int* d
   P.eps_abs = c.osqp_eps_abs; P.eps_rel = c.osqp_eps_rel; P.eps_prim_inf = 1e-4;
   P.vmax = vmax; P.amax = amax;
   pop_prof_begin(h, POP_STAGE_QP);
-  k_qp_admm<true><<<n_agents, kTt, kSmemTiles, h->stream>>>(*d, P, d_hpoly, d_rows);
+  k_qp_admm<true><<<n_agents, kTt, kSmemTiles, st>>>(*d, P, d_hpoly, d_rows, a0);
   POP_LAUNCH_CHECK(h);
-  k_qp_admm<false><<<n_agents, kT, kSmemBytes, h->stream>>>(*d, P, d_hpoly, d_rows);
-  POP_LAUNCH_CHECK(h);
+  static const bool skip_big = getenv("POP_QP_SKIP_BIG") != nullptr;   // experiment switch
+  if (!skip_big) {
+    k_qp_admm<false><<<n_agents, kT, kSmemBytes, st>>>(*d, P, d_hpoly, d_rows, a0);
+    POP_LAUNCH_CHECK(h);
+  }
   pop_prof_end(h, POP_STAGE_QP, 2);
   return POP_OK;
 }

@@ -3,6 +3,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "pop_internal.h"
@@ -18,6 +19,15 @@ int pop_fail(pop_handle* h, int code, const char* fmt, ...) {
 }
 
 static thread_local std::string g_create_err;
+
+// The planning stages run as per-group chains on up to 32 side streams (k_cycle.cu); ask the driver for
+// that many hardware work queues unless the host application already chose a value.  Takes effect
+// only if libpop.so is loaded before the CUDA context is created.
+namespace {
+struct ConnEnv {
+  ConnEnv() { setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0); }
+} g_conn_env;
+}  // namespace
 
 int pop_ensure_scratch(pop_handle* h, size_t dev_bytes, size_t host_bytes) {
   if (dev_bytes > h->d_scratch_bytes) {
@@ -51,7 +61,7 @@ static cudaEvent_t prof_event(pop_handle* h) {
 static thread_local cudaEvent_t g_open_begin[POP_STAGE_COUNT];
 
 void pop_prof_begin(pop_handle* h, int stage) {
-  if (!h->prof.enabled) return;
+  if (!h->prof.enabled || (h->prof.map_only && stage > POP_STAGE_PEERS)) return;
   cudaEvent_t e = prof_event(h);
   cudaEventRecord(e, h->stream);
   g_open_begin[stage] = e;
@@ -59,7 +69,7 @@ void pop_prof_begin(pop_handle* h, int stage) {
 void pop_prof_end(pop_handle* h, int stage, int n_launches) {
   h->n_launches += n_launches;
   h->prof.launches[stage] += n_launches;
-  if (!h->prof.enabled) return;
+  if (!h->prof.enabled || (h->prof.map_only && stage > POP_STAGE_PEERS)) return;
   cudaEvent_t e = prof_event(h);
   cudaEventRecord(e, h->stream);
   h->prof.pending.push_back({stage, {g_open_begin[stage], e}});
@@ -191,6 +201,10 @@ int pop_destroy(pop_handle* h) {
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   popk_vox_free(h);
+  for (cudaStream_t s : h->side) cudaStreamDestroy(s);
+  for (cudaEvent_t e : h->side_done) cudaEventDestroy(e);
+  if (h->fork_ev) cudaEventDestroy(h->fork_ev);
+  h->side.clear(); h->side_done.clear(); h->fork_ev = nullptr;
   void* ptrs[] = {h->d_grid, h->d_cloud, h->d_cyl, h->d_poses, h->d_occ_list, h->d_occ_count, h->d_body,
                   h->d_body_count, h->d_traj_all, h->d_traj_send, h->d_peer_pos, h->d_peer_valid,
                   h->d_scratch};
@@ -380,6 +394,7 @@ int pop_map_download(pop_handle* h, int agent, float* out) {
 int pop_profile_enable(pop_handle* h, int on) {
   if (!h) return POP_E_INVALID;
   h->prof.enabled = on != 0;
+  h->prof.map_only = on == 2;
   return POP_OK;
 }
 

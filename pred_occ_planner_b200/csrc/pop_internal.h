@@ -32,6 +32,7 @@ struct PopCylDev {  // pop_cylinder reduced to what the voxel update reads
 
 struct PopProfile {
   bool enabled = false;
+  bool map_only = false;   // time the map stages only (the planning stages then run pipelined over agent groups)
   float ms[POP_STAGE_COUNT] = {0};
   int64_t launches[POP_STAGE_COUNT] = {0};
   std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> pending;
@@ -83,6 +84,10 @@ struct pop_handle {
   QpDev* qp = nullptr;
   PlanDev* plan = nullptr;
   PopProfile prof;
+  // agent-group pipelining of the planning stages (k_cycle.cu)
+  std::vector<cudaStream_t> side;
+  std::vector<cudaEvent_t> side_done;
+  cudaEvent_t fork_ev = nullptr;
 };
 
 // error helpers -----------------------------------------------------------------------------
@@ -116,7 +121,7 @@ int popk_download(pop_handle* h, int agent, float* d_out);
 // planning stage launchers -------------------------------------------------------------------------
 int popk_astar_alloc(pop_handle* h);
 void popk_astar_free(pop_handle* h);
-int popk_astar_run(pop_handle* h);   // inputs resident in the A* device buffers
+int popk_astar_run(pop_handle* h, cudaStream_t st, int a0, int na);   // agents [a0, a0+na); inputs resident
 double* popk_astar_path_dev(pop_handle* h);
 int* popk_astar_len_dev(pop_handle* h);
 int* popk_astar_ret_dev(pop_handle* h);
@@ -126,7 +131,8 @@ double* popk_astar_tstart_dev(pop_handle* h);
 
 int popk_corridor_alloc(pop_handle* h);
 void popk_corridor_free(pop_handle* h);
-int popk_corridor_run(pop_handle* h, const double* d_path, const int* d_len, const double* d_start);
+int popk_corridor_run(pop_handle* h, const double* d_path, const int* d_len, const double* d_start, cudaStream_t st,
+                      int a0, int na);
 int popk_corridor_check_err(pop_handle* h);
 double* popk_corridor_hpoly_dev(pop_handle* h);
 int* popk_corridor_rows_dev(pop_handle* h);
@@ -136,7 +142,8 @@ double* popk_corridor_tst_dev(pop_handle* h);
 
 int popk_qp_alloc(pop_handle* h, int n_agents);
 void popk_qp_free(pop_handle* h);
-int popk_qp_run(pop_handle* h, int n_agents, const double* d_hpoly, const int* d_rows, double vmax, double amax);
+int popk_qp_run(pop_handle* h, int n_agents, const double* d_hpoly, const int* d_rows, double vmax, double amax,
+                cudaStream_t st = nullptr, int a0 = 0);
 int* popk_qp_npieces_dev(pop_handle* h);
 double* popk_qp_init_dev(pop_handle* h);
 double* popk_qp_goal_dev(pop_handle* h);

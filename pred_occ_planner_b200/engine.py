@@ -178,7 +178,9 @@ class PopEngine:
         return s.value, r.value
 
     # -- measurement -----------------------------------------------------------------------------
-    def profile_enable(self, on: bool = True):
+    def profile_enable(self, on: bool | int = True):
+        """0 off, 1 every stage (planning stages serialised over the batch), 2 map stages only (planning
+        stages stay pipelined over agent groups)."""
         self._check(self.lib.pop_profile_enable(self._h, int(on)))
 
     def profile_read(self, reset: bool = True):

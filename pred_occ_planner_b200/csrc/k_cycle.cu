@@ -17,7 +17,8 @@ constexpr int kSepInts = poplp::work_ints(kSepRows);
 constexpr int kSepWarps = 148 * 8;
 
 // one warp (lane 0) per (ego, peer) pair, grid-stride over pairs
-__global__ void __launch_bounds__(128) k_separate(int n_local, int n_total, int id_base, double t0,
+// Agents [a0, a0 + n_local) against every peer; warp w of this launch works in workspace slot w0 + w.
+__global__ void __launch_bounds__(128) k_separate(int a0, int w0, int n_local, int n_total, int id_base, double t0,
                                                   const int* __restrict__ n_pieces, const int* __restrict__ qp_status,
                                                   const double* __restrict__ cpts,
                                                   const pop_traj_record* __restrict__ trajs, double* __restrict__ wd,
@@ -25,12 +26,12 @@ __global__ void __launch_bounds__(128) k_separate(int n_local, int n_total, int 
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if ((threadIdx.x & 31) != 0) return;
   const int total_warps = (gridDim.x * blockDim.x) >> 5;
-  double* rowsM = wd + static_cast<size_t>(warp) * kSepDoubles;
+  double* rowsM = wd + static_cast<size_t>(w0 + warp) * kSepDoubles;
   double* rhs = rowsM + 4 * kSepRows;
   double* lpw = rhs + kSepRows;
-  int* lpi = wi + static_cast<size_t>(warp) * kSepInts;
+  int* lpi = wi + static_cast<size_t>(w0 + warp) * kSepInts;
   for (long long pair = warp; pair < static_cast<long long>(n_local) * n_total; pair += total_warps) {
-    const int a = static_cast<int>(pair / n_total), i = static_cast<int>(pair % n_total);
+    const int a = a0 + static_cast<int>(pair / n_total), i = static_cast<int>(pair % n_total);
     if (i == id_base + a) continue;
     const int M = n_pieces[a];
     const int st = qp_status[a];
@@ -96,11 +97,11 @@ __global__ void k_prepare_qp(int a0, int n, double tau, const double* __restrict
   for (int k = 0; k < POP_MAX_PIECES; k++) dur[a * POP_MAX_PIECES + k] = k < M ? tau : 0.0;
 }
 
-__global__ void k_finalize(int n, int id_base, double t_plan, double tau, const int* __restrict__ ret,
+__global__ void k_finalize(int a0, int n, int id_base, double t_plan, double tau, const int* __restrict__ ret,
                            const int* __restrict__ npoly, const int* __restrict__ qp_status,
                            const int* __restrict__ safe, const double* __restrict__ cpts,
                            int* __restrict__ status, pop_traj_record* __restrict__ send, int* __restrict__ traj_ids) {
-  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  const int a = a0 + blockIdx.x * blockDim.x + threadIdx.x;   // n = end of the range
   if (a >= n) return;
   int st = POP_REPLAN_OK;
   if (ret[a] == POP_ASTAR_NO_PATH || ret[a] == POP_ASTAR_SEARCH_ERR) st = POP_REPLAN_FAIL_ASTAR;
@@ -166,18 +167,21 @@ void pop_plan_free(pop_handle* h) {
   h->plan = nullptr;
 }
 
-static int run_separation(pop_handle* h, double t_now, const int* d_np, const int* d_st, const double* d_cpts) {
+// separation check of agents [a0, a0+na) on stream st with the workspace slots [w0, w0+nw)
+static int run_separation(pop_handle* h, double t_now, const int* d_np, const int* d_st, const double* d_cpts,
+                          cudaStream_t st, int a0, int na, int w0, int nw, bool timed) {
   PlanDev* d = h->plan;
-  pop_prof_begin(h, POP_STAGE_SEPARATION);
+  if (timed) pop_prof_begin(h, POP_STAGE_SEPARATION);
   int launches = 0;
   if (h->have_traj && h->cfg.n_agents_total > 1) {
-    k_separate<<<kSepWarps / 4, 128, 0, h->stream>>>(h->cfg.n_agents_local, h->cfg.n_agents_total, h->cfg.agent_id_base,
-                                                     t_now, d_np, d_st, d_cpts, h->d_traj_all, d->sep_wd, d->sep_wi,
-                                                     d->safe);
+    const int blocks = nw / 4 > 0 ? nw / 4 : 1;
+    k_separate<<<blocks, 128, 0, st>>>(a0, w0, na, h->cfg.n_agents_total, h->cfg.agent_id_base, t_now, d_np, d_st,
+                                       d_cpts, h->d_traj_all, d->sep_wd, d->sep_wi, d->safe);
     POP_LAUNCH_CHECK(h);
     launches = 1;
   }
-  pop_prof_end(h, POP_STAGE_SEPARATION, launches);
+  if (timed) pop_prof_end(h, POP_STAGE_SEPARATION, launches);
+  else h->n_launches += launches;
   return POP_OK;
 }
 
@@ -249,17 +253,20 @@ static int cycle_enqueue(pop_handle* h, double t_map, double t_plan) {
                                                   popk_qp_init_dev(h), popk_qp_goal_dev(h), popk_qp_dur_dev(h));
     POP_LAUNCH_CHECK(h);
     if ((rc = popk_qp_run(h, na, popk_corridor_hpoly_dev(h), popk_corridor_rows_dev(h), c.opt_max_vel, c.opt_max_acc, st, a0))) return rc;
+    const int wper = (kSepWarps / n_groups) & ~3;   // workspace slots of this group (multiple of 4 warps)
+    if ((rc = run_separation(h, t_plan, popk_qp_npieces_dev(h), popk_qp_status_dev(h), popk_qp_cpts_dev(h), st, a0, na,
+                             gi * wper, wper, n_groups == 1))) return rc;
+    k_finalize<<<(na + 127) / 128, 128, 0, st>>>(a0, a0 + na, c.agent_id_base, t_plan, c.corridor_tau, popk_astar_ret_dev(h),
+                                                popk_qp_npieces_dev(h), popk_qp_status_dev(h), d->safe,
+                                                popk_qp_cpts_dev(h), d->status, h->d_traj_send, d->traj_ids);
+    POP_LAUNCH_CHECK(h);
+    h->n_launches += 2;   // k_prepare_qp + k_finalize
     if (n_groups > 1) {
       POP_CUDA(h, cudaEventRecord(h->side_done[gi], st));
       POP_CUDA(h, cudaStreamWaitEvent(h->stream, h->side_done[gi], 0));
     }
   }
-  if ((rc = run_separation(h, t_plan, popk_qp_npieces_dev(h), popk_qp_status_dev(h), popk_qp_cpts_dev(h)))) return rc;
-  k_finalize<<<(nl + 127) / 128, 128, 0, h->stream>>>(nl, c.agent_id_base, t_plan, c.corridor_tau, popk_astar_ret_dev(h),
-                                                     popk_qp_npieces_dev(h), popk_qp_status_dev(h), d->safe,
-                                                     popk_qp_cpts_dev(h), d->status, h->d_traj_send, d->traj_ids);
-  POP_LAUNCH_CHECK(h);
-  h->n_launches += 3;
+  h->n_launches += 1;   // k_fill_times
   return POP_OK;
 }
 
@@ -278,7 +285,7 @@ int pop_separation_check_batch(pop_handle* h, const int32_t* n_pieces, const dou
   POP_CUDA(h, cudaMemcpyAsync(d->sep_st, ones.data(), sizeof(int) * nl, cudaMemcpyHostToDevice, h->stream));
   POP_CUDA(h, cudaMemcpyAsync(d->safe, ones.data(), sizeof(int) * nl, cudaMemcpyHostToDevice, h->stream));
   POP_CUDA(h, cudaMemcpyAsync(d->sep_cpts, cpts, sizeof(double) * POP_MAX_PIECES * 15 * nl, cudaMemcpyHostToDevice, h->stream));
-  rc = run_separation(h, t_now, d->sep_np, d->sep_st, d->sep_cpts);
+  rc = run_separation(h, t_now, d->sep_np, d->sep_st, d->sep_cpts, h->stream, 0, nl, 0, kSepWarps, true);
   if (rc) return rc;
   std::vector<int> safe(nl);
   POP_CUDA(h, cudaMemcpyAsync(safe.data(), d->safe, sizeof(int) * nl, cudaMemcpyDeviceToHost, h->stream));

@@ -84,7 +84,7 @@ __device__ __forceinline__ double limit_scaling(double v) {
 // Row capacity: every thread owns up to kSlots rows (row = slot*kT + tid); more rows (or a
 // problem that does not fit the shared-memory plan below) make the solve report status -20
 // (host: POP_E_CAPACITY).
-constexpr int kSlotsMax = 4;            // shared-memory factor path; the register-tile path owns 3
+constexpr int kSlotsMax = 6;            // shared-memory factor path (2 304 rows); the register-tile path owns 3
 constexpr int kRowCap = kT * kSlotsMax;
 constexpr int kMaxStruct = 9 * (POP_MAX_PIECES + 1) + 21 * POP_MAX_PIECES;  // 369 structured rows < kT
 constexpr int kSmemBytes = 232448;   // 227 KB opt-in maximum per CTA on sm_100a
@@ -117,6 +117,7 @@ struct Smem {
   unsigned short cptr[kMaxN + 2];   // start of column c in pc (padded: start = 2c mod 16)
   unsigned short clen[kMaxN + 2];   // entries of column c
   int pc_len, max_clen;
+  long long dbg[4];   // POP_QP_PHASE_PROF: cycles of K assembly, Cholesky, substitution + tiles
 };
 constexpr int kHdrBytes = (sizeof(Smem) + 15) / 16 * 16;
 
@@ -283,6 +284,9 @@ __device__ void factorize(Smem& S, double* __restrict__ Linv, double (&T)[NT], c
                           const int* __restrict__ csc_idx, const double* __restrict__ Pblk) {
   const int n = S.n, ms = S.ms;
   const int tid = threadIdx.x;
+#ifdef POP_QP_PHASE_PROF
+  const long long tf0 = clock64();
+#endif
   for (int e = tid; e < n * kBand; e += blockDim.x) {
     const int c = e / kBand, d = e % kBand, r = c + d;
     double v = 0.0;
@@ -313,6 +317,9 @@ __device__ void factorize(Smem& S, double* __restrict__ Linv, double (&T)[NT], c
     Kb[e] = v;
   }
   __syncthreads();
+#ifdef POP_QP_PHASE_PROF
+  const long long tf1 = clock64();
+#endif
   if (tid < 32) {
     const int lane = tid;
     int udi[4], udk[4];   // trailing-window entries of this lane: (di, dk), 1 <= dk <= di <= 15
@@ -344,6 +351,9 @@ __device__ void factorize(Smem& S, double* __restrict__ Linv, double (&T)[NT], c
     }
   }
   __syncthreads();
+#ifdef POP_QP_PHASE_PROF
+  const long long tf2 = clock64();
+#endif
   {
     const int c = tid;
     const int nst = 6 * ti.NB;   // staging row length (TILES)
@@ -398,6 +408,9 @@ __device__ void factorize(Smem& S, double* __restrict__ Linv, double (&T)[NT], c
     }
   }
   __syncthreads();
+#ifdef POP_QP_PHASE_PROF
+  if (tid == 0) { S.dbg[0] += tf1 - tf0; S.dbg[1] += tf2 - tf1; S.dbg[2] += clock64() - tf2; }
+#endif
 }
 
 // ---- K^-1 application, register-tile path (n <= 150) -----------------------------------------
@@ -605,12 +618,12 @@ __device__ __forceinline__ double gather_col(const double* __restrict__ pq, int 
 }
 
 // TILES = true: problems with n <= 150 and m <= 3 kT rows (L^-1 in registers, 3 row slots per
-// thread); TILES = false: the rest (L^-1 streamed from shared memory, 4 row slots).  Both variants
+// thread); TILES = false: the rest (L^-1 streamed from shared memory, 6 row slots).  Both variants
 // are launched over the whole batch; each CTA returns at once if the problem is not its kind.
 template <bool TILES>
 __global__ void __launch_bounds__(TILES ? kTt : kT, 1) k_qp_admm(QpDev Dv, QpParams P, const double* __restrict__ hpoly_all,
                                                                  const int* __restrict__ rows_all, int a0) {
-  constexpr int kSlots = TILES ? 3 : 4;
+  constexpr int kSlots = TILES ? 3 : kSlotsMax;
   constexpr int KT = TILES ? kTt : kT;   // threads of this variant
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Smem& S = *reinterpret_cast<Smem*>(smem_raw);
@@ -653,6 +666,7 @@ __global__ void __launch_bounds__(TILES ? kTt : kT, 1) k_qp_admm(QpDev Dv, QpPar
     // boxes 2, acceleration boxes 3, safety rows 3
     S.nnz = 87 * M + 15 * S.face_off[M];   // 36 per join/end pair + 24 + 27 box entries per piece
     S.status = 0; S.fail = 0; S.rho = RHO0; S.c_scale = 1.0;
+    S.dbg[0] = S.dbg[1] = S.dbg[2] = S.dbg[3] = 0;
     S.rho_v[0] = RHO_MIN; S.rho_v[1] = RHO0; S.rho_v[2] = RHO_EQ * RHO0;
     for (int k = 0; k < 3; k++) S.rinv_v[k] = 1. / S.rho_v[k];
   }
@@ -666,16 +680,19 @@ __global__ void __launch_bounds__(TILES ? kTt : kT, 1) k_qp_admm(QpDev Dv, QpPar
   const int part1_len = 6 * NBt * NBpt, part2_len = part1_len;
   // TILES: [staging 36 NB | Kb 16 n] during a factorisation, [partA | partB] during the iterations
   const int linv_len = TILES ? max(36 * NBt + n * kBand, part1_len + part2_len) : linv_off((n + 1) & ~1);
-  const size_t dyn_bytes = sizeof(double) * (static_cast<size_t>(linv_len) + (TILES ? 0 : n * kBand) + nnz + 16 * n + 2 + 128) +
+  // the banded K lives inside the staging area (TILES) or on top of the product array (it is dead
+  // during a factorisation and rewritten right after), so it costs no shared memory of its own
+  const int pc_len_max = max(nnz + 16 * n + 2 + 128, TILES ? 0 : n * kBand);
+  const size_t dyn_bytes = sizeof(double) * (static_cast<size_t>(linv_len) + pc_len_max) +
                            ((m + 15) & ~15) + 16 + (TILES ? sizeof(double) * 2 * static_cast<size_t>(m) : 0);
   if (m > kRowCap || kHdrBytes + dyn_bytes > (TILES ? kSmemTiles : kSmemBytes)) {
     if (tid == 0) { Dv.status[a] = -20; Dv.iters[a] = 0; }
     return;
   }
   double* Linv = reinterpret_cast<double*>(smem_raw + kHdrBytes);
-  double* Kb = TILES ? Linv + 36 * NBt : Linv + linv_len;
-  double* pc = TILES ? Linv + linv_len : Kb + n * kBand;
-  signed char* type = reinterpret_cast<signed char*>(pc + nnz + 16 * n + 2 + 128);
+  double* pc = Linv + linv_len;
+  double* Kb = TILES ? Linv + 36 * NBt : pc;
+  signed char* type = reinterpret_cast<signed char*>(pc + pc_len_max);
   // tile variant: row scalings and their reciprocals stay in shared memory for
   // the termination / rho-adaptation events (the other variant reads them from global memory)
   double* Es = reinterpret_cast<double*>(type + ((m + 15) & ~15));
@@ -1148,7 +1165,10 @@ __global__ void __launch_bounds__(TILES ? kTt : kT, 1) k_qp_admm(QpDev Dv, QpPar
     Dv.prof[a * 8 + 2] = now - clk_loop;
     Dv.prof[a * 8 + 3] = n_fact;
     Dv.prof[a * 8 + 4] = clk_g; Dv.prof[a * 8 + 5] = clk_k; Dv.prof[a * 8 + 6] = clk_r;
-    Dv.prof[a * 8 + 7] = clk_e; Dv.prof[a * 8 + 0] = clk_e1; Dv.prof[a * 8 + 1] = clk_e2;   // PHASE_PROF builds only
+    Dv.prof[a * 8 + 7] = clk_e;
+#ifdef POP_QP_PHASE_PROF
+    Dv.prof[a * 8 + 4] = S.dbg[0]; Dv.prof[a * 8 + 5] = S.dbg[1]; Dv.prof[a * 8 + 6] = S.dbg[2];   // factorisation split
+#endif
   }
 #undef COL0
 #undef DST0

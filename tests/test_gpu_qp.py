@@ -104,3 +104,57 @@ def test_infeasible_and_degenerate(oracle):
         assert iters[0] == it
         if st in (1, 2):
             assert _close(cpts[0, :5 * len(t)], X)
+
+
+def _tube_problem(M, faces_per_piece, rng):
+    """A straight tube of overlapping boxes along x with extra (redundant) random faces, so that the
+    row count can be pushed past the register-tile kernel's limits."""
+    polys = []
+    step = 0.3
+    for i in range(M):
+        lo = np.array([i * step - 0.5, -1.0, 0.0])
+        hi = np.array([(i + 1) * step + 0.5, 1.0, 2.0])
+        h = [[-1, 0, 0, lo[0]], [1, 0, 0, -hi[0]], [0, -1, 0, lo[1]], [0, 1, 0, -hi[1]], [0, 0, -1, lo[2]], [0, 0, 1, -hi[2]]]
+        c = (lo + hi) / 2
+        while len(h) < faces_per_piece:
+            nrm = rng.normal(size=3)
+            nrm /= np.linalg.norm(nrm)
+            d = 2.5 + rng.uniform(0, 1)            # far outside the box: never active
+            h.append([nrm[0], nrm[1], nrm[2], -(nrm @ c) - d])
+        polys.append(h)
+    start = [0.0, 0, 1, 0.5, 0, 0, 0, 0, 0]
+    end = [M * step, 0.2, 1.1, 0.3, 0, 0, 0, 0, 0]
+    return polys, start, end, [0.3] * M
+
+
+@pytest.mark.parametrize("M,faces", [(12, 8), (11, 20), (10, 38), (8, 48)])
+def test_large_problems_take_the_shared_memory_variant(oracle, M, faces):
+    """12- and 11-piece problems (n = 180, 165 > 150) and problems with more than 3*384 rows (up to 2 304) go to the
+    kernel variant that streams the packed inverse factor from shared memory: same parity bar."""
+    rng = np.random.default_rng(M * 100 + faces)
+    polys, s, e, t = _tube_problem(M, faces, rng)
+    cfg = cases.cfg_c1(p.POP_CELL_U8)
+    eng = p.PopEngine(cfg)
+    hp, rows = oracle.pack_polys(polys)
+    dur = np.zeros(POP_MAX_PIECES)
+    dur[:M] = t
+    cpts, status, iters = eng.qp_solve_batch([M], [s], [e], [dur], [hp], [rows], 2.0, 6.0)
+    st, X, it = oracle.qp_solve(cfg, s, e, t, polys, vmax=2.0, amax=6.0)
+    assert status[0] == st, (status[0], st)
+    assert iters[0] == it
+    assert st in (1, 2)
+    assert _close(cpts[0, :5 * M], X)
+
+
+def test_row_capacity_is_reported(oracle):
+    """More rows than any kernel variant holds → POP_E_CAPACITY, not a wrong answer."""
+    rng = np.random.default_rng(1)
+    polys, s, e, t = _tube_problem(12, 48, rng)    # 369 + 5*576 rows
+    cfg = cases.cfg_c1(p.POP_CELL_U8)
+    eng = p.PopEngine(cfg)
+    hp, rows = oracle.pack_polys(polys)
+    dur = np.zeros(POP_MAX_PIECES)
+    dur[:12] = t
+    with pytest.raises(p.PopError) as err:
+        eng.qp_solve_batch([12], [s], [e], [dur], [hp], [rows], 2.0, 6.0)
+    assert err.value.code == -4

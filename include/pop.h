@@ -277,9 +277,83 @@ int pop_traj_publish_local(pop_handle* h);
  * *recv_dev = n_agents_total records consumed by the next map update. */
 int pop_traj_buffers(pop_handle* h, void** send_dev, void** recv_dev);
 
+/* ---- K1d: DSP particle map (real-perception SOGM producer) -------------------------------- */
+/* Parameters of dsp_map::DSPMap.  The reference fixes most of them at compile time
+ * (plan_env/include/plan_env/map_parameters.h:5-53) or in the node that owns the map
+ * (plan_env/src/risk_mapping_node.cpp:232-241).  Grid size, resolution and the number of future
+ * slices come from the pop_config of the handle the map is attached to (MAP_*_VOXEL_NUM,
+ * VOXEL_RESOLUTION, PREDICTION_TIMES). */
+#define POP_DSP_MAX_T 40
+typedef struct pop_dsp_config {
+  int32_t half_fov_h, half_fov_v;       /* 43, 29 degrees (map_parameters.h:22-24) */
+  int32_t angle_resolution;             /* ANGLE_RESOLUTION 1 degree */
+  int32_t max_particle_num_voxel;       /* MAX_PARTICLE_NUM_VOXEL 7; storage is 2x (SAFE_PARTICLE_NUM_VOXEL), <= 8 */
+  int32_t pyramid_capacity;             /* SAFE_PARTICLE_NUM_PYRAMID = (V*7 + 1e5) / (360*180) * 2; 0 = derive */
+  int32_t max_points_per_pyramid;       /* observation_max_points_num_one_pyramid 100 */
+  int32_t max_points;                   /* MAX_POINT_NUM 5000 valid points after the voxel filter */
+  int32_t max_input_points;             /* capacity of one agent's raw camera cloud */
+  int32_t new_born_particle_number_each_point; /* 20 (risk_mapping_node.cpp:236) */
+  int32_t dynamic_cluster_max_point_num;       /* DYNAMIC_CLUSTER_MAX_POINT_NUM 200 */
+  float   dynamic_cluster_max_center_height;   /* DYNAMIC_CLUSTER_MAX_CENTER_HEIGHT 1.5 */
+  float   new_born_particle_weight;     /* 0.0001 (risk_mapping_node.cpp:238) */
+  float   sigma_observation;            /* map/sigma_observation */
+  float   kappa;                        /* 0.01 */
+  float   p_detection;                  /* 0.95 */
+  float   voxel_filter_resolution;      /* map/resolution of the voxel filter, 0.15 */
+  float   obstacle_thickness_for_occlusion; /* 0.3 */
+  float   occupancy_threshold;          /* map/risk_threshold_voxel (occupied-voxel export) */
+  float   position_prediction_stddev;   /* setPredictionVariance(0.01, 0.01): table generator only */
+  float   velocity_prediction_stddev;
+  float   prediction_future_time[POP_DSP_MAX_T]; /* nt entries, seconds (map_parameters.h:18) */
+  int32_t n_randoms;                    /* GAUSSIAN_RANDOMS_NUM (1e7 in the reference) */
+  int32_t _pad;
+  uint64_t seed;                        /* table generator seed (the reference uses time(NULL)) */
+} pop_dsp_config;
+
+/* reference defaults for the grid of `cfg` (pyramid_capacity derived) */
+void pop_dsp_default_config(const pop_config* cfg, pop_dsp_config* out);
+/* One DSPMap per local agent, standing where risk_mapping_node's `dsp_map_` stood
+ * (risk_mapping_node.cpp:38).  Requires cell_dtype F32.  Tables are generated from `seed`. */
+int pop_dsp_attach(pop_handle* h, const pop_dsp_config* cfg);
+/* Replace the noise tables: p_gaussian_randoms, v_gaussian_randoms (dsp_dynamic.h:114-116) and the
+ * stream rand() would have produced (generateRandomFloat :1687-1689); n entries each, shared by all
+ * local agents, every agent's sequence counters reset to 0. */
+int pop_dsp_set_random_tables(pop_handle* h, const float* p_gauss, const float* v_gauss,
+                              const int32_t* rand_stream, int n);
+/* cloudCallback for every local agent (risk_mapping_node.cpp:155-188): filterPointCloud (voxel-grid
+ * filter, camera->body axes, range, cap), DSPMap::update (dsp_dynamic.h:165-364), publishMap ->
+ * RiskBase::futureRiskCallback (risk_base.cpp:60-80: the [V][T] future risk becomes the agent's SOGM,
+ * then peers are projected).  cam = n_local x max_input_points x 3 camera-frame points, counts n_local,
+ * poses n_local x 3, quats n_local x 4 (w,x,y,z), one stamp.  out_ok (may be NULL) n_local: 1 updated,
+ * 0 rejected (invalid odometry, dsp_dynamic.h:183-204). */
+int pop_dsp_update(pop_handle* h, const float* cam, const int32_t* counts, const float* poses,
+                   const float* quats, double stamp, int32_t* out_ok);
+/* Same, with points already filtered into the body frame (valid_clouds_): pts = n_local x max_points x 3. */
+int pop_dsp_update_filtered(pop_handle* h, const float* pts, const int32_t* counts, const float* poses,
+                            const float* quats, double stamp, int32_t* out_ok);
+/* filterPointCloud alone (risk_mapping_node.cpp:74-99) for one agent: out = max_points x 3. */
+int pop_dsp_filter(pop_handle* h, int agent, const float* cam, int n, float* out, int32_t* n_out);
+/* Parity/debug views in the reference's layouts:
+ *   particles  voxels_with_particle[V][2*max_particle_num_voxel][8] (flag vx vy vz px py pz weight)
+ *   voxels     voxels_objects_number[V][0..3] (occupancy weight, mean velocity)
+ *   observations point_cloud[NP][max_points_per_pyramid][5], counts[NP], max_length[NP]
+ *   pyramids   pyramids_in_fov[NP][pyramid_capacity][3]
+ *   points_with_velocity input_cloud_with_velocity: n x 7 (x y z intensity vx vy vz)
+ *   stats      8 x int32: particles dropped on a full voxel, on a full pyramid, moved out, newborn
+ *              added (cumulative), sequence counters of the three tables, update counter */
+int pop_dsp_download_particles(pop_handle* h, int agent, float* out);
+int pop_dsp_download_voxels(pop_handle* h, int agent, float* out);
+int pop_dsp_download_observations(pop_handle* h, int agent, float* pc, int32_t* counts, float* max_length);
+int pop_dsp_download_pyramids(pop_handle* h, int agent, int32_t* out);
+int pop_dsp_download_points_with_velocity(pop_handle* h, int agent, float* out, int cap, int32_t* n_out);
+int pop_dsp_stats(pop_handle* h, int agent, int32_t* out);
+/* getOccupancyMap (dsp_dynamic.h:402-420): centres of the voxels whose occupancy weight exceeds
+ * occupancy_threshold, ascending voxel index; out = cap x 3 floats. */
+int pop_dsp_occupied(pop_handle* h, int agent, float* out, int cap, int32_t* n_out);
+
 /* ---- measurement ------------------------------------------------------------------------ */
 enum { POP_STAGE_VOXEL_UPDATE = 0, POP_STAGE_PEERS = 1, POP_STAGE_ASTAR = 2, POP_STAGE_CORRIDOR = 3,
-       POP_STAGE_QP = 4, POP_STAGE_SEPARATION = 5, POP_STAGE_COUNT = 8 };
+       POP_STAGE_QP = 4, POP_STAGE_SEPARATION = 5, POP_STAGE_DSP = 6, POP_STAGE_COUNT = 8 };
 /* CUDA-event bracketing of the stages on the handle's stream.  on = 1: every stage (the planning
  * stages then run one after the other over the whole batch, so the per-stage times mean something);
  * on = 2: the map stages only (voxel update, peers) — the planning stages stay pipelined over agent

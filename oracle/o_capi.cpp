@@ -71,6 +71,11 @@ int orc_map_obstacle_points(void* h, double t0, double t1, const double* lc, con
   for (int i = 0; i < std::min(n, cap); i++) { out[3 * i] = v[i].x; out[3 * i + 1] = v[i].y; out[3 * i + 2] = v[i].z; }
   return n;
 }
+// parity helper: load risk_maps_ ([V][T]) as received from "map/future_risk" (risk_base.cpp:60-68)
+void orc_map_set_risk(void* h, const float* in) {
+  Grid& g = static_cast<OrcMap*>(h)->grid;
+  std::copy(in, in + g.risk.size(), g.risk.begin());
+}
 void orc_map_download(void* h, float* out) {
   const Grid& g = static_cast<OrcMap*>(h)->grid;
   std::copy(g.risk.begin(), g.risk.end(), out);

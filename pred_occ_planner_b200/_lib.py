@@ -92,6 +92,31 @@ class PopConfig(C.Structure):
         return c
 
 
+POP_DSP_MAX_T = 40
+
+
+class PopDspConfig(C.Structure):
+    """pop_dsp_config (include/pop.h): parameters of one dsp_map::DSPMap."""
+    _fields_ = [
+        ("half_fov_h", C.c_int32), ("half_fov_v", C.c_int32), ("angle_resolution", C.c_int32),
+        ("max_particle_num_voxel", C.c_int32), ("pyramid_capacity", C.c_int32),
+        ("max_points_per_pyramid", C.c_int32), ("max_points", C.c_int32), ("max_input_points", C.c_int32),
+        ("new_born_particle_number_each_point", C.c_int32), ("dynamic_cluster_max_point_num", C.c_int32),
+        ("dynamic_cluster_max_center_height", C.c_float), ("new_born_particle_weight", C.c_float),
+        ("sigma_observation", C.c_float), ("kappa", C.c_float), ("p_detection", C.c_float),
+        ("voxel_filter_resolution", C.c_float), ("obstacle_thickness_for_occlusion", C.c_float),
+        ("occupancy_threshold", C.c_float), ("position_prediction_stddev", C.c_float),
+        ("velocity_prediction_stddev", C.c_float),
+        ("prediction_future_time", C.c_float * POP_DSP_MAX_T),
+        ("n_randoms", C.c_int32), ("_pad", C.c_int32), ("seed", C.c_uint64),
+    ]
+
+    def copy(self) -> "PopDspConfig":
+        c = PopDspConfig()
+        C.memmove(C.byref(c), C.byref(self), C.sizeof(PopDspConfig))
+        return c
+
+
 class PopCycleIO(C.Structure):
     _fields_ = [("start", C.POINTER(C.c_double)), ("goal", C.POINTER(C.c_double)),
                 ("poses", C.POINTER(C.c_float)), ("t_map", C.c_double), ("t_plan", C.c_double),
@@ -142,6 +167,19 @@ SYMBOLS = [
     ("pop_profile_read", _I, [_VP, _PF, C.POINTER(C.c_int64), _I]),
     ("pop_qp_profile", _I, [_VP, _I, C.POINTER(C.c_int64)]),
     ("pop_kernel_launches", C.c_int64, [_VP]),
+    ("pop_dsp_default_config", None, [C.POINTER(PopConfig), C.POINTER(PopDspConfig)]),
+    ("pop_dsp_attach", _I, [_VP, C.POINTER(PopDspConfig)]),
+    ("pop_dsp_set_random_tables", _I, [_VP, _PF, _PF, _PI32, _I]),
+    ("pop_dsp_update", _I, [_VP, _PF, _PI32, _PF, _PF, _D, _PI32]),
+    ("pop_dsp_update_filtered", _I, [_VP, _PF, _PI32, _PF, _PF, _D, _PI32]),
+    ("pop_dsp_filter", _I, [_VP, _I, _PF, _I, _PF, _PI32]),
+    ("pop_dsp_download_particles", _I, [_VP, _I, _PF]),
+    ("pop_dsp_download_voxels", _I, [_VP, _I, _PF]),
+    ("pop_dsp_download_observations", _I, [_VP, _I, _PF, _PI32, _PF]),
+    ("pop_dsp_download_pyramids", _I, [_VP, _I, _PI32]),
+    ("pop_dsp_download_points_with_velocity", _I, [_VP, _I, _PF, _I, _PI32]),
+    ("pop_dsp_stats", _I, [_VP, _I, _PI32]),
+    ("pop_dsp_occupied", _I, [_VP, _I, _PF, _I, _PI32]),
 ]
 
 _lib = None

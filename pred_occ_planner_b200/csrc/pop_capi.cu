@@ -201,6 +201,7 @@ int pop_destroy(pop_handle* h) {
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   popk_vox_free(h);
+  popk_dsp_free(h);
   for (cudaStream_t s : h->side) cudaStreamDestroy(s);
   for (cudaEvent_t e : h->side_done) cudaEventDestroy(e);
   if (h->fork_ev) cudaEventDestroy(h->fork_ev);

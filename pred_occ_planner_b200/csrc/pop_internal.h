@@ -44,6 +44,7 @@ struct AstarDev;   // k_astar.cu
 struct CorridorDev;  // k_corridor.cu
 struct QpDev;      // k_qp.cu
 struct PlanDev;    // corridor + QP workspaces
+struct DspDev;     // k_dsp.cu: DSP particle maps
 
 struct pop_handle {
   pop_config cfg;
@@ -83,6 +84,7 @@ struct pop_handle {
   CorridorDev* corridor = nullptr;
   QpDev* qp = nullptr;
   PlanDev* plan = nullptr;
+  DspDev* dsp = nullptr;
   PopProfile prof;
   // agent-group pipelining of the planning stages (k_cycle.cu)
   std::vector<cudaStream_t> side;
@@ -102,6 +104,7 @@ int pop_fail(pop_handle* h, int code, const char* fmt, ...);
 #define POP_LAUNCH_CHECK(h) POP_CUDA(h, cudaGetLastError())
 
 void pop_plan_free(pop_handle* h);
+void popk_dsp_free(pop_handle* h);
 int pop_ensure_scratch(pop_handle* h, size_t dev_bytes, size_t host_bytes);
 void pop_prof_begin(pop_handle* h, int stage);
 void pop_prof_end(pop_handle* h, int stage, int n_launches);

@@ -132,3 +132,64 @@ def straight_trajs(start_pos: np.ndarray, goal: np.ndarray, t_start: float, spee
             for k in range(5):
                 rec["cpts"][i, p * 5 + k] = p0 + v * piece_dur * k / 4.0
     return rec
+
+
+def quat_yaw(yaw: float) -> np.ndarray:
+    """(w, x, y, z) of a rotation about +z."""
+    return np.array([math.cos(yaw / 2), 0.0, 0.0, math.sin(yaw / 2)], np.float32)
+
+
+def _quat_matrix(q) -> np.ndarray:
+    w, x, y, z = [float(v) for v in q]
+    return np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                     [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                     [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+
+
+def render_depth_cloud(cyl, pos, quat, t: float = 0.0, half_fov=(43.0, 29.0), pitch_deg: float = 0.5,
+                       max_range: float = 6.0, ground_z: float = 0.0, noise: float = 0.0, seed: int = 0):
+    """What the reference's depth camera would publish on "map/cloud" (uav_simulator/local_sensing): one
+    ray per `pitch_deg` over the field of view, nearest hit with the vertical cylinders (moved to time t)
+    or the ground plane, returned in the CAMERA frame (x right, y down, z forward) that
+    filterPointCloud expects (risk_mapping_node.cpp:82-84: body x = z_c, y = -x_c, z = -y_c)."""
+    pos = np.asarray(pos, np.float64)
+    R = _quat_matrix(quat)
+    az = np.deg2rad(np.arange(-half_fov[0] + pitch_deg / 2, half_fov[0], pitch_deg))
+    el = np.deg2rad(np.arange(-half_fov[1] + pitch_deg / 2, half_fov[1], pitch_deg))
+    A, E = np.meshgrid(az, el, indexing="ij")
+    d_body = np.stack([np.cos(E) * np.cos(A), np.cos(E) * np.sin(A), np.sin(E)], axis=-1).reshape(-1, 3)
+    d = d_body @ R.T
+    best = np.full(len(d), np.inf)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        tg = (ground_z - pos[2]) / d[:, 2]
+    tg = np.where((tg > 0) & np.isfinite(tg), tg, np.inf)
+    best = np.minimum(best, tg)
+    for c in cyl:
+        cx, cy = c["x"] + c["vx"] * t, c["y"] + c["vy"] * t
+        r = c["w"] / 2
+        ox, oy = pos[0] - cx, pos[1] - cy
+        a = d[:, 0] ** 2 + d[:, 1] ** 2
+        b = 2 * (ox * d[:, 0] + oy * d[:, 1])
+        cc = ox * ox + oy * oy - r * r
+        disc = b * b - 4 * a * cc
+        with np.errstate(divide="ignore", invalid="ignore"):
+            th = (-b - np.sqrt(np.where(disc >= 0, disc, np.nan))) / (2 * a)
+        zh = pos[2] + th * d[:, 2]
+        ok = np.isfinite(th) & (th > 0) & (zh >= ground_z) & (zh <= c["h"])
+        best = np.minimum(best, np.where(ok, th, np.inf))
+    hit = best < max_range
+    pts_body = d_body[hit] * best[hit, None]
+    if noise > 0:
+        pts_body = pts_body + _rng(seed).normal(0, noise, pts_body.shape)
+    cam = np.stack([-pts_body[:, 1], -pts_body[:, 2], pts_body[:, 0]], axis=1)
+    return np.ascontiguousarray(cam, np.float32)
+
+
+def dsp_random_tables(n: int, seed: int, p_std: float = 0.01, v_std: float = 0.01):
+    """The three noise inputs of the DSP map (dsp_dynamic.h:114-116, 1220-1231, 1687-1689): position and
+    velocity Gaussian tables and the rand() stream (int32 in [0, RAND_MAX])."""
+    rng = _rng(seed)
+    pg = rng.normal(0.0, p_std, n).astype(np.float32)
+    vg = rng.normal(0.0, v_std, n).astype(np.float32)
+    ur = rng.integers(0, 2 ** 31 - 1, n, dtype=np.int64).astype(np.int32)
+    return pg, vg, ur

@@ -55,6 +55,10 @@ class OracleMap:
         p = np.ascontiguousarray(p, np.float32)
         self.lib.orc_map_set_pose(self.h, _p(p, C.c_float))
 
+    def set_risk(self, risk):
+        risk = np.ascontiguousarray(risk, np.float32)
+        self.lib.orc_map_set_risk(self.h, _p(risk, C.c_float))
+
     def kernel_size(self):
         return self.lib.orc_map_kernel_size(self.h)
 
@@ -132,6 +136,9 @@ class OracleLib:
 
     def map(self, cfg) -> OracleMap:
         return OracleMap(self.lib, cfg)
+
+    def dsp(self, cfg, dcfg) -> "OracleDsp":
+        return OracleDsp(self.lib, cfg, dcfg)
 
     def ego_particles(self, size):
         size = np.ascontiguousarray(size, np.float64)
@@ -230,3 +237,86 @@ class OracleLib:
         out = np.zeros(25)
         self.lib.orc_bernstein_coeff(_p(out, C.c_double))
         return out.reshape(5, 5)
+
+
+class OracleDsp:
+    """orc::DspMap — sequential restatement of dsp_map::DSPMap + filterPointCloud (oracle/o_dsp.cpp)."""
+
+    def __init__(self, lib, cfg, dcfg):
+        self.lib, self.cfg, self.d = lib, cfg, dcfg
+        lib.orc_dsp_create.restype = C.c_void_p
+        self.h = C.c_void_p(lib.orc_dsp_create(C.byref(cfg), C.byref(dcfg)))
+        self.V = cfg.nx * cfg.ny * cfg.nz
+        self.S = 2 * dcfg.max_particle_num_voxel
+        self.NP = (dcfg.half_fov_h * 2 // dcfg.angle_resolution) * (dcfg.half_fov_v * 2 // dcfg.angle_resolution)
+
+    def __del__(self):
+        try:
+            self.lib.orc_dsp_destroy(self.h)
+        except Exception:
+            pass
+
+    def set_random_tables(self, pg, vg, ur):
+        pg = np.ascontiguousarray(pg, np.float32)
+        vg = np.ascontiguousarray(vg, np.float32)
+        ur = np.ascontiguousarray(ur, np.int32)
+        self.lib.orc_dsp_set_random_tables(self.h, _p(pg, C.c_float), _p(vg, C.c_float), _p(ur, C.c_int32), len(pg))
+
+    def filter(self, cam):
+        cam = np.ascontiguousarray(cam, np.float32).reshape(-1, 3)
+        out = np.zeros((self.d.max_points, 3), np.float32)
+        n = self.lib.orc_dsp_filter(self.h, _p(cam, C.c_float), len(cam), _p(out, C.c_float))
+        return out[:n].copy()
+
+    def update_filtered(self, pts, pos, quat, stamp):
+        pts = np.ascontiguousarray(pts, np.float32).reshape(-1, 3)
+        pos = np.ascontiguousarray(pos, np.float32)
+        quat = np.ascontiguousarray(quat, np.float32)
+        return self.lib.orc_dsp_update_filtered(self.h, _p(pts, C.c_float), len(pts), _p(pos, C.c_float),
+                                                _p(quat, C.c_float), C.c_double(stamp))
+
+    def update(self, cam, pos, quat, stamp):
+        cam = np.ascontiguousarray(cam, np.float32).reshape(-1, 3)
+        pos = np.ascontiguousarray(pos, np.float32)
+        quat = np.ascontiguousarray(quat, np.float32)
+        return self.lib.orc_dsp_update(self.h, _p(cam, C.c_float), len(cam), _p(pos, C.c_float),
+                                       _p(quat, C.c_float), C.c_double(stamp))
+
+    def export(self, thr=None):
+        """[V][T] future risk (clears the accumulators) and the number of occupied voxels."""
+        out = np.zeros((self.V, self.cfg.nt), np.float32)
+        n = self.lib.orc_dsp_export(self.h, _p(out, C.c_float),
+                                    C.c_float(self.d.occupancy_threshold if thr is None else thr))
+        return out, n
+
+    def particles(self):
+        out = np.zeros((self.V, self.S, 8), np.float32)
+        self.lib.orc_dsp_particles(self.h, _p(out, C.c_float))
+        return out
+
+    def voxels(self):
+        out = np.zeros((self.V, 4), np.float32)
+        self.lib.orc_dsp_voxels(self.h, _p(out, C.c_float))
+        return out
+
+    def observations(self):
+        pc = np.zeros((self.NP, self.d.max_points_per_pyramid, 5), np.float32)
+        cnt = np.zeros(self.NP, np.int32)
+        ml = np.zeros(self.NP, np.float32)
+        self.lib.orc_dsp_observations(self.h, _p(pc, C.c_float), _p(cnt, C.c_int32), _p(ml, C.c_float))
+        return pc, cnt, ml
+
+    def pyramids(self):
+        out = np.zeros((self.NP, self.d.pyramid_capacity, 3), np.int32)
+        self.lib.orc_dsp_pyramids(self.h, _p(out, C.c_int32))
+        return out
+
+    def points_with_velocity(self, cap=8192):
+        out = np.zeros((cap, 7), np.float32)
+        n = self.lib.orc_dsp_points_with_velocity(self.h, _p(out, C.c_float), cap)
+        return out[:min(n, cap)].copy()
+
+    def stats(self):
+        out = np.zeros(8, np.int32)
+        self.lib.orc_dsp_stats(self.h, _p(out, C.c_int32))
+        return out

@@ -262,6 +262,10 @@ typedef struct pop_cycle_io {
  * (baseline_fake.cpp:253-453) preceded by the map update it reads.  Host inputs are copied
  * in, results copied out (this is the call `e2e` in bench.py times). */
 int pop_replan_cycle(pop_handle* h, const pop_cycle_io* io);
+/* The planning half of the cycle on the SOGM as the last map update left it — BaselinePlanner::replan x N
+ * (plan_manager/src/baseline.cpp:253-453) reading the map the particle-map node produced
+ * (pop_dsp_update) or a ground-truth update.  io->poses and io->t_map are ignored. */
+int pop_plan_cycle(pop_handle* h, const pop_cycle_io* io);
 /* Same cycle with inputs already resident on the device (uploaded by the previous
  * pop_replan_cycle/pop_set_* calls); nothing is copied to the host. Async. */
 int pop_replan_cycle_resident(pop_handle* h, double t_map, double t_plan);

@@ -76,6 +76,7 @@ void orc_map_set_risk(void* h, const float* in) {
   Grid& g = static_cast<OrcMap*>(h)->grid;
   std::copy(in, in + g.risk.size(), g.risk.begin());
 }
+void orc_map_set_time(void* h, double t_map) { static_cast<OrcMap*>(h)->grid.t_map = t_map; }
 void orc_map_download(void* h, float* out) {
   const Grid& g = static_cast<OrcMap*>(h)->grid;
   std::copy(g.risk.begin(), g.risk.end(), out);

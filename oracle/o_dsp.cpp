@@ -782,6 +782,11 @@ int orc_dsp_points_with_velocity(void* h, float* out, int cap) {
   }
   return n;
 }
+// the assignment step alone (cross-checked against scipy in the CPU tests): out[r] = column or -1
+void orc_dsp_assign(const double* cost, int nr, int nc, int32_t* out) {
+  const std::vector<int> a = assign_min_cost(std::vector<double>(cost, cost + static_cast<size_t>(nr) * nc), nr, nc);
+  std::copy(a.begin(), a.end(), out);
+}
 void orc_dsp_stats(void* h, int32_t* out) {  // voxel-full, pyramid-full, moved out, newborn, seq p/v/u
   DspMap& m = static_cast<OrcDsp*>(h)->m;
   out[0] = m.stat_vox_full; out[1] = m.stat_pyr_full; out[2] = m.stat_out; out[3] = m.stat_born;

@@ -159,6 +159,7 @@ SYMBOLS = [
     ("pop_qp_solve_batch", _I, [_VP, _I, _PI32, _PD, _PD, _PD, _PD, _PI32, _D, _D, _PD, _PI32, _PI32]),
     ("pop_separation_check_batch", _I, [_VP, _PI32, _PD, _D, _PI8]),
     ("pop_replan_cycle", _I, [_VP, C.POINTER(PopCycleIO)]),
+    ("pop_plan_cycle", _I, [_VP, C.POINTER(PopCycleIO)]),
     ("pop_replan_cycle_resident", _I, [_VP, _D, _D]),
     ("pop_cycle_results", _I, [_VP, _PI32, C.POINTER(PopTrajRecord)]),
     ("pop_traj_publish_local", _I, [_VP]),

@@ -216,7 +216,7 @@ static int plan_groups(pop_handle* h, int nl) {
 }
 
 // the whole cycle on the stream; inputs (cloud, cylinders, poses, peers, start, goal) resident
-static int cycle_enqueue(pop_handle* h, double t_map, double t_plan) {
+static int cycle_enqueue(pop_handle* h, double t_map, double t_plan, bool update_map = true) {
   int rc;
   if ((rc = popk_astar_alloc(h))) return rc;
   if ((rc = popk_corridor_alloc(h))) return rc;
@@ -225,10 +225,14 @@ static int cycle_enqueue(pop_handle* h, double t_map, double t_plan) {
   PlanDev* d = h->plan;
   const pop_config& c = h->cfg;
   const int nl = c.n_agents_local;
-  h->t_map = t_map;
-  if ((rc = popk_voxel_update(h))) return rc;
-  if ((rc = popk_peer_project(h))) return rc;
-  h->map_ready = true;
+  if (update_map) {
+    h->t_map = t_map;
+    if ((rc = popk_voxel_update(h))) return rc;
+    if ((rc = popk_peer_project(h))) return rc;
+    h->map_ready = true;
+  } else {
+    t_map = h->t_map;   // the SOGM as the last map update (ground truth or particle map) left it
+  }
   k_fill_times<<<(nl + 127) / 128, 128, 0, h->stream>>>(nl, t_plan - t_map, t_plan, popk_astar_tstart_dev(h),
                                                        popk_corridor_tst_dev(h), d->safe);
   POP_LAUNCH_CHECK(h);
@@ -300,16 +304,29 @@ int pop_replan_cycle_resident(pop_handle* h, double t_map, double t_plan) {
   return cycle_enqueue(h, t_map, t_plan);
 }
 
+static int replan_cycle_io(pop_handle* h, const pop_cycle_io* io, bool update_map);
+
 int pop_replan_cycle(pop_handle* h, const pop_cycle_io* io) {
   if (!h || !io || !io->start || !io->goal || !io->poses || !io->status || !io->traj) return POP_E_INVALID;
+  return replan_cycle_io(h, io, true);
+}
+
+int pop_plan_cycle(pop_handle* h, const pop_cycle_io* io) {
+  if (!h || !io || !io->start || !io->goal || !io->status || !io->traj) return POP_E_INVALID;
+  if (!h->map_ready) return pop_fail(h, POP_E_STATE, "no map yet: call pop_dsp_update or pop_map_update_gt first");
+  return replan_cycle_io(h, io, false);
+}
+
+static int replan_cycle_io(pop_handle* h, const pop_cycle_io* io, bool update_map) {
   int rc;
   if ((rc = popk_astar_alloc(h))) return rc;
   if ((rc = plan_alloc(h))) return rc;
   const int nl = h->cfg.n_agents_local;
-  POP_CUDA(h, cudaMemcpyAsync(h->d_poses, io->poses, sizeof(float) * 3 * nl, cudaMemcpyHostToDevice, h->stream));
+  if (update_map)
+    POP_CUDA(h, cudaMemcpyAsync(h->d_poses, io->poses, sizeof(float) * 3 * nl, cudaMemcpyHostToDevice, h->stream));
   POP_CUDA(h, cudaMemcpyAsync(popk_astar_start_dev(h), io->start, sizeof(double) * 9 * nl, cudaMemcpyHostToDevice, h->stream));
   POP_CUDA(h, cudaMemcpyAsync(popk_astar_goal_dev(h), io->goal, sizeof(double) * 3 * nl, cudaMemcpyHostToDevice, h->stream));
-  if ((rc = cycle_enqueue(h, io->t_map, io->t_plan))) return rc;
+  if ((rc = cycle_enqueue(h, io->t_map, io->t_plan, update_map))) return rc;
   POP_CUDA(h, cudaMemcpyAsync(io->status, h->plan->status, sizeof(int) * nl, cudaMemcpyDeviceToHost, h->stream));
   POP_CUDA(h, cudaMemcpyAsync(io->traj, h->d_traj_send, sizeof(pop_traj_record) * nl, cudaMemcpyDeviceToHost, h->stream));
   POP_CUDA(h, cudaStreamSynchronize(h->stream));

@@ -159,6 +159,18 @@ class PopEngine:
         self._t_map = float(t_map)
         return status, traj
 
+    def plan_cycle(self, start, goal, t_plan):
+        """Planning half of the cycle (A* → corridor → QP → separation) on the SOGM of the last map update,
+        e.g. the particle map's (`DspMaps.cloudCallback`): BaselinePlanner::replan (baseline.cpp:253-453)."""
+        n = self.n_local
+        start, goal = _f64(start, (n, 9)), _f64(goal, (n, 3))
+        status = np.zeros(n, np.int32)
+        traj = np.zeros(n, TRAJ_DTYPE)
+        io = _lib.PopCycleIO(as_ptr(start, C.c_double), as_ptr(goal, C.c_double), None, 0.0, float(t_plan),
+                             as_ptr(status, C.c_int32), traj.ctypes.data_as(C.POINTER(PopTrajRecord)))
+        self._check(self.lib.pop_plan_cycle(self._h, C.byref(io)))
+        return status, traj
+
     def replan_cycle_resident(self, t_map, t_plan):
         self._check(self.lib.pop_replan_cycle_resident(self._h, float(t_map), float(t_plan)))
 

@@ -59,6 +59,9 @@ class OracleMap:
         risk = np.ascontiguousarray(risk, np.float32)
         self.lib.orc_map_set_risk(self.h, _p(risk, C.c_float))
 
+    def set_time(self, t_map):
+        self.lib.orc_map_set_time(self.h, C.c_double(t_map))
+
     def kernel_size(self):
         return self.lib.orc_map_kernel_size(self.h)
 

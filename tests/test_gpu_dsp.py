@@ -156,3 +156,45 @@ def test_occupied_export_and_queries(pop, oracle):
     assert np.array_equal(eng.agent_map(0).getClearOcccupancy(q, t), om.query(q, t))
     assert (om.query(q, t) == 1).sum() > 20
     eng.close()
+
+
+def test_plan_cycle_on_particle_map(pop, oracle):
+    """The real-perception cycle: particle-map frames, then A* -> corridors -> QP on the SOGM they wrote
+    (pop_plan_cycle).  The oracle plans on a grid loaded with the device's own risk values, so the planning
+    half is compared at the north-star tolerance: status identical, control points within 1e-4 relative."""
+    from pred_occ_planner_b200 import worldgen
+    from tests import oracle_cycle
+    n = 2
+    cfg, d, eng, maps, orcs = _setup(pop, oracle, n)
+    cyl = cases.dsp_scene()
+    for k in range(6):
+        clouds, poses, quats = [], [], []
+        for a in range(n):
+            pos, quat, st = _flight(a, k)
+            clouds.append(worldgen.render_depth_cloud(cyl, pos, quat, t=0.1 * k))
+            poses.append(pos)
+            quats.append(quat)
+        maps.cloudCallback(clouds, np.array(poses), np.array(quats), st)
+    start = np.zeros((n, 9))
+    goal = np.zeros((n, 3))
+    for a in range(n):
+        start[a, :3] = poses[a]
+        start[a, 3] = 1.0
+        goal[a] = [4.0, 0.5 * a, 1.0]
+    status, traj = eng.plan_cycle(start, goal, st + 0.02)
+    n_ok = 0
+    for a in range(n):
+        om = oracle.map(cfg)
+        om.set_pose(poses[a])
+        om.set_time(st)
+        om.set_risk(eng.agent_map(a).risk_maps())
+        rs, rec, stats = oracle_cycle.replan(om, None, a, start[a], goal[a], st + 0.02)
+        assert rs == status[a], (a, rs, status[a], stats.tolist())
+        if rs == 0:
+            n_ok += 1
+            M = int(rec["n_pieces"])
+            assert traj["n_pieces"][a] == M
+            g, r = traj["cpts"][a][:5 * M], rec["cpts"][:5 * M]
+            assert np.abs(g - r).max() <= 1e-4 * max(1.0, np.abs(r).max())
+    assert n_ok >= 1
+    eng.close()

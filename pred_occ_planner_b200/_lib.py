@@ -21,7 +21,7 @@ POP_CELL_F32, POP_CELL_U8 = 0, 1
 POP_KERNEL_DISC_Z0, POP_KERNEL_CUBE = 0, 1
 POP_QUERY_FAKE, POP_QUERY_RISKBASE = 0, 1
 
-STAGE_NAMES = ["voxel_update", "peers", "astar", "corridor", "qp", "separation", "r6", "r7"]
+STAGE_NAMES = ["voxel_update", "peers", "astar", "corridor", "qp", "separation", "dsp", "r7"]
 ERRORS = {0: "OK", -1: "INVALID", -2: "NO_DEVICE", -3: "CUDA", -4: "CAPACITY", -5: "STATE",
           -6: "UNSUPPORTED"}
 

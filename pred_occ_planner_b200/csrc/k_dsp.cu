@@ -1566,9 +1566,15 @@ int popk_dsp_update(pop_handle* h, int filtered) {
                                        d->stats);
   POP_LAUNCH_CHECK(h); launches++;
   // --- occupancy, future deposits into the SOGM, resampling ---
-  for (int a = 0; a < A; a++)
-    if (d->h_frame[a].ok)
-      POP_CUDA(h, cudaMemsetAsync(h->d_grid + a * h->geom.agent_stride, 0, sizeof(float) * static_cast<size_t>(G.V) * G.T, st));
+  for (int a = 0; a < A;) {   // runs of accepted agents: one bulk-store launch per run (one launch in all if every update is accepted)
+    if (!d->h_frame[a].ok) { a++; continue; }
+    int b = a;
+    while (b < A && d->h_frame[b].ok) b++;
+    const int rc = popk_grid_clear(h, a, b - a);
+    if (rc) return rc;
+    launches++;
+    a = b;
+  }
   k_dsp_occupancy<<<gv, 256, 0, st>>>(G, d->frame, d->flags, d->pa, d->pb, d->vobj, h->d_grid, h->geom.agent_stride);
   POP_LAUNCH_CHECK(h); launches++;
   pop_prof_end(h, POP_STAGE_DSP, launches);

@@ -87,6 +87,7 @@ struct DspDev {
   int updates = 0;
 };
 
+int popk_grid_clear(pop_handle* h, int a0, int na);   // k_map.cu
 int popk_dsp_alloc(pop_handle* h, const pop_dsp_config* c);
 void popk_dsp_free(pop_handle* h);
 // filtered = 0: d->cam holds camera clouds (frame.n_in points) -> filter; 1: d->pts / d->npts already set

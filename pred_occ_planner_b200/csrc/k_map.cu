@@ -623,6 +623,24 @@ static int clear_mode() {
   return mode;
 }
 
+// zero the SOGM grids of agents [a0, a0+na) with the TMA bulk-store kernel (the particle map's
+// accumulators are cleared once per update, dsp_dynamic.h:461-465)
+int popk_grid_clear(pop_handle* h, int a0, int na) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(k_clear_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, kClearTile);
+    attr_set = true;
+  }
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
+  const unsigned long long total = h->geom.agent_stride * static_cast<unsigned long long>(na);
+  const unsigned long long tiles = (total + kClearTile - 1) / kClearTile;
+  const unsigned grid = static_cast<unsigned>(tiles < static_cast<unsigned long long>(sms) * 4 ? tiles : sms * 4);
+  k_clear_tma<<<grid, 128, kClearTile, h->stream>>>(h->d_grid + h->geom.agent_stride * a0, total);
+  POP_LAUNCH_CHECK(h);
+  return POP_OK;
+}
+
 int popk_voxel_update(pop_handle* h) {
   const PopGeom& g = h->geom;
   const int nl = h->cfg.n_agents_local;

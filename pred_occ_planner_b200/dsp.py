@@ -52,9 +52,16 @@ class DspMaps:
         """One frame for every local agent: clouds = list of [n,3] camera-frame arrays (or body-frame
         `valid_clouds_` when filtered=True), poses [n_local,3], quats [n_local,4] (w,x,y,z).  Returns the
         per-agent accepted flags (DSPMap::update's return value)."""
-        e = self.eng
         cap = self.d.max_points if filtered else self.d.max_input_points
         buf, counts = self._pack(clouds, cap)
+        return self.cloudCallbackPacked(buf, counts, poses, quats, stamp, filtered)
+
+    def pack(self, clouds, filtered: bool = False):
+        """(buffer [n_local, capacity, 3] float32, counts) in the layout pop_dsp_update takes."""
+        return self._pack(clouds, self.d.max_points if filtered else self.d.max_input_points)
+
+    def cloudCallbackPacked(self, buf, counts, poses, quats, stamp: float, filtered: bool = False):
+        e = self.eng
         poses = np.ascontiguousarray(poses, np.float32).reshape(self.n_local, 3)
         quats = np.ascontiguousarray(quats, np.float32).reshape(self.n_local, 4)
         ok = np.zeros(self.n_local, np.int32)

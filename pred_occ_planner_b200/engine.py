@@ -199,8 +199,8 @@ class PopEngine:
         ms = np.zeros(POP_STAGE_COUNT, np.float32)
         ln = np.zeros(POP_STAGE_COUNT, np.int64)
         self._check(self.lib.pop_profile_read(self._h, as_ptr(ms, C.c_float), as_ptr(ln, C.c_int64), int(reset)))
-        return ({STAGE_NAMES[i]: float(ms[i]) for i in range(6)},
-                {STAGE_NAMES[i]: int(ln[i]) for i in range(6)})
+        return ({STAGE_NAMES[i]: float(ms[i]) for i in range(7)},
+                {STAGE_NAMES[i]: int(ln[i]) for i in range(7)})
 
     def qp_profile(self, n: int) -> np.ndarray:
         out = np.zeros((n, 8), np.int64)

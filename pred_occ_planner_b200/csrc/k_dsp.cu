@@ -150,6 +150,8 @@ __device__ __forceinline__ void set_flag_byte(uint4& f, int p, unsigned v) {
   w = (w & ~(0xffu << sh)) | (v << sh);
 }
 
+constexpr int kFilterSmemKeys = 16384;
+
 // ---------------------------------------------------------------------------------------------
 // A2  filterPointCloud (risk_mapping_node.cpp:74-99): pcl::VoxelGrid centroid per leaf in ascending leaf
 // index, camera -> body axes, range test in double, first max_points kept.  One CTA per agent.
@@ -158,16 +160,14 @@ __global__ void __launch_bounds__(1024) k_dsp_filter(DspGeo G, const DspFrame* _
                                                      unsigned long long* __restrict__ keys_all,
                                                      float* __restrict__ pts_all, int* __restrict__ npts,
                                                      int* __restrict__ err) {
+  extern __shared__ unsigned long long s_keys[];   // kFilterSmemKeys sort keys
   const int a = blockIdx.x, tid = threadIdx.x;
   __shared__ unsigned s_mn[3], s_mx[3];
   __shared__ int s_w[33];
-  __shared__ int s_n;
   const int n = fr[a].n_in;
   const float* cam = cam_all + static_cast<size_t>(a) * G.MAXIN * 3;
-  unsigned long long* keys = keys_all + static_cast<size_t>(a) * G.NPOW2;
   float* pts = pts_all + static_cast<size_t>(a) * G.MAXPTS * 3;
   if (tid < 3) { s_mn[tid] = 0xffffffffu; s_mx[tid] = 0u; }
-  if (tid == 0) s_n = 0;
   __syncthreads();
   const float inv = 1.0f / G.filt;
   for (int i = tid; i < n; i += blockDim.x) {
@@ -181,6 +181,8 @@ __global__ void __launch_bounds__(1024) k_dsp_filter(DspGeo G, const DspFrame* _
   __syncthreads();
   int np2 = 1;
   while (np2 < n) np2 <<= 1;
+  // clouds of up to kFilterSmemKeys points are sorted in shared memory, larger ones in their (L2-resident) global segment
+  unsigned long long* keys = np2 <= kFilterSmemKeys ? s_keys : keys_all + static_cast<size_t>(a) * G.NPOW2;
   if (s_mx[0] == 0u || n == 0) {  // no finite point
     if (tid == 0) npts[a] = 0;
     return;
@@ -654,13 +656,18 @@ __global__ void __launch_bounds__(256) k_dsp_pred_move(DspGeo G, const DspFrame*
                                                        uint8_t* __restrict__ r_slot, uint8_t* __restrict__ r_state,
                                                        float4* __restrict__ r_a, float4* __restrict__ r_b,
                                                        int* __restrict__ vhead_all, int* __restrict__ pcount_all,
-                                                       int* __restrict__ stats, int* __restrict__ err) {
+                                                       int* __restrict__ stats, int* __restrict__ err,
+                                                       const int* __restrict__ act_all, const int* __restrict__ nact,
+                                                       int* __restrict__ touch_all, int* __restrict__ ntouch) {
   const int a = blockIdx.y;
   if (!fr[a].ok) return;
-  const int v = blockIdx.x * blockDim.x + threadIdx.x;
-  if (v >= G.V) return;
+  const int* act = act_all + static_cast<size_t>(a) * G.V;
+  int* touch = touch_all + static_cast<size_t>(a) * G.V;
+  const int na = nact[a];
+  for (int ai = blockIdx.x * blockDim.x + threadIdx.x; ai < na; ai += gridDim.x * blockDim.x) {
+  const int v = act[ai];
   const uint4 f = *reinterpret_cast<const uint4*>(flags_all + (static_cast<size_t>(a) * G.V + v) * kDspSlotStride);
-  if ((f.x | f.y | f.z | f.w) == 0u) return;
+  if ((f.x | f.y | f.z | f.w) == 0u) continue;
   const int nplanes = G.nph + 1 + G.npv + 1;
   const float* bph = bp_all + static_cast<size_t>(a) * nplanes * 3;
   const float* bpv = bph + 3 * (G.nph + 1);
@@ -692,8 +699,11 @@ __global__ void __launch_bounds__(256) k_dsp_pred_move(DspGeo G, const DspFrame*
     r_state[rbase + r] = 3;  // bit0 placed in its voxel, bit1 admitted to its pyramid
     r_a[rbase + r] = A;
     r_b[rbase + r] = B;
-    r_next[rbase + r] = atomicExch(&vhead[dest], r);
+    const int old = atomicExch(&vhead[dest], r);
+    r_next[rbase + r] = old;
+    if (old < 0) touch[atomicAdd(&ntouch[a], 1)] = dest;   // first arrival: the voxel joins the touched list (<= V entries)
     if (py >= 0) atomicAdd(&pcount[py], 1);
+  }
   }
 }
 
@@ -726,15 +736,15 @@ __global__ void __launch_bounds__(256) k_dsp_pyr_fill(DspGeo G, const DspFrame* 
                                                       int* __restrict__ plist) {
   const int a = blockIdx.y;
   if (!fr[a].ok) return;
-  const int r = blockIdx.x * blockDim.x + threadIdx.x;
   const int n = nrec[a] < G.RCAP ? nrec[a] : G.RCAP;
-  if (r >= n) return;
   const size_t rbase = static_cast<size_t>(a) * G.RCAP;
-  const int py = r_pyr[rbase + r];
-  if (py < 0) return;
-  const int pos = poff_all[static_cast<size_t>(a) * (G.NP + 1) + py] +
-                  atomicAdd(&pcur_all[static_cast<size_t>(a) * (G.NP + 1) + py], 1);
-  plist[rbase + pos] = r;
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < n; r += gridDim.x * blockDim.x) {
+    const int py = r_pyr[rbase + r];
+    if (py < 0) continue;
+    const int pos = poff_all[static_cast<size_t>(a) * (G.NP + 1) + py] +
+                    atomicAdd(&pcur_all[static_cast<size_t>(a) * (G.NP + 1) + py], 1);
+    plist[rbase + pos] = r;
+  }
 }
 
 // P4: order every pyramid's candidates by sweep time (warp per pyramid, rank by counting)
@@ -767,14 +777,17 @@ __global__ void __launch_bounds__(256) k_dsp_pred_voxel(DspGeo G, const DspFrame
                                                         const unsigned* __restrict__ r_key,
                                                         const int* __restrict__ r_next, const int* __restrict__ r_pyr,
                                                         uint8_t* __restrict__ r_slot, uint8_t* __restrict__ r_state,
-                                                        const int* __restrict__ vhead_all) {
+                                                        const int* __restrict__ vhead_all,
+                                                        const int* __restrict__ touch_all,
+                                                        const int* __restrict__ ntouch) {
   const int a = blockIdx.y;
   if (!fr[a].ok) return;
   if (round > 1 && changed_all[a * (kDspMaxIter + 2) + round - 1] == 0) return;
-  const int u = blockIdx.x * blockDim.x + threadIdx.x;
-  if (u >= G.V) return;
+  const int nt = ntouch[a];
+  for (int ti = blockIdx.x * blockDim.x + threadIdx.x; ti < nt; ti += gridDim.x * blockDim.x) {
+  const int u = touch_all[static_cast<size_t>(a) * G.V + ti];
   const int head = vhead_all[static_cast<size_t>(a) * G.V + u];
-  if (head < 0) return;
+  if (head < 0) continue;
   const size_t rbase = static_cast<size_t>(a) * G.RCAP;
   const uint4 f = *reinterpret_cast<const uint4*>(flags_all + (static_cast<size_t>(a) * G.V + u) * kDspSlotStride);
   unsigned mask = 0, proc = 0;
@@ -819,6 +832,7 @@ __global__ void __launch_bounds__(256) k_dsp_pred_voxel(DspGeo G, const DspFrame
         if (admitted) mask |= 1u << s;
       }
     }
+  }
   }
 }
 
@@ -865,16 +879,21 @@ __global__ void __launch_bounds__(256) k_dsp_pred_commit(DspGeo G, const DspFram
                                                          const uint8_t* __restrict__ r_state,
                                                          const float4* __restrict__ r_a, const float4* __restrict__ r_b,
                                                          int* __restrict__ vhead_all, int* __restrict__ stats,
-                                                         int* __restrict__ err) {
+                                                         int* __restrict__ err, const int* __restrict__ list_all,
+                                                         const int* __restrict__ nlist, int touched_pass) {
   const int a = blockIdx.y;
   if (!fr[a].ok) return;
-  const int u = blockIdx.x * blockDim.x + threadIdx.x;
-  if (u >= G.V) return;
-  if (u == 0 && changed_all[a * (kDspMaxIter + 2) + kDspMaxIter] != 0) atomicOr(err, 32);  // no fixed point
+  if (blockIdx.x == 0 && threadIdx.x == 0 && changed_all[a * (kDspMaxIter + 2) + kDspMaxIter] != 0)
+    atomicOr(err, 32);  // no fixed point
+  const int nl = nlist[a];
+  for (int li = blockIdx.x * blockDim.x + threadIdx.x; li < nl; li += gridDim.x * blockDim.x) {
+  const int u = list_all[static_cast<size_t>(a) * G.V + li];
   uint4* fp = reinterpret_cast<uint4*>(flags_all + (static_cast<size_t>(a) * G.V + u) * kDspSlotStride);
   uint4 f = *fp;
   const int head = vhead_all[static_cast<size_t>(a) * G.V + u];
-  if (head < 0 && (f.x | f.y | f.z | f.w) == 0u) return;
+  // pass 1 (touched list, runs first): voxels that held nothing; pass 2 (active list): every voxel that held something
+  if (touched_pass && (f.x | f.y | f.z | f.w) != 0u) continue;
+  if (head < 0 && (f.x | f.y | f.z | f.w) == 0u) continue;
   bool dirty = false;
   for (int p = 0; p < G.S; p++) {
     const unsigned fl = flag_byte(f, p);
@@ -900,6 +919,7 @@ __global__ void __launch_bounds__(256) k_dsp_pred_commit(DspGeo G, const DspFram
   if (head >= 0) vhead_all[static_cast<size_t>(a) * G.V + u] = -1;
   if (n_vox) atomicAdd(&stats[8 * a + 0], n_vox);
   if (n_pyr) atomicAdd(&stats[8 * a + 1], n_pyr);
+  }
 }
 
 // pyramids_in_fov: the admitted particles of every pyramid in sweep order, with a copy of their state
@@ -1031,7 +1051,8 @@ __global__ void __launch_bounds__(1024) k_dsp_born(DspGeo G, const DspFrame* __r
                                                    int* __restrict__ seq_all, int* __restrict__ b_dest,
                                                    int* __restrict__ b_next, float4* __restrict__ b_a,
                                                    float4* __restrict__ b_b, int* __restrict__ vhead_all,
-                                                   int* __restrict__ err) {
+                                                   int* __restrict__ err, int* __restrict__ touch2_all,
+                                                   int* __restrict__ ntouch2) {
   extern __shared__ unsigned char smem_raw[];
   const int a = blockIdx.x, tid = threadIdx.x, nth = blockDim.x;
   if (!fr[a].ok) return;
@@ -1154,7 +1175,9 @@ __global__ void __launch_bounds__(1024) k_dsp_born(DspGeo G, const DspFrame* __r
         b_dest[bi] = vi;
         b_a[bi] = make_float4(vx, vy, vz, w_born);
         b_b[bi] = make_float4(px, py, pz, 0.f);
-        b_next[bi] = atomicExch(&vhead[vi], static_cast<int>(static_cast<size_t>(q) * G.NB + p));
+        const int old = atomicExch(&vhead[vi], static_cast<int>(static_cast<size_t>(q) * G.NB + p));
+        b_next[bi] = old;
+        if (old < 0) touch2_all[static_cast<size_t>(a) * G.V + atomicAdd(&ntouch2[a], 1)] = vi;
       }
     } else if (q < n) {
       for (int p = 0; p < G.NB; p++) b_dest[bbase + static_cast<size_t>(q) * G.NB + p] = -1;
@@ -1175,13 +1198,16 @@ __global__ void __launch_bounds__(256) k_dsp_born_place(DspGeo G, const DspFrame
                                                         uint8_t* __restrict__ flags_all, float4* __restrict__ pa_all,
                                                         float4* __restrict__ pb_all, const int* __restrict__ b_next,
                                                         const float4* __restrict__ b_a, const float4* __restrict__ b_b,
-                                                        int* __restrict__ vhead_all, int* __restrict__ stats) {
+                                                        int* __restrict__ vhead_all, int* __restrict__ stats,
+                                                        const int* __restrict__ touch2_all,
+                                                        const int* __restrict__ ntouch2) {
   const int a = blockIdx.y;
   if (!fr[a].ok) return;
-  const int u = blockIdx.x * blockDim.x + threadIdx.x;
-  if (u >= G.V) return;
+  const int nt = ntouch2[a];
+  for (int ti = blockIdx.x * blockDim.x + threadIdx.x; ti < nt; ti += gridDim.x * blockDim.x) {
+  const int u = touch2_all[static_cast<size_t>(a) * G.V + ti];
   const int head = vhead_all[static_cast<size_t>(a) * G.V + u];
-  if (head < 0) return;
+  if (head < 0) continue;
   vhead_all[static_cast<size_t>(a) * G.V + u] = -1;
   const size_t bbase = static_cast<size_t>(a) * G.MAXPTS * G.NB;
   uint4* fp = reinterpret_cast<uint4*>(flags_all + (static_cast<size_t>(a) * G.V + u) * kDspSlotStride);
@@ -1204,6 +1230,7 @@ __global__ void __launch_bounds__(256) k_dsp_born_place(DspGeo G, const DspFrame
   }
   *fp = f;
   if (born) atomicAdd(&stats[8 * a + 3], born);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1213,15 +1240,32 @@ __global__ void __launch_bounds__(256) k_dsp_born_place(DspGeo G, const DspFrame
 __global__ void __launch_bounds__(256) k_dsp_occupancy(DspGeo G, const DspFrame* __restrict__ fr,
                                                        uint8_t* __restrict__ flags_all, float4* __restrict__ pa_all,
                                                        float4* __restrict__ pb_all, float4* __restrict__ vobj_all,
-                                                       uint8_t* __restrict__ grid, unsigned long long agent_stride) {
+                                                       uint8_t* __restrict__ grid, unsigned long long agent_stride,
+                                                       const int* __restrict__ act_all, const int* __restrict__ nact,
+                                                       const int* __restrict__ touch_all, const int* __restrict__ ntouch,
+                                                       const int* __restrict__ touch2_all,
+                                                       const int* __restrict__ ntouch2, int* __restrict__ vstamp_all,
+                                                       int stamp, int* __restrict__ act_next_all,
+                                                       int* __restrict__ nact_next) {
   const int a = blockIdx.y;
-  if (!fr[a].ok) return;
-  const int v = blockIdx.x * blockDim.x + threadIdx.x;
-  if (v >= G.V) return;
+  const int n0 = nact[a];
+  int* act_next = act_next_all + static_cast<size_t>(a) * G.V;
+  if (!fr[a].ok) {  // rejected update: the map is untouched, its active list carries over
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n0; i += gridDim.x * blockDim.x)
+      act_next[i] = act_all[static_cast<size_t>(a) * G.V + i];
+    if (blockIdx.x == 0 && threadIdx.x == 0) nact_next[a] = n0;
+    return;
+  }
+  const int n1 = ntouch[a], n2 = ntouch2[a];
+  for (int li = blockIdx.x * blockDim.x + threadIdx.x; li < n0 + n1 + n2; li += gridDim.x * blockDim.x) {
+  const int v = li < n0 ? act_all[static_cast<size_t>(a) * G.V + li]
+                        : li < n0 + n1 ? touch_all[static_cast<size_t>(a) * G.V + li - n0]
+                                       : touch2_all[static_cast<size_t>(a) * G.V + li - n0 - n1];
+  if (atomicExch(&vstamp_all[static_cast<size_t>(a) * G.V + v], stamp) == stamp) continue;  // listed more than once
   uint4* fp = reinterpret_cast<uint4*>(flags_all + (static_cast<size_t>(a) * G.V + v) * kDspSlotStride);
   uint4 f = *fp;
   float4* vo = vobj_all + static_cast<size_t>(a) * G.V + v;
-  if ((f.x | f.y | f.z | f.w) == 0u) { *vo = make_float4(0.f, 0.f, 0.f, 0.f); return; }
+  if ((f.x | f.y | f.z | f.w) == 0u) { *vo = make_float4(0.f, 0.f, 0.f, 0.f); continue; }
   float* sogm = reinterpret_cast<float*>(grid + a * agent_stride);
   float4* pa = pa_all + (static_cast<size_t>(a) * G.V + v) * G.S;
   float4* pb = pb_all + (static_cast<size_t>(a) * G.V + v) * G.S;
@@ -1292,6 +1336,8 @@ __global__ void __launch_bounds__(256) k_dsp_occupancy(DspGeo G, const DspFrame*
     }
   }
   *fp = f;
+  if ((f.x | f.y | f.z | f.w) != 0u) act_next[atomicAdd(&nact_next[a], 1)] = v;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1342,6 +1388,9 @@ size_t vel_smem_bytes(const DspGeo& G) {
   return sizeof(float) * 3 * G.MAXPTS + sizeof(int) * 3 * G.MAXPTS + sizeof(int) * 4 * kDspMaxClusters +
          sizeof(float) * 7 * kDspMaxClusters;
 }
+size_t filter_smem_bytes(const DspGeo& G) {
+  return sizeof(unsigned long long) * static_cast<size_t>(G.NPOW2 < kFilterSmemKeys ? G.NPOW2 : kFilterSmemKeys);
+}
 size_t bin_smem_bytes(const DspGeo& G) {
   const int nplanes = G.nph + 1 + G.npv + 1;
   return sizeof(float) * ((nplanes * 3 + 3) & ~3) + sizeof(int) * 2 * G.NP + sizeof(int) * 1024;
@@ -1365,8 +1414,12 @@ void popk_dsp_free(pop_handle* h) {
                   d->ncv, d->cl_last, d->ncl_last, d->cost, d->nrec, d->r_key, d->r_dest, d->r_next, d->r_pyr,
                   d->r_slot, d->r_state, d->r_a, d->r_b, d->vhead, d->pcount, d->poff, d->pcur, d->plist,
                   d->plist2, d->changed, d->pyr_n, d->pyr_ref, d->pyr_p, d->b_dest, d->b_next, d->b_a, d->b_b,
-                  d->seq, d->stats, d->err};
+                  d->seq, d->stats, d->err, d->act[0], d->act[1], d->nact[0], d->nact[1], d->touch, d->ntouch,
+                  d->touch2, d->ntouch2, d->vstamp, d->ok_dev};
   for (void* p : ptrs) if (p) cudaFree(p);
+  if (d->side) cudaStreamDestroy(d->side);
+  if (d->ev_fork) cudaEventDestroy(d->ev_fork);
+  if (d->ev_join) cudaEventDestroy(d->ev_join);
   delete d;
   h->dsp = nullptr;
 }
@@ -1453,6 +1506,14 @@ int popk_dsp_alloc(pop_handle* h, const pop_dsp_config* c) {
   DSP_ALLOC(d->pyr_p, static_cast<size_t>(A) * G.NP * G.PCAP);
   const size_t bcap = static_cast<size_t>(A) * G.MAXPTS * G.NB;
   DSP_ALLOC(d->b_dest, bcap); DSP_ALLOC(d->b_next, bcap); DSP_ALLOC(d->b_a, bcap); DSP_ALLOC(d->b_b, bcap);
+  const size_t AV = static_cast<size_t>(A) * G.V;
+  DSP_ALLOC(d->act[0], AV); DSP_ALLOC(d->act[1], AV); DSP_ALLOC(d->nact[0], A); DSP_ALLOC(d->nact[1], A);
+  DSP_ALLOC(d->touch, AV); DSP_ALLOC(d->ntouch, A); DSP_ALLOC(d->touch2, AV); DSP_ALLOC(d->ntouch2, A);
+  DSP_ALLOC(d->vstamp, AV);
+  DSP_ALLOC(d->ok_dev, A);
+  POP_CUDA(h, cudaStreamCreateWithFlags(&d->side, cudaStreamNonBlocking));
+  POP_CUDA(h, cudaEventCreateWithFlags(&d->ev_fork, cudaEventDisableTiming));
+  POP_CUDA(h, cudaEventCreateWithFlags(&d->ev_join, cudaEventDisableTiming));
   DSP_ALLOC(d->seq, A * 4);
   DSP_ALLOC(d->stats, A * 8);
   DSP_ALLOC(d->err, 1);
@@ -1487,6 +1548,8 @@ int popk_dsp_alloc(pop_handle* h, const pop_dsp_config* c) {
   d->h_frame.resize(A);
   POP_CUDA(h, cudaFuncSetAttribute(k_dsp_velocity, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    static_cast<int>(vel_smem_bytes(G))));
+  POP_CUDA(h, cudaFuncSetAttribute(k_dsp_filter, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   static_cast<int>(filter_smem_bytes(G))));
   POP_CUDA(h, cudaFuncSetAttribute(k_dsp_bin, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    static_cast<int>(bin_smem_bytes(G))));
   POP_CUDA(h, cudaFuncSetAttribute(k_dsp_born, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1496,7 +1559,7 @@ int popk_dsp_alloc(pop_handle* h, const pop_dsp_config* c) {
 
 int popk_dsp_filter_only(pop_handle* h) {
   DspDev* d = h->dsp;
-  k_dsp_filter<<<d->nl, 1024, 0, h->stream>>>(d->G, d->frame, d->cam, d->fkeys, d->pts, d->npts, d->err);
+  k_dsp_filter<<<d->nl, 1024, filter_smem_bytes(d->G), h->stream>>>(d->G, d->frame, d->cam, d->fkeys, d->pts, d->npts, d->err);
   POP_LAUNCH_CHECK(h);
   h->n_launches++;
   return POP_OK;
@@ -1510,35 +1573,51 @@ int popk_dsp_update(pop_handle* h, int filtered) {
   int launches = 0;
   pop_prof_begin(h, POP_STAGE_DSP);
   if (!filtered) {
-    k_dsp_filter<<<A, 1024, 0, st>>>(G, d->frame, d->cam, d->fkeys, d->pts, d->npts, d->err);
+    k_dsp_filter<<<A, 1024, filter_smem_bytes(G), st>>>(G, d->frame, d->cam, d->fkeys, d->pts, d->npts, d->err);
     POP_LAUNCH_CHECK(h); launches++;
   }
   k_dsp_bin<<<A, 1024, bin_smem_bytes(G), st>>>(G, d->frame, d->bp_ori, d->bp, d->pts, d->npts, d->rot, d->pobs,
                                                 d->obs, d->obs_num, d->obs_maxlen, d->valid);
   POP_LAUNCH_CHECK(h); launches++;
-  k_dsp_velocity<<<A, 1024, vel_smem_bytes(G), st>>>(G, d->frame, d->rot, d->npts, d->ur, d->seq, d->cv, d->ncv,
-                                                     d->cl_last, d->ncl_last, d->cost, d->err);
+  // velocityEstimationThread runs beside prediction + update, as the reference's side thread does (:305-320);
+  // it shares only the rand() sequence counter with the newborn step, which waits for it
+  POP_CUDA(h, cudaEventRecord(d->ev_fork, st));
+  POP_CUDA(h, cudaStreamWaitEvent(d->side, d->ev_fork, 0));
+  k_dsp_velocity<<<A, 1024, vel_smem_bytes(G), d->side>>>(G, d->frame, d->rot, d->npts, d->ur, d->seq, d->cv, d->ncv,
+                                                          d->cl_last, d->ncl_last, d->cost, d->err);
   POP_LAUNCH_CHECK(h); launches++;
+  POP_CUDA(h, cudaEventRecord(d->ev_join, d->side));
   // --- prediction ---
   POP_CUDA(h, cudaMemsetAsync(d->nrec, 0, sizeof(int) * A, st));
   POP_CUDA(h, cudaMemsetAsync(d->pcount, 0, sizeof(int) * static_cast<size_t>(A) * (G.NP + 1), st));
   POP_CUDA(h, cudaMemsetAsync(d->changed, 0, sizeof(int) * A * (kDspMaxIter + 2), st));
-  const dim3 gv((G.V + 255) / 256, A);
+  POP_CUDA(h, cudaMemsetAsync(d->ntouch, 0, sizeof(int) * A, st));
+  POP_CUDA(h, cudaMemsetAsync(d->ntouch2, 0, sizeof(int) * A, st));
+  int* act = d->act[d->cur];
+  int* nact = d->nact[d->cur];
+  int* act_next = d->act[d->cur ^ 1];
+  int* nact_next = d->nact[d->cur ^ 1];
+  POP_CUDA(h, cudaMemsetAsync(nact_next, 0, sizeof(int) * A, st));
+  // the per-voxel passes walk work lists (grid-stride): enough CTAs to fill the GPU, no more
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
+  const int per_agent = (sms * 8 + A - 1) / A;
+  const int vblocks = (G.V + 255) / 256;
+  const dim3 gv(per_agent < vblocks ? per_agent : vblocks, A);
   const dim3 gp((G.NP * 32 + 255) / 256, A);
   k_dsp_pred_move<<<gv, 256, 0, st>>>(G, d->frame, d->bp, d->flags, d->pa, d->pb, d->nrec, d->r_key, d->r_dest,
                                       d->r_next, d->r_pyr, d->r_slot, d->r_state, d->r_a, d->r_b, d->vhead, d->pcount,
-                                      d->stats, d->err);
+                                      d->stats, d->err, act, nact, d->touch, d->ntouch);
   POP_LAUNCH_CHECK(h); launches++;
   k_dsp_pyr_scan<<<A, 1024, 0, st>>>(G, d->frame, d->pcount, d->poff, d->pcur);
   POP_LAUNCH_CHECK(h); launches++;
-  const dim3 gr((G.RCAP + 255) / 256, A);
-  k_dsp_pyr_fill<<<gr, 256, 0, st>>>(G, d->frame, d->nrec, d->r_pyr, d->poff, d->pcur, d->plist);
+  k_dsp_pyr_fill<<<gv, 256, 0, st>>>(G, d->frame, d->nrec, d->r_pyr, d->poff, d->pcur, d->plist);
   POP_LAUNCH_CHECK(h); launches++;
   k_dsp_pyr_sort<<<gp, 256, 0, st>>>(G, d->frame, d->r_key, d->poff, d->plist, d->plist2);
   POP_LAUNCH_CHECK(h); launches++;
   for (int round = 1; round <= kDspMaxIter; round++) {
     k_dsp_pred_voxel<<<gv, 256, 0, st>>>(G, d->frame, round, d->changed, d->flags, d->r_key, d->r_next, d->r_pyr,
-                                         d->r_slot, d->r_state, d->vhead);
+                                         d->r_slot, d->r_state, d->vhead, d->touch, d->ntouch);
     POP_LAUNCH_CHECK(h); launches++;
     k_dsp_pred_pyr<<<gp, 256, 0, st>>>(G, d->frame, round, d->changed, d->poff, d->plist2, d->r_state);
     POP_LAUNCH_CHECK(h); launches++;
@@ -1547,7 +1626,12 @@ int popk_dsp_update(pop_handle* h, int filtered) {
                                        d->r_b, d->pyr_n, d->pyr_ref, d->pyr_p);
   POP_LAUNCH_CHECK(h); launches++;
   k_dsp_pred_commit<<<gv, 256, 0, st>>>(G, d->frame, d->changed, d->flags, d->pa, d->pb, d->r_key, d->r_next,
-                                        d->r_pyr, d->r_slot, d->r_state, d->r_a, d->r_b, d->vhead, d->stats, d->err);
+                                        d->r_pyr, d->r_slot, d->r_state, d->r_a, d->r_b, d->vhead, d->stats, d->err,
+                                        d->touch, d->ntouch, 1);
+  POP_LAUNCH_CHECK(h); launches++;
+  k_dsp_pred_commit<<<gv, 256, 0, st>>>(G, d->frame, d->changed, d->flags, d->pa, d->pb, d->r_key, d->r_next,
+                                        d->r_pyr, d->r_slot, d->r_state, d->r_a, d->r_b, d->vhead, d->stats, d->err,
+                                        act, nact, 0);
   POP_LAUNCH_CHECK(h); launches++;
   // --- update ---
   k_dsp_update_ck<<<dim3((G.MAXPTS + 127) / 128, A), 128, 0, st>>>(G, d->frame, d->npts, d->pobs, d->obs, d->valid,
@@ -1558,12 +1642,13 @@ int popk_dsp_update(pop_handle* h, int filtered) {
                                                                        d->pa, d->pdf);
   POP_LAUNCH_CHECK(h); launches++;
   // --- newborn ---
+  POP_CUDA(h, cudaStreamWaitEvent(st, d->ev_join, 0));
   k_dsp_born<<<A, 1024, sizeof(float) * G.MAXPTS, st>>>(G, d->frame, d->cv, d->ncv, d->obs, d->obs_num, d->flags,
                                                         d->pa, d->pg, d->vg, d->ur, d->seq, d->b_dest, d->b_next,
-                                                        d->b_a, d->b_b, d->vhead, d->err);
+                                                        d->b_a, d->b_b, d->vhead, d->err, d->touch2, d->ntouch2);
   POP_LAUNCH_CHECK(h); launches++;
   k_dsp_born_place<<<gv, 256, 0, st>>>(G, d->frame, d->flags, d->pa, d->pb, d->b_next, d->b_a, d->b_b, d->vhead,
-                                       d->stats);
+                                       d->stats, d->touch2, d->ntouch2);
   POP_LAUNCH_CHECK(h); launches++;
   // --- occupancy, future deposits into the SOGM, resampling ---
   for (int a = 0; a < A;) {   // runs of accepted agents: one bulk-store launch per run (one launch in all if every update is accepted)
@@ -1575,10 +1660,13 @@ int popk_dsp_update(pop_handle* h, int filtered) {
     launches++;
     a = b;
   }
-  k_dsp_occupancy<<<gv, 256, 0, st>>>(G, d->frame, d->flags, d->pa, d->pb, d->vobj, h->d_grid, h->geom.agent_stride);
-  POP_LAUNCH_CHECK(h); launches++;
-  pop_prof_end(h, POP_STAGE_DSP, launches);
   d->updates++;
+  k_dsp_occupancy<<<gv, 256, 0, st>>>(G, d->frame, d->flags, d->pa, d->pb, d->vobj, h->d_grid, h->geom.agent_stride,
+                                      act, nact, d->touch, d->ntouch, d->touch2, d->ntouch2, d->vstamp, d->updates,
+                                      act_next, nact_next);
+  POP_LAUNCH_CHECK(h); launches++;
+  d->cur ^= 1;
+  pop_prof_end(h, POP_STAGE_DSP, launches);
   return POP_OK;
 }
 

@@ -76,6 +76,16 @@ struct DspDev {
   float4* pyr_p = nullptr;    // [A][NP][PCAP] (px, py, pz, weight)
   // newborn records, index = point*NB + p
   int* b_dest = nullptr; int* b_next = nullptr; float4* b_a = nullptr; float4* b_b = nullptr;  // [A][MAXPTS*NB]
+  // voxel work lists (a voxel appears at most once in each): the per-voxel passes never sweep the grid
+  int* act[2] = {nullptr, nullptr};   // [A][V] voxels holding particles, ping-pong (written by the occupancy pass)
+  int* nact[2] = {nullptr, nullptr};  // [A]
+  int* touch = nullptr; int* ntouch = nullptr;     // [A][V] voxels that received a moved particle this update
+  int* touch2 = nullptr; int* ntouch2 = nullptr;   // [A][V] voxels that received a newborn particle
+  int* ok_dev = nullptr;      // [A] accepted flags of the current update (mask of the peer projection)
+  int* vstamp = nullptr;      // [A][V] update id of the last occupancy pass over the voxel (de-duplication)
+  int cur = 0;                // which act[] is current
+  cudaStream_t side = nullptr;         // clustering/assignment runs beside prediction+update (the reference's side thread)
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   int* seq = nullptr;         // [A][4] sequence counters of the three tables
   int* stats = nullptr;       // [A][8]
   int* err = nullptr;         // [1] device-side error flags

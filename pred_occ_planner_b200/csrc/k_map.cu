@@ -174,12 +174,14 @@ __global__ void __launch_bounds__(256) k_peer_scatter(PopGeom g, uint8_t* __rest
                                                       const double* __restrict__ peer_pos,
                                                       const int8_t* __restrict__ peer_valid,
                                                       const double* __restrict__ body,
-                                                      const int* __restrict__ body_count) {
+                                                      const int* __restrict__ body_count,
+                                                      const int* __restrict__ agent_ok) {
   // thread per (ego a, peer i, slice k, body particle j); j fastest
   const long long tid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const long long per_agent = static_cast<long long>(n_total) * g.nt * POP_MAX_BODY;
   if (tid >= per_agent * n_local) return;
   const int a = static_cast<int>(tid / per_agent);
+  if (agent_ok && !agent_ok[a]) return;   // this agent's map was not refreshed (rejected particle-map update)
   long long r = tid % per_agent;
   const int i = static_cast<int>(r / (g.nt * POP_MAX_BODY));
   r %= g.nt * POP_MAX_BODY;
@@ -714,11 +716,11 @@ int popk_peer_project(pop_handle* h) {
   if (h->cfg.cell_dtype == POP_CELL_U8)
     k_peer_scatter<uint8_t><<<blocks, 256, 0, h->stream>>>(g, h->d_grid, h->d_poses, nl, ntot,
                                                           h->cfg.agent_id_base, h->d_peer_pos,
-                                                          h->d_peer_valid, h->d_body, h->d_body_count);
+                                                          h->d_peer_valid, h->d_body, h->d_body_count, h->d_agent_ok);
   else
     k_peer_scatter<float><<<blocks, 256, 0, h->stream>>>(g, h->d_grid, h->d_poses, nl, ntot,
                                                         h->cfg.agent_id_base, h->d_peer_pos,
-                                                        h->d_peer_valid, h->d_body, h->d_body_count);
+                                                        h->d_peer_valid, h->d_body, h->d_body_count, h->d_agent_ok);
   POP_LAUNCH_CHECK(h);
   pop_prof_end(h, POP_STAGE_PEERS, 2);
   return POP_OK;

@@ -93,7 +93,18 @@ int run_update(pop_handle* h, const float* in, int stride_pts, const int32_t* co
   if (rc) return rc;
   h->t_map = stamp;
   h->map_ready = true;
-  rc = popk_peer_project(h);   // RiskBase::futureRiskCallback -> addOtherAgents (risk_base.cpp:70-72)
+  // RiskBase::futureRiskCallback -> addOtherAgents (risk_base.cpp:70-72); an agent whose update was rejected
+  // published no new future risk, so its grid (peers included) stays as it was
+  bool all_ok = true;
+  std::vector<int> okv(A);
+  for (int a = 0; a < A; a++) { okv[a] = d->h_frame[a].ok; all_ok = all_ok && okv[a]; }
+  if (!all_ok) {
+    POP_CUDA(h, cudaMemcpyAsync(d->ok_dev, okv.data(), sizeof(int) * A, cudaMemcpyHostToDevice, h->stream));
+    POP_CUDA(h, cudaStreamSynchronize(h->stream));   // okv is a stack-owned staging buffer
+    h->d_agent_ok = d->ok_dev;
+  }
+  rc = popk_peer_project(h);
+  h->d_agent_ok = nullptr;
   if (rc) return rc;
   return check_device_err(h);
 }

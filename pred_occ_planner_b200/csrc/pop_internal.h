@@ -74,6 +74,7 @@ struct pop_handle {
   double* d_peer_pos = nullptr;   // n_total x nt x 3 world positions of peers per slice
   int8_t* d_peer_valid = nullptr; // n_total x nt
   bool have_body = false, have_traj = false;
+  const int* d_agent_ok = nullptr; // optional per-agent mask of the peer projection (set around a particle-map update)
 
   // scratch for host<->device staging (pinned) and queries
   void* h_pinned = nullptr; size_t h_pinned_bytes = 0;

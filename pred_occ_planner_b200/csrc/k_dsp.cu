@@ -664,7 +664,9 @@ __global__ void __launch_bounds__(256) k_dsp_pred_move(DspGeo G, const DspFrame*
   const int* act = act_all + static_cast<size_t>(a) * G.V;
   int* touch = touch_all + static_cast<size_t>(a) * G.V;
   const int na = nact[a];
-  for (int ai = blockIdx.x * blockDim.x + threadIdx.x; ai < na; ai += gridDim.x * blockDim.x) {
+  // 16 lanes per active voxel, one slot each
+  const int lane16 = threadIdx.x & 15;
+  for (int ai = (blockIdx.x * blockDim.x + threadIdx.x) >> 4; ai < na; ai += (gridDim.x * blockDim.x) >> 4) {
   const int v = act[ai];
   const uint4 f = *reinterpret_cast<const uint4*>(flags_all + (static_cast<size_t>(a) * G.V + v) * kDspSlotStride);
   if ((f.x | f.y | f.z | f.w) == 0u) continue;
@@ -675,7 +677,7 @@ __global__ void __launch_bounds__(256) k_dsp_pred_move(DspGeo G, const DspFrame*
   const size_t rbase = static_cast<size_t>(a) * G.RCAP;
   int* vhead = vhead_all + static_cast<size_t>(a) * G.V;
   int* pcount = pcount_all + static_cast<size_t>(a) * (G.NP + 1);
-  for (int p = 0; p < G.S; p++) {
+  for (int p = lane16; p < G.S; p += 16) {
     const unsigned fl = flag_byte(f, p);
     if (fl != DSP_F_VALID && fl != DSP_F_COPY) continue;  // 0.1 < flag < 6
     const size_t si = (static_cast<size_t>(a) * G.V + v) * G.S + p;
@@ -754,17 +756,18 @@ __global__ void __launch_bounds__(256) k_dsp_pyr_sort(DspGeo G, const DspFrame* 
                                                       int* __restrict__ plist2) {
   const int a = blockIdx.y;
   if (!fr[a].ok) return;
-  const int py = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (py >= G.NP) return;
+  const int lane = threadIdx.x & 31;
   const size_t rbase = static_cast<size_t>(a) * G.RCAP;
   const int* poff = poff_all + static_cast<size_t>(a) * (G.NP + 1);
-  const int b = poff[py], e = poff[py + 1];
-  for (int i = b + lane; i < e; i += 32) {
-    const int r = plist[rbase + i];
-    const unsigned key = r_key[rbase + r];
-    int rank = 0;
-    for (int j = b; j < e; j++) rank += (r_key[rbase + plist[rbase + j]] < key);
-    plist2[rbase + b + rank] = r;
+  for (int py = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; py < G.NP; py += (gridDim.x * blockDim.x) >> 5) {
+    const int b = poff[py], e = poff[py + 1];
+    for (int i = b + lane; i < e; i += 32) {
+      const int r = plist[rbase + i];
+      const unsigned key = r_key[rbase + r];
+      int rank = 0;
+      for (int j = b; j < e; j++) rank += (r_key[rbase + plist[rbase + j]] < key);
+      plist2[rbase + b + rank] = r;
+    }
   }
 }
 
@@ -844,12 +847,13 @@ __global__ void __launch_bounds__(256) k_dsp_pred_pyr(DspGeo G, const DspFrame* 
   if (!fr[a].ok) return;
   int* changed = changed_all + a * (kDspMaxIter + 2);
   if (round > 1 && changed[round - 1] == 0) return;
-  const int py = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (py >= G.NP) return;
+  const int lane = threadIdx.x & 31;
   const size_t rbase = static_cast<size_t>(a) * G.RCAP;
   const int* poff = poff_all + static_cast<size_t>(a) * (G.NP + 1);
+  int diff = 0;
+  for (int py = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; py < G.NP; py += (gridDim.x * blockDim.x) >> 5) {
   const int b = poff[py], e = poff[py + 1];
-  int running = 0, diff = 0;
+  int running = 0;
   for (int i0 = b; i0 < e; i0 += 32) {
     const int i = i0 + lane;
     int r = -1;
@@ -863,6 +867,7 @@ __global__ void __launch_bounds__(256) k_dsp_pred_pyr(DspGeo G, const DspFrame* 
       if (adm != (st & 2u)) { diff++; r_state[rbase + r] = static_cast<uint8_t>((st & 1u) | adm); }
     }
     running += __popc(bal);
+  }
   }
   for (int o = 16; o > 0; o >>= 1) diff += __shfl_xor_sync(0xffffffffu, diff, o);
   if (lane == 0 && diff) atomicAdd(&changed[round], diff);
@@ -934,10 +939,10 @@ __global__ void __launch_bounds__(256) k_dsp_pyr_commit(DspGeo G, const DspFrame
                                                         float4* __restrict__ pyr_p) {
   const int a = blockIdx.y;
   if (!fr[a].ok) return;
-  const int py = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (py >= G.NP) return;
+  const int lane = threadIdx.x & 31;
   const size_t rbase = static_cast<size_t>(a) * G.RCAP;
   const int* poff = poff_all + static_cast<size_t>(a) * (G.NP + 1);
+  for (int py = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; py < G.NP; py += (gridDim.x * blockDim.x) >> 5) {
   const int b = poff[py], e = poff[py + 1];
   const size_t tb = (static_cast<size_t>(a) * G.NP + py) * G.PCAP;
   int running = 0;
@@ -957,6 +962,7 @@ __global__ void __launch_bounds__(256) k_dsp_pyr_commit(DspGeo G, const DspFrame
     running += __popc(bal);
   }
   if (lane == 0) pyr_n[static_cast<size_t>(a) * G.NP + py] = running < G.PCAP ? running : G.PCAP;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1604,7 +1610,8 @@ int popk_dsp_update(pop_handle* h, int filtered) {
   const int per_agent = (sms * 8 + A - 1) / A;
   const int vblocks = (G.V + 255) / 256;
   const dim3 gv(per_agent < vblocks ? per_agent : vblocks, A);
-  const dim3 gp((G.NP * 32 + 255) / 256, A);
+  const int pblocks = (G.NP * 32 + 255) / 256;
+  const dim3 gp(per_agent < pblocks ? per_agent : pblocks, A);
   k_dsp_pred_move<<<gv, 256, 0, st>>>(G, d->frame, d->bp, d->flags, d->pa, d->pb, d->nrec, d->r_key, d->r_dest,
                                       d->r_next, d->r_pyr, d->r_slot, d->r_state, d->r_a, d->r_b, d->vhead, d->pcount,
                                       d->stats, d->err, act, nact, d->touch, d->ntouch);

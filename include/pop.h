@@ -355,6 +355,32 @@ int pop_dsp_stats(pop_handle* h, int agent, int32_t* out);
  * occupancy_threshold, ascending voxel index; out = cap x 3 floats. */
 int pop_dsp_occupied(pop_handle* h, int agent, float* out, int cap, int32_t* n_out);
 
+/* ---- K0: depth sensor of the simulator (feeds the particle map without leaving the device) ------ */
+/* Pinhole camera of uav_simulator/local_sensing (params/camera.yaml; pcl_render_node.cpp:317-338). */
+typedef struct pop_camera {
+  float   fx, fy, cx, cy;
+  int32_t width, height;
+  float   sensing_horizon;       /* metres from the body position (pcl_render_node.cpp:241) */
+  int32_t _pad;
+  double  cam2body[16];          /* cam02body, row-major 4x4 (:338) */
+} pop_camera;
+/* reference camera (640x480, fx 387.229, horizon 6 m) scaled to width x height */
+void pop_camera_default(pop_camera* cam, int width, int height);
+int pop_render_set_camera(pop_handle* h, const pop_camera* cam);
+/* DepthRender::render_pose + render_currentpose + render_pcl_world for every local agent
+ * (uav_simulator/local_sensing/src/depth_render.cu:2-58, pcl_render_node.cpp:219-285): the world cloud of
+ * pop_set_world_cloud is splatted into one depth image per agent (int32 millimetres, 999999 = empty) and
+ * back-projected to camera-frame points within the sensing horizon.  pos n_local x 3, quat n_local x 4
+ * (w,x,y,z) body poses in double.  The clouds stay on the device as the input of pop_dsp_update_rendered;
+ * out_depth_mm (n_local x height x width) and out_counts (n_local) may be NULL. */
+int pop_render_depth(pop_handle* h, const double* pos, const double* quat, int32_t* out_depth_mm,
+                     int32_t* out_counts);
+/* the rendered camera-frame cloud of one agent: out = cap x 3 floats, u-major pixel order */
+int pop_render_download_cloud(pop_handle* h, int agent, float* out, int cap, int32_t* n_out);
+/* pop_dsp_update on the clouds the last pop_render_depth left on the device (no host cloud at all) */
+int pop_dsp_update_rendered(pop_handle* h, const float* poses, const float* quats, double stamp,
+                            int32_t* out_ok);
+
 /* ---- measurement ------------------------------------------------------------------------ */
 enum { POP_STAGE_VOXEL_UPDATE = 0, POP_STAGE_PEERS = 1, POP_STAGE_ASTAR = 2, POP_STAGE_CORRIDOR = 3,
        POP_STAGE_QP = 4, POP_STAGE_SEPARATION = 5, POP_STAGE_DSP = 6, POP_STAGE_COUNT = 8 };

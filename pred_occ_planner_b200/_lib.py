@@ -117,6 +117,13 @@ class PopDspConfig(C.Structure):
         return c
 
 
+class PopCamera(C.Structure):
+    """pop_camera (include/pop.h): pinhole depth camera of uav_simulator/local_sensing."""
+    _fields_ = [("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float), ("cy", C.c_float),
+                ("width", C.c_int32), ("height", C.c_int32), ("sensing_horizon", C.c_float), ("_pad", C.c_int32),
+                ("cam2body", C.c_double * 16)]
+
+
 class PopCycleIO(C.Structure):
     _fields_ = [("start", C.POINTER(C.c_double)), ("goal", C.POINTER(C.c_double)),
                 ("poses", C.POINTER(C.c_float)), ("t_map", C.c_double), ("t_plan", C.c_double),
@@ -181,6 +188,11 @@ SYMBOLS = [
     ("pop_dsp_download_points_with_velocity", _I, [_VP, _I, _PF, _I, _PI32]),
     ("pop_dsp_stats", _I, [_VP, _I, _PI32]),
     ("pop_dsp_occupied", _I, [_VP, _I, _PF, _I, _PI32]),
+    ("pop_camera_default", None, [C.POINTER(PopCamera), _I, _I]),
+    ("pop_render_set_camera", _I, [_VP, C.POINTER(PopCamera)]),
+    ("pop_render_depth", _I, [_VP, _PD, _PD, _PI32, _PI32]),
+    ("pop_render_download_cloud", _I, [_VP, _I, _PF, _I, _PI32]),
+    ("pop_dsp_update_rendered", _I, [_VP, _PF, _PF, _D, _PI32]),
 ]
 
 _lib = None

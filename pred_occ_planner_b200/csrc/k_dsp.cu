@@ -159,12 +159,12 @@ __global__ void __launch_bounds__(1024) k_dsp_filter(DspGeo G, const DspFrame* _
                                                      const float* __restrict__ cam_all,
                                                      unsigned long long* __restrict__ keys_all,
                                                      float* __restrict__ pts_all, int* __restrict__ npts,
-                                                     int* __restrict__ err) {
+                                                     int* __restrict__ err, const int* __restrict__ cam_counts) {
   extern __shared__ unsigned long long s_keys[];   // kFilterSmemKeys sort keys
   const int a = blockIdx.x, tid = threadIdx.x;
   __shared__ unsigned s_mn[3], s_mx[3];
   __shared__ int s_w[33];
-  const int n = fr[a].n_in;
+  const int n = cam_counts ? cam_counts[a] : fr[a].n_in;   // rendered clouds carry their size on the device
   const float* cam = cam_all + static_cast<size_t>(a) * G.MAXIN * 3;
   float* pts = pts_all + static_cast<size_t>(a) * G.MAXPTS * 3;
   if (tid < 3) { s_mn[tid] = 0xffffffffu; s_mx[tid] = 0u; }
@@ -1421,7 +1421,7 @@ void popk_dsp_free(pop_handle* h) {
                   d->r_slot, d->r_state, d->r_a, d->r_b, d->vhead, d->pcount, d->poff, d->pcur, d->plist,
                   d->plist2, d->changed, d->pyr_n, d->pyr_ref, d->pyr_p, d->b_dest, d->b_next, d->b_a, d->b_b,
                   d->seq, d->stats, d->err, d->act[0], d->act[1], d->nact[0], d->nact[1], d->touch, d->ntouch,
-                  d->touch2, d->ntouch2, d->vstamp, d->ok_dev};
+                  d->touch2, d->ntouch2, d->vstamp, d->ok_dev, d->depth, d->cam_counts, d->rpose, d->rpose_d};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (d->side) cudaStreamDestroy(d->side);
   if (d->ev_fork) cudaEventDestroy(d->ev_fork);
@@ -1565,7 +1565,8 @@ int popk_dsp_alloc(pop_handle* h, const pop_dsp_config* c) {
 
 int popk_dsp_filter_only(pop_handle* h) {
   DspDev* d = h->dsp;
-  k_dsp_filter<<<d->nl, 1024, filter_smem_bytes(d->G), h->stream>>>(d->G, d->frame, d->cam, d->fkeys, d->pts, d->npts, d->err);
+  k_dsp_filter<<<d->nl, 1024, filter_smem_bytes(d->G), h->stream>>>(d->G, d->frame, d->cam, d->fkeys, d->pts, d->npts, d->err,
+                                                                    d->use_cam_counts ? d->cam_counts : nullptr);
   POP_LAUNCH_CHECK(h);
   h->n_launches++;
   return POP_OK;
@@ -1579,7 +1580,8 @@ int popk_dsp_update(pop_handle* h, int filtered) {
   int launches = 0;
   pop_prof_begin(h, POP_STAGE_DSP);
   if (!filtered) {
-    k_dsp_filter<<<A, 1024, filter_smem_bytes(G), st>>>(G, d->frame, d->cam, d->fkeys, d->pts, d->npts, d->err);
+    k_dsp_filter<<<A, 1024, filter_smem_bytes(G), st>>>(G, d->frame, d->cam, d->fkeys, d->pts, d->npts, d->err,
+                                                                d->use_cam_counts ? d->cam_counts : nullptr);
     POP_LAUNCH_CHECK(h); launches++;
   }
   k_dsp_bin<<<A, 1024, bin_smem_bytes(G), st>>>(G, d->frame, d->bp_ori, d->bp, d->pts, d->npts, d->rot, d->pobs,

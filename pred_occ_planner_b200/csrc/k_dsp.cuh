@@ -86,6 +86,14 @@ struct DspDev {
   int cur = 0;                // which act[] is current
   cudaStream_t side = nullptr;         // clustering/assignment runs beside prediction+update (the reference's side thread)
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  // depth sensor (k_render.cu): rendered clouds land in `cam`, their sizes in `cam_counts`
+  pop_camera camera;
+  bool have_camera = false;
+  int* depth = nullptr;       // [A][height*width] millimetres
+  int* cam_counts = nullptr;  // [A]
+  float* rpose = nullptr;     // [A][32]: cam_pose r (9 f32) t (3 f32) | cam2world (16 f64 packed as 2 f32 each is avoided: see k_render.cu)
+  double* rpose_d = nullptr;  // [A][20]: cam2world (16) + body position (3) + pad
+  bool use_cam_counts = false;  // the next update reads cloud sizes from cam_counts (rendered input)
   int* seq = nullptr;         // [A][4] sequence counters of the three tables
   int* stats = nullptr;       // [A][8]
   int* err = nullptr;         // [1] device-side error flags

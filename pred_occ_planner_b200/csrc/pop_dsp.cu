@@ -77,6 +77,10 @@ int run_update(pop_handle* h, const float* in, int stride_pts, const int32_t* co
   DspDev* d = h->dsp;
   const int A = d->nl;
   const int cap = filtered ? d->G.MAXPTS : d->G.MAXIN;
+  const bool rendered = in == nullptr;   // clouds and their sizes are already on the device (pop_render_depth)
+  std::vector<int32_t> zero_counts(A, 0);
+  if (rendered) counts = zero_counts.data();
+  d->use_cam_counts = rendered;
   for (int a = 0; a < A; a++)
     if (counts[a] < 0 || counts[a] > cap) return pop_fail(h, POP_E_CAPACITY, "agent %d: %d points exceed the capacity %d", a, counts[a], cap);
   make_frames(h, counts, poses, quats, stamp, out_ok);
@@ -191,6 +195,15 @@ int pop_dsp_update(pop_handle* h, const float* cam, const int32_t* counts, const
   return run_update(h, cam, h->dsp->G.MAXIN, counts, poses, quats, stamp, out_ok, 0);
 }
 
+int pop_dsp_update_rendered(pop_handle* h, const float* poses, const float* quats, double stamp, int32_t* out_ok) {
+  int rc = check(h, 0);
+  if (rc) return rc;
+  if (!poses || !quats) return POP_E_INVALID;
+  if (!h->dsp->have_camera || !h->dsp->use_cam_counts)
+    return pop_fail(h, POP_E_STATE, "no rendered clouds: call pop_render_depth first");
+  return run_update(h, nullptr, h->dsp->G.MAXIN, nullptr, poses, quats, stamp, out_ok, 0);
+}
+
 int pop_dsp_update_filtered(pop_handle* h, const float* pts, const int32_t* counts, const float* poses,
                             const float* quats, double stamp, int32_t* out_ok) {
   int rc = check(h, 0);
@@ -206,6 +219,7 @@ int pop_dsp_filter(pop_handle* h, int agent, const float* cam, int n, float* out
   if (n < 0 || n > d->G.MAXIN || !out || !n_out) return POP_E_INVALID;
   for (int a = 0; a < d->nl; a++) { memset(&d->h_frame[a], 0, sizeof(DspFrame)); }
   d->h_frame[agent].n_in = n;
+  d->use_cam_counts = false;
   POP_CUDA(h, cudaMemcpyAsync(d->frame, d->h_frame.data(), sizeof(DspFrame) * d->nl, cudaMemcpyHostToDevice, h->stream));
   if (n > 0)
     POP_CUDA(h, cudaMemcpyAsync(d->cam + static_cast<size_t>(agent) * d->G.MAXIN * 3, cam, sizeof(float) * 3 * n,

@@ -80,6 +80,49 @@ class DspMaps:
         e._check(e.lib.pop_dsp_filter(e._h, agent, as_ptr(cam, C.c_float), len(cam), as_ptr(out, C.c_float), C.byref(n)))
         return out[:n.value].copy()
 
+    # -- depth sensor (uav_simulator/local_sensing) ----------------------------------------------
+    def set_camera(self, width: int = 160, height: int = 120, cam: "_lib.PopCamera | None" = None):
+        """DepthRender::set_para (depth_render.cu:83-91): the reference camera scaled to width x height."""
+        e = self.eng
+        if cam is None:
+            cam = _lib.PopCamera()
+            e.lib.pop_camera_default(C.byref(cam), int(width), int(height))
+        e._check(e.lib.pop_render_set_camera(e._h, C.byref(cam)))
+        self.camera = cam
+        return cam
+
+    def render(self, pos, quat, want_depth: bool = False):
+        """render_currentpose + render_pcl_world for every local agent from the engine's world cloud; the
+        camera-frame clouds stay on the device for `cloudCallbackRendered`.  Returns (counts, depth_mm|None)."""
+        e = self.eng
+        pos = np.ascontiguousarray(pos, np.float64).reshape(self.n_local, 3)
+        quat = np.ascontiguousarray(quat, np.float64).reshape(self.n_local, 4)
+        counts = np.zeros(self.n_local, np.int32)
+        depth = np.zeros((self.n_local, self.camera.height, self.camera.width), np.int32) if want_depth else None
+        e._check(e.lib.pop_render_depth(e._h, as_ptr(pos, C.c_double), as_ptr(quat, C.c_double),
+                                        as_ptr(depth, C.c_int32) if want_depth else None, as_ptr(counts, C.c_int32)))
+        return counts, depth
+
+    def rendered_cloud(self, agent: int):
+        cap = self.d.max_input_points
+        out = np.zeros((cap, 3), np.float32)
+        n = C.c_int32(0)
+        e = self.eng
+        e._check(e.lib.pop_render_download_cloud(e._h, agent, as_ptr(out, C.c_float), cap, C.byref(n)))
+        return out[:n.value].copy()
+
+    def cloudCallbackRendered(self, poses, quats, stamp: float):
+        """cloudCallback on the clouds the last `render` left on the device."""
+        e = self.eng
+        poses = np.ascontiguousarray(poses, np.float32).reshape(self.n_local, 3)
+        quats = np.ascontiguousarray(quats, np.float32).reshape(self.n_local, 4)
+        ok = np.zeros(self.n_local, np.int32)
+        e._check(e.lib.pop_dsp_update_rendered(e._h, as_ptr(poses, C.c_float), as_ptr(quats, C.c_float), float(stamp),
+                                               as_ptr(ok, C.c_int32)))
+        e._poses = poses.copy()
+        e._t_map = float(stamp)
+        return ok
+
     # -- parity views ---------------------------------------------------------------------------
     def particles(self, agent: int):
         out = np.zeros((self.V, self.S, 8), np.float32)

@@ -323,3 +323,19 @@ class OracleDsp:
         out = np.zeros(8, np.int32)
         self.lib.orc_dsp_stats(self.h, _p(out, C.c_int32))
         return out
+
+
+def render(cam, pos, quat, cloud, cap=1 << 20):
+    """orc::render_* — the simulator's depth sensor for one agent: (depth_mm [H,W], camera-frame cloud,
+    world-frame cloud) (oracle/o_render.cpp)."""
+    lib = load().lib
+    pos = np.ascontiguousarray(pos, np.float64).reshape(3)
+    quat = np.ascontiguousarray(quat, np.float64).reshape(4)
+    cloud = np.ascontiguousarray(cloud, np.float32).reshape(-1, 3)
+    depth = np.zeros((cam.height, cam.width), np.int32)
+    oc = np.zeros((cap, 3), np.float32)
+    ow = np.zeros((cap, 3), np.float32)
+    n = lib.orc_render(C.byref(cam), _p(pos, C.c_double), _p(quat, C.c_double), _p(cloud, C.c_float), len(cloud),
+                       _p(depth, C.c_int32), _p(oc, C.c_float), _p(ow, C.c_float), cap)
+    assert n <= cap
+    return depth, oc[:n].copy(), ow[:n].copy()

@@ -381,6 +381,27 @@ int pop_render_download_cloud(pop_handle* h, int agent, float* out, int cap, int
 int pop_dsp_update_rendered(pop_handle* h, const float* poses, const float* quats, double stamp,
                             int32_t* out_ok);
 
+/* ---- after the optimiser: trajectory server, closed loop, evaluation, wire format ------------- */
+/* Trajectory-server sampling (traj_server/src/bezier_traj_server.cpp:194-275: traj_.getPos/getVel/getAcc at
+ * the command times).  all_agents = 0: the local agents' own last published trajectories; 1: every agent of the
+ * swarm as last received.  t_abs n_t absolute times; out_pva (n_agents x n_t x 9: pos, vel, acc), out_valid
+ * (n_agents x n_t: 0 outside [start, start + duration] or without a trajectory). */
+int pop_traj_sample_batch(pop_handle* h, int all_agents, const double* t_abs, int n_t, double* out_pva,
+                          int8_t* out_valid);
+/* Closed loop with a perfectly tracking drone (uav_simulator/fake_drone: position command -> odometry): every
+ * local agent's resident state (the `start` of the next pop_replan_cycle_resident) and map centre become its
+ * commanded state at t_next; past the end of its trajectory it holds the end point, without one it stays. Async. */
+int pop_swarm_advance(pop_handle* h, double t_next);
+/* the resident agent states: out_start n_local x 9 */
+int pop_swarm_states(pop_handle* h, double* out_start);
+/* MultiAgentLogger::getMinObsDist / getMinUAVDist (eval_helper/include/eval_helper/multi_eval.hpp:240-275) for
+ * the local agents at time t: distance to the nearest cylinder surface (as last set) and to the nearest agent. */
+int pop_eval_metrics(pop_handle* h, double t, double* out_min_obs, double* out_min_uav);
+/* traj_utils/BezierTraj (msg:1-9) in ROS1 serialisation.  to_wire returns the byte count (out = NULL: size
+ * only); from_wire returns the bytes consumed.  start/pub times pass through ros::Time (nanoseconds). */
+int pop_traj_to_wire(const pop_traj_record* rec, double pub_time, uint8_t* out, int cap);
+int pop_traj_from_wire(const uint8_t* in, int n, pop_traj_record* rec, double* pub_time);
+
 /* ---- measurement ------------------------------------------------------------------------ */
 enum { POP_STAGE_VOXEL_UPDATE = 0, POP_STAGE_PEERS = 1, POP_STAGE_ASTAR = 2, POP_STAGE_CORRIDOR = 3,
        POP_STAGE_QP = 4, POP_STAGE_SEPARATION = 5, POP_STAGE_DSP = 6, POP_STAGE_COUNT = 8 };

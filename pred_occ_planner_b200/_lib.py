@@ -193,6 +193,12 @@ SYMBOLS = [
     ("pop_render_depth", _I, [_VP, _PD, _PD, _PI32, _PI32]),
     ("pop_render_download_cloud", _I, [_VP, _I, _PF, _I, _PI32]),
     ("pop_dsp_update_rendered", _I, [_VP, _PF, _PF, _D, _PI32]),
+    ("pop_traj_sample_batch", _I, [_VP, _I, _PD, _I, _PD, _PI8]),
+    ("pop_swarm_advance", _I, [_VP, _D]),
+    ("pop_swarm_states", _I, [_VP, _PD]),
+    ("pop_eval_metrics", _I, [_VP, _D, _PD, _PD]),
+    ("pop_traj_to_wire", _I, [C.POINTER(PopTrajRecord), _D, C.POINTER(C.c_uint8), _I]),
+    ("pop_traj_from_wire", _I, [C.POINTER(C.c_uint8), _I, C.POINTER(PopTrajRecord), _PD]),
 ]
 
 _lib = None

@@ -171,6 +171,32 @@ class PopEngine:
         self._check(self.lib.pop_plan_cycle(self._h, C.byref(io)))
         return status, traj
 
+    # -- after the optimiser ---------------------------------------------------------------------
+    def traj_sample_batch(self, t_abs, all_agents: bool = False):
+        """Trajectory-server sampling (bezier_traj_server.cpp:194-275): (pva [n, n_t, 9], valid [n, n_t])."""
+        t_abs = _f64(t_abs).reshape(-1)
+        n = self.n_total if all_agents else self.n_local
+        out = np.zeros((n, len(t_abs), 9))
+        valid = np.zeros((n, len(t_abs)), np.int8)
+        self._check(self.lib.pop_traj_sample_batch(self._h, int(all_agents), as_ptr(t_abs, C.c_double), len(t_abs),
+                                                   as_ptr(out, C.c_double), as_ptr(valid, C.c_int8)))
+        return out, valid
+
+    def swarm_advance(self, t_next: float):
+        """Every local agent moves to its commanded state at t_next (perfect tracking); resident, async."""
+        self._check(self.lib.pop_swarm_advance(self._h, float(t_next)))
+
+    def swarm_states(self):
+        out = np.zeros((self.n_local, 9))
+        self._check(self.lib.pop_swarm_states(self._h, as_ptr(out, C.c_double)))
+        return out
+
+    def eval_metrics(self, t: float):
+        """(min obstacle distance, min inter-agent distance) per local agent (multi_eval.hpp:240-275)."""
+        mo, mu = np.zeros(self.n_local), np.zeros(self.n_local)
+        self._check(self.lib.pop_eval_metrics(self._h, float(t), as_ptr(mo, C.c_double), as_ptr(mu, C.c_double)))
+        return mo, mu
+
     def replan_cycle_resident(self, t_map, t_plan):
         self._check(self.lib.pop_replan_cycle_resident(self._h, float(t_map), float(t_plan)))
 

@@ -155,6 +155,9 @@ struct Search {
       coef[i][0] = p0;
     }
     double t_delta = t_d / 10;
+    // the reference loops forever when t_d == 0 (goal reached before the first expansion: `time += 0`) and takes
+    // a NaN t_d for a successful shot; both are treated as "no shot" here and in the CUDA path
+    if (!(t_delta > 0.0) || !std::isfinite(t_d)) return false;
     for (double time = t_delta; time <= t_d; time += t_delta) {
       double tp[4];
       for (int j = 0; j < 4; j++) tp[j] = std::pow(time, j);

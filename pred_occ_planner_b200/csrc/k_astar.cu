@@ -343,8 +343,10 @@ __global__ void __launch_bounds__(kThreads) k_astar(PopGeom g, AstarParams P, As
                 coef[i][0] = p0;
               }
               const double t_delta = t_d / 10;
-              bool ok = true;
-              for (double time = t_delta; time <= t_d; time += t_delta) {
+              // t_d == 0 (goal reached before the first expansion) makes the reference's loop spin forever and a
+              // NaN t_d passes as a successful shot: both count as "no shot"
+              bool ok = t_delta > 0.0 && isfinite(t_d);
+              for (double time = t_delta; ok && time <= t_d; time += t_delta) {
                 const double tp[4] = {1.0, time, time * time, pop_pow_int(time, 3)};
                 double coord[3];
                 for (int d = 0; d < 3; d++)

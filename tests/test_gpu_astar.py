@@ -98,3 +98,17 @@ def test_repeated_searches_reuse_pools(oracle):
         again = eng.astar_search_batch(start, goal, np.full(2, 0.02))
         for x, y in zip(first, again):
             assert np.array_equal(x, y)
+
+
+def test_goal_equal_to_start_terminates(oracle):
+    """Degenerate shot (optimal time 0) must end the search instead of spinning (see the CPU test)."""
+    n = 3
+    cfg = cases.cfg_c1(p.POP_CELL_U8, n_local=n, n_total=n)
+    cloud, cyl = cases.world_c1()
+    start = np.zeros((n, 9))
+    start[:, :3] = [[-4, 0, 1.0], [0.3, 0.2, 1.0], [2.0, -1.0, 1.2]]
+    goal = start[:, :3].copy()
+    goal[0] = [4.0, 0, 1.0]          # one ordinary search beside two degenerate ones
+    mism, ret, stats = _run(oracle, cfg, cloud, cyl, start, goal, start[:, :3].astype(np.float32), 0.0, 0.02)
+    assert not mism, mism
+    assert ret[0] in (3, 4, 5) and ret[1] == 0 and ret[2] == 0

@@ -117,3 +117,51 @@ def test_separation_check(oracle):
     want = [oracle_cycle.safe_after_opt(cfg, (body[0], body[1], recs), a, cpts[a, :20], 4, 5.0) for a in range(n)]
     assert safe.astype(bool).tolist() == want
     assert any(want) and not all(want)
+
+
+def test_full_size_c3_cycle_properties():
+    """BASELINE config 3 at full size — 256 agents on one GPU, 500x500x60 voxels @0.1 m, T = 20, static and
+    moving cylinders, the whole A* + corridor + QP cycle (77 GB of SOGM).  Too large for the oracle, so the
+    cycle is judged by size-independent properties: every published trajectory starts at its agent's state,
+    respects the dynamic limits, stays in free space of the slices it crosses and makes progress to the goal;
+    a second, resident run of the same cycle reproduces the first bit for bit."""
+    n = 256
+    cfg = cases.cfg_small_c2(p.POP_CELL_U8, n_local=n, n_total=n, nx=500, ny=500, nz=60, nt=20)
+    cloud, cyl = cases.world_moving(1237, (50.0, 50.0, 6.0), 60, 60)
+    start, goal = p.worldgen.lattice_agents(n, arena=(50.0, 50.0), seed=3)
+    poses = start[:, :3].astype(np.float32)
+    eng = p.PopEngine(cfg)
+    eng.set_world_cloud(cloud)
+    eng.set_cylinders(cyl)
+    eng.set_body_particles(*p.worldgen.body_table(n, [0.4, 0.4, 0.45]))
+    eng.set_trajectories(np.zeros(n, p.TRAJ_DTYPE))
+    t0 = 5.0
+    status, traj = eng.replan_cycle(start, goal, poses, t0, t0 + 0.02)
+    ok = np.nonzero(status == 0)[0]
+    assert len(ok) >= n // 2, np.bincount(status, minlength=5).tolist()
+    ts = np.arange(0.0, 0.8, 0.1) + t0 + 0.02
+    pva, valid = eng.traj_sample_batch(ts)
+    free = total = 0
+    progress = []
+    for a in ok:
+        M = int(traj["n_pieces"][a])
+        assert 1 <= M <= p.POP_MAX_PIECES and traj["valid"][a] == 1 and traj["start_time"][a] == t0 + 0.02
+        c = traj["cpts"][a][:5 * M]
+        assert np.abs(c[0] - start[a, :3]).max() < 1e-3      # starts where the agent is (ADMM tolerance 1e-3)
+        T = float(traj["duration"][a][:M].sum())
+        m = valid[a].astype(bool) & (ts - (t0 + 0.02) <= T)
+        v = np.linalg.norm(pva[a, m, 3:6], axis=1)
+        acc = np.abs(pva[a, m, 6:9])
+        # the boxes bind the derivative control points up to the ADMM tolerance (and status 2 = solved inaccurate
+        # is accepted, bezier_optimizer.cpp:279): sampled derivatives stay within a loose multiple of the limits
+        assert v.max() <= 1.25 * np.sqrt(3) * cfg.opt_max_vel and acc.max() <= 1.5 * cfg.opt_max_acc
+        occ = eng.agent_map(int(a)).getClearOcccupancy(pva[a, m, :3], (ts[m] - t0).astype(np.float64))
+        free += int((occ == 0).sum())
+        total += int(m.sum())
+        progress.append(np.linalg.norm(start[a, :3] - goal[a]) - np.linalg.norm(c[5 * M - 1] - goal[a]))
+    assert free >= 0.99 * total, (free, total)
+    assert np.median(progress) > 0.5 and np.mean(np.array(progress) > 0) > 0.8   # detours happen; most agents advance
+    eng.replan_cycle_resident(t0, t0 + 0.02)
+    st2, tr2 = eng.cycle_results()
+    assert np.array_equal(st2, status) and np.array_equal(tr2["cpts"][ok], traj["cpts"][ok])
+    eng.close()

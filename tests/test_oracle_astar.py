@@ -52,3 +52,14 @@ def test_deterministic(oracle):
     r1 = m.astar(start, [3, -3, 1.2], 0.1)
     r2 = m.astar(start, [3, -3, 1.2], 0.1)
     assert r1[0] == r2[0] and np.array_equal(r1[1], r2[1]) and np.array_equal(r1[2], r2[2])
+
+
+def test_goal_equal_to_start_terminates(oracle):
+    """The first popped node is already at the goal and the optimal shot time is 0: the reference's
+    computeShotTraj then loops `time += 0` forever (fake_risk_hybrid_a_star.cpp:500-515).  Treated as "no shot":
+    the search ends with NO_PATH, like any near-end hit without a parent."""
+    cfg, m = _setup(oracle, [0, 0, 1.0])
+    start = np.zeros(9)
+    start[:3] = [0.3, 0.2, 1.0]
+    ret, path, stats = m.astar(start, start[:3], 0.0)
+    assert ret == 0 and len(path) == 0

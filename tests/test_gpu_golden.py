@@ -50,3 +50,41 @@ def test_config1_against_committed_vectors(cell):
     assert st[0] == int(g["replan_status"]) and tr["n_pieces"][0] == int(g["record_n_pieces"])
     rc = g["record_cpts"]
     assert np.abs(tr["cpts"][0] - rc).max() <= RTOL * max(1.0, np.abs(rc).max())
+
+
+def test_sensor_and_particle_map_against_committed_vectors():
+    """Depth sensor + particle map on the fixed 6-frame flight of scripts/make_golden_dsp.py against
+    tests/golden/oracle_dsp.npz: depth images, voxel-filter output, every live particle, drop counters and
+    voxel occupancy bit-exact; future risk within 1e-5 relative (atomic fp32 deposits)."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(GOLD), os.pardir, "scripts"))
+    from make_golden_dsp import scenario
+    from pred_occ_planner_b200 import dsp
+    g = np.load(os.path.join(GOLD, "oracle_dsp.npz"))
+    cfg, d, cam, cloud, tabs, frames = scenario()
+    eng = p.PopEngine(cfg)
+    maps = dsp.DspMaps(eng, d)
+    maps.set_camera(cam=cam)
+    maps.set_random_tables(*tabs)
+    eng.set_world_cloud(cloud)
+    for k, (pos, quat, st) in enumerate(frames):
+        counts, depth = maps.render(pos[None], quat[None], want_depth=True)
+        if k in (0, 5):
+            assert np.array_equal(depth[0], g[f"depth_{k}"]) and counts[0] == int(g[f"ncloud_{k}"])
+            assert np.array_equal(maps.filterPointCloud(0, maps.rendered_cloud(0)), g[f"filtered_{k}"])
+            maps.render(pos[None], quat[None])      # the filter call above consumed the rendered input
+        assert maps.cloudCallbackRendered(pos[None].astype(np.float32), quat[None].astype(np.float32), st).tolist() == [1]
+        assert np.array_equal(maps.stats(0)[:7], g[f"stats_{k}"][:7]), k
+        assert len(maps.getOccupancyMap(0)) == int(g[f"nocc_{k}"])
+    parts = maps.particles(0)
+    live = np.argwhere(parts[:, :, 0] > 0.1).astype(np.int32)
+    assert np.array_equal(live, g["live_slots"])
+    assert np.array_equal(parts[live[:, 0], live[:, 1]], g["live_state"])
+    vox = maps.voxels(0)
+    occ = np.nonzero(vox[:, 0] > 0)[0].astype(np.int32)
+    assert np.array_equal(occ, g["vox_idx"]) and np.array_equal(vox[occ], g["vox_val"])
+    risk = eng.agent_map(0).risk_maps()
+    nz = np.argwhere(risk != 0).astype(np.int32)
+    assert np.array_equal(nz, g["risk_idx"])
+    assert np.allclose(risk[nz[:, 0], nz[:, 1]], g["risk_val"], rtol=1e-5, atol=1e-6)
+    eng.close()

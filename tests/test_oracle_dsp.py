@@ -180,3 +180,30 @@ def test_noise_tables_wrap_and_determinism(oracle):
         outs.append((m.particles(), m.stats()))
     assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
     assert 0 <= outs[0][1][4] < 4096
+
+
+def test_oracle_reproduces_committed_vectors(oracle):
+    """tests/golden/oracle_dsp.npz pins the oracle itself (sensor + particle map) against accidental change."""
+    import os
+    import sys
+    from tests import oracle_lib
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(root, "scripts"))
+    from make_golden_dsp import scenario
+    g = np.load(os.path.join(root, "tests", "golden", "oracle_dsp.npz"))
+    cfg, d, cam, cloud, tabs, frames = scenario()
+    m = oracle.dsp(cfg, d)
+    m.set_random_tables(*tabs)
+    for k, (pos, quat, st) in enumerate(frames):
+        depth, pc, _ = oracle_lib.render(cam, pos, quat, cloud)
+        if k in (0, 5):
+            assert np.array_equal(depth, g[f"depth_{k}"]) and np.array_equal(m.filter(pc), g[f"filtered_{k}"])
+        assert m.update(pc, pos.astype(np.float32), quat.astype(np.float32), st) == 1
+        risk, nocc = m.export()
+        assert np.array_equal(m.stats(), g[f"stats_{k}"]) and nocc == int(g[f"nocc_{k}"])
+    parts = m.particles()
+    live = g["live_slots"]
+    assert np.array_equal(np.argwhere(parts[:, :, 0] > 0.1), live)
+    assert np.array_equal(parts[live[:, 0], live[:, 1]], g["live_state"])
+    nz = g["risk_idx"]
+    assert np.array_equal(np.argwhere(risk != 0), nz) and np.array_equal(risk[nz[:, 0], nz[:, 1]], g["risk_val"])

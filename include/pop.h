@@ -402,6 +402,36 @@ int pop_eval_metrics(pop_handle* h, double t, double* out_min_obs, double* out_m
 int pop_traj_to_wire(const pop_traj_record* rec, double pub_time, uint8_t* out, int cap);
 int pop_traj_from_wire(const uint8_t* in, int n, pop_traj_record* rec, double* pub_time);
 
+/* ---- raycast map: log-odds occupancy from projected depth points ---------------- */
+/* Parameters of GridMap (plan_env/src/grid_map.cpp:15-131, "grid_map/..." ROS params). */
+typedef struct pop_gridmap_config {
+  double  resolution;
+  double  map_size[3];            /* map_size_x/y/z; origin = (-x/2, -y/2, ground_height) */
+  double  local_update_range[3];
+  double  obstacles_inflation;
+  double  p_hit, p_miss, p_min, p_max, p_occ;   /* 0.70 0.35 0.12 0.97 0.80 */
+  double  max_ray_length;
+  double  virtual_ceil_height;
+  double  ground_height;
+  int32_t local_map_margin;
+  int32_t max_points;             /* capacity of one frame's projected points per map */
+} pop_gridmap_config;
+typedef struct pop_gridmap pop_gridmap;
+void pop_gridmap_default_config(pop_gridmap_config* cfg);
+/* n_maps independent GridMaps (one per drone) on one GPU, updated by the same launches */
+int pop_gridmap_create(const pop_gridmap_config* cfg, int n_maps, int device, void* stream, pop_gridmap** out);
+int pop_gridmap_destroy(pop_gridmap* g);
+const char* pop_gridmap_last_error(const pop_gridmap* g);
+/* updateOccupancyCallback after projectDepthImage (grid_map.cpp:585-640): raycastProcess (:313-456) +
+ * clearAndInflateLocalMap (:477-583) for every map.  pts = n_maps x max_points x 3 world-frame doubles
+ * (proj_points_), counts n_maps, cam_pos n_maps x 3 (must lie inside the map). */
+int pop_gridmap_update(pop_gridmap* g, const double* pts, const int32_t* counts, const double* cam_pos);
+/* getOccupancy / getInflateOccupancy (grid_map.h:333-349): -1 outside the map, else 0/1; either output may be NULL */
+int pop_gridmap_query(pop_gridmap* g, int map, const double* pos, int n, int8_t* out_occ, int8_t* out_inflate);
+/* occupancy_buffer_ (log-odds doubles, x-major), occupancy_buffer_inflate_, local_bound_min/max (6 ints) */
+int pop_gridmap_download(pop_gridmap* g, int map, double* occ, int8_t* inflate, int32_t* bounds);
+int pop_gridmap_dims(const pop_gridmap* g, int32_t* out3);
+
 /* ---- measurement ------------------------------------------------------------------------ */
 enum { POP_STAGE_VOXEL_UPDATE = 0, POP_STAGE_PEERS = 1, POP_STAGE_ASTAR = 2, POP_STAGE_CORRIDOR = 3,
        POP_STAGE_QP = 4, POP_STAGE_SEPARATION = 5, POP_STAGE_DSP = 6, POP_STAGE_COUNT = 8 };

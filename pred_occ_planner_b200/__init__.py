@@ -4,8 +4,8 @@ projection.  The compute lives in libpop.so (hand-written sm_100a CUDA behind in
 this package is the thin host mirror of the reference's interfaces."""
 from ._lib import (POP_CELL_F32, POP_CELL_U8, POP_KERNEL_CUBE, POP_KERNEL_DISC_Z0, POP_MAX_BODY,
                    POP_MAX_FACES, POP_MAX_PATH, POP_MAX_PIECES, POP_QUERY_FAKE, POP_QUERY_RISKBASE,
-                   CYL_DTYPE, TRAJ_DTYPE, PopConfig, PopDspConfig, PopError, default_config, load)
+                   CYL_DTYPE, TRAJ_DTYPE, PopConfig, PopDspConfig, PopGridmapConfig, PopError, default_config, load)
 from .engine import AgentMap, PopEngine
-from . import dsp, swarm, wire, worldgen
+from . import dsp, gridmap, swarm, wire, worldgen
 
-__all__ = ["PopEngine", "AgentMap", "PopConfig", "PopError", "default_config", "load", "dsp", "swarm", "wire", "worldgen"]
+__all__ = ["PopEngine", "AgentMap", "PopConfig", "PopError", "default_config", "load", "dsp", "gridmap", "swarm", "wire", "worldgen"]

@@ -124,6 +124,15 @@ class PopCamera(C.Structure):
                 ("cam2body", C.c_double * 16)]
 
 
+class PopGridmapConfig(C.Structure):
+    """pop_gridmap_config (include/pop.h): parameters of GridMap (plan_env/src/grid_map.cpp:15-131)."""
+    _fields_ = [("resolution", C.c_double), ("map_size", C.c_double * 3), ("local_update_range", C.c_double * 3),
+                ("obstacles_inflation", C.c_double),
+                ("p_hit", C.c_double), ("p_miss", C.c_double), ("p_min", C.c_double), ("p_max", C.c_double),
+                ("p_occ", C.c_double), ("max_ray_length", C.c_double), ("virtual_ceil_height", C.c_double),
+                ("ground_height", C.c_double), ("local_map_margin", C.c_int32), ("max_points", C.c_int32)]
+
+
 class PopCycleIO(C.Structure):
     _fields_ = [("start", C.POINTER(C.c_double)), ("goal", C.POINTER(C.c_double)),
                 ("poses", C.POINTER(C.c_float)), ("t_map", C.c_double), ("t_plan", C.c_double),
@@ -199,6 +208,14 @@ SYMBOLS = [
     ("pop_eval_metrics", _I, [_VP, _D, _PD, _PD]),
     ("pop_traj_to_wire", _I, [C.POINTER(PopTrajRecord), _D, C.POINTER(C.c_uint8), _I]),
     ("pop_traj_from_wire", _I, [C.POINTER(C.c_uint8), _I, C.POINTER(PopTrajRecord), _PD]),
+    ("pop_gridmap_default_config", None, [C.POINTER(PopGridmapConfig)]),
+    ("pop_gridmap_create", _I, [C.POINTER(PopGridmapConfig), _I, _I, _VP, C.POINTER(_VP)]),
+    ("pop_gridmap_destroy", _I, [_VP]),
+    ("pop_gridmap_last_error", C.c_char_p, [_VP]),
+    ("pop_gridmap_update", _I, [_VP, _PD, _PI32, _PD]),
+    ("pop_gridmap_query", _I, [_VP, _I, _PD, _I, _PI8, _PI8]),
+    ("pop_gridmap_download", _I, [_VP, _I, _PD, _PI8, _PI32]),
+    ("pop_gridmap_dims", _I, [_VP, _PI32]),
 ]
 
 _lib = None

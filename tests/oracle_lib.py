@@ -339,3 +339,33 @@ def render(cam, pos, quat, cloud, cap=1 << 20):
                        _p(depth, C.c_int32), _p(oc, C.c_float), _p(ow, C.c_float), cap)
     assert n <= cap
     return depth, oc[:n].copy(), ow[:n].copy()
+
+
+class OracleGridMap:
+    """orc::GridMapO — sequential restatement of GridMap::raycastProcess + clearAndInflateLocalMap
+    (oracle/o_gridmap.cpp)."""
+
+    def __init__(self, cfg):
+        self.lib = load().lib
+        self.lib.orc_gridmap_create.restype = C.c_void_p
+        self.h = C.c_void_p(self.lib.orc_gridmap_create(C.byref(cfg)))
+        d = np.zeros(3, np.int32)
+        self.lib.orc_gridmap_dims(self.h, _p(d, C.c_int32))
+        self.dims = tuple(int(v) for v in d)
+
+    def __del__(self):
+        try:
+            self.lib.orc_gridmap_destroy(self.h)
+        except Exception:
+            pass
+
+    def update(self, pts, cam):
+        pts = np.ascontiguousarray(pts, np.float64).reshape(-1, 3)
+        cam = np.ascontiguousarray(cam, np.float64).reshape(3)
+        self.lib.orc_gridmap_update(self.h, _p(pts, C.c_double), len(pts), _p(cam, C.c_double))
+
+    def buffers(self):
+        n = self.dims[0] * self.dims[1] * self.dims[2]
+        occ, inf, b = np.zeros(n), np.zeros(n, np.int8), np.zeros(6, np.int32)
+        self.lib.orc_gridmap_download(self.h, _p(occ, C.c_double), _p(inf, C.c_int8), _p(b, C.c_int32))
+        return occ.reshape(self.dims), inf.reshape(self.dims), b

@@ -1,0 +1,113 @@
+"""GPU parity of the raycast map (log-odds GridMap) against the sequential oracle: occupancy_buffer_ (doubles),
+occupancy_buffer_inflate_ and the local bounds bit-exact, frame after frame, including the frames after the
+reference's char flags wrap (frame 128 on)."""
+import numpy as np
+import pytest
+
+import pred_occ_planner_b200 as p
+from pred_occ_planner_b200 import gridmap, worldgen
+from tests import oracle_lib
+
+pytestmark = pytest.mark.gpu
+
+
+def _cfg():
+    c = gridmap.default_gridmap_config()
+    c.map_size[0], c.map_size[1], c.map_size[2] = 20.0, 20.0, 4.0
+    c.local_map_margin = 5
+    c.max_points = 20000
+    return c
+
+
+def _scene():
+    cloud, cyl = worldgen.make_world(11, arena=(10.0, 10.0, 3.0), n_static=8, n_moving=0, height=3.0)
+    gx, gy = np.meshgrid(np.arange(-5, 5, 0.1), np.arange(-5, 5, 0.1), indexing="ij")
+    ground = np.stack([gx.ravel(), gy.ravel(), np.zeros(gx.size)], axis=1).astype(np.float32)
+    return np.concatenate([cloud, ground]).astype(np.float32)
+
+
+def _frame(cam, cloud, a, k):
+    pos = np.array([-4.0 + 0.15 * k, -1.0 + 1.0 * a, 1.0 + 0.1 * a])
+    yaw = 0.1 * a + 0.05 * k
+    quat = np.array([np.cos(yaw / 2), 0, 0, np.sin(yaw / 2)])
+    _, _, pw = oracle_lib.render(cam, pos, quat, cloud)
+    return pos, pw.astype(np.float64)
+
+
+def _same(maps, m, orc):
+    occ_g, inf_g, b_g = maps.buffers(m)
+    occ_o, inf_o, b_o = orc.buffers()
+    bad = []
+    if not np.array_equal(b_g, b_o):
+        bad.append(f"bounds {b_g.tolist()} vs {b_o.tolist()}")
+    if not np.array_equal(occ_g, occ_o):
+        bad.append(f"log-odds differ in {np.count_nonzero(occ_g != occ_o)} voxels")
+    if not np.array_equal(inf_g, inf_o):
+        bad.append(f"inflated map differs in {np.count_nonzero(inf_g != inf_o)} voxels")
+    return bad
+
+
+def test_depth_camera_frames_bit_exact():
+    n = 2
+    c = _cfg()
+    cam = p._lib.PopCamera()
+    p.load().pop_camera_default(p._lib.C.byref(cam), 160, 120)
+    cloud = _scene()
+    maps = gridmap.GridMaps(c, n_maps=n)
+    orcs = [oracle_lib.OracleGridMap(c) for _ in range(n)]
+    for k in range(6):
+        clouds, cams = [], []
+        for a in range(n):
+            pos, pw = _frame(cam, cloud, a, k)
+            if k == 3 and a == 1:
+                pw = np.concatenate([pw, [[30.0, 0.0, 1.0], [0.0, -40.0, 0.5], [9.0, 9.0, 3.5]]])   # outside / far points
+            clouds.append(pw)
+            cams.append(pos)
+            orcs[a].update(pw, pos)
+        maps.updateOccupancy(clouds, np.array(cams))
+        for a in range(n):
+            bad = _same(maps, a, orcs[a])
+            assert not bad, f"frame {k} map {a}: " + "; ".join(bad)
+    occ, inf, _ = maps.buffers(0)
+    assert (occ > np.log(c.p_occ / (1 - c.p_occ))).sum() > 200 and inf.sum() > 1000
+    # queries
+    rng = np.random.default_rng(0)
+    q = rng.uniform([-11, -11, -0.5], [11, 11, 4.5], (5000, 3))
+    o, i = maps.getOccupancy(0, q), maps.getInflateOccupancy(0, q)
+    org = np.array([-10.0, -10.0, c.ground_height])
+    inside = np.all((q >= org + 1e-4) & (q <= org + np.array([20.0, 20.0, 4.0]) - 1e-4), axis=1)
+    idx = np.floor((q[inside] - org) / c.resolution).astype(int)
+    assert (o[~inside] == -1).all() and (i[~inside] == -1).all()
+    assert np.array_equal(o[inside], (occ[idx[:, 0], idx[:, 1], idx[:, 2]] > np.log(c.p_occ / (1 - c.p_occ))).astype(np.int8))
+    assert np.array_equal(i[inside], inf[idx[:, 0], idx[:, 1], idx[:, 2]])
+    maps.close()
+
+
+def test_parity_across_the_flag_wrap():
+    """135 small frames: up to frame 127 ray ends are de-duplicated and rays stop on earlier rays; from frame 128
+    the reference's char flags no longer match its int counter and every point casts a full ray."""
+    c = _cfg()
+    maps = gridmap.GridMaps(c, n_maps=1)
+    orc = oracle_lib.OracleGridMap(c)
+    rng = np.random.default_rng(4)
+    base = rng.uniform([1.0, -2.0, 0.2], [4.0, 2.0, 2.2], (300, 3))
+    for k in range(135):
+        pos = np.array([-1.0 + 0.01 * k, 0.0, 1.0])
+        pts = np.concatenate([base + rng.normal(0, 0.02, base.shape), base[:40]])   # repeated end voxels
+        maps.updateOccupancy([pts], pos[None])
+        orc.update(pts, pos)
+        if k in (0, 60, 126, 127, 128, 134):
+            bad = _same(maps, 0, orc)
+            assert not bad, f"frame {k}: " + "; ".join(bad)
+    maps.close()
+
+
+def test_empty_frames_and_errors():
+    c = _cfg()
+    maps = gridmap.GridMaps(c, n_maps=2)
+    maps.updateOccupancy([np.zeros((0, 3)), np.zeros((0, 3))], np.zeros((2, 3)) + [0, 0, 1.0])
+    occ, inf, _ = maps.buffers(1)
+    assert (occ < np.log(c.p_min / (1 - c.p_min))).all() and not inf.any()    # all unknown
+    with pytest.raises(p.PopError):
+        maps.updateOccupancy([np.zeros((1, 3)), np.zeros((1, 3))], np.array([[0, 0, 1.0], [50.0, 0, 1.0]]))   # camera outside
+    maps.close()

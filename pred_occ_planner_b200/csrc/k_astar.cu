@@ -241,6 +241,7 @@ __global__ void __launch_bounds__(kThreads) k_astar(PopGeom g, AstarParams P, As
   int* heap = reinterpret_cast<int*>(f + P.cap);              // [cap]
   __shared__ Prim prim[kMaxPrim];
   __shared__ int s_tmp_node[kMaxPrim], s_tmp_owner[kMaxPrim], s_tmp_src[kMaxPrim];
+  __shared__ int s_leader[kMaxPrim], s_slot[kMaxPrim];
   __shared__ int s_ntmp, s_heap_size, s_use, s_iter, s_ret, s_done, s_cur, s_init, s_shot, s_term;
   __shared__ double s_cur_state[6], s_cur_time, s_cur_g, s_end[6], s_start[9], s_time_origin, s_center[3];
   __shared__ int s_cur_index[3], s_cur_tidx, s_end_index[3];
@@ -433,6 +434,21 @@ __global__ void __launch_bounds__(kThreads) k_astar(PopGeom g, AstarParams P, As
         pr.valid = valid;
       }
       __syncthreads();
+      // same-voxel duplicates among this expansion's new nodes (:345-360): the reference scans the list of nodes
+      // created so far for every primitive; here every primitive finds, in parallel, the first earlier valid
+      // primitive of its voxel (the one that will have created the node), so the ordered commit below is O(n)
+      if (tid < n_inputs) {
+        int leader = tid;
+        const Prim& pr = prim[tid];
+        if (pr.valid && pr.node < 0) {
+          for (int j = 0; j < tid; j++) {
+            const Prim& q = prim[j];
+            if (q.valid && q.id[0] == pr.id[0] && q.id[1] == pr.id[1] && q.id[2] == pr.id[2]) { leader = j; break; }
+          }
+        }
+        s_leader[tid] = leader;
+      }
+      __syncthreads();
 
       // ---- phase 2: ordered commit (:345-419) ----
       if (tid == 0) {
@@ -440,22 +456,18 @@ __global__ void __launch_bounds__(kThreads) k_astar(PopGeom g, AstarParams P, As
         for (int i = 0; i < n_inputs; i++) {
           Prim& pr = prim[i];
           if (!pr.valid) continue;
-          bool prune = false;
-          for (int j = 0; j < s_ntmp; j++) {
-            const Prim& q = prim[s_tmp_src[j]];
-            if (pr.id[0] == q.id[0] && pr.id[1] == q.id[1] && pr.id[2] == q.id[2]) {
-              prune = true;
-              const int en = s_tmp_node[j];
-              if (pr.f < f[en]) { f[en] = pr.f; s_tmp_owner[j] = i; }
-              break;
-            }
+          if (pr.node < 0 && s_leader[i] != i) {   // an earlier primitive of this expansion created the node
+            const int j = s_slot[s_leader[i]];
+            const int en = s_tmp_node[j];
+            if (pr.f < f[en]) { f[en] = pr.f; s_tmp_owner[j] = i; }
+            continue;
           }
-          if (prune) continue;
           if (pr.node < 0) {
             const int id = s_use;
             f[id] = pr.f;
             heap_push(heap, f, s_heap_size, id);
             s_tmp_node[s_ntmp] = id; s_tmp_owner[s_ntmp] = i; s_tmp_src[s_ntmp] = i;
+            s_slot[i] = s_ntmp;
             s_ntmp++;
             s_use++;
             if (s_use == P.cap) { s_done = 1; s_ret = POP_ASTAR_NO_PATH; s_term = -1; break; }

@@ -78,6 +78,36 @@ template <> struct Cell<float> {
   }
 };
 
+// Sum of the (2S+1) x (2S+1) x (2SZ+1) collision footprint in the reference's order (x outer, y, z inner), one
+// x-plane at a time: the plane's cells are loaded together, then added in order; see geom_query.
+template <typename C, int S, int SZ>
+__device__ __forceinline__ int geom_region_sum(const PopGeom& g, const uint8_t* grid, size_t slice, int ix, int iy,
+                                               int iz, float thr) {
+  constexpr int NY = 2 * S + 1, NZ = 2 * SZ + 1;
+  float sum = 0.0f;
+#pragma unroll
+  for (int dx = -S; dx <= S; dx++) {
+    const int x = ix + dx;
+    const bool xin = x >= 0 && x < g.nx;
+    float v[NY * NZ];
+#pragma unroll
+    for (int dy = -S; dy <= S; dy++) {
+      const int y = iy + dy;
+#pragma unroll
+      for (int dz = -SZ; dz <= SZ; dz++) {
+        const int z = iz + dz;
+        const bool in = xin && y >= 0 && y < g.ny && z >= 0 && z < g.nz;
+        v[(dy + S) * NZ + dz + SZ] =
+            in ? Cell<C>::load(grid, slice + static_cast<size_t>(z) * g.nx * g.ny + static_cast<size_t>(y) * g.nx + x) : 0.0f;
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < NY * NZ; k++) sum = __fadd_rn(sum, v[k]);
+    if (sum > thr) return 1;
+  }
+  return 0;
+}
+
 // getClearOcccupancy(pos, int t): fake_particle_risk_voxel.cpp:309-330 / risk_base.cpp:228-250.
 // Kernel order x outer, y, z inner with early exit, as in the reference.
 template <typename C>
@@ -104,6 +134,15 @@ __device__ __forceinline__ int geom_query(const PopGeom& g, const uint8_t* grid,
   const size_t slice = static_cast<size_t>(t) * g.V;
   const int s = g.inf_step;
   const int sz = g.kernel_shape == POP_KERNEL_DISC_Z0 ? 0 : s;
+  // Cells are non-negative, so the running sum never decreases and the reference's early exit ("return 1 as soon
+  // as the sum exceeds the threshold") equals comparing the sum of each x-plane, taken in the same order, once per
+  // plane.  That lets the loads of a plane be issued together instead of one dependent load per cell (the A*
+  // inner loop is bound by exactly this latency).  Out-of-range cells contribute 0, which changes neither the sum
+  // nor the comparison.
+  if (s == 2 && sz == 0) return geom_region_sum<C, 2, 0>(g, grid, slice, ix, iy, iz, thr);
+  if (s == 1 && sz == 1) return geom_region_sum<C, 1, 1>(g, grid, slice, ix, iy, iz, thr);
+  if (s == 2 && sz == 2) return geom_region_sum<C, 2, 2>(g, grid, slice, ix, iy, iz, thr);
+  if (s == 1 && sz == 0) return geom_region_sum<C, 1, 0>(g, grid, slice, ix, iy, iz, thr);
   float sum = 0.0f;
   for (int dx = -s; dx <= s; dx++) {
     const int x = ix + dx;

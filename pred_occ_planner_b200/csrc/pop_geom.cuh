@@ -143,6 +143,8 @@ __device__ __forceinline__ int geom_query(const PopGeom& g, const uint8_t* grid,
   if (s == 1 && sz == 1) return geom_region_sum<C, 1, 1>(g, grid, slice, ix, iy, iz, thr);
   if (s == 2 && sz == 2) return geom_region_sum<C, 2, 2>(g, grid, slice, ix, iy, iz, thr);
   if (s == 1 && sz == 0) return geom_region_sum<C, 1, 0>(g, grid, slice, ix, iy, iz, thr);
+  if (s == 3 && sz == 0) return geom_region_sum<C, 3, 0>(g, grid, slice, ix, iy, iz, thr);
+  if (s == 4 && sz == 0) return geom_region_sum<C, 4, 0>(g, grid, slice, ix, iy, iz, thr);   // 0.45 m clearance at 0.1 m
   float sum = 0.0f;
   for (int dx = -s; dx <= s; dx++) {
     const int x = ix + dx;

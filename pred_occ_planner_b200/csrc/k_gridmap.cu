@@ -79,8 +79,9 @@ struct GmMap {
 // K1: clip every projected point, count its end voxel, elect the casting point per end voxel (:337-377)
 __global__ void __launch_bounds__(256) k_gm_points(GmGeo G, const GmMap* __restrict__ maps, const double* __restrict__ pts_all,
                                                    const int* __restrict__ counts, const double* __restrict__ cam_all,
-                                                   int dedupe) {
+                                                   const int* __restrict__ flags_work) {
   const int m = blockIdx.y;
+  const int dedupe = flags_work[m];
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= counts[m]) return;
   const GmMap M = maps[m];
@@ -171,9 +172,11 @@ __device__ int gm_trace(const GmGeo& G, const double* pw, const double* cam, con
 
 // K2: rays in index order (one CTA per map)
 __global__ void __launch_bounds__(256) k_gm_rays(GmGeo G, const GmMap* __restrict__ maps, const int* __restrict__ counts,
-                                                 const double* __restrict__ cam_all, int prune, int* __restrict__ err) {
+                                                 const double* __restrict__ cam_all, const int* __restrict__ flags_work,
+                                                 int* __restrict__ err) {
   extern __shared__ unsigned smem[];
   const int m = blockIdx.x, tid = threadIdx.x;
+  const int prune = flags_work[m];
   const GmMap M = maps[m];
   const int np = counts[m];
   if (np == 0) return;
@@ -365,7 +368,9 @@ __global__ void k_gm_query(GmGeo G, GmMap M, const double* __restrict__ pos, int
 struct pop_gridmap {
   pop_gridmap_config cfg;
   GmGeo G;
-  int n_maps = 0, device = 0, frame = 0;
+  int n_maps = 0, device = 0;
+  std::vector<int> frame;        // md_.raycast_num_ of every map (advances only on frames with points, :316-320)
+  int* d_flags = nullptr;
   cudaStream_t stream = nullptr;
   bool own_stream = false;
   std::string err;
@@ -497,7 +502,9 @@ int pop_gridmap_create(const pop_gridmap_config* c, int n_maps, int device, void
   g->d_cam = static_cast<double*>(alloc(sizeof(double) * 3 * n_maps));
   g->d_counts = static_cast<int*>(alloc(sizeof(int) * n_maps));
   g->d_err = static_cast<int*>(alloc(sizeof(int)));
-  if (!ok || !g->d_maps || !g->d_pts || !g->d_cam || !g->d_counts || !g->d_err) { cudaGetLastError(); return fail(POP_E_CUDA); }
+  g->d_flags = static_cast<int*>(alloc(sizeof(int) * n_maps));
+  g->frame.assign(n_maps, 0);
+  if (!ok || !g->d_maps || !g->d_pts || !g->d_cam || !g->d_counts || !g->d_err || !g->d_flags) { cudaGetLastError(); return fail(POP_E_CUDA); }
   if (cudaMemcpyAsync(g->d_maps, g->h_maps.data(), sizeof(GmMap) * n_maps, cudaMemcpyHostToDevice, g->stream) != cudaSuccess ||
       cudaStreamSynchronize(g->stream) != cudaSuccess)
     return fail(POP_E_CUDA);
@@ -526,11 +533,16 @@ int pop_gridmap_update(pop_gridmap* g, const double* pts, const int32_t* counts,
   GM_CUDA(g, cudaMemcpyAsync(g->d_counts, counts, sizeof(int) * A, cudaMemcpyHostToDevice, st));
   GM_CUDA(g, cudaMemcpyAsync(g->d_cam, cam_pos, sizeof(double) * 3 * A, cudaMemcpyHostToDevice, st));
   if (maxn == 0) { GM_CUDA(g, cudaStreamSynchronize(st)); return POP_OK; }
-  g->frame += 1;                               // md_.raycast_num_
-  const int flags_work = g->frame <= 127;      // vector<char> flags vs the int counter
+  std::vector<int> flags_work(A);
+  for (int m = 0; m < A; m++) {
+    if (counts[m] > 0) g->frame[m] += 1;           // md_.raycast_num_
+    flags_work[m] = g->frame[m] <= 127;            // vector<char> flags vs the int counter
+  }
+  GM_CUDA(g, cudaMemcpyAsync(g->d_flags, flags_work.data(), sizeof(int) * A, cudaMemcpyHostToDevice, st));
+  GM_CUDA(g, cudaStreamSynchronize(st));           // flags_work is stack-owned
   k_gm_frame_reset<<<(A + 63) / 64, 64, 0, st>>>(g->d_maps, A);
-  k_gm_points<<<dim3((maxn + 255) / 256, A), 256, 0, st>>>(G, g->d_maps, g->d_pts, g->d_counts, g->d_cam, flags_work);
-  k_gm_rays<<<A, 256, g->rays_smem, st>>>(G, g->d_maps, g->d_counts, g->d_cam, flags_work, g->d_err);
+  k_gm_points<<<dim3((maxn + 255) / 256, A), 256, 0, st>>>(G, g->d_maps, g->d_pts, g->d_counts, g->d_cam, g->d_flags);
+  k_gm_rays<<<A, 256, g->rays_smem, st>>>(G, g->d_maps, g->d_counts, g->d_cam, g->d_flags, g->d_err);
   k_gm_update<<<dim3(64, A), 256, 0, st>>>(G, g->d_maps, g->d_counts, g->d_cam);
   k_gm_clear<<<dim3(128, A), 256, 0, st>>>(G, g->d_maps, g->d_counts);
   k_gm_inflate<<<dim3(128, A), 256, 0, st>>>(G, g->d_maps, g->d_counts);

@@ -91,8 +91,8 @@ struct DspDev {
   bool have_camera = false;
   int* depth = nullptr;       // [A][height*width] millimetres
   int* cam_counts = nullptr;  // [A]
-  float* rpose = nullptr;     // [A][32]: cam_pose r (9 f32) t (3 f32) | cam2world (16 f64 packed as 2 f32 each is avoided: see k_render.cu)
-  double* rpose_d = nullptr;  // [A][20]: cam2world (16) + body position (3) + pad
+  float* rpose = nullptr;     // [A][12]: cam_pose = cam2world^-1 as the splat kernel's float parameters, r (9) then t (3)
+  double* rpose_d = nullptr;  // [A][20]: cam2world (16, row-major) + body position (3) + pad, for the back-projection
   bool use_cam_counts = false;  // the next update reads cloud sizes from cam_counts (rendered input)
   int* seq = nullptr;         // [A][4] sequence counters of the three tables
   int* stats = nullptr;       // [A][8]

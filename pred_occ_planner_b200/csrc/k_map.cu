@@ -464,9 +464,19 @@ __global__ void __launch_bounds__(256) k_vox_fill(PopGeom g, int H, int nbands, 
 
 constexpr int kTileThreads = 256;
 constexpr int kTileChunk = 32 * 1024;   // bytes per bulk store
-constexpr int kTileMax = 96 * 1024;     // tile bytes: two CTAs per SM
+constexpr int kTileMaxDefault = 96 * 1024;   // tile bytes: two CTAs per SM (POP_TILE_KB overrides: smaller tiles, more CTAs per SM)
+static int tile_max_bytes() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("POP_TILE_KB");
+    v = e ? atoi(e) * 1024 : kTileMaxDefault;
+    if (v < 16 * 1024) v = 16 * 1024;
+    if (v > 200 * 1024) v = 200 * 1024;
+  }
+  return v;
+}
 
-__global__ void __launch_bounds__(kTileThreads, 2) k_vox_tiles(PopGeom g, int H, int nbands, float reach_per_slice,
+__global__ void __launch_bounds__(kTileThreads) k_vox_tiles(PopGeom g, int H, int nbands, float reach_per_slice,
                                                                uint8_t* __restrict__ grid, int n_agents,
                                                                const float* __restrict__ poses,
                                                                const PopCylDev* __restrict__ cyl, int n_cyl,
@@ -551,6 +561,7 @@ void popk_vox_free(pop_handle* h) {
 // band height: the largest H with nx*H <= kTileMax whose tiles start and end on 16-byte boundaries
 // (bulk-copy alignment); 0 if the grid cannot be tiled that way
 static int vox_band_rows(const PopGeom& g) {
+  const int kTileMax = tile_max_bytes();
   if (static_cast<long long>(g.nx) * g.ny <= kTileMax) return (g.nx * g.ny) % 16 == 0 ? g.ny : 0;
   int step = 1;
   while ((g.nx * step) % 16) step++;        // <= 16
@@ -607,7 +618,13 @@ static int vox_update_tiles(pop_handle* h, int sms, int* launches) {
   }
   // rows a voxel can move per slice: |vy|*dt/res (the kernel adds a 2-row rounding margin)
   const float reach = h->max_abs_vy * g.dt / g.res;
-  k_vox_tiles<<<2 * sms, kTileThreads, smem, h->stream>>>(g, H, nbands, reach, h->d_grid, nl, h->d_poses, h->d_cyl,
+  // persistent CTAs: as many as fit per SM with this tile size
+  static int per_sm = 0;
+  if (per_sm == 0) {
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_vox_tiles, kTileThreads, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+    if (per_sm > 8) per_sm = 8;
+  }
+  k_vox_tiles<<<per_sm * sms, kTileThreads, smem, h->stream>>>(g, H, nbands, reach, h->d_grid, nl, h->d_poses, h->d_cyl,
                                                          h->n_cyl, d->off, d->ent0, d->entf, cap);
   POP_LAUNCH_CHECK(h);
   (*launches)++;

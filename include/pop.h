@@ -431,6 +431,24 @@ int pop_gridmap_query(pop_gridmap* g, int map, const double* pos, int n, int8_t*
 /* occupancy_buffer_ (log-odds doubles, x-major), occupancy_buffer_inflate_, local_bound_min/max (6 ints) */
 int pop_gridmap_download(pop_gridmap* g, int map, double* occ, int8_t* inflate, int32_t* bounds);
 int pop_gridmap_dims(const pop_gridmap* g, int32_t* out3);
+/* GridMap::projectDepthImage parameters ("grid_map/..." ROS params, grid_map.cpp:29-42) */
+typedef struct pop_depth_params {
+  double  fx, fy, cx, cy;
+  double  k_depth_scaling_factor;    /* raw depth units per metre (1000 for millimetres) */
+  double  depth_filter_mindist, depth_filter_maxdist;
+  int32_t use_depth_filter;          /* the reference default is true */
+  int32_t depth_filter_margin;
+  int32_t skip_pixel;
+  int32_t rows, cols;
+  int32_t _pad;
+} pop_depth_params;
+int pop_gridmap_set_depth_params(pop_gridmap* g, const pop_depth_params* p);
+/* updateOccupancyCallback from a depth image: projectDepthImage (grid_map.cpp:210-311, including its first-frame
+ * skip with the depth filter and its pointer-stepping quirks) + raycastProcess + clearAndInflateLocalMap.
+ * depth = n_maps x rows x cols uint16, camera_r = n_maps x 9 row-major (camera_r_m_), cam_pos = n_maps x 3. */
+int pop_gridmap_update_depth(pop_gridmap* g, const uint16_t* depth, const double* camera_r, const double* cam_pos);
+/* the projected points of the last pop_gridmap_update_depth (proj_points_): out = cap x 3 doubles */
+int pop_gridmap_projected_points(pop_gridmap* g, int map, double* out, int cap, int32_t* n_out);
 
 /* ---- measurement ------------------------------------------------------------------------ */
 enum { POP_STAGE_VOXEL_UPDATE = 0, POP_STAGE_PEERS = 1, POP_STAGE_ASTAR = 2, POP_STAGE_CORRIDOR = 3,

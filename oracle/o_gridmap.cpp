@@ -230,6 +230,47 @@ void GridMapO::clear_and_inflate() {   // :477-583
   }
 }
 
+// projectDepthImage :210-311.  Quirks kept: without the filter the row pointer advances by ONE per sampled pixel
+// whatever skip_pixel is; with the filter the zero test reads the pixel AFTER the pointer advanced by skip_pixel
+// (the next sample; past the end of the image it is undefined in the reference and read as non-zero here), and the
+// very first frame only arms has_first_depth_.
+int project_depth(const pop_depth_params& P, bool& has_first, const uint16_t* img, const double* R, const double* cam,
+                  double max_ray, double* out, int cap) {
+  int n = 0;
+  auto emit = [&](int u, int v, double depth) {
+    const double x = (u - P.cx) * depth / P.fx, y = (v - P.cy) * depth / P.fy, z = depth;
+    if (n < cap)
+      for (int i = 0; i < 3; i++) out[3 * n + i] = ((R[3 * i] * x + R[3 * i + 1] * y) + R[3 * i + 2] * z) + cam[i];
+    n++;
+  };
+  const long long total = static_cast<long long>(P.rows) * P.cols;
+  if (!P.use_depth_filter) {
+    for (int v = 0; v < P.rows; v += P.skip_pixel) {
+      long long ptr = static_cast<long long>(v) * P.cols;
+      for (int u = 0; u < P.cols; u += P.skip_pixel) {
+        const double depth = img[ptr++] / P.k_depth_scaling_factor;
+        emit(u, v, depth);
+      }
+    }
+  } else {
+    if (!has_first) { has_first = true; return 0; }
+    const double inv_factor = 1.0 / P.k_depth_scaling_factor;
+    for (int v = P.depth_filter_margin; v < P.rows - P.depth_filter_margin; v += P.skip_pixel) {
+      long long ptr = static_cast<long long>(v) * P.cols + P.depth_filter_margin;
+      for (int u = P.depth_filter_margin; u < P.cols - P.depth_filter_margin; u += P.skip_pixel) {
+        double depth = img[ptr] * inv_factor;
+        ptr += P.skip_pixel;
+        const unsigned next = ptr < total ? img[ptr] : 1u;
+        if (next == 0) depth = max_ray + 0.1;
+        else if (depth < P.depth_filter_mindist) continue;
+        else if (depth > P.depth_filter_maxdist) depth = max_ray + 0.1;
+        emit(u, v, depth);
+      }
+    }
+  }
+  return n;
+}
+
 }  // namespace orc
 
 using namespace orc;
@@ -242,6 +283,14 @@ void orc_gridmap_update(void* h, const double* pts, int n, const double* cam) {
   GridMapO* m = static_cast<GridMapO*>(h);
   m->raycast(pts, n, cam);
   if (n > 0) m->clear_and_inflate();
+}
+// projectDepthImage alone; has_first is the map's has_first_depth_ flag (in/out)
+int orc_gridmap_project(const pop_depth_params* P, int* has_first, const uint16_t* img, const double* R, const double* cam,
+                        double max_ray, double* out, int cap) {
+  bool hf = *has_first != 0;
+  const int n = project_depth(*P, hf, img, R, cam, max_ray, out, cap);
+  *has_first = hf ? 1 : 0;
+  return n;
 }
 void orc_gridmap_download(void* h, double* occ, int8_t* inflate, int32_t* bounds) {
   GridMapO* m = static_cast<GridMapO*>(h);

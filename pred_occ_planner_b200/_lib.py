@@ -133,6 +133,15 @@ class PopGridmapConfig(C.Structure):
                 ("ground_height", C.c_double), ("local_map_margin", C.c_int32), ("max_points", C.c_int32)]
 
 
+class PopDepthParams(C.Structure):
+    """pop_depth_params (include/pop.h): GridMap::projectDepthImage parameters."""
+    _fields_ = [("fx", C.c_double), ("fy", C.c_double), ("cx", C.c_double), ("cy", C.c_double),
+                ("k_depth_scaling_factor", C.c_double), ("depth_filter_mindist", C.c_double),
+                ("depth_filter_maxdist", C.c_double), ("use_depth_filter", C.c_int32),
+                ("depth_filter_margin", C.c_int32), ("skip_pixel", C.c_int32), ("rows", C.c_int32),
+                ("cols", C.c_int32), ("_pad", C.c_int32)]
+
+
 class PopCycleIO(C.Structure):
     _fields_ = [("start", C.POINTER(C.c_double)), ("goal", C.POINTER(C.c_double)),
                 ("poses", C.POINTER(C.c_float)), ("t_map", C.c_double), ("t_plan", C.c_double),
@@ -216,6 +225,9 @@ SYMBOLS = [
     ("pop_gridmap_query", _I, [_VP, _I, _PD, _I, _PI8, _PI8]),
     ("pop_gridmap_download", _I, [_VP, _I, _PD, _PI8, _PI32]),
     ("pop_gridmap_dims", _I, [_VP, _PI32]),
+    ("pop_gridmap_set_depth_params", _I, [_VP, C.POINTER(PopDepthParams)]),
+    ("pop_gridmap_update_depth", _I, [_VP, C.POINTER(C.c_uint16), _PD, _PD]),
+    ("pop_gridmap_projected_points", _I, [_VP, _I, _PD, _I, _PI32]),
 ]
 
 _lib = None

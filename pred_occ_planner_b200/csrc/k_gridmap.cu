@@ -336,6 +336,77 @@ __global__ void __launch_bounds__(256) k_gm_inflate(GmGeo G, const GmMap* __rest
   }
 }
 
+// projectDepthImage :210-311 for every map: one CTA walks the sampled pixels in the reference's (v, u) order and
+// compacts the projected points in that order (the order is the order the rays are cast in).  Quirks kept: without
+// the filter the row pointer advances by one per sampled pixel whatever skip_pixel is; with the filter the zero
+// test reads the pixel after the pointer advanced by skip_pixel (non-zero past the end of the image).
+__global__ void __launch_bounds__(1024) k_gm_project(pop_depth_params P, double max_ray, const unsigned short* __restrict__ img_all,
+                                                     const double* __restrict__ R_all, const double* __restrict__ cam_all,
+                                                     const int* __restrict__ active, double* __restrict__ pts_all,
+                                                     int max_pts, int* __restrict__ counts, int* __restrict__ err) {
+  __shared__ int s_w[33];
+  const int m = blockIdx.x, tid = threadIdx.x;
+  if (!active[m]) { if (tid == 0) counts[m] = 0; return; }
+  const long long total = static_cast<long long>(P.rows) * P.cols;
+  const unsigned short* img = img_all + static_cast<size_t>(m) * total;
+  const double* R = R_all + 9 * m;
+  const double* cam = cam_all + 3 * m;
+  double* out = pts_all + static_cast<size_t>(m) * max_pts * 3;
+  const int mg = P.use_depth_filter ? P.depth_filter_margin : 0;
+  const int nu = P.cols - 2 * mg > 0 ? (P.cols - 2 * mg + P.skip_pixel - 1) / P.skip_pixel : 0;
+  const int nv = P.rows - 2 * mg > 0 ? (P.rows - 2 * mg + P.skip_pixel - 1) / P.skip_pixel : 0;
+  const int nsamp = nu * nv;
+  const double inv_factor = 1.0 / P.k_depth_scaling_factor;
+  int carry = 0;
+  for (int base = 0; base < nsamp; base += blockDim.x) {
+    const int s = base + tid;
+    bool keep = false;
+    double x = 0, y = 0, z = 0;
+    if (s < nsamp) {
+      const int jv = s / nu, ju = s % nu;
+      const int v = mg + jv * P.skip_pixel, u = mg + ju * P.skip_pixel;
+      double depth;
+      if (!P.use_depth_filter) {
+        depth = img[static_cast<long long>(v) * P.cols + ju] / P.k_depth_scaling_factor;
+        keep = true;
+      } else {
+        const long long ptr = static_cast<long long>(v) * P.cols + u;
+        depth = img[ptr] * inv_factor;
+        const unsigned next = ptr + P.skip_pixel < total ? img[ptr + P.skip_pixel] : 1u;
+        keep = true;
+        if (next == 0) depth = max_ray + 0.1;
+        else if (depth < P.depth_filter_mindist) keep = false;
+        else if (depth > P.depth_filter_maxdist) depth = max_ray + 0.1;
+      }
+      x = (u - P.cx) * depth / P.fx; y = (v - P.cy) * depth / P.fy; z = depth;
+    }
+    // ordered compaction (block-wide exclusive scan)
+    const int lane = tid & 31, w = tid >> 5;
+    int inc = keep ? 1 : 0;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+    __syncthreads();
+    if (lane == 31) s_w[w] = inc;
+    __syncthreads();
+    if (w == 0) {
+      int xv = s_w[lane], xi = xv;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, xi, o); if (lane >= o) xi += t; }
+      s_w[lane] = xi - xv;
+      if (lane == 31) s_w[32] = xi;
+    }
+    __syncthreads();
+    const int pos = carry + inc - (keep ? 1 : 0) + s_w[w];
+    if (keep && pos < max_pts)
+      for (int i = 0; i < 3; i++) out[3 * pos + i] = ((R[3 * i] * x + R[3 * i + 1] * y) + R[3 * i + 2] * z) + cam[i];
+    carry += s_w[32];
+  }
+  if (tid == 0) {
+    if (carry > max_pts) atomicOr(err, 2);
+    counts[m] = carry < max_pts ? carry : max_pts;
+  }
+}
+
 __global__ void k_gm_frame_reset(const GmMap* __restrict__ maps, int n_maps) {
   const int m = blockIdx.x * blockDim.x + threadIdx.x;
   if (m >= n_maps) return;
@@ -370,6 +441,12 @@ struct pop_gridmap {
   GmGeo G;
   int n_maps = 0, device = 0;
   std::vector<int> frame;        // md_.raycast_num_ of every map (advances only on frames with points, :316-320)
+  pop_depth_params depth;        // projectDepthImage parameters
+  bool have_depth = false;
+  std::vector<int> has_first;    // md_.has_first_depth_ per map
+  std::vector<int32_t> last_counts;
+  unsigned short* d_img = nullptr;
+  double* d_R = nullptr;
   int* d_flags = nullptr;
   cudaStream_t stream = nullptr;
   bool own_stream = false;
@@ -423,6 +500,8 @@ int pop_gridmap_destroy(pop_gridmap* g) {
   if (g->stream) cudaStreamSynchronize(g->stream);
   for (void* p : g->allocs) cudaFree(p);
   if (g->d_q) cudaFree(g->d_q);
+  if (g->d_img) cudaFree(g->d_img);
+  if (g->d_R) cudaFree(g->d_R);
   if (g->own_stream && g->stream) cudaStreamDestroy(g->stream);
   delete g;
   return POP_OK;
@@ -512,26 +591,13 @@ int pop_gridmap_create(const pop_gridmap_config* c, int n_maps, int device, void
   return POP_OK;
 }
 
-int pop_gridmap_update(pop_gridmap* g, const double* pts, const int32_t* counts, const double* cam_pos) {
-  if (!g || !pts || !counts || !cam_pos) return POP_E_INVALID;
+// raycastProcess + clearAndInflateLocalMap on the points resident in d_pts; counts = host copy of d_counts
+static int gm_run(pop_gridmap* g, const int32_t* counts) {
   const GmGeo& G = g->G;
   const int A = g->n_maps;
-  int maxn = 0;
-  for (int m = 0; m < A; m++) {
-    if (counts[m] < 0 || counts[m] > G.max_pts) return gm_fail(g, POP_E_CAPACITY, "map %d: %d points exceed max_points=%d", m, counts[m], G.max_pts);
-    const double* c = cam_pos + 3 * m;
-    for (int k = 0; k < 3; k++)
-      if (!(c[k] >= G.bmin[k] + 1e-4 && c[k] <= G.bmax[k] - 1e-4))
-        return gm_fail(g, POP_E_INVALID, "map %d: the camera must be inside the map (the reference indexes out of bounds otherwise)", m);
-    maxn = counts[m] > maxn ? counts[m] : maxn;
-  }
   cudaStream_t st = g->stream;
-  for (int m = 0; m < A; m++)
-    if (counts[m] > 0)
-      GM_CUDA(g, cudaMemcpyAsync(g->d_pts + static_cast<size_t>(m) * G.max_pts * 3, pts + static_cast<size_t>(m) * G.max_pts * 3,
-                                 sizeof(double) * 3 * counts[m], cudaMemcpyHostToDevice, st));
-  GM_CUDA(g, cudaMemcpyAsync(g->d_counts, counts, sizeof(int) * A, cudaMemcpyHostToDevice, st));
-  GM_CUDA(g, cudaMemcpyAsync(g->d_cam, cam_pos, sizeof(double) * 3 * A, cudaMemcpyHostToDevice, st));
+  int maxn = 0;
+  for (int m = 0; m < A; m++) maxn = counts[m] > maxn ? counts[m] : maxn;
   if (maxn == 0) { GM_CUDA(g, cudaStreamSynchronize(st)); return POP_OK; }
   std::vector<int> flags_work(A);
   for (int m = 0; m < A; m++) {
@@ -552,9 +618,92 @@ int pop_gridmap_update(pop_gridmap* g, const double* pts, const int32_t* counts,
   GM_CUDA(g, cudaStreamSynchronize(st));
   if (e) {
     cudaMemsetAsync(g->d_err, 0, sizeof(int), st);
+    if (e & 2) return gm_fail(g, POP_E_CAPACITY, "the depth image projects to more than max_points=%d points", G.max_pts);
     return gm_fail(g, POP_E_CAPACITY, "a ray left the %d^3 voxel box around the camera or exceeded %d voxels", G.B, kMaxPath);
   }
   return POP_OK;
+}
+
+static int gm_check_cameras(pop_gridmap* g, const double* cam_pos) {
+  const GmGeo& G = g->G;
+  for (int m = 0; m < g->n_maps; m++) {
+    const double* c = cam_pos + 3 * m;
+    for (int k = 0; k < 3; k++)
+      if (!(c[k] >= G.bmin[k] + 1e-4 && c[k] <= G.bmax[k] - 1e-4))
+        return gm_fail(g, POP_E_INVALID, "map %d: the camera must be inside the map (the reference indexes out of bounds otherwise)", m);
+  }
+  return POP_OK;
+}
+
+int pop_gridmap_update(pop_gridmap* g, const double* pts, const int32_t* counts, const double* cam_pos) {
+  if (!g || !pts || !counts || !cam_pos) return POP_E_INVALID;
+  const GmGeo& G = g->G;
+  const int A = g->n_maps;
+  for (int m = 0; m < A; m++)
+    if (counts[m] < 0 || counts[m] > G.max_pts) return gm_fail(g, POP_E_CAPACITY, "map %d: %d points exceed max_points=%d", m, counts[m], G.max_pts);
+  int rc = gm_check_cameras(g, cam_pos);
+  if (rc) return rc;
+  cudaStream_t st = g->stream;
+  for (int m = 0; m < A; m++)
+    if (counts[m] > 0)
+      GM_CUDA(g, cudaMemcpyAsync(g->d_pts + static_cast<size_t>(m) * G.max_pts * 3, pts + static_cast<size_t>(m) * G.max_pts * 3,
+                                 sizeof(double) * 3 * counts[m], cudaMemcpyHostToDevice, st));
+  GM_CUDA(g, cudaMemcpyAsync(g->d_counts, counts, sizeof(int) * A, cudaMemcpyHostToDevice, st));
+  GM_CUDA(g, cudaMemcpyAsync(g->d_cam, cam_pos, sizeof(double) * 3 * A, cudaMemcpyHostToDevice, st));
+  return gm_run(g, counts);
+}
+
+int pop_gridmap_set_depth_params(pop_gridmap* g, const pop_depth_params* p) {
+  if (!g || !p) return POP_E_INVALID;
+  if (p->rows < 1 || p->cols < 1 || p->skip_pixel < 1 || p->depth_filter_margin < 0 || !(p->fx > 0) || !(p->fy > 0) ||
+      !(p->k_depth_scaling_factor > 0))
+    return gm_fail(g, POP_E_INVALID, "bad depth parameters");
+  const size_t npix = static_cast<size_t>(p->rows) * p->cols;
+  if (g->d_img) { cudaFree(g->d_img); g->d_img = nullptr; }
+  if (g->d_R) { cudaFree(g->d_R); g->d_R = nullptr; }
+  GM_CUDA(g, cudaMalloc(&g->d_img, sizeof(unsigned short) * npix * g->n_maps));
+  GM_CUDA(g, cudaMalloc(&g->d_R, sizeof(double) * 9 * g->n_maps));
+  g->depth = *p;
+  g->have_depth = true;
+  g->has_first.assign(g->n_maps, 0);
+  return POP_OK;
+}
+
+int pop_gridmap_update_depth(pop_gridmap* g, const uint16_t* depth, const double* camera_r, const double* cam_pos) {
+  if (!g || !depth || !camera_r || !cam_pos) return POP_E_INVALID;
+  if (!g->have_depth) return gm_fail(g, POP_E_STATE, "no depth parameters (pop_gridmap_set_depth_params)");
+  int rc = gm_check_cameras(g, cam_pos);
+  if (rc) return rc;
+  const int A = g->n_maps;
+  cudaStream_t st = g->stream;
+  const size_t npix = static_cast<size_t>(g->depth.rows) * g->depth.cols;
+  // with the depth filter the first frame of a map only arms has_first_depth_ (:244-246)
+  std::vector<int> active(A, 1);
+  if (g->depth.use_depth_filter)
+    for (int m = 0; m < A; m++) { active[m] = g->has_first[m]; g->has_first[m] = 1; }
+  GM_CUDA(g, cudaMemcpyAsync(g->d_img, depth, sizeof(unsigned short) * npix * A, cudaMemcpyHostToDevice, st));
+  GM_CUDA(g, cudaMemcpyAsync(g->d_R, camera_r, sizeof(double) * 9 * A, cudaMemcpyHostToDevice, st));
+  GM_CUDA(g, cudaMemcpyAsync(g->d_cam, cam_pos, sizeof(double) * 3 * A, cudaMemcpyHostToDevice, st));
+  GM_CUDA(g, cudaMemcpyAsync(g->d_flags, active.data(), sizeof(int) * A, cudaMemcpyHostToDevice, st));
+  k_gm_project<<<A, 1024, 0, st>>>(g->depth, g->G.max_ray, g->d_img, g->d_R, g->d_cam, g->d_flags, g->d_pts, g->G.max_pts,
+                                   g->d_counts, g->d_err);
+  GM_CUDA(g, cudaGetLastError());
+  std::vector<int32_t> counts(A);
+  GM_CUDA(g, cudaMemcpyAsync(counts.data(), g->d_counts, sizeof(int) * A, cudaMemcpyDeviceToHost, st));
+  GM_CUDA(g, cudaStreamSynchronize(st));
+  g->last_counts = counts;
+  return gm_run(g, counts.data());
+}
+
+int pop_gridmap_projected_points(pop_gridmap* g, int map, double* out, int cap, int32_t* n_out) {
+  if (!g || map < 0 || map >= g->n_maps || !out || !n_out || cap < 0) return POP_E_INVALID;
+  if (g->last_counts.empty()) return gm_fail(g, POP_E_STATE, "no depth frame has been projected yet");
+  const int n = g->last_counts[map];
+  *n_out = n;
+  const int m = n < cap ? n : cap;
+  if (m > 0)
+    GM_CUDA(g, cudaMemcpy(out, g->d_pts + static_cast<size_t>(map) * g->G.max_pts * 3, sizeof(double) * 3 * m, cudaMemcpyDeviceToHost));
+  return n > cap ? POP_E_CAPACITY : POP_OK;
 }
 
 int pop_gridmap_query(pop_gridmap* g, int map, const double* pos, int n, int8_t* out_occ, int8_t* out_inflate) {

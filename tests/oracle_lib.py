@@ -369,3 +369,17 @@ class OracleGridMap:
         occ, inf, b = np.zeros(n), np.zeros(n, np.int8), np.zeros(6, np.int32)
         self.lib.orc_gridmap_download(self.h, _p(occ, C.c_double), _p(inf, C.c_int8), _p(b, C.c_int32))
         return occ.reshape(self.dims), inf.reshape(self.dims), b
+
+
+def gridmap_project(params, has_first, img, R, cam, max_ray, cap=1 << 20):
+    """orc::project_depth — GridMap::projectDepthImage for one map; returns (points, has_first')."""
+    lib = load().lib
+    img = np.ascontiguousarray(img, np.uint16)
+    R = np.ascontiguousarray(R, np.float64).reshape(9)
+    cam = np.ascontiguousarray(cam, np.float64).reshape(3)
+    out = np.zeros((cap, 3))
+    hf = C.c_int(int(has_first))
+    n = lib.orc_gridmap_project(C.byref(params), C.byref(hf), img.ctypes.data_as(C.POINTER(C.c_uint16)),
+                                _p(R, C.c_double), _p(cam, C.c_double), C.c_double(max_ray), _p(out, C.c_double), cap)
+    assert n <= cap
+    return out[:n].copy(), bool(hf.value)

@@ -116,3 +116,43 @@ def test_empty_frames_and_errors():
     with pytest.raises(p.PopError):
         maps.updateOccupancy([np.zeros((1, 3)), np.zeros((1, 3))], np.array([[0, 0, 1.0], [50.0, 0, 1.0]]))   # camera outside
     maps.close()
+
+
+def test_depth_image_pipeline_bit_exact():
+    """projectDepthImage on the device (ordered compaction, the reference's pointer quirks) feeding the raycast:
+    projected points and all map buffers equal the oracle's, with and without the depth filter."""
+    cam = p._lib.PopCamera()
+    p.load().pop_camera_default(p._lib.C.byref(cam), 160, 120)
+    cloud = _scene()
+    n = 2
+    for use_filter in (True, False):
+        c = _cfg()
+        maps = gridmap.GridMaps(c, n_maps=n)
+        P = gridmap.depth_params(cam.height, cam.width, cam.fx, cam.fy, cam.cx, cam.cy, use_filter=use_filter,
+                                 skip_pixel=2, margin=2, mindist=0.2, maxdist=5.0)
+        maps.setDepthParams(P)
+        orcs = [oracle_lib.OracleGridMap(c) for _ in range(n)]
+        has_first = [False] * n
+        # cam02body of the simulator: camera z forward = body x, camera x = -body y, camera y = -body z
+        c2b = np.array([[0.0, 0.0, 1.0], [-1.0, 0.0, 0.0], [0.0, -1.0, 0.0]])
+        for k in range(4):
+            imgs, Rs, cams = [], [], []
+            for a in range(n):
+                pos = np.array([-4.0 + 0.15 * k, -1.0 + 1.0 * a, 1.0 + 0.1 * a])
+                yaw = 0.1 * a + 0.05 * k
+                quat = np.array([np.cos(yaw / 2), 0, 0, np.sin(yaw / 2)])
+                depth, _, _ = oracle_lib.render(cam, pos, quat, cloud)
+                img = np.where(depth >= 65535, 0, depth).astype(np.uint16)     # empty pixels -> 0, millimetres
+                Rb = np.array([[np.cos(yaw), -np.sin(yaw), 0], [np.sin(yaw), np.cos(yaw), 0], [0, 0, 1.0]])
+                imgs.append(img); Rs.append(Rb @ c2b); cams.append(pos)
+            maps.updateOccupancyFromDepth(np.stack(imgs), np.stack(Rs), np.stack(cams))
+            for a in range(n):
+                pts, has_first[a] = oracle_lib.gridmap_project(P, has_first[a], imgs[a], Rs[a], cams[a], c.max_ray_length)
+                got = maps.projectedPoints(a)
+                assert got.shape == pts.shape and np.array_equal(got, pts), (use_filter, k, a)
+                orcs[a].update(pts, cams[a])
+                bad = _same(maps, a, orcs[a])
+                assert not bad, f"filter {use_filter} frame {k} map {a}: " + "; ".join(bad)
+        occ, inf, _ = maps.buffers(0)
+        assert (occ > np.log(c.p_min / (1 - c.p_min)) + 0.5).sum() > 50     # voxels that collected hits
+        maps.close()

@@ -80,3 +80,33 @@ def test_rays_of_a_frame_stop_on_earlier_rays():
         m.update(pts, cam)
     occ2 = m.buffers()[0]
     assert occ2[idx(pts[0])] == lo(c.p_max) and abs(occ2[idx(pts[1])] - lo(c.p_min)) < 1e-12
+
+
+def test_depth_projection():
+    """projectDepthImage: pinhole back-projection in (v, u) order; the first filtered frame only arms the filter;
+    too-near pixels are skipped, too-far and (next-sample) zero pixels become max-range free rays."""
+    from pred_occ_planner_b200 import gridmap
+    rows, cols = 24, 32
+    P = gridmap.depth_params(rows, cols, 30.0, 30.0, 16.0, 12.0, use_filter=True, skip_pixel=2, margin=2,
+                             mindist=0.2, maxdist=5.0)
+    img = np.full((rows, cols), 3000, np.uint16)
+    img[6, 10] = 100        # nearer than mindist: skipped
+    img[8, 12] = 9000       # farther than maxdist: max_ray + 0.1
+    img[10, 16] = 0         # zero at a sampled pixel: the PREVIOUS sample (u = 14) is the one turned into a free ray
+    R = np.eye(3)
+    cam = np.array([0.0, 0.0, 1.0])
+    pts, hf = oracle_lib.gridmap_project(P, False, img, R, cam, 4.5)
+    assert len(pts) == 0 and hf                               # first frame
+    pts, hf = oracle_lib.gridmap_project(P, True, img, R, cam, 4.5)
+    nu, nv = len(range(2, cols - 2, 2)), len(range(2, rows - 2, 2))
+    assert len(pts) == nu * nv - 2                            # the too-near pixel and the zero pixel itself (depth 0)
+    z = pts[:, 2] - 1.0
+    assert np.isclose(z, 3.0).sum() == nu * nv - 4 and np.isclose(z, 4.6).sum() == 2   # 9000 and the sample before the zero
+    # first sample: u = v = 2
+    assert np.allclose(pts[0], [(2 - 16.0) * 3.0 / 30.0, (2 - 12.0) * 3.0 / 30.0, 4.0])
+    # without the filter the row pointer advances by one per sample (skip_pixel = 2 reads columns 0, 1, 2, ...)
+    P2 = gridmap.depth_params(rows, cols, 30.0, 30.0, 16.0, 12.0, use_filter=False, skip_pixel=2)
+    img2 = np.tile(np.arange(cols, dtype=np.uint16) * 100 + 1000, (rows, 1))
+    pts2, _ = oracle_lib.gridmap_project(P2, False, img2, R, cam, 4.5)
+    assert len(pts2) == (cols // 2) * (rows // 2)
+    assert np.allclose(pts2[:4, 2] - 1.0, [1.0, 1.1, 1.2, 1.3])

@@ -64,3 +64,31 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
                 txt = open(os.path.join(dp, f)).read()
                 assert "oracle" not in txt.lower(), f"{f} mentions the oracle"
+
+
+def test_default_configs_carry_the_reference_values(pop):
+    """Defaults that need no device: the particle map's compile-time constants (map_parameters.h), the raycast
+    map's "grid_map/..." parameters and the simulator camera."""
+    cfg = pop.default_config()
+    d = pop.PopDspConfig()
+    pop.load().pop_dsp_default_config(C.byref(cfg), C.byref(d))
+    assert (d.half_fov_h, d.half_fov_v, d.angle_resolution, d.max_particle_num_voxel) == (43, 29, 1, 7)
+    V = cfg.nx * cfg.ny * cfg.nz
+    assert d.pyramid_capacity == int(V * 7 + 1e5) // (360 * 180) * 2 == 20        # SAFE_PARTICLE_NUM_PYRAMID
+    assert d.max_points == 5000 and d.new_born_particle_number_each_point == 20 and d.max_points_per_pyramid == 100
+    assert abs(d.new_born_particle_weight - 1e-4) < 1e-9 and abs(d.prediction_future_time[5] - 1.8) < 1e-6
+    g = pop.PopGridmapConfig()
+    pop.load().pop_gridmap_default_config(C.byref(g))
+    assert (g.p_hit, g.p_miss, g.p_min, g.p_max, g.p_occ) == (0.70, 0.35, 0.12, 0.97, 0.80)
+    cam = pop._lib.PopCamera()
+    pop.load().pop_camera_default(C.byref(cam), 640, 480)
+    assert abs(cam.fx - 387.229248046875) < 1e-4 and cam.sensing_horizon == 6.0
+    assert list(cam.cam2body) == [0, 0, 1, 0, -1, 0, 0, 0, 0, -1, 0, 0, 0, 0, 0, 1]   # pcl_render_node.cpp:338
+
+
+@pytest.mark.skipif(_has_gpu(), reason="only meaningful without a CUDA device")
+def test_raycast_map_has_no_cpu_fallback(pop):
+    from pred_occ_planner_b200 import gridmap
+    with pytest.raises(pop.PopError) as e:
+        gridmap.GridMaps(n_maps=1)
+    assert e.value.code == -2  # POP_E_NO_DEVICE

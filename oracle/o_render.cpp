@@ -63,9 +63,12 @@ void render_depth(const pop_camera& c, const double cam2world[16], const float* 
     if (ux < 0 || ux >= W || uy < 0 || uy >= H) continue;
     const float dist = tz;
     const int dist_mm = static_cast<int>(dist * 1000.0f + 0.5f);
-    const int rad = static_cast<int>(0.0573 * c.fx / dist + 0.5f);
-    for (int i = -rad; i <= rad; i++)
-      for (int j = -rad; j <= rad; j++) {
+    // a radius beyond the image covers the whole image: capped before the int conversion (out of range in the
+    // reference for a point millimetres from the lens)
+    const double rd = 0.0573 * c.fx / dist + 0.5f;
+    const int rad = rd > 8192.0 ? 8192 : static_cast<int>(rd);
+    for (int i = std::max(-rad, -uy); i <= std::min(rad, H - 1 - uy); i++)
+      for (int j = std::max(-rad, -ux); j <= std::min(rad, W - 1 - ux); j++) {
         const int x = ux + j, y = uy + i;
         if (x < 0 || x >= W || y < 0 || y >= H) continue;
         int32_t& d = depth[static_cast<size_t>(y) * W + x];

@@ -79,7 +79,7 @@ struct GmMap {
 // K1: clip every projected point, count its end voxel, elect the casting point per end voxel (:337-377)
 __global__ void __launch_bounds__(256) k_gm_points(GmGeo G, const GmMap* __restrict__ maps, const double* __restrict__ pts_all,
                                                    const int* __restrict__ counts, const double* __restrict__ cam_all,
-                                                   const int* __restrict__ flags_work) {
+                                                   const int* __restrict__ flags_work, int* __restrict__ err) {
   const int m = blockIdx.y;
   const int dedupe = flags_work[m];
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -116,6 +116,11 @@ __global__ void __launch_bounds__(256) k_gm_points(GmGeo G, const GmMap* __restr
       occ = 0;
     }
   }
+  if (!(isfinite(pw[0]) && isfinite(pw[1]) && isfinite(pw[2]))) {   // depth-derived points are finite; refuse others
+    atomicOr(err, 4);
+    M.endv[i] = -2;
+    return;
+  }
   int id[3];
   gm_pos_to_index(G, pw, id);
   int a = gm_addr(G, id);
@@ -146,8 +151,9 @@ __device__ int gm_trace(const GmGeo& G, const double* pw, const double* cam, con
     tmax[k] = gm_intbound(s[k], d[k]);
     tdelta[k] = static_cast<double>(st[k]) / d[k];
   }
-  int len = 0;
+  int len = 0, steps = 0;
   while (!(x[0] == ex[0] && x[1] == ex[1] && x[2] == ex[2])) {
+    if (++steps > 4 * cap) { *bad = true; return len; }   // non-finite input: the reference's loop would not end
     // the voxel whose centre ((ray + 0.5) * res) the reference hands to setCacheOccupancy
     int id[3];
     for (int k = 0; k < 3; k++) {
@@ -195,7 +201,7 @@ __global__ void __launch_bounds__(256) k_gm_rays(GmGeo G, const GmMap* __restric
     if (tid < kChunk) {
       const int i = base + tid;
       int len = -1;
-      if (i < np && (!prune || M.endv[i] < 0 || M.first_end[M.endv[i]] == i)) {
+      if (i < np && M.endv[i] != -2 && (!prune || M.endv[i] < 0 || M.first_end[M.endv[i]] == i)) {
         bool bad = false;
         len = gm_trace(G, M.pw + static_cast<size_t>(i) * 3, cam, box0, paths + tid * kMaxPath, kMaxPath, &bad);
         if (bad) atomicOr(err, 1);
@@ -607,7 +613,7 @@ static int gm_run(pop_gridmap* g, const int32_t* counts) {
   GM_CUDA(g, cudaMemcpyAsync(g->d_flags, flags_work.data(), sizeof(int) * A, cudaMemcpyHostToDevice, st));
   GM_CUDA(g, cudaStreamSynchronize(st));           // flags_work is stack-owned
   k_gm_frame_reset<<<(A + 63) / 64, 64, 0, st>>>(g->d_maps, A);
-  k_gm_points<<<dim3((maxn + 255) / 256, A), 256, 0, st>>>(G, g->d_maps, g->d_pts, g->d_counts, g->d_cam, g->d_flags);
+  k_gm_points<<<dim3((maxn + 255) / 256, A), 256, 0, st>>>(G, g->d_maps, g->d_pts, g->d_counts, g->d_cam, g->d_flags, g->d_err);
   k_gm_rays<<<A, 256, g->rays_smem, st>>>(G, g->d_maps, g->d_counts, g->d_cam, g->d_flags, g->d_err);
   k_gm_update<<<dim3(64, A), 256, 0, st>>>(G, g->d_maps, g->d_counts, g->d_cam);
   k_gm_clear<<<dim3(128, A), 256, 0, st>>>(G, g->d_maps, g->d_counts);
@@ -618,6 +624,7 @@ static int gm_run(pop_gridmap* g, const int32_t* counts) {
   GM_CUDA(g, cudaStreamSynchronize(st));
   if (e) {
     cudaMemsetAsync(g->d_err, 0, sizeof(int), st);
+    if (e & 4) return gm_fail(g, POP_E_INVALID, "non-finite projected points");
     if (e & 2) return gm_fail(g, POP_E_CAPACITY, "the depth image projects to more than max_points=%d points", G.max_pts);
     return gm_fail(g, POP_E_CAPACITY, "a ray left the %d^3 voxel box around the camera or exceeded %d voxels", G.B, kMaxPath);
   }

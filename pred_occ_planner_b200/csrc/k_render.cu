@@ -36,12 +36,18 @@ __global__ void __launch_bounds__(256) k_depth_splat(pop_camera cam, const float
   const int uy = static_cast<int>(ty / tz * cam.fy + cam.cy + 0.5);
   if (ux < 0 || ux >= cam.width || uy < 0 || uy >= cam.height) return;
   const int dist_mm = static_cast<int>(tz * 1000.0f + 0.5f);
-  const int rad = static_cast<int>(0.0573 * cam.fx / tz + 0.5f);
-  const int side = 2 * rad + 1;
+  // footprint radius; a radius beyond the image covers the whole image, so it is capped before the int conversion
+  // (a point millimetres from the lens would otherwise give an astronomically large loop — and an out-of-range
+  // double -> int conversion in the reference)
+  const double rd = 0.0573 * cam.fx / tz + 0.5f;
+  const int rad = rd > 8192.0 ? 8192 : static_cast<int>(rd);
+  // only the part of the footprint inside the image is visited (the reference skips the rest pixel by pixel)
+  const int x0 = max(ux - rad, 0), x1 = min(ux + rad, cam.width - 1);
+  const int y0 = max(uy - rad, 0), y1 = min(uy + rad, cam.height - 1);
+  const int sx = x1 - x0 + 1, sy = y1 - y0 + 1;
   int* depth = depth_all + static_cast<size_t>(a) * cam.width * cam.height;
-  for (int e = lane; e < side * side; e += 16) {
-    const int x = ux + e % side - rad, y = uy + e / side - rad;
-    if (x < 0 || x >= cam.width || y < 0 || y >= cam.height) continue;
+  for (int e = lane; e < sx * sy; e += 16) {
+    const int x = x0 + e % sx, y = y0 + e / sx;
     atomicMin(depth + static_cast<size_t>(y) * cam.width + x, dist_mm);
   }
 }

@@ -75,3 +75,15 @@ def test_device_resident_perception_loop(pop, oracle):
         maps.cloudCallback([np.zeros((0, 3), np.float32)] * n, pos.astype(np.float32), quat.astype(np.float32), st + 0.1)
         maps.cloudCallbackRendered(pos.astype(np.float32), quat.astype(np.float32), st + 0.2)
     eng.close()
+
+
+def test_point_on_the_lens(pop):
+    """Footprints far larger than the image are clipped to it (and capped before the int conversion)."""
+    cfg, d, eng, maps, cam, cloud = _setup(pop, 1)
+    near = np.array([[-3.998, -1.0, 1.0], [-4.0 + 1e-7, -1.0, 1.0], [-1.0, -1.0, 1.0]], np.float32)
+    eng.set_world_cloud(near)
+    pos, quat = _poses(1, 0)
+    counts, depth = maps.render(pos, quat, want_depth=True)
+    ref_depth, ref_cam, _ = oracle_lib.render(cam, pos[0], quat[0], near)
+    assert np.array_equal(depth[0], ref_depth) and counts[0] == len(ref_cam)
+    eng.close()

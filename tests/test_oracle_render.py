@@ -50,3 +50,12 @@ def test_occlusion_horizon_and_pose():
     assert (depth == 999999).all() and len(pc) == 0
     depth, pc, _ = oracle_lib.render(cam, [0, 0, 0], [1, 0, 0, 0], np.zeros((0, 3), np.float32))
     assert (depth == 999999).all() and len(pc) == 0
+
+
+def test_point_on_the_lens_fills_the_image_and_terminates():
+    """A point millimetres in front of the camera has a footprint radius of ~1e4 pixels: it covers the whole
+    image (the reference would loop over 1e8 pixel offsets and overflow its int conversion closer still)."""
+    cam = _camera()
+    depth, pc, _ = oracle_lib.render(cam, [0, 0, 0], [1, 0, 0, 0], np.array([[0.002, 0.0, 0.0], [1e-7, 0.0, 0.0]], np.float32))
+    assert (depth == 0).all() or (depth == 2).all()       # the nearer one rounds to 0 mm and wins everywhere
+    assert len(pc) == 0 or np.allclose(pc[:, 2], 0.002)

@@ -601,6 +601,10 @@ void DspMap::occupancy_resample() {
 int DspMap::update(int n, const float* pts, const float* pos, double stamp, const float* q) {
   if (first) { last_pos[0] = pos[0]; last_pos[1] = pos[1]; last_pos[2] = pos[2]; last_stamp = stamp; first = false; }
   if (std::fabs(q[0]) > 1.001f || std::fabs(q[1]) > 1.001f || std::fabs(q[2]) > 1.001f || std::fabs(q[3]) > 1.001f) return 0;
+  // non-finite odometry passes the reference's comparisons; rejected here and in the CUDA path
+  for (int k = 0; k < 4; k++) if (!std::isfinite(q[k])) return 0;
+  for (int k = 0; k < 3; k++) if (!std::isfinite(pos[k])) return 0;
+  if (!std::isfinite(stamp)) return 0;
   const float dx = pos[0] - last_pos[0], dy = pos[1] - last_pos[1], dz = pos[2] - last_pos[2];
   const float dt = static_cast<float>(stamp - last_stamp);
   if (std::fabs(dx) > 10.f || std::fabs(dy) > 10.f || std::fabs(dz) > 10.f || dt < 0.f || dt > 10.f) return 0;

@@ -55,6 +55,11 @@ void make_frames(pop_handle* h, const int32_t* counts, const float* poses, const
     for (int k = 0; k < 4; k++) f.q[k] = q[k];
     for (int k = 0; k < 3; k++) f.pos[k] = p[k];
     bool ok = !(std::fabs(q[0]) > 1.001f || std::fabs(q[1]) > 1.001f || std::fabs(q[2]) > 1.001f || std::fabs(q[3]) > 1.001f);
+    // non-finite odometry passes the reference's comparisons and poisons the whole map; it is rejected like any
+    // other invalid odometry
+    for (int k = 0; k < 4; k++) ok = ok && std::isfinite(q[k]);
+    for (int k = 0; k < 3; k++) ok = ok && std::isfinite(p[k]);
+    ok = ok && std::isfinite(stamp);
     if (ok) {
       const float dx = p[0] - d->last_pos[3 * a], dy = p[1] - d->last_pos[3 * a + 1], dz = p[2] - d->last_pos[3 * a + 2];
       const float dt = static_cast<float>(stamp - d->last_stamp[a]);
@@ -83,6 +88,11 @@ int run_update(pop_handle* h, const float* in, int stride_pts, const int32_t* co
   d->use_cam_counts = rendered;
   for (int a = 0; a < A; a++)
     if (counts[a] < 0 || counts[a] > cap) return pop_fail(h, POP_E_CAPACITY, "agent %d: %d points exceed the capacity %d", a, counts[a], cap);
+  if (filtered)   // points that skip the voxel filter (which drops non-finite ones, as PCL does) must be finite
+    for (int a = 0; a < A; a++)
+      for (int i = 0; i < 3 * counts[a]; i++)
+        if (!std::isfinite(in[static_cast<size_t>(a) * stride_pts * 3 + i]))
+          return pop_fail(h, POP_E_INVALID, "agent %d: non-finite filtered point", a);
   make_frames(h, counts, poses, quats, stamp, out_ok);
   POP_CUDA(h, cudaMemcpyAsync(d->frame, d->h_frame.data(), sizeof(DspFrame) * A, cudaMemcpyHostToDevice, h->stream));
   float* dst = filtered ? d->pts : d->cam;

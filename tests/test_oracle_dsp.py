@@ -207,3 +207,14 @@ def test_oracle_reproduces_committed_vectors(oracle):
     assert np.array_equal(parts[live[:, 0], live[:, 1]], g["live_state"])
     nz = g["risk_idx"]
     assert np.array_equal(np.argwhere(risk != 0), nz) and np.array_equal(risk[nz[:, 0], nz[:, 1]], g["risk_val"])
+
+
+def test_non_finite_odometry_is_rejected(oracle):
+    cfg, d, m = _make(oracle)
+    pts = np.array([[2.0, 0.0, 0.5]], np.float32)
+    assert m.update_filtered(pts, [0, 0, 1.0], [1, 0, 0, 0], 1.0) == 1
+    before = m.particles()
+    assert m.update_filtered(pts, [np.nan, 0, 1.0], [1, 0, 0, 0], 1.1) == 0
+    assert m.update_filtered(pts, [0, 0, 1.0], [np.nan, 0, 0, 0], 1.1) == 0
+    assert m.update_filtered(pts, [0, 0, 1.0], [1, 0, 0, 0], np.inf) == 0
+    assert np.array_equal(m.particles(), before)

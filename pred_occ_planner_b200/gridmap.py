@@ -82,6 +82,26 @@ class GridMaps:
                                                   as_ptr(b, C.c_int32)))
         return occ.reshape(self.dims), inf.reshape(self.dims), b
 
+    def setDepthParams(self, params):
+        self.depth = params
+        self._check(self.lib.pop_gridmap_set_depth_params(self._h, C.byref(params)))
+
+    def updateOccupancyFromDepth(self, depth, camera_r, cam_pos):
+        """projectDepthImage + raycastProcess + clearAndInflateLocalMap: depth [n_maps, rows, cols] uint16,
+        camera_r [n_maps, 3, 3] (camera to world), cam_pos [n_maps, 3]."""
+        depth = np.ascontiguousarray(depth, np.uint16).reshape(self.n_maps, self.depth.rows, self.depth.cols)
+        R = np.ascontiguousarray(camera_r, np.float64).reshape(self.n_maps, 9)
+        cam = np.ascontiguousarray(cam_pos, np.float64).reshape(self.n_maps, 3)
+        self._check(self.lib.pop_gridmap_update_depth(self._h, depth.ctypes.data_as(C.POINTER(C.c_uint16)),
+                                                      as_ptr(R, C.c_double), as_ptr(cam, C.c_double)))
+
+    def projectedPoints(self, m: int):
+        cap = self.cfg.max_points
+        out = np.zeros((cap, 3))
+        n = C.c_int32(0)
+        self._check(self.lib.pop_gridmap_projected_points(self._h, m, as_ptr(out, C.c_double), cap, C.byref(n)))
+        return out[:n.value].copy()
+
 
 def depth_params(rows: int, cols: int, fx: float, fy: float, cx: float, cy: float, use_filter: bool = True,
                  skip_pixel: int = 2, margin: int = 2, mindist: float = 0.2, maxdist: float = 5.0,
@@ -95,30 +115,3 @@ def depth_params(rows: int, cols: int, fx: float, fy: float, cx: float, cy: floa
     p.depth_filter_margin, p.skip_pixel, p.rows, p.cols = margin, skip_pixel, rows, cols
     return p
 
-
-def _set_depth_params(self, params):
-    self.depth = params
-    self._check(self.lib.pop_gridmap_set_depth_params(self._h, C.byref(params)))
-
-
-def _update_depth(self, depth, camera_r, cam_pos):
-    """projectDepthImage + raycastProcess + clearAndInflateLocalMap: depth [n_maps, rows, cols] uint16,
-    camera_r [n_maps, 3, 3] (camera to world), cam_pos [n_maps, 3]."""
-    depth = np.ascontiguousarray(depth, np.uint16).reshape(self.n_maps, self.depth.rows, self.depth.cols)
-    R = np.ascontiguousarray(camera_r, np.float64).reshape(self.n_maps, 9)
-    cam = np.ascontiguousarray(cam_pos, np.float64).reshape(self.n_maps, 3)
-    self._check(self.lib.pop_gridmap_update_depth(self._h, depth.ctypes.data_as(C.POINTER(C.c_uint16)),
-                                                  as_ptr(R, C.c_double), as_ptr(cam, C.c_double)))
-
-
-def _projected_points(self, m: int):
-    cap = self.cfg.max_points
-    out = np.zeros((cap, 3))
-    n = C.c_int32(0)
-    self._check(self.lib.pop_gridmap_projected_points(self._h, m, as_ptr(out, C.c_double), cap, C.byref(n)))
-    return out[:n.value].copy()
-
-
-GridMaps.setDepthParams = _set_depth_params
-GridMaps.updateOccupancyFromDepth = _update_depth
-GridMaps.projectedPoints = _projected_points

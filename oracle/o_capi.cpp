@@ -143,6 +143,19 @@ int orc_firi(const double* bd24, const double* pc, int n, const double* a, const
   return rows;
 }
 
+// the same with the caller's initial radii r (in/out), as firi::firi's own signature has them
+int orc_firi_r(const double* bd24, const double* pc, int n, const double* a, const double* b, int iterations,
+               uint64_t seed, double* r, double* out_h, int cap_rows) {
+  std::vector<V3d> pts(n);
+  for (int i = 0; i < n; i++) pts[i] = V3d{pc[3 * i], pc[3 * i + 1], pc[3 * i + 2]};
+  Poly poly;
+  uint64_t s = seed;
+  if (!firi(bd24, pts, V3d{a[0], a[1], a[2]}, V3d{b[0], b[1], b[2]}, poly, r, iterations, &s)) return 0;
+  const int rows = poly.rows();
+  for (int i = 0; i < std::min(rows, cap_rows) * 4; i++) out_h[i] = poly.h[i];
+  return rows;
+}
+
 // corridor stage; out_hpoly = POP_MAX_PIECES x POP_MAX_FACES x 4; returns number of corridors
 int orc_corridor(void* h, const double* path, int n, const double* start9, double traj_start_time,
                  double* out_hpoly, int32_t* out_rows, double* out_goal) {

@@ -565,3 +565,24 @@ CorridorResult corridor_stage(const Grid& g, const pop_config& c, const std::vec
 }
 
 }  // namespace orc
+
+// test hooks: the MVIE cost at one point and maxVolInsEllipsoid alone (tests/test_ref_pins.py compares them with
+// the reference's own firi.hpp compiled into oracle/_ref/libref.so)
+extern "C" double orc_cost_mvie(const double* A, int M, double smooth_eps, double penalty_wt, const double* x, double* grad) {
+  orc::MvieData D;
+  D.M = M; D.smooth_eps = smooth_eps; D.penalty = penalty_wt;
+  D.A.assign(A, A + static_cast<size_t>(M) * 3);
+  return orc::cost_mvie(D, x, grad);
+}
+extern "C" int orc_mvie(const double* hpoly, int M, double* R, double* p, double* r, uint64_t seed) {
+  std::vector<double> h(hpoly, hpoly + static_cast<size_t>(M) * 4);
+  uint64_t s = seed;
+  return orc::max_vol_ins_ellipsoid(h, R, p, r, &s) ? 1 : 0;
+}
+extern "C" int orc_lbfgs_mvie(const double* A, int M, double smooth_eps, double penalty_wt, double* x, double* fx) {
+  orc::MvieData D;
+  D.M = M; D.smooth_eps = smooth_eps; D.penalty = penalty_wt;
+  D.A.assign(A, A + static_cast<size_t>(M) * 3);
+  orc::LbfgsParams P;
+  return orc::lbfgs9(D, x, *fx, P, nullptr);
+}

@@ -97,6 +97,35 @@ static double intbound(double s, double ds) {
 }
 static int signum(int x) { return x == 0 ? 0 : x < 0 ? -1 : 1; }
 
+// RayCaster (plan_env/src/raycast.cpp:242-335): setInput floors both ends to voxel coordinates and prepares the
+// per-axis crossing times; step hands out the current voxel, stops at the end voxel, else advances along the axis
+// with the smallest crossing time (ties: y before x, z before both).
+struct RayDda {
+  int x[3], ex[3], st[3];
+  double tmax[3], tdelta[3];
+  bool set_input(const double* s, const double* e) {
+    for (int k = 0; k < 3; k++) {
+      x[k] = static_cast<int>(std::floor(s[k]));
+      ex[k] = static_cast<int>(std::floor(e[k]));
+      const double d = ex[k] - x[k];
+      st[k] = signum(static_cast<int>(d));
+      tmax[k] = intbound(s[k], d);
+      tdelta[k] = static_cast<double>(st[k]) / d;
+    }
+    return !(st[0] == 0 && st[1] == 0 && st[2] == 0);
+  }
+  bool step(double* ray) {
+    for (int k = 0; k < 3; k++) ray[k] = static_cast<double>(x[k]);
+    if (x[0] == ex[0] && x[1] == ex[1] && x[2] == ex[2]) return false;
+    if (tmax[0] < tmax[1]) {
+      if (tmax[0] < tmax[2]) { x[0] += st[0]; tmax[0] += tdelta[0]; } else { x[2] += st[2]; tmax[2] += tdelta[2]; }
+    } else {
+      if (tmax[1] < tmax[2]) { x[1] += st[1]; tmax[1] += tdelta[1]; } else { x[2] += st[2]; tmax[2] += tdelta[2]; }
+    }
+    return true;
+  }
+};
+
 void GridMapO::raycast(const double* pts, int np, const double* cam) {
   if (np == 0) return;
   raycast_num += 1;
@@ -127,27 +156,12 @@ void GridMapO::raycast(const double* pts, int np, const double* cam) {
       if (flag_rayend[vox] == raycast_num) continue;         // char vs int: true only while raycast_num <= 127
       flag_rayend[vox] = static_cast<char>(raycast_num);
     }
-    // RayCaster::setInput(pt_w / res, camera / res) + step loop
-    double s[3], e[3];
+    // RayCaster::setInput(pt_w / res, camera / res) + step loop (:379-395)
+    double s[3], e[3], ray[3];
     for (int k = 0; k < 3; k++) { s[k] = pw[k] / res; e[k] = cam[k] / res; }
-    int x[3], ex[3], st[3];
-    double d[3], tmax[3], tdelta[3];
-    for (int k = 0; k < 3; k++) {
-      x[k] = static_cast<int>(std::floor(s[k]));
-      ex[k] = static_cast<int>(std::floor(e[k]));
-      d[k] = ex[k] - x[k];
-      st[k] = signum(static_cast<int>(d[k]));
-      tmax[k] = intbound(s[k], d[k]);
-      tdelta[k] = static_cast<double>(st[k]) / d[k];
-    }
-    while (true) {
-      const double ray[3] = {static_cast<double>(x[0]), static_cast<double>(x[1]), static_cast<double>(x[2])};
-      if (x[0] == ex[0] && x[1] == ex[1] && x[2] == ex[2]) break;
-      if (tmax[0] < tmax[1]) {
-        if (tmax[0] < tmax[2]) { x[0] += st[0]; tmax[0] += tdelta[0]; } else { x[2] += st[2]; tmax[2] += tdelta[2]; }
-      } else {
-        if (tmax[1] < tmax[2]) { x[1] += st[1]; tmax[1] += tdelta[1]; } else { x[2] += st[2]; tmax[2] += tdelta[2]; }
-      }
+    RayDda dda;
+    dda.set_input(s, e);
+    while (dda.step(ray)) {
       const double tmp[3] = {(ray[0] + 0.5) * res, (ray[1] + 0.5) * res, (ray[2] + 0.5) * res};
       const int v = set_cache(tmp, 0);
       if (v < 0) continue;
@@ -275,6 +289,19 @@ int project_depth(const pop_depth_params& P, bool& has_first, const uint16_t* im
 
 using namespace orc;
 extern "C" {
+// the DDA alone, driven as raycastProcess drives it: every voxel for which step() returned true
+int orc_raycaster(const double* start, const double* end, double* out, int cap, int* set_ok) {
+  RayDda dda;
+  const bool ok = dda.set_input(start, end);
+  if (set_ok) *set_ok = ok ? 1 : 0;
+  double ray[3];
+  int n = 0;
+  while (dda.step(ray)) {
+    if (n < cap) for (int k = 0; k < 3; k++) out[3 * n + k] = ray[k];
+    if (++n > (1 << 22)) break;
+  }
+  return n;
+}
 void* orc_gridmap_create(const pop_gridmap_config* c) { GridMapO* m = new GridMapO(); m->init(*c); return m; }
 void orc_gridmap_destroy(void* h) { delete static_cast<GridMapO*>(h); }
 void orc_gridmap_dims(void* h, int32_t* out) { GridMapO* m = static_cast<GridMapO*>(h); out[0] = m->n[0]; out[1] = m->n[1]; out[2] = m->n[2]; }

@@ -1,0 +1,62 @@
+"""Regenerates tests/golden/ref_pins.npz: outputs of the REFERENCE's own code (oracle/_ref/libref.so =
+plan_env/src/raycast.cpp, traj_utils/sdlp.hpp, sfc_gen/lbfgs.hpp, sfc_gen/firi.hpp compiled unmodified from
+/root/reference; see oracle/Makefile) on the seeded cases of tests/ref_lib.py.  tests/test_ref_pins.py checks the
+oracle against these vectors wherever the library itself is not available.  Needs /root/reference.
+
+    python scripts/make_golden_ref.py
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+N_RAYS, N_LP, N_COST, N_LBFGS, N_MVIE, N_FIRI = 300, 200, 60, 40, 40, 45
+
+
+def main():
+    from tests import ref_lib as rl
+    ref = rl.load()
+    assert ref is not None, "oracle/_ref/libref.so cannot be built here (no /root/reference)"
+    out = {}
+    paths, oks = [], []
+    for s, e in rl.ray_cases(N_RAYS):
+        p, ok = ref.raycaster(s, e)
+        paths.append(p.astype(np.int16))
+        oks.append(ok)
+    out["ray_path"], out["ray_offs"] = rl.pack(paths)
+    out["ray_ok"] = np.array(oks, np.int8)
+    vals, xs = [], []
+    for c, A, b in rl.lp_cases(N_LP):
+        v, x = ref.linprog(c, A, b)
+        vals.append(v)
+        xs.append(np.pad(x, (0, 4 - len(x))))
+    out["lp_val"], out["lp_x"] = np.array(vals), np.array(xs)
+    cg = []
+    for A, x in rl.mvie_cost_cases(N_COST):
+        c, g = ref.cost_mvie(A, x)
+        cg.append(np.r_[c, g])
+    out["cost"] = np.array(cg)
+    lb = []
+    for A, x0 in rl.lbfgs_cases(N_LBFGS):
+        ret, x, f = ref.lbfgs_mvie(A, x0)
+        lb.append(np.r_[ret, f, x])
+    out["lbfgs"] = np.array(lb)
+    mv = []
+    for h in rl.poly_cases(N_MVIE):
+        ok, R, p, r = ref.mvie(h, np.eye(3), np.zeros(3), np.full(3, 0.3))
+        vol, Q, viol = rl.ellipsoid(R, p, r, h)
+        mv.append(np.r_[ok, vol, viol, p, Q.ravel()])
+    out["mvie"] = np.array(mv)
+    for it in (1, 2, 4):
+        hs = [ref.firi(bd, pc, a, b, it, r0)[0] for bd, pc, a, b, r0, lo, hi in rl.firi_cases(N_FIRI)]
+        out[f"firi{it}"], out[f"firi{it}_offs"] = rl.pack(hs)
+    path = os.path.join(ROOT, "tests", "golden", "ref_pins.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, os.path.getsize(path), "bytes")
+
+
+if __name__ == "__main__":
+    main()

@@ -23,7 +23,8 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    srcs = [os.path.join(ORACLE_DIR, f) for f in os.listdir(ORACLE_DIR) if f.endswith((".cpp", ".hpp"))]
+    srcs = [os.path.join(ORACLE_DIR, f) for f in os.listdir(ORACLE_DIR)
+            if f.endswith((".cpp", ".hpp")) and f.startswith(("o_", "oracle"))]   # ref_glue.cpp belongs to _ref/libref.so
     srcs.append(os.path.join(ROOT, "include", "pop.h"))
     if not os.path.exists(LIB) or any(os.path.getmtime(s) > os.path.getmtime(LIB) for s in srcs):
         build()

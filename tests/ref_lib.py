@@ -1,0 +1,270 @@
+"""ctypes binding of oracle/_ref/libref.so — the REFERENCE's own raycast.cpp, sdlp.hpp, lbfgs.hpp and firi.hpp,
+compiled unmodified from /root/reference against a stand-in for the absent Eigen (oracle/ref_build/Eigen/Eigen,
+oracle/ref_glue.cpp, oracle/Makefile).  Test infrastructure: pins the oracle's restatement of those files.
+The library exists only where it was built (this container; it travels to the GPU box as a built file);
+`load()` returns None elsewhere and the tests fall back to the committed vectors in tests/golden/ref_pins.npz,
+which scripts/make_golden_ref.py wrote from this library.  Also holds the seeded case generators that the
+generator script and the tests share."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+LIB = os.path.join(ORACLE_DIR, "_ref", "libref.so")
+REFERENCE = "/root/reference"
+DP = C.POINTER(C.c_double)
+D = C.c_double
+
+
+def P(a):
+    return a.ctypes.data_as(DP)
+
+
+class RefLib:
+    def __init__(self, lib):
+        self.lib = lib
+        lib.ref_linprog.restype = C.c_double
+        lib.ref_cost_mvie.restype = C.c_double
+
+    def raycaster(self, start, end, cap=8192):
+        out = np.zeros((cap, 3))
+        ok = C.c_int(0)
+        n = self.lib.ref_raycaster(P(start), P(end), P(out), cap, C.byref(ok))
+        assert n <= cap
+        return out[:n].copy(), ok.value
+
+    def linprog(self, c, A, b):
+        c = np.ascontiguousarray(c, np.float64)
+        A = np.ascontiguousarray(A, np.float64).reshape(-1, len(c))
+        b = np.ascontiguousarray(b, np.float64)
+        x = np.zeros(len(c))
+        return self.lib.ref_linprog(len(c), P(c), P(A), P(b), len(b), P(x)), x
+
+    def cost_mvie(self, A, x, eps=1e-2, wt=1e3):
+        g = np.zeros(9)
+        return self.lib.ref_cost_mvie(P(A), len(A), D(eps), D(wt), P(x), P(g)), g
+
+    def lbfgs_mvie(self, A, x0, eps=1e-2, wt=1e3):
+        x = x0.copy()
+        f = D(0)
+        ret = self.lib.ref_lbfgs_mvie(P(A), len(A), D(eps), D(wt), P(x), C.byref(f))
+        return ret, x, f.value
+
+    def mvie(self, h, R, p, r):
+        R, p, r = R.copy().ravel(), p.copy(), r.copy()
+        ok = self.lib.ref_mvie(P(h), len(h), P(R), P(p), P(r))
+        return ok, R.reshape(3, 3), p, r
+
+    def firi(self, bd, pc, a, b, iterations, r0=None, cap=256):
+        out = np.zeros((cap, 4))
+        r = np.ones(3) if r0 is None else np.array(r0, np.float64)
+        pc = np.ascontiguousarray(pc, np.float64).reshape(-1, 3)
+        n = self.lib.ref_firi(P(bd), len(bd), P(pc), len(pc), P(a), P(b), int(iterations), P(r), P(out), cap)
+        assert n <= cap
+        return out[:n].copy(), r
+
+
+_ref = False
+
+
+def load():
+    """The reference library, built on demand where /root/reference exists; None where it cannot exist."""
+    global _ref
+    if _ref is not False:
+        return _ref
+    if os.environ.get("POP_NO_REF"):     # exercise the golden-only path where the library does exist
+        _ref = None
+        return _ref
+    if os.path.isdir(REFERENCE):
+        subprocess.run(["make", "-C", ORACLE_DIR, "-s", "_ref/libref.so"], check=True)
+    _ref = RefLib(C.CDLL(LIB)) if os.path.exists(LIB) else None
+    return _ref
+
+
+# oracle-side hooks with the same signatures -----------------------------------------------------------------
+class OrcHooks:
+    def __init__(self, oracle):
+        self.o = oracle
+        self.lib = oracle.lib
+        self.lib.orc_cost_mvie.restype = C.c_double
+
+    def raycaster(self, start, end, cap=8192):
+        out = np.zeros((cap, 3))
+        ok = C.c_int(0)
+        n = self.lib.orc_raycaster(P(start), P(end), P(out), cap, C.byref(ok))
+        assert n <= cap
+        return out[:n].copy(), ok.value
+
+    def linprog(self, c, A, b, seed=1):
+        return self.o.linprog(c, A, b, seed=seed)
+
+    def cost_mvie(self, A, x, eps=1e-2, wt=1e3):
+        g = np.zeros(9)
+        return self.lib.orc_cost_mvie(P(A), len(A), D(eps), D(wt), P(x), P(g)), g
+
+    def lbfgs_mvie(self, A, x0, eps=1e-2, wt=1e3):
+        x = x0.copy()
+        f = D(0)
+        ret = self.lib.orc_lbfgs_mvie(P(A), len(A), D(eps), D(wt), P(x), C.byref(f))
+        return ret, x, f.value
+
+    def mvie(self, h, R, p, r, seed=1):
+        R, p, r = R.copy().ravel(), p.copy(), r.copy()
+        ok = self.lib.orc_mvie(P(h), len(h), P(R), P(p), P(r), C.c_uint64(seed))
+        return ok, R.reshape(3, 3), p, r
+
+    def firi(self, bd, pc, a, b, iterations, r0=None, seed=1, cap=256):
+        out = np.zeros((cap, 4))
+        r = np.ones(3) if r0 is None else np.array(r0, np.float64)
+        pc = np.ascontiguousarray(pc, np.float64).reshape(-1, 3)
+        n = self.lib.orc_firi_r(P(bd), P(pc), len(pc), P(a), P(b), int(iterations), C.c_uint64(seed), P(r), P(out), cap)
+        assert n <= cap
+        return out[:n].copy(), r
+
+
+# seeded cases ----------------------------------------------------------------------------------------------------
+def ray_cases(n, seed=0):
+    """(start, end) in voxel units as raycastProcess passes them: generic, on voxel boundaries, axis-aligned,
+    sub-voxel."""
+    rng = np.random.default_rng(seed)
+    out = []
+    for i in range(n):
+        s = rng.uniform(-60, 60, 3)
+        e = rng.uniform(-60, 60, 3)
+        if i % 5 == 0:
+            s = np.round(s * 2) / 2
+        if i % 7 == 0:
+            e[rng.integers(3)] = s[rng.integers(3)]
+        if i % 11 == 0:
+            e = s.copy()
+            e[rng.integers(3)] += rng.uniform(-0.4, 0.4)
+        if i % 13 == 0:
+            e = np.round(e)
+        out.append((s, e))
+    return out
+
+
+def lp_cases(n, seed=1):
+    """(c, A, b): bounded polytopes around the origin, boxes, duplicated rows, and random (mostly unbounded or
+    infeasible) systems, d = 2..4."""
+    rng = np.random.default_rng(seed)
+    out = []
+    for it in range(n):
+        d = int(rng.integers(2, 5))
+        m = int(rng.integers(d + 1, 60))
+        A = rng.normal(size=(m, d))
+        kind = it % 4
+        if kind in (0, 3):
+            A /= np.linalg.norm(A, axis=1, keepdims=True)
+            b = rng.uniform(0.5, 2, m)
+            A = np.vstack([A, np.eye(d), -np.eye(d)])
+            b = np.concatenate([b, np.full(2 * d, 5.0)])
+            if kind == 3:
+                A = np.vstack([A, A[:3]])
+                b = np.concatenate([b, b[:3]])
+        elif kind == 1:
+            b = rng.normal(size=m)
+        else:
+            A = np.vstack([np.eye(d), -np.eye(d)])
+            b = np.concatenate([rng.uniform(0, 1, d), rng.uniform(0, 1, d)])
+        out.append((rng.normal(size=d), np.ascontiguousarray(A), np.ascontiguousarray(b)))
+    return out
+
+
+def mvie_cost_cases(n, seed=3):
+    rng = np.random.default_rng(seed)
+    out = []
+    for _ in range(n):
+        M = int(rng.integers(4, 40))
+        A = np.ascontiguousarray(rng.normal(size=(M, 3)) * rng.uniform(0.2, 3))
+        x = np.concatenate([rng.normal(size=3) * 0.2, rng.uniform(0.3, 1.5, 3), rng.normal(size=3) * 0.3])
+        out.append((A, x))
+    return out
+
+
+def lbfgs_cases(n, seed=4):
+    """Faces a.x <= 1 around the origin (what maxVolInsEllipsoid hands to L-BFGS) and a start inside."""
+    rng = np.random.default_rng(seed)
+    out = []
+    for _ in range(n):
+        M = int(rng.integers(6, 30))
+        nrm = rng.normal(size=(M, 3))
+        nrm /= np.linalg.norm(nrm, axis=1, keepdims=True)
+        A = np.vstack([nrm / rng.uniform(0.5, 3, (M, 1)), np.eye(3) / 3, -np.eye(3) / 3])
+        x0 = np.array([0, 0, 0, 0.3, 0.3, 0.3, 0, 0, 0.0])
+        x0[:3] += rng.normal(size=3) * 0.02
+        out.append((np.ascontiguousarray(A), x0))
+    return out
+
+
+def poly_cases(n, seed=5):
+    """H-polytopes (rows h0 x + h1 y + h2 z + h3 <= 0): a box around the origin cut by random planes."""
+    rng = np.random.default_rng(seed)
+    out = []
+    for _ in range(n):
+        lo, hi = -rng.uniform(1, 3, 3), rng.uniform(1, 3, 3)
+        rows = []
+        for i in range(3):
+            r = np.zeros(4); r[i] = 1; r[3] = -hi[i]; rows.append(r)
+            r = np.zeros(4); r[i] = -1; r[3] = lo[i]; rows.append(r)
+        for _j in range(int(rng.integers(0, 14))):
+            nv = rng.normal(size=3)
+            nv /= np.linalg.norm(nv)
+            rows.append(np.array([*nv, -rng.uniform(0.4, 2.0)]) * rng.uniform(0.5, 2))
+        out.append(np.ascontiguousarray(np.array(rows)))
+    return out
+
+
+def firi_cases(n, seed=2):
+    """(bd, pc, a, b, r0): a line segment in a box with uniformly scattered obstacle points kept 0.25 m off the
+    segment; r0 = firi's in/out initial radii (unit for two cases in three, anisotropic otherwise)."""
+    rng = np.random.default_rng(seed)
+    out = []
+    for k in range(n):
+        a = rng.uniform(-2, 2, 3)
+        b = a + rng.uniform(-1.5, 1.5, 3)
+        lo = np.minimum(a, b) - rng.uniform(0.5, 2, 3)
+        hi = np.maximum(a, b) + rng.uniform(0.5, 2, 3)
+        bd = np.zeros((6, 4))
+        for i in range(3):
+            bd[2 * i, i] = 1; bd[2 * i, 3] = -hi[i]
+            bd[2 * i + 1, i] = -1; bd[2 * i + 1, 3] = lo[i]
+        pc = rng.uniform(lo, hi, (int(rng.integers(0, 120)), 3))
+        ab = b - a
+        t = np.clip(((pc - a) @ ab) / max(ab @ ab, 1e-12), 0, 1)
+        pc = np.ascontiguousarray(pc[np.linalg.norm(pc - (a + t[:, None] * ab), axis=1) > 0.25])
+        r0 = np.ones(3) if k % 3 else rng.uniform(0.4, 2.5, 3)
+        out.append((bd, pc, a, b, r0, lo, hi))
+    return out
+
+
+def ellipsoid(R, p, r, h):
+    """(volume factor, Q = R diag(r^2) R', worst normalised face violation) of an ellipsoid inside polytope h."""
+    E = R @ np.diag(r)
+    hn = np.linalg.norm(h[:, :3], axis=1)
+    viol = ((np.linalg.norm(h[:, :3] @ E, axis=1) + h[:, :3] @ p + h[:, 3]) / hn).max()
+    return float(np.prod(r)), E @ E.T, float(viol)
+
+
+def poly_iou(h1, h2, lo, hi, n=20000, seed=9):
+    S = np.random.default_rng(seed).uniform(lo, hi, (n, 3))
+    S1 = np.c_[S, np.ones(n)]
+    in1, in2 = (S1 @ h1.T <= 0).all(1), (S1 @ h2.T <= 0).all(1)
+    return (in1 & in2).sum() / max(1, (in1 | in2).sum())
+
+
+# ragged arrays in an .npz ---------------------------------------------------------------------------------------
+def pack(arrs):
+    arrs = [np.asarray(a) for a in arrs]
+    flat = np.concatenate([a.ravel() for a in arrs]) if arrs else np.zeros(0)
+    return flat, np.cumsum([0] + [a.size for a in arrs]).astype(np.int64)
+
+
+def unpack(flat, offs, cols=None):
+    out = [flat[offs[i]:offs[i + 1]] for i in range(len(offs) - 1)]
+    return [a.reshape(-1, cols) for a in out] if cols else out

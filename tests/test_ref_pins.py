@@ -1,0 +1,173 @@
+"""Pins of the oracle against the REFERENCE's own code.
+
+`oracle/_ref/libref.so` is the reference's plan_env/src/raycast.cpp, traj_utils/sdlp.hpp, sfc_gen/lbfgs.hpp and
+sfc_gen/firi.hpp compiled unmodified (oracle/Makefile; Eigen replaced by the stand-in oracle/ref_build/Eigen/Eigen).
+Every test runs the oracle's restatement on seeded cases and compares it with
+
+  * the committed outputs of that library (tests/golden/ref_pins.npz, scripts/make_golden_ref.py) — always;
+  * the library itself on a larger sweep — where it exists (this container, and the GPU box it travels to).
+
+What is exact and what is not: the DDA is integer stepping on scalar doubles — identical voxel sequences.  costMVIE,
+the Lewis-Overton line search and the L-BFGS loop are deterministic given their inputs — identical to the last bit
+(status, cost, all nine variables).  The LP shuffles its constraints (the reference with a function-static
+mt19937_64, the oracle with a caller-owned LCG), so optima agree to 1e-7, not bitwise.  maxVolInsEllipsoid starts
+L-BFGS from the LP's interior point and stops it on a 1e-7 relative cost decrease, so two correct runs agree in
+volume to ~1e-3 and differ more along flat directions; firi's first polytope (before any ellipsoid) is identical,
+later ones are compared as sets (both valid corridors, intersection-over-union)."""
+import os
+
+import numpy as np
+import pytest
+
+from tests import ref_lib as rl
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden", "ref_pins.npz")
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return np.load(GOLD)
+
+
+@pytest.fixture(scope="module")
+def orc(oracle):
+    return rl.OrcHooks(oracle)
+
+
+@pytest.fixture(scope="module")
+def ref():
+    return rl.load()
+
+
+def test_golden_file_is_current(ref, gold):
+    """Where the reference library can be built, the committed vectors are what it produces today."""
+    if ref is None:
+        pytest.skip("oracle/_ref/libref.so not present (no /root/reference here)")
+    paths = rl.unpack(gold["ray_path"], gold["ray_offs"], 3)
+    for (s, e), want in zip(rl.ray_cases(40), paths):
+        assert np.array_equal(ref.raycaster(s, e)[0], want)
+    for (A, x0), want in zip(rl.lbfgs_cases(10), gold["lbfgs"]):
+        ret, x, f = ref.lbfgs_mvie(A, x0)
+        assert ret == want[0] and f == want[1] and np.array_equal(x, want[2:])
+
+
+# ---- RayCaster (plan_env/src/raycast.cpp:242-335) -----------------------------------------------------------------
+def test_raycaster_voxel_sequences_identical(orc, ref, gold):
+    cases = rl.ray_cases(len(gold["ray_ok"]))
+    paths = rl.unpack(gold["ray_path"], gold["ray_offs"], 3)
+    total = 0
+    for (s, e), want, ok in zip(cases, paths, gold["ray_ok"]):
+        got, gok = orc.raycaster(s, e)
+        assert gok == ok and np.array_equal(got, want)
+        total += len(got)
+    assert total > 20000
+    if ref is not None:
+        for s, e in rl.ray_cases(5000, seed=17):
+            a, b = ref.raycaster(s, e), orc.raycaster(s, e)
+            assert a[1] == b[1] and np.array_equal(a[0], b[0])
+
+
+# ---- sdlp::linprog (traj_utils/sdlp.hpp:708-785) ------------------------------------------------------------------
+def _lp_check(v_ref, x_ref, v, x, A, b):
+    unb_ref = not np.isfinite(v_ref) or abs(v_ref) > 1e12
+    unb = not np.isfinite(v) or abs(v) > 1e12
+    assert unb_ref == unb
+    if unb:
+        if np.isposinf(v_ref) or np.isposinf(v):      # infeasible is +inf on both sides
+            assert v_ref == v
+        return 0
+    assert abs(v - v_ref) <= 1e-9 * max(1.0, abs(v_ref))
+    assert np.abs(x - x_ref).max() <= 1e-7
+    assert (A @ x - b).max() <= 1e-9
+    return 1
+
+
+def test_linprog_matches_reference(orc, ref, gold):
+    finite = 0
+    for i, (c, A, b) in enumerate(rl.lp_cases(len(gold["lp_val"]))):
+        v, x = orc.linprog(c, A, b, seed=i + 1)
+        finite += _lp_check(gold["lp_val"][i], gold["lp_x"][i][:len(c)], v, x, A, b)
+    assert finite > 100
+    if ref is not None:
+        for i, (c, A, b) in enumerate(rl.lp_cases(1500, seed=23)):
+            vr, xr = ref.linprog(c, A, b)
+            v, x = orc.linprog(c, A, b, seed=i + 7)
+            _lp_check(vr, xr, v, x, A, b)
+
+
+# ---- firi::costMVIE, lbfgs::lbfgs_optimize (firi.hpp:74-137, lbfgs.hpp:276-720) -------------------------------------
+def test_mvie_cost_and_gradient_bit_identical(orc, ref, gold):
+    for (A, x), want in zip(rl.mvie_cost_cases(len(gold["cost"])), gold["cost"]):
+        c, g = orc.cost_mvie(A, x)
+        assert c == want[0] and np.array_equal(g, want[1:])
+    if ref is not None:
+        for A, x in rl.mvie_cost_cases(1000, seed=31):
+            cr, gr = ref.cost_mvie(A, x)
+            c, g = orc.cost_mvie(A, x)
+            assert c == cr and np.array_equal(g, gr)
+
+
+def test_lbfgs_runs_bit_identical(orc, ref, gold):
+    """Same data, same start: the whole optimisation (every line search, every two-loop update, the stop test) lands on
+    the same nine doubles, the same cost and the same status."""
+    for (A, x0), want in zip(rl.lbfgs_cases(len(gold["lbfgs"])), gold["lbfgs"]):
+        ret, x, f = orc.lbfgs_mvie(A, x0)
+        assert ret == want[0] and f == want[1] and np.array_equal(x, want[2:])
+    if ref is not None:
+        for A, x0 in rl.lbfgs_cases(300, seed=37):
+            a, b = ref.lbfgs_mvie(A, x0), orc.lbfgs_mvie(A, x0)
+            assert a[0] == b[0] and a[2] == b[2] and np.array_equal(a[1], b[1])
+
+
+# ---- firi::maxVolInsEllipsoid (firi.hpp:143-214) ------------------------------------------------------------------
+def test_mvie_same_optimum(orc, ref, gold):
+    rel = []
+    for k, (h, want) in enumerate(zip(rl.poly_cases(len(gold["mvie"])), gold["mvie"])):
+        ok, R, p, r = orc.mvie(h, np.eye(3), np.zeros(3), np.full(3, 0.3), seed=k + 1)
+        vol, Q, viol = rl.ellipsoid(R, p, r, h)
+        assert ok == want[0] == 1
+        assert abs(np.linalg.det(R) - 1.0) < 1e-12                 # a proper rotation, as the reference enforces
+        assert viol < 2e-3 and want[2] < 2e-3                       # inscribed up to the penalty's softness
+        rel.append(abs(vol - want[1]) / want[1])
+        assert np.abs(p - want[3:6]).max() < 5e-2
+        assert np.abs(Q - want[6:].reshape(3, 3)).max() <= 5e-2 * np.abs(Q).max()
+    assert max(rel) < 2e-3 and np.median(rel) < 2e-5
+
+
+# ---- firi::firi (firi.hpp:216-365) --------------------------------------------------------------------------------
+def test_firi_first_polytope_identical(orc, ref, gold):
+    """One iteration = the polytope construction alone (tangent planes, boundary/obstacle ordering, back-transform),
+    from the caller's radii: identical rows in identical order."""
+    cases = rl.firi_cases(len(gold["firi1_offs"]) - 1)
+    for k, ((bd, pc, a, b, r0, lo, hi), want) in enumerate(zip(cases, rl.unpack(gold["firi1"], gold["firi1_offs"], 4))):
+        got, _ = orc.firi(bd, pc, a, b, 1, r0, seed=k + 1)
+        assert got.shape == want.shape and np.array_equal(got, want)
+    if ref is not None:
+        for k, (bd, pc, a, b, r0, lo, hi) in enumerate(rl.firi_cases(200, seed=41)):
+            assert np.array_equal(orc.firi(bd, pc, a, b, 1, r0, seed=k + 1)[0], ref.firi(bd, pc, a, b, 1, r0)[0])
+
+
+@pytest.mark.parametrize("iterations", [2, 4])
+def test_firi_iterated_same_corridor(orc, gold, iterations):
+    cases = rl.firi_cases(len(gold["firi1_offs"]) - 1)
+    wants = rl.unpack(gold[f"firi{iterations}"], gold[f"firi{iterations}_offs"], 4)
+    ious = []
+    for k, ((bd, pc, a, b, r0, lo, hi), want) in enumerate(zip(cases, wants)):
+        got, _ = orc.firi(bd, pc, a, b, iterations, r0, seed=k + 1)
+        for h in (got, want):                                       # both are valid corridors of the same problem
+            assert (h @ np.r_[a, 1] <= 1e-9).all() and (h @ np.r_[b, 1] <= 1e-9).all()
+            if len(pc):
+                assert ((np.c_[pc, np.ones(len(pc))] @ h.T).max(1) > -1e-5).all()
+        assert abs(len(got) - len(want)) <= 3
+        ious.append(rl.poly_iou(got, want, lo, hi))
+    assert np.median(ious) > 0.999 and min(ious) > 0.85
+
+
+def test_firi_refuses_like_reference(orc, ref):
+    """a or b outside the boundary polytope: firi returns false (firi.hpp:227-229)."""
+    bd, pc, a, b, r0, lo, hi = rl.firi_cases(1)[0]
+    out = a.copy()
+    out[0] = hi[0] + 0.5
+    assert len(orc.firi(bd, pc, out, b, 2)[0]) == 0
+    if ref is not None:
+        assert len(ref.firi(bd, pc, out, b, 2)[0]) == 0

@@ -1,6 +1,6 @@
 // ref_glue.cpp — C entry points into the REFERENCE's own code (TEST INFRASTRUCTURE; builds oracle/_ref/libref.so).
 //
-// Compiled together with /root/reference/plan_env/src/raycast.cpp and the reference headers
+// Compiled together with /root/reference/plan_env/src/raycast.cpp, traj_utils/src/bernstein.cpp and the reference headers
 // plan_manager/include/sfc_gen/{firi,lbfgs}.hpp and traj_utils/include/traj_utils/sdlp.hpp — unmodified, from where
 // they lie — against oracle/ref_build/Eigen/Eigen (a stand-in for the absent Eigen; see that file for what it does
 // and does not reproduce).  Nothing here restates reference arithmetic: each function only marshals flat arrays
@@ -12,6 +12,7 @@
 
 #include <plan_env/raycast.h>
 #include "sfc_gen/firi.hpp"
+#include "traj_utils/bernstein.hpp"
 
 // sdlp::linprog<d>: min c.x s.t. A x <= b, A row-major m x d (sdlp.hpp:708-785)
 template <int d>
@@ -115,6 +116,24 @@ int ref_lbfgs_mvie(const double* A, int M, double smooth_eps, double penalty_wt,
   for (int k = 0; k < 9; k++) x[k] = xv(k);
   *fx = f;
   return ret;
+}
+
+// Bernstein::Bezier (traj_utils/src/bernstein.cpp): dur[M], cpts[5M x 3] row-major; deriv 0/1/2 = getPos/getVel/getAcc
+void ref_bezier_eval(const double* dur, int M, const double* cpts, const double* t, int n, int deriv, double* out) {
+  Eigen::MatrixX3d c(5 * M, 3);
+  for (int i = 0; i < 5 * M; i++) for (int k = 0; k < 3; k++) c(i, k) = cpts[3 * i + k];
+  Bernstein::Bezier b(std::vector<double>(dur, dur + M), c);
+  for (int i = 0; i < n; i++) {
+    const Eigen::Vector3d p = deriv == 0 ? b.getPos(t[i]) : deriv == 1 ? b.getVel(t[i]) : b.getAcc(t[i]);
+    for (int k = 0; k < 3; k++) out[3 * i + k] = p(k);
+  }
+}
+// getMaxVelRate (order 1) / getMaxAccRate (order 2)
+double ref_bezier_max_rate(const double* dur, int M, const double* cpts, int order) {
+  Eigen::MatrixX3d c(5 * M, 3);
+  for (int i = 0; i < 5 * M; i++) for (int k = 0; k < 3; k++) c(i, k) = cpts[3 * i + k];
+  Bernstein::Bezier b(std::vector<double>(dur, dur + M), c);
+  return order == 1 ? b.getMaxVelRate() : b.getMaxAccRate();
 }
 
 }  // extern "C"

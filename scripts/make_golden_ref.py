@@ -1,5 +1,5 @@
 """Regenerates tests/golden/ref_pins.npz: outputs of the REFERENCE's own code (oracle/_ref/libref.so =
-plan_env/src/raycast.cpp, traj_utils/sdlp.hpp, sfc_gen/lbfgs.hpp, sfc_gen/firi.hpp compiled unmodified from
+plan_env/src/raycast.cpp, traj_utils/sdlp.hpp, sfc_gen/lbfgs.hpp, sfc_gen/firi.hpp, traj_utils/src/bernstein.cpp compiled unmodified from
 /root/reference; see oracle/Makefile) on the seeded cases of tests/ref_lib.py.  tests/test_ref_pins.py checks the
 oracle against these vectors wherever the library itself is not available.  Needs /root/reference.
 
@@ -13,7 +13,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-N_RAYS, N_LP, N_COST, N_LBFGS, N_MVIE, N_FIRI = 300, 200, 60, 40, 40, 45
+N_RAYS, N_LP, N_COST, N_LBFGS, N_MVIE, N_FIRI, N_BEZ = 300, 200, 60, 40, 40, 45, 40
 
 
 def main():
@@ -53,6 +53,12 @@ def main():
     for it in (1, 2, 4):
         hs = [ref.firi(bd, pc, a, b, it, r0)[0] for bd, pc, a, b, r0, lo, hi in rl.firi_cases(N_FIRI)]
         out[f"firi{it}"], out[f"firi{it}_offs"] = rl.pack(hs)
+    bz, rates = [], []
+    for dur, cp, t in rl.bezier_cases(N_BEZ):
+        bz.append(np.stack([ref.bezier_eval(dur, cp, t, d) for d in (0, 1, 2)]))
+        rates.append([ref.bezier_max_rate(dur, cp, 1), ref.bezier_max_rate(dur, cp, 2)])
+    out["bezier"], out["bezier_offs"] = rl.pack(bz)
+    out["bezier_rates"] = np.array(rates)
     path = os.path.join(ROOT, "tests", "golden", "ref_pins.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path), "bytes")

@@ -30,6 +30,7 @@ class RefLib:
         self.lib = lib
         lib.ref_linprog.restype = C.c_double
         lib.ref_cost_mvie.restype = C.c_double
+        lib.ref_bezier_max_rate.restype = C.c_double
 
     def raycaster(self, start, end, cap=8192):
         out = np.zeros((cap, 3))
@@ -67,6 +68,15 @@ class RefLib:
         n = self.lib.ref_firi(P(bd), len(bd), P(pc), len(pc), P(a), P(b), int(iterations), P(r), P(out), cap)
         assert n <= cap
         return out[:n].copy(), r
+
+
+    def bezier_eval(self, dur, cpts, t, deriv=0):
+        out = np.zeros((len(t), 3))
+        self.lib.ref_bezier_eval(P(dur), len(dur), P(cpts), P(t), len(t), int(deriv), P(out))
+        return out
+
+    def bezier_max_rate(self, dur, cpts, order):
+        return self.lib.ref_bezier_max_rate(P(dur), len(dur), P(cpts), int(order))
 
 
 _ref = False
@@ -240,6 +250,20 @@ def firi_cases(n, seed=2):
         pc = np.ascontiguousarray(pc[np.linalg.norm(pc - (a + t[:, None] * ab), axis=1) > 0.25])
         r0 = np.ones(3) if k % 3 else rng.uniform(0.4, 2.5, 3)
         out.append((bd, pc, a, b, r0, lo, hi))
+    return out
+
+
+def bezier_cases(n, seed=6):
+    """(durations, control points 5M x 3, sample times incl. 0, the piece joints, the end and past the end)."""
+    rng = np.random.default_rng(seed)
+    out = []
+    for _ in range(n):
+        M = int(rng.integers(1, 9))
+        dur = rng.uniform(0.2, 2.5, M)
+        cp = np.ascontiguousarray(rng.normal(size=(5 * M, 3)) * 3)
+        T = dur.sum()
+        t = np.concatenate([rng.uniform(0, T, 20), [0.0, T, T + 0.3], np.cumsum(dur)])
+        out.append((dur, cp, t))
     return out
 
 

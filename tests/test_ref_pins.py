@@ -1,7 +1,7 @@
 """Pins of the oracle against the REFERENCE's own code.
 
-`oracle/_ref/libref.so` is the reference's plan_env/src/raycast.cpp, traj_utils/sdlp.hpp, sfc_gen/lbfgs.hpp and
-sfc_gen/firi.hpp compiled unmodified (oracle/Makefile; Eigen replaced by the stand-in oracle/ref_build/Eigen/Eigen).
+`oracle/_ref/libref.so` is the reference's plan_env/src/raycast.cpp, traj_utils/sdlp.hpp, sfc_gen/lbfgs.hpp,
+sfc_gen/firi.hpp and traj_utils/src/bernstein.cpp compiled unmodified (oracle/Makefile; Eigen replaced by the stand-in oracle/ref_build/Eigen/Eigen).
 Every test runs the oracle's restatement on seeded cases and compares it with
 
   * the committed outputs of that library (tests/golden/ref_pins.npz, scripts/make_golden_ref.py) — always;
@@ -13,7 +13,9 @@ the Lewis-Overton line search and the L-BFGS loop are deterministic given their 
 mt19937_64, the oracle with a caller-owned LCG), so optima agree to 1e-7, not bitwise.  maxVolInsEllipsoid starts
 L-BFGS from the LP's interior point and stops it on a 1e-7 relative cost decrease, so two correct runs agree in
 volume to ~1e-3 and differ more along flat directions; firi's first polytope (before any ellipsoid) is identical,
-later ones are compared as sets (both valid corridors, intersection-over-union)."""
+later ones are compared as sets (both valid corridors, intersection-over-union).  Bezier evaluation is three small
+matrix products whose summation order the oracle fixes one way and the stand-in another: 1e-14 relative (99 % of the
+samples are identical)."""
 import os
 
 import numpy as np
@@ -171,3 +173,25 @@ def test_firi_refuses_like_reference(orc, ref):
     assert len(orc.firi(bd, pc, out, b, 2)[0]) == 0
     if ref is not None:
         assert len(ref.firi(bd, pc, out, b, 2)[0]) == 0
+
+
+# ---- Bernstein::Bezier (traj_utils/src/bernstein.cpp) ---------------------------------------------------------------
+def test_bezier_evaluation_matches_reference(oracle, ref, gold):
+    cases = rl.bezier_cases(len(gold["bezier_rates"]))
+    wants = rl.unpack(gold["bezier"], gold["bezier_offs"])
+    same = total = 0
+    for (dur, cp, t), want, rates in zip(cases, wants, gold["bezier_rates"]):
+        want = want.reshape(3, len(t), 3)
+        for d in (0, 1, 2):
+            got = oracle.bezier_eval(dur, cp, t, deriv=d)
+            assert np.abs(got - want[d]).max() <= 1e-14 * max(1.0, np.abs(want[d]).max())
+            same += int(np.array_equal(got, want[d]))
+            total += 1
+        for o in (1, 2):
+            assert abs(oracle.bezier_max_rate(dur, cp, o) - rates[o - 1]) <= 1e-14 * max(1.0, rates[o - 1])
+    assert same >= 0.9 * total
+    if ref is not None:
+        for dur, cp, t in rl.bezier_cases(300, seed=43):
+            for d in (0, 1, 2):
+                a, b = ref.bezier_eval(dur, cp, t, d), oracle.bezier_eval(dur, cp, t, deriv=d)
+                assert np.abs(a - b).max() <= 1e-14 * max(1.0, np.abs(a).max())

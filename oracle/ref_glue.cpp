@@ -1,6 +1,7 @@
 // ref_glue.cpp — C entry points into the REFERENCE's own code (TEST INFRASTRUCTURE; builds oracle/_ref/libref.so).
 //
-// Compiled together with /root/reference/plan_env/src/raycast.cpp, traj_utils/src/bernstein.cpp and the reference headers
+// Compiled together with /root/reference/plan_env/src/raycast.cpp, traj_utils/src/bernstein.cpp,
+// traj_opt/src/bezier_optimizer.cpp and the reference headers
 // plan_manager/include/sfc_gen/{firi,lbfgs}.hpp and traj_utils/include/traj_utils/sdlp.hpp — unmodified, from where
 // they lie — against oracle/ref_build/Eigen/Eigen (a stand-in for the absent Eigen; see that file for what it does
 // and does not reproduce).  Nothing here restates reference arithmetic: each function only marshals flat arrays
@@ -13,6 +14,10 @@
 #include <plan_env/raycast.h>
 #include "sfc_gen/firi.hpp"
 #include "traj_utils/bernstein.hpp"
+#include "bernstein/bezier_optimizer.hpp"   // finds oracle/ref_build/iosqp.hpp (a recorder, not a solver) before the reference's
+
+#include <iostream>
+#include <sstream>
 
 // sdlp::linprog<d>: min c.x s.t. A x <= b, A row-major m x d (sdlp.hpp:708-785)
 template <int d>
@@ -134,6 +139,34 @@ double ref_bezier_max_rate(const double* dur, int M, const double* cpts, int ord
   for (int i = 0; i < 5 * M; i++) for (int k = 0; k < 3; k++) c(i, k) = cpts[3 * i + k];
   Bernstein::Bezier b(std::vector<double>(dur, dur + M), c);
   return order == 1 ? b.getMaxVelRate() : b.getMaxAccRate();
+}
+
+// traj_opt::BezierOpt::setup (bezier_optimizer.cpp:26-285): init9 / goal9 = [pos; vel; acc] row-major 3 x 3, dur[M],
+// hpoly = M blocks of max_rows x 4 with rows[i] valid rows each.  Writes Q (n x n), A (m x n), lb, ub row-major when
+// non-null (n = 15 M) and returns m.  The reference prints its row counts to stdout; that is swallowed here.
+int ref_qp_setup(int M, const double* init9, const double* goal9, const double* dur, const double* hpoly, int max_rows,
+                 const int32_t* rows, double vmax, double amax, double* outQ, double* outA, double* outl, double* outu) {
+  Eigen::Matrix3d s, e;
+  for (int i = 0; i < 3; i++) for (int k = 0; k < 3; k++) { s(i, k) = init9[3 * i + k]; e(i, k) = goal9[3 * i + k]; }
+  std::vector<traj_opt::PolyhedronH> cs;
+  for (int i = 0; i < M; i++) {
+    traj_opt::PolyhedronH h(rows[i], 4);
+    for (int j = 0; j < rows[i]; j++) for (int k = 0; k < 4; k++) h(j, k) = hpoly[(static_cast<size_t>(i) * max_rows + j) * 4 + k];
+    cs.push_back(h);
+  }
+  std::ostringstream sink;
+  std::streambuf* old = std::cout.rdbuf(sink.rdbuf());
+  traj_opt::BezierOpt opt;
+  opt.setup(s, e, std::vector<double>(dur, dur + M), cs, vmax, amax);
+  std::cout.rdbuf(old);
+  const Eigen::MatrixXd Q = opt.getQ(), A = opt.getA(), lb = opt.getlb();
+  const Eigen::VectorXd ub = opt.getb();
+  const int n = Q.rows(), m = A.rows();
+  if (outQ) for (int i = 0; i < n; i++) for (int j = 0; j < n; j++) outQ[static_cast<size_t>(i) * n + j] = Q(i, j);
+  if (outA) for (int i = 0; i < m; i++) for (int j = 0; j < n; j++) outA[static_cast<size_t>(i) * n + j] = A(i, j);
+  if (outl) for (int i = 0; i < m; i++) outl[i] = lb(i);
+  if (outu) for (int i = 0; i < m; i++) outu[i] = ub(i);
+  return m;
 }
 
 }  // extern "C"

@@ -1,5 +1,5 @@
 """Regenerates tests/golden/ref_pins.npz: outputs of the REFERENCE's own code (oracle/_ref/libref.so =
-plan_env/src/raycast.cpp, traj_utils/sdlp.hpp, sfc_gen/lbfgs.hpp, sfc_gen/firi.hpp, traj_utils/src/bernstein.cpp compiled unmodified from
+plan_env/src/raycast.cpp, traj_utils/sdlp.hpp, sfc_gen/lbfgs.hpp, sfc_gen/firi.hpp, traj_utils/src/bernstein.cpp, traj_opt/src/bezier_optimizer.cpp compiled unmodified from
 /root/reference; see oracle/Makefile) on the seeded cases of tests/ref_lib.py.  tests/test_ref_pins.py checks the
 oracle against these vectors wherever the library itself is not available.  Needs /root/reference.
 
@@ -13,7 +13,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-N_RAYS, N_LP, N_COST, N_LBFGS, N_MVIE, N_FIRI, N_BEZ = 300, 200, 60, 40, 40, 45, 40
+N_RAYS, N_LP, N_COST, N_LBFGS, N_MVIE, N_FIRI, N_BEZ, N_QP = 300, 200, 60, 40, 40, 45, 40, 12
 
 
 def main():
@@ -59,6 +59,10 @@ def main():
         rates.append([ref.bezier_max_rate(dur, cp, 1), ref.bezier_max_rate(dur, cp, 2)])
     out["bezier"], out["bezier_offs"] = rl.pack(bz)
     out["bezier_rates"] = np.array(rates)
+    qps = []
+    for init, goal, dur, polys, vmax, amax in rl.qp_cases(N_QP, max_pieces=4):
+        qps.append(np.concatenate([a.ravel() for a in ref.qp_setup(init, goal, dur, polys, vmax, amax)]))
+    out["qp"], out["qp_offs"] = rl.pack(qps)
     path = os.path.join(ROOT, "tests", "golden", "ref_pins.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path), "bytes")

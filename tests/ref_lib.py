@@ -78,6 +78,23 @@ class RefLib:
     def bezier_max_rate(self, dur, cpts, order):
         return self.lib.ref_bezier_max_rate(P(dur), len(dur), P(cpts), int(order))
 
+    def qp_setup(self, init, goal, dur, polys, vmax, amax):
+        """BezierOpt::setup -> (Q, A, lb, ub) as the reference assembles them."""
+        M = len(dur)
+        rows = np.array([len(h) for h in polys], np.int32)
+        cap = int(rows.max())
+        hp = np.zeros((M, cap, 4))
+        for i, h in enumerate(polys):
+            hp[i, :len(h)] = h
+        i9, g9 = np.ascontiguousarray(init, np.float64).reshape(9), np.ascontiguousarray(goal, np.float64).reshape(9)
+        dur = np.ascontiguousarray(dur, np.float64)
+        args = (M, P(i9), P(g9), P(dur), P(hp), cap, rows.ctypes.data_as(C.POINTER(C.c_int32)), D(vmax), D(amax))
+        m = self.lib.ref_qp_setup(*args, None, None, None, None)
+        n = 15 * M
+        Q, A, l, u = np.zeros((n, n)), np.zeros((m, n)), np.zeros(m), np.zeros(m)
+        self.lib.ref_qp_setup(*args, P(Q), P(A), P(l), P(u))
+        return Q, A, l, u
+
 
 _ref = False
 
@@ -264,6 +281,18 @@ def bezier_cases(n, seed=6):
         T = dur.sum()
         t = np.concatenate([rng.uniform(0, T, 20), [0.0, T, T + 0.3], np.cumsum(dur)])
         out.append((dur, cp, t))
+    return out
+
+
+def qp_cases(n, seed=7, max_pieces=8):
+    """(init, goal [pos; vel; acc], durations, one H-polytope per piece, vmax, amax)."""
+    rng = np.random.default_rng(seed)
+    out = []
+    for _ in range(n):
+        M = int(rng.integers(1, max_pieces + 1))
+        polys = [np.c_[rng.normal(size=(r, 3)), -rng.uniform(0.5, 3, r)] for r in rng.integers(4, 20, M)]
+        out.append((rng.normal(size=(3, 3)), rng.normal(size=(3, 3)), rng.uniform(0.3, 2.5, M), polys,
+                    float(rng.uniform(1, 4)), float(rng.uniform(1, 5))))
     return out
 
 

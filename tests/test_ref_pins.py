@@ -1,7 +1,8 @@
 """Pins of the oracle against the REFERENCE's own code.
 
 `oracle/_ref/libref.so` is the reference's plan_env/src/raycast.cpp, traj_utils/sdlp.hpp, sfc_gen/lbfgs.hpp,
-sfc_gen/firi.hpp and traj_utils/src/bernstein.cpp compiled unmodified (oracle/Makefile; Eigen replaced by the stand-in oracle/ref_build/Eigen/Eigen).
+sfc_gen/firi.hpp, traj_utils/src/bernstein.cpp and traj_opt/src/bezier_optimizer.cpp compiled unmodified
+(oracle/Makefile; Eigen replaced by the stand-in oracle/ref_build/Eigen/Eigen, the OSQP wrapper by a recorder).
 Every test runs the oracle's restatement on seeded cases and compares it with
 
   * the committed outputs of that library (tests/golden/ref_pins.npz, scripts/make_golden_ref.py) — always;
@@ -15,7 +16,9 @@ L-BFGS from the LP's interior point and stops it on a 1e-7 relative cost decreas
 volume to ~1e-3 and differ more along flat directions; firi's first polytope (before any ellipsoid) is identical,
 later ones are compared as sets (both valid corridors, intersection-over-union).  Bezier evaluation is three small
 matrix products whose summation order the oracle fixes one way and the stand-in another: 1e-14 relative (99 % of the
-samples are identical)."""
+samples are identical).  BezierOpt::setup only places and scales constants: Q, A, lb, ub identical.  The OSQP solver
+itself is third-party and absent; its restatement in oracle/o_qp.cpp is NOT pinned here (tests/test_golden_reference.py
+holds the reference's own QP fixture)."""
 import os
 
 import numpy as np
@@ -195,3 +198,17 @@ def test_bezier_evaluation_matches_reference(oracle, ref, gold):
             for d in (0, 1, 2):
                 a, b = ref.bezier_eval(dur, cp, t, d), oracle.bezier_eval(dur, cp, t, deriv=d)
                 assert np.abs(a - b).max() <= 1e-14 * max(1.0, np.abs(a).max())
+
+
+# ---- traj_opt::BezierOpt::setup (traj_opt/src/bezier_optimizer.cpp:26-250) -----------------------------------------
+def test_qp_assembly_identical(oracle, ref, gold):
+    """Min-jerk cost, continuity / dynamical / corridor rows and both bound vectors exactly as the reference builds them
+    (same row order, same scaling by the piece durations, -OSQP_INFTY = -1e30 on the one-sided rows)."""
+    wants = rl.unpack(gold["qp"], gold["qp_offs"])
+    for (init, goal, dur, polys, vmax, amax), want in zip(rl.qp_cases(len(wants), max_pieces=4), wants):
+        got = oracle.qp_setup(init, goal, dur, polys, vmax=vmax, amax=amax)
+        assert np.array_equal(np.concatenate([a.ravel() for a in got]), want)
+    if ref is not None:
+        for init, goal, dur, polys, vmax, amax in rl.qp_cases(60, seed=47):
+            got, want = oracle.qp_setup(init, goal, dur, polys, vmax=vmax, amax=amax), ref.qp_setup(init, goal, dur, polys, vmax, amax)
+            assert all(np.array_equal(a, b) for a, b in zip(got, want))

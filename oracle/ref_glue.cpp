@@ -1,7 +1,7 @@
 // ref_glue.cpp — C entry points into the REFERENCE's own code (TEST INFRASTRUCTURE; builds oracle/_ref/libref.so).
 //
 // Compiled together with /root/reference/plan_env/src/raycast.cpp, traj_utils/src/bernstein.cpp,
-// traj_opt/src/bezier_optimizer.cpp and the reference headers
+// traj_opt/src/bezier_optimizer.cpp, path_searching/src/fake_risk_hybrid_a_star.cpp and the reference headers
 // plan_manager/include/sfc_gen/{firi,lbfgs}.hpp and traj_utils/include/traj_utils/sdlp.hpp — unmodified, from where
 // they lie — against oracle/ref_build/Eigen/Eigen (a stand-in for the absent Eigen; see that file for what it does
 // and does not reproduce).  Nothing here restates reference arithmetic: each function only marshals flat arrays
@@ -18,6 +18,28 @@
 
 #include <iostream>
 #include <sstream>
+
+// the hybrid A*: its private counters (use_node_num_, iter_num_) are read back below
+#define private public
+#define protected public
+#include <path_searching/fake_risk_hybrid_a_star.h>
+#undef private
+#undef protected
+
+// path_searching/src/dyn_a_star.cpp (the base class's own grid A*, not on the path, needs the real GridMap) is not
+// compiled; its out-of-line members are stubbed so that the vtable links
+AStar::~AStar() {}
+void AStar::reset() {}
+void AStar::init() {}
+void AStar::init(const Eigen::Vector3d&, const Eigen::Vector3i&) {}
+void AStar::setParam(ros::NodeHandle&) {}
+void AStar::setEnvironment(const GridMap::Ptr&) {}
+void AStar::initEnvironment(GridMap::Ptr, const Eigen::Vector3i) {}
+double AStar::getDiagHeu(GridNodePtr, GridNodePtr) { return 0.0; }
+double AStar::getManhHeu(GridNodePtr, GridNodePtr) { return 0.0; }
+double AStar::getEuclHeu(GridNodePtr, GridNodePtr) { return 0.0; }
+ASTAR_RET AStar::search(Eigen::Vector3d, Eigen::Vector3d) { return NO_PATH; }
+std::vector<Eigen::Vector3d> AStar::getPath() { return {}; }
 
 // sdlp::linprog<d>: min c.x s.t. A x <= b, A row-major m x d (sdlp.hpp:708-785)
 template <int d>
@@ -167,6 +189,49 @@ int ref_qp_setup(int M, const double* init9, const double* goal9, const double* 
   if (outl) for (int i = 0; i < m; i++) outl[i] = lb(i);
   if (outu) for (int i = 0; i < m; i++) outu[i] = ub(i);
   return m;
+}
+
+// FakeRiskHybridAstar driven as FakeBaselinePlanner::replan drives it (baseline_fake.cpp:280-305): reset, search with
+// init = true, once more with init = false on NO_PATH, then getPathWithVel(corridor_tau).  prm = max_tau, init_max_tau,
+// max_vel, max_acc, w_time, horizon, resolution_astar, time_resolution, lambda_heu, allocate_num, check_num, tolerance,
+// corridor_tau (search/... of fake_risk_hybrid_a_star.cpp:62-82).  start9 = pos, vel, acc.  out_path n x 6;
+// stats = iterations, nodes used, retried, occupancy queries.  Returns ASTAR_RET.
+int ref_astar(const double* prm, FakeParticleRiskVoxel::query_dt_fn query, void* map, const float* pose3,
+              const double* start9, const double* goal3, double t_start, double* out_path, int cap, int* out_n, int* stats) {
+  ros::NodeHandle nh;
+  const char* names[] = {"search/max_tau", "search/init_max_tau", "search/max_vel", "search/max_acc", "search/w_time",
+                         "search/horizon", "search/resolution_astar", "search/time_resolution", "search/lambda_heu",
+                         "search/allocate_num", "search/check_num", "search/tolerance"};
+  for (int i = 0; i < 12; i++) nh.values[names[i]] = prm[i];
+  FakeParticleRiskVoxel::Ptr m(new FakeParticleRiskVoxel());
+  m->query = query; m->map = map;
+  m->pose = Eigen::Vector3f(pose3[0], pose3[1], pose3[2]);
+  std::ostringstream sink;
+  std::streambuf* old = std::cout.rdbuf(sink.rdbuf());
+  FakeRiskHybridAstar a;
+  a.setParam(nh);
+  a.setEnvironment(m);
+  a.init(Eigen::Vector3d::Zero(), Eigen::Vector3d(10, 10, 4));          // baseline_fake.cpp:28
+  const Eigen::Vector3d sp(start9[0], start9[1], start9[2]), sv(start9[3], start9[4], start9[5]),
+      sa(start9[6], start9[7], start9[8]), gp(goal3[0], goal3[1], goal3[2]);
+  a.reset();
+  int retried = 0;
+  ASTAR_RET rst = a.search(sp, sv, sa, gp, Eigen::Vector3d(0, 0, 0), true, true, t_start);
+  if (rst == 0) {
+    a.reset();
+    rst = a.search(sp, sv, sa, gp, Eigen::Vector3d(0, 0, 0), false, true, t_start);
+    retried = 1;
+  }
+  int n = 0;
+  if (rst != NO_PATH) {
+    const std::vector<Eigen::Matrix<double, 6, 1>> path = a.getPathWithVel(prm[12]);
+    n = static_cast<int>(path.size());
+    for (int i = 0; i < n && i < cap; i++) for (int k = 0; k < 6; k++) out_path[6 * i + k] = path[i](k);
+  }
+  std::cout.rdbuf(old);
+  if (out_n) *out_n = n;
+  if (stats) { stats[0] = a.iter_num_; stats[1] = a.use_node_num_; stats[2] = retried; stats[3] = static_cast<int>(m->n_queries); }
+  return static_cast<int>(rst);
 }
 
 }  // extern "C"

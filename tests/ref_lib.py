@@ -96,6 +96,23 @@ class RefLib:
         return Q, A, l, u
 
 
+    def astar(self, cfg, omap, pose, start9, goal3, t_start, cap=256):
+        """The reference's FakeRiskHybridAstar, driven as FakeBaselinePlanner::replan drives it, on the oracle map
+        `omap` (occupancy queries go straight to liboracle's orc_map_query_dt)."""
+        from tests import oracle_lib
+        prm = np.array([cfg.max_tau, cfg.max_tau, cfg.max_vel, cfg.max_acc, cfg.w_time, cfg.horizon, cfg.resolution_astar,
+                        cfg.time_resolution_astar, cfg.lambda_heu, cfg.allocate_num, cfg.check_num, cfg.tolerance,
+                        cfg.corridor_tau], np.float64)
+        q = C.cast(oracle_lib.load().lib.orc_map_query_dt, C.c_void_p)
+        pose = np.ascontiguousarray(pose, np.float32)
+        start9, goal3 = np.ascontiguousarray(start9, np.float64), np.ascontiguousarray(goal3, np.float64)
+        out, n, st = np.zeros((cap, 6)), C.c_int(0), np.zeros(4, np.int32)
+        ret = self.lib.ref_astar(P(prm), q, omap.h, pose.ctypes.data_as(C.POINTER(C.c_float)), P(start9), P(goal3),
+                                 D(t_start), P(out), cap, C.byref(n), st.ctypes.data_as(C.POINTER(C.c_int32)))
+        assert n.value <= cap
+        return ret, out[:n.value].copy(), st
+
+
 _ref = False
 
 
@@ -293,6 +310,28 @@ def qp_cases(n, seed=7, max_pieces=8):
         polys = [np.c_[rng.normal(size=(r, 3)), -rng.uniform(0.5, 3, r)] for r in rng.integers(4, 20, M)]
         out.append((rng.normal(size=(3, 3)), rng.normal(size=(3, 3)), rng.uniform(0.3, 2.5, M), polys,
                     float(rng.uniform(1, 4)), float(rng.uniform(1, 5))))
+    return out
+
+
+def astar_world():
+    """BASELINE config 1 grid (66 x 66 x 20 @0.15 m) with 12 static pillars and 8 moving cylinders."""
+    from tests import cases
+    return cases.cfg_c1(), cases.world_moving(77, (10.0, 10.0, 3.0), 12, 8)
+
+
+def astar_cases(n, seed=8):
+    """(pose, start [pos vel acc], goal, time of the start on the map): agents scattered over the arena, goals up
+    to 6 m away (some too close to search: NO_PATH after the retry)."""
+    rng = np.random.default_rng(seed)
+    out = []
+    for _ in range(n):
+        pose = np.array([rng.uniform(-4, 4), rng.uniform(-3, 3), 1.0], np.float32)
+        start = np.zeros(9)
+        start[:3] = pose.astype(np.float64) + rng.uniform(-0.3, 0.3, 3) * [1, 1, 0.2]
+        start[3:6] = rng.uniform(-1, 1, 3) * [1, 1, 0.2]
+        start[6:9] = rng.uniform(-1, 1, 3) * [1, 1, 0.1]
+        goal = start[:3] + rng.uniform(-6, 6, 3) * [1, 1, 0.05]
+        out.append((pose, start, goal, float(rng.uniform(0, 0.25))))
     return out
 
 

@@ -1,8 +1,9 @@
 """Pins of the oracle against the REFERENCE's own code.
 
 `oracle/_ref/libref.so` is the reference's plan_env/src/raycast.cpp, traj_utils/sdlp.hpp, sfc_gen/lbfgs.hpp,
-sfc_gen/firi.hpp, traj_utils/src/bernstein.cpp and traj_opt/src/bezier_optimizer.cpp compiled unmodified
-(oracle/Makefile; Eigen replaced by the stand-in oracle/ref_build/Eigen/Eigen, the OSQP wrapper by a recorder).
+sfc_gen/firi.hpp, traj_utils/src/bernstein.cpp, traj_opt/src/bezier_optimizer.cpp and
+path_searching/src/fake_risk_hybrid_a_star.cpp compiled unmodified (oracle/Makefile; Eigen replaced by the stand-in
+oracle/ref_build/Eigen/Eigen, the OSQP wrapper by a recorder, ROS and the map class by minimal stand-ins).
 Every test runs the oracle's restatement on seeded cases and compares it with
 
   * the committed outputs of that library (tests/golden/ref_pins.npz, scripts/make_golden_ref.py) — always;
@@ -18,7 +19,8 @@ later ones are compared as sets (both valid corridors, intersection-over-union).
 matrix products whose summation order the oracle fixes one way and the stand-in another: 1e-14 relative (99 % of the
 samples are identical).  BezierOpt::setup only places and scales constants: Q, A, lb, ub identical.  The OSQP solver
 itself is third-party and absent; its restatement in oracle/o_qp.cpp is NOT pinned here (tests/test_golden_reference.py
-holds the reference's own QP fixture)."""
+holds the reference's own QP fixture).  The hybrid A* is a deterministic search over doubles: return code, expansion
+and node counts and every sampled path state identical (its occupancy queries are answered by the oracle's grid)."""
 import os
 
 import numpy as np
@@ -212,3 +214,30 @@ def test_qp_assembly_identical(oracle, ref, gold):
         for init, goal, dur, polys, vmax, amax in rl.qp_cases(60, seed=47):
             got, want = oracle.qp_setup(init, goal, dur, polys, vmax=vmax, amax=amax), ref.qp_setup(init, goal, dur, polys, vmax, amax)
             assert all(np.array_equal(a, b) for a, b in zip(got, want))
+
+
+# ---- FakeRiskHybridAstar (path_searching/src/fake_risk_hybrid_a_star.cpp) -------------------------------------------
+def test_hybrid_astar_identical(oracle, ref, gold):
+    """The reference's own search — motion primitives, pruning by (voxel, time slice), heuristic via the quartic,
+    one-shot trajectories, open-set order — and the oracle's restatement, on the same grid with moving obstacles:
+    same ASTAR_RET, same number of expansions and nodes, same retry, the same path to the last bit."""
+    cfg, (cloud, cyl) = rl.astar_world()
+    heads = gold["astar_head"]
+    paths = rl.unpack(gold["astar_path"], gold["astar_offs"], 6)
+    found = 0
+    for (pose, start, goal, t0), head, want in zip(rl.astar_cases(len(heads)), heads, paths):
+        m = oracle.map(cfg)
+        m.set_pose(pose)
+        m.update_gt(cloud, cyl, 0.0)
+        ret, pth, st = m.astar(start, goal, t0, cap=256)
+        assert [ret, st[0], st[1], st[2]] == head.tolist()
+        assert pth.shape == want.shape and np.array_equal(pth, want)
+        found += int(ret != 0)
+    assert found >= len(heads) // 2
+    if ref is not None:
+        for pose, start, goal, t0 in rl.astar_cases(60, seed=53):
+            m = oracle.map(cfg)
+            m.set_pose(pose)
+            m.update_gt(cloud, cyl, 0.0)
+            a, b = ref.astar(cfg, m, pose, start, goal, t0), m.astar(start, goal, t0, cap=256)
+            assert a[0] == b[0] and np.array_equal(a[1], b[1]) and np.array_equal(a[2][:3], b[2][:3])

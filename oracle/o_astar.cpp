@@ -5,6 +5,10 @@
 // Quirks kept on purpose: hash INSERT keys use (int)time while lookups use timeToIndex()
 // (:387 vs :269-271); open-set nodes are re-scored in place without re-heapifying (:345-362,
 // :401-412); the heuristic is scaled by (1 + tie_breaker) (:456).
+// PINNED against the reference's own fake_risk_hybrid_a_star.cpp, compiled unmodified into oracle/_ref/libref.so
+// (oracle/Makefile; ROS and the map class replaced by stand-ins, occupancy answered by this oracle's grid):
+// return code, expansion / node counts, retry and every sampled path state identical — tests/test_ref_pins.py,
+// committed vectors tests/golden/ref_pins.npz.
 #include <algorithm>
 #include <array>
 #include <queue>

@@ -1,6 +1,8 @@
 // o_bezier.cpp — oracle: Bernstein/Bezier evaluation (TEST INFRASTRUCTURE).
 // Follows traj_utils/src/bernstein.cpp:25-59,80-88,117-196 and
 // traj_utils/include/traj_utils/bernstein.hpp:98-177 of the reference.
+// PINNED twice: the reference's own known-answer tests (tests/test_golden_reference.py) and its bernstein.cpp
+// compiled into oracle/_ref/libref.so (1e-14 relative, 99 % of samples identical; tests/test_ref_pins.py).
 #include "oracle.hpp"
 
 namespace orc {

@@ -5,6 +5,11 @@
 // plan_manager/src/baseline_fake.cpp:127-228 (helpers) and :296-411 (stage).
 // Deviations: Eigen::JacobiSVD of the 3x3 factor is replaced by a cyclic Jacobi eigen-solve of
 // L L^T (same ellipsoid, axis signs may differ); LP shuffles are seeded per call (see o_lp.cpp).
+// PINNED against the reference's own firi.hpp / lbfgs.hpp / sdlp.hpp compiled unmodified into oracle/_ref/libref.so
+// (Eigen replaced by a stand-in, oracle/ref_build/Eigen/Eigen): costMVIE and whole L-BFGS runs bit-identical, the
+// first FIRI polytope identical, maxVolInsEllipsoid the same optimum to the optimiser's own stopping tolerance,
+// iterated corridors compared as sets — tests/test_ref_pins.py.  The corridor stage around firi
+// (baseline_fake.cpp, ROS-bound) remains PARITY UNPINNED.
 #include <algorithm>
 #include <cfloat>
 #include <limits>

@@ -3,7 +3,9 @@
 //   :458-475 (closetPointInMap), :477-583 (clearAndInflateLocalMap)
 //   plan_env/src/raycast.cpp:17-31, 242-335 (RayCaster::setInput / step)
 //   plan_env/include/plan_env/grid_map.h:261-420 (index helpers, occupancy getters)
-// PARITY UNPINNED by the reference's tests (none exist for GridMap); every step is integer counting or a
+// The DDA (RayDda below) is PINNED against the reference's own raycast.cpp compiled into oracle/_ref/libref.so:
+// identical voxel sequences on 25 000 rays (tests/test_ref_pins.py).  The rest (grid_map.cpp needs ROS, PCL and
+// OpenCV) is PARITY UNPINNED by the reference's tests (none exist for GridMap); every step is integer counting or a
 // fixed sequence of IEEE double operations.  Quirk kept: flag_rayend_ / flag_traverse_ are vector<char>
 // compared with the int frame counter raycast_num_, so ray-end de-duplication and the early break on voxels
 // traversed by an earlier ray of the same frame only work for the first 127 frames.

@@ -7,6 +7,8 @@
 // Deviation: the reference shuffles constraints with a function-static
 // mt19937_64 (result depends on global call history); here the shuffle is a Fisher-Yates
 // driven by a caller-owned 64-bit LCG so CPU and GPU agree call by call.
+// PINNED against the reference's own sdlp.hpp compiled into oracle/_ref/libref.so: optimum and minimiser within
+// 1e-9 / 1e-7 on bounded problems, same infeasible / unbounded classification (tests/test_ref_pins.py).
 #include <cmath>
 #include <limits>
 #include <vector>

@@ -1,6 +1,8 @@
 // o_peers.cpp — oracle: peer-trajectory particles projected into the SOGM (TEST INFRASTRUCTURE).
 // Follows traj_coordinator/src/particles.cpp:62-87,291-422 and
 // plan_env/src/fake_particle_risk_voxel.cpp:175-218 of the reference.
+// PARITY UNPINNED: particles.cpp needs ROS message types and GLPK; checked by property tests only
+// (tests/test_oracle_map.py); its Bezier evaluation is the pinned one of o_bezier.cpp.
 #include "oracle.hpp"
 
 namespace orc {

@@ -14,6 +14,9 @@
 //       reduced system (P + sigma I + A' diag(rho) A) x = rhs with a dense Cholesky.
 // PARITY UNPINNED against OSQP itself (not available here); pinned properties: the reference's
 // own QP test fixture (traj_opt/test/test_bezier_opt.cpp:47-221).
+// qp_setup is PINNED against the reference's own bezier_optimizer.cpp compiled into oracle/_ref/libref.so: Q, A, lb,
+// ub identical (tests/test_ref_pins.py).  osqp_solve has no reference build to compare with (OSQP is absent): pinned
+// only by the reference's QP fixture (tests/test_golden_reference.py) and a tight-tolerance cross-solve.
 #include <algorithm>
 #include <cmath>
 #include <cstdio>

@@ -2,6 +2,8 @@
 // Follows path_searching/src/fake_risk_hybrid_a_star.cpp:85-107 (reset), :114-421 (search),
 // :423-457 (estimateHeuristic), :459-519 (computeShotTraj), :521-585 (cubic/quartic),
 // :663-694 (getPathWithVel), :795-836 and the call site plan_manager/src/baseline_fake.cpp:264-296.
+// path_searching/src/risk_hybrid_a_star.cpp (the planner over RiskBase maps) is the same search except for the
+// one-shot collision check, which it runs against slice 0 (:514); selected by pop_config.query_variant.
 // Quirks kept on purpose: hash INSERT keys use (int)time while lookups use timeToIndex()
 // (:387 vs :269-271); open-set nodes are re-scored in place without re-heapifying (:345-362,
 // :401-412); the heuristic is scaled by (1 + tie_breaker) (:456).
@@ -170,7 +172,9 @@ struct Search {
       // Eigen dot of dynamic 4-vectors, SSE2 packets of two: (c0 t0 + c2 t2) + (c1 t1 + c3 t3)
       for (int d = 0; d < 3; d++)
         cp[d] = (coef[d][0] * tp[0] + coef[d][2] * tp[2]) + (coef[d][1] * tp[1] + coef[d][3] * tp[3]);
-      if (query_dt(g, coord, time) != 0) return false;
+      // FakeRiskHybridAstar checks the shot at its own time (fake_risk_hybrid_a_star.cpp:521); RiskHybridAstar, the
+      // planner of the real-perception path, checks it against the current slice only (risk_hybrid_a_star.cpp:514)
+      if (query_dt(g, coord, g.query_variant == POP_QUERY_FAKE ? time : 0.0) != 0) return false;
     }
     is_shot_succ = true;
     return true;

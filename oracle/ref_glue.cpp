@@ -25,6 +25,7 @@
 #include <path_searching/fake_risk_hybrid_a_star.h>
 #undef private
 #undef protected
+#include "ref_astar_driver.hpp"
 
 // path_searching/src/dyn_a_star.cpp (the base class's own grid A*, not on the path, needs the real GridMap) is not
 // compiled; its out-of-line members are stubbed so that the vtable links
@@ -191,47 +192,11 @@ int ref_qp_setup(int M, const double* init9, const double* goal9, const double* 
   return m;
 }
 
-// FakeRiskHybridAstar driven as FakeBaselinePlanner::replan drives it (baseline_fake.cpp:280-305): reset, search with
-// init = true, once more with init = false on NO_PATH, then getPathWithVel(corridor_tau).  prm = max_tau, init_max_tau,
-// max_vel, max_acc, w_time, horizon, resolution_astar, time_resolution, lambda_heu, allocate_num, check_num, tolerance,
-// corridor_tau (search/... of fake_risk_hybrid_a_star.cpp:62-82).  start9 = pos, vel, acc.  out_path n x 6;
-// stats = iterations, nodes used, retried, occupancy queries.  Returns ASTAR_RET.
+// FakeRiskHybridAstar on FakeParticleRiskVoxel (see ref_astar_driver.hpp); RiskHybridAstar is ref_astar_risk in ref_glue_risk.cpp
 int ref_astar(const double* prm, FakeParticleRiskVoxel::query_dt_fn query, void* map, const float* pose3,
               const double* start9, const double* goal3, double t_start, double* out_path, int cap, int* out_n, int* stats) {
-  ros::NodeHandle nh;
-  const char* names[] = {"search/max_tau", "search/init_max_tau", "search/max_vel", "search/max_acc", "search/w_time",
-                         "search/horizon", "search/resolution_astar", "search/time_resolution", "search/lambda_heu",
-                         "search/allocate_num", "search/check_num", "search/tolerance"};
-  for (int i = 0; i < 12; i++) nh.values[names[i]] = prm[i];
-  FakeParticleRiskVoxel::Ptr m(new FakeParticleRiskVoxel());
-  m->query = query; m->map = map;
-  m->pose = Eigen::Vector3f(pose3[0], pose3[1], pose3[2]);
-  std::ostringstream sink;
-  std::streambuf* old = std::cout.rdbuf(sink.rdbuf());
-  FakeRiskHybridAstar a;
-  a.setParam(nh);
-  a.setEnvironment(m);
-  a.init(Eigen::Vector3d::Zero(), Eigen::Vector3d(10, 10, 4));          // baseline_fake.cpp:28
-  const Eigen::Vector3d sp(start9[0], start9[1], start9[2]), sv(start9[3], start9[4], start9[5]),
-      sa(start9[6], start9[7], start9[8]), gp(goal3[0], goal3[1], goal3[2]);
-  a.reset();
-  int retried = 0;
-  ASTAR_RET rst = a.search(sp, sv, sa, gp, Eigen::Vector3d(0, 0, 0), true, true, t_start);
-  if (rst == 0) {
-    a.reset();
-    rst = a.search(sp, sv, sa, gp, Eigen::Vector3d(0, 0, 0), false, true, t_start);
-    retried = 1;
-  }
-  int n = 0;
-  if (rst != NO_PATH) {
-    const std::vector<Eigen::Matrix<double, 6, 1>> path = a.getPathWithVel(prm[12]);
-    n = static_cast<int>(path.size());
-    for (int i = 0; i < n && i < cap; i++) for (int k = 0; k < 6; k++) out_path[6 * i + k] = path[i](k);
-  }
-  std::cout.rdbuf(old);
-  if (out_n) *out_n = n;
-  if (stats) { stats[0] = a.iter_num_; stats[1] = a.use_node_num_; stats[2] = retried; stats[3] = static_cast<int>(m->n_queries); }
-  return static_cast<int>(rst);
+  return run_astar<FakeRiskHybridAstar, FakeParticleRiskVoxel>(prm, query, map, pose3, start9, goal3, t_start, out_path,
+                                                               cap, out_n, stats);
 }
 
 }  // extern "C"

@@ -332,7 +332,8 @@ __global__ void __launch_bounds__(kThreads) k_astar(PopGeom g, AstarParams P, As
           if (reach_horizon || near_end || exceed_time) {
             s_term = cur;
             if (near_end) {
-              // computeShotTraj (:459-519); queried with the time ALONG the shot, as in the reference
+              // computeShotTraj (:459-519); FakeRiskHybridAstar queries with the time ALONG the shot
+              // (fake_risk_hybrid_a_star.cpp:521), RiskHybridAstar with the current slice (risk_hybrid_a_star.cpp:514)
               double t_d;
               heuristic(P, cs, s_end, &t_d);
               double coef[3][4];
@@ -352,7 +353,7 @@ __global__ void __launch_bounds__(kThreads) k_astar(PopGeom g, AstarParams P, As
                 double coord[3];
                 for (int d = 0; d < 3; d++)
                   coord[d] = (coef[d][0] * tp[0] + coef[d][2] * tp[2]) + (coef[d][1] * tp[1] + coef[d][3] * tp[3]);
-                if (query_dt<C>(g, ag, pose, coord, time) != 0) { ok = false; break; }
+                if (query_dt<C>(g, ag, pose, coord, g.query_variant == POP_QUERY_FAKE ? time : 0.0) != 0) { ok = false; break; }
               }
               if (ok) s_shot = 1;
             }

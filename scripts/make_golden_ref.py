@@ -1,5 +1,5 @@
 """Regenerates tests/golden/ref_pins.npz: outputs of the REFERENCE's own code (oracle/_ref/libref.so =
-plan_env/src/raycast.cpp, traj_utils/sdlp.hpp, sfc_gen/lbfgs.hpp, sfc_gen/firi.hpp, traj_utils/src/bernstein.cpp, traj_opt/src/bezier_optimizer.cpp, path_searching/src/fake_risk_hybrid_a_star.cpp compiled unmodified from
+plan_env/src/raycast.cpp, traj_utils/sdlp.hpp, sfc_gen/lbfgs.hpp, sfc_gen/firi.hpp, traj_utils/src/bernstein.cpp, traj_opt/src/bezier_optimizer.cpp, path_searching/src/{fake_,}risk_hybrid_a_star.cpp compiled unmodified from
 /root/reference; see oracle/Makefile) on the seeded cases of tests/ref_lib.py.  tests/test_ref_pins.py checks the
 oracle against these vectors wherever the library itself is not available.  Needs /root/reference.
 
@@ -65,17 +65,17 @@ def main():
     out["qp"], out["qp_offs"] = rl.pack(qps)
     from tests import oracle_lib
     orc = oracle_lib.load()
-    cfg, (cloud, cyl) = rl.astar_world()
-    paths, heads = [], []
-    for pose, start, goal, t0 in rl.astar_cases(N_ASTAR):
-        m = orc.map(cfg)
-        m.set_pose(pose)
-        m.update_gt(cloud, cyl, 0.0)
-        ret, pth, st = ref.astar(cfg, m, pose, start, goal, t0)
-        paths.append(pth)
-        heads.append([ret, st[0], st[1], st[2]])
-    out["astar_path"], out["astar_offs"] = rl.pack(paths)
-    out["astar_head"] = np.array(heads, np.int32)
+    for key, (cfg, (cloud, cyl)), risk, seed in (("astar", rl.astar_world(), False, 8), ("astar_risk", rl.astar_world_risk(), True, 9)):
+        paths, heads = [], []
+        for pose, start, goal, t0 in rl.astar_cases(N_ASTAR, seed=seed):
+            m = orc.map(cfg)
+            m.set_pose(pose)
+            m.update_gt(cloud, cyl, 0.0)
+            ret, pth, st = ref.astar(cfg, m, pose, start, goal, t0, risk=risk)
+            paths.append(pth)
+            heads.append([ret, st[0], st[1], st[2]])
+        out[key + "_path"], out[key + "_offs"] = rl.pack(paths)
+        out[key + "_head"] = np.array(heads, np.int32)
     path = os.path.join(ROOT, "tests", "golden", "ref_pins.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path), "bytes")

@@ -96,9 +96,9 @@ class RefLib:
         return Q, A, l, u
 
 
-    def astar(self, cfg, omap, pose, start9, goal3, t_start, cap=256):
-        """The reference's FakeRiskHybridAstar, driven as FakeBaselinePlanner::replan drives it, on the oracle map
-        `omap` (occupancy queries go straight to liboracle's orc_map_query_dt)."""
+    def astar(self, cfg, omap, pose, start9, goal3, t_start, cap=256, risk=False):
+        """The reference's FakeRiskHybridAstar (or, risk=True, RiskHybridAstar), driven as (Fake)BaselinePlanner::replan
+        drives it, on the oracle map `omap` (occupancy queries go straight to liboracle's orc_map_query_dt)."""
         from tests import oracle_lib
         prm = np.array([cfg.max_tau, cfg.max_tau, cfg.max_vel, cfg.max_acc, cfg.w_time, cfg.horizon, cfg.resolution_astar,
                         cfg.time_resolution_astar, cfg.lambda_heu, cfg.allocate_num, cfg.check_num, cfg.tolerance,
@@ -107,7 +107,7 @@ class RefLib:
         pose = np.ascontiguousarray(pose, np.float32)
         start9, goal3 = np.ascontiguousarray(start9, np.float64), np.ascontiguousarray(goal3, np.float64)
         out, n, st = np.zeros((cap, 6)), C.c_int(0), np.zeros(4, np.int32)
-        ret = self.lib.ref_astar(P(prm), q, omap.h, pose.ctypes.data_as(C.POINTER(C.c_float)), P(start9), P(goal3),
+        ret = (self.lib.ref_astar_risk if risk else self.lib.ref_astar)(P(prm), q, omap.h, pose.ctypes.data_as(C.POINTER(C.c_float)), P(start9), P(goal3),
                                  D(t_start), P(out), cap, C.byref(n), st.ctypes.data_as(C.POINTER(C.c_int32)))
         assert n.value <= cap
         return ret, out[:n.value].copy(), st
@@ -317,6 +317,16 @@ def astar_world():
     """BASELINE config 1 grid (66 x 66 x 20 @0.15 m) with 12 static pillars and 8 moving cylinders."""
     from tests import cases
     return cases.cfg_c1(), cases.world_moving(77, (10.0, 10.0, 3.0), 12, 8)
+
+
+def astar_world_risk():
+    """The same world queried the RiskBase way (risk_base.cpp:228-260: ground / ceiling count as occupied, threshold
+    risk_threshold_region - t * decay), thresholds chosen so that one occupied cell blocks at every slice."""
+    import pred_occ_planner_b200 as p
+    cfg, world = astar_world()
+    cfg.query_variant = p.POP_QUERY_RISKBASE
+    cfg.risk_threshold_region, cfg.risk_region_decay = 0.9, 0.05
+    return cfg, world
 
 
 def astar_cases(n, seed=8):

@@ -217,15 +217,18 @@ def test_qp_assembly_identical(oracle, ref, gold):
 
 
 # ---- FakeRiskHybridAstar (path_searching/src/fake_risk_hybrid_a_star.cpp) -------------------------------------------
-def test_hybrid_astar_identical(oracle, ref, gold):
+@pytest.mark.parametrize("risk", [False, True])
+def test_hybrid_astar_identical(oracle, ref, gold, risk):
     """The reference's own search — motion primitives, pruning by (voxel, time slice), heuristic via the quartic,
     one-shot trajectories, open-set order — and the oracle's restatement, on the same grid with moving obstacles:
-    same ASTAR_RET, same number of expansions and nodes, same retry, the same path to the last bit."""
-    cfg, (cloud, cyl) = rl.astar_world()
-    heads = gold["astar_head"]
-    paths = rl.unpack(gold["astar_path"], gold["astar_offs"], 6)
+    same ASTAR_RET, same number of expansions and nodes, same retry, the same path to the last bit.  Both classes:
+    FakeRiskHybridAstar (ground-truth map) and RiskHybridAstar (RiskBase map; its one-shot check looks at slice 0)."""
+    cfg, (cloud, cyl) = rl.astar_world_risk() if risk else rl.astar_world()
+    key = "astar_risk" if risk else "astar"
+    heads = gold[key + "_head"]
+    paths = rl.unpack(gold[key + "_path"], gold[key + "_offs"], 6)
     found = 0
-    for (pose, start, goal, t0), head, want in zip(rl.astar_cases(len(heads)), heads, paths):
+    for (pose, start, goal, t0), head, want in zip(rl.astar_cases(len(heads), seed=9 if risk else 8), heads, paths):
         m = oracle.map(cfg)
         m.set_pose(pose)
         m.update_gt(cloud, cyl, 0.0)
@@ -239,5 +242,5 @@ def test_hybrid_astar_identical(oracle, ref, gold):
             m = oracle.map(cfg)
             m.set_pose(pose)
             m.update_gt(cloud, cyl, 0.0)
-            a, b = ref.astar(cfg, m, pose, start, goal, t0), m.astar(start, goal, t0, cap=256)
+            a, b = ref.astar(cfg, m, pose, start, goal, t0, risk=risk), m.astar(start, goal, t0, cap=256)
             assert a[0] == b[0] and np.array_equal(a[1], b[1]) and np.array_equal(a[2][:3], b[2][:3])

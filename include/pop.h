@@ -204,7 +204,9 @@ int pop_map_download(pop_handle* h, int agent, float* out);
 /* ---- K2: kinodynamic hybrid A* -------------------------------------------------------- */
 /* FakeRiskHybridAstar::reset + search(+retry with init=false) + getPathWithVel(corridor_tau)
  * for n = n_agents_local agents (fake_risk_hybrid_a_star.cpp:85-107,114-421,663-694;
- * call site baseline_fake.cpp:268-296).
+ * call site baseline_fake.cpp:268-296).  With query_variant = POP_QUERY_RISKBASE it is RiskHybridAstar
+ * (risk_hybrid_a_star.cpp, call site baseline.cpp:268-296): the same search, except that the one-shot
+ * trajectory is checked against slice 0 (:514) instead of its own time (fake_...:521).
  *   start   n x 9  (pos, vel, acc)        goal n x 3
  *   t_start n      (traj_start_time - map time)
  *   out_ret n      ASTAR_RET of the search whose path is returned

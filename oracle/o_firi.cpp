@@ -463,21 +463,22 @@ bool corridor_valid(const std::vector<double>& h, uint64_t* rng) {
   return !std::isinf(rst);
 }
 
-// ShrinkCorridor(corridor, path) (baseline_fake.cpp:215-228)
-void shrink(std::vector<double>& h, const double path[3], double shrink_size) {
+// ShrinkCorridor(corridor, path): the simulator planner leaves front / back and top / bottom faces alone
+// (baseline_fake.cpp:215-228); the real-perception planner shrinks every face (baseline.cpp:213-226)
+void shrink(std::vector<double>& h, const double path[3], double shrink_size, bool keep_end_faces) {
   const int m = static_cast<int>(h.size() / 4);
   for (int i = 0; i < m; i++) {
     const double A = h[i * 4], B = h[i * 4 + 1], C = h[i * 4 + 2];
     const double n[3] = {A, B, C}, z[3] = {0, 0, 1};
-    if (dot3(n, path) / norm3(n) / norm3(path) > 0.8) continue;
-    if (std::abs(dot3(n, z)) / norm3(n) > 0.8) continue;
+    if (keep_end_faces && dot3(n, path) / norm3(n) / norm3(path) > 0.8) continue;
+    if (keep_end_faces && std::abs(dot3(n, z)) / norm3(n) > 0.8) continue;
     h[i * 4 + 3] += std::sqrt(A * A + B * B + C * C) * shrink_size;
   }
 }
 
 // checkGoalReachability (baseline_fake.cpp:143-182)
 bool goal_reachable(const std::vector<double>& h, const double start[3], double goal[3], uint64_t seed_base,
-                    int corridor_idx) {
+                    int corridor_idx, int kind0 = 3) {
   const int m = static_cast<int>(h.size() / 4);
   if (m <= 0) return true;
   double mx = -INFINITY;
@@ -490,7 +491,7 @@ bool goal_reachable(const std::vector<double>& h, const double start[3], double 
   for (int i = 0; i < m; i++) { for (int k = 0; k < 3; k++) A[i * 3 + k] = h[i * 4 + k]; b[i] = -h[i * 4 + 3]; }
   double c[3] = {-goal[0] + start[0], -goal[1] + start[1], -goal[2] + start[2]};
   double gmax[3], gmin[3];
-  uint64_t r1 = lp_seed(seed_base, corridor_idx, 3), r2 = lp_seed(seed_base, corridor_idx, 4);
+  uint64_t r1 = lp_seed(seed_base, corridor_idx, kind0), r2 = lp_seed(seed_base, corridor_idx, kind0 + 1);
   linprog(3, c, A.data(), b.data(), m, gmax, &r1);
   for (int k = 0; k < 3; k++) c[k] = goal[k] - start[k];
   linprog(3, c, A.data(), b.data(), m, gmin, &r2);
@@ -498,14 +499,55 @@ bool goal_reachable(const std::vector<double>& h, const double start[3], double 
   return false;
 }
 
+// The tail of the corridor stage: adjacent corridors must intersect, enough corridors must be left, the local goal is
+// pulled back to the last corridor that contains it.  The reference's two planners differ here; `real` selects
+// BaselinePlanner::replan (baseline.cpp:363-403) against FakeBaselinePlanner::replan (baseline_fake.cpp:366-411):
+//   non-intersecting corridors i, i+1 (i >= 2): the real planner also drops corridor i (:371 against :374);
+//   it fails with at most one corridor left (:381 against "none", :384);
+//   it tests the last corridor once before the backward search (:389) — and that test moves the goal when it fails.
+// polys holds the valid prefix of corridors; returns false when the replan fails here.
+bool corridor_tail(bool real, uint64_t seed_base, std::vector<Poly>& polys, const std::vector<double>& path,
+                   const double start[9], double goal[6]) {
+  // the reference underflows `size() - 1` on an empty list
+  for (int i = 0; i + 1 < static_cast<int>(polys.size()); i++) {
+    std::vector<double> both = polys[i].h;
+    both.insert(both.end(), polys[i + 1].h.begin(), polys[i + 1].h.end());
+    uint64_t rng_i = lp_seed(seed_base, i, 2);
+    if (!corridor_valid(both, &rng_i)) {
+      if (i < 2) { polys.clear(); return false; }
+      polys.erase(polys.begin() + (real ? i : i + 1), polys.end());
+      break;
+    }
+  }
+  if (polys.size() <= (real ? 1u : 0u)) { polys.clear(); return false; }
+  int gi = static_cast<int>(polys.size()) - 1;
+  double goal_pos[3] = {path[gi * 6], path[gi * 6 + 1], path[gi * 6 + 2]};
+  double goal_vel[3] = {path[gi * 6 + 3], path[gi * 6 + 4], path[gi * 6 + 5]};
+  bool search = true;
+  if (real) search = !goal_reachable(polys.back().h, start, goal_pos, seed_base, gi, 5);
+  for (int it = static_cast<int>(polys.size()) - 1; search && it != 0; it--) {
+    if (goal_reachable(polys[it].h, start, goal_pos, seed_base, it)) {
+      polys.erase(polys.begin() + it + 1, polys.end());
+      const int idx = static_cast<int>(polys.size()) - 1;
+      for (int k = 0; k < 3; k++) { goal_pos[k] = path[idx * 6 + k]; goal_vel[k] = path[idx * 6 + 3 + k]; }
+      break;
+    }
+  }
+  for (int k = 0; k < 3; k++) { goal[k] = goal_pos[k]; goal[3 + k] = goal_vel[k]; }
+  return true;
+}
+
 }  // namespace
 
-// Corridor stage of FakeBaselinePlanner::replan (baseline_fake.cpp:296-411).
+// Corridor stage of FakeBaselinePlanner::replan (baseline_fake.cpp:296-411) or, on a RiskBase-style map
+// (pop_config.query_variant), of BaselinePlanner::replan (baseline.cpp:296-403): the same code up to the shrink rule
+// and the tail rules above.
 // path = n x 6 from getPathWithVel; the LP seed base is pop_config.agent_id_base (callers set it
 // to the agent's global id).
 CorridorResult corridor_stage(const Grid& g, const pop_config& c, const std::vector<double>& path,
                               const double start[9], double traj_start_time) {
   CorridorResult res;
+  const bool real = g.query_variant != POP_QUERY_FAKE;
   const uint64_t seed_base = static_cast<uint64_t>(c.agent_id_base);
   const int n = static_cast<int>(path.size() / 6);
   std::vector<V3d> wpts(n);
@@ -536,35 +578,12 @@ CorridorResult corridor_stage(const Grid& g, const pop_config& c, const std::vec
     uint64_t rng = lp_seed(seed_base, i, 0);
     firi(bd, pc, wpts[i], wpts[i + 1], poly, r, 2, &rng);
     const double dir[3] = {wpts[i + 1].x - wpts[i].x, wpts[i + 1].y - wpts[i].y, wpts[i + 1].z - wpts[i].z};
-    shrink(poly.h, dir, c.shrink_size);
+    shrink(poly.h, dir, c.shrink_size, !real);
     uint64_t rng_v = lp_seed(seed_base, i, 1);
     if (!corridor_valid(poly.h, &rng_v)) break;
     res.polys.push_back(poly);
   }
-  // adjacent corridors must intersect (:366-378); the reference underflows on an empty list
-  for (int i = 0; i + 1 < static_cast<int>(res.polys.size()); i++) {
-    std::vector<double> both = res.polys[i].h;
-    both.insert(both.end(), res.polys[i + 1].h.begin(), res.polys[i + 1].h.end());
-    uint64_t rng_i = lp_seed(seed_base, i, 2);
-    if (!corridor_valid(both, &rng_i)) {
-      if (i < 2) { res.polys.clear(); return res; }
-      res.polys.erase(res.polys.begin() + i + 1, res.polys.end());
-      break;
-    }
-  }
-  if (res.polys.empty()) return res;
-  int gi = static_cast<int>(res.polys.size()) - 1;
-  double goal_pos[3] = {path[gi * 6], path[gi * 6 + 1], path[gi * 6 + 2]};
-  double goal_vel[3] = {path[gi * 6 + 3], path[gi * 6 + 4], path[gi * 6 + 5]};
-  for (int it = static_cast<int>(res.polys.size()) - 1; it != 0; it--) {
-    if (goal_reachable(res.polys[it].h, start, goal_pos, seed_base, it)) {
-      res.polys.erase(res.polys.begin() + it + 1, res.polys.end());
-      const int idx = static_cast<int>(res.polys.size()) - 1;
-      for (int k = 0; k < 3; k++) { goal_pos[k] = path[idx * 6 + k]; goal_vel[k] = path[idx * 6 + 3 + k]; }
-      break;
-    }
-  }
-  for (int k = 0; k < 3; k++) { res.goal[k] = goal_pos[k]; res.goal[3 + k] = goal_vel[k]; }
+  if (!corridor_tail(real, seed_base, res.polys, path, start, res.goal)) return res;
   res.ok = true;
   return res;
 }
@@ -590,4 +609,25 @@ extern "C" int orc_lbfgs_mvie(const double* A, int M, double smooth_eps, double 
   D.A.assign(A, A + static_cast<size_t>(M) * 3);
   orc::LbfgsParams P;
   return orc::lbfgs9(D, x, *fx, P, nullptr);
+}
+// the tail alone on given corridors (hpoly POP_MAX_PIECES x POP_MAX_FACES x 4, rows, valid per segment): returns the
+// number kept (0 = fail); tests/test_device_logic_on_host.py compares it with the device source compiled for the host
+extern "C" int orc_corridor_tail(int variant, uint64_t seed_base, int n, const double* path, const double* hpoly,
+                                 const int32_t* rows, const int32_t* valid, const double* start9, double* out_goal) {
+  std::vector<orc::Poly> polys;
+  for (int i = 0; i < n - 1 && i < POP_MAX_PIECES; i++) {
+    if (!valid[i]) break;
+    orc::Poly p;
+    p.h.assign(hpoly + static_cast<size_t>(i) * POP_MAX_FACES * 4, hpoly + (static_cast<size_t>(i) * POP_MAX_FACES + rows[i]) * 4);
+    polys.push_back(p);
+  }
+  std::vector<double> pv(path, path + static_cast<size_t>(n) * 6);
+  if (!orc::corridor_tail(variant != POP_QUERY_FAKE, seed_base, polys, pv, start9, out_goal)) return 0;
+  return static_cast<int>(polys.size());
+}
+// ShrinkCorridor(corridor, path) alone, in place
+extern "C" void orc_shrink(int variant, double* h, int m, const double* dir, double shrink_size) {
+  std::vector<double> v(h, h + static_cast<size_t>(m) * 4);
+  orc::shrink(v, dir, shrink_size, variant == POP_QUERY_FAKE);
+  std::copy(v.begin(), v.end(), h);
 }

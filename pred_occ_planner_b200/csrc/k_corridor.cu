@@ -17,6 +17,7 @@
 
 #include "pop_geom.cuh"
 #include "pop_lp.cuh"
+#include "pop_corridor_finish.cuh"
 
 namespace {
 
@@ -31,13 +32,6 @@ struct SegInfo {       // one path segment of one agent
   int j0, j1;
   int lx, ly, lz, hx, hy, hz;
 };
-
-__device__ __forceinline__ unsigned long long lp_seed(unsigned long long base, int segment, int kind) {
-  unsigned long long z = base * 0x9e3779b97f4a7c15ull + static_cast<unsigned long long>(segment) * 16 + kind + 1;
-  z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
-  z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
-  return z ^ (z >> 31);
-}
 
 __device__ __forceinline__ double dot3(const double* a, const double* b) { return (a[0] * b[0] + a[1] * b[1]) + a[2] * b[2]; }
 __device__ __forceinline__ double norm3(const double* a) { return sqrt(dot3(a, a)); }
@@ -701,14 +695,16 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_corridor_firi(
       __syncwarp();
     }
   }
-  // ShrinkCorridor(hPoly, path) (baseline_fake.cpp:215-228)
+  // ShrinkCorridor(hPoly, path): the simulator planner leaves front / back and top / bottom faces alone
+  // (baseline_fake.cpp:215-228); the real-perception planner shrinks every face (baseline.cpp:213-226)
   const double path[3] = {S.b[0] - S.a[0], S.b[1] - S.a[1], S.b[2] - S.a[2]};
+  const bool keep_end_faces = g.query_variant == POP_QUERY_FAKE;
   for (int i = lane; i < nH; i += 32) {
     double* h = W.hP[i];
     const double n3[3] = {h[0], h[1], h[2]}, z3[3] = {0, 0, 1};
     bool skip = false;
-    if (dot3(n3, path) / norm3(n3) / norm3(path) > 0.8) skip = true;
-    if (!skip && fabs(dot3(n3, z3)) / norm3(n3) > 0.8) skip = true;
+    if (keep_end_faces && dot3(n3, path) / norm3(n3) / norm3(path) > 0.8) skip = true;
+    if (keep_end_faces && !skip && fabs(dot3(n3, z3)) / norm3(n3) > 0.8) skip = true;
     if (!skip) h[3] += sqrt(h[0] * h[0] + h[1] * h[1] + h[2] * h[2]) * shrink_size;
   }
   __syncwarp();
@@ -725,10 +721,11 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_corridor_firi(
 // per-agent tail: cut at first invalid corridor, intersections, goal reachability
 // =================================================================================================
 __global__ void k_corridor_finish(const double* __restrict__ path, const int* __restrict__ len,
-                                  const double* __restrict__ start, int id_base, const double* __restrict__ seg_h,
-                                  const int* __restrict__ seg_rows, const int* __restrict__ seg_valid,
-                                  double* __restrict__ scr_all, int* __restrict__ scri_all,
-                                  int* __restrict__ out_npoly, double* __restrict__ out_goal, int a0, int n_agents) {
+                                  const double* __restrict__ start, int id_base, int variant,
+                                  const double* __restrict__ seg_h, const int* __restrict__ seg_rows,
+                                  const int* __restrict__ seg_valid, double* __restrict__ scr_all,
+                                  int* __restrict__ scri_all, int* __restrict__ out_npoly, double* __restrict__ out_goal,
+                                  int a0, int n_agents) {
   const int a = a0 + blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);   // n_agents = end of the range
   if (a >= n_agents || (threadIdx.x & 31) != 0) return;
   // reuse segment 0's scratch of this agent: holds up to kLpRows rows of LP workspace
@@ -736,79 +733,11 @@ __global__ void k_corridor_finish(const double* __restrict__ path, const int* __
   int* scri = scri_all + static_cast<size_t>(a) * POP_MAX_PIECES * kScrInts;
   double* lpw = scr + kScrLp;
   double* ab = scr + static_cast<size_t>(kScrDoubles);  // segment 1's scratch: 4 * kLpRows doubles fit
-  const unsigned long long seed_base = static_cast<unsigned long long>(id_base + a);
-  const int n = len[a];
-  const double* P = path + static_cast<size_t>(a) * POP_MAX_PATH * 6;
-  const double* H = seg_h + static_cast<size_t>(a) * POP_MAX_PIECES * POP_MAX_FACES * 4;
-  const int* rows = seg_rows + a * POP_MAX_PIECES;
-  int np = 0;
-  for (int i = 0; i < n - 1 && i < POP_MAX_PIECES; i++) {
-    if (!seg_valid[a * POP_MAX_PIECES + i]) break;
-    np++;
-  }
-  bool fail = false;
-  // adjacent corridors must intersect (baseline_fake.cpp:366-378)
-  for (int i = 0; i + 1 < np; i++) {
-    const int m0 = rows[i], m1 = rows[i + 1];
-    for (int k = 0; k < m0; k++) {
-      const double* h = H + (static_cast<size_t>(i) * POP_MAX_FACES + k) * 4;
-      for (int q = 0; q < 3; q++) ab[k * 4 + q] = h[q];
-      ab[k * 4 + 3] = -h[3];
-    }
-    for (int k = 0; k < m1; k++) {
-      const double* h = H + (static_cast<size_t>(i + 1) * POP_MAX_FACES + k) * 4;
-      for (int q = 0; q < 3; q++) ab[(m0 + k) * 4 + q] = h[q];
-      ab[(m0 + k) * 4 + 3] = -h[3];
-    }
-    const double c[3] = {0, 0, 0};
-    double x[3];
-    unsigned long long rng = lp_seed(seed_base, i, 2);
-    const double rst = poplp::linprog<3>(c, ab, 4, ab + 3, 4, m0 + m1, x, &rng, lpw, scri);
-    if (isinf(rst)) {
-      if (i < 2) { fail = true; break; }
-      np = i + 1;
-      break;
-    }
-  }
-  if (fail || np == 0) { out_npoly[a] = 0; return; }
-  const double* sp = start + a * 9;
-  int gi = np - 1;
-  double goal_pos[3] = {P[gi * 6], P[gi * 6 + 1], P[gi * 6 + 2]};
-  double goal_vel[3] = {P[gi * 6 + 3], P[gi * 6 + 4], P[gi * 6 + 5]};
-  for (int it = np - 1; it != 0; it--) {
-    // checkGoalReachability (baseline_fake.cpp:143-182)
-    const int m = rows[it];
-    const double* h = H + static_cast<size_t>(it) * POP_MAX_FACES * 4;
-    bool reachable;
-    if (m <= 0) reachable = true;
-    else {
-      double mx = -INFINITY;
-      for (int k = 0; k < m; k++) {
-        const double v = ((h[k * 4] * goal_pos[0] + h[k * 4 + 1] * goal_pos[1]) + h[k * 4 + 2] * goal_pos[2]) + h[k * 4 + 3] * 1.0;
-        mx = fmax(mx, v);
-      }
-      if (mx <= 0) reachable = true;
-      else {
-        for (int k = 0; k < m; k++) { for (int q = 0; q < 3; q++) ab[k * 4 + q] = h[k * 4 + q]; ab[k * 4 + 3] = -h[k * 4 + 3]; }
-        double c[3] = {-goal_pos[0] + sp[0], -goal_pos[1] + sp[1], -goal_pos[2] + sp[2]};
-        double gmax[3], gmin[3];
-        unsigned long long r1 = lp_seed(seed_base, it, 3), r2 = lp_seed(seed_base, it, 4);
-        poplp::linprog<3>(c, ab, 4, ab + 3, 4, m, gmax, &r1, lpw, scri);
-        for (int q = 0; q < 3; q++) c[q] = goal_pos[q] - sp[q];
-        poplp::linprog<3>(c, ab, 4, ab + 3, 4, m, gmin, &r2, lpw, scri);
-        for (int q = 0; q < 3; q++) goal_pos[q] = 0.5 * (gmax[q] + gmin[q]);
-        reachable = false;
-      }
-    }
-    if (reachable) {
-      np = it + 1;
-      const int idx = np - 1;
-      for (int q = 0; q < 3; q++) { goal_pos[q] = P[idx * 6 + q]; goal_vel[q] = P[idx * 6 + 3 + q]; }
-      break;
-    }
-  }
-  out_npoly[a] = np;
-  for (int q = 0; q < 3; q++) { out_goal[a * 6 + q] = goal_pos[q]; out_goal[a * 6 + 3 + q] = goal_vel[q]; }
+  out_npoly[a] = corridor_finish_agent(variant, static_cast<unsigned long long>(id_base + a), len[a],
+                                       path + static_cast<size_t>(a) * POP_MAX_PATH * 6,
+                                       seg_h + static_cast<size_t>(a) * POP_MAX_PIECES * POP_MAX_FACES * 4,
+                                       seg_rows + a * POP_MAX_PIECES, seg_valid + a * POP_MAX_PIECES, start + a * 9, ab,
+                                       lpw, scri, out_goal + a * 6);
 }
 
 }  // namespace
@@ -892,7 +821,7 @@ int popk_corridor_run(pop_handle* h, const double* d_path, const int* d_len, con
       h->geom, h->d_poses, d->segs, d->pts, d->cap, c.shrink_size, c.agent_id_base, d->distRs, d->tang, d->flags,
       d->scr, d->scri, d->seg_h, d->seg_rows, d->seg_valid, seg0, seg0 + ns, d->err);
   POP_LAUNCH_CHECK(h);
-  k_corridor_finish<<<(na + 3) / 4, 128, 0, st>>>(d_path, d_len, d_start, c.agent_id_base, d->seg_h,
+  k_corridor_finish<<<(na + 3) / 4, 128, 0, st>>>(d_path, d_len, d_start, c.agent_id_base, c.query_variant, d->seg_h,
                                                                  d->seg_rows, d->seg_valid, d->scr, d->scri, d->npoly,
                                                                  d->goal, a0, a0 + na);
   POP_LAUNCH_CHECK(h);

@@ -4,6 +4,8 @@ pred_occ_planner_b200/csrc/pop_lp.cuh (Seidel LP) and pop_corridor_finish.cuh (p
 intersection cut, minimum corridor count, goal search — for both planners of the reference, see the header) contain
 no thread indices or intrinsics, so tests/csrc/corridor_finish_host.cpp builds the SAME source with g++ and this file
 compares it with the oracle on seeded cases — bit for bit, since both sides draw the LP shuffles from the same LCG.
+pop_bezier.cuh uses CUDA's round-to-nearest intrinsics only; tests/csrc/bezier_host.cpp maps them to the plain
+operators and checks the evaluation against the reference's own outputs.
 It is how kernel-side logic gets exercised in `-m "not gpu"` runs; the GPU parity tests still go through the C ABI."""
 import ctypes as C
 import os
@@ -23,18 +25,52 @@ DP = C.POINTER(C.c_double)
 IP = C.POINTER(C.c_int32)
 
 
-@pytest.fixture(scope="module")
-def dev():
-    csrc = os.path.join(os.path.dirname(HERE), "pred_occ_planner_b200", "csrc")
-    deps = [SRC, os.path.join(csrc, "pop_lp.cuh"), os.path.join(csrc, "pop_corridor_finish.cuh")]
-    if not os.path.exists(OUT) or any(os.path.getmtime(d) > os.path.getmtime(OUT) for d in deps):
-        os.makedirs(os.path.dirname(OUT), exist_ok=True)
+CSRC = os.path.join(os.path.dirname(HERE), "pred_occ_planner_b200", "csrc")
+
+
+def _build(src, out, headers):
+    deps = [src] + [os.path.join(CSRC, h) for h in headers]
+    if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
+        os.makedirs(os.path.dirname(out), exist_ok=True)
         cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
         subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-Wl,--exclude-libs,ALL",
-                        "-I" + cuda_inc, "-o", OUT, SRC], check=True)
-    lib = C.CDLL(OUT)
+                        "-I" + cuda_inc, "-o", out, src], check=True)
+    return C.CDLL(out)
+
+
+@pytest.fixture(scope="module")
+def dev():
+    lib = _build(SRC, OUT, ["pop_lp.cuh", "pop_corridor_finish.cuh"])
     lib.dev_linprog.restype = C.c_double
     return lib
+
+
+@pytest.fixture(scope="module")
+def dev_bezier():
+    return _build(os.path.join(HERE, "csrc", "bezier_host.cpp"), os.path.join(HERE, "_build", "libdevbezier.so"),
+                  ["pop_bezier.cuh"])
+
+
+def test_device_bezier_source_against_reference_vectors(dev_bezier, oracle):
+    """pop_bezier.cuh (what the peer projection, the trajectory server and the separation check evaluate trajectories
+    with) compiled for the host, against the outputs of the reference's own bernstein.cpp (tests/golden/ref_pins.npz)
+    and against the oracle: 1e-14 relative, almost always identical (the device source raises s to integer powers
+    with an error-free product instead of pow())."""
+    gold = np.load(os.path.join(HERE, "golden", "ref_pins.npz"))
+    wants = rl.unpack(gold["bezier"], gold["bezier_offs"])
+    same = total = 0
+    for (dur, cp, t), want in zip(rl.bezier_cases(len(wants)), wants):
+        want = want.reshape(3, len(t), 3)
+        for d in (0, 1, 2):
+            out = np.zeros((len(t), 3))
+            dev_bezier.dev_bezier_eval(dur.ctypes.data_as(DP), len(dur), cp.ctypes.data_as(DP), t.ctypes.data_as(DP),
+                                       len(t), d, out.ctypes.data_as(DP))
+            assert np.abs(out - want[d]).max() <= 1e-14 * max(1.0, np.abs(want[d]).max())
+            ora = oracle.bezier_eval(dur, cp, t, deriv=d)
+            assert np.abs(out - ora).max() <= 1e-14 * max(1.0, np.abs(ora).max())
+            same += int(np.array_equal(out, want[d]))
+            total += 1
+    assert same >= 0.9 * total
 
 
 def test_device_lp_equals_oracle_lp(dev, oracle):

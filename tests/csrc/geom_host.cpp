@@ -1,0 +1,61 @@
+// geom_host.cpp — TEST INFRASTRUCTURE: the product's device grid geometry and occupancy query
+// (pred_occ_planner_b200/csrc/pop_geom.cuh: index math of map.h:153-215, getClearOcccupancy of
+// fake_particle_risk_voxel.cpp:309-330 / risk_base.cpp:228-250) compiled for the host.  CUDA's fp32 round-to-nearest
+// intrinsics are the plain operators on the host with contraction off; the atomics only have to compile (the query
+// path does not use them).
+#include <cmath>
+#include <cstdint>
+#include <cuda_runtime.h>
+
+static inline float __fadd_rn(float a, float b) { return a + b; }
+static inline float __fsub_rn(float a, float b) { return a - b; }
+static inline float __fmul_rn(float a, float b) { return a * b; }
+static inline float __fdiv_rn(float a, float b) { return a / b; }
+static inline unsigned atomicOr(unsigned* p, unsigned v) { unsigned o = *p; *p |= v; return o; }
+static inline unsigned atomicCAS(unsigned* p, unsigned c, unsigned v) { unsigned o = *p; if (o == c) *p = v; return o; }
+static inline float atomicExch(float* p, float v) { float o = *p; *p = v; return o; }
+static inline float atomicAdd(float* p, float v) { float o = *p; *p += v; return o; }
+
+#include "../../pred_occ_planner_b200/csrc/pop_geom.cuh"
+
+// PopGeom from the configuration, as derive_geometry does (pop_capi.cu:78-103)
+static PopGeom geom_of(const pop_config& c) {
+  PopGeom g{};
+  g.nx = c.nx; g.ny = c.ny; g.nz = c.nz; g.nt = c.nt;
+  g.V = c.nx * c.ny * c.nz;
+  g.res = c.resolution;
+  g.dt = c.time_resolution;
+  g.rx = static_cast<float>(c.nx / 2) * g.res;
+  g.ry = static_cast<float>(c.ny / 2) * g.res;
+  g.rz = static_cast<float>(c.nz / 2) * g.res;
+  g.risk_threshold = c.risk_threshold;
+  g.clearance = c.clearance;
+  g.ground = c.ground_height;
+  g.ceiling = c.ceiling_height;
+  g.thr_region = c.risk_threshold_region;
+  g.decay_region = c.risk_region_decay;
+  g.decay_voxel = c.risk_voxel_decay;
+  g.inf_step = static_cast<int>(c.clearance / c.resolution);
+  g.kernel_shape = c.kernel_shape;
+  g.query_variant = c.query_variant;
+  return g;
+}
+
+extern "C" {
+// grid: one agent's SOGM in the device layout [t][z][y][x] (u8 or f32 cells per cfg->cell_dtype)
+void dev_query(const pop_config* cfg, const void* grid, const float* pose, const double* pos, const int32_t* t, int n,
+               int8_t* out) {
+  const PopGeom g = geom_of(*cfg);
+  const uint8_t* base = static_cast<const uint8_t*>(grid);
+  for (int i = 0; i < n; i++)
+    out[i] = static_cast<int8_t>(cfg->cell_dtype == POP_CELL_U8
+                                     ? geom_query<uint8_t>(g, base, pose[0], pose[1], pose[2], pos[3 * i], pos[3 * i + 1], pos[3 * i + 2], t[i])
+                                     : geom_query<float>(g, base, pose[0], pose[1], pose[2], pos[3 * i], pos[3 * i + 1], pos[3 * i + 2], t[i]));
+}
+// voxel index of a map-frame point and the world position of a voxel (getVoxelIndex / getVoxelPosition)
+int dev_voxel_index(const pop_config* cfg, float x, float y, float z) { return geom_voxel_index(geom_of(*cfg), x, y, z); }
+float dev_axis_position(const pop_config* cfg, int i, int axis, float pose) {
+  const PopGeom g = geom_of(*cfg);
+  return geom_axis_position(i, axis == 0 ? g.rx : axis == 1 ? g.ry : g.rz, g.res, pose);
+}
+}

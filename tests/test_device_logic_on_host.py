@@ -5,7 +5,8 @@ intersection cut, minimum corridor count, goal search — for both planners of t
 no thread indices or intrinsics, so tests/csrc/corridor_finish_host.cpp builds the SAME source with g++ and this file
 compares it with the oracle on seeded cases — bit for bit, since both sides draw the LP shuffles from the same LCG.
 pop_bezier.cuh uses CUDA's round-to-nearest intrinsics only; tests/csrc/bezier_host.cpp maps them to the plain
-operators and checks the evaluation against the reference's own outputs.
+operators and checks the evaluation against the reference's own outputs; tests/csrc/geom_host.cpp does the same
+for pop_geom.cuh (voxel index math and the occupancy query that k_query runs and k_astar inlines).
 It is how kernel-side logic gets exercised in `-m "not gpu"` runs; the GPU parity tests still go through the C ABI."""
 import ctypes as C
 import os
@@ -177,3 +178,47 @@ def test_the_two_planners_differ_where_the_reference_does(dev):
     assert run(p.POP_QUERY_FAKE, 2)[0] == 1 and run(p.POP_QUERY_RISKBASE, 2)[0] == 0
     assert run(p.POP_QUERY_FAKE, 5)[0] == 3 and run(p.POP_QUERY_RISKBASE, 5)[0] == 2
     assert np.array_equal(run(p.POP_QUERY_FAKE, 5)[1][:3], pts[2]) and np.array_equal(run(p.POP_QUERY_RISKBASE, 5)[1][:3], pts[1])
+
+
+@pytest.fixture(scope="module")
+def dev_geom():
+    return _build(os.path.join(HERE, "csrc", "geom_host.cpp"), os.path.join(HERE, "_build", "libdevgeom.so"),
+                  ["pop_geom.cuh", "pop_internal.h"])
+
+
+@pytest.mark.parametrize("variant,kernel,clearance,cell", [
+    (p.POP_QUERY_FAKE, p.POP_KERNEL_DISC_Z0, 0.45, p.POP_CELL_F32),      # simulator map: 5 x 5 x 1 footprint
+    (p.POP_QUERY_FAKE, p.POP_KERNEL_DISC_Z0, 0.45, p.POP_CELL_U8),
+    (p.POP_QUERY_RISKBASE, p.POP_KERNEL_CUBE, 0.15, p.POP_CELL_F32),     # RiskBase: 3 x 3 x 3 cube, decaying threshold
+    (p.POP_QUERY_RISKBASE, p.POP_KERNEL_CUBE, 0.3, p.POP_CELL_F32),      # 5 x 5 x 5
+    (p.POP_QUERY_FAKE, p.POP_KERNEL_DISC_Z0, 0.6, p.POP_CELL_U8),        # a footprint without a specialised plane sum
+])
+def test_device_query_source_equals_oracle(dev_geom, oracle, variant, kernel, clearance, cell):
+    """geom_query (what k_query runs and k_astar inlines) on the host, on a grid built by the oracle from a world with
+    moving cylinders: every answer equal — inside, on the borders, outside the box, below ground, above the ceiling,
+    at every slice."""
+    cfg, (cloud, cyl) = rl.astar_world()
+    cfg.query_variant, cfg.kernel_shape, cfg.clearance, cfg.cell_dtype = variant, kernel, clearance, cell
+    if variant == p.POP_QUERY_RISKBASE:
+        cfg.risk_threshold_region, cfg.risk_region_decay = 0.9, 0.05
+    rng = np.random.default_rng(11)
+    for k in range(3):
+        pose = np.array([rng.uniform(-3, 3), rng.uniform(-3, 3), 1.0 + 0.1 * k], np.float32)
+        m = oracle.map(cfg)
+        m.set_pose(pose)
+        m.update_gt(cloud, cyl, 0.0)
+        risk = m.risk_maps()                                             # [V][T]
+        grid = np.ascontiguousarray(risk.T)                              # device layout [t][z][y][x]
+        if cell == p.POP_CELL_U8:
+            assert np.isin(risk, (0.0, 1.0)).all()
+            grid = grid.astype(np.uint8)
+        n = 20000
+        pos = pose.astype(np.float64) + rng.uniform(-5.6, 5.6, (n, 3)) * [1, 1, 0.4]
+        pos[::50, 2] = rng.uniform(-1, 5, len(pos[::50]))                # below ground / above the ceiling
+        t = rng.integers(0, cfg.nt, n).astype(np.int32)
+        got = np.zeros(n, np.int8)
+        dev_geom.dev_query(C.byref(cfg), grid.ctypes.data_as(C.c_void_p), pose.ctypes.data_as(C.POINTER(C.c_float)),
+                           pos.ctypes.data_as(DP), t.ctypes.data_as(IP), n, got.ctypes.data_as(C.POINTER(C.c_int8)))
+        want = m.query(pos, t)
+        assert np.array_equal(got, want), np.flatnonzero(got != want)[:5]
+        assert (want == 1).sum() > 50 and (want == 0).sum() > 1000 and ((want == -1).sum() > 100 or variant)

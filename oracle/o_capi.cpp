@@ -49,6 +49,24 @@ void orc_map_add_other_agents(void* h, const double* offs, const int32_t* counts
   Swarm s = make_swarm(m->cfg, offs, counts, recs);
   add_other_agents(m->grid, s, ego_id);
 }
+// getParticlesWithRisk(idx_agent, t0) of drone ego_id's coordinator for nq queries (tests/test_ref_pins.py compares it
+// with the reference's ParticleATC): out_n[q] = -1 when it returns false, else the particle count
+void orc_particles_with_risk(const pop_config* cfg, int ego_id, const double* offs, const int32_t* counts,
+                             const pop_traj_record* recs, int nq, const int32_t* q_agent, const double* q_t0,
+                             double* out_pts, float* out_risks, int cap, int32_t* out_n) {
+  Swarm s = make_swarm(*cfg, offs, counts, recs);
+  for (int q = 0; q < nq; q++) {
+    std::vector<V3d> pts;
+    std::vector<float> risks;
+    const bool ok = particles_with_risk(s, ego_id, q_agent[q], q_t0[q], pts, risks);
+    out_n[q] = ok ? static_cast<int32_t>(pts.size()) : -1;
+    for (int i = 0; ok && i < static_cast<int>(pts.size()) && i < cap; i++) {
+      double* o = out_pts + (static_cast<size_t>(q) * cap + i) * 3;
+      o[0] = pts[i].x; o[1] = pts[i].y; o[2] = pts[i].z;
+      out_risks[static_cast<size_t>(q) * cap + i] = risks[i];
+    }
+  }
+}
 void orc_map_add_particles(void* h, const double* pts, const float* risks, int n, int t) {
   add_particles(static_cast<OrcMap*>(h)->grid, reinterpret_cast<const V3d*>(pts), risks, n, t);
 }
@@ -211,6 +229,19 @@ int orc_qp_solve(const pop_config* cfg, int M, const double* init9, const double
   return r.status;
 }
 
+// the point sets isSafeAfterOpt would hand to the separator, per active peer: |A|, |B|, B's points; returns the LP count
+int orc_safe_after_opt_sets(const pop_config* cfg, const double* offs, const int32_t* counts, const pop_traj_record* recs,
+                            int ego_id, const double* cpts, int M, double t0, double* out, int cap) {
+  Swarm s = make_swarm(*cfg, offs, counts, recs);
+  std::vector<double> trace;
+  g_sep_trace = &trace;
+  safe_after_opt(s, ego_id, std::vector<double>(cpts, cpts + 15 * M), M, t0);
+  g_sep_trace = nullptr;
+  int lps = 0;
+  for (size_t i = 0; i < trace.size();) { lps++; i += 2 + 3 * static_cast<size_t>(trace[i + 1]); }
+  for (size_t i = 0; i < trace.size() && static_cast<int>(i) < cap; i++) out[i] = trace[i];
+  return lps;
+}
 int orc_separable(const double* A, int na, const double* B, int nb) {
   std::vector<V3d> a(na), b(nb);
   for (int i = 0; i < na; i++) a[i] = V3d{A[3 * i], A[3 * i + 1], A[3 * i + 2]};

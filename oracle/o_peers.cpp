@@ -1,8 +1,10 @@
 // o_peers.cpp — oracle: peer-trajectory particles projected into the SOGM (TEST INFRASTRUCTURE).
 // Follows traj_coordinator/src/particles.cpp:62-87,291-422 and
 // plan_env/src/fake_particle_risk_voxel.cpp:175-218 of the reference.
-// PARITY UNPINNED: particles.cpp needs ROS message types and GLPK; checked by property tests only
-// (tests/test_oracle_map.py); its Bezier evaluation is the pinned one of o_bezier.cpp.
+// ego_particles and particles_with_risk are PINNED against the reference's own particles.cpp compiled into
+// oracle/_ref/libref.so (ROS, the two message types and the GLPK separator replaced by stand-ins): validity, points
+// and risks identical (tests/test_ref_pins.py).  add_other_agents (the deposit into the grid,
+// fake_particle_risk_voxel.cpp) remains PARITY UNPINNED; property tests in tests/test_oracle_map.py.
 #include "oracle.hpp"
 
 namespace orc {

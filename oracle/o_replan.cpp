@@ -8,6 +8,8 @@
 
 namespace orc {
 
+std::vector<double>* g_sep_trace = nullptr;
+
 // isSafeAfterOpt: ego control points vs every active peer's remaining control points
 bool safe_after_opt(const Swarm& s, int ego_id, const std::vector<double>& cpts, int M, double t0) {
   std::vector<V3d> A;
@@ -26,6 +28,12 @@ bool safe_after_opt(const Swarm& s, int ego_id, const std::vector<double>& cpts,
       }
       std::vector<V3d> B;
       for (int i = piece * 5; i < r.n_pieces * 5; i++) B.push_back(V3d{r.cpts[i * 3], r.cpts[i * 3 + 1], r.cpts[i * 3 + 2]});
+      if (g_sep_trace) {   // test hook: the point sets instead of the LP (see orc_safe_after_opt_sets)
+        g_sep_trace->push_back(static_cast<double>(A.size()));
+        g_sep_trace->push_back(static_cast<double>(B.size()));
+        for (const V3d& p : B) { g_sep_trace->push_back(p.x); g_sep_trace->push_back(p.y); g_sep_trace->push_back(p.z); }
+        continue;
+      }
       if (!separable(A, B)) return false;
     }
   }

@@ -1,5 +1,6 @@
-// ros/ros.h — a STAND-IN for the slice of roscpp that path_searching's headers and fake_risk_hybrid_a_star.cpp touch:
-// NodeHandle::param (parameter lookup with a default) and the ROS_* logging macros (discarded).  TEST INFRASTRUCTURE
+// ros/ros.h — a STAND-IN for the slice of roscpp that path_searching's and traj_coordinator's sources touch:
+// NodeHandle::param (parameter lookup with a default), inert subscribe / advertise / createTimer, ros::Time with a
+// settable now(), and the ROS_* logging macros (discarded).  TEST INFRASTRUCTURE
 // (oracle/_ref only); ROS itself is absent from this image.
 #ifndef POP_ROS_STANDIN_H
 #define POP_ROS_STANDIN_H
@@ -7,6 +8,33 @@
 #include <string>
 
 namespace ros {
+// time: now() is whatever the test set (ros::Time::set_now), so the reference's wall-clock reads are inputs
+class Time {
+ public:
+  double sec_ = 0.0;
+  Time() {}
+  explicit Time(double s) : sec_(s) {}
+  double toSec() const { return sec_; }
+  static double& now_value() { static double v = 0.0; return v; }
+  static void set_now(double s) { now_value() = s; }
+  static Time now() { return Time(now_value()); }
+};
+class Duration {
+ public:
+  double sec_ = 0.0;
+  Duration() {}
+  explicit Duration(double s) : sec_(s) {}
+  double toSec() const { return sec_; }
+};
+struct TimerEvent {};
+struct TransportHints { TransportHints& tcpNoDelay() { return *this; } };
+class Subscriber {};
+class Timer {};
+class Publisher {
+ public:
+  template <class M> void publish(const M&) const {}
+};
+
 class NodeHandle {
  public:
   std::map<std::string, double> values;
@@ -17,6 +45,10 @@ class NodeHandle {
     var = static_cast<T>(it->second);
     return true;
   }
+  // topics and timers are never driven: the tests call the callbacks directly
+  template <class... A> Subscriber subscribe(const std::string&, int, A&&...) { return Subscriber(); }
+  template <class M> Publisher advertise(const std::string&, int) { return Publisher(); }
+  template <class... A> Timer createTimer(Duration, A&&...) { return Timer(); }
 };
 }  // namespace ros
 

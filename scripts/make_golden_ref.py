@@ -1,5 +1,5 @@
 """Regenerates tests/golden/ref_pins.npz: outputs of the REFERENCE's own code (oracle/_ref/libref.so =
-plan_env/src/raycast.cpp, traj_utils/sdlp.hpp, sfc_gen/lbfgs.hpp, sfc_gen/firi.hpp, traj_utils/src/bernstein.cpp, traj_opt/src/bezier_optimizer.cpp, path_searching/src/{fake_,}risk_hybrid_a_star.cpp compiled unmodified from
+plan_env/src/raycast.cpp, traj_utils/sdlp.hpp, sfc_gen/lbfgs.hpp, sfc_gen/firi.hpp, traj_utils/src/bernstein.cpp, traj_opt/src/bezier_optimizer.cpp, path_searching/src/{fake_,}risk_hybrid_a_star.cpp, traj_coordinator/src/particles.cpp compiled unmodified from
 /root/reference; see oracle/Makefile) on the seeded cases of tests/ref_lib.py.  tests/test_ref_pins.py checks the
 oracle against these vectors wherever the library itself is not available.  Needs /root/reference.
 
@@ -76,6 +76,14 @@ def main():
             heads.append([ret, st[0], st[1], st[2]])
         out[key + "_path"], out[key + "_offs"] = rl.pack(paths)
         out[key + "_head"] = np.array(heads, np.int32)
+    cfg, size, ego, offs, counts, recs, qa, qt = rl.peer_case()
+    out["peer_ego"] = ref.ego_particles(size)
+    pts, rk, on = ref.particles_with_risk(cfg.n_agents_total, ego, size, offs, counts, recs, 10.0, qa, qt)
+    out["peer_pts"], out["peer_risks"], out["peer_n"] = pts, rk, on
+    cpts, dur, M, nows = rl.sep_case()
+    sets = [rl.ref_sep_sets(ref, cfg.n_agents_total, ego, size, offs, counts, recs, now, cpts, dur, M) for now in nows]
+    out["sep_n"] = np.array([s[0] for s in sets], np.int32)
+    out["sep_sets"] = np.stack([s[1] for s in sets])
     path = os.path.join(ROOT, "tests", "golden", "ref_pins.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path), "bytes")

@@ -113,6 +113,65 @@ class RefLib:
         return ret, out[:n.value].copy(), st
 
 
+    def ego_particles(self, size):
+        size = np.ascontiguousarray(size, np.float64)
+        out = np.zeros((64, 3))
+        n = self.lib.ref_ego_particles(P(size), P(out), 64)
+        return out[:n].copy()
+
+    def particles_with_risk(self, n, ego, size, offs, counts, recs, now, q_agent, q_t0):
+        """ParticleATC of drone `ego` after receiving the peers' body particles and trajectories:
+        getParticlesWithRisk for every (agent, t0) query -> (points nq x cap x 3, risks, counts; -1 = false)."""
+        return peer_queries(self.lib.ref_particles_with_risk, (n, ego, P(np.ascontiguousarray(size, np.float64)), C.c_float(0.0),
+                            P(offs), offs.shape[1], counts.ctypes.data_as(C.POINTER(C.c_int32)),
+                            C.c_void_p(recs.ctypes.data), D(now)), offs.shape[1], q_agent, q_t0)
+
+
+def sep_sets(fn, pre, post, cap=4096):
+    """(number of separating-plane LPs, flat record |A|, |B|, B's points per LP) of one isSafeAfterOpt."""
+    out = np.zeros(cap)
+    n = fn(*pre, *post, P(out), cap)
+    return n, out
+
+
+def sep_case(seed=13, M=5):
+    rng = np.random.default_rng(seed)
+    return np.ascontiguousarray(rng.normal(size=(5 * M, 3))), np.full(M, 0.3), M, (9.0, 10.2, 10.95, 11.5, 12.5)
+
+
+def ref_sep_sets(ref, n, ego, size, offs, counts, recs, now, cpts, dur, M):
+    return sep_sets(ref.lib.ref_safe_after_opt_sets,
+                    (n, ego, P(np.ascontiguousarray(size, np.float64)), P(offs), offs.shape[1],
+                     counts.ctypes.data_as(C.POINTER(C.c_int32)), C.c_void_p(recs.ctypes.data), D(now)),
+                    (P(cpts), P(dur), M))
+
+
+def peer_queries(fn, pre, cap, q_agent, q_t0):
+    nq = len(q_agent)
+    pts, rk, on = np.zeros((nq, cap, 3)), np.zeros((nq, cap), np.float32), np.zeros(nq, np.int32)
+    fn(*pre, nq, q_agent.ctypes.data_as(C.POINTER(C.c_int32)), P(q_t0), P(pts), rk.ctypes.data_as(C.POINTER(C.c_float)), cap,
+       on.ctypes.data_as(C.POINTER(C.c_int32)))
+    return pts, rk, on
+
+
+def peer_case(seed=3, n=8, ego=2, nq=300):
+    """A swarm of n drones on straight Bezier trajectories from t = 10 s: one has not published, one starts later;
+    queries (agent, time) before, during and after the trajectories, the ego drone included."""
+    import pred_occ_planner_b200 as p
+    from pred_occ_planner_b200 import worldgen
+    from tests import cases
+    cfg = cases.cfg_c1(p.POP_CELL_F32, n_local=1, n_total=n)
+    size = np.array(list(cfg.drone_size), np.float64)
+    rng = np.random.default_rng(seed)
+    trajs = worldgen.straight_trajs(rng.uniform(-4, 4, (n, 3)), rng.uniform(-4, 4, (n, 3)), 10.0, 1.5, 6, 0.3)
+    trajs["n_pieces"][5] = 0
+    trajs["start_time"][6] = 10.9
+    offs, counts = worldgen.body_table(n, size, ego_id=ego)
+    q_agent = rng.integers(0, n, nq).astype(np.int32)
+    q_t0 = rng.uniform(9.5, 13.0, nq)
+    return cfg, size, ego, offs, counts, np.ascontiguousarray(trajs), q_agent, q_t0
+
+
 _ref = False
 
 

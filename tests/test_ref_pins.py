@@ -2,7 +2,7 @@
 
 `oracle/_ref/libref.so` is the reference's plan_env/src/raycast.cpp, traj_utils/sdlp.hpp, sfc_gen/lbfgs.hpp,
 sfc_gen/firi.hpp, traj_utils/src/bernstein.cpp, traj_opt/src/bezier_optimizer.cpp and
-path_searching/src/fake_risk_hybrid_a_star.cpp compiled unmodified (oracle/Makefile; Eigen replaced by the stand-in
+path_searching/src/{fake_,}risk_hybrid_a_star.cpp, traj_coordinator/src/particles.cpp compiled unmodified (oracle/Makefile; Eigen replaced by the stand-in
 oracle/ref_build/Eigen/Eigen, the OSQP wrapper by a recorder, ROS and the map class by minimal stand-ins).
 Every test runs the oracle's restatement on seeded cases and compares it with
 
@@ -244,3 +244,46 @@ def test_hybrid_astar_identical(oracle, ref, gold, risk):
             m.update_gt(cloud, cyl, 0.0)
             a, b = ref.astar(cfg, m, pose, start, goal, t0, risk=risk), m.astar(start, goal, t0, cap=256)
             assert a[0] == b[0] and np.array_equal(a[1], b[1]) and np.array_equal(a[2][:3], b[2][:3])
+
+
+# ---- ParticleATC (traj_coordinator/src/particles.cpp:62-87, 131-191, 291-422) ---------------------------------------
+def test_peer_particles_identical(oracle, ref, gold):
+    """The swarm coordinator's side of the peer projection: body particles (own: exact, peers': float32 on the wire),
+    trajectories as received, and for every (peer, time) the particles getParticlesWithRisk hands to the map — with
+    its rules for a peer that has not published, has not started, has finished, or is the ego drone.  Identical."""
+    import ctypes as C
+    cfg, size, ego, offs, counts, recs, qa, qt = rl.peer_case()
+    ego_pts = np.zeros((64, 3))
+    n = oracle.lib.orc_ego_particles(rl.P(size), rl.P(ego_pts), 64)
+    assert np.array_equal(ego_pts[:n], gold["peer_ego"])
+    got = rl.peer_queries(oracle.lib.orc_particles_with_risk,
+                          (C.byref(cfg), ego, rl.P(offs), counts.ctypes.data_as(C.POINTER(C.c_int32)), C.c_void_p(recs.ctypes.data)),
+                          offs.shape[1], qa, qt)
+    assert np.array_equal(got[2], gold["peer_n"]) and np.array_equal(got[0], gold["peer_pts"])
+    assert np.array_equal(got[1], gold["peer_risks"])
+    assert (got[2] > 0).sum() > 50 and (got[2] < 0).sum() > 50
+    if ref is not None:
+        cfg, size, ego, offs, counts, recs, qa, qt = rl.peer_case(seed=59, n=10, ego=7, nq=500)
+        a = ref.particles_with_risk(10, ego, size, offs, counts, recs, 10.0, qa, qt)
+        b = rl.peer_queries(oracle.lib.orc_particles_with_risk,
+                            (C.byref(cfg), ego, rl.P(offs), counts.ctypes.data_as(C.POINTER(C.c_int32)), C.c_void_p(recs.ctypes.data)),
+                            offs.shape[1], qa, qt)
+        assert all(np.array_equal(x, y) for x, y in zip(a, b))
+
+
+def test_separation_check_point_sets_identical(oracle, ref, gold):
+    """isSafeAfterOpt up to the LP (the GLPK solver is absent): which peers are checked at a given time and which of
+    their control points are left — identical.  The LP itself: tests/test_golden_reference.py (the reference's own
+    separable sets) and tests/test_oracle_corridor_qp.py."""
+    import ctypes as C
+    cfg, size, ego, offs, counts, recs, qa, qt = rl.peer_case()
+    cpts, dur, M, nows = rl.sep_case()
+    for k, now in enumerate(nows):
+        n, sets = rl.sep_sets(oracle.lib.orc_safe_after_opt_sets,
+                              (C.byref(cfg), rl.P(offs), counts.ctypes.data_as(C.POINTER(C.c_int32)), C.c_void_p(recs.ctypes.data),
+                               ego, rl.P(cpts), M, rl.D(now)), ())
+        assert n == gold["sep_n"][k] and np.array_equal(sets, gold["sep_sets"][k])
+        if ref is not None:
+            r = rl.ref_sep_sets(ref, cfg.n_agents_total, ego, size, offs, counts, recs, now, cpts, dur, M)
+            assert r[0] == n and np.array_equal(r[1], sets)
+    assert gold["sep_n"].max() >= 5 and gold["sep_n"].min() == 0

@@ -1,8 +1,7 @@
 // ref_glue.cpp — C entry points into the REFERENCE's own code (TEST INFRASTRUCTURE; builds oracle/_ref/libref.so).
 //
-// Compiled together with /root/reference/plan_env/src/raycast.cpp, traj_utils/src/bernstein.cpp,
-// traj_opt/src/bezier_optimizer.cpp, path_searching/src/fake_risk_hybrid_a_star.cpp and the reference headers
-// plan_manager/include/sfc_gen/{firi,lbfgs}.hpp and traj_utils/include/traj_utils/sdlp.hpp — unmodified, from where
+// Compiled together with the reference files listed in oracle/Makefile (raycast.cpp, bernstein.cpp, bezier_optimizer.cpp,
+// both hybrid A* sources, particles.cpp, and the headers firi.hpp / lbfgs.hpp / sdlp.hpp) — unmodified, from where
 // they lie — against oracle/ref_build/Eigen/Eigen (a stand-in for the absent Eigen; see that file for what it does
 // and does not reproduce).  Nothing here restates reference arithmetic: each function only marshals flat arrays
 // into the reference's argument types and back.  Used by tests/test_ref_pins.py to pin oracle/o_gridmap.cpp's

@@ -242,6 +242,24 @@ int orc_safe_after_opt_sets(const pop_config* cfg, const double* offs, const int
   for (size_t i = 0; i < trace.size() && static_cast<int>(i) < cap; i++) out[i] = trace[i];
   return lps;
 }
+// the ADMM solver alone on a dense problem  min 1/2 x'Qx  s.t. l <= Ax <= u  (what IOSQP::setMats hands to OSQP);
+// lets the reference's own planner, compiled into oracle/_ref/libref.so, run end to end (ref_glue_planner.cpp)
+int orc_osqp_dense(const pop_config* cfg, int n, int m, const double* Q, const double* A, const double* l, const double* u,
+                   double* x, int* iters) {
+  QpProblem p;
+  p.n = n; p.m = m;
+  p.Q.assign(Q, Q + static_cast<size_t>(n) * n);
+  p.A.assign(A, A + static_cast<size_t>(m) * n);
+  p.l.assign(l, l + m);
+  p.u.assign(u, u + m);
+  OsqpSettings S;
+  S.eps_abs = cfg->osqp_eps_abs; S.eps_rel = cfg->osqp_eps_rel; S.max_iter = cfg->osqp_max_iter;
+  S.check_termination = cfg->osqp_check_termination; S.adaptive_rho_interval = cfg->osqp_adaptive_rho_interval;
+  OsqpResult r = osqp_solve(p, S);
+  for (int i = 0; i < n; i++) x[i] = r.x[i];
+  if (iters) *iters = r.iters;
+  return r.status;
+}
 int orc_separable(const double* A, int na, const double* B, int nb) {
   std::vector<V3d> a(na), b(nb);
   for (int i = 0; i < na; i++) a[i] = V3d{A[3 * i], A[3 * i + 1], A[3 * i + 2]};

@@ -26,6 +26,8 @@ class Duration {
   explicit Duration(double s) : sec_(s) {}
   double toSec() const { return sec_; }
 };
+inline Duration operator-(const Time& a, const Time& b) { return Duration(a.sec_ - b.sec_); }
+inline Time operator+(const Time& a, const Duration& d) { return Time(a.sec_ + d.sec_); }
 struct TimerEvent {};
 struct TransportHints { TransportHints& tcpNoDelay() { return *this; } };
 class Subscriber {};
@@ -42,6 +44,13 @@ class NodeHandle {
   bool param(const std::string& name, T& var, const T& dflt) const {
     auto it = values.find(name);
     if (it == values.end()) { var = dflt; return false; }
+    var = static_cast<T>(it->second);
+    return true;
+  }
+  template <class T>
+  bool getParam(const std::string& name, T& var) const {
+    auto it = values.find(name);
+    if (it == values.end()) return false;
     var = static_cast<T>(it->second);
     return true;
   }

@@ -45,7 +45,7 @@ int ref_ego_particles(const double* size, double* out, int cap) {
   return static_cast<int>(p.size());
 }
 
-static void feed(ParticleATC& atc, int n, int ego_id, const double* offs, int max_body, const int32_t* counts,
+void ref_feed_atc(ParticleATC& atc, int n, int ego_id, const double* offs, int max_body, const int32_t* counts,
                  const pop_traj_record* recs, double now) {
   for (int i = 0; i < n; i++) {
     if (i == ego_id) continue;
@@ -92,7 +92,7 @@ void ref_particles_with_risk(int n, int ego_id, const double* size, float replan
   nh.values["swarm/replan_risk_rate"] = replan_risk_rate;
   ParticleATC atc(nh);
   atc.init();
-  feed(atc, n, ego_id, offs, max_body, counts, recs, now);
+  ref_feed_atc(atc, n, ego_id, offs, max_body, counts, recs, now);
   for (int q = 0; q < nq; q++) {
     std::vector<Eigen::Vector3d> pts;
     std::vector<float> risks;
@@ -121,7 +121,7 @@ int ref_safe_after_opt_sets(int n, int ego_id, const double* size, const double*
   nh.values["swarm/drone_size_x"] = size[0]; nh.values["swarm/drone_size_y"] = size[1]; nh.values["swarm/drone_size_z"] = size[2];
   ParticleATC atc(nh);
   atc.init();
-  feed(atc, n, ego_id, offs, max_body, counts, recs, now);
+  ref_feed_atc(atc, n, ego_id, offs, max_body, counts, recs, now);
   Eigen::MatrixX3d c(5 * M, 3);
   for (int i = 0; i < 5 * M; i++) for (int k = 0; k < 3; k++) c(i, k) = cpts[3 * i + k];
   Bernstein::Bezier traj(std::vector<double>(dur, dur + M), c);

@@ -1,5 +1,5 @@
 """Regenerates tests/golden/ref_pins.npz: outputs of the REFERENCE's own code (oracle/_ref/libref.so =
-plan_env/src/raycast.cpp, traj_utils/sdlp.hpp, sfc_gen/lbfgs.hpp, sfc_gen/firi.hpp, traj_utils/src/bernstein.cpp, traj_opt/src/bezier_optimizer.cpp, path_searching/src/{fake_,}risk_hybrid_a_star.cpp, traj_coordinator/src/particles.cpp compiled unmodified from
+plan_env/src/raycast.cpp, traj_utils/sdlp.hpp, sfc_gen/lbfgs.hpp, sfc_gen/firi.hpp, traj_utils/src/bernstein.cpp, traj_opt/src/bezier_optimizer.cpp, path_searching/src/{fake_,}risk_hybrid_a_star.cpp, traj_coordinator/src/particles.cpp, plan_manager/src/baseline_fake.cpp compiled unmodified from
 /root/reference; see oracle/Makefile) on the seeded cases of tests/ref_lib.py.  tests/test_ref_pins.py checks the
 oracle against these vectors wherever the library itself is not available.  Needs /root/reference.
 
@@ -13,7 +13,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-N_RAYS, N_LP, N_COST, N_LBFGS, N_MVIE, N_FIRI, N_BEZ, N_QP, N_ASTAR = 300, 200, 60, 40, 40, 45, 40, 12, 40
+N_RAYS, N_LP, N_COST, N_LBFGS, N_MVIE, N_FIRI, N_BEZ, N_QP, N_ASTAR, N_REPLAN = 300, 200, 60, 40, 40, 45, 40, 12, 40, 30
 
 
 def main():
@@ -76,6 +76,18 @@ def main():
             heads.append([ret, st[0], st[1], st[2]])
         out[key + "_path"], out[key + "_offs"] = rl.pack(paths)
         out[key + "_head"] = np.array(heads, np.int32)
+    cfg, (cloud, cyl) = rl.astar_world()
+    heads, cps = [], []
+    for pose, start, goal, ts in rl.astar_cases(N_REPLAN, seed=67):
+        m = orc.map(cfg)
+        m.set_pose(pose)
+        m.update_gt(cloud, cyl, 0.0)
+        m.set_time(100.0)
+        ok, M, cp, st = ref.replan(cfg, m, pose, 100.0, 100.0 + ts, start, goal)
+        heads.append([ok, M, st[0], st[1], st[3]])
+        cps.append(cp)
+    out["replan_head"] = np.array(heads, np.int32)
+    out["replan_cpts"], out["replan_offs"] = rl.pack(cps)
     cfg, size, ego, offs, counts, recs, qa, qt = rl.peer_case()
     out["peer_ego"] = ref.ego_particles(size)
     pts, rk, on = ref.particles_with_risk(cfg.n_agents_total, ego, size, offs, counts, recs, 10.0, qa, qt)

@@ -113,6 +113,21 @@ class RefLib:
         return ret, out[:n.value].copy(), st
 
 
+    def replan(self, cfg, omap, pose, t_map, t_plan, start9, goal3):
+        """The reference's FakeBaselinePlanner::replan on the oracle map `omap` (queries and obstacle points answered by
+        liboracle, the OSQP solve behind IOSQP by the oracle's ADMM): (ok, pieces, control points 5M x 3, stats =
+        A* iterations, A* nodes, pieces, QP iterations)."""
+        from tests import oracle_lib
+        ol = oracle_lib.load().lib
+        fns = [C.cast(f, C.c_void_p) for f in (ol.orc_map_query_dt, ol.orc_map_obstacle_points, ol.orc_osqp_dense)]
+        pose = np.ascontiguousarray(pose, np.float32)
+        start9, goal3 = np.ascontiguousarray(start9, np.float64), np.ascontiguousarray(goal3, np.float64)
+        M, dur, cp, st = C.c_int(0), np.zeros(16), np.zeros((80, 3)), np.zeros(4, np.int32)
+        ok = self.lib.ref_replan(C.byref(cfg), *fns, omap.h, pose.ctypes.data_as(C.POINTER(C.c_float)), D(t_map), None, None,
+                                 None, D(t_plan), D(t_plan), P(start9), P(goal3), C.byref(M), P(dur), P(cp),
+                                 st.ctypes.data_as(C.POINTER(C.c_int32)))
+        return ok, M.value, cp[:5 * M.value].copy(), st
+
     def ego_particles(self, size):
         size = np.ascontiguousarray(size, np.float64)
         out = np.zeros((64, 3))

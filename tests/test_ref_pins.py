@@ -287,3 +287,46 @@ def test_separation_check_point_sets_identical(oracle, ref, gold):
             r = rl.ref_sep_sets(ref, cfg.n_agents_total, ego, size, offs, counts, recs, now, cpts, dur, M)
             assert r[0] == n and np.array_equal(r[1], sets)
     assert gold["sep_n"].max() >= 5 and gold["sep_n"].min() == 0
+
+
+# ---- FakeBaselinePlanner::replan (plan_manager/src/baseline_fake.cpp:265-453) ----------------------------------------
+def test_whole_replan_against_the_reference_planner(oracle, ref, gold):
+    """The reference's planner end to end — its own A*, corridor stage (bounding boxes, obstacle points per segment, FIRI,
+    shrink, validity / intersection / goal LPs), QP assembly and trajectory hand-over — run on the oracle's grid with the
+    oracle's ADMM behind its solver wrapper, against the oracle's replan on 30 problems with moving obstacles: the same
+    replans succeed and fail, with the same number of A* expansions and trajectory pieces; control points agree to the
+    solver's own tolerance (eps 1e-3; FIRI's ellipsoid step stops L-BFGS on a 1e-7 cost decrease, so corridor faces of
+    two correct runs differ by ~1e-4 and the QP optimum moves with them) — median below 1e-4."""
+    from tests import oracle_cycle
+    cfg, (cloud, cyl) = rl.astar_world()
+    heads = gold["replan_head"]
+    wants = rl.unpack(gold["replan_cpts"], gold["replan_offs"], 3)
+    rel, n_ok = [], 0
+    for (pose, start, goal, ts), head, want in zip(rl.astar_cases(len(heads), seed=67), heads, wants):
+        m = oracle.map(cfg)
+        m.set_pose(pose)
+        m.update_gt(cloud, cyl, 0.0)
+        m.set_time(100.0)
+        rs, rec, st = oracle_cycle.replan(m, None, 0, start, goal, 100.0 + ts)
+        assert (rs == 0) == bool(head[0]), (rs, head.tolist())
+        assert st[1] == head[2]                                        # A* expansions
+        if rs == 0:
+            M = int(rec["n_pieces"])
+            assert M == head[1]
+            got = np.asarray(rec["cpts"]).reshape(-1, 3)[:5 * M]
+            rel.append(np.abs(got - want).max() / max(1.0, np.abs(want).max()))
+            n_ok += 1
+    assert n_ok >= 10 and max(rel) < 1e-2 and np.median(rel) < 1e-4, (n_ok, max(rel), np.median(rel))
+    if ref is not None:
+        for pose, start, goal, ts in rl.astar_cases(15, seed=73):
+            m = oracle.map(cfg)
+            m.set_pose(pose)
+            m.update_gt(cloud, cyl, 0.0)
+            m.set_time(100.0)
+            ok, M, cp, st = ref.replan(cfg, m, pose, 100.0, 100.0 + ts, start, goal)
+            rs, rec, so = oracle_cycle.replan(m, None, 0, start, goal, 100.0 + ts)
+            assert (rs == 0) == bool(ok) and so[1] == st[0]
+            if ok:
+                assert int(rec["n_pieces"]) == M
+                got = np.asarray(rec["cpts"]).reshape(-1, 3)[:5 * M]
+                assert np.abs(got - cp).max() <= 1e-2 * max(1.0, np.abs(cp).max())

@@ -1,5 +1,5 @@
 """Regenerates tests/golden/ref_pins.npz: outputs of the REFERENCE's own code (oracle/_ref/libref.so =
-plan_env/src/raycast.cpp, traj_utils/sdlp.hpp, sfc_gen/lbfgs.hpp, sfc_gen/firi.hpp, traj_utils/src/bernstein.cpp, traj_opt/src/bezier_optimizer.cpp, path_searching/src/{fake_,}risk_hybrid_a_star.cpp, traj_coordinator/src/particles.cpp, plan_manager/src/baseline_fake.cpp compiled unmodified from
+plan_env/src/raycast.cpp, traj_utils/sdlp.hpp, sfc_gen/lbfgs.hpp, sfc_gen/firi.hpp, traj_utils/src/bernstein.cpp, traj_opt/src/bezier_optimizer.cpp, path_searching/src/{fake_,}risk_hybrid_a_star.cpp, traj_coordinator/src/particles.cpp, plan_manager/src/baseline{_fake,}.cpp compiled unmodified from
 /root/reference; see oracle/Makefile) on the seeded cases of tests/ref_lib.py.  tests/test_ref_pins.py checks the
 oracle against these vectors wherever the library itself is not available.  Needs /root/reference.
 
@@ -76,18 +76,25 @@ def main():
             heads.append([ret, st[0], st[1], st[2]])
         out[key + "_path"], out[key + "_offs"] = rl.pack(paths)
         out[key + "_head"] = np.array(heads, np.int32)
-    cfg, (cloud, cyl) = rl.astar_world()
-    heads, cps = [], []
-    for pose, start, goal, ts in rl.astar_cases(N_REPLAN, seed=67):
-        m = orc.map(cfg)
-        m.set_pose(pose)
-        m.update_gt(cloud, cyl, 0.0)
-        m.set_time(100.0)
-        ok, M, cp, st = ref.replan(cfg, m, pose, 100.0, 100.0 + ts, start, goal)
-        heads.append([ok, M, st[0], st[1], st[3]])
-        cps.append(cp)
-    out["replan_head"] = np.array(heads, np.int32)
-    out["replan_cpts"], out["replan_offs"] = rl.pack(cps)
+    from tests import oracle_cycle
+    for key, (cfg, (cloud, cyl)), risk, seed in (("replan", rl.astar_world(), False, 67), ("replan_risk", rl.astar_world_risk(), True, 79)):
+        heads, cps = [], []
+        for pose, start, goal, ts in rl.astar_cases(N_REPLAN, seed=seed):
+            m = orc.map(cfg)
+            m.set_pose(pose)
+            m.update_gt(cloud, cyl, 0.0)
+            m.set_time(100.0)
+            # without a single valid corridor both planners index an empty list (`hPolys.size() - 1` underflows,
+            # baseline_fake.cpp:366 / baseline.cpp:363): undefined behaviour, not run
+            if oracle_cycle.replan(m, None, 0, start, goal, 100.0 + ts)[0] == 2:
+                heads.append([-1, 0, 0, 0, 0])
+                cps.append(np.zeros((0, 3)))
+                continue
+            ok, M, cp, st = ref.replan(cfg, m, pose, 100.0, 100.0 + ts, start, goal, risk=risk)
+            heads.append([ok, M, st[0], st[1], st[3]])
+            cps.append(cp)
+        out[key + "_head"] = np.array(heads, np.int32)
+        out[key + "_cpts"], out[key + "_offs"] = rl.pack(cps)
     cfg, size, ego, offs, counts, recs, qa, qt = rl.peer_case()
     out["peer_ego"] = ref.ego_particles(size)
     pts, rk, on = ref.particles_with_risk(cfg.n_agents_total, ego, size, offs, counts, recs, 10.0, qa, qt)

@@ -113,8 +113,8 @@ class RefLib:
         return ret, out[:n.value].copy(), st
 
 
-    def replan(self, cfg, omap, pose, t_map, t_plan, start9, goal3):
-        """The reference's FakeBaselinePlanner::replan on the oracle map `omap` (queries and obstacle points answered by
+    def replan(self, cfg, omap, pose, t_map, t_plan, start9, goal3, risk=False):
+        """The reference's FakeBaselinePlanner::replan (risk=True: BaselinePlanner::replan) on the oracle map `omap` (queries and obstacle points answered by
         liboracle, the OSQP solve behind IOSQP by the oracle's ADMM): (ok, pieces, control points 5M x 3, stats =
         A* iterations, A* nodes, pieces, QP iterations)."""
         from tests import oracle_lib
@@ -123,7 +123,7 @@ class RefLib:
         pose = np.ascontiguousarray(pose, np.float32)
         start9, goal3 = np.ascontiguousarray(start9, np.float64), np.ascontiguousarray(goal3, np.float64)
         M, dur, cp, st = C.c_int(0), np.zeros(16), np.zeros((80, 3)), np.zeros(4, np.int32)
-        ok = self.lib.ref_replan(C.byref(cfg), *fns, omap.h, pose.ctypes.data_as(C.POINTER(C.c_float)), D(t_map), None, None,
+        ok = (self.lib.ref_replan_risk if risk else self.lib.ref_replan)(C.byref(cfg), *fns, omap.h, pose.ctypes.data_as(C.POINTER(C.c_float)), D(t_map), None, None,
                                  None, D(t_plan), D(t_plan), P(start9), P(goal3), C.byref(M), P(dur), P(cp),
                                  st.ctypes.data_as(C.POINTER(C.c_int32)))
         return ok, M.value, cp[:5 * M.value].copy(), st
@@ -400,6 +400,7 @@ def astar_world_risk():
     cfg, world = astar_world()
     cfg.query_variant = p.POP_QUERY_RISKBASE
     cfg.risk_threshold_region, cfg.risk_region_decay = 0.9, 0.05
+    cfg.risk_voxel_decay = 0.01          # obstacle-point threshold risk_threshold - decay * slice stays positive
     return cfg, world
 
 

@@ -289,25 +289,32 @@ def test_separation_check_point_sets_identical(oracle, ref, gold):
     assert gold["sep_n"].max() >= 5 and gold["sep_n"].min() == 0
 
 
-# ---- FakeBaselinePlanner::replan (plan_manager/src/baseline_fake.cpp:265-453) ----------------------------------------
-def test_whole_replan_against_the_reference_planner(oracle, ref, gold):
-    """The reference's planner end to end — its own A*, corridor stage (bounding boxes, obstacle points per segment, FIRI,
-    shrink, validity / intersection / goal LPs), QP assembly and trajectory hand-over — run on the oracle's grid with the
-    oracle's ADMM behind its solver wrapper, against the oracle's replan on 30 problems with moving obstacles: the same
-    replans succeed and fail, with the same number of A* expansions and trajectory pieces; control points agree to the
-    solver's own tolerance (eps 1e-3; FIRI's ellipsoid step stops L-BFGS on a 1e-7 cost decrease, so corridor faces of
-    two correct runs differ by ~1e-4 and the QP optimum moves with them) — median below 1e-4."""
+# ---- FakeBaselinePlanner::replan / BaselinePlanner::replan (plan_manager/src/baseline_fake.cpp, baseline.cpp) -------
+@pytest.mark.parametrize("risk", [False, True])
+def test_whole_replan_against_the_reference_planner(oracle, ref, gold, risk):
+    """The reference's planners end to end — their own A*, corridor stage (bounding boxes, obstacle points per segment,
+    FIRI, shrink, validity / intersection / goal LPs), QP assembly and trajectory hand-over — run on the oracle's grid
+    with the oracle's ADMM behind their solver wrapper, against the oracle's replan on problems with moving obstacles:
+    the same replans succeed and fail, with the same number of A* expansions and trajectory pieces; control points
+    agree to the solver's own tolerance (eps 1e-3; FIRI's ellipsoid step stops L-BFGS on a 1e-7 cost decrease, so
+    corridor faces of two correct runs differ by ~1e-4 and the QP optimum moves with them) — median below 1e-4.
+    risk=False: FakeBaselinePlanner on the ground-truth map; risk=True: BaselinePlanner on a RiskBase-style map, whose
+    rules differ (every face shrunk, corridor cut and count, goal search)."""
     from tests import oracle_cycle
-    cfg, (cloud, cyl) = rl.astar_world()
-    heads = gold["replan_head"]
-    wants = rl.unpack(gold["replan_cpts"], gold["replan_offs"], 3)
+    cfg, (cloud, cyl) = rl.astar_world_risk() if risk else rl.astar_world()
+    key, seed = ("replan_risk", 79) if risk else ("replan", 67)
+    heads = gold[key + "_head"]
+    wants = rl.unpack(gold[key + "_cpts"], gold[key + "_offs"], 3)
     rel, n_ok = [], 0
-    for (pose, start, goal, ts), head, want in zip(rl.astar_cases(len(heads), seed=67), heads, wants):
+    for (pose, start, goal, ts), head, want in zip(rl.astar_cases(len(heads), seed=seed), heads, wants):
         m = oracle.map(cfg)
         m.set_pose(pose)
         m.update_gt(cloud, cyl, 0.0)
         m.set_time(100.0)
         rs, rec, st = oracle_cycle.replan(m, None, 0, start, goal, 100.0 + ts)
+        if head[0] < 0:                                                # not run: see scripts/make_golden_ref.py
+            assert rs == 2
+            continue
         assert (rs == 0) == bool(head[0]), (rs, head.tolist())
         assert st[1] == head[2]                                        # A* expansions
         if rs == 0:
@@ -323,8 +330,10 @@ def test_whole_replan_against_the_reference_planner(oracle, ref, gold):
             m.set_pose(pose)
             m.update_gt(cloud, cyl, 0.0)
             m.set_time(100.0)
-            ok, M, cp, st = ref.replan(cfg, m, pose, 100.0, 100.0 + ts, start, goal)
             rs, rec, so = oracle_cycle.replan(m, None, 0, start, goal, 100.0 + ts)
+            if rs == 2:
+                continue
+            ok, M, cp, st = ref.replan(cfg, m, pose, 100.0, 100.0 + ts, start, goal, risk=risk)
             assert (rs == 0) == bool(ok) and so[1] == st[0]
             if ok:
                 assert int(rec["n_pieces"]) == M

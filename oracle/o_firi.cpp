@@ -8,8 +8,8 @@
 // PINNED against the reference's own firi.hpp / lbfgs.hpp / sdlp.hpp compiled unmodified into oracle/_ref/libref.so
 // (Eigen replaced by a stand-in, oracle/ref_build/Eigen/Eigen): costMVIE and whole L-BFGS runs bit-identical, the
 // first FIRI polytope identical, maxVolInsEllipsoid the same optimum to the optimiser's own stopping tolerance,
-// iterated corridors compared as sets — tests/test_ref_pins.py.  The corridor stage around firi
-// (baseline_fake.cpp, ROS-bound) remains PARITY UNPINNED.
+// iterated corridors compared as sets — tests/test_ref_pins.py.  The corridor stage around firi is pinned through the
+// whole replan of both reference planners (see o_replan.cpp).
 #include <algorithm>
 #include <cfloat>
 #include <limits>

@@ -4,6 +4,9 @@
 // is what FiniteStateMachineFake::publishTrajectory broadcasts
 // (plan_manager/src/fake_plan_manager.cpp:364-399; durations narrowed to float32 by
 // traj_utils/msg/BezierTraj.msg:8).
+// PINNED end to end against the reference's own planners compiled into oracle/_ref/libref.so (baseline_fake.cpp and
+// baseline.cpp, with the map and the OSQP solve answered through callbacks by this oracle): same successes and failures,
+// A* expansions and piece counts, control points at the solver's tolerance — tests/test_ref_pins.py.
 #include "oracle.hpp"
 
 namespace orc {

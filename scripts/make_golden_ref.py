@@ -95,6 +95,22 @@ def main():
             cps.append(cp)
         out[key + "_head"] = np.array(heads, np.int32)
         out[key + "_cpts"], out[key + "_offs"] = rl.pack(cps)
+    # one batch with a common plan time: what pop_replan_cycle can be compared with directly (tests/test_gpu_zz_...)
+    cfg, (cloud, cyl) = rl.astar_world()
+    heads, cps = [], []
+    for pose, start, goal, _ in rl.astar_cases(24, seed=83):
+        m = orc.map(cfg)
+        m.set_pose(pose)
+        m.update_gt(cloud, cyl, 100.0)
+        if oracle_cycle.replan(m, None, 0, start, goal, 100.02)[0] == 2:
+            heads.append([-1, 0, 0, 0, 0])
+            cps.append(np.zeros((0, 3)))
+            continue
+        ok, M, cp, st = ref.replan(cfg, m, pose, 100.0, 100.02, start, goal)
+        heads.append([ok, M, st[0], st[1], st[3]])
+        cps.append(cp)
+    out["batch_head"] = np.array(heads, np.int32)
+    out["batch_cpts"], out["batch_offs"] = rl.pack(cps)
     cfg, size, ego, offs, counts, recs, qa, qt = rl.peer_case()
     out["peer_ego"] = ref.ego_particles(size)
     pts, rk, on = ref.particles_with_risk(cfg.n_agents_total, ego, size, offs, counts, recs, 10.0, qa, qt)

@@ -1,4 +1,6 @@
-"""The CUDA hybrid A* against outputs of the REFERENCE's own search — no oracle in between.
+"""The CUDA path against outputs of the REFERENCE's own code — no oracle in between.
+
+First the hybrid A*, then the whole replan cycle (below).
 
 tests/golden/ref_pins.npz holds what path_searching/src/fake_risk_hybrid_a_star.cpp (compiled unmodified into
 oracle/_ref/libref.so, see oracle/Makefile and scripts/make_golden_ref.py) returned for 40 seeded problems on a grid
@@ -50,3 +52,45 @@ def test_astar_batch_equals_reference_outputs(cell):
             bad.append((a, int(ret[a]), stats[a].tolist(), heads[a].tolist(), int(ln[a]), len(want[a])))
     assert not bad, bad
     assert (ret != 0).sum() >= n // 2
+
+
+def test_replan_cycle_against_the_reference_planner():
+    """pop_replan_cycle (CUDA voxel update, A*, corridors, QP, record) for 24 agents at one plan time, against what the
+    reference's own FakeBaselinePlanner::replan returned for each of them (compiled unmodified into oracle/_ref/libref.so;
+    recorded in tests/golden/ref_pins.npz by scripts/make_golden_ref.py, where the map and the OSQP solve behind the
+    reference's wrapper are the oracle's).  The same replans succeed, with the same number of pieces; control points
+    within 1e-2 relative — the solver runs at eps 1e-3 and the corridor faces of two correct runs differ by ~1e-4
+    (FIRI's L-BFGS stopping rule; LP shuffles: mt19937 there, an LCG here).  One borderline status flip is tolerated."""
+    gold = np.load(GOLD)
+    heads = gold["batch_head"]
+    wants = rl.unpack(gold["batch_cpts"], gold["batch_offs"], 3)
+    n = len(heads)
+    probs = rl.astar_cases(n, seed=83)
+    _, (cloud, cyl) = rl.astar_world()
+    cfg = cases.cfg_c1(p.POP_CELL_U8, n_local=n, n_total=n)
+    start = np.stack([pr[1] for pr in probs])
+    goal = np.stack([pr[2] for pr in probs])
+    poses = np.stack([pr[0] for pr in probs]).astype(np.float32)
+    eng = p.PopEngine(cfg)
+    eng.set_world_cloud(cloud)
+    eng.set_cylinders(cyl)
+    eng.set_body_particles(*p.worldgen.body_table(n, list(cfg.drone_size)))
+    eng.set_trajectories(np.zeros(n, p.TRAJ_DTYPE))        # nobody has published: no peers, as in the recorded runs
+    status, traj = eng.replan_cycle(start, goal, poses, 100.0, 100.02)
+    eng.close()
+    flips, rel, n_ok = [], [], 0
+    for a in range(n):
+        if heads[a, 0] < 0:                                # no valid corridor: the reference was not run (undefined there)
+            assert status[a] != 0
+            continue
+        if (status[a] == 0) != bool(heads[a, 0]):
+            flips.append((a, int(status[a]), heads[a].tolist()))
+            continue
+        if status[a] == 0:
+            M = int(heads[a, 1])
+            assert int(traj["n_pieces"][a]) == M, (a, int(traj["n_pieces"][a]), M)
+            got = np.asarray(traj["cpts"][a]).reshape(-1, 3)[:5 * M]
+            rel.append(np.abs(got - wants[a]).max() / max(1.0, np.abs(wants[a]).max()))
+            n_ok += 1
+    assert len(flips) <= 1, flips
+    assert n_ok >= n // 3 and max(rel) <= 1e-2 and np.median(rel) <= 1e-3, (n_ok, max(rel), float(np.median(rel)))

@@ -13,3 +13,5 @@ from tests import test_gpu_zz_reference_vectors as t  # noqa: E402
 for cell in (p.POP_CELL_F32, p.POP_CELL_U8):
     t.test_astar_batch_equals_reference_outputs(cell)
     print(f"cell {cell}: CUDA A* == reference outputs on 40 problems ({time.time() - t0:.1f} s)", flush=True)
+t.test_replan_cycle_against_the_reference_planner()
+print(f"pop_replan_cycle agrees with the reference planner's recorded outputs on 24 agents ({time.time() - t0:.1f} s)", flush=True)

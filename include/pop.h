@@ -73,7 +73,9 @@ enum {
 #define POP_MAX_FACES  48   /* faces kept per corridor polytope */
 
 /* One ground-truth obstacle, plan_env/include/plan_env/fake_particle_risk_voxel.h:31-44.
- * type 3 = vertical cylinder; other types are skipped by this build. */
+ * type 3 = vertical cylinder (visualization_msgs::Marker::CYLINDER, dynamic_forest_seq_sensing.cpp:199): x, y, w = diameter;
+ * type 2 = vertical ring (Marker::SPHERE, :205-254; MovingCircle): centre x, y, z, w = 2 * inner radius, orientation q;
+ * other types own no voxel (the reference prints "unknown type"). */
 typedef struct pop_cylinder {
   int32_t type;
   int32_t _pad;
@@ -179,6 +181,13 @@ int pop_set_trajectories(pop_handle* h, const pop_traj_record* recs);
  * peer-trajectory particles (addParticlesToRiskMap :291-301). t_map = last_update_time_. */
 int pop_map_update_gt(pop_handle* h, double t_map);
 
+/* RiskBase::updateTimeCallback + futureRiskCallback (plan_env/src/risk_base.cpp:60-80; risk_base.h:85) for every local
+ * agent: the [VOXEL_NUM][PREDICTION_TIMES] float grid a risk_mapping_node published on "map/future_risk"
+ * (risk_mapping_node.cpp:105-150) becomes the agent's SOGM, stamp becomes the map time, then the peers are projected
+ * (addOtherAgents :136-168).  risk = n_agents_local x V x T floats; poses (n_local x 3, may be NULL = unchanged) are the
+ * map centres.  Needs POP_CELL_F32.  (pop_dsp_update produces the same grid on the device without this copy.) */
+int pop_map_future_risk(pop_handle* h, const float* risk, const float* poses, double stamp);
+
 /* getClearOcccupancy(pos, int t) (fake_particle_risk_voxel.cpp:309-330 / risk_base.cpp:228-250)
  * pos = n x 3 doubles (world), t_idx = n slice indices, out = n results in {-1,0,1}. */
 int pop_map_query(pop_handle* h, int agent, const double* pos, const int32_t* t_idx, int n,
@@ -186,6 +195,13 @@ int pop_map_query(pop_handle* h, int agent, const double* pos, const int32_t* t_
 /* getClearOcccupancy(pos, double dt) (:343-348 / risk_base.cpp:256-260). */
 int pop_map_query_dt(pop_handle* h, int agent, const double* pos, const double* dt, int n,
                      int8_t* out);
+/* MapBase::getInflateOccupancy (plan_env/include/plan_env/map.h:120-122, map.cpp:345-395): the single-voxel test of
+ * the kept map interface.  mode 0 = (pos), 1 = (pos, int t) with t[i] the slice index, 2 = (pos, double t) testing
+ * slices ceil(t / time_resolution) and floor(t / time_resolution).  t = n doubles (ignored for mode 0);
+ * out = n results in {-1 out of range, 0, 1}.  A slice index equal to PREDICTION_TIMES (which the reference reads one
+ * slice past the end) answers -1 in mode 1 and is clamped to nt - 1 in mode 2. */
+int pop_map_query_inflate(pop_handle* h, int agent, const double* pos, const double* t, int mode, int n,
+                          int8_t* out);
 /* MapBase::getObstaclePoints(points, t_start, t_end, lc, hc) (map.cpp:463-531; RiskBase
  * variant risk_base.cpp:295-337). out = cap x 3 doubles in the reference's emission order
  * (z, y, x, slice); *n_out = number the reference would have emitted (may exceed cap →

@@ -101,6 +101,23 @@ class RiskVoxelMap {
     e_.check(pop_map_query_dt(e_.handle(), agent_, pos.data(), &dt, 1, &out));
     return out;
   }
+  // MapBase::getInflateOccupancy in its three forms (map.h:120-122)
+  int getInflateOccupancy(const Vec3& pos) const {
+    int8_t out = 0;
+    e_.check(pop_map_query_inflate(e_.handle(), agent_, pos.data(), nullptr, 0, 1, &out));
+    return out;
+  }
+  int getInflateOccupancy(const Vec3& pos, int t) const {
+    int8_t out = 0;
+    const double td = t;
+    e_.check(pop_map_query_inflate(e_.handle(), agent_, pos.data(), &td, 1, 1, &out));
+    return out;
+  }
+  int getInflateOccupancy(const Vec3& pos, double t) const {
+    int8_t out = 0;
+    e_.check(pop_map_query_inflate(e_.handle(), agent_, pos.data(), &t, 2, 1, &out));
+    return out;
+  }
   // batched form the planner should prefer: pos = n x 3
   std::vector<int8_t> getClearOcccupancy(const std::vector<double>& pos, const std::vector<int32_t>& t) const {
     std::vector<int8_t> out(t.size());

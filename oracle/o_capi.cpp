@@ -80,6 +80,11 @@ void orc_map_query_dt(void* h, const double* pos, const double* dt, int n, int8_
   for (int i = 0; i < n; i++)
     out[i] = static_cast<int8_t>(query_dt(g, V3d{pos[3 * i], pos[3 * i + 1], pos[3 * i + 2]}, dt[i]));
 }
+void orc_map_inflate_query(void* h, int mode, const double* pos, const double* t, int n, int8_t* out) {
+  const Grid& g = static_cast<OrcMap*>(h)->grid;
+  for (int i = 0; i < n; i++)
+    out[i] = static_cast<int8_t>(inflate_query(g, V3d{pos[3 * i], pos[3 * i + 1], pos[3 * i + 2]}, mode, t[i]));
+}
 int orc_map_obstacle_points(void* h, double t0, double t1, const double* lc, const double* hc,
                             double* out, int cap) {
   std::vector<V3d> v;

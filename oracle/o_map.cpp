@@ -1,8 +1,10 @@
 // o_map.cpp — oracle: SOGM grid, ground-truth update, occupancy queries (TEST INFRASTRUCTURE).
 // Follows plan_env/src/fake_particle_risk_voxel.cpp, plan_env/src/risk_base.cpp,
 // plan_env/src/map.cpp and plan_env/include/plan_env/map.h of the reference.
-// PARITY UNPINNED: those files need ROS and PCL to compile and the reference has no tests for them; this restatement
-// is checked by property and ground-truth-scene tests only (tests/test_oracle_map.py).
+// PINNED: plan_env/src/map.cpp, fake_particle_risk_voxel.cpp and risk_base.cpp are compiled unmodified into
+// oracle/_ref/libref_map_*.so (oracle/Makefile, ref_glue_map.cpp; stand-ins for ROS, PCL and Eigen's fp32 geometry) and
+// tests/test_ref_map_pins.py compares every function of this file with them bit for bit (live and through
+// tests/golden/ref_map_pins.npz).
 #include <algorithm>
 
 #include "oracle.hpp"
@@ -42,6 +44,22 @@ void Grid::init(const pop_config& c) {
   risk.assign(static_cast<size_t>(V()) * nt, 0.f);
 }
 
+// fp32 3-vector helpers in the evaluation order of Eigen 3.3's scalar code path, which is what the reference's
+// Vector3f / Quaternionf / Hyperplane<float, 3> expressions compile to: reductions of a fixed-size 3-vector pair
+// c0 + (c1 + c2) (Core/Redux.h, redux_novec_unroller), cross is the plain formula (Geometry/OrthoMethods.h),
+// q * v = v + w * (2 vec x v) + vec x (2 vec x v) (Geometry/Quaternion.h, _transformVector).
+static inline V3f add3(V3f a, V3f b) { return V3f{a.x + b.x, a.y + b.y, a.z + b.z}; }
+static inline V3f sub3(V3f a, V3f b) { return V3f{a.x - b.x, a.y - b.y, a.z - b.z}; }
+static inline float dot3(V3f a, V3f b) { return a.x * b.x + (a.y * b.y + a.z * b.z); }
+static inline float norm3(V3f a) { return std::sqrt(dot3(a, a)); }
+static inline V3f cross3(V3f a, V3f b) { return V3f{a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x}; }
+static inline V3f quat_rotate(float w, V3f q, V3f v) {
+  V3f uv = cross3(q, v);
+  uv = add3(uv, uv);
+  const V3f c = cross3(q, uv);
+  return V3f{(v.x + w * uv.x) + c.x, (v.y + w * uv.y) + c.y, (v.z + w * uv.z) + c.z};
+}
+
 // fake_particle_risk_voxel.cpp:80-170
 void gt_update(Grid& g, const float* cloud, int n, const pop_cylinder* cyl, int ncyl,
                double t_map) {
@@ -78,14 +96,33 @@ void gt_update(Grid& g, const float* cloud, int n, const pop_cylinder* cyl, int 
     for (int c = 0; c < ncyl; c++) {
       if (cyl[c].type == 3) {
         V3f pc{static_cast<float>(cyl[c].x), static_cast<float>(cyl[c].y), pt.z};
-        float dx = pt.x - pc.x, dy = pt.y - pc.y, dz = pt.z - pc.z;
-        float dist = std::sqrt(dx * dx + dy * dy + dz * dz);
+        float dist = norm3(V3f{pt.x - pc.x, pt.y - pc.y, pt.z - pc.z});
         if (dist <= cyl[c].w + g.clearance) {  // evaluated in double
           vel = V3f{static_cast<float>(cyl[c].vx), static_cast<float>(cyl[c].vy), 0.0F};
           break;
         }
+      } else if (cyl[c].type == 2) {  // :139-150 vertical ring (MovingCircle), fp32 Eigen geometry
+        const V3f pc{static_cast<float>(cyl[c].x), static_cast<float>(cyl[c].y), static_cast<float>(cyl[c].z)};
+        const float qw = static_cast<float>(cyl[c].qw);
+        const V3f qv{static_cast<float>(cyl[c].qx), static_cast<float>(cyl[c].qy), static_cast<float>(cyl[c].qz)};
+        // Hyperplane::Through(p0, p0 + q*(0,1,0), p0 + q*(1,0,0)): normal = (p2 - p0) x (p1 - p0), normalised
+        const V3f p1 = add3(pc, quat_rotate(qw, qv, V3f{0, 1, 0}));
+        const V3f p2 = add3(pc, quat_rotate(qw, qv, V3f{1, 0, 0}));
+        V3f nrm = cross3(sub3(p2, pc), sub3(p1, pc));
+        const float nn = norm3(nrm);
+        nrm = V3f{nrm.x / nn, nrm.y / nn, nrm.z / nn};
+        const float off = -dot3(pc, nrm);
+        const float sd = dot3(nrm, pt) + off;                                  // signedDistance(pt)
+        const V3f b{pt.x - sd * nrm.x, pt.y - sd * nrm.y, pt.z - sd * nrm.z};  // projection(pt)
+        const float dist_to_plane = std::fabs(sd);
+        const float dist = norm3(sub3(pc, b));
+        // `abs(cyl.w / 2 - dist) < 2 * resolution_`: the left side is a double, 2 * res an fp32 product
+        if (std::fabs(cyl[c].w / 2 - dist) < 2 * g.res && dist_to_plane < 2 * g.res) {
+          vel = V3f{static_cast<float>(cyl[c].vx), static_cast<float>(cyl[c].vy), 0.0F};
+          break;
+        }
       }
-      // type 2 (ring obstacles) and unknown types are not produced by this repo's inputs
+      // other types only make the reference print "unknown type"
     }
     for (int k = 1; k < T; k++) {
       const float kf = static_cast<float>(k);
@@ -141,6 +178,33 @@ int query_dt(const Grid& g, V3d pos, double dt) {
   int tf = std::floor(dt / g.dt);
   tf = tf > (g.nt - 1) ? g.nt - 1 : tf;
   return query(g, pos, tf);
+}
+
+// MapBase::getInflateOccupancy (map.cpp:345-395): the single-voxel test of the kept map interface (map.h:120-122).
+// mode 0 (pos) = slice 0, mode 1 (pos, int t), mode 2 (pos, double t) = slices ceil(t / dt) and floor(t / dt).
+// Deviations: the reference lets t == PREDICTION_TIMES through (`t > PREDICTION_TIMES` / clamps to PREDICTION_TIMES)
+// and then reads one slice past the end (the aliasing of SURVEY Appendix A Q2); here such a slice index answers -1
+// (mode 1) or is clamped to nt - 1 (mode 2).  Negative indices answer -1.
+int inflate_query(const Grid& g, V3d pos, int mode, double t) {
+  const V3f pf{static_cast<float>(pos.x) - g.pose.x, static_cast<float>(pos.y) - g.pose.y,
+               static_cast<float>(pos.z) - g.pose.z};
+  const int idx = g.index(pf);
+  if (!g.in_range(pf)) return -1;
+  if (idx < 0 || idx >= g.V()) return -1;  // see gt_update: rounding at the border
+  if (mode == 0) return g.at(idx, 0) > g.risk_threshold ? 1 : 0;
+  if (mode == 1) {
+    const int ti = static_cast<int>(t);
+    if (ti < 0 || ti >= g.nt) return -1;
+    return g.at(idx, ti) > g.risk_threshold ? 1 : 0;
+  }
+  int tc = std::ceil(t / g.dt);
+  tc = tc > g.nt - 1 ? g.nt - 1 : tc;
+  int tf = std::floor(t / g.dt);
+  tf = tf > g.nt - 1 ? g.nt - 1 : tf;
+  if (tc < 0 || tf < 0) return -1;
+  if (g.at(idx, tc) > g.risk_threshold) return 1;
+  if (g.at(idx, tf) > g.risk_threshold) return 1;
+  return 0;
 }
 
 // map.cpp:463-531 (Fake inherits MapBase's) / risk_base.cpp:295-337.

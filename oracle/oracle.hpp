@@ -78,6 +78,7 @@ void add_particles(Grid& g, const V3d* pts, const float* risks, int n, int t_ind
 // getClearOcccupancy(pos,int t) / (pos,double dt)
 int query(const Grid& g, V3d pos, int t);
 int query_dt(const Grid& g, V3d pos, double dt);
+int inflate_query(const Grid& g, V3d pos, int mode, double t);
 // getObstaclePoints(points,t_start,t_end,lc,hc) (map.cpp:463-531 / risk_base.cpp:295-337)
 void obstacle_points(const Grid& g, double t_start, double t_end, V3d lc, V3d hc,
                      std::vector<V3d>& out);

@@ -4,6 +4,9 @@
 // (oracle/_ref only); ROS itself is absent from this image.
 #ifndef POP_ROS_STANDIN_H
 #define POP_ROS_STANDIN_H
+#include <iostream>   // roscpp's headers bring <iostream>, <math.h> and <stdlib.h>; the reference relies on that:
+#include <math.h>     // map.cpp:477 prints with std::cout, fake_particle_risk_voxel.cpp:145 calls the global abs() on a
+#include <stdlib.h>   // double — with libstdc++'s <stdlib.h>/<math.h> wrappers visible that is std::abs(double), not abs(int)
 #include <map>
 #include <string>
 
@@ -56,7 +59,7 @@ class NodeHandle {
   }
   // topics and timers are never driven: the tests call the callbacks directly
   template <class... A> Subscriber subscribe(const std::string&, int, A&&...) { return Subscriber(); }
-  template <class M> Publisher advertise(const std::string&, int) { return Publisher(); }
+  template <class M> Publisher advertise(const std::string&, int, bool = false) { return Publisher(); }
   template <class... A> Timer createTimer(Duration, A&&...) { return Timer(); }
 };
 }  // namespace ros

@@ -1,0 +1,1 @@
+// stand-in: named by plan_env/map.h, nothing of it is used

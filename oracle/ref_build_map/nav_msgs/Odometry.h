@@ -1,0 +1,7 @@
+// nav_msgs/Odometry.h — a STAND-IN with the pose fields MapBase::odomCallback reads (map.cpp:158-170).
+// TEST INFRASTRUCTURE (oracle/_ref only).  Same guard as oracle/ref_build/nav_msgs/Odometry.h, which it shadows.
+#ifndef POP_ODOMETRY_STANDIN_H
+#define POP_ODOMETRY_STANDIN_H
+#include <geometry_msgs/PoseStamped.h>
+namespace nav_msgs { struct Odometry { geometry_msgs::Header header; geometry_msgs::PoseWithCovariance pose; typedef std::shared_ptr<const Odometry> ConstPtr; }; }
+#endif

@@ -174,8 +174,10 @@ SYMBOLS = [
     ("pop_set_body_particles", _I, [_VP, _PD, _PI32]),
     ("pop_set_trajectories", _I, [_VP, C.POINTER(PopTrajRecord)]),
     ("pop_map_update_gt", _I, [_VP, _D]),
+    ("pop_map_future_risk", _I, [_VP, _PF, _PF, _D]),
     ("pop_map_query", _I, [_VP, _I, _PD, _PI32, _I, _PI8]),
     ("pop_map_query_dt", _I, [_VP, _I, _PD, _PD, _I, _PI8]),
+    ("pop_map_query_inflate", _I, [_VP, _I, _PD, _PD, _I, _I, _PI8]),
     ("pop_map_obstacle_points", _I, [_VP, _I, _D, _D, _PD, _PD, _PD, _I, C.POINTER(_I)]),
     ("pop_map_add_particles", _I, [_VP, _I, _PD, _PF, _I, _I]),
     ("pop_map_download", _I, [_VP, _I, _PF]),

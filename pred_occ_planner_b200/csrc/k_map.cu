@@ -111,18 +111,8 @@ __global__ void __launch_bounds__(128) k_future_slices(PopGeom g, uint8_t* __res
     const float pty = geom_axis_position(iy, g.ry, g.res, posey);
     const float ptz = geom_axis_position(iz, g.rz, g.res, posez);
     float vx = 0.f, vy = 0.f;
-    for (int c = 0; c < n_cyl; c++) {
-      if (scyl[c].type != 3) continue;
-      const float dx = __fsub_rn(ptx, scyl[c].x), dy = __fsub_rn(pty, scyl[c].y);
-      const float dz = __fsub_rn(ptz, ptz);
-      const float dist = __fsqrt_rn(
-          __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
-      if (static_cast<double>(dist) <= __dadd_rn(scyl[c].w, static_cast<double>(g.clearance))) {
-        vx = scyl[c].vx;
-        vy = scyl[c].vy;
-        break;
-      }
-    }
+    const int own = geom_gt_owner(g, scyl, n_cyl, ptx, pty, ptz);
+    if (own >= 0) { vx = scyl[own].vx; vy = scyl[own].vy; }
     for (int k = 1; k < g.nt; k++) {
       const float kf = static_cast<float>(k);
       const float qx = __fsub_rn(__fadd_rn(ptx, __fmul_rn(__fmul_rn(vx, g.dt), kf)), posex);
@@ -235,6 +225,17 @@ __global__ void k_query(PopGeom g, const uint8_t* __restrict__ ag, const float* 
       geom_query<C>(g, ag, pose[0], pose[1], pose[2], pos[3 * i], pos[3 * i + 1], pos[3 * i + 2], t));
 }
 
+// getInflateOccupancy batched: mode 0 (pos), 1 (pos, int t), 2 (pos, double t); ts = n doubles (ignored for mode 0)
+template <typename C>
+__global__ void k_query_inflate(PopGeom g, const uint8_t* __restrict__ ag, const float* __restrict__ pose,
+                                const double* __restrict__ pos, const double* __restrict__ ts, int mode, int n,
+                                int8_t* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  out[i] = static_cast<int8_t>(geom_inflate_query<C>(g, ag, pose[0], pose[1], pose[2], pos[3 * i], pos[3 * i + 1],
+                                                     pos[3 * i + 2], mode, mode ? ts[i] : 0.0));
+}
+
 // =============================================================================================
 // A15 obstacle points in a box × slice range, emitted in the reference's order (z, y, x, slice)
 // (map.cpp:463-531).  One CTA; each thread owns a contiguous run of box voxels, block scan of
@@ -313,6 +314,18 @@ __global__ void k_download(PopGeom g, const uint8_t* __restrict__ ag, float* __r
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
     const size_t v = i / g.nt, t = i % g.nt;
     out[i] = Cell<C>::load(ag, t * g.V + v);
+  }
+}
+
+// RiskBase::futureRiskCallback's copy (risk_base.cpp:60-68): in[v*T + t] (the "map/future_risk" layout) -> [t][v] cells
+template <typename C>
+__global__ void k_upload(PopGeom g, uint8_t* __restrict__ ag, const float* __restrict__ in) {
+  const size_t n = static_cast<size_t>(g.V) * g.nt;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const size_t t = i / g.V, v = i % g.V;   // coalesced writes; the strided reads hit L2
+    if (sizeof(C) == 4) reinterpret_cast<float*>(ag)[i] = in[v * g.nt + t];
+    else ag[i] = static_cast<uint8_t>(in[v * g.nt + t]);
   }
 }
 
@@ -438,22 +451,12 @@ __global__ void __launch_bounds__(256) k_vox_fill(PopGeom g, int H, int nbands, 
   if (!(1.0f > g.risk_threshold)) return;
   const int lf = vox_future_layer(g, iz, posez);
   if (lf < 0) return;
-  // owner: first type-3 cylinder with |corner - axis| <= w + clearance (compared in double)
+  // owner: first cylinder or ring, in id order, whose test the voxel corner passes (geom_gt_owner)
   const float ptx = geom_axis_position(ix, g.rx, g.res, posex);
   const float pty = geom_axis_position(iy, g.ry, g.res, posey);
   const float ptz = geom_axis_position(iz, g.rz, g.res, posez);
-  unsigned owner = 0xffffu;
-  for (int c = 0; c < n_cyl; c++) {
-    if (scyl[c].type != 3) continue;
-    const float dx = __fsub_rn(ptx, scyl[c].x), dy = __fsub_rn(pty, scyl[c].y);
-    const float dz = __fsub_rn(ptz, ptz);
-    const float dist = __fsqrt_rn(
-        __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
-    if (static_cast<double>(dist) <= __dadd_rn(scyl[c].w, static_cast<double>(g.clearance))) {
-      owner = static_cast<unsigned>(c);
-      break;
-    }
-  }
+  const int own = geom_gt_owner(g, scyl, n_cyl, ptx, pty, ptz);
+  const unsigned owner = own >= 0 ? static_cast<unsigned>(own) : 0xffffu;
   const int l = a * 2 + 1, key = lf * nbands + band;
   const int pos = off[l * (nkeys + 1) + key] + atomicAdd(&cur[l * nkeys + key], 1);
   if (pos < cap)
@@ -757,6 +760,19 @@ int popk_query(pop_handle* h, int agent, const double* d_pos, const int32_t* d_t
   return POP_OK;
 }
 
+int popk_query_inflate(pop_handle* h, int agent, const double* d_pos, const double* d_t, int mode, int n, int8_t* d_out) {
+  const PopGeom& g = h->geom;
+  const uint8_t* ag = h->d_grid + agent * g.agent_stride;
+  const float* pose = h->d_poses + 3 * agent;
+  if (h->cfg.cell_dtype == POP_CELL_U8)
+    k_query_inflate<uint8_t><<<(n + 127) / 128, 128, 0, h->stream>>>(g, ag, pose, d_pos, d_t, mode, n, d_out);
+  else
+    k_query_inflate<float><<<(n + 127) / 128, 128, 0, h->stream>>>(g, ag, pose, d_pos, d_t, mode, n, d_out);
+  POP_LAUNCH_CHECK(h);
+  h->n_launches++;
+  return POP_OK;
+}
+
 // slice range and voxel box of getObstaclePoints, in the reference's double arithmetic
 // (map.cpp:469-492); slice indices clamped to nt-1 (the reference reads one slice past the end)
 static BoxSpec make_box(const PopGeom& g, const float pose[3], double t_map, double t_start,
@@ -792,6 +808,18 @@ int popk_obstacle_points(pop_handle* h, int agent, double t_start, double t_end,
     k_obstacle_points<uint8_t><<<1, 1024, 0, h->stream>>>(g, ag, h->d_poses + 3 * agent, b, d_out, cap, d_count);
   else
     k_obstacle_points<float><<<1, 1024, 0, h->stream>>>(g, ag, h->d_poses + 3 * agent, b, d_out, cap, d_count);
+  POP_LAUNCH_CHECK(h);
+  h->n_launches++;
+  return POP_OK;
+}
+
+int popk_upload(pop_handle* h, int agent, const float* d_in) {
+  const PopGeom& g = h->geom;
+  uint8_t* ag = h->d_grid + agent * g.agent_stride;
+  if (h->cfg.cell_dtype == POP_CELL_U8)
+    k_upload<uint8_t><<<1184, 256, 0, h->stream>>>(g, ag, d_in);
+  else
+    k_upload<float><<<1184, 256, 0, h->stream>>>(g, ag, d_in);
   POP_LAUNCH_CHECK(h);
   h->n_launches++;
   return POP_OK;

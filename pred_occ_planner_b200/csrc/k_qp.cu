@@ -1166,7 +1166,7 @@ __global__ void __launch_bounds__(TILES ? kTt : kT, 1) k_qp_admm(QpDev Dv, QpPar
     Dv.prof[a * 8 + 3] = n_fact;
     Dv.prof[a * 8 + 4] = clk_g; Dv.prof[a * 8 + 5] = clk_k; Dv.prof[a * 8 + 6] = clk_r;
     Dv.prof[a * 8 + 7] = clk_e;
-#ifdef POP_QP_PHASE_PROF
+#if defined(POP_QP_PHASE_PROF) && POP_QP_PHASE_PROF == 2
     Dv.prof[a * 8 + 4] = S.dbg[0]; Dv.prof[a * 8 + 5] = S.dbg[1]; Dv.prof[a * 8 + 6] = S.dbg[2];   // factorisation split
 #endif
   }

@@ -6,6 +6,7 @@
 #include <cstdlib>
 #include <cstring>
 
+#include "pop_geom.cuh"
 #include "pop_internal.h"
 
 int pop_fail(pop_handle* h, int code, const char* fmt, ...) {
@@ -243,15 +244,8 @@ int pop_set_cylinders(pop_handle* h, const pop_cylinder* cyl, int n) {
   std::vector<PopCylDev> v(n);
   float max_vy = 0.f;
   for (int i = 0; i < n; i++) {
-    // casts of fake_particle_risk_voxel.cpp:133,137: Vector3f(cyl.x, cyl.y, .), Vector3f(cyl.vx, cyl.vy, 0)
-    v[i].x = static_cast<float>(cyl[i].x);
-    v[i].y = static_cast<float>(cyl[i].y);
-    v[i].vx = static_cast<float>(cyl[i].vx);
-    v[i].vy = static_cast<float>(cyl[i].vy);
-    v[i].w = cyl[i].w;
-    v[i].type = cyl[i].type;
-    v[i]._pad = 0;
-    if (v[i].type == 3 && std::fabs(v[i].vy) > max_vy) max_vy = std::fabs(v[i].vy);
+    geom_cyl_prepare(cyl[i], &v[i]);
+    if ((v[i].type == 3 || v[i].type == 2) && std::fabs(v[i].vy) > max_vy) max_vy = std::fabs(v[i].vy);
   }
   h->max_abs_vy = max_vy;
   if (n > 0) POP_CUDA(h, cudaMemcpyAsync(h->d_cyl, v.data(), sizeof(PopCylDev) * n, cudaMemcpyHostToDevice, h->stream));
@@ -339,6 +333,27 @@ int pop_map_query_dt(pop_handle* h, int agent, const double* pos, const double* 
   return query_common(h, agent, pos, nullptr, dt, n, out);
 }
 
+int pop_map_query_inflate(pop_handle* h, int agent, const double* pos, const double* t, int mode, int n, int8_t* out) {
+  if (!h || agent < 0 || agent >= h->cfg.n_agents_local || n < 0 || mode < 0 || mode > 2 ||
+      (n > 0 && (!pos || !out || (mode && !t)))) return POP_E_INVALID;
+  if (!h->map_ready) return pop_fail(h, POP_E_STATE, "query before the first map update");
+  if (n == 0) return POP_OK;
+  const size_t bpos = sizeof(double) * 3 * n, bt = sizeof(double) * n;
+  int rc = pop_ensure_scratch(h, bpos + bt + n + 64, 0);
+  if (rc) return rc;
+  uint8_t* d = static_cast<uint8_t*>(h->d_scratch);
+  double* d_pos = reinterpret_cast<double*>(d);
+  double* d_t = reinterpret_cast<double*>(d + bpos);
+  int8_t* d_out = reinterpret_cast<int8_t*>(d + bpos + bt);
+  POP_CUDA(h, cudaMemcpyAsync(d_pos, pos, bpos, cudaMemcpyHostToDevice, h->stream));
+  if (mode) POP_CUDA(h, cudaMemcpyAsync(d_t, t, bt, cudaMemcpyHostToDevice, h->stream));
+  rc = popk_query_inflate(h, agent, d_pos, d_t, mode, n, d_out);
+  if (rc) return rc;
+  POP_CUDA(h, cudaMemcpyAsync(out, d_out, n, cudaMemcpyDeviceToHost, h->stream));
+  POP_CUDA(h, cudaStreamSynchronize(h->stream));
+  return POP_OK;
+}
+
 int pop_map_obstacle_points(pop_handle* h, int agent, double t_start, double t_end, const double lc[3],
                             const double hc[3], double* out, int cap, int* n_out) {
   if (!h || agent < 0 || agent >= h->cfg.n_agents_local || !lc || !hc || cap < 0 || !n_out || (cap > 0 && !out)) return POP_E_INVALID;
@@ -376,6 +391,29 @@ int pop_map_add_particles(pop_handle* h, int agent, const double* pts, const flo
   rc = popk_add_particles(h, agent, d_pts, d_r, n, t_index);
   if (rc) return rc;
   POP_CUDA(h, cudaStreamSynchronize(h->stream));
+  return POP_OK;
+}
+
+int pop_map_future_risk(pop_handle* h, const float* risk, const float* poses, double stamp) {
+  if (!h || !risk) return POP_E_INVALID;
+  if (h->cfg.cell_dtype != POP_CELL_F32) return pop_fail(h, POP_E_UNSUPPORTED, "future-risk grids hold float risks: use POP_CELL_F32");
+  const size_t per = sizeof(float) * static_cast<size_t>(h->geom.V) * h->geom.nt;
+  int rc = pop_ensure_scratch(h, per, 0);
+  if (rc) return rc;
+  if (poses) {
+    rc = pop_set_poses(h, poses);
+    if (rc) return rc;
+  }
+  for (int a = 0; a < h->cfg.n_agents_local; a++) {
+    POP_CUDA(h, cudaMemcpyAsync(h->d_scratch, reinterpret_cast<const uint8_t*>(risk) + per * a, per, cudaMemcpyHostToDevice, h->stream));
+    rc = popk_upload(h, a, static_cast<const float*>(h->d_scratch));
+    if (rc) return rc;
+  }
+  h->t_map = stamp;
+  rc = popk_peer_project(h);
+  if (rc) return rc;
+  POP_CUDA(h, cudaStreamSynchronize(h->stream));
+  h->map_ready = true;
   return POP_OK;
 }
 

@@ -27,6 +27,97 @@ __device__ __forceinline__ float geom_axis_position(int i, float range, float re
   return __fadd_rn(__fsub_rn(__fmul_rn(static_cast<float>(i), res), range), pose);
 }
 
+// ---- ground-truth obstacle ownership (fake_particle_risk_voxel.cpp:127-152) --------------------------------------
+// fp32 3-vector arithmetic in the order Eigen 3.3's scalar code path evaluates the reference's Vector3f / Quaternionf
+// / Hyperplane<float, 3> expressions: reductions of a 3-vector pair c0 + (c1 + c2) (Core/Redux.h), cross is the plain
+// formula, q * v = v + w (2 vec x v) + vec x (2 vec x v) (Geometry/Quaternion.h).  POP_F* are the round-to-nearest
+// intrinsics on the device and the plain operators in host code (no FMA contraction there: -ffp-contract=off).
+#if defined(__CUDA_ARCH__) || !defined(__CUDACC__)
+#define POP_FADD(a, b) __fadd_rn(a, b)
+#define POP_FSUB(a, b) __fsub_rn(a, b)
+#define POP_FMUL(a, b) __fmul_rn(a, b)
+#define POP_FDIV(a, b) __fdiv_rn(a, b)
+#define POP_FSQRT(a) __fsqrt_rn(a)
+#else
+#define POP_FADD(a, b) ((a) + (b))
+#define POP_FSUB(a, b) ((a) - (b))
+#define POP_FMUL(a, b) ((a) * (b))
+#define POP_FDIV(a, b) ((a) / (b))
+#define POP_FSQRT(a) sqrtf(a)
+#endif
+__host__ __device__ __forceinline__ float geom_dot3(const float* a, const float* b) {
+  return POP_FADD(POP_FMUL(a[0], b[0]), POP_FADD(POP_FMUL(a[1], b[1]), POP_FMUL(a[2], b[2])));
+}
+__host__ __device__ __forceinline__ void geom_cross3(const float* a, const float* b, float* o) {
+  o[0] = POP_FSUB(POP_FMUL(a[1], b[2]), POP_FMUL(a[2], b[1]));
+  o[1] = POP_FSUB(POP_FMUL(a[2], b[0]), POP_FMUL(a[0], b[2]));
+  o[2] = POP_FSUB(POP_FMUL(a[0], b[1]), POP_FMUL(a[1], b[0]));
+}
+// q = (w, x, y, z)
+__host__ __device__ __forceinline__ void geom_quat_rotate(const float* q, const float* v, float* o) {
+  float uv[3], c[3];
+  geom_cross3(q + 1, v, uv);
+  for (int k = 0; k < 3; k++) uv[k] = POP_FADD(uv[k], uv[k]);
+  geom_cross3(q + 1, uv, c);
+  for (int k = 0; k < 3; k++) o[k] = POP_FADD(POP_FADD(v[k], POP_FMUL(q[0], uv[k])), c[k]);
+}
+// Hyperplane::Through(p0, p0 + q*(0,1,0), p0 + q*(1,0,0)) (fake_particle_risk_voxel.cpp:141-143): normal and offset
+__host__ __device__ __forceinline__ void geom_ring_plane(float cx, float cy, float cz, const float* q, float* n, float* off) {
+  const float pc[3] = {cx, cy, cz}, ey[3] = {0.f, 1.f, 0.f}, ex[3] = {1.f, 0.f, 0.f};
+  float r1[3], r2[3], v0[3], v1[3];
+  geom_quat_rotate(q, ey, r1);
+  geom_quat_rotate(q, ex, r2);
+  for (int k = 0; k < 3; k++) {
+    v0[k] = POP_FSUB(POP_FADD(pc[k], r2[k]), pc[k]);   // p2 - p0
+    v1[k] = POP_FSUB(POP_FADD(pc[k], r1[k]), pc[k]);   // p1 - p0
+  }
+  geom_cross3(v0, v1, n);
+  const float nn = POP_FSQRT(geom_dot3(n, n));
+  for (int k = 0; k < 3; k++) n[k] = POP_FDIV(n[k], nn);
+  *off = -geom_dot3(pc, n);
+}
+// pop_cylinder -> what the voxel update reads: the casts of fake_particle_risk_voxel.cpp:133,137,140-141 and, for a
+// ring, its plane
+__host__ __device__ __forceinline__ void geom_cyl_prepare(const pop_cylinder& c, PopCylDev* o) {
+  o->x = static_cast<float>(c.x);
+  o->y = static_cast<float>(c.y);
+  o->z = static_cast<float>(c.z);
+  o->vx = static_cast<float>(c.vx);
+  o->vy = static_cast<float>(c.vy);
+  o->w = c.w;
+  o->type = c.type;
+  o->n[0] = o->n[1] = o->n[2] = o->off = 0.f;
+  if (c.type == 2) {
+    const float q[4] = {static_cast<float>(c.qw), static_cast<float>(c.qx), static_cast<float>(c.qy), static_cast<float>(c.qz)};
+    geom_ring_plane(o->x, o->y, o->z, q, o->n, &o->off);
+  }
+}
+// The obstacle that owns the occupied voxel whose corner is (ptx, pty, ptz): the first, in id order, of
+//   type 3 (cylinder): |corner - (x, y, corner.z)| <= w + clearance, compared in double (:131-138);
+//   type 2 (ring): |w / 2 - dist(centre, projection on the ring's plane)| < 2 res (a double against an fp32 product)
+//                  and distance to the plane < 2 res (:139-150).
+// Returns its index or -1 (velocity 0).
+__device__ __forceinline__ int geom_gt_owner(const PopGeom& g, const PopCylDev* __restrict__ cyl, int n_cyl, float ptx,
+                                             float pty, float ptz) {
+  const float pt[3] = {ptx, pty, ptz};
+  const float two_res = POP_FMUL(2.0f, g.res);
+  for (int c = 0; c < n_cyl; c++) {
+    if (cyl[c].type == 3) {
+      const float d[3] = {POP_FSUB(ptx, cyl[c].x), POP_FSUB(pty, cyl[c].y), POP_FSUB(ptz, ptz)};
+      const float dist = POP_FSQRT(geom_dot3(d, d));
+      if (static_cast<double>(dist) <= cyl[c].w + static_cast<double>(g.clearance)) return c;
+    } else if (cyl[c].type == 2) {
+      const float sd = POP_FADD(geom_dot3(cyl[c].n, pt), cyl[c].off);
+      const float pc[3] = {cyl[c].x, cyl[c].y, cyl[c].z};
+      float d[3];
+      for (int k = 0; k < 3; k++) d[k] = POP_FSUB(pc[k], POP_FSUB(pt[k], POP_FMUL(sd, cyl[c].n[k])));
+      const float dist = POP_FSQRT(geom_dot3(d, d));
+      if (fabs(cyl[c].w / 2 - static_cast<double>(dist)) < static_cast<double>(two_res) && fabsf(sd) < two_res) return c;
+    }
+  }
+  return -1;
+}
+
 // ---- cell access -----------------------------------------------------------------------------
 // Layout: [agent][t][z][y][x], x fastest, one slice = V cells.  u8 cells hold exact small
 // integers (0/1 ground truth + unit peer risks); f32 cells hold the reference's float risks.
@@ -161,5 +252,33 @@ __device__ __forceinline__ int geom_query(const PopGeom& g, const uint8_t* grid,
       }
     }
   }
+  return 0;
+}
+
+// MapBase::getInflateOccupancy (map.cpp:345-395): single-voxel test.  mode 0 (pos): slice 0; mode 1 (pos, int t);
+// mode 2 (pos, double t): slices ceil(t / dt) and floor(t / dt).  A slice index equal to PREDICTION_TIMES, which the
+// reference lets through to read one slice past the end, answers -1 (mode 1) or is clamped to nt - 1 (mode 2).
+template <typename C>
+__device__ __forceinline__ int geom_inflate_query(const PopGeom& g, const uint8_t* grid, float posex, float posey,
+                                                  float posez, double px, double py, double pz, int mode, double t) {
+  const float fx = __fsub_rn(static_cast<float>(px), posex);
+  const float fy = __fsub_rn(static_cast<float>(py), posey);
+  const float fz = __fsub_rn(static_cast<float>(pz), posez);
+  const int idx = geom_voxel_index(g, fx, fy, fz);
+  if (!geom_in_range_f(g, fx, fy, fz)) return -1;
+  if (idx < 0 || idx >= g.V) return -1;
+  if (mode == 0) return Cell<C>::load(grid, idx) > g.risk_threshold ? 1 : 0;
+  if (mode == 1) {
+    const int ti = static_cast<int>(t);
+    if (ti < 0 || ti >= g.nt) return -1;
+    return Cell<C>::load(grid, static_cast<size_t>(ti) * g.V + idx) > g.risk_threshold ? 1 : 0;
+  }
+  const double q = t / static_cast<double>(g.dt);
+  int tc = static_cast<int>(ceil(q)), tf = static_cast<int>(floor(q));
+  tc = tc > g.nt - 1 ? g.nt - 1 : tc;
+  tf = tf > g.nt - 1 ? g.nt - 1 : tf;
+  if (tc < 0 || tf < 0) return -1;
+  if (Cell<C>::load(grid, static_cast<size_t>(tc) * g.V + idx) > g.risk_threshold) return 1;
+  if (Cell<C>::load(grid, static_cast<size_t>(tf) * g.V + idx) > g.risk_threshold) return 1;
   return 0;
 }

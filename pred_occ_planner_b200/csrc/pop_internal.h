@@ -25,9 +25,10 @@ struct PopGeom {
 struct PopCylDev {  // pop_cylinder reduced to what the voxel update reads
   float x, y;       // (float)cyl.x, (float)cyl.y
   float vx, vy;     // (float)cyl.vx, (float)cyl.vy
-  double w;         // compared in double: dist <= cyl.w + clearance_
-  int type;
-  int _pad;
+  double w;         // compared in double: dist <= cyl.w + clearance_ (type 3), |w / 2 - dist| < 2 res (type 2)
+  int type;         // 3 vertical cylinder, 2 vertical ring (fake_particle_risk_voxel.cpp:131-150)
+  float z;          // (float)cyl.z: ring centre
+  float n[3], off;  // type 2: the ring's plane, Hyperplane<float, 3>::Through(centre, centre + q*(0,1,0), centre + q*(1,0,0))
 };
 
 struct PopProfile {
@@ -63,7 +64,7 @@ struct pop_handle {
   int n_cloud = 0;
   PopCylDev* d_cyl = nullptr;
   int n_cyl = 0;
-  float max_abs_vy = 0.f;         // largest |vy| of the type-3 cylinders (tile reach of the voxel update)
+  float max_abs_vy = 0.f;         // largest |vy| of the obstacles that can own voxels (tile reach of the voxel update)
   float* d_poses = nullptr;       // n_local x 3
   int* d_occ_list = nullptr;      // n_local x max_cloud_points voxel indices of slice 0
   int* d_occ_count = nullptr;     // n_local
@@ -116,11 +117,13 @@ void popk_vox_free(pop_handle* h);
 int popk_peer_project(pop_handle* h);        // peer trajectories → particles → grid (K5)
 int popk_query(pop_handle* h, int agent, const double* d_pos, const int32_t* d_t,
                const double* d_dt, int n, int8_t* d_out);
+int popk_query_inflate(pop_handle* h, int agent, const double* d_pos, const double* d_t, int mode, int n, int8_t* d_out);
 int popk_obstacle_points(pop_handle* h, int agent, double t_start, double t_end, const double* lc,
                          const double* hc, double* d_out, int cap, int* d_count);
 int popk_add_particles(pop_handle* h, int agent, const double* d_pts, const float* d_risks, int n,
                        int t_index);
 int popk_download(pop_handle* h, int agent, float* d_out);
+int popk_upload(pop_handle* h, int agent, const float* d_in);
 
 // planning stage launchers -------------------------------------------------------------------------
 int popk_astar_alloc(pop_handle* h);

@@ -86,6 +86,19 @@ class PopEngine:
         self._check(self.lib.pop_map_update_gt(self._h, float(t_map)))
         self._t_map = float(t_map)
 
+    def map_future_risk(self, risk: np.ndarray, stamp: float, poses: np.ndarray | None = None):
+        """RiskBase::futureRiskCallback for every local agent: risk = n_local x V x T floats as published on
+        "map/future_risk"; then the peers are projected (risk_base.cpp:60-80)."""
+        c = self.cfg
+        risk = np.ascontiguousarray(risk, np.float32).reshape(self.n_local, c.nx * c.ny * c.nz, c.nt)
+        pp = None
+        if poses is not None:
+            poses = np.ascontiguousarray(poses, dtype=np.float32).reshape(self.n_local, 3)
+            self._poses = poses.copy()
+            pp = as_ptr(poses, C.c_float)
+        self._check(self.lib.pop_map_future_risk(self._h, as_ptr(risk, C.c_float), pp, float(stamp)))
+        self._t_map = float(stamp)
+
     def agent_map(self, agent: int) -> "AgentMap":
         return AgentMap(self, agent)
 
@@ -263,6 +276,19 @@ class AgentMap:
             tt = np.ascontiguousarray(np.broadcast_to(np.asarray(t, np.float64), (n,)))
             e._check(e.lib.pop_map_query_dt(e._h, self.agent, as_ptr(pos, C.c_double), as_ptr(tt, C.c_double), n,
                                             as_ptr(out, C.c_int8)))
+        return out
+
+    def getInflateOccupancy(self, pos, t=None):
+        """MapBase::getInflateOccupancy (map.cpp:345-395): t None → (pos); int t → (pos, int t) slice index;
+        float t → (pos, double t) seconds, testing the slices either side.  -1 out of range, 0, 1."""
+        pos = _f64(pos).reshape(-1, 3)
+        n = len(pos)
+        out = np.zeros(n, np.int8)
+        mode = 0 if t is None else (1 if np.issubdtype(np.asarray(t).dtype, np.integer) else 2)
+        tt = np.ascontiguousarray(np.broadcast_to(np.asarray(0.0 if t is None else t, np.float64), (n,)))
+        e = self.eng
+        e._check(e.lib.pop_map_query_inflate(e._h, self.agent, as_ptr(pos, C.c_double), as_ptr(tt, C.c_double), mode, n,
+                                             as_ptr(out, C.c_int8)))
         return out
 
     def getObstaclePoints(self, t_start, t_end, lower_corner, higher_corner, cap=None):

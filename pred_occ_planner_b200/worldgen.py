@@ -54,6 +54,41 @@ def make_world(seed: int, arena=(30.0, 30.0, 5.0), n_static=0, n_moving=40, v_ma
     return np.ascontiguousarray(cloud), cyl
 
 
+def make_rings(seed: int, arena=(30.0, 30.0, 5.0), n=4, v_max=1.0, r_range=(0.7, 2.5), z_range=(0.8, 2.0),
+               thickness=0.1, res_gen=0.1):
+    """Vertical ring obstacles as the reference's simulator makes them (uav_simulator/map_generator/include/
+    map_generator/moving_circle.h:43-110; "mixed" worlds of simulator_fake.launch:43-48): an ellipse of radii
+    r +- thickness/2 in a vertical plane turned by a random yaw, one point every res_gen/2 rad.  Their ground-truth
+    markers are of type 2 (SPHERE) with scale.x = 2 r2, the ring's pose and quaternion
+    (dynamic_forest_seq_sensing.cpp:205-254), which the ground-truth map's ring test reads
+    (plan_env/src/fake_particle_risk_voxel.cpp:139-150).  Returns (cloud float32 [m,3], rings CYL_DTYPE [n])."""
+    rng = _rng(seed)
+    ax, ay = arena[0] / 2 - 1.0, arena[1] / 2 - 1.0
+    cyl = np.zeros(n, dtype=CYL_DTYPE)
+    clouds = []
+    for i in range(n):
+        x, y, z = rng.uniform(-ax, ax), rng.uniform(-ay, ay), rng.uniform(*z_range)
+        vx, vy = rng.uniform(-v_max, v_max), rng.uniform(-v_max, v_max)
+        theta = rng.uniform(0.0, 2 * math.pi)
+        r = rng.uniform(*r_range)
+        x = math.floor(x / res_gen) * res_gen + res_gen / 2.0
+        y = math.floor(y / res_gen) * res_gen + res_gen / 2.0
+        z = math.floor(z / res_gen) * res_gen + res_gen / 2.0
+        rot = np.array([[math.cos(theta), -math.sin(theta), 0.0], [math.sin(theta), math.cos(theta), 0.0], [0.0, 0.0, 1.0]])
+        # q = Quaterniond(rot) * AngleAxisd(pi / 2, UnitY)
+        w1, v1 = math.cos(theta / 2), np.array([0.0, 0.0, math.sin(theta / 2)])
+        w2, v2 = math.cos(math.pi / 4), np.array([0.0, math.sin(math.pi / 4), 0.0])
+        qw = w1 * w2 - float(v1 @ v2)
+        qv = w1 * v2 + w2 * v1 + np.cross(v1, v2)
+        r1, r2 = r + thickness / 2, r - thickness / 2
+        ang = np.arange(0.0, 2 * math.pi, res_gen / 2)
+        local = np.stack([np.zeros_like(ang), r1 * np.cos(ang), r2 * np.sin(ang)], axis=1)
+        clouds.append((local @ rot.T + [x, y, z]).astype(np.float32))
+        cyl[i] = (2, 0, x, y, z, 2 * r2, z, vx, vy, qw, qv[0], qv[1], qv[2])
+    cloud = np.concatenate(clouds, axis=0) if clouds else np.zeros((0, 3), np.float32)
+    return np.ascontiguousarray(cloud), cyl
+
+
 def circle_agents(n: int, radius: float, z: float = 1.0):
     """Agents on a circle heading to their antipodes: (start [n,9] pos/vel/acc, goal [n,3])."""
     ang = 2 * np.pi * np.arange(n) / n

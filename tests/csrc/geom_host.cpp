@@ -11,6 +11,7 @@ static inline float __fadd_rn(float a, float b) { return a + b; }
 static inline float __fsub_rn(float a, float b) { return a - b; }
 static inline float __fmul_rn(float a, float b) { return a * b; }
 static inline float __fdiv_rn(float a, float b) { return a / b; }
+static inline float __fsqrt_rn(float a) { return sqrtf(a); }
 static inline unsigned atomicOr(unsigned* p, unsigned v) { unsigned o = *p; *p |= v; return o; }
 static inline unsigned atomicCAS(unsigned* p, unsigned c, unsigned v) { unsigned o = *p; if (o == c) *p = v; return o; }
 static inline float atomicExch(float* p, float v) { float o = *p; *p = v; return o; }
@@ -57,5 +58,13 @@ int dev_voxel_index(const pop_config* cfg, float x, float y, float z) { return g
 float dev_axis_position(const pop_config* cfg, int i, int axis, float pose) {
   const PopGeom g = geom_of(*cfg);
   return geom_axis_position(i, axis == 0 ? g.rx : axis == 1 ? g.ry : g.rz, g.res, pose);
+}
+// owner (index into cyl, -1 none) of each voxel corner, as the ground-truth voxel update decides it
+void dev_gt_owner(const pop_config* cfg, const pop_cylinder* cyl, int n_cyl, const float* corners, int n, int32_t* out) {
+  const PopGeom g = geom_of(*cfg);
+  PopCylDev* d = new PopCylDev[n_cyl > 0 ? n_cyl : 1];
+  for (int c = 0; c < n_cyl; c++) geom_cyl_prepare(cyl[c], &d[c]);
+  for (int i = 0; i < n; i++) out[i] = geom_gt_owner(g, d, n_cyl, corners[3 * i], corners[3 * i + 1], corners[3 * i + 2]);
+  delete[] d;
 }
 }

@@ -96,6 +96,16 @@ class OracleMap:
             self.lib.orc_map_query_dt(self.h, _p(pos, C.c_double), _p(tt, C.c_double), n, _p(out, C.c_int8))
         return out
 
+    def inflate_query(self, pos, t=None):
+        """getInflateOccupancy(pos) / (pos, int t) / (pos, double t)"""
+        pos = np.ascontiguousarray(pos, np.float64).reshape(-1, 3)
+        n = len(pos)
+        out = np.zeros(n, np.int8)
+        mode = 0 if t is None else (1 if np.issubdtype(np.asarray(t).dtype, np.integer) else 2)
+        tt = np.ascontiguousarray(np.broadcast_to(np.asarray(0.0 if t is None else t, np.float64), (n,)))
+        self.lib.orc_map_inflate_query(self.h, mode, _p(pos, C.c_double), _p(tt, C.c_double), n, _p(out, C.c_int8))
+        return out
+
     def obstacle_points(self, t0, t1, lc, hc, cap=200000):
         lc = np.ascontiguousarray(lc, np.float64)
         hc = np.ascontiguousarray(hc, np.float64)

@@ -43,10 +43,17 @@ class Publisher {
 class NodeHandle {
  public:
   std::map<std::string, double> values;
+  // parameters of node handles the test cannot reach (a `ros::NodeHandle nh("~")` local to the reference's main())
+  static std::map<std::string, double>& global_values() { static std::map<std::string, double> g; return g; }
+  NodeHandle() {}
+  explicit NodeHandle(const std::string&) {}
   template <class T>
   bool param(const std::string& name, T& var, const T& dflt) const {
     auto it = values.find(name);
-    if (it == values.end()) { var = dflt; return false; }
+    if (it == values.end()) {
+      it = global_values().find(name);
+      if (it == global_values().end()) { var = dflt; return false; }
+    }
     var = static_cast<T>(it->second);
     return true;
   }
@@ -62,6 +69,13 @@ class NodeHandle {
   template <class M> Publisher advertise(const std::string&, int, bool = false) { return Publisher(); }
   template <class... A> Timer createTimer(Duration, A&&...) { return Timer(); }
 };
+// process start-up and spinning: nothing to do, the tests call the callbacks
+inline void init(int&, char**, const std::string&) {}
+class AsyncSpinner { public: explicit AsyncSpinner(int) {} void start() {} void stop() {} };
+inline void waitForShutdown() {}
+inline void spin() {}
+inline void spinOnce() {}
+inline bool ok() { return false; }
 }  // namespace ros
 
 #define ROS_INFO(...) ((void)0)

@@ -14,6 +14,7 @@ template <class P> struct PointCloud {
   typedef std::shared_ptr<const PointCloud<P>> ConstPtr;
   void push_back(const P& p) { points.push_back(p); }
   size_t size() const { return points.size(); }
+  bool empty() const { return points.empty(); }
   void clear() { points.clear(); width = height = 0; }
   typename std::vector<P>::iterator begin() { return points.begin(); }
   typename std::vector<P>::iterator end() { return points.end(); }

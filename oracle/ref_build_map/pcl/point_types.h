@@ -10,6 +10,7 @@ struct PointXYZ {
 };
 struct PointXYZRGB { float x = 0, y = 0, z = 0; uint8_t r = 0, g = 0, b = 0; };
 struct PointXYZRGBA { float x = 0, y = 0, z = 0; uint8_t r = 0, g = 0, b = 0, a = 0; };
+struct PointNormal { float x = 0, y = 0, z = 0, normal_x = 0, normal_y = 0, normal_z = 0, curvature = 0; };
 struct PointXYZINormal { float x = 0, y = 0, z = 0, intensity = 0, normal_x = 0, normal_y = 0, normal_z = 0, curvature = 0; };
 }  // namespace pcl
 #endif

@@ -48,20 +48,24 @@ __device__ __forceinline__ bool dsp_vidx(const DspGeo& G, float px, float py, fl
   return true;
 }
 
-// rotateVectorByQuaternion :1379-1401 (att * (0, v) * att.inverse(), scalar products, left to right)
+// rotateVectorByQuaternion :1379-1401 (att * (0, v) * att.inverse())
 __device__ __forceinline__ void dsp_rotate(const float* v, const float* q, float* out) {
+  // Eigen 3.3 on x86-64 compiles Quaternionf * Quaternionf to its SSE kernel (Geometry/arch/Geometry_SSE.h,
+  // quat_product<Architecture::SSE, ., ., float>), whose lanes pair the eight products as written here; the squared norm of
+  // inverse() is a packet reduction, (x^2 + z^2) + (y^2 + w^2) (predux<Packet4f> without SSE3), and conjugate / n2 divides
+  // every coefficient.  This is the arithmetic the reference's binary runs on the hosts this repo is measured on.
   const float aw = q[0], ax = q[1], ay = q[2], az = q[3];
   const float bw = 0.f, bx = v[0], by = v[1], bz = v[2];
-  const float tw = aw * bw - ax * bx - ay * by - az * bz;
-  const float tx = aw * bx + ax * bw + ay * bz - az * by;
-  const float ty = aw * by + ay * bw + az * bx - ax * bz;
-  const float tz = aw * bz + az * bw + ax * by - ay * bx;
-  const float n2 = ax * ax + ay * ay + az * az + aw * aw;
+  const float tx = (ax * bw - az * by) + (ay * bz + aw * bx);
+  const float ty = (ay * bw - ax * bz) + (az * bx + aw * by);
+  const float tz = (az * bw - ay * bx) + (ax * by + aw * bz);
+  const float tw = (aw * bw - ax * bx) - (az * bz + ay * by);
+  const float n2 = (ax * ax + az * az) + (ay * ay + aw * aw);
   float iw = 0.f, ix = 0.f, iy = 0.f, iz = 0.f;
   if (n2 > 0.f) { iw = aw / n2; ix = -ax / n2; iy = -ay / n2; iz = -az / n2; }
-  out[0] = tw * ix + tx * iw + ty * iz - tz * iy;
-  out[1] = tw * iy + ty * iw + tz * ix - tx * iz;
-  out[2] = tw * iz + tz * iw + tx * iy - ty * ix;
+  out[0] = (tx * iw - tz * iy) + (ty * iz + tw * ix);
+  out[1] = (ty * iw - tx * iz) + (tz * ix + tw * iy);
+  out[2] = (tz * iw - ty * ix) + (tx * iy + tw * iz);
 }
 
 __device__ __forceinline__ float dot3(float x1, float y1, float z1, const float* b) {

@@ -284,6 +284,13 @@ int pop_replan_cycle(pop_handle* h, const pop_cycle_io* io);
  * (plan_manager/src/baseline.cpp:253-453) reading the map the particle-map node produced
  * (pop_dsp_update) or a ground-truth update.  io->poses and io->t_map are ignored. */
 int pop_plan_cycle(pop_handle* h, const pop_cycle_io* io);
+/* BaselinePlanner::isTrajSafe(T) x N (plan_manager/src/baseline.cpp:45-68 = baseline_fake.cpp:53-76), the FSM's trigger
+ * for an early replan (fake_plan_manager.cpp:144): every local agent's own trajectory (the last one a cycle published for
+ * it; pieces of corridor_tau seconds) is sampled every 0.1 s from wall-clock time t_now up to min(T, its duration) and
+ * tested with getClearOcccupancy(pos, dt) on the agent's current SOGM.  out_safe n_local (1 safe, 0 = a sample was
+ * occupied); out_t_unsafe (may be NULL) n_local: time of that sample relative to the trajectory start, else -1.
+ * T = fsm/colli_check_duration (2.0 in the reference's configs). */
+int pop_traj_safe_batch(pop_handle* h, double t_now, double T, int8_t* out_safe, double* out_t_unsafe);
 /* Same cycle with inputs already resident on the device (uploaded by the previous
  * pop_replan_cycle/pop_set_* calls); nothing is copied to the host. Async. */
 int pop_replan_cycle_resident(pop_handle* h, double t_map, double t_plan);

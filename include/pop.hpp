@@ -77,6 +77,12 @@ class Engine {
     check(pop_plan_cycle(h_, &io));
     return status;
   }
+  // BaselinePlanner::isTrajSafe(T) x N at wall-clock time t_now (1 = safe)
+  std::vector<int8_t> isTrajSafe(double t_now, double T) {
+    std::vector<int8_t> safe(cfg_.n_agents_local);
+    check(pop_traj_safe_batch(h_, t_now, T, safe.data(), nullptr));
+    return safe;
+  }
   void publishLocal() { check(pop_traj_publish_local(h_)); }
   void advance(double t_next) { check(pop_swarm_advance(h_, t_next)); }
 

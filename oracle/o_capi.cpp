@@ -287,6 +287,12 @@ int orc_replan(void* h, const double* offs, const int32_t* counts, const pop_tra
   return replan(m->grid, c, nullptr, ego_id, start9, goal3, t_plan, out, stats);
 }
 
+// isTrajSafe for nq (now, T) pairs on one trajectory record: out[q] 1 safe / 0, t_unsafe[q] relative time or -1
+void orc_traj_safe(void* h, const pop_traj_record* rec, double tau, int nq, const double* now, const double* T, int8_t* out,
+                   double* t_unsafe) {
+  const Grid& g = static_cast<OrcMap*>(h)->grid;
+  for (int q = 0; q < nq; q++) out[q] = traj_safe(g, *rec, tau, now[q], T[q], t_unsafe ? &t_unsafe[q] : nullptr) ? 1 : 0;
+}
 int orc_safe_after_opt(const pop_config* cfg, const double* offs, const int32_t* counts,
                        const pop_traj_record* recs, int ego_id, const double* cpts, int M, double t0) {
   Swarm s = make_swarm(*cfg, offs, counts, recs);

@@ -43,6 +43,30 @@ bool safe_after_opt(const Swarm& s, int ego_id, const std::vector<double>& cpts,
   return true;
 }
 
+// BaselinePlanner::isTrajSafe(T) (plan_manager/src/baseline.cpp:45-68 = baseline_fake.cpp:53-76): the planner's own
+// trajectory (pieces of `tau` seconds each — the double corridor_tau the optimiser was given, not the float32 of the
+// wire record) sampled every 0.1 s from `t_now` to min(T, duration); false at the first sample whose occupancy query
+// answers 1.  The sample times accumulate (`t += 0.1`), so they are reproduced by the same running sum.
+bool traj_safe(const Grid& g, const pop_traj_record& r, double tau, double t_now, double T, double* t_unsafe) {
+  if (t_unsafe) *t_unsafe = -1.0;
+  double t0 = t_now - r.start_time;
+  if (t0 < 0) t0 = 0;
+  if (t0 > T) return true;
+  if (r.n_pieces <= 0) return true;   // an empty traj_ has duration 0: the loop below never runs
+  const Bezier traj(std::vector<double>(r.n_pieces, tau), std::vector<double>(r.cpts, r.cpts + 15 * r.n_pieces));
+  const double dur = traj.T;
+  T = T > dur ? dur : T;
+  for (double t = t0; t < T; t += 0.1) {
+    const V3d pos = traj.pos(t);
+    const double dt = t + r.start_time - g.t_map;
+    if (query_dt(g, pos, dt) == 1) {
+      if (t_unsafe) *t_unsafe = t;
+      return false;
+    }
+  }
+  return true;
+}
+
 // returns POP_REPLAN_*; fills `out` on success
 int replan(const Grid& g, const pop_config& c, const Swarm* swarm, int ego_id, const double start[9],
            const double goal[3], double t_plan, pop_traj_record* out, int* stats) {

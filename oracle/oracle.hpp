@@ -169,6 +169,7 @@ bool separable(const std::vector<V3d>& A, const std::vector<V3d>& B);
 // Cycle — plan_manager/src/baseline_fake.cpp:253-453 + particles.cpp:223-283
 bool safe_after_opt(const Swarm& s, int ego_id, const std::vector<double>& cpts, int M, double t0);
 extern std::vector<double>* g_sep_trace;   // test hook: when set, safe_after_opt records its point sets instead of solving
+bool traj_safe(const Grid& g, const pop_traj_record& r, double tau, double t_now, double T, double* t_unsafe);
 int replan(const Grid& g, const pop_config& c, const Swarm* swarm, int ego_id, const double start[9],
            const double goal[3], double t_plan, pop_traj_record* out, int* stats);
 

@@ -18,3 +18,9 @@ extern "C" int ref_replan(const pop_config* cfg, FakeParticleRiskVoxel::query_dt
   return run_replan<FakeBaselinePlanner, FakeBaselineParameters>(cfg, query, obstacles, osqp, map, pose3, map_time, offs, counts,
                                                                  recs, now, t, start9, goal3, out_M, out_dur, out_cpts, stats);
 }
+
+extern "C" void ref_traj_safe(const pop_config* cfg, FakeParticleRiskVoxel::query_dt_fn query, void* map, const float* pose3,
+                              double map_time, int M, const double* dur, const double* cpts, double traj_start_time, int nq,
+                              const double* now, const double* T, int8_t* out) {
+  run_traj_safe<FakeBaselinePlanner, FakeBaselineParameters>(cfg, query, map, pose3, map_time, M, dur, cpts, traj_start_time, nq, now, T, out);
+}

@@ -28,16 +28,7 @@ static int solve_adapter(int n, int m, const double* P, const double*, const dou
 }
 
 
-template <class Planner, class Params>
-static int run_replan(const pop_config* cfg, FakeParticleRiskVoxel::query_dt_fn query, FakeParticleRiskVoxel::obstacle_fn obstacles,
-                      dense_osqp_fn osqp, void* map, const float* pose3, double map_time, const double* offs,
-                      const int32_t* counts, const pop_traj_record* recs, double now, double t, const double* start9,
-                      const double* goal3, int* out_M, double* out_dur, double* out_cpts, int* stats) {
-  std::ostringstream sink;
-  std::streambuf* old = std::cout.rdbuf(sink.rdbuf());
-  ros::Time::set_now(now);
-  ros::NodeHandle nh;
-  const pop_config& c = *cfg;
+static void fill_params(ros::NodeHandle& nh, const pop_config& c) {
   nh.values["search/max_tau"] = c.max_tau; nh.values["search/init_max_tau"] = c.max_tau;
   nh.values["search/max_vel"] = c.max_vel; nh.values["search/max_acc"] = c.max_acc;
   nh.values["search/w_time"] = c.w_time; nh.values["search/horizon"] = c.horizon;
@@ -51,6 +42,19 @@ static int run_replan(const pop_config* cfg, FakeParticleRiskVoxel::query_dt_fn 
   nh.values["swarm/drone_size_x"] = c.drone_size[0]; nh.values["swarm/drone_size_y"] = c.drone_size[1];
   nh.values["swarm/drone_size_z"] = c.drone_size[2];
   nh.values["swarm/replan_risk_rate"] = c.replan_risk_rate; nh.values["swarm/num_resample"] = c.num_resample;
+}
+
+template <class Planner, class Params>
+static int run_replan(const pop_config* cfg, FakeParticleRiskVoxel::query_dt_fn query, FakeParticleRiskVoxel::obstacle_fn obstacles,
+                      dense_osqp_fn osqp, void* map, const float* pose3, double map_time, const double* offs,
+                      const int32_t* counts, const pop_traj_record* recs, double now, double t, const double* start9,
+                      const double* goal3, int* out_M, double* out_dur, double* out_cpts, int* stats) {
+  std::ostringstream sink;
+  std::streambuf* old = std::cout.rdbuf(sink.rdbuf());
+  ros::Time::set_now(now);
+  ros::NodeHandle nh;
+  const pop_config& c = *cfg;
+  fill_params(nh, c);
   Params prm(nh);
   Planner planner(nh, nh, nh, prm);
   planner.init();
@@ -79,3 +83,29 @@ static int run_replan(const pop_config* cfg, FakeParticleRiskVoxel::query_dt_fn 
   return ok ? 1 : 0;
 }
 
+// isTrajSafe(T) (baseline_fake.cpp:53-76 / baseline.cpp:45-68) of a planner that holds the trajectory (dur[M], cpts 5M x 3,
+// started at traj_start_time) over the map behind `query`, asked at nq wall-clock times now[q] with horizons T[q].
+template <class Planner, class Params>
+static void run_traj_safe(const pop_config* cfg, FakeParticleRiskVoxel::query_dt_fn query, void* map, const float* pose3,
+                          double map_time, int M, const double* dur, const double* cpts, double traj_start_time, int nq,
+                          const double* now, const double* T, int8_t* out) {
+  std::ostringstream sink;
+  std::streambuf* old = std::cout.rdbuf(sink.rdbuf());
+  ros::NodeHandle nh;
+  fill_params(nh, *cfg);
+  Params prm(nh);
+  Planner planner(nh, nh, nh, prm);
+  planner.init();
+  planner.map_->query = query; planner.map_->map = map;
+  planner.map_->pose = Eigen::Vector3f(pose3[0], pose3[1], pose3[2]);
+  planner.map_->map_time = map_time;
+  Eigen::MatrixX3d c(5 * M, 3);
+  for (int i = 0; i < 5 * M; i++) for (int k = 0; k < 3; k++) c(i, k) = cpts[3 * i + k];
+  planner.traj_ = Bernstein::Bezier(std::vector<double>(dur, dur + M), c);
+  planner.traj_start_time_ = traj_start_time;
+  for (int q = 0; q < nq; q++) {
+    ros::Time::set_now(now[q]);
+    out[q] = planner.isTrajSafe(T[q]) ? 1 : 0;
+  }
+  std::cout.rdbuf(old);
+}

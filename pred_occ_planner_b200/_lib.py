@@ -174,6 +174,7 @@ SYMBOLS = [
     ("pop_set_body_particles", _I, [_VP, _PD, _PI32]),
     ("pop_set_trajectories", _I, [_VP, C.POINTER(PopTrajRecord)]),
     ("pop_map_update_gt", _I, [_VP, _D]),
+    ("pop_traj_safe_batch", _I, [_VP, _D, _D, _PI8, _PD]),
     ("pop_map_future_risk", _I, [_VP, _PF, _PF, _D]),
     ("pop_map_query", _I, [_VP, _I, _PD, _PI32, _I, _PI8]),
     ("pop_map_query_dt", _I, [_VP, _I, _PD, _PD, _I, _PI8]),

@@ -10,6 +10,7 @@
 #include <cstring>
 
 #include "pop_bezier.cuh"
+#include "pop_geom.cuh"
 #include "pop_internal.h"
 
 namespace {
@@ -37,6 +38,41 @@ __global__ void k_traj_sample(const pop_traj_record* __restrict__ recs, int n_ag
   const bool ok = sample_record(recs[a], t_abs[k], pva);
   for (int q = 0; q < 9; q++) out[static_cast<size_t>(i) * 9 + q] = pva[q];
   valid[i] = ok ? 1 : 0;
+}
+
+// BaselinePlanner::isTrajSafe(T) (plan_manager/src/baseline.cpp:45-68 = baseline_fake.cpp:53-76) for every local agent:
+// its own trajectory (the last one it planned; pieces of tau = corridor_tau seconds in double, as the optimiser was
+// given them — not the float32 durations of the wire record) sampled every 0.1 s from t_now to min(T, duration) by the
+// reference's running sum `t += 0.1`; unsafe at the first sample whose getClearOcccupancy(pos, dt) answers 1.
+template <typename C>
+__global__ void k_traj_safe(PopGeom g, const uint8_t* __restrict__ grid, const float* __restrict__ poses,
+                            const pop_traj_record* __restrict__ send, int n_local, double tau, double t_map, double t_now,
+                            double T, int8_t* __restrict__ safe, double* __restrict__ t_unsafe) {
+  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= n_local) return;
+  const pop_traj_record& r = send[a];
+  int8_t ok = 1;
+  double tu = -1.0;
+  double t0 = __dsub_rn(t_now, r.start_time);
+  if (t0 < 0) t0 = 0;
+  if (!(t0 > T) && r.n_pieces > 0 && r.n_pieces <= POP_MAX_PIECES) {
+    double durs[POP_MAX_PIECES], dur = 0.0;
+    for (int k = 0; k < POP_MAX_PIECES; k++) durs[k] = tau;
+    for (int k = 0; k < r.n_pieces; k++) dur = __dadd_rn(dur, tau);
+    const double Tc = T > dur ? dur : T;
+    const uint8_t* ag = grid + a * g.agent_stride;
+    const float px = poses[3 * a], py = poses[3 * a + 1], pz = poses[3 * a + 2];
+    for (double t = t0; t < Tc; t = __dadd_rn(t, 0.1)) {
+      double pos[3];
+      pop_bezier_eval(durs, r.n_pieces, r.cpts, t, 0, pos);
+      const double dt = __dsub_rn(__dadd_rn(t, r.start_time), t_map);
+      int ti = static_cast<int>(floor(__ddiv_rn(dt, static_cast<double>(g.dt))));
+      ti = ti > g.nt - 1 ? g.nt - 1 : ti;
+      if (geom_query<C>(g, ag, px, py, pz, pos[0], pos[1], pos[2], ti) == 1) { ok = 0; tu = t; break; }
+    }
+  }
+  safe[a] = ok;
+  t_unsafe[a] = tu;
 }
 
 // perfect tracking: the state handed to the next replan is the commanded state at t_next; past the end of the
@@ -137,6 +173,28 @@ int pop_traj_sample_batch(pop_handle* h, int all_agents, const double* t_abs, in
   h->n_launches++;
   POP_CUDA(h, cudaMemcpyAsync(out_pva, d_out, sizeof(double) * 9 * n_out, cudaMemcpyDeviceToHost, h->stream));
   POP_CUDA(h, cudaMemcpyAsync(out_valid, d_valid, n_out, cudaMemcpyDeviceToHost, h->stream));
+  POP_CUDA(h, cudaStreamSynchronize(h->stream));
+  return POP_OK;
+}
+
+int pop_traj_safe_batch(pop_handle* h, double t_now, double T, int8_t* out_safe, double* out_t_unsafe) {
+  if (!h || !out_safe) return POP_E_INVALID;
+  if (!h->map_ready) return pop_fail(h, POP_E_STATE, "isTrajSafe before the first map update");
+  const int nl = h->cfg.n_agents_local;
+  int rc = pop_ensure_scratch(h, nl * (sizeof(double) + 1) + 64, 0);
+  if (rc) return rc;
+  double* d_tu = static_cast<double*>(h->d_scratch);
+  int8_t* d_safe = reinterpret_cast<int8_t*>(d_tu + nl);
+  if (h->cfg.cell_dtype == POP_CELL_U8)
+    k_traj_safe<uint8_t><<<(nl + 63) / 64, 64, 0, h->stream>>>(h->geom, h->d_grid, h->d_poses, h->d_traj_send, nl, h->cfg.corridor_tau,
+                                                             h->t_map, t_now, T, d_safe, d_tu);
+  else
+    k_traj_safe<float><<<(nl + 63) / 64, 64, 0, h->stream>>>(h->geom, h->d_grid, h->d_poses, h->d_traj_send, nl, h->cfg.corridor_tau,
+                                                           h->t_map, t_now, T, d_safe, d_tu);
+  POP_LAUNCH_CHECK(h);
+  h->n_launches++;
+  POP_CUDA(h, cudaMemcpyAsync(out_safe, d_safe, nl, cudaMemcpyDeviceToHost, h->stream));
+  if (out_t_unsafe) POP_CUDA(h, cudaMemcpyAsync(out_t_unsafe, d_tu, sizeof(double) * nl, cudaMemcpyDeviceToHost, h->stream));
   POP_CUDA(h, cudaStreamSynchronize(h->stream));
   return POP_OK;
 }

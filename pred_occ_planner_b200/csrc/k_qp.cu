@@ -91,7 +91,7 @@ constexpr int kSmemBytes = 232448;   // 227 KB opt-in maximum per CTA on sm_100a
 constexpr int kRedN = 12;
 constexpr int kVec = kMaxN + 6;      // vectors padded so 6-wide tile loads stay in bounds
 constexpr int kTileNB = 25;          // register-tile path: n <= 150 → <= 325 tiles of 6x6
-// Shared memory of the register-tile variant: header + partial sums (150 x 28 + 26 x 150) + Kb + products
+// Shared memory of the register-tile variant: header + staging / partial sums (25 x 150) + Kb + products
 // + types for n <= 150, m <= 3 kT.  Leaving the rest of the 256 KB to L1 keeps the set-up arrays
 // and the few spilled row constants close.
 constexpr int kSmemTiles = 136 * 1024;
@@ -114,8 +114,10 @@ struct Smem {
   double rho_v[3], rinv_v[3];   // indexed by type+1: loose, inequality, equality
   int face_off[POP_MAX_PIECES + 1];
   int M, n, m, ms, nnz, status, fail;
-  unsigned short cptr[kMaxN + 2];   // start of column c in pc (padded: start = 2c mod 16)
+  unsigned short cptr[kMaxN + 2];   // start of column c in pc
   unsigned short clen[kMaxN + 2];   // entries of column c
+  unsigned short cstr[kMaxN + 2];   // of which in structured rows (set-up only)
+  unsigned short rounds[POP_MAX_PIECES];   // gather rounds of piece i: columns padded to 8 * rounds entries
   int pc_len, max_clen;
   long long dbg[4];   // POP_QP_PHASE_PROF: cycles of K assembly, Cholesky, substitution + tiles
 };
@@ -264,7 +266,7 @@ __device__ __forceinline__ int linv_off(int i) {
   return (i & 1) ? 2 * (q + 1) * (q + 1) : 2 * q * (q + 1);
 }
 
-struct TileId { int rb, cb, NB, NBp; bool act; };
+struct TileId { int rb, cb, NB; bool act; };
 
 // K = P + sigma I + A' diag(rho) A → banded Cholesky → L^-1, all in shared memory.
 //   1. thread per band entry: P block + safety rows (same control point only) + structured rows
@@ -415,68 +417,68 @@ __device__ void factorize(Smem& S, double* __restrict__ Linv, double (&T)[NT], c
 
 // ---- K^-1 application, register-tile path (n <= 150) -----------------------------------------
 // Thread t < NB(NB+1)/2 holds the 6x6 tile (rb, cb), cb <= rb, of the SYMMETRIC K^-1 (NB = ceil(n/6))
-// and uses it for both triangles in one pass:
-//   partA[6 rb + i][cb] = tile[i][:] . rhs[6 cb ..]        (row side)
-//   partB[6 cb + j][rb] = tile[:][j] . rhs[6 rb ..]        (column side, off-diagonal tiles only)
-//   xt[i] = sum_cb partA[i][cb] + sum_rb partB[i][rb]      (two lanes per output, one per side)
-// then x = alpha xt + (1 - alpha) x_prev.  partA and partB, both [6NB][NBp], are zero outside the
-// entries the tiles write, so the sums run over whole rows / columns without masking.  FMA is
-// fine here: bit parity of this solve with a CPU factorisation is not attainable anyway.
+// and uses it for both triangles in one pass.  Partial sums go to ONE dense array P[NB][Lp]:
+//   P[cb][6 rb + i] = tile[i][:] . rhs[6 cb ..]        (row side)
+//   P[rb][6 cb + j] = tile[:][j] . rhs[6 rb ..]        (column side, off-diagonal tiles only)
+// Row k of P therefore holds, for every output i in block b, the contribution of column block k (k <= b: a row
+// side, k > b: a column side): every entry is written exactly once per application — nothing to zero, nothing to
+// mask — and xt[i] = sum_k P[k][i].  Each side is six contiguous doubles (three 16-byte stores); Lp = 2 (mod 4)
+// makes the lanes of a quarter-warp (consecutive cb, stride Lp or 6 doubles) fall on distinct 16-byte bank groups,
+// and the reduction reads 32 consecutive doubles per warp and k.  Then x = alpha xt + (1 - alpha) x_prev.
+// FMA is fine here: bit parity of this solve with a CPU factorisation is not attainable anyway.
 template <int NT>
 __device__ __forceinline__ void kkt_tiles(Smem& S, const double (&T)[NT], const TileId& ti,
-                                          double* __restrict__ partA, double* __restrict__ partB) {
+                                          double* __restrict__ P, int Lp) {
   const int n = S.n, tid = threadIdx.x;
   if (ti.act) {
     const double2* xc = reinterpret_cast<const double2*>(S.rhs + 6 * ti.cb);
-    const double2* xr = reinterpret_cast<const double2*>(S.rhs + 6 * ti.rb);
     const double2 c01 = xc[0], c23 = xc[1], c45 = xc[2];
-    double* outA = partA + (6 * ti.rb) * ti.NBp + ti.cb;
+    double s[6];
 #pragma unroll
     for (int i = 0; i < 6; i++) {
-      double s = T[i * 6] * c01.x;
-      s = fma(T[i * 6 + 1], c01.y, s);
-      s = fma(T[i * 6 + 2], c23.x, s);
-      s = fma(T[i * 6 + 3], c23.y, s);
-      s = fma(T[i * 6 + 4], c45.x, s);
-      s = fma(T[i * 6 + 5], c45.y, s);
-      outA[i * ti.NBp] = s;
+      double a = T[i * 6] * c01.x;
+      a = fma(T[i * 6 + 1], c01.y, a);
+      a = fma(T[i * 6 + 2], c23.x, a);
+      a = fma(T[i * 6 + 3], c23.y, a);
+      a = fma(T[i * 6 + 4], c45.x, a);
+      a = fma(T[i * 6 + 5], c45.y, a);
+      s[i] = a;
     }
+    double2* outA = reinterpret_cast<double2*>(P + ti.cb * Lp + 6 * ti.rb);
+    outA[0] = make_double2(s[0], s[1]); outA[1] = make_double2(s[2], s[3]); outA[2] = make_double2(s[4], s[5]);
     if (ti.rb != ti.cb) {
+      const double2* xr = reinterpret_cast<const double2*>(S.rhs + 6 * ti.rb);
       const double2 r01 = xr[0], r23 = xr[1], r45 = xr[2];
       double o[6];
 #pragma unroll
       for (int j = 0; j < 6; j++) {
-        double s = T[j] * r01.x;
-        s = fma(T[6 + j], r01.y, s);
-        s = fma(T[12 + j], r23.x, s);
-        s = fma(T[18 + j], r23.y, s);
-        s = fma(T[24 + j], r45.x, s);
-        s = fma(T[30 + j], r45.y, s);
-        o[j] = s;
+        double a = T[j] * r01.x;
+        a = fma(T[6 + j], r01.y, a);
+        a = fma(T[12 + j], r23.x, a);
+        a = fma(T[18 + j], r23.y, a);
+        a = fma(T[24 + j], r45.x, a);
+        a = fma(T[30 + j], r45.y, a);
+        o[j] = a;
       }
-      double* outB = partB + (6 * ti.cb) * ti.NBp + ti.rb;
-#pragma unroll
-      for (int j = 0; j < 6; j++) outB[j * ti.NBp] = o[j];
+      double2* outB = reinterpret_cast<double2*>(P + ti.rb * Lp + 6 * ti.cb);
+      outB[0] = make_double2(o[0], o[1]); outB[1] = make_double2(o[2], o[3]); outB[2] = make_double2(o[4], o[5]);
     }
   }
   __syncthreads();
-  {
-    // both sides keep the same [output][NBp] layout, so the two lanes of an output run the same
-    // instruction stream (no divergence): NBp/2 16-byte loads each
-    const int i = tid >> 1, side = tid & 1;
-    double a = 0, b = 0;
-    if (i < n) {
-      const double2* pr = reinterpret_cast<const double2*>((side ? partB : partA) + i * ti.NBp);
-      const int cnt = ti.NBp >> 1;
-#pragma unroll 4
-      for (int k = 0; k < cnt; k++) { const double2 v = pr[k]; a += v.x; b += v.y; }
+  if (tid < n) {
+    // rows NB .. 4 ceil(NB / 4) of P are zero (never written by a tile): a uniform loop of four independent
+    // loads and adds per round, no predicates
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    const double* pr = P + tid;
+    const int rounds = (ti.NB + 3) >> 2, step = 4 * Lp;
+    for (int k = 0; k < rounds; k++) {
+      const double v0 = pr[0], v1 = pr[Lp], v2 = pr[2 * Lp], v3 = pr[3 * Lp];
+      pr += step;
+      a0 += v0; a1 += v1; a2 += v2; a3 += v3;
     }
-    double xt = a + b;
-    xt += __shfl_xor_sync(0xffffffffu, xt, 1);
-    if (i < n && side == 0) {
-      S.xt[i] = xt;
-      S.x[i] = ALPHA * xt + (1.0 - ALPHA) * S.xp[i];
-    }
+    const double xt = (a0 + a1) + (a2 + a3);
+    S.xt[tid] = xt;
+    S.x[tid] = ALPHA * xt + (1.0 - ALPHA) * S.xp[tid];
   }
   __syncthreads();
 }
@@ -597,20 +599,17 @@ __device__ __forceinline__ void kkt_solve(Smem& S, const double* __restrict__ Li
   __syncthreads();
 }
 
-// (A' u)_c = sum of the column-c segment of pc: 2 lanes per column (n <= 180 → 360 threads),
-// the lane's first entry and entry count stay in registers; fixed order, one shuffle.  Every
-// thread of the CTA calls this; the even lane of column c < n gets the sum.
-// `trips` is the CTA-wide maximum entry count rounded up to 4, so the loop is uniform and fully
-// pipelined (4 independent loads per trip); entries past the lane's own count are read (they belong
-// to the next column or the padded tail of pc) and masked to +0.0.
-__device__ __forceinline__ double gather_col(const double* __restrict__ pq, int cnt, int trips) {
+// (A' u)_c = sum of the column-c segment of pc.  Warp i gathers the 15 columns of piece i, two lanes per column
+// (lane h takes entries h, h + 2, ... with four accumulators, then one shuffle).  All columns of a piece are padded
+// with never-written zero slots to the same length 8 R_i (+2 slots of skew, see the set-up), so the loop is
+// warp-uniform, unpredicated and unmasked: R_i rounds of four independent loads and adds per lane.  Fixed order.
+// Every thread of the CTA calls this; the even lane of a column gets the sum.
+__device__ __forceinline__ double gather_col(const double* __restrict__ pq, int rounds) {
   double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
-  for (int k = 0; k < trips; k += 4) {
-    const double v0 = pq[2 * k], v1 = pq[2 * k + 2], v2 = pq[2 * k + 4], v3 = pq[2 * k + 6];
-    s0 += k < cnt ? v0 : 0.0;
-    s1 += k + 1 < cnt ? v1 : 0.0;
-    s2 += k + 2 < cnt ? v2 : 0.0;
-    s3 += k + 3 < cnt ? v3 : 0.0;
+  for (int r = 0; r < rounds; r++) {
+    const double v0 = pq[0], v1 = pq[2], v2 = pq[4], v3 = pq[6];
+    pq += 8;
+    s0 += v0; s1 += v1; s2 += v2; s3 += v3;
   }
   double s = (s0 + s1) + (s2 + s3);
   s += __shfl_xor_sync(0xffffffffu, s, 1);
@@ -674,15 +673,16 @@ __global__ void __launch_bounds__(TILES ? kTt : kT, 1) k_qp_admm(QpDev Dv, QpPar
   const int n = S.n, m = S.m, ms = S.ms, nnz = S.nnz;
   if (((n + 5) / 6 <= kTileNB && m <= 3 * kTt) != TILES) return;   // the other variant's problem
   const int NBt = (n + 5) / 6;
-  // TILES: staging rows (6 x 6NB) / partial sums (6NB x NBp) instead of the packed factor
-  int NBpt = ((NBt + 1) & ~1) | 2;
-  if (NBpt < NBt) NBpt += 4;
-  const int part1_len = 6 * NBt * NBpt, part2_len = part1_len;
-  // TILES: [staging 36 NB | Kb 16 n] during a factorisation, [partA | partB] during the iterations
-  const int linv_len = TILES ? max(36 * NBt + n * kBand, part1_len + part2_len) : linv_off((n + 1) & ~1);
+  // TILES: staging rows (6 x 6NB) / partial sums P[NB][Lp] instead of the packed factor
+  int Lpt = 6 * NBt;
+  if ((Lpt & 3) != 2) Lpt += 2;   // Lp = 2 (mod 4): see kkt_tiles
+  // TILES: [staging 36 NB | Kb 16 n] during a factorisation, P during the iterations
+  const int linv_len = TILES ? max(36 * NBt + n * kBand, ((NBt + 3) & ~3) * Lpt) : linv_off((n + 1) & ~1);
   // the banded K lives inside the staging area (TILES) or on top of the product array (it is dead
   // during a factorisation and rewritten right after), so it costs no shared memory of its own
-  const int pc_len_max = max(nnz + 16 * n + 2 + 128, TILES ? 0 : n * kBand);
+  // product array: every column of piece i takes 8 R_i + 2 slots, R_i = ceil(longest column of the piece / 8); a column
+  // holds one entry per face of its piece plus at most 11 structured entries
+  const int pc_len_max = max(15 * (S.face_off[M] + 20 * M) + 8, TILES ? 0 : n * kBand);
   const size_t dyn_bytes = sizeof(double) * (static_cast<size_t>(linv_len) + pc_len_max) +
                            ((m + 15) & ~15) + 16 + (TILES ? sizeof(double) * 2 * static_cast<size_t>(m) : 0);
   if (m > kRowCap || kHdrBytes + dyn_bytes > (TILES ? kSmemTiles : kSmemBytes)) {
@@ -710,43 +710,67 @@ __global__ void __launch_bounds__(TILES ? kTt : kT, 1) k_qp_admm(QpDev Dv, QpPar
   }
   for (int e = tid; e < M * 225; e += KT) Pblk[e] = Dv.QM[e % 225];
   for (int e = tid; e < linv_len; e += KT) Linv[e] = 0.0;   // row pads stay zero
-  for (int e = tid; e < nnz + 16 * n + 2 + 128; e += KT) pc[e] = 0.0;   // pads are read (masked) by gather_col: keep them finite
+  for (int e = tid; e < pc_len_max; e += KT) pc[e] = 0.0;   // the pad slots of the columns stay zero for the whole solve
   if (tid < kVec) { S.D[tid] = 1.0; S.x[tid] = 0.0; S.xp[tid] = 0.0; S.xt[tid] = 0.0; S.rhs[tid] = 0.0; S.tn[tid] = 0.0; S.rd[tid] = 0.0; }
   __syncthreads();
-  // column index: entries of column j in ascending row order
-  if (tid == 0) csc_ptr[0] = 0;
-  if (tid < n) {
-    int cnt = 0;
-    for (int r = 0; r < m; r++)
-      for (int k = 0; k < kEll; k++) if (ell_col[r * kEll + k] == tid) cnt++;
-    S.tn[tid] = cnt;
-  }
-  __syncthreads();
-  if (tid == 0) {
-    int run = 0, prun = 0;
-    for (int j = 0; j < n; j++) {
-      const int len = static_cast<int>(S.tn[j]);
-      while ((prun & 15) != ((2 * j) & 15)) prun++;
-      S.cptr[j] = static_cast<unsigned short>(prun);
-      S.clen[j] = static_cast<unsigned short>(len);
-      prun += len;
-      run += len;
-      csc_ptr[j + 1] = run;
+  // column index: entries of column j in ascending row order.  A column holds its structured entries (rows < ms:
+  // boundary / continuity rows and the velocity and acceleration boxes) first, then one entry per face of its piece
+  // (safety row of face j, control point k, dimension d sits in column 15 i + 3 k + d), so only the structured rows
+  // need a scan: their column numbers are staged in shared memory (the product array is still free) and every
+  // column thread walks that list with broadcast loads; the safety entries are placed in parallel by formula.
+  {
+    int* scol = reinterpret_cast<int*>(pc);   // [ms][6]
+    for (int e = tid; e < ms * kEll; e += KT) scol[e] = ell_col[e];
+    if (tid == 0) csc_ptr[0] = 0;
+    __syncthreads();
+    if (tid < n) {
+      int cnt = 0;
+      for (int e = 0; e < ms * kEll; e++) cnt += scol[e] == tid;
+      S.cstr[tid] = static_cast<unsigned short>(cnt);
+      const int i = tid / 15;
+      S.clen[tid] = static_cast<unsigned short>(cnt + S.face_off[i + 1] - S.face_off[i]);
     }
-    S.pc_len = prun;
-    int mx = 0;
-    for (int j = 0; j < n; j++) mx = max(mx, static_cast<int>(S.clen[j]));
-    S.max_clen = mx;
-    if (run != nnz || prun > nnz + 16 * n) S.fail = 2;
+    __syncthreads();
+    if (tid == 0) {
+      // Column c of piece i starts at base_i + (c - 15 i) S_i with S_i = 8 R_i + 2: S_i = 2 (mod 8) spreads the 30 lanes
+      // of the gathering warp (entry h + 2k of 15 consecutive columns) evenly over the 16 eight-byte bank pairs.
+      int run = 0, prun = 0, mx = 0;
+      for (int i = 0; i < M; i++) {
+        int L = 0;
+        for (int j = 15 * i; j < 15 * i + 15; j++) L = max(L, static_cast<int>(S.clen[j]));
+        const int R = (L + 7) >> 3, Si = 8 * R + 2;
+        S.rounds[i] = static_cast<unsigned short>(R);
+        for (int j = 0; j < 15; j++) S.cptr[15 * i + j] = static_cast<unsigned short>(prun + j * Si);
+        prun += 15 * Si;
+        mx = max(mx, L);
+      }
+      for (int j = 0; j < n; j++) { run += S.clen[j]; csc_ptr[j + 1] = run; }
+      S.pc_len = prun;
+      S.max_clen = mx;
+      if (run != nnz || prun + 1 > pc_len_max) S.fail = 2;
+    }
+    __syncthreads();
+    if (tid < n) {
+      int w = csc_ptr[tid], pw = S.cptr[tid];
+      for (int e = 0; e < ms * kEll; e++)
+        if (scol[e] == tid) { dstv[e] = static_cast<unsigned short>(pw++); csc_idx[w++] = e; }
+    }
+    for (int r = ms + tid; r < m; r += KT) {
+      const int q = (r - ms) / 5, k = (r - ms) % 5;
+      int i = 0;
+      while (i + 1 < M && q >= S.face_off[i + 1]) i++;
+      const int j = q - S.face_off[i];
+#pragma unroll
+      for (int d = 0; d < 3; d++) {
+        const int c = 15 * i + 3 * k + d;
+        dstv[r * kEll + d] = static_cast<unsigned short>(S.cptr[c] + S.cstr[c] + j);
+        csc_idx[csc_ptr[c] + S.cstr[c] + j] = r * kEll + d;
+      }
+    }
+    __syncthreads();
+    for (int e = tid; e < ms * kEll + 2; e += KT) pc[e >> 1] = 0.0;   // the staging area goes back to the product array
+    __syncthreads();
   }
-  __syncthreads();
-  if (tid < n) {
-    int w = csc_ptr[tid], pw = S.cptr[tid];
-    for (int r = 0; r < m; r++)
-      for (int k = 0; k < kEll; k++)
-        if (ell_col[r * kEll + k] == tid) { dstv[r * kEll + k] = static_cast<unsigned short>(pw++); csc_idx[w++] = r * kEll + k; }
-  }
-  __syncthreads();
   if (S.fail) {
     if (tid == 0) { Dv.status[a] = -21; Dv.iters[a] = 0; }
     return;
@@ -819,8 +843,6 @@ __global__ void __launch_bounds__(TILES ? kTt : kT, 1) k_qp_admm(QpDev Dv, QpPar
   // ---- register tile of L^-1 (n <= 150) ----
   TileId ti;
   ti.NB = (n + 5) / 6;
-  ti.NBp = ((ti.NB + 1) & ~1) | 2;   // even, = 2 (mod 4): row stride is an odd number of 16-byte units
-  if (ti.NBp < ti.NB) ti.NBp += 4;
   constexpr bool tiles = TILES;
   ti.rb = 0; ti.cb = 0;
   {
@@ -836,10 +858,12 @@ __global__ void __launch_bounds__(TILES ? kTt : kT, 1) k_qp_admm(QpDev Dv, QpPar
   auto refactor = [&]() {
     const long long c0k = clock64();
     factorize<TILES>(S, Linv, T, ti, Kb, type, ell_col, ell_val, csc_ptr, csc_idx, Pblk);
-    if constexpr (TILES) {   // the staging area becomes the partial-sum buffers: zero outside the tiles
-      for (int e = tid; e < linv_len; e += KT) Linv[e] = 0.0;
-      __syncthreads();
+    if constexpr (TILES) {   // the staging area becomes P again: its pad rows (NB .. 4 ceil(NB / 4)) must read as zero
+      for (int e = NBt * Lpt + tid; e < ((NBt + 3) & ~3) * Lpt; e += KT) Linv[e] = 0.0;
+    } else {                 // the banded K sat on the product array: its pad slots must read as zero again
+      for (int e = tid; e < pc_len_max; e += KT) pc[e] = 0.0;
     }
+    __syncthreads();
     clk_fact += clock64() - c0k; n_fact++;
   };
   refactor();
@@ -901,11 +925,11 @@ __global__ void __launch_bounds__(TILES ? kTt : kT, 1) k_qp_admm(QpDev Dv, QpPar
   auto dot0 = [&](const double* x) {
     double s = 0;
 #pragma unroll
-    for (int k = 0; k < kEll; k++) s += v0[k] * x[COL0(k)];
+    for (int k = 0; k < kEll; k++) s = fma(v0[k], x[COL0(k)], s);   // fused: see kkt_tiles on bit parity
     return s;
   };
   auto dots = [&](int s, const double* x) {
-    return (vs[s][0] * x[bs[s]] + vs[s][1] * x[bs[s] + 1]) + vs[s][2] * x[bs[s] + 2];
+    return fma(vs[s][2], x[bs[s] + 2], fma(vs[s][1], x[bs[s] + 1], vs[s][0] * x[bs[s]]));
   };
   auto put0 = [&](double u) {
 #pragma unroll
@@ -923,12 +947,14 @@ __global__ void __launch_bounds__(TILES ? kTt : kT, 1) k_qp_admm(QpDev Dv, QpPar
       if ((s + 1) * KT < m) puts(s, sel == 0 ? S.rho_v[1] * zs[s] - ys[s] : (sel == 1 ? ys[s] : dy[s + 1]));
   };
 
-  const int gc = tid >> 1;                    // this thread's gather column
-  const bool gl0 = (tid & 1) == 0 && gc < n;
-  // entries cptr[gc] + lane, +2, ... of the column: first entry and count of this lane
-  const double* gq = pc + (gc < n ? S.cptr[gc] + (tid & 1) : 0);
-  const int gcnt = gc < n ? (S.clen[gc] + 1 - (tid & 1)) >> 1 : 0;
-  const int gtrips = (((S.max_clen + 1) >> 1) + 3) & ~3;   // uniform trip count of gather_col
+  // gather role: warp i < M takes piece i, lanes 2q and 2q + 1 its column 15 i + q (lanes 30, 31 and the warps beyond M
+  // run the same loop on valid memory and drop the result)
+  const int gw = tid >> 5, gln = tid & 31;
+  const bool gact = gw < M && gln < 30;
+  const int gc = gact ? 15 * gw + (gln >> 1) : 0;
+  const bool gl0 = gact && (gln & 1) == 0;
+  const double* gq = pc + (gact ? S.cptr[gc] + (gln & 1) : 0);
+  const int grounds = gw < M ? S.rounds[gw] : 0;
 
   // ---- ADMM ----
   int iter, status = 0;
@@ -958,7 +984,7 @@ __global__ void __launch_bounds__(TILES ? kTt : kT, 1) k_qp_admm(QpDev Dv, QpPar
       if ((s + 1) * KT + tid < m) row_norms(dots(s, S.x), zs[s], (s + 1) * KT + tid);
     write_p(1, dy);
     __syncthreads();
-    const double aty = gather_col(gq, gcnt, gtrips);
+    const double aty = gather_col(gq, grounds);
     if (gl0) {
       const int b = gc / 15, rr = gc % 15;
       double px = 0;
@@ -1007,7 +1033,7 @@ __global__ void __launch_bounds__(TILES ? kTt : kT, 1) k_qp_admm(QpDev Dv, QpPar
       __syncthreads();
       write_p(2, dy);
       __syncthreads();
-      const double s = gather_col(gq, gcnt, gtrips);
+      const double s = gather_col(gq, grounds);
       const double v = gl0 ? fabs((1.0 / S.D[gc]) * s) : 0.0;
       const double nrm = block_max(v, S.red);
       return nrm < eps * nd;
@@ -1040,7 +1066,7 @@ __global__ void __launch_bounds__(TILES ? kTt : kT, 1) k_qp_admm(QpDev Dv, QpPar
 #endif
     // x_prev <- x ; rhs = sigma x_prev - q + A' w with w = rho z - y
     {
-      const double s = gather_col(gq, gcnt, gtrips);
+      const double s = gather_col(gq, grounds);
       if (gl0) {
         const double xv = S.x[gc];
         S.xp[gc] = xv;
@@ -1051,7 +1077,7 @@ __global__ void __launch_bounds__(TILES ? kTt : kT, 1) k_qp_admm(QpDev Dv, QpPar
 #ifdef POP_QP_PHASE_PROF
     const long long t1 = clock64();
 #endif
-    if constexpr (TILES) kkt_tiles(S, T, ti, Linv, Linv + part1_len);
+    if constexpr (TILES) kkt_tiles(S, T, ti, Linv, Lpt);
     else kkt_solve(S, Linv);
 #ifdef POP_QP_PHASE_PROF
     const long long t2 = clock64();

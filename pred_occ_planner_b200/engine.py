@@ -99,6 +99,14 @@ class PopEngine:
         self._check(self.lib.pop_map_future_risk(self._h, as_ptr(risk, C.c_float), pp, float(stamp)))
         self._t_map = float(stamp)
 
+    def is_traj_safe(self, t_now: float, T: float = 2.0):
+        """BaselinePlanner::isTrajSafe(T) for every local agent at wall-clock time t_now:
+        (safe flags int8 [n_local], relative time of the first occupied sample or -1)."""
+        safe = np.zeros(self.n_local, np.int8)
+        tu = np.zeros(self.n_local)
+        self._check(self.lib.pop_traj_safe_batch(self._h, float(t_now), float(T), as_ptr(safe, C.c_int8), as_ptr(tu, C.c_double)))
+        return safe, tu
+
     def agent_map(self, agent: int) -> "AgentMap":
         return AgentMap(self, agent)
 

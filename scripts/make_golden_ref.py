@@ -119,6 +119,8 @@ def main():
     sets = [rl.ref_sep_sets(ref, cfg.n_agents_total, ego, size, offs, counts, recs, now, cpts, dur, M) for now in nows]
     out["sep_n"] = np.array([s[0] for s in sets], np.int32)
     out["sep_sets"] = np.stack([s[1] for s in sets])
+    out["traj_safe"] = np.concatenate([ref.traj_safe(cfg, m, pose, t_map, rec, cfg.corridor_tau, now, T)
+                                       for cfg, m, pose, t_map, rec, now, T in rl.traj_safe_cases(orc)])
     path = os.path.join(ROOT, "tests", "golden", "ref_pins.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path), "bytes")

@@ -106,6 +106,18 @@ class OracleMap:
         self.lib.orc_map_inflate_query(self.h, mode, _p(pos, C.c_double), _p(tt, C.c_double), n, _p(out, C.c_int8))
         return out
 
+    def traj_safe(self, rec, tau, now, T):
+        """isTrajSafe(T) at wall-clock times `now` for the trajectory record `rec` with piece duration tau:
+        (safe flags, relative time of the first unsafe sample or -1)."""
+        rec = np.ascontiguousarray(rec)
+        now = np.ascontiguousarray(np.atleast_1d(now), np.float64)
+        T = np.ascontiguousarray(np.broadcast_to(np.asarray(T, np.float64), now.shape))
+        out = np.zeros(len(now), np.int8)
+        tu = np.zeros(len(now))
+        self.lib.orc_traj_safe(self.h, C.c_void_p(rec.ctypes.data), C.c_double(tau), len(now), _p(now, C.c_double),
+                               _p(T, C.c_double), _p(out, C.c_int8), _p(tu, C.c_double))
+        return out, tu
+
     def obstacle_points(self, t0, t1, lc, hc, cap=200000):
         lc = np.ascontiguousarray(lc, np.float64)
         hc = np.ascontiguousarray(hc, np.float64)

@@ -128,6 +128,24 @@ class RefLib:
                                  st.ctypes.data_as(C.POINTER(C.c_int32)))
         return ok, M.value, cp[:5 * M.value].copy(), st
 
+    def traj_safe(self, cfg, omap, pose, t_map, rec, tau, now, T, risk=False):
+        """The reference's (Fake)BaselinePlanner::isTrajSafe(T) for a planner holding the trajectory of record `rec`
+        (pieces of tau seconds) over the oracle map `omap`, asked at wall-clock times `now`."""
+        from tests import oracle_lib
+        ol = oracle_lib.load().lib
+        q = C.cast(ol.orc_map_query_dt, C.c_void_p)
+        pose = np.ascontiguousarray(pose, np.float32)
+        M = int(rec["n_pieces"])
+        dur = np.full(M, tau, np.float64)
+        cp = np.ascontiguousarray(rec["cpts"][:5 * M], np.float64)
+        now = np.ascontiguousarray(np.atleast_1d(now), np.float64)
+        T = np.ascontiguousarray(np.broadcast_to(np.asarray(T, np.float64), now.shape))
+        out = np.zeros(len(now), np.int8)
+        (self.lib.ref_traj_safe_risk if risk else self.lib.ref_traj_safe)(
+            C.byref(cfg), q, omap.h, pose.ctypes.data_as(C.POINTER(C.c_float)), D(t_map), M, P(dur), P(cp),
+            D(float(rec["start_time"])), len(now), P(now), P(T), out.ctypes.data_as(C.POINTER(C.c_int8)))
+        return out
+
     def ego_particles(self, size):
         size = np.ascontiguousarray(size, np.float64)
         out = np.zeros((64, 3))
@@ -445,3 +463,28 @@ def pack(arrs):
 def unpack(flat, offs, cols=None):
     out = [flat[offs[i]:offs[i + 1]] for i in range(len(offs) - 1)]
     return [a.reshape(-1, cols) for a in out] if cols else out
+
+
+def traj_safe_cases(orc, n=14, seed=67):
+    """isTrajSafe problems: a trajectory planned by the oracle on the map of t = 100, then asked about on maps taken
+    later from a drifted pose (so that some samples have become occupied): (cfg, map, pose, t_map, record, now[], T[])."""
+    from tests import oracle_cycle
+    cfg, (cloud, cyl) = astar_world()
+    rng = np.random.default_rng(seed + 1)
+    out = []
+    for pose, start, goal, ts in astar_cases(n, seed=seed):
+        m = orc.map(cfg)
+        m.set_pose(pose)
+        m.update_gt(cloud, cyl, 100.0)
+        st, rec, _ = oracle_cycle.replan(m, None, 0, start, goal, 100.0 + ts)
+        if st != 0:
+            continue
+        for t_map in (100.0, 100.6, 101.1):
+            p2 = (pose + np.float32([0.3, 0.2, 0]) * np.float32(t_map - 100.0)).astype(np.float32)
+            m2 = orc.map(cfg)
+            m2.set_pose(p2)
+            m2.update_gt(cloud, cyl, t_map)
+            now = float(rec["start_time"]) + rng.uniform(-0.3, 2.0, 6)
+            T = rng.choice([0.5, 1.0, 2.0, 5.0], 6)
+            out.append((cfg, m2, p2, t_map, rec, now, T))
+    return out

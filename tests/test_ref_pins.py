@@ -339,3 +339,21 @@ def test_whole_replan_against_the_reference_planner(oracle, ref, gold, risk):
                 assert int(rec["n_pieces"]) == M
                 got = np.asarray(rec["cpts"]).reshape(-1, 3)[:5 * M]
                 assert np.abs(got - cp).max() <= 1e-2 * max(1.0, np.abs(cp).max())
+
+
+def test_is_traj_safe_equals_reference(oracle, ref, gold):
+    """BaselinePlanner::isTrajSafe (baseline_fake.cpp:53-76; the same code in baseline.cpp:45-68): running-sum sample
+    times, clamping of the horizon to the trajectory's duration, queries by time — identical booleans."""
+    got, live = [], []
+    for cfg, m, pose, t_map, rec, now, T in rl.traj_safe_cases(oracle):
+        a, tu = m.traj_safe(rec, cfg.corridor_tau, now, T)
+        assert ((tu >= 0) == (a == 0)).all()
+        got.append(a)
+        if ref is not None:
+            live.append(ref.traj_safe(cfg, m, pose, t_map, rec, cfg.corridor_tau, now, T))
+            assert np.array_equal(ref.traj_safe(cfg, m, pose, t_map, rec, cfg.corridor_tau, now, T, risk=True), live[-1])
+    got = np.concatenate(got)
+    assert np.array_equal(got, gold["traj_safe"])
+    assert (got == 0).sum() > 10 and (got == 1).sum() > 50
+    if live:
+        assert np.array_equal(np.concatenate(live), got)

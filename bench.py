@@ -2,19 +2,29 @@
 """bench.py — agent-replans/s of the per-replan hot path (SOGM update → hybrid A* → corridors →
 Bezier QP → peer projection/separation) on N B200s, one process per GPU.
 
-Workload (BASELINE.json configs[1]): 64 agents per GPU, 30x30x5 m arena, 300x300x50 voxels @0.1 m,
-20 time slices of 0.1 s, 40 moving cylinders, 10 Hz replan.  A step = one replan cycle of every
-local agent.  `value` times K steps with inputs resident in HBM (CUDA events on the stream the
-kernels run on, max over ranks); `e2e` times the same cycle through the C-ABI call a plan_manager
-would make (pop_replan_cycle) with pinned HOST buffers: cloud/obstacle/agent-state uploads and
-status/trajectory downloads inside the timed region.  `--impl reference` times the CPU oracle (the
-reference as a whole cannot be built here; the files that can pin the oracle, see oracle/Makefile) on the box's host cores on a bounded sample of the same batch.
+Workload: a BASELINE.json config (default configs[1] = "c2": 64 agents per GPU, 30x30x5 m arena, 300x300x50 voxels
+@0.1 m, 20 time slices of 0.1 s, 40 moving cylinders, 10 Hz replan; `--config c3|c4` for the larger ones) flown as a
+CLOSED LOOP: a step = one replan cycle of every local agent at simulated time T0 + 0.1 s * step; between steps the
+obstacles move with their ground-truth velocities (the cloud with them), every agent moves along the trajectory it
+planned (perfect tracking, what uav_simulator/fake_drone does) and the freshly planned trajectories are exchanged.
+Both arms fly the same script from the same initial state: steps 0-1 pre-roll, W warm-up steps, K timed steps.
+
+`value` times the K steps with every input resident in HBM (world states staged on the device beforehand, agent
+states advanced on the device; CUDA events on the stream the kernels run on, max over ranks).  `e2e` times the same
+cycle through the C-ABI call a plan_manager would make (pop_replan_cycle) with pinned HOST buffers: cloud, obstacle
+states and agent states uploaded, status and trajectories downloaded, every step, inside the timed region.
+`--impl reference` flies the same closed loop with the CPU oracle (oracle/liboracle.so: the reference's path restated
+and pinned against the reference's own sources compiled here; the reference as a whole needs
+ROS/Eigen/PCL/OSQP/GLPK) on all host threads.  The GPU line's `cpu_baseline` is that same oracle cycle run on the
+exact inputs of one GPU step, which also yields the `parity` object (statuses and control points compared).
 """
 from __future__ import annotations
 
 import argparse
+import glob
 import json
 import os
+import re
 import subprocess
 import sys
 import threading
@@ -30,64 +40,102 @@ os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 
 METRIC = "agent-replans/s (SOGM+A*+corridor+QP cycle)"
 UNIT = "agent-replans/s"
-# dram__bytes_read.sum + dram__bytes_write.sum of the four voxel-update launches of one cycle at this
-# workload, from the committed `ncu --set full` capture (profiles/r01d_voxel_update.txt)
-NCU_VOXEL_TRAFFIC = int(0.986112e6 + 0.03328e6 + 1.02528e6 + 0.8e6 + 30.07488e6 + 5.702543e9)
+DT = 0.1          # replan period (10 Hz)
+LOOKAHEAD = 0.02  # traj_start_time - map stamp
+T0 = 100.0
+PREROLL = 2
+
+# BASELINE.json configs[1..3]; SURVEY §8d gives the synthetic inputs
+CONFIGS = {
+    "c2": dict(grid=(300, 300, 50, 20), arena=(30.0, 30.0, 5.0), n_static=0, n_moving=40, agents=64, layout="circle",
+               radius=13.0, pitch=64.0, seed=1236,
+               label="c2: 64 agents/GPU, 300x300x50 @0.1 m, T=20, 40 moving cylinders, 10 Hz"),
+    "c3": dict(grid=(500, 500, 60, 20), arena=(50.0, 50.0, 6.0), n_static=60, n_moving=60, agents=256, layout="lattice",
+               pitch=128.0, seed=1237,
+               label="c3: 256 agents/GPU, 500x500x60 @0.1 m, T=20, 60 static + 60 moving cylinders, 10 Hz"),
+    "c4": dict(grid=(500, 500, 60, 20), arena=(50.0, 50.0, 6.0), n_static=60, n_moving=60, agents=128, layout="lattice",
+               pitch=128.0, seed=1238,
+               label="c4: 128 agents/GPU (1 024 on 8 GPUs), c3 arena per GPU, T=20, allgather each cycle, 10 Hz"),
+    "small": dict(grid=(120, 120, 30, 10), arena=(12.0, 12.0, 3.0), n_static=0, n_moving=10, agents=8, layout="circle",
+                  radius=4.5, pitch=32.0, seed=1236, label="small harness smoke (not a bench number)"),
+}
 
 
-# ------------------------------------------------------------------------------------------------
-ARENA_PITCH = 64.0   # metres between the arenas of consecutive ranks (arena 30 m + local box 30 m < pitch)
+class Scenario:
+    """One rank's share of a config: configuration, world script, initial agent states."""
+
+    def __init__(self, name: str, n_local: int, n_total: int, id_base: int, default_config=None):
+        import pred_occ_planner_b200 as p
+        k = CONFIGS[name]
+        self.name, self.k = name, k
+        c = (default_config or p.default_config)()   # the CPU arm passes the oracle's: it never loads libpop
+        c.nx, c.ny, c.nz, c.nt = k["grid"]
+        c.resolution = 0.1
+        c.time_resolution = 0.1
+        c.resolution_astar = 0.1
+        c.time_resolution_astar = 0.2
+        c.corridor_tau = 0.2
+        c.cell_dtype = p.POP_CELL_U8
+        c.n_agents_local, c.n_agents_total, c.agent_id_base = n_local, n_total, id_base
+        c.max_obstacle_points = 16384
+        c.max_cloud_points = 1 << 19
+        self.cfg = c
+        world = n_total // n_local
+        rank = id_base // n_local + int(os.environ.get("POP_BENCH_ARENA_SHIFT", "0"))   # diagnosis: fly in a later rank's arena
+        self.shift = rank * k["pitch"]
+        cloud, cyl, owner = p.worldgen.make_world(k["seed"], arena=k["arena"], n_static=k["n_static"], n_moving=k["n_moving"],
+                                                  return_owner=True)
+        # every rank flies its own copy of the arena, translated along x (weak scaling as BASELINE config 4 words it:
+        # "arena per GPU"); all trajectories are still exchanged and every rank's peer projection scans all records
+        cloud[:, 0] += np.float32(self.shift)
+        cyl["x"] += self.shift
+        self.cloud0, self.cyl0, self.owner = cloud, cyl, owner
+        self.max_abs_vy = float(np.abs(cyl["vy"]).max()) if len(cyl) else 0.0
+        if k["layout"] == "circle":
+            s0, g0 = p.worldgen.circle_agents(n_local, k["radius"])
+        else:
+            s0, g0 = p.worldgen.lattice_agents(n_local, arena=k["arena"][:2], seed=3)
+        start = np.tile(s0, (world, 1))
+        goal = np.tile(g0, (world, 1))
+        for r in range(world):
+            off = (r + int(os.environ.get("POP_BENCH_ARENA_SHIFT", "0"))) * k["pitch"]
+            start[r * n_local:(r + 1) * n_local, 0] += off
+            goal[r * n_local:(r + 1) * n_local, 0] += off
+        self.start_all, self.goal_all = start, goal
+        self.body = p.worldgen.body_table(n_total, [0.4, 0.4, 0.45])
+
+    def t(self, step: int) -> float:
+        return T0 + DT * step
+
+    def world(self, step: int):
+        """(cloud, cylinders) of this rank's arena at step `step`"""
+        import pred_occ_planner_b200 as p
+        return p.worldgen.advance_world(self.cloud0, self.cyl0, self.owner, DT * step)
 
 
-def workload(n_local: int, n_total: int, id_base: int, small: bool = False):
-    """BASELINE config 2 per GPU.  Weak scaling follows config 4 ("c3-style arena per GPU, allgather each
-    cycle"): every rank flies its own 64-agent swarm in its own copy of the arena, translated by
-    ARENA_PITCH along x, so per-GPU work is constant; all trajectories are still exchanged and every
-    rank's peer projection scans all n_total records."""
-    import pred_occ_planner_b200 as p
-    c = p.default_config()
-    if small:   # CPU-only smoke of the harness logic
-        c.nx, c.ny, c.nz, c.nt = 120, 120, 30, 10
-        arena, radius, ncyl = (12.0, 12.0, 3.0), 4.5, 10
-    else:
-        c.nx, c.ny, c.nz, c.nt = 300, 300, 50, 20
-        arena, radius, ncyl = (30.0, 30.0, 5.0), 13.0, 40
-    c.resolution = 0.1
-    c.time_resolution = 0.1
-    c.resolution_astar = 0.1
-    c.time_resolution_astar = 0.2
-    c.corridor_tau = 0.2
-    c.cell_dtype = p.POP_CELL_U8
-    c.n_agents_local, c.n_agents_total, c.agent_id_base = n_local, n_total, id_base
-    c.max_obstacle_points = 16384
-    rank, world = id_base // n_local, n_total // n_local
-    rank += int(os.environ.get("POP_BENCH_ARENA_SHIFT", "0"))   # diagnosis: fly rank 0 in a later rank's arena
-    cloud, cyl = p.worldgen.make_world(1236, arena=arena, n_static=0, n_moving=ncyl)
-    cloud = cloud.copy()
-    cloud[:, 0] += np.float32(rank * ARENA_PITCH)
-    cyl = cyl.copy()
-    cyl["x"] += rank * ARENA_PITCH
-    s0, g0 = p.worldgen.circle_agents(n_local, radius)
-    start = np.tile(s0, (world, 1))
-    goal = np.tile(g0, (world, 1))
-    for r in range(world):
-        start[r * n_local:(r + 1) * n_local, 0] += r * ARENA_PITCH
-        goal[r * n_local:(r + 1) * n_local, 0] += r * ARENA_PITCH
-    shift = int(os.environ.get("POP_BENCH_ARENA_SHIFT", "0")) * ARENA_PITCH
-    start[:, 0] += shift
-    goal[:, 0] += shift
-    body = p.worldgen.body_table(n_total, [0.4, 0.4, 0.45])
-    return c, cloud, cyl, start, goal, body
-
-
-def advance_world(cloud0, cyl0, t):
-    """Ground-truth world at time t: cylinders translate at constant velocity (no wall bounce
-    inside the few seconds a bench covers); the cloud is regenerated by translation."""
-    import pred_occ_planner_b200 as p
-    cyl = cyl0.copy()
-    cyl["x"] += cyl0["vx"] * t
-    cyl["y"] += cyl0["vy"] * t
-    return cyl
+def advance_states(orc, start, recs, t_next):
+    """Perfect tracking on the host (what pop_swarm_advance does on the device, k_follow.cu:k_swarm_advance): every
+    agent takes the commanded state of its own last trajectory at t_next; past its end it holds the end point; without
+    one it stays."""
+    out = start.copy()
+    for a in range(len(start)):
+        r = recs[a]
+        M = int(r["n_pieces"])
+        if M <= 0 or t_next < r["start_time"]:
+            out[a, 3:] = 0.0
+            continue
+        dur = r["duration"][:M].astype(np.float64)
+        tt = t_next - float(r["start_time"])
+        T = 0.0
+        for x in dur:
+            T += float(x)
+        if tt <= T:
+            for d in range(3):
+                out[a, 3 * d:3 * d + 3] = orc.bezier_eval(dur, r["cpts"][:5 * M], [tt], d)[0]
+        else:
+            out[a, :3] = orc.bezier_eval(dur, r["cpts"][:5 * M], [T], 0)[0]
+            out[a, 3:] = 0.0
+    return out
 
 
 class ClockSampler:
@@ -144,51 +192,102 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def ncu_voxel_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of the voxel-update launches of one cycle, parsed from the newest
+    committed `ncu --set full` summary (profiles/*voxel_update.txt, written by scripts/ncu_summary.py); None if there
+    is none.  Only meaningful for the c2 workload at 64 agents, which is what those captures are of."""
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*voxel_update.txt")))
+    if not files:
+        return None, None
+    unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    per_kernel = {}
+    name = None
+    for ln in open(files[-1]):
+        if ln.startswith("## "):
+            m = re.search(r"k_vox_\w+", ln)
+            name = m.group(0) if m else None
+        m = re.match(r"(dram__bytes_(?:read|write)\.sum)\s+([\d.,]+)\s+(\w+)", ln)
+        if m and name:
+            # one launch of each voxel-update kernel per cycle: keep the last capture of every kernel
+            per_kernel.setdefault(name, {})[m.group(1)] = float(m.group(2).replace(",", "")) * unit.get(m.group(3), 1.0)
+    total = sum(sum(v.values()) for v in per_kernel.values())
+    return (int(total) if total > 0 else None), os.path.basename(files[-1])
+
+
 # ------------------------------------------------------------------------------------------------
-def cpu_cycle(cfg, cloud, cyl, start, goal, body, recs, n_sample, threads, t_map, t_plan):
+def cpu_cycle(sc, cloud, cyl, start, goal, recs, n_sample, threads, t_map, records=None):
     """Oracle cycle (map update + peers + A* + corridor + QP + separation) for the first n_sample
     local agents on `threads` host threads. Returns (seconds, status)."""
     from tests import oracle_cycle
+    cfg = sc.cfg
     a0 = cfg.agent_id_base
-    poses = start[a0:a0 + cfg.n_agents_local, :3].astype(np.float32)
-    return oracle_cycle.cycle_batch(cfg, a0, a0 + n_sample, threads, cloud, cyl, poses,
-                                    (body[0], body[1], recs), start[a0:a0 + cfg.n_agents_local],
-                                    goal[a0:a0 + cfg.n_agents_local], t_map, t_plan)
+    poses = start[:, :3].astype(np.float32)
+    return oracle_cycle.cycle_batch(cfg, a0, a0 + n_sample, threads, cloud, cyl, poses, (sc.body[0], sc.body[1], recs),
+                                    start, goal, t_map, t_map + LOOKAHEAD, records=records)
 
 
 def run_reference(args, rank, world):
+    """The reference arm: the same closed loop flown by the CPU oracle on all host threads.  At N > 1 only rank 0's
+    arena is flown (the arenas are independent copies), as a bounded sample of the N-GPU workload.  No GPU, no libpop
+    compute: pred_occ_planner_b200 is imported for the configuration struct and the world generator only."""
     if rank != 0:
         return
     import pred_occ_planner_b200 as p
+    from tests import oracle_lib
+    orc = oracle_lib.load()
     n_local = args.agents
-    cfg, cloud, cyl, start, goal, body = workload(n_local, n_local * world, 0, args.small)
+    sc = Scenario(args.config, n_local, n_local * world, 0, default_config=oracle_lib.default_config)
     threads = os.cpu_count() or 1
-    recs = p.worldgen.straight_trajs(start[:, :3], goal, -0.05, 1.0, 10, 0.2)   # peers already flying
-    # size the per-step sample from one probe so that the whole run stays within ~2.5 minutes
+    start = sc.start_all[:n_local].copy()
+    goal = sc.goal_all[:n_local].copy()
+    recs_all = np.zeros(n_local * world, p.TRAJ_DTYPE)
+    own = np.zeros(n_local, p.TRAJ_DTYPE)
+    n_steps = PREROLL + args.warmup + args.steps
+    # bound the run to a few minutes: fly the whole batch if one step fits the budget, else the first n_sample agents
+    cloud, cyl = sc.world(0)
     probe_n = min(n_local, threads)
-    sec, _ = cpu_cycle(cfg, cloud, cyl, start, goal, body, recs, probe_n, threads, 0.0, 0.02)
-    per_agent_wall = sec / probe_n
-    budget = 150.0 / max(1, args.steps + args.warmup)
-    n_sample = int(max(min(n_local, threads), min(n_local, budget / max(per_agent_wall, 1e-6))))
-    for _ in range(args.warmup):
-        cpu_cycle(cfg, cloud, cyl, start, goal, body, recs, n_sample, threads, 0.0, 0.02)
-    t0 = time.perf_counter()
+    sec, _ = cpu_cycle(sc, cloud, cyl, start, goal, recs_all, probe_n, threads, sc.t(0))
+    budget = 170.0 / n_steps
+    n_sample = int(max(probe_n, min(n_local, budget / max(sec / probe_n, 1e-6))))
     ok = 0
-    for i in range(args.steps):
-        sec, st = cpu_cycle(cfg, cloud, cyl, start, goal, body, recs, n_sample, threads, 0.1 * i, 0.1 * i + 0.02)
-        ok += int((st[:n_sample] == 0).sum())
-    dt = time.perf_counter() - t0
-    value = n_sample * args.steps / dt
-    sample = f"{n_sample} of {n_local} agents of the batch per step, {args.steps} steps, {threads} threads"
+    dt_timed = 0.0
+    for s in range(n_steps):
+        cloud, cyl = sc.world(s)
+        if s > 0:
+            start = advance_states(orc, start, own, sc.t(s))
+        t0 = time.perf_counter()
+        _, st = cpu_cycle(sc, cloud, cyl, start, goal, recs_all, n_sample, threads, sc.t(s), records=own)
+        el = time.perf_counter() - t0
+        recs_all[:n_local] = own    # "/broadcast_traj": peers see this cycle's trajectories in the next one
+        if s >= PREROLL + args.warmup:
+            dt_timed += el
+            ok += int((st[:n_sample] == 0).sum())
+    value = n_sample * args.steps / dt_timed
+    sample = (f"{n_sample} of {n_local} agents of rank 0's arena per step, closed loop, {args.steps} timed steps after "
+              f"{PREROLL}+{args.warmup} untimed, {threads} host threads")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": 1e3 * dt_timed / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32 grid / f64 planning", "data": "synthetic",
-            "config": {"workload": "c2: 64 agents/GPU, 300x300x50 @0.1 m, T=20, 40 moving cylinders, 10 Hz",
-                       "note": "CPU oracle (restated reference path; the reference needs ROS/Eigen/PCL/OSQP/GLPK)"},
+            "config": config_dict(sc, world, None, None),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "replans_ok_frac": ok / max(1, n_sample * args.steps)}
+            "replans_ok_frac": ok / max(1, n_sample * args.steps),
+            "note": "CPU oracle = the reference's path restated in C++ and pinned against the reference's own sources "
+                    "compiled here (DESIGN.md §2); the reference as a whole needs ROS/Eigen/PCL/OSQP/GLPK"}
     emit(line)
+
+
+def config_dict(sc, world, cloud_points, rec_bytes):
+    """The `config` object; identical keys in both arms."""
+    c = sc.cfg
+    V = c.nx * c.ny * c.nz
+    return {"workload": sc.k["label"], "name": sc.name, "agents_per_gpu": c.n_agents_local,
+            "agents_total": c.n_agents_local * world, "grid": [c.nx, c.ny, c.nz, c.nt], "cell": "u8 (GPU) / f32 (CPU)",
+            "loop": "closed: obstacles move, agents track their planned trajectories, trajectories exchanged every step",
+            "parallelism": f"agents sharded x{world}, one arena per GPU",
+            "l2": "inputs larger than L2 (per-step SOGM writes %.2f GB per GPU)" % (c.n_agents_local * V * c.nt / 1e9),
+            "collective": "1 allgather of 1536 B trajectory records per cycle" if world > 1
+            else "single rank: device-to-device publish"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -263,60 +362,75 @@ def run_b200(args, rank, world, local_rank):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     n_total = args.agents * world
     id_base, n_local = p.swarm.shard(n_total, world, rank)
-    cfg, cloud, cyl0, start_all, goal_all, body = workload(n_local, n_total, id_base, args.small)
+    sc = Scenario(args.config, n_local, n_total, id_base)
+    cfg = sc.cfg
     sl = slice(id_base, id_base + n_local)
-    start, goal = start_all[sl].copy(), goal_all[sl].copy()
+    start0, goal = sc.start_all[sl].copy(), sc.goal_all[sl].copy()
+    W, K = args.warmup, args.steps
+    n_steps = PREROLL + W + K
     # a dedicated non-default stream: libpop enqueues on it and the CUDA events below time it
     stream = torch.cuda.Stream(device=local_rank)
     torch.cuda.set_stream(stream)
-    eng = p.PopEngine(cfg, device=local_rank, stream=stream.cuda_stream)
-    eng.set_world_cloud(cloud)
-    eng.set_cylinders(cyl0)
-    eng.set_body_particles(*body)
-    eng.set_trajectories(np.zeros(n_total, p.TRAJ_DTYPE))
-    # '/broadcast_traj': one allgather of fixed-size trajectory records per cycle, issued on the
-    # current torch stream (= the engine's) straight between libpop's device buffers
-    xchg = p.swarm.TrajExchange(n_total, world, rank, engine=eng, device=local_rank)
-    exchange = xchg.step
-    if os.environ.get("POP_BENCH_EXCHANGE") == "local":   # diagnosis only: no collective, each rank keeps its own records
-        exchange = eng.traj_publish_local
     rec_bytes = p.swarm.RECORD_BYTES
 
-    # pinned host staging for the e2e path
     def pinned(a):
         t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
         return t, t.numpy()
 
-    _c, h_cloud = pinned(cloud)
-    _s, h_start = pinned(start)
+    # the world script, staged once: pinned host copies for the e2e path, device copies for the resident path
+    worlds = [sc.world(s) for s in range(n_steps + 4)]
+    keep, h_clouds, h_cyls, d_clouds, d_cyls = [], [], [], [], []
+    for cloud, cyl in worlds:
+        tc, hc = pinned(cloud)
+        ty, hy = pinned(cyl.view(np.uint8))
+        keep += [tc, ty]
+        h_clouds.append(hc)
+        h_cyls.append(hy.view(p.CYL_DTYPE))
+        d_clouds.append(tc.to(f"cuda:{local_rank}", non_blocking=True))
+        d_cyls.append(ty.to(f"cuda:{local_rank}", non_blocking=True))
+    torch.cuda.synchronize()
+    _s, h_start = pinned(start0)
     _g, h_goal = pinned(goal)
-    _p, h_poses = pinned(start[:, :3].astype(np.float32))
-    h2d = h_cloud.nbytes + cyl0.nbytes + h_start.nbytes + h_goal.nbytes + h_poses.nbytes
-    d2h = n_local * (4 + rec_bytes)
+    _p, h_poses = pinned(start0[:, :3].astype(np.float32))
+    n_cloud = len(worlds[0][0])
+    h2d = h_clouds[0].nbytes + h_cyls[0].nbytes + h_start.nbytes + h_goal.nbytes + h_poses.nbytes
+    d2h = n_local * (4 + rec_bytes) + h_start.nbytes   # statuses + trajectory records + the agents' new states
 
-    def e2e_step(i, t0):
-        eng.set_world_cloud(h_cloud)
-        eng.set_cylinders(cyl0)
-        st, tr = eng.replan_cycle(h_start, h_goal, h_poses, t0 + 0.1 * i, t0 + 0.1 * i + 0.02)
+    def new_engine():
+        eng = p.PopEngine(cfg, device=local_rank, stream=stream.cuda_stream)
+        eng.set_body_particles(*sc.body)
+        eng.set_trajectories(np.zeros(n_total, p.TRAJ_DTYPE))
+        # '/broadcast_traj': one allgather of fixed-size trajectory records per cycle, issued on the
+        # current torch stream (= the engine's) straight between libpop's device buffers
+        xchg = p.swarm.TrajExchange(n_total, world, rank, engine=eng, device=local_rank)
+        exchange = xchg.step
+        if os.environ.get("POP_BENCH_EXCHANGE") == "local":   # diagnosis only: no collective
+            exchange = eng.traj_publish_local
+        return eng, exchange
+
+    # ================= e2e: host buffers in, results out, every step =================
+    eng, exchange = new_engine()
+
+    def e2e_step(s):
+        if s > 0:   # odometry: the drone tracked its trajectory; the planner reads its state back
+            eng.swarm_advance(sc.t(s))
+            h_start[:] = eng.swarm_states()
+            h_poses[:] = h_start[:, :3]
+        eng.set_world_cloud(h_clouds[s])
+        eng.set_cylinders(h_cyls[s])
+        st, tr = eng.replan_cycle(h_start, h_goal, h_poses, sc.t(s), sc.t(s) + LOOKAHEAD)
         exchange()
-        return st
+        return st, tr
 
-    # ---- pre-roll: a few closed-loop cycles so peers have live trajectories and agents move ----
-    T0 = 100.0
-    st = e2e_step(0, T0)
-    st = e2e_step(1, T0)
-    eng.sync()
-
-    # ---- e2e: host buffers in, results out, every step ----
-    for i in range(args.warmup):
-        e2e_step(2 + i, T0)
+    for s in range(PREROLL + W):
+        e2e_step(s)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     t_begin = time.perf_counter()
     ok_e2e = 0
-    for i in range(args.steps):
-        ok_e2e += int((e2e_step(2 + args.warmup + i, T0) == 0).sum())
+    for s in range(PREROLL + W, n_steps):
+        ok_e2e += int((e2e_step(s)[0] == 0).sum())
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -326,14 +440,59 @@ def run_b200(args, rank, world, local_rank):
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         e2e_s = float(tt.item())
 
-    # ---- device-resident: inputs already in HBM, nothing crosses PCIe ----
-    T1 = T0 + 0.1 * (2 + args.warmup + args.steps)
+    # ---- parity + CPU baseline (rank 0 at N = 1): one more step, the oracle on exactly its inputs ----
+    parity = cpu_base = None
+    if world == 1 and not args.no_cpu_baseline:
+        from tests import oracle_lib
+        orc = oracle_lib.load()
+        s = n_steps
+        eng.swarm_advance(sc.t(s))
+        h_start[:] = eng.swarm_states()
+        h_poses[:] = h_start[:, :3]
+        peers = eng.get_trajectories()          # the table this step's map update reads
+        eng.set_world_cloud(h_clouds[s])
+        eng.set_cylinders(h_cyls[s])
+        st_gpu, tr_gpu = eng.replan_cycle(h_start, h_goal, h_poses, sc.t(s), sc.t(s) + LOOKAHEAD)
+        threads = os.cpu_count() or 1
+        own = np.zeros(n_local, p.TRAJ_DTYPE)
+        sec, st_cpu = cpu_cycle(sc, worlds[s][0], worlds[s][1], h_start.copy(), goal, peers, n_local, threads, sc.t(s), records=own)
+        both = (st_gpu == 0) & (st_cpu == 0)
+        rel = 0.0
+        for a in np.flatnonzero(both):
+            M = int(own["n_pieces"][a])
+            if M != int(tr_gpu["n_pieces"][a]):
+                rel = float("inf")
+                continue
+            x, y = tr_gpu["cpts"][a][:5 * M], own["cpts"][a][:5 * M]
+            rel = max(rel, float(np.abs(x - y).max() / max(1.0, np.abs(y).max())))
+        parity = {"agents": int(n_local), "status_equal": int((st_gpu == st_cpu).sum()), "both_ok": int(both.sum()),
+                  "max_rel_cpts": rel, "tolerance": 1e-4, "step": s,
+                  "against": "CPU oracle (port) on the same cloud, obstacle states, agent states and peer table"}
+        cpu_base = {"value": n_local / sec, "unit": UNIT, "cores": threads, "kind": "port",
+                    "sample": f"all {n_local} agents of step {s} (the parity step), one cycle, {threads} host threads"}
+    eng.close()
+
+    # ================= device-resident: the same script, nothing crosses PCIe =================
+    eng, exchange = new_engine()
+
+    def resident_step(s):
+        if s > 0:
+            eng.swarm_advance(sc.t(s))
+        eng.set_world_cloud_dev(d_clouds[s].data_ptr(), n_cloud)
+        eng.set_cylinders_dev(d_cyls[s].data_ptr(), len(sc.cyl0), sc.max_abs_vy)
+        eng.replan_cycle_resident(sc.t(s), sc.t(s) + LOOKAHEAD)
+        exchange()
+
+    # step 0 places the agents (host states once); afterwards everything stays on the device
+    eng.set_world_cloud(h_clouds[0])
+    eng.set_cylinders(h_cyls[0])
+    eng.replan_cycle(start0, goal, start0[:, :3].astype(np.float32), sc.t(0), sc.t(0) + LOOKAHEAD)
+    exchange()
     # mode 2: CUDA events around the map stages only (the roofline kernel); the planning stages keep
     # running pipelined over agent groups exactly as they do with profiling off
     eng.profile_enable(2)
-    for i in range(args.warmup):
-        eng.replan_cycle_resident(T1 + 0.1 * i, T1 + 0.1 * i + 0.02)
-        exchange()
+    for s in range(1, PREROLL + W):
+        resident_step(s)
     eng.profile_read(True)
     launches0 = eng.kernel_launches()
     sampler = ClockSampler(local_rank)
@@ -343,13 +502,11 @@ def run_b200(args, rank, world, local_rank):
     if rank == 0:
         sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    T2 = T1 + 0.1 * args.warmup
     ev0.record(stream)
     host_t0 = time.perf_counter()
-    for i in range(args.steps):
-        eng.replan_cycle_resident(T2 + 0.1 * i, T2 + 0.1 * i + 0.02)
-        exchange()
-    host_enqueue_ms = 1e3 * (time.perf_counter() - host_t0) / args.steps   # host time to enqueue one cycle
+    for s in range(PREROLL + W, n_steps):
+        resident_step(s)
+    host_enqueue_ms = 1e3 * (time.perf_counter() - host_t0) / K   # host time to enqueue one cycle
     ev1.record(stream)
     torch.cuda.synchronize()
     if world > 1:
@@ -368,66 +525,49 @@ def run_b200(args, rank, world, local_rank):
     eng.profile_enable(1)
     n_serial = 3
     for i in range(n_serial):
-        eng.replan_cycle_resident(T2 + 0.1 * (args.steps + i), T2 + 0.1 * (args.steps + i) + 0.02)
-        exchange()
+        resident_step(n_steps + i)
     serial_ms, _ = eng.profile_read(True)
     eng.profile_enable(0)
 
     if rank == 0:
-        ms_step = ms_total / args.steps
-        value = n_total * args.steps / (ms_total * 1e-3)
-        e2e_value = n_total * args.steps / e2e_s
+        ms_step = ms_total / K
+        value = n_total * K / (ms_total * 1e-3)
+        e2e_value = n_total * K / e2e_s
         peak, peak_src = peaks()
         cell = 1
         V = cfg.nx * cfg.ny * cfg.nz
-        vox_ms = stage_ms["voxel_update"] / args.steps
+        vox_ms = stage_ms["voxel_update"] / K
         # algorithmic bytes of the voxel update: every SOGM cell written once + cloud read
         # once per agent + scattered future-slice deposits (<= one per cloud point and slice)
-        alg_bytes = n_local * (V * cfg.nt * cell + len(cloud) * 12 + len(cloud) * (cfg.nt - 1) * cell)
+        alg_bytes = n_local * (V * cfg.nt * cell + n_cloud * 12 + n_cloud * (cfg.nt - 1) * cell)
         achieved = alg_bytes / (vox_ms * 1e-3) / 1e9 if vox_ms > 0 else 0.0
+        traffic, traffic_src = ncu_voxel_traffic() if (sc.name == "c2" and n_local == 64) else (None, None)
+        conf = config_dict(sc, world, n_cloud, rec_bytes)
+        conf["cloud_points"] = int(n_cloud)
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K,
+            "warmup": W, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u8 grid / f64 planning", "data": "synthetic",
-            "config": {"workload": "c2: 64 agents/GPU, 300x300x50 @0.1 m, T=20, 40 moving cylinders, 10 Hz"
-                       if not args.small else "small harness smoke",
-                       "agents_per_gpu": n_local, "agents_total": n_total, "grid": [cfg.nx, cfg.ny, cfg.nz, cfg.nt],
-                       "cell": "u8", "cloud_points": int(len(cloud)), "parallelism": f"agents sharded x{world}, one arena per GPU",
-                       "l2": "inputs larger than L2 (per-step SOGM writes %.2f GB)" % (n_local * V * cfg.nt * cell / 1e9),
-                       "collective": "1 allgather of %d B trajectory records per cycle" % rec_bytes if world > 1
-                       else "single rank: device-to-device publish"},
+            "config": conf,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "ms_per_step": 1e3 * e2e_s / args.steps, "replans_ok_frac": ok_e2e / (n_local * args.steps)},
+                    "ms_per_step": 1e3 * e2e_s / K, "replans_ok_frac": ok_e2e / (n_local * K)},
             "gpu_launches": int(launches),
             "host_enqueue_ms_per_step": host_enqueue_ms,
             "clocks": clocks,
-            "roofline": {"kernel": "voxel update (k_vox_count + k_vox_scan + k_vox_fill + k_vox_tiles; k_vox_tiles = 0.86 of it)", "bound": "hbm",
+            "roofline": {"kernel": "voxel update (k_vox_count + k_vox_scan + k_vox_fill + k_vox_tiles)", "bound": "hbm",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": NCU_VOXEL_TRAFFIC if not args.small and n_local == 64 else None, "peak_source": peak_src, "algorithmic_bytes_per_step": int(alg_bytes),
-                         "ms_per_step": vox_ms},
+                         "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                         "algorithmic_bytes_per_step": int(alg_bytes), "ms_per_step": vox_ms},
             "stage_ms_serialised": {k: v / n_serial for k, v in serial_ms.items()},
             "stage_note": "untimed extra pass with the planning stages run one after the other over the whole batch; "
                           "in the timed region they are pipelined over agent groups on side streams",
             "replans_ok_frac": ok_frac,
+            "parity": parity,
+            "cpu_baseline": cpu_base,
         }
-        if not args.no_cpu_baseline and world == 1:
-            threads = os.cpu_count() or 1
-            recs = p.worldgen.straight_trajs(start_all[:, :3], goal_all, -0.05, 1.0, 10, 0.2)
-            n_s = min(n_local, threads)
-            sec, _ = cpu_cycle(cfg, cloud, cyl0, start_all, goal_all, body, recs, n_s, threads, 0.0, 0.02)
-            reps = max(1, int(15.0 / max(sec, 1e-3)))
-            reps = min(reps, 8)
-            t0 = time.perf_counter()
-            for r in range(reps):
-                cpu_cycle(cfg, cloud, cyl0, start_all, goal_all, body, recs, n_s, threads, 0.1 * r, 0.1 * r + 0.02)
-            dt = time.perf_counter() - t0
-            line["cpu_baseline"] = {"value": n_s * reps / dt, "unit": UNIT, "cores": threads, "kind": "port",
-                                    "sample": f"{n_s} agents of the batch x {reps} cycles on {threads} threads (oracle)"}
-        else:
-            line["cpu_baseline"] = None
     eng.close()
     if rank == 0:
-        if world == 1 and not args.small and not args.no_dsp:
+        if world == 1 and sc.name == "c2" and not args.no_dsp:
             line["dsp"] = dsp_leg(stream, local_rank, not args.no_cpu_baseline)
         emit(line)
     if world > 1:
@@ -464,11 +604,16 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--agents", type=int, default=64, help="agents per GPU")
+    ap.add_argument("--config", default="c2", choices=sorted(CONFIGS), help="BASELINE.json workload (default configs[1])")
+    ap.add_argument("--agents", type=int, default=None, help="agents per GPU (default: the config's)")
     ap.add_argument("--small", action="store_true", help="tiny grid (harness smoke only; not a bench number)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-dsp", action="store_true", help="skip the particle-map leg")
     args = ap.parse_args()
+    if args.small:
+        args.config = "small"
+    if args.agents is None:
+        args.agents = CONFIGS[args.config]["agents"]
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

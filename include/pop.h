@@ -164,6 +164,11 @@ void        pop_default_config(pop_config* cfg);
 int pop_set_world_cloud(pop_handle* h, const float* pts, int n);
 /* Ground-truth obstacle states: "map/state" (groundTruthStateCallback :244-264). */
 int pop_set_cylinders(pop_handle* h, const pop_cylinder* cyl, int n);
+/* The same two inputs from DEVICE memory (a simulator or sensor pipeline that already lives on the GPU): enqueued on
+ * the handle's stream, asynchronous, nothing crosses PCIe.  cyl_dev = n pop_cylinder records in device memory;
+ * max_abs_vy = the largest |vy| among them (the host-side bound the tiled voxel update sizes its reach with). */
+int pop_set_world_cloud_dev(pop_handle* h, const float* pts_dev, int n);
+int pop_set_cylinders_dev(pop_handle* h, const pop_cylinder* cyl_dev, int n, double max_abs_vy);
 /* Map centre per local agent: MapBase::pose_ set by odom/pose callbacks (map.cpp:139-168).
  * poses = n_agents_local x 3 float32. */
 int pop_set_poses(pop_handle* h, const float* poses);
@@ -174,6 +179,9 @@ int pop_set_body_particles(pop_handle* h, const double* offs, const int32_t* cou
 /* Peer trajectories as last received: ParticleATC::swarm_trajs_ (particles.cpp:131-191).
  * recs = n_agents_total records indexed by global drone id. */
 int pop_set_trajectories(pop_handle* h, const pop_traj_record* recs);
+
+/* The table pop_set_trajectories / the allgather filled, read back (n_agents_total records). */
+int pop_get_trajectories(pop_handle* h, pop_traj_record* recs);
 
 /* ---- K1f + K5: SOGM update ------------------------------------------------------------- */
 /* FakeParticleRiskVoxel::updateMap for every local agent (fake_particle_risk_voxel.cpp:80-222):
@@ -300,6 +308,22 @@ int pop_cycle_results(pop_handle* h, int32_t* status, pop_traj_record* traj);
 /* Single-rank stand-in for the allgather: copies this handle's freshly published records into
  * its own receive buffer at [agent_id_base, agent_id_base + n_agents_local). Async. */
 int pop_traj_publish_local(pop_handle* h);
+/* ---- multi-GPU: the trajectory exchange, owned by the handle ------------------------------------------------------ */
+/* One process (or host thread) per GPU, each with one handle holding an equal block of the swarm in rank order
+ * (agent_id_base = rank * n_agents_local).  "/broadcast_traj" (plan_manager/src/fake_plan_manager.cpp:364-399 ->
+ * traj_coordinator/src/particles.cpp:131-191) becomes ONE ncclAllGather of n_agents_local 1536-byte records per cycle:
+ *   pop_comm_unique_id   rank 0 creates the 128-byte NCCL id (ncclGetUniqueId) and hands it to every rank by the
+ *                        host's own means (MPI, a file, torch.distributed, ...);
+ *   pop_comm_init        ncclCommInitRank; the handle owns the communicator until pop_destroy.  world = 1 needs no id;
+ *   pop_exchange_trajs   after a cycle: allgather of the records the cycle published (send buffer) into the table the
+ *                        next map update projects (receive buffer), on the handle's stream, asynchronous.  Without a
+ *                        communicator (single GPU) it is the device-to-device publish of pop_traj_publish_local.
+ * NCCL is loaded at run time (libnccl.so.2); POP_E_UNSUPPORTED if it is not there. */
+#define POP_COMM_ID_BYTES 128
+int pop_comm_unique_id(void* id_out /* POP_COMM_ID_BYTES */);
+int pop_comm_init(pop_handle* h, const void* nccl_unique_id, int rank, int world);
+int pop_comm_info(const pop_handle* h, int* rank, int* world, int* nccl_version);
+int pop_exchange_trajs(pop_handle* h);
 /* Device buffers for the per-cycle trajectory allgather ("/broadcast_traj",
  * plan_manager/src/fake_plan_manager.cpp:364-399 → particles.cpp:131-191):
  * *send_dev = n_agents_local records produced by the last cycle,

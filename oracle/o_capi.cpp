@@ -2,6 +2,8 @@
 #include <algorithm>
 #include <cstdio>
 
+#include <cstring>
+
 #include "oracle.hpp"
 
 using namespace orc;
@@ -27,6 +29,44 @@ static Swarm make_swarm(const pop_config& c, const double* offs, const int32_t* 
 }
 
 extern "C" {
+
+// The reference's simulator defaults (plan_env/include/plan_env/map_parameters.h:5-13, fake_particle_risk_voxel.h:28-29,
+// plan_manager/config/sim_fake.yaml with the fall-backs of map.cpp:15-40, fake_risk_hybrid_a_star.cpp:62-82,
+// baseline_fake.h:84-113, particles.cpp:28-34; OSQP defaults of iosqp.hpp:87-89) — the oracle's own statement of them, so
+// that the CPU arm of bench.py needs nothing from libpop.  tests/test_abi.py checks it against pop_default_config.
+void orc_default_config(pop_config* c) {
+  std::memset(c, 0, sizeof(*c));
+  c->abi_version = POP_ABI_VERSION;
+  c->nx = 66; c->ny = 66; c->nz = 20; c->nt = 9;
+  c->resolution = 0.15f;
+  c->time_resolution = 0.2f;
+  c->risk_threshold = 0.2f;
+  c->clearance = 0.45f;
+  c->ground_height = -0.01f;
+  c->ceiling_height = 3.0f;
+  c->risk_threshold_region = 1.2f;
+  c->risk_region_decay = 0.2f;
+  c->risk_voxel_decay = 0.2f;
+  c->kernel_shape = POP_KERNEL_DISC_Z0;
+  c->query_variant = POP_QUERY_FAKE;
+  c->cell_dtype = POP_CELL_F32;
+  c->n_agents_local = 1; c->n_agents_total = 1; c->agent_id_base = 0;
+  c->drone_size[0] = 0.4; c->drone_size[1] = 0.4; c->drone_size[2] = 0.45;
+  c->replan_risk_rate = 0.f;
+  c->num_resample = 10;
+  c->max_tau = 2.0; c->max_vel = 2.0; c->max_acc = 6.0; c->w_time = 5.0; c->horizon = 5.0;
+  c->lambda_heu = 5.0; c->resolution_astar = 0.15; c->time_resolution_astar = 0.3;
+  c->allocate_num = 10000; c->check_num = 1; c->tolerance = 1;
+  c->corridor_tau = 0.3; c->init_range = 1.2; c->shrink_size = 0.2;
+  c->opt_max_vel = 2.0; c->opt_max_acc = 6.0;
+  c->max_cloud_points = 1 << 18;
+  c->max_cylinders = 256;
+  c->max_obstacle_points = 16384;
+  c->osqp_max_iter = 4000;
+  c->osqp_adaptive_rho_interval = 25;
+  c->osqp_check_termination = 25;
+  c->osqp_eps_abs = 1e-3; c->osqp_eps_rel = 1e-3;
+}
 
 void* orc_map_create(const pop_config* cfg) {
   OrcMap* m = new OrcMap();
@@ -305,7 +345,7 @@ int orc_safe_after_opt(const pop_config* cfg, const double* offs, const int32_t*
 double orc_cycle_batch(const pop_config* cfg, int a0, int a1, int n_threads, const float* cloud, int n_cloud,
                        const pop_cylinder* cyl, int n_cyl, const float* poses, const double* offs,
                        const int32_t* counts, const pop_traj_record* recs, const double* start, const double* goal,
-                       double t_map, double t_plan, int32_t* status_out);
+                       double t_map, double t_plan, int32_t* status_out, pop_traj_record* recs_out);
 
 }  // extern "C"
 
@@ -317,7 +357,7 @@ extern "C" double orc_cycle_batch(const pop_config* cfg, int a0, int a1, int n_t
                                   int n_cloud, const pop_cylinder* cyl, int n_cyl, const float* poses,
                                   const double* offs, const int32_t* counts, const pop_traj_record* recs,
                                   const double* start, const double* goal, double t_map, double t_plan,
-                                  int32_t* status_out) {
+                                  int32_t* status_out, pop_traj_record* recs_out) {
   const auto t0 = std::chrono::steady_clock::now();
   std::atomic<int> next(a0);
   Swarm swarm;
@@ -335,7 +375,7 @@ extern "C" double orc_cycle_batch(const pop_config* cfg, int a0, int a1, int n_t
       pop_config c = *cfg;
       c.agent_id_base = a;
       status_out[local] = replan(g, c, recs ? &swarm : nullptr, a, start + 9 * local, goal + 3 * local, t_plan,
-                                 nullptr, nullptr);
+                                 recs_out ? &recs_out[local] : nullptr, nullptr);   // records of failed replans stay untouched
     }
   };
   std::vector<std::thread> th;

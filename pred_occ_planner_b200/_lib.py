@@ -170,6 +170,13 @@ SYMBOLS = [
     ("pop_default_config", None, [C.POINTER(PopConfig)]),
     ("pop_set_world_cloud", _I, [_VP, _PF, _I]),
     ("pop_set_cylinders", _I, [_VP, C.POINTER(PopCylinder), _I]),
+    ("pop_set_world_cloud_dev", _I, [_VP, _VP, _I]),
+    ("pop_set_cylinders_dev", _I, [_VP, _VP, _I, _D]),
+    ("pop_get_trajectories", _I, [_VP, C.POINTER(PopTrajRecord)]),
+    ("pop_comm_unique_id", _I, [_VP]),
+    ("pop_comm_init", _I, [_VP, _VP, _I, _I]),
+    ("pop_comm_info", _I, [_VP, C.POINTER(_I), C.POINTER(_I), C.POINTER(_I)]),
+    ("pop_exchange_trajs", _I, [_VP]),
     ("pop_set_poses", _I, [_VP, _PF]),
     ("pop_set_body_particles", _I, [_VP, _PD, _PI32]),
     ("pop_set_trajectories", _I, [_VP, C.POINTER(PopTrajRecord)]),

@@ -675,6 +675,7 @@ extern "C" int pop_astar_search_batch(pop_handle* h, const double* start, const 
                                       const double* t_start, int32_t* out_ret, double* out_path,
                                       int32_t* out_len, int32_t* out_stats) {
   if (!h || !start || !goal || !t_start || !out_ret || !out_path || !out_len) return POP_E_INVALID;
+  PopDeviceGuard guard(h);
   if (!h->map_ready) return pop_fail(h, POP_E_STATE, "A* before the first map update");
   int rc = popk_astar_alloc(h);
   if (rc) return rc;

@@ -853,6 +853,7 @@ extern "C" int pop_corridor_batch(pop_handle* h, const double* path, const int32
                                   int32_t* out_npoly, double* out_goal) {
   if (!h || !path || !len || !start || !traj_start_time || !out_hpoly || !out_rows || !out_npoly || !out_goal)
     return POP_E_INVALID;
+  PopDeviceGuard guard(h);
   if (!h->map_ready) return pop_fail(h, POP_E_STATE, "corridor stage before the first map update");
   int rc = popk_corridor_alloc(h);
   if (rc) return rc;

@@ -279,6 +279,7 @@ extern "C" {
 int pop_separation_check_batch(pop_handle* h, const int32_t* n_pieces, const double* cpts, double t_now,
                                int8_t* out_safe) {
   if (!h || !n_pieces || !cpts || !out_safe) return POP_E_INVALID;
+  PopDeviceGuard guard(h);
   int rc = plan_alloc(h);
   if (rc) return rc;
   PlanDev* d = h->plan;
@@ -300,6 +301,7 @@ int pop_separation_check_batch(pop_handle* h, const int32_t* n_pieces, const dou
 
 int pop_replan_cycle_resident(pop_handle* h, double t_map, double t_plan) {
   if (!h) return POP_E_INVALID;
+  PopDeviceGuard guard(h);
   if (!h->astar) return pop_fail(h, POP_E_STATE, "no resident inputs: call pop_replan_cycle (or pop_astar_search_batch) once first");
   return cycle_enqueue(h, t_map, t_plan);
 }
@@ -308,11 +310,13 @@ static int replan_cycle_io(pop_handle* h, const pop_cycle_io* io, bool update_ma
 
 int pop_replan_cycle(pop_handle* h, const pop_cycle_io* io) {
   if (!h || !io || !io->start || !io->goal || !io->poses || !io->status || !io->traj) return POP_E_INVALID;
+  PopDeviceGuard guard(h);
   return replan_cycle_io(h, io, true);
 }
 
 int pop_plan_cycle(pop_handle* h, const pop_cycle_io* io) {
   if (!h || !io || !io->start || !io->goal || !io->status || !io->traj) return POP_E_INVALID;
+  PopDeviceGuard guard(h);
   if (!h->map_ready) return pop_fail(h, POP_E_STATE, "no map yet: call pop_dsp_update or pop_map_update_gt first");
   return replan_cycle_io(h, io, false);
 }
@@ -338,6 +342,7 @@ static int replan_cycle_io(pop_handle* h, const pop_cycle_io* io, bool update_ma
 
 extern "C" int pop_cycle_results(pop_handle* h, int32_t* status, pop_traj_record* traj) {
   if (!h) return POP_E_INVALID;
+  PopDeviceGuard guard(h);
   if (!h->plan) return pop_fail(h, POP_E_STATE, "no cycle has run yet");
   const int nl = h->cfg.n_agents_local;
   if (status) POP_CUDA(h, cudaMemcpyAsync(status, h->plan->status, sizeof(int) * nl, cudaMemcpyDeviceToHost, h->stream));
@@ -348,6 +353,7 @@ extern "C" int pop_cycle_results(pop_handle* h, int32_t* status, pop_traj_record
 
 extern "C" int pop_traj_publish_local(pop_handle* h) {
   if (!h) return POP_E_INVALID;
+  PopDeviceGuard guard(h);
   POP_CUDA(h, cudaMemcpyAsync(h->d_traj_all + h->cfg.agent_id_base, h->d_traj_send,
                               sizeof(pop_traj_record) * h->cfg.n_agents_local, cudaMemcpyDeviceToDevice, h->stream));
   h->have_traj = true;

@@ -158,6 +158,7 @@ extern "C" {
 int pop_traj_sample_batch(pop_handle* h, int all_agents, const double* t_abs, int n_t, double* out_pva,
                           int8_t* out_valid) {
   if (!h || !t_abs || n_t < 1 || !out_pva || !out_valid) return POP_E_INVALID;
+  PopDeviceGuard guard(h);
   const int n = all_agents ? h->cfg.n_agents_total : h->cfg.n_agents_local;
   const pop_traj_record* recs = all_agents ? h->d_traj_all : h->d_traj_send;
   const size_t n_out = static_cast<size_t>(n) * n_t;
@@ -179,6 +180,7 @@ int pop_traj_sample_batch(pop_handle* h, int all_agents, const double* t_abs, in
 
 int pop_traj_safe_batch(pop_handle* h, double t_now, double T, int8_t* out_safe, double* out_t_unsafe) {
   if (!h || !out_safe) return POP_E_INVALID;
+  PopDeviceGuard guard(h);
   if (!h->map_ready) return pop_fail(h, POP_E_STATE, "isTrajSafe before the first map update");
   const int nl = h->cfg.n_agents_local;
   int rc = pop_ensure_scratch(h, nl * (sizeof(double) + 1) + 64, 0);
@@ -201,6 +203,7 @@ int pop_traj_safe_batch(pop_handle* h, double t_now, double T, int8_t* out_safe,
 
 int pop_swarm_advance(pop_handle* h, double t_next) {
   if (!h) return POP_E_INVALID;
+  PopDeviceGuard guard(h);
   if (!h->astar) return pop_fail(h, POP_E_STATE, "no resident agent states: run a cycle first");
   const int nl = h->cfg.n_agents_local;
   k_swarm_advance<<<(nl + 127) / 128, 128, 0, h->stream>>>(h->d_traj_send, nl, t_next, popk_astar_start_dev(h), h->d_poses);
@@ -211,6 +214,7 @@ int pop_swarm_advance(pop_handle* h, double t_next) {
 
 int pop_swarm_states(pop_handle* h, double* out_start) {
   if (!h || !out_start) return POP_E_INVALID;
+  PopDeviceGuard guard(h);
   if (!h->astar) return pop_fail(h, POP_E_STATE, "no resident agent states: run a cycle first");
   POP_CUDA(h, cudaMemcpyAsync(out_start, popk_astar_start_dev(h), sizeof(double) * 9 * h->cfg.n_agents_local,
                               cudaMemcpyDeviceToHost, h->stream));
@@ -220,6 +224,7 @@ int pop_swarm_states(pop_handle* h, double* out_start) {
 
 int pop_eval_metrics(pop_handle* h, double t, double* out_min_obs, double* out_min_uav) {
   if (!h || !out_min_obs || !out_min_uav) return POP_E_INVALID;
+  PopDeviceGuard guard(h);
   if (!h->astar) return pop_fail(h, POP_E_STATE, "no resident agent states: run a cycle first");
   const int nl = h->cfg.n_agents_local;
   int rc = pop_ensure_scratch(h, sizeof(double) * 2 * nl, 0);

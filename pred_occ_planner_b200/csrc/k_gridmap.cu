@@ -465,6 +465,16 @@ struct pop_gridmap {
   size_t rays_smem = 0;
 };
 
+// see PopDeviceGuard (pop_internal.h): the map's device is current inside every entry point, the caller's afterwards
+struct GmDeviceGuard {
+  int prev = -1;
+  bool switched = false;
+  explicit GmDeviceGuard(const pop_gridmap* g) {
+    if (g && cudaGetDevice(&prev) == cudaSuccess && prev != g->device) switched = cudaSetDevice(g->device) == cudaSuccess;
+  }
+  ~GmDeviceGuard() { if (switched) cudaSetDevice(prev); }
+};
+
 static int gm_fail(pop_gridmap* g, int code, const char* fmt, ...) {
   char buf[512];
   va_list ap;
@@ -502,6 +512,8 @@ const char* pop_gridmap_last_error(const pop_gridmap* g) { return g ? g->err.c_s
 
 int pop_gridmap_destroy(pop_gridmap* g) {
   if (!g) return POP_OK;
+  int prev = -1;
+  if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
   cudaSetDevice(g->device);
   if (g->stream) cudaStreamSynchronize(g->stream);
   for (void* p : g->allocs) cudaFree(p);
@@ -510,6 +522,7 @@ int pop_gridmap_destroy(pop_gridmap* g) {
   if (g->d_R) cudaFree(g->d_R);
   if (g->own_stream && g->stream) cudaStreamDestroy(g->stream);
   delete g;
+  if (prev >= 0) cudaSetDevice(prev);
   return POP_OK;
 }
 
@@ -526,6 +539,11 @@ int pop_gridmap_create(const pop_gridmap_config* c, int n_maps, int device, void
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) { cudaGetLastError(); return POP_E_NO_DEVICE; }
   pop_gridmap* g = new pop_gridmap();
   g->cfg = *c; g->n_maps = n_maps; g->device = device;
+  struct Restore {   // leave the caller's current device as it was
+    int prev = -1;
+    Restore() { if (cudaGetDevice(&prev) != cudaSuccess) prev = -1; }
+    ~Restore() { if (prev >= 0) cudaSetDevice(prev); }
+  } restore;
   auto fail = [&](int code) { pop_gridmap_destroy(g); return code; };
   if (cudaSetDevice(device) != cudaSuccess) return fail(POP_E_NO_DEVICE);
   if (stream) g->stream = static_cast<cudaStream_t>(stream);
@@ -644,6 +662,7 @@ static int gm_check_cameras(pop_gridmap* g, const double* cam_pos) {
 
 int pop_gridmap_update(pop_gridmap* g, const double* pts, const int32_t* counts, const double* cam_pos) {
   if (!g || !pts || !counts || !cam_pos) return POP_E_INVALID;
+  GmDeviceGuard guard(g);
   const GmGeo& G = g->G;
   const int A = g->n_maps;
   for (int m = 0; m < A; m++)
@@ -662,6 +681,7 @@ int pop_gridmap_update(pop_gridmap* g, const double* pts, const int32_t* counts,
 
 int pop_gridmap_set_depth_params(pop_gridmap* g, const pop_depth_params* p) {
   if (!g || !p) return POP_E_INVALID;
+  GmDeviceGuard guard(g);
   if (p->rows < 1 || p->cols < 1 || p->skip_pixel < 1 || p->depth_filter_margin < 0 || !(p->fx > 0) || !(p->fy > 0) ||
       !(p->k_depth_scaling_factor > 0))
     return gm_fail(g, POP_E_INVALID, "bad depth parameters");
@@ -678,6 +698,7 @@ int pop_gridmap_set_depth_params(pop_gridmap* g, const pop_depth_params* p) {
 
 int pop_gridmap_update_depth(pop_gridmap* g, const uint16_t* depth, const double* camera_r, const double* cam_pos) {
   if (!g || !depth || !camera_r || !cam_pos) return POP_E_INVALID;
+  GmDeviceGuard guard(g);
   if (!g->have_depth) return gm_fail(g, POP_E_STATE, "no depth parameters (pop_gridmap_set_depth_params)");
   int rc = gm_check_cameras(g, cam_pos);
   if (rc) return rc;
@@ -704,6 +725,7 @@ int pop_gridmap_update_depth(pop_gridmap* g, const uint16_t* depth, const double
 
 int pop_gridmap_projected_points(pop_gridmap* g, int map, double* out, int cap, int32_t* n_out) {
   if (!g || map < 0 || map >= g->n_maps || !out || !n_out || cap < 0) return POP_E_INVALID;
+  GmDeviceGuard guard(g);
   if (g->last_counts.empty()) return gm_fail(g, POP_E_STATE, "no depth frame has been projected yet");
   const int n = g->last_counts[map];
   *n_out = n;
@@ -715,6 +737,7 @@ int pop_gridmap_projected_points(pop_gridmap* g, int map, double* out, int cap, 
 
 int pop_gridmap_query(pop_gridmap* g, int map, const double* pos, int n, int8_t* out_occ, int8_t* out_inflate) {
   if (!g || map < 0 || map >= g->n_maps || !pos || n < 0) return POP_E_INVALID;
+  GmDeviceGuard guard(g);
   if (n == 0) return POP_OK;
   const size_t bytes = sizeof(double) * 3 * n + 2 * static_cast<size_t>(n) + 64;
   if (bytes > g->d_q_bytes) {
@@ -737,6 +760,7 @@ int pop_gridmap_query(pop_gridmap* g, int map, const double* pos, int n, int8_t*
 
 int pop_gridmap_download(pop_gridmap* g, int map, double* occ, int8_t* inflate, int32_t* bounds) {
   if (!g || map < 0 || map >= g->n_maps) return POP_E_INVALID;
+  GmDeviceGuard guard(g);
   const GmMap& M = g->h_maps[map];
   if (occ) GM_CUDA(g, cudaMemcpyAsync(occ, M.occ, sizeof(double) * g->G.N, cudaMemcpyDeviceToHost, g->stream));
   if (inflate) GM_CUDA(g, cudaMemcpyAsync(inflate, M.inflate, g->G.N, cudaMemcpyDeviceToHost, g->stream));

@@ -1305,6 +1305,7 @@ extern "C" int pop_qp_solve_batch(pop_handle* h, int n, const int32_t* n_pieces,
                                   int32_t* out_iters) {
   if (!h || n <= 0 || !n_pieces || !init || !goal || !dur || !hpoly || !rows || !out_cpts || !out_status)
     return POP_E_INVALID;
+  PopDeviceGuard guard(h);
   for (int i = 0; i < n; i++) {
     if (n_pieces[i] < 0 || n_pieces[i] > POP_MAX_PIECES) return pop_fail(h, POP_E_CAPACITY, "problem %d has %d pieces (max %d)", i, n_pieces[i], POP_MAX_PIECES);
     for (int k = 0; k < n_pieces[i]; k++)
@@ -1341,6 +1342,7 @@ extern "C" int pop_qp_solve_batch(pop_handle* h, int n, const int32_t* n_pieces,
 // loop} and the number of factorisations; out = n x 8 int64.
 extern "C" int pop_qp_profile(pop_handle* h, int n, int64_t* out) {
   if (!h || !out || n <= 0) return POP_E_INVALID;
+  PopDeviceGuard guard(h);
   if (!h->qp || n > h->qp->cap_agents) return pop_fail(h, POP_E_STATE, "no QP launch to report on");
   POP_CUDA(h, cudaMemcpyAsync(out, h->qp->prof, sizeof(long long) * 8 * n, cudaMemcpyDeviceToHost, h->stream));
   POP_CUDA(h, cudaStreamSynchronize(h->stream));

@@ -156,6 +156,7 @@ void pop_camera_default(pop_camera* c, int width, int height) {
 
 int pop_render_set_camera(pop_handle* h, const pop_camera* cam) {
   if (!h || !cam) return POP_E_INVALID;
+  PopDeviceGuard guard(h);
   if (!h->dsp) return pop_fail(h, POP_E_STATE, "attach the particle map first (pop_dsp_attach): the sensor renders into its input buffers");
   if (cam->width < 1 || cam->height < 1 || !(cam->fx > 0) || !(cam->fy > 0)) return pop_fail(h, POP_E_INVALID, "bad camera");
   DspDev* d = h->dsp;
@@ -172,6 +173,7 @@ int pop_render_set_camera(pop_handle* h, const pop_camera* cam) {
 
 int pop_render_depth(pop_handle* h, const double* pos, const double* quat, int32_t* out_depth_mm, int32_t* out_counts) {
   if (!h || !pos || !quat) return POP_E_INVALID;
+  PopDeviceGuard guard(h);
   if (!h->dsp || !h->dsp->have_camera) return pop_fail(h, POP_E_STATE, "no camera (pop_render_set_camera)");
   DspDev* d = h->dsp;
   const pop_camera& c = d->camera;
@@ -226,6 +228,7 @@ int pop_render_depth(pop_handle* h, const double* pos, const double* quat, int32
 
 int pop_render_download_cloud(pop_handle* h, int agent, float* out, int cap, int32_t* n_out) {
   if (!h || !out || !n_out || cap < 0) return POP_E_INVALID;
+  PopDeviceGuard guard(h);
   if (!h->dsp || !h->dsp->have_camera) return pop_fail(h, POP_E_STATE, "no camera (pop_render_set_camera)");
   if (agent < 0 || agent >= h->dsp->nl) return POP_E_INVALID;
   DspDev* d = h->dsp;

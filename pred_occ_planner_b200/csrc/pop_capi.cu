@@ -163,6 +163,11 @@ int pop_create(const pop_config* cfg, int device, void* stream, pop_handle** out
   pop_handle* h = new pop_handle();
   h->cfg = *cfg;
   h->device = device;
+  struct Restore {   // the caller's current device is the caller's business: put it back on every exit
+    int prev = -1;
+    Restore() { if (cudaGetDevice(&prev) != cudaSuccess) prev = -1; }
+    ~Restore() { if (prev >= 0) cudaSetDevice(prev); }
+  } restore;
   auto fail = [&](int code) { pop_destroy(h); return code; };
   if (cudaSetDevice(device) != cudaSuccess) return fail(POP_E_NO_DEVICE);
   if (stream) {
@@ -199,8 +204,11 @@ int pop_create(const pop_config* cfg, int device, void* stream, pop_handle** out
 
 int pop_destroy(pop_handle* h) {
   if (!h) return POP_OK;
+  int prev = -1;
+  if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
+  pop_comm_free(h);
   popk_vox_free(h);
   popk_dsp_free(h);
   for (cudaStream_t s : h->side) cudaStreamDestroy(s);
@@ -217,6 +225,7 @@ int pop_destroy(pop_handle* h) {
   for (cudaEvent_t e : h->prof.pool) cudaEventDestroy(e);
   if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
   delete h;
+  if (prev >= 0) cudaSetDevice(prev);
   return POP_OK;
 }
 
@@ -224,6 +233,7 @@ const char* pop_last_error(const pop_handle* h) { return h ? h->err.c_str() : "n
 
 int pop_sync(pop_handle* h) {
   if (!h) return POP_E_INVALID;
+  PopDeviceGuard guard(h);
   POP_CUDA(h, cudaStreamSynchronize(h->stream));
   return POP_OK;
 }
@@ -231,6 +241,7 @@ int pop_sync(pop_handle* h) {
 // ---- inputs ----------------------------------------------------------------------------------
 int pop_set_world_cloud(pop_handle* h, const float* pts, int n) {
   if (!h || n < 0 || (n > 0 && !pts)) return POP_E_INVALID;
+  PopDeviceGuard guard(h);
   if (n > h->cfg.max_cloud_points) return pop_fail(h, POP_E_CAPACITY, "cloud of %d points exceeds max_cloud_points=%d", n, h->cfg.max_cloud_points);
   if (n > 0) POP_CUDA(h, cudaMemcpyAsync(h->d_cloud, pts, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, h->stream));
   POP_CUDA(h, cudaStreamSynchronize(h->stream));
@@ -240,6 +251,7 @@ int pop_set_world_cloud(pop_handle* h, const float* pts, int n) {
 
 int pop_set_cylinders(pop_handle* h, const pop_cylinder* cyl, int n) {
   if (!h || n < 0 || (n > 0 && !cyl)) return POP_E_INVALID;
+  PopDeviceGuard guard(h);
   if (n > h->cfg.max_cylinders) return pop_fail(h, POP_E_CAPACITY, "%d cylinders exceed max_cylinders=%d", n, h->cfg.max_cylinders);
   std::vector<PopCylDev> v(n);
   float max_vy = 0.f;
@@ -254,8 +266,36 @@ int pop_set_cylinders(pop_handle* h, const pop_cylinder* cyl, int n) {
   return POP_OK;
 }
 
+// device-resident world inputs: the same two setters with device pointers, enqueued on the handle's stream (async)
+static __global__ void k_cyl_prepare(const pop_cylinder* __restrict__ in, int n, PopCylDev* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) geom_cyl_prepare(in[i], &out[i]);
+}
+int pop_set_world_cloud_dev(pop_handle* h, const float* pts_dev, int n) {
+  if (!h || n < 0 || (n > 0 && !pts_dev)) return POP_E_INVALID;
+  PopDeviceGuard guard(h);
+  if (n > h->cfg.max_cloud_points) return pop_fail(h, POP_E_CAPACITY, "cloud of %d points exceeds max_cloud_points=%d", n, h->cfg.max_cloud_points);
+  if (n > 0) POP_CUDA(h, cudaMemcpyAsync(h->d_cloud, pts_dev, sizeof(float) * 3 * n, cudaMemcpyDeviceToDevice, h->stream));
+  h->n_cloud = n;
+  return POP_OK;
+}
+int pop_set_cylinders_dev(pop_handle* h, const pop_cylinder* cyl_dev, int n, double max_abs_vy) {
+  if (!h || n < 0 || (n > 0 && !cyl_dev) || !(max_abs_vy >= 0.0)) return POP_E_INVALID;
+  PopDeviceGuard guard(h);
+  if (n > h->cfg.max_cylinders) return pop_fail(h, POP_E_CAPACITY, "%d cylinders exceed max_cylinders=%d", n, h->cfg.max_cylinders);
+  if (n > 0) {
+    k_cyl_prepare<<<(n + 63) / 64, 64, 0, h->stream>>>(cyl_dev, n, h->d_cyl);
+    POP_LAUNCH_CHECK(h);
+    h->n_launches++;
+  }
+  h->max_abs_vy = static_cast<float>(max_abs_vy);
+  h->n_cyl = n;
+  return POP_OK;
+}
+
 int pop_set_poses(pop_handle* h, const float* poses) {
   if (!h || !poses) return POP_E_INVALID;
+  PopDeviceGuard guard(h);
   POP_CUDA(h, cudaMemcpyAsync(h->d_poses, poses, sizeof(float) * 3 * h->cfg.n_agents_local, cudaMemcpyHostToDevice, h->stream));
   POP_CUDA(h, cudaStreamSynchronize(h->stream));
   return POP_OK;
@@ -263,6 +303,7 @@ int pop_set_poses(pop_handle* h, const float* poses) {
 
 int pop_set_body_particles(pop_handle* h, const double* offs, const int32_t* counts) {
   if (!h || !offs || !counts) return POP_E_INVALID;
+  PopDeviceGuard guard(h);
   const int nt = h->cfg.n_agents_total;
   for (int i = 0; i < nt; i++)
     if (counts[i] < 0 || counts[i] > POP_MAX_BODY) return pop_fail(h, POP_E_CAPACITY, "agent %d has %d body particles (max %d)", i, counts[i], POP_MAX_BODY);
@@ -275,14 +316,24 @@ int pop_set_body_particles(pop_handle* h, const double* offs, const int32_t* cou
 
 int pop_set_trajectories(pop_handle* h, const pop_traj_record* recs) {
   if (!h || !recs) return POP_E_INVALID;
+  PopDeviceGuard guard(h);
   POP_CUDA(h, cudaMemcpyAsync(h->d_traj_all, recs, sizeof(pop_traj_record) * h->cfg.n_agents_total, cudaMemcpyHostToDevice, h->stream));
   POP_CUDA(h, cudaStreamSynchronize(h->stream));
   h->have_traj = true;
   return POP_OK;
 }
 
+int pop_get_trajectories(pop_handle* h, pop_traj_record* recs) {
+  if (!h || !recs) return POP_E_INVALID;
+  PopDeviceGuard guard(h);
+  POP_CUDA(h, cudaMemcpyAsync(recs, h->d_traj_all, sizeof(pop_traj_record) * h->cfg.n_agents_total, cudaMemcpyDeviceToHost, h->stream));
+  POP_CUDA(h, cudaStreamSynchronize(h->stream));
+  return POP_OK;
+}
+
 int pop_traj_buffers(pop_handle* h, void** send_dev, void** recv_dev) {
   if (!h) return POP_E_INVALID;
+  PopDeviceGuard guard(h);
   if (send_dev) *send_dev = h->d_traj_send;
   if (recv_dev) *recv_dev = h->d_traj_all;
   h->have_traj = true;  // the caller fills recv_dev (allgather) before the next map update
@@ -292,6 +343,7 @@ int pop_traj_buffers(pop_handle* h, void** send_dev, void** recv_dev) {
 // ---- map ---------------------------------------------------------------------------------------
 int pop_map_update_gt(pop_handle* h, double t_map) {
   if (!h) return POP_E_INVALID;
+  PopDeviceGuard guard(h);
   h->t_map = t_map;
   int rc = popk_voxel_update(h);
   if (rc) return rc;
@@ -325,10 +377,12 @@ static int query_common(pop_handle* h, int agent, const double* pos, const int32
 }
 
 int pop_map_query(pop_handle* h, int agent, const double* pos, const int32_t* t_idx, int n, int8_t* out) {
+  PopDeviceGuard guard(h);
   if (n > 0 && !t_idx) return POP_E_INVALID;
   return query_common(h, agent, pos, t_idx, nullptr, n, out);
 }
 int pop_map_query_dt(pop_handle* h, int agent, const double* pos, const double* dt, int n, int8_t* out) {
+  PopDeviceGuard guard(h);
   if (n > 0 && !dt) return POP_E_INVALID;
   return query_common(h, agent, pos, nullptr, dt, n, out);
 }
@@ -336,6 +390,7 @@ int pop_map_query_dt(pop_handle* h, int agent, const double* pos, const double* 
 int pop_map_query_inflate(pop_handle* h, int agent, const double* pos, const double* t, int mode, int n, int8_t* out) {
   if (!h || agent < 0 || agent >= h->cfg.n_agents_local || n < 0 || mode < 0 || mode > 2 ||
       (n > 0 && (!pos || !out || (mode && !t)))) return POP_E_INVALID;
+  PopDeviceGuard guard(h);
   if (!h->map_ready) return pop_fail(h, POP_E_STATE, "query before the first map update");
   if (n == 0) return POP_OK;
   const size_t bpos = sizeof(double) * 3 * n, bt = sizeof(double) * n;
@@ -357,6 +412,7 @@ int pop_map_query_inflate(pop_handle* h, int agent, const double* pos, const dou
 int pop_map_obstacle_points(pop_handle* h, int agent, double t_start, double t_end, const double lc[3],
                             const double hc[3], double* out, int cap, int* n_out) {
   if (!h || agent < 0 || agent >= h->cfg.n_agents_local || !lc || !hc || cap < 0 || !n_out || (cap > 0 && !out)) return POP_E_INVALID;
+  PopDeviceGuard guard(h);
   if (!h->map_ready) return pop_fail(h, POP_E_STATE, "obstacle points before the first map update");
   int rc = pop_ensure_scratch(h, sizeof(double) * 3 * cap + 64, 0);
   if (rc) return rc;
@@ -376,6 +432,7 @@ int pop_map_obstacle_points(pop_handle* h, int agent, double t_start, double t_e
 
 int pop_map_add_particles(pop_handle* h, int agent, const double* pts, const float* risks, int n, int t_index) {
   if (!h || agent < 0 || agent >= h->cfg.n_agents_local || n < 0 || t_index < 0 || t_index >= h->cfg.nt || (n > 0 && (!pts || !risks))) return POP_E_INVALID;
+  PopDeviceGuard guard(h);
   if (n == 0) return POP_OK;
   if (h->cfg.cell_dtype == POP_CELL_U8)
     for (int i = 0; i < n; i++)
@@ -396,6 +453,7 @@ int pop_map_add_particles(pop_handle* h, int agent, const double* pts, const flo
 
 int pop_map_future_risk(pop_handle* h, const float* risk, const float* poses, double stamp) {
   if (!h || !risk) return POP_E_INVALID;
+  PopDeviceGuard guard(h);
   if (h->cfg.cell_dtype != POP_CELL_F32) return pop_fail(h, POP_E_UNSUPPORTED, "future-risk grids hold float risks: use POP_CELL_F32");
   const size_t per = sizeof(float) * static_cast<size_t>(h->geom.V) * h->geom.nt;
   int rc = pop_ensure_scratch(h, per, 0);
@@ -419,6 +477,7 @@ int pop_map_future_risk(pop_handle* h, const float* risk, const float* poses, do
 
 int pop_map_download(pop_handle* h, int agent, float* out) {
   if (!h || agent < 0 || agent >= h->cfg.n_agents_local || !out) return POP_E_INVALID;
+  PopDeviceGuard guard(h);
   const size_t bytes = sizeof(float) * static_cast<size_t>(h->geom.V) * h->geom.nt;
   int rc = pop_ensure_scratch(h, bytes, 0);
   if (rc) return rc;
@@ -432,6 +491,7 @@ int pop_map_download(pop_handle* h, int agent, float* out) {
 // ---- measurement -------------------------------------------------------------------------------
 int pop_profile_enable(pop_handle* h, int on) {
   if (!h) return POP_E_INVALID;
+  PopDeviceGuard guard(h);
   h->prof.enabled = on != 0;
   h->prof.map_only = on == 2;
   return POP_OK;
@@ -439,6 +499,7 @@ int pop_profile_enable(pop_handle* h, int on) {
 
 int pop_profile_read(pop_handle* h, float* ms, int64_t* launches, int reset) {
   if (!h) return POP_E_INVALID;
+  PopDeviceGuard guard(h);
   POP_CUDA(h, cudaStreamSynchronize(h->stream));
   for (auto& p : h->prof.pending) {
     float t = 0.f;

@@ -156,6 +156,7 @@ void pop_dsp_default_config(const pop_config* g, pop_dsp_config* c) {
 
 int pop_dsp_attach(pop_handle* h, const pop_dsp_config* c) {
   if (!h || !c) return POP_E_INVALID;
+  PopDeviceGuard guard(h);
   if (h->cfg.cell_dtype != POP_CELL_F32) return pop_fail(h, POP_E_UNSUPPORTED, "the particle map needs f32 SOGM cells");
   if (c->max_particle_num_voxel < 1 || 2 * c->max_particle_num_voxel > kDspSlotStride)
     return pop_fail(h, POP_E_INVALID, "max_particle_num_voxel must be in [1, %d]", kDspSlotStride / 2);
@@ -185,6 +186,7 @@ int pop_dsp_attach(pop_handle* h, const pop_dsp_config* c) {
 }
 
 int pop_dsp_set_random_tables(pop_handle* h, const float* pg, const float* vg, const int32_t* ur, int n) {
+  PopDeviceGuard guard(h);
   int rc = check(h, 0);
   if (rc) return rc;
   DspDev* d = h->dsp;
@@ -199,6 +201,7 @@ int pop_dsp_set_random_tables(pop_handle* h, const float* pg, const float* vg, c
 
 int pop_dsp_update(pop_handle* h, const float* cam, const int32_t* counts, const float* poses, const float* quats,
                    double stamp, int32_t* out_ok) {
+  PopDeviceGuard guard(h);
   int rc = check(h, 0);
   if (rc) return rc;
   if (!cam || !counts || !poses || !quats) return POP_E_INVALID;
@@ -206,6 +209,7 @@ int pop_dsp_update(pop_handle* h, const float* cam, const int32_t* counts, const
 }
 
 int pop_dsp_update_rendered(pop_handle* h, const float* poses, const float* quats, double stamp, int32_t* out_ok) {
+  PopDeviceGuard guard(h);
   int rc = check(h, 0);
   if (rc) return rc;
   if (!poses || !quats) return POP_E_INVALID;
@@ -216,6 +220,7 @@ int pop_dsp_update_rendered(pop_handle* h, const float* poses, const float* quat
 
 int pop_dsp_update_filtered(pop_handle* h, const float* pts, const int32_t* counts, const float* poses,
                             const float* quats, double stamp, int32_t* out_ok) {
+  PopDeviceGuard guard(h);
   int rc = check(h, 0);
   if (rc) return rc;
   if (!pts || !counts || !poses || !quats) return POP_E_INVALID;
@@ -223,6 +228,7 @@ int pop_dsp_update_filtered(pop_handle* h, const float* pts, const int32_t* coun
 }
 
 int pop_dsp_filter(pop_handle* h, int agent, const float* cam, int n, float* out, int32_t* n_out) {
+  PopDeviceGuard guard(h);
   int rc = check(h, agent);
   if (rc) return rc;
   DspDev* d = h->dsp;
@@ -247,6 +253,7 @@ int pop_dsp_filter(pop_handle* h, int agent, const float* cam, int n, float* out
 }
 
 int pop_dsp_download_particles(pop_handle* h, int agent, float* out) {
+  PopDeviceGuard guard(h);
   int rc = check(h, agent);
   if (rc) return rc;
   const size_t bytes = sizeof(float) * 8 * static_cast<size_t>(h->dsp->G.V) * h->dsp->G.S;
@@ -260,6 +267,7 @@ int pop_dsp_download_particles(pop_handle* h, int agent, float* out) {
 }
 
 int pop_dsp_download_voxels(pop_handle* h, int agent, float* out) {
+  PopDeviceGuard guard(h);
   int rc = check(h, agent);
   if (rc) return rc;
   const DspGeo& G = h->dsp->G;
@@ -270,6 +278,7 @@ int pop_dsp_download_voxels(pop_handle* h, int agent, float* out) {
 }
 
 int pop_dsp_download_observations(pop_handle* h, int agent, float* pc, int32_t* counts, float* max_length) {
+  PopDeviceGuard guard(h);
   int rc = check(h, agent);
   if (rc) return rc;
   DspDev* d = h->dsp;
@@ -289,6 +298,7 @@ int pop_dsp_download_observations(pop_handle* h, int agent, float* pc, int32_t* 
 }
 
 int pop_dsp_download_pyramids(pop_handle* h, int agent, int32_t* out) {
+  PopDeviceGuard guard(h);
   int rc = check(h, agent);
   if (rc) return rc;
   DspDev* d = h->dsp;
@@ -311,6 +321,7 @@ int pop_dsp_download_pyramids(pop_handle* h, int agent, int32_t* out) {
 }
 
 int pop_dsp_download_points_with_velocity(pop_handle* h, int agent, float* out, int cap, int32_t* n_out) {
+  PopDeviceGuard guard(h);
   int rc = check(h, agent);
   if (rc) return rc;
   DspDev* d = h->dsp;
@@ -325,6 +336,7 @@ int pop_dsp_download_points_with_velocity(pop_handle* h, int agent, float* out, 
 }
 
 int pop_dsp_stats(pop_handle* h, int agent, int32_t* out) {
+  PopDeviceGuard guard(h);
   int rc = check(h, agent);
   if (rc) return rc;
   DspDev* d = h->dsp;
@@ -338,6 +350,7 @@ int pop_dsp_stats(pop_handle* h, int agent, int32_t* out) {
 }
 
 int pop_dsp_occupied(pop_handle* h, int agent, float* out, int cap, int32_t* n_out) {
+  PopDeviceGuard guard(h);
   int rc = check(h, agent);
   if (rc) return rc;
   if (cap < 0 || !n_out) return POP_E_INVALID;

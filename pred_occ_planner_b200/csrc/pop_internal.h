@@ -46,6 +46,7 @@ struct CorridorDev;  // k_corridor.cu
 struct QpDev;      // k_qp.cu
 struct PlanDev;    // corridor + QP workspaces
 struct DspDev;     // k_dsp.cu: DSP particle maps
+struct CommDev;    // pop_comm.cu: the NCCL communicator of the trajectory exchange
 
 struct pop_handle {
   pop_config cfg;
@@ -87,6 +88,7 @@ struct pop_handle {
   QpDev* qp = nullptr;
   PlanDev* plan = nullptr;
   DspDev* dsp = nullptr;
+  CommDev* comm = nullptr;
   PopProfile prof;
   // agent-group pipelining of the planning stages (k_cycle.cu)
   std::vector<cudaStream_t> side;
@@ -105,7 +107,21 @@ int pop_fail(pop_handle* h, int code, const char* fmt, ...);
   } while (0)
 #define POP_LAUNCH_CHECK(h) POP_CUDA(h, cudaGetLastError())
 
+// Every entry point that touches the device runs with the handle's device current and restores the caller's on exit
+// (a process may hold handles on several GPUs, or switch devices between calls).
+struct PopDeviceGuard {
+  int prev = -1;
+  bool switched = false;
+  explicit PopDeviceGuard(const pop_handle* h) {
+    if (h && cudaGetDevice(&prev) == cudaSuccess && prev != h->device) switched = cudaSetDevice(h->device) == cudaSuccess;
+  }
+  ~PopDeviceGuard() { if (switched) cudaSetDevice(prev); }
+  PopDeviceGuard(const PopDeviceGuard&) = delete;
+  PopDeviceGuard& operator=(const PopDeviceGuard&) = delete;
+};
+
 void pop_plan_free(pop_handle* h);
+void pop_comm_free(pop_handle* h);
 void popk_dsp_free(pop_handle* h);
 int pop_ensure_scratch(pop_handle* h, size_t dev_bytes, size_t host_bytes);
 void pop_prof_begin(pop_handle* h, int stage);

@@ -36,6 +36,7 @@ class PopEngine:
             raise PopError(rc, "pop_create failed (no CUDA device → NO_DEVICE; there is no CPU fallback)")
         self.n_local = cfg.n_agents_local
         self.n_total = cfg.n_agents_total
+        self.device = int(device)
 
     # -- plumbing ----------------------------------------------------------------------------
     def _check(self, rc: int):
@@ -64,6 +65,20 @@ class PopEngine:
     def set_cylinders(self, cyl: np.ndarray):
         cyl = np.ascontiguousarray(cyl, dtype=_lib.CYL_DTYPE)
         self._check(self.lib.pop_set_cylinders(self._h, cyl.ctypes.data_as(C.POINTER(PopCylinder)), len(cyl)))
+
+    def set_world_cloud_dev(self, ptr: int, n: int):
+        """world cloud already in device memory (n x 3 float32 at device address ptr); async on the engine's stream"""
+        self._check(self.lib.pop_set_world_cloud_dev(self._h, C.c_void_p(ptr), int(n)))
+
+    def set_cylinders_dev(self, ptr: int, n: int, max_abs_vy: float):
+        """obstacle states already in device memory (n pop_cylinder records at device address ptr); async"""
+        self._check(self.lib.pop_set_cylinders_dev(self._h, C.c_void_p(ptr), int(n), float(max_abs_vy)))
+
+    def get_trajectories(self) -> np.ndarray:
+        """the peers' table as the next map update will read it (n_total records)"""
+        recs = np.zeros(self.n_total, TRAJ_DTYPE)
+        self._check(self.lib.pop_get_trajectories(self._h, recs.ctypes.data_as(C.POINTER(PopTrajRecord))))
+        return recs
 
     def set_poses(self, poses: np.ndarray):
         poses = np.ascontiguousarray(poses, dtype=np.float32).reshape(self.n_local, 3)
@@ -230,6 +245,28 @@ class PopEngine:
 
     def traj_publish_local(self):
         self._check(self.lib.pop_traj_publish_local(self._h))
+
+    # -- multi-GPU exchange (csrc/pop_comm.cu) ------------------------------------------------
+    def comm_unique_id(self) -> bytes:
+        """ncclGetUniqueId: create on rank 0, hand to every rank"""
+        buf = (C.c_uint8 * 128)()
+        rc = self.lib.pop_comm_unique_id(C.cast(buf, C.c_void_p))
+        if rc != 0:
+            raise PopError(rc, "pop_comm_unique_id failed (libnccl.so.2 not loadable?)")
+        return bytes(buf)
+
+    def comm_init(self, unique_id: bytes | None, rank: int, world: int):
+        buf = (C.c_uint8 * 128).from_buffer_copy(unique_id) if unique_id is not None else None
+        self._check(self.lib.pop_comm_init(self._h, C.cast(buf, C.c_void_p) if buf is not None else None, int(rank), int(world)))
+
+    def comm_info(self):
+        r, w, v = C.c_int(0), C.c_int(0), C.c_int(0)
+        self._check(self.lib.pop_comm_info(self._h, C.byref(r), C.byref(w), C.byref(v)))
+        return r.value, w.value, v.value
+
+    def exchange_trajs(self):
+        """one ncclAllGather of this cycle's trajectory records (or the local publish on a single GPU); async"""
+        self._check(self.lib.pop_exchange_trajs(self._h))
 
     def traj_buffers(self):
         s, r = C.c_void_p(), C.c_void_p()

@@ -9,8 +9,9 @@ Here the same one-cycle-delayed semantics come from an allgather of `pop_traj_re
 (include/pop.h) placed between cycle k's QP and cycle k+1's map update.  Body particles
 ("/broadcast_particles", particles.cpp:25,62-87) are static and are gathered once at start-up.
 
-torch.distributed is only the transport (NCCL over NVLink on GPUs, gloo on CPU for the tests);
-the buffers are libpop's own device allocations, wrapped zero-copy.
+On GPUs the allgather is issued by libpop itself (pop_comm_init / pop_exchange_trajs, csrc/pop_comm.cu: NCCL over
+NVLink on the handle's stream); torch.distributed only carries the 128-byte communicator id at start-up, and on CPU
+(gloo) the host-array path the tests exercise.
 """
 from __future__ import annotations
 
@@ -37,43 +38,44 @@ def owner(agent_id: int, n_total: int, world: int) -> int:
     return agent_id // (n_total // world)
 
 
-class _DevBytes:
-    """__cuda_array_interface__ view of a raw device pointer (no copy, no ownership)."""
-
-    def __init__(self, ptr: int, nbytes: int):
-        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
-
-
 class TrajExchange:
     """The per-cycle "/broadcast_traj" step.
 
-    device mode (engine given): wraps the engine's send / receive buffers as torch tensors once and
-    issues `all_gather_into_tensor` on the CURRENT torch stream (make that the engine's stream);
-    world == 1 falls back to the engine's device-to-device publish.
+    device mode (engine given): the exchange lives behind the C ABI — `pop_comm_init` gives the engine's handle an
+    NCCL communicator (the 128-byte id is created on rank 0 by `pop_comm_unique_id` and broadcast here over the
+    default torch.distributed group, whatever its backend) and `step()` is `pop_exchange_trajs`: one ncclAllGather
+    on the engine's stream between libpop's own buffers; world == 1 is the device-to-device publish.
     host mode (engine None): numpy records in, numpy records out over the default process group
     (gloo) — the path the CPU tests exercise.
     """
 
-    def __init__(self, n_total: int, world: int, rank: int, engine=None, device: int | None = None):
+    def __init__(self, n_total: int, world: int, rank: int, engine=None, device: int | None = None, unique_id: bytes | None = None):
         self.world, self.rank, self.n_total = world, rank, n_total
         self.id_base, self.n_local = shard(n_total, world, rank)
         self.engine = engine
         self.bytes_per_cycle = self.n_local * RECORD_BYTES
-        self._send = self._recv = None
-        if engine is not None and world > 1:
-            import torch
-            send_ptr, recv_ptr = engine.traj_buffers()
-            dev = f"cuda:{device if device is not None else 0}"
-            self._send = torch.as_tensor(_DevBytes(send_ptr, self.n_local * RECORD_BYTES), device=dev)
-            self._recv = torch.as_tensor(_DevBytes(recv_ptr, n_total * RECORD_BYTES), device=dev)
+        if engine is not None:
+            if device is not None and device != engine.device:
+                raise ValueError(f"engine lives on cuda:{engine.device}, not cuda:{device}")
+            if world > 1 and unique_id is None:
+                unique_id = self._broadcast_id(engine, rank)
+            engine.comm_init(unique_id, rank, world)
+
+    @staticmethod
+    def _broadcast_id(engine, rank: int) -> bytes:
+        import torch
+        import torch.distributed as dist
+        buf = torch.zeros(128, dtype=torch.uint8)
+        if rank == 0:
+            buf = torch.frombuffer(bytearray(engine.comm_unique_id()), dtype=torch.uint8).clone()
+        if dist.get_backend() == "nccl":
+            buf = buf.to(f"cuda:{engine.device}")
+        dist.broadcast(buf, src=0)
+        return bytes(buf.cpu().numpy().tobytes())
 
     def step(self, local_records: np.ndarray | None = None) -> np.ndarray | None:
         if self.engine is not None:
-            if self.world > 1:
-                import torch.distributed as dist
-                dist.all_gather_into_tensor(self._recv, self._send)
-            else:
-                self.engine.traj_publish_local()
+            self.engine.exchange_trajs()
             return None
         import torch
         import torch.distributed as dist

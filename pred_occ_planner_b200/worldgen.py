@@ -21,8 +21,9 @@ def _rng(seed: int) -> np.random.Generator:
 
 
 def make_world(seed: int, arena=(30.0, 30.0, 5.0), n_static=0, n_moving=40, v_max=1.0,
-               w_range=(0.5, 1.0), height=4.0, res_gen=0.1):
-    """Returns (cloud float32 [n,3], cylinders CYL_DTYPE [n_static+n_moving])."""
+               w_range=(0.5, 1.0), height=4.0, res_gen=0.1, return_owner=False):
+    """Returns (cloud float32 [n,3], cylinders CYL_DTYPE [n_static+n_moving]) and, with return_owner, the index of the
+    cylinder each cloud point belongs to (int32 [n]) so that a caller can move the cloud with its obstacles."""
     rng = _rng(seed)
     ax, ay = arena[0] / 2 - 1.0, arena[1] / 2 - 1.0
     n = n_static + n_moving
@@ -51,7 +52,23 @@ def make_world(seed: int, arena=(30.0, 30.0, 5.0), n_static=0, n_moving=40, v_ma
         clouds.append(pts.astype(np.float32))
         cyl[i] = (3, 0, x, y, 0.0, w, height, vx, vy, 1.0, 0.0, 0.0, 0.0)
     cloud = np.concatenate(clouds, axis=0) if clouds else np.zeros((0, 3), np.float32)
+    if return_owner:
+        owner = np.concatenate([np.full(len(c), i, np.int32) for i, c in enumerate(clouds)]) if clouds else np.zeros(0, np.int32)
+        return np.ascontiguousarray(cloud), cyl, owner
     return np.ascontiguousarray(cloud), cyl
+
+
+def advance_world(cloud0: np.ndarray, cyl0: np.ndarray, owner: np.ndarray, dt: float):
+    """The ground-truth world dt seconds later: every obstacle translated by its velocity (the reference's simulator
+    moves them by a fixed step per 10 Hz tick and reflects at the arena walls, moving_cylinder.h:140-154; the few
+    seconds a bench covers stay inside the walls, so the reflection is left out), its cloud points with it."""
+    cyl = cyl0.copy()
+    cyl["x"] = cyl0["x"] + cyl0["vx"] * dt
+    cyl["y"] = cyl0["y"] + cyl0["vy"] * dt
+    cloud = cloud0.copy()
+    cloud[:, 0] += (cyl0["vx"][owner] * dt).astype(np.float32)
+    cloud[:, 1] += (cyl0["vy"][owner] * dt).astype(np.float32)
+    return cloud, cyl
 
 
 def make_rings(seed: int, arena=(30.0, 30.0, 5.0), n=4, v_max=1.0, r_range=(0.7, 2.5), z_range=(0.8, 2.0),

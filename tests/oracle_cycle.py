@@ -43,8 +43,10 @@ def safe_after_opt(cfg, swarm, ego_id, cpts, M, t0):
                                        C.c_double(t0)))
 
 
-def cycle_batch(cfg, a0, a1, n_threads, cloud, cyl, poses, swarm, start, goal, t_map, t_plan):
-    """Multi-threaded CPU cycle (map update + replan) for agents [a0, a1); returns (seconds, status)."""
+def cycle_batch(cfg, a0, a1, n_threads, cloud, cyl, poses, swarm, start, goal, t_map, t_plan, records=None):
+    """Multi-threaded CPU cycle (map update + replan) for agents [a0, a1); returns (seconds, status).
+    records (n_agents_local TRAJ_DTYPE, optional): the entries of successful replans are overwritten with the new
+    trajectory records, failed ones keep what they held (as k_finalize does)."""
     lib = oracle_lib.load().lib
     lib.orc_cycle_batch.restype = C.c_double
     cloud = np.ascontiguousarray(cloud, np.float32)
@@ -63,5 +65,5 @@ def cycle_batch(cfg, a0, a1, n_threads, cloud, cyl, poses, swarm, start, goal, t
     sec = lib.orc_cycle_batch(C.byref(cfg), int(a0), int(a1), int(n_threads), _p(cloud, C.c_float), len(cloud),
                               C.c_void_p(cyl.ctypes.data), len(cyl), _p(poses, C.c_float), offs_p, counts_p, recs_p,
                               _p(start, C.c_double), _p(goal, C.c_double), C.c_double(t_map), C.c_double(t_plan),
-                              _p(status, C.c_int32))
+                              _p(status, C.c_int32), C.c_void_p(records.ctypes.data) if records is not None else None)
     return sec, status

@@ -35,6 +35,14 @@ def load():
     return _lib
 
 
+def default_config():
+    """pop_config with the reference's simulator defaults, from the oracle (no libpop involved)."""
+    from pred_occ_planner_b200._lib import PopConfig
+    cfg = PopConfig()
+    load().lib.orc_default_config(C.byref(cfg))
+    return cfg
+
+
 def _p(a, t):
     return a.ctypes.data_as(C.POINTER(t))
 

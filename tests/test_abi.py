@@ -92,3 +92,11 @@ def test_raycast_map_has_no_cpu_fallback(pop):
     with pytest.raises(pop.PopError) as e:
         gridmap.GridMaps(n_maps=1)
     assert e.value.code == -2  # POP_E_NO_DEVICE
+
+
+def test_oracle_default_config_equals_libpops(pop, oracle):
+    """bench.py's CPU arm takes its configuration from the oracle (it must not load libpop): both statements of the
+    reference's simulator defaults are the same bytes."""
+    from tests import oracle_lib
+    a, b = pop.default_config(), oracle_lib.default_config()
+    assert bytes(a) == bytes(b)

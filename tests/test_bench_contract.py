@@ -32,3 +32,13 @@ def test_reference_arm_prints_one_contract_line():
 def test_reference_arm_other_ranks_stay_silent():
     out = _run({"RANK": "1", "WORLD_SIZE": "2", "LOCAL_RANK": "1"})
     assert out.strip() == ""
+
+
+def test_reference_arm_does_not_load_libpop():
+    """The CPU arm is the checker's code only: configuration from the oracle, world from the pure-Python generator —
+    libpop.so (the product) is never mapped into that process."""
+    code = ("import sys, runpy; sys.argv = ['bench.py', '--impl', 'reference', '--small', '--steps', '1', '--warmup', '0'];"
+            "runpy.run_path(%r, run_name='__main__');"
+            "maps = open('/proc/self/maps').read(); assert 'liboracle.so' in maps; assert 'libpop.so' not in maps" % os.path.join(ROOT, "bench.py"))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]

@@ -124,8 +124,8 @@ typedef struct pop_config {
   int32_t n_agents_total;         /* swarm size over all ranks */
   int32_t agent_id_base;          /* global id of local agent 0 */
   double  drone_size[3];          /* swarm/drone_size_{x,y,z} */
-  float   replan_risk_rate;       /* swarm/replan_risk_rate (only 0 supported) */
-  int32_t num_resample;           /* swarm/num_resample */
+  float   replan_risk_rate;       /* swarm/replan_risk_rate; > 0 resamples peer particles (pop_set_resample_noise), F32 cells */
+  int32_t num_resample;           /* swarm/num_resample, 1..16 */
   /* --- hybrid A* (search/...) --- */
   double  max_tau, max_vel, max_acc, w_time, horizon, lambda_heu;
   double  resolution_astar, time_resolution_astar;
@@ -180,6 +180,13 @@ int pop_set_body_particles(pop_handle* h, const double* offs, const int32_t* cou
  * recs = n_agents_total records indexed by global drone id. */
 int pop_set_trajectories(pop_handle* h, const pop_traj_record* recs);
 
+/* Peer-uncertainty resampling (swarm/replan_risk_rate > 0; ParticleATC::getParticlesWithRisk, particles.cpp:365-408):
+ * every projected peer particle becomes num_resample Gaussian copies with stddev replan_risk_rate * (t - t_start),
+ * weighted by their density and normalised per particle.  The reference draws the offsets from a generator it seeds
+ * with time(NULL) inside each call; here they are an input: z = n_triples x 3 standard-normal values (nx, ny, nz before
+ * scaling by the stddev), consumed from the start for every (peer, slice), particle j taking triples j * num_resample ...
+ * (wrapping).  pop_create installs the sequence libstdc++ yields for the clock value 1.  Needs POP_CELL_F32. */
+int pop_set_resample_noise(pop_handle* h, const float* z, int n_triples);
 /* The table pop_set_trajectories / the allgather filled, read back (n_agents_total records). */
 int pop_get_trajectories(pop_handle* h, pop_traj_record* recs);
 

@@ -3,6 +3,7 @@
 #include <cstdio>
 
 #include <cstring>
+#include <random>
 
 #include "oracle.hpp"
 
@@ -13,11 +14,15 @@ struct OrcMap {
   Grid grid;
 };
 
+static std::vector<float> g_resample_noise;   // orc_set_resample_noise
+
 static Swarm make_swarm(const pop_config& c, const double* offs, const int32_t* counts,
                         const pop_traj_record* recs) {
   Swarm s;
   s.n_agents = c.n_agents_total;
   s.replan_risk_rate = c.replan_risk_rate;
+  s.num_resample = c.num_resample;
+  s.noise = g_resample_noise;
   s.body.resize(s.n_agents);
   for (int i = 0; i < s.n_agents; i++)
     for (int k = 0; k < counts[i]; k++) {
@@ -106,6 +111,16 @@ void orc_particles_with_risk(const pop_config* cfg, int ego_id, const double* of
       out_risks[static_cast<size_t>(q) * cap + i] = risks[i];
     }
   }
+}
+// the standard-normal triples the peer resampling consumes (replan_risk_rate > 0), for every swarm built afterwards
+void orc_set_resample_noise(const float* z, int n_triples) { g_resample_noise.assign(z, z + 3 * static_cast<size_t>(n_triples)); }
+// What libstdc++ hands ParticleATC::getParticlesWithRisk (particles.cpp:382-392): std::default_random_engine(seed) feeding
+// three std::normal_distribution<float> objects in turn (each keeps its own spare value).  Generated with unit
+// deviation: the distribution returns ret * stddev + mean, so these are the `ret`s.
+void orc_libstdcxx_normal_triples(unsigned long seed, int n_triples, float* out) {
+  std::default_random_engine gen(seed);
+  std::normal_distribution<float> nx(0.0, 1.0f), ny(0.0, 1.0f), nz(0.0, 1.0f);
+  for (int i = 0; i < n_triples; i++) { out[3 * i] = nx(gen); out[3 * i + 1] = ny(gen); out[3 * i + 2] = nz(gen); }
 }
 void orc_map_add_particles(void* h, const double* pts, const float* risks, int n, int t) {
   add_particles(static_cast<OrcMap*>(h)->grid, reinterpret_cast<const V3d*>(pts), risks, n, t);

@@ -31,7 +31,7 @@ static Bezier record_traj(const pop_traj_record& r, double& t_end) {
   return Bezier(dur, c);
 }
 
-// getWaypoints (:316-344) + getParticlesWithRisk (:346-422), replan_risk_rate == 0 branch
+// getWaypoints (:316-344) + getParticlesWithRisk (:346-422)
 bool particles_with_risk(const Swarm& s, int ego_id, int idx_agent, double t0,
                          std::vector<V3d>& pts, std::vector<float>& risks) {
   const pop_traj_record& r = s.trajs[idx_agent];
@@ -59,9 +59,30 @@ bool particles_with_risk(const Swarm& s, int ego_id, int idx_agent, double t0,
   if (pos_stddev < 1e-3) {
     for (const V3d& e : way) { pts.push_back(e); risks.push_back(1.0f); }
   } else {
-    // Gaussian resampling seeded with time(NULL) in the reference (:382): not reproducible,
-    // not restated. Callers must keep replan_risk_rate == 0.
-    return false;
+    // Gaussian resampling (:376-408).  The reference draws nx, ny, nz from three std::normal_distribution<float>(0, stddev)
+    // objects over ONE std::default_random_engine seeded with time(NULL) *inside this call*: every call made within the
+    // same second replays the same sequence from its start.  Made an input here: `noise` holds the standard-normal
+    // triples in consumption order (libstdc++'s distribution returns ret * stddev + mean, so z * stddev + 0.0f is the very
+    // value it would have returned), read from the start in every call.
+    const int R = s.num_resample;
+    const size_t n_tr = s.noise.size() / 3;
+    if (n_tr == 0) return false;
+    size_t q = 0;
+    for (const V3d& e : way) {
+      std::vector<float> buf;
+      buf.reserve(R);
+      for (int i = 0; i < R; i++) {
+        const float* z = &s.noise[3 * (q % n_tr)];
+        q++;
+        const float nx = z[0] * pos_stddev + 0.0f, ny = z[1] * pos_stddev + 0.0f, nz = z[2] * pos_stddev + 0.0f;
+        pts.push_back(V3d{e.x + static_cast<double>(nx), e.y + static_cast<double>(ny), e.z + static_cast<double>(nz)});
+        buf.push_back(std::exp(-0.5f * (nx * nx + ny * ny + nz * nz) / (pos_stddev * pos_stddev)));
+      }
+      float sum = 0.0f;
+      for (float r : buf) sum += r;                 // std::accumulate(..., 0.0f)
+      for (float& r : buf) r = r * R / sum;         // r * num_resample_ / sum, left to right in float
+      risks.insert(risks.end(), buf.begin(), buf.end());
+    }
   }
   return true;
 }

@@ -110,6 +110,8 @@ struct Swarm {
   std::vector<std::vector<V3d>> body;  // particles_buffer_ per global id
   std::vector<pop_traj_record> trajs;  // swarm_trajs_ by id (n_pieces==0 → absent)
   float replan_risk_rate = 0.f;
+  int num_resample = 10;
+  std::vector<float> noise;            // standard-normal triples (nx, ny, nz) the Gaussian resampling consumes, see o_peers.cpp
 };
 std::vector<V3d> ego_particles(const double size[3]);  // initEgoParticles :62-75
 // getParticlesWithRisk (:346-422) for rate==0; returns validity

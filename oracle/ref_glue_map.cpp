@@ -16,6 +16,13 @@
 #include <pthread.h>
 #include <sstream>
 
+// ParticleATC::getParticlesWithRisk seeds its resampling engine with time(NULL) (particles.cpp:382): the library answers
+// that call itself (linked -Bsymbolic-functions), so the seed is an input of the test
+#include <ctime>
+static time_t g_fake_time = 1;
+extern "C" time_t time(time_t* t) noexcept { if (t) *t = g_fake_time; return g_fake_time; }
+extern "C" void refmap_set_time_seed(long s) { g_fake_time = static_cast<time_t>(s); }
+
 #define private public
 #define protected public
 #if REF_MAP_KIND == 0

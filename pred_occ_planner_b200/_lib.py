@@ -173,6 +173,7 @@ SYMBOLS = [
     ("pop_set_world_cloud_dev", _I, [_VP, _VP, _I]),
     ("pop_set_cylinders_dev", _I, [_VP, _VP, _I, _D]),
     ("pop_get_trajectories", _I, [_VP, C.POINTER(PopTrajRecord)]),
+    ("pop_set_resample_noise", _I, [_VP, _PF, _I]),
     ("pop_comm_unique_id", _I, [_VP]),
     ("pop_comm_init", _I, [_VP, _VP, _I, _I]),
     ("pop_comm_info", _I, [_VP, C.POINTER(_I), C.POINTER(_I), C.POINTER(_I)]),

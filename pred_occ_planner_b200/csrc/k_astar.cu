@@ -619,14 +619,21 @@ int popk_astar_alloc(pop_handle* h) {
   ok &= cudaMalloc(&d->d_path, static_cast<size_t>(d->n_agents) * POP_MAX_PATH * 6 * sizeof(double)) == cudaSuccess;
   ok &= cudaMalloc(&d->d_len, d->n_agents * sizeof(int)) == cudaSuccess;
   ok &= cudaMalloc(&d->d_stats, d->n_agents * 4 * sizeof(int)) == cudaSuccess;
+  // the handle keeps the workspace only if every allocation and attribute call succeeded: a failed attempt frees
+  // what it got and leaves h->astar null, so the next call tries again instead of launching on null pointers
   h->astar = d;
-  if (!ok) { cudaGetLastError(); return pop_fail(h, POP_E_CUDA, "A* pool allocation failed"); }
-  POP_CUDA(h, cudaMemsetAsync(d->hkey, 0, nh * sizeof(unsigned long long), h->stream));
-  POP_CUDA(h, cudaMemsetAsync(d->gen, 0, d->n_agents * sizeof(unsigned), h->stream));
-  POP_CUDA(h, cudaMemsetAsync(d->d_path, 0, static_cast<size_t>(d->n_agents) * POP_MAX_PATH * 6 * sizeof(double), h->stream));
-  const size_t smem = static_cast<size_t>(d->cap) * 12 + 16;
-  POP_CUDA(h, cudaFuncSetAttribute(k_astar<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-  POP_CUDA(h, cudaFuncSetAttribute(k_astar<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  auto finish = [&]() -> int {
+    if (!ok) { cudaGetLastError(); return pop_fail(h, POP_E_CUDA, "A* pool allocation failed"); }
+    POP_CUDA(h, cudaMemsetAsync(d->hkey, 0, nh * sizeof(unsigned long long), h->stream));
+    POP_CUDA(h, cudaMemsetAsync(d->gen, 0, d->n_agents * sizeof(unsigned), h->stream));
+    POP_CUDA(h, cudaMemsetAsync(d->d_path, 0, static_cast<size_t>(d->n_agents) * POP_MAX_PATH * 6 * sizeof(double), h->stream));
+    const size_t smem = static_cast<size_t>(d->cap) * 12 + 16;
+    POP_CUDA(h, cudaFuncSetAttribute(k_astar<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    POP_CUDA(h, cudaFuncSetAttribute(k_astar<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    return POP_OK;
+  };
+  const int rc = finish();
+  if (rc != POP_OK) { popk_astar_free(h); return rc; }
   return POP_OK;
 }
 

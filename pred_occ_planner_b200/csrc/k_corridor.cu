@@ -783,12 +783,17 @@ int popk_corridor_alloc(pop_handle* h) {
   ok &= cudaMalloc(&d->goal, d->n_agents * 6 * sizeof(double)) == cudaSuccess;
   ok &= cudaMalloc(&d->tst, d->n_agents * sizeof(double)) == cudaSuccess;
   ok &= cudaMalloc(&d->err, sizeof(int)) == cudaSuccess;
-  if (!ok) { cudaGetLastError(); return pop_fail(h, POP_E_CUDA, "corridor workspace allocation failed"); }
-  POP_CUDA(h, cudaMemsetAsync(d->err, 0, sizeof(int), h->stream));
-  POP_CUDA(h, cudaMemsetAsync(d->seg_h, 0, ns * POP_MAX_FACES * 4 * sizeof(double), h->stream));
-  POP_CUDA(h, cudaMemsetAsync(d->goal, 0, d->n_agents * 6 * sizeof(double), h->stream));
   static_assert(4 * kLpRows <= kScrDoubles, "finish kernel borrows one segment scratch for A|b");
-  return POP_OK;
+  auto finish = [&]() -> int {   // as popk_astar_alloc: a failed attempt leaves h->corridor null
+    if (!ok) { cudaGetLastError(); return pop_fail(h, POP_E_CUDA, "corridor workspace allocation failed"); }
+    POP_CUDA(h, cudaMemsetAsync(d->err, 0, sizeof(int), h->stream));
+    POP_CUDA(h, cudaMemsetAsync(d->seg_h, 0, ns * POP_MAX_FACES * 4 * sizeof(double), h->stream));
+    POP_CUDA(h, cudaMemsetAsync(d->goal, 0, d->n_agents * 6 * sizeof(double), h->stream));
+    return POP_OK;
+  };
+  const int rc = finish();
+  if (rc != POP_OK) popk_corridor_free(h);
+  return rc;
 }
 
 void popk_corridor_free(pop_handle* h) {

@@ -149,10 +149,20 @@ static int plan_alloc(pop_handle* h) {
   ok &= cudaMalloc(&d->sep_np, sizeof(int) * nl) == cudaSuccess;
   ok &= cudaMalloc(&d->sep_st, sizeof(int) * nl) == cudaSuccess;
   ok &= cudaMalloc(&d->sep_cpts, sizeof(double) * POP_MAX_PIECES * 15 * nl) == cudaSuccess;
-  if (!ok) { cudaGetLastError(); return pop_fail(h, POP_E_CUDA, "cycle workspace allocation failed"); }
-  POP_CUDA(h, cudaMemsetAsync(d->traj_ids, 0, sizeof(int) * nl, h->stream));
-  POP_CUDA(h, cudaMemsetAsync(d->status, 0, sizeof(int) * nl, h->stream));
-  return POP_OK;
+  auto finish = [&]() -> int {
+    if (!ok) { cudaGetLastError(); return pop_fail(h, POP_E_CUDA, "cycle workspace allocation failed"); }
+    POP_CUDA(h, cudaMemsetAsync(d->traj_ids, 0, sizeof(int) * nl, h->stream));
+    POP_CUDA(h, cudaMemsetAsync(d->status, 0, sizeof(int) * nl, h->stream));
+    return POP_OK;
+  };
+  const int rc = finish();
+  if (rc != POP_OK) {   // leave no half-built workspace behind: the next call allocates again
+    void* ptrs[] = {d->sep_wd, d->sep_wi, d->safe, d->status, d->traj_ids, d->sep_np, d->sep_st, d->sep_cpts};
+    for (void* q : ptrs) if (q) cudaFree(q);
+    delete d;
+    h->plan = nullptr;
+  }
+  return rc;
 }
 
 void pop_plan_free(pop_handle* h) {

@@ -132,10 +132,10 @@ __global__ void __launch_bounds__(128) k_future_slices(PopGeom g, uint8_t* __res
 // local agents; (b) scatter body particles into each ego grid (addParticlesToRiskMap,
 // fake_particle_risk_voxel.cpp:178-218,291-301).
 // =============================================================================================
-__global__ void k_peer_positions(int n_total, int nt, float dt, double t_map,
+__global__ void k_peer_positions(int n_total, int nt, float dt, double t_map, float risk_rate,
                                  const pop_traj_record* __restrict__ trajs,
                                  const int* __restrict__ body_count, double* __restrict__ pos,
-                                 int8_t* __restrict__ valid) {
+                                 int8_t* __restrict__ valid, float* __restrict__ sigma) {
   const int tid = blockIdx.x * blockDim.x + threadIdx.x;
   if (tid >= n_total * nt) return;
   const int i = tid / nt, k = tid % nt;
@@ -152,6 +152,8 @@ __global__ void k_peer_positions(int n_total, int nt, float dt, double t_map,
       double p3[3];
       pop_bezier_eval(r.duration, r.n_pieces, r.cpts, __dsub_rn(tk, r.start_time), 0, p3);
       pos[3 * tid] = p3[0]; pos[3 * tid + 1] = p3[1]; pos[3 * tid + 2] = p3[2];
+      // pos_stddev = replan_risk_rate_ * static_cast<float>(t0 - ptr->time_start) (particles.cpp:372)
+      sigma[tid] = __fmul_rn(risk_rate, static_cast<float>(__dsub_rn(tk, r.start_time)));
     }
   }
   valid[tid] = ok;
@@ -165,7 +167,9 @@ __global__ void __launch_bounds__(256) k_peer_scatter(PopGeom g, uint8_t* __rest
                                                       const int8_t* __restrict__ peer_valid,
                                                       const double* __restrict__ body,
                                                       const int* __restrict__ body_count,
-                                                      const int* __restrict__ agent_ok) {
+                                                      const int* __restrict__ agent_ok,
+                                                      const float* __restrict__ peer_sigma, int n_resample,
+                                                      const float* __restrict__ noise, int n_noise) {
   // thread per (ego a, peer i, slice k, body particle j); j fastest
   const long long tid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const long long per_agent = static_cast<long long>(n_total) * g.nt * POP_MAX_BODY;
@@ -181,14 +185,50 @@ __global__ void __launch_bounds__(256) k_peer_scatter(PopGeom g, uint8_t* __rest
   if (!peer_valid[i * g.nt + k]) return;
   const double* p = peer_pos + 3 * (static_cast<size_t>(i) * g.nt + k);
   const double* e = body + 3 * (static_cast<size_t>(i) * POP_MAX_BODY + j);
-  // (pt + e) - (double)pose, then float cast
-  const float x = static_cast<float>(__dsub_rn(__dadd_rn(p[0], e[0]), static_cast<double>(poses[3 * a])));
-  const float y = static_cast<float>(__dsub_rn(__dadd_rn(p[1], e[1]), static_cast<double>(poses[3 * a + 1])));
-  const float z = static_cast<float>(__dsub_rn(__dadd_rn(p[2], e[2]), static_cast<double>(poses[3 * a + 2])));
-  if (!geom_in_range_f(g, x, y, z)) return;
-  const int idx = geom_voxel_index(g, x, y, z);
-  if (idx < 0 || idx >= g.V) return;
-  Cell<C>::add(grid + a * g.agent_stride, static_cast<size_t>(k) * g.V + idx, 1.0f);
+  const double pose3[3] = {static_cast<double>(poses[3 * a]), static_cast<double>(poses[3 * a + 1]), static_cast<double>(poses[3 * a + 2])};
+  const float sg = peer_sigma[i * g.nt + k];
+  if (static_cast<double>(sg) < 1e-3 || n_noise <= 0) {   // `if (pos_stddev < 1e-3)`: the particle itself, risk 1 (particles.cpp:378-384)
+    // (pt + e) - (double)pose, then float cast
+    const float x = static_cast<float>(__dsub_rn(__dadd_rn(p[0], e[0]), pose3[0]));
+    const float y = static_cast<float>(__dsub_rn(__dadd_rn(p[1], e[1]), pose3[1]));
+    const float z = static_cast<float>(__dsub_rn(__dadd_rn(p[2], e[2]), pose3[2]));
+    if (!geom_in_range_f(g, x, y, z)) return;
+    const int idx = geom_voxel_index(g, x, y, z);
+    if (idx < 0 || idx >= g.V) return;
+    Cell<C>::add(grid + a * g.agent_stride, static_cast<size_t>(k) * g.V + idx, 1.0f);
+    return;
+  }
+  // Gaussian resampling (particles.cpp:385-408): n_resample copies displaced by (nx, ny, nz) = noise triple * stddev,
+  // weighted exp(-|n|^2 / (2 stddev^2)), the weights of one particle normalised to sum n_resample.  The reference
+  // re-seeds its engine in every call, so every (peer, slice) replays the noise sequence from its start: particle j
+  // takes triples j * n_resample ... (wrapping around the table).  exp is evaluated in double and rounded once, which
+  // is what a correctly rounded expf (glibc's) returns.
+  float risk[16];
+  int cell[16];
+  float sum = 0.0f;
+  const float s2 = __fmul_rn(sg, sg);
+  for (int r = 0; r < n_resample; r++) {
+    const float* zt = noise + 3 * ((static_cast<long long>(j) * n_resample + r) % n_noise);
+    const float nx = __fadd_rn(__fmul_rn(zt[0], sg), 0.0f), ny = __fadd_rn(__fmul_rn(zt[1], sg), 0.0f),
+                nz = __fadd_rn(__fmul_rn(zt[2], sg), 0.0f);
+    const float q = __fadd_rn(__fadd_rn(__fmul_rn(nx, nx), __fmul_rn(ny, ny)), __fmul_rn(nz, nz));
+    const float arg = __fdiv_rn(__fmul_rn(-0.5f, q), s2);
+    risk[r] = static_cast<float>(exp(static_cast<double>(arg)));
+    sum = __fadd_rn(sum, risk[r]);
+    const float x = static_cast<float>(__dsub_rn(__dadd_rn(__dadd_rn(p[0], e[0]), static_cast<double>(nx)), pose3[0]));
+    const float y = static_cast<float>(__dsub_rn(__dadd_rn(__dadd_rn(p[1], e[1]), static_cast<double>(ny)), pose3[1]));
+    const float z = static_cast<float>(__dsub_rn(__dadd_rn(__dadd_rn(p[2], e[2]), static_cast<double>(nz)), pose3[2]));
+    int idx = -1;
+    if (geom_in_range_f(g, x, y, z)) {
+      idx = geom_voxel_index(g, x, y, z);
+      if (idx < 0 || idx >= g.V) idx = -1;
+    }
+    cell[r] = idx;
+  }
+  const float rn = static_cast<float>(n_resample);
+  for (int r = 0; r < n_resample; r++)
+    if (cell[r] >= 0)
+      Cell<C>::add(grid + a * g.agent_stride, static_cast<size_t>(k) * g.V + cell[r], __fdiv_rn(__fmul_rn(risk[r], rn), sum));
 }
 
 // addParticlesToRiskMap for caller-provided particles (map-frame doubles)
@@ -729,18 +769,21 @@ int popk_peer_project(pop_handle* h) {
   const int nl = h->cfg.n_agents_local, ntot = h->cfg.n_agents_total;
   pop_prof_begin(h, POP_STAGE_PEERS);
   k_peer_positions<<<(ntot * g.nt + 127) / 128, 128, 0, h->stream>>>(
-      ntot, g.nt, g.dt, h->t_map, h->d_traj_all, h->d_body_count, h->d_peer_pos, h->d_peer_valid);
+      ntot, g.nt, g.dt, h->t_map, h->cfg.replan_risk_rate, h->d_traj_all, h->d_body_count, h->d_peer_pos, h->d_peer_valid,
+      h->d_peer_sigma);
   POP_LAUNCH_CHECK(h);
   const long long n = static_cast<long long>(nl) * ntot * g.nt * POP_MAX_BODY;
   const unsigned blocks = static_cast<unsigned>((n + 255) / 256);
   if (h->cfg.cell_dtype == POP_CELL_U8)
     k_peer_scatter<uint8_t><<<blocks, 256, 0, h->stream>>>(g, h->d_grid, h->d_poses, nl, ntot,
                                                           h->cfg.agent_id_base, h->d_peer_pos,
-                                                          h->d_peer_valid, h->d_body, h->d_body_count, h->d_agent_ok);
+                                                          h->d_peer_valid, h->d_body, h->d_body_count, h->d_agent_ok,
+                                                          h->d_peer_sigma, h->cfg.num_resample, h->d_noise, h->n_noise);
   else
     k_peer_scatter<float><<<blocks, 256, 0, h->stream>>>(g, h->d_grid, h->d_poses, nl, ntot,
                                                         h->cfg.agent_id_base, h->d_peer_pos,
-                                                        h->d_peer_valid, h->d_body, h->d_body_count, h->d_agent_ok);
+                                                        h->d_peer_valid, h->d_body, h->d_body_count, h->d_agent_ok,
+                                                          h->d_peer_sigma, h->cfg.num_resample, h->d_noise, h->n_noise);
   POP_LAUNCH_CHECK(h);
   pop_prof_end(h, POP_STAGE_PEERS, 2);
   return POP_OK;

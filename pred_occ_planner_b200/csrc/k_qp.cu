@@ -1247,14 +1247,20 @@ int popk_qp_alloc(pop_handle* h, int n_agents) {
   ok &= cudaMalloc(&d->status, na * sizeof(int)) == cudaSuccess;
   ok &= cudaMalloc(&d->iters, na * sizeof(int)) == cudaSuccess;
   ok &= cudaMalloc(&d->prof, na * 8 * sizeof(long long)) == cudaSuccess;
-  if (!ok) { cudaGetLastError(); return pop_fail(h, POP_E_CUDA, "QP workspace allocation failed"); }
-  double QM[225];
-  host_jerk_block(QM);
-  POP_CUDA(h, cudaMemcpyAsync(d->QM, QM, sizeof(QM), cudaMemcpyHostToDevice, h->stream));
-  POP_CUDA(h, cudaMemsetAsync(d->cpts, 0, na * POP_MAX_PIECES * 15 * sizeof(double), h->stream));
-  POP_CUDA(h, cudaStreamSynchronize(h->stream));
-  POP_CUDA(h, cudaFuncSetAttribute(k_qp_admm<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTiles));
-  POP_CUDA(h, cudaFuncSetAttribute(k_qp_admm<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+  // as popk_astar_alloc: a failed attempt frees what it got and leaves h->qp null
+  auto finish = [&]() -> int {
+    if (!ok) { cudaGetLastError(); return pop_fail(h, POP_E_CUDA, "QP workspace allocation failed"); }
+    double QM[225];
+    host_jerk_block(QM);
+    POP_CUDA(h, cudaMemcpyAsync(d->QM, QM, sizeof(QM), cudaMemcpyHostToDevice, h->stream));
+    POP_CUDA(h, cudaMemsetAsync(d->cpts, 0, na * POP_MAX_PIECES * 15 * sizeof(double), h->stream));
+    POP_CUDA(h, cudaStreamSynchronize(h->stream));
+    POP_CUDA(h, cudaFuncSetAttribute(k_qp_admm<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTiles));
+    POP_CUDA(h, cudaFuncSetAttribute(k_qp_admm<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    return POP_OK;
+  };
+  const int rc = finish();
+  if (rc != POP_OK) { popk_qp_free(h); return rc; }
   return POP_OK;
 }
 

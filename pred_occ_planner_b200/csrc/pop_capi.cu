@@ -5,6 +5,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <random>
+#include <vector>
 
 #include "pop_geom.cuh"
 #include "pop_internal.h"
@@ -154,7 +156,9 @@ int pop_create(const pop_config* cfg, int device, void* stream, pop_handle** out
       cfg->time_resolution <= 0.f || cfg->max_cloud_points <= 0 || cfg->max_cylinders <= 0)
     return POP_E_INVALID;
   if (cfg->cell_dtype != POP_CELL_U8 && cfg->cell_dtype != POP_CELL_F32) return POP_E_INVALID;
-  if (cfg->replan_risk_rate != 0.f) return POP_E_UNSUPPORTED;
+  if (cfg->replan_risk_rate < 0.f || cfg->num_resample < 1 || cfg->num_resample > 16) return POP_E_INVALID;
+  // resampled peer particles carry fractional risks (particles.cpp:395-402): they need float cells
+  if (cfg->replan_risk_rate != 0.f && cfg->cell_dtype != POP_CELL_F32) return POP_E_UNSUPPORTED;
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) {
     cudaGetLastError();
@@ -191,13 +195,26 @@ int pop_create(const pop_config* cfg, int device, void* stream, pop_handle** out
   ok &= cudaMalloc(&h->d_traj_send, sizeof(pop_traj_record) * nl) == cudaSuccess;
   ok &= cudaMalloc(&h->d_peer_pos, sizeof(double) * 3 * nt * cfg->nt) == cudaSuccess;
   ok &= cudaMalloc(&h->d_peer_valid, static_cast<size_t>(nt) * cfg->nt) == cudaSuccess;
+  ok &= cudaMalloc(&h->d_peer_sigma, sizeof(float) * nt * cfg->nt) == cudaSuccess;
   if (!ok) { cudaGetLastError(); return fail(POP_E_CUDA); }
   cudaMemsetAsync(h->d_grid, 0, h->geom.agent_stride * nl + 256, h->stream);
   cudaMemsetAsync(h->d_poses, 0, sizeof(float) * 3 * nl, h->stream);
   cudaMemsetAsync(h->d_traj_all, 0, sizeof(pop_traj_record) * nt, h->stream);
   cudaMemsetAsync(h->d_traj_send, 0, sizeof(pop_traj_record) * nl, h->stream);
   cudaMemsetAsync(h->d_body_count, 0, sizeof(int) * nt, h->stream);
+  cudaMemsetAsync(h->d_peer_sigma, 0, sizeof(float) * nt * cfg->nt, h->stream);
   if (cudaStreamSynchronize(h->stream) != cudaSuccess) return fail(POP_E_CUDA);
+  if (cfg->replan_risk_rate != 0.f) {
+    // The reference seeds a std::default_random_engine with time(NULL) inside every getParticlesWithRisk call and draws
+    // nx, ny, nz from three std::normal_distribution<float> objects over it (particles.cpp:382-392).  Default table: that
+    // very sequence for the clock value 1, one triple per (body particle, copy); pop_set_resample_noise replaces it.
+    const int n_tr = POP_MAX_BODY * cfg->num_resample;
+    std::vector<float> z(3 * static_cast<size_t>(n_tr));
+    std::default_random_engine gen(1);
+    std::normal_distribution<float> nx(0.0, 1.0f), ny(0.0, 1.0f), nz(0.0, 1.0f);
+    for (int i = 0; i < n_tr; i++) { z[3 * i] = nx(gen); z[3 * i + 1] = ny(gen); z[3 * i + 2] = nz(gen); }
+    if (pop_set_resample_noise(h, z.data(), n_tr) != POP_OK) return fail(POP_E_CUDA);
+  }
   *out = h;
   return POP_OK;
 }
@@ -216,7 +233,7 @@ int pop_destroy(pop_handle* h) {
   if (h->fork_ev) cudaEventDestroy(h->fork_ev);
   h->side.clear(); h->side_done.clear(); h->fork_ev = nullptr;
   void* ptrs[] = {h->d_grid, h->d_cloud, h->d_cyl, h->d_poses, h->d_occ_list, h->d_occ_count, h->d_body,
-                  h->d_body_count, h->d_traj_all, h->d_traj_send, h->d_peer_pos, h->d_peer_valid,
+                  h->d_body_count, h->d_traj_all, h->d_traj_send, h->d_peer_pos, h->d_peer_valid, h->d_peer_sigma, h->d_noise,
                   h->d_scratch};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (h->h_pinned) cudaFreeHost(h->h_pinned);
@@ -320,6 +337,18 @@ int pop_set_trajectories(pop_handle* h, const pop_traj_record* recs) {
   POP_CUDA(h, cudaMemcpyAsync(h->d_traj_all, recs, sizeof(pop_traj_record) * h->cfg.n_agents_total, cudaMemcpyHostToDevice, h->stream));
   POP_CUDA(h, cudaStreamSynchronize(h->stream));
   h->have_traj = true;
+  return POP_OK;
+}
+
+int pop_set_resample_noise(pop_handle* h, const float* z, int n_triples) {
+  if (!h || !z || n_triples < 1) return POP_E_INVALID;
+  PopDeviceGuard guard(h);
+  POP_CUDA(h, cudaStreamSynchronize(h->stream));
+  if (h->d_noise) { cudaFree(h->d_noise); h->d_noise = nullptr; h->n_noise = 0; }
+  POP_CUDA(h, cudaMalloc(&h->d_noise, sizeof(float) * 3 * n_triples));
+  POP_CUDA(h, cudaMemcpyAsync(h->d_noise, z, sizeof(float) * 3 * n_triples, cudaMemcpyHostToDevice, h->stream));
+  POP_CUDA(h, cudaStreamSynchronize(h->stream));
+  h->n_noise = n_triples;
   return POP_OK;
 }
 

@@ -75,6 +75,9 @@ struct pop_handle {
   pop_traj_record* d_traj_send = nullptr;  // n_local (allgather send buffer)
   double* d_peer_pos = nullptr;   // n_total x nt x 3 world positions of peers per slice
   int8_t* d_peer_valid = nullptr; // n_total x nt
+  float* d_peer_sigma = nullptr;  // n_total x nt: pos_stddev of the peer resampling (replan_risk_rate > 0)
+  float* d_noise = nullptr;       // n_noise standard-normal triples consumed by the resampling
+  int n_noise = 0;
   bool have_body = false, have_traj = false;
   const int* d_agent_ok = nullptr; // optional per-agent mask of the peer projection (set around a particle-map update)
 

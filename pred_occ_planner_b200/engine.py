@@ -74,6 +74,11 @@ class PopEngine:
         """obstacle states already in device memory (n pop_cylinder records at device address ptr); async"""
         self._check(self.lib.pop_set_cylinders_dev(self._h, C.c_void_p(ptr), int(n), float(max_abs_vy)))
 
+    def set_resample_noise(self, z: np.ndarray):
+        """standard-normal triples of the peer resampling (replan_risk_rate > 0), see pop_set_resample_noise"""
+        z = np.ascontiguousarray(z, np.float32).reshape(-1, 3)
+        self._check(self.lib.pop_set_resample_noise(self._h, as_ptr(z, C.c_float), len(z)))
+
     def get_trajectories(self) -> np.ndarray:
         """the peers' table as the next map update will read it (n_total records)"""
         recs = np.zeros(self.n_total, TRAJ_DTYPE)

@@ -43,6 +43,19 @@ def default_config():
     return cfg
 
 
+def set_resample_noise(z):
+    """standard-normal triples consumed by the oracle's peer resampling (replan_risk_rate > 0)"""
+    z = np.ascontiguousarray(z, np.float32).reshape(-1, 3)
+    load().lib.orc_set_resample_noise(z.ctypes.data_as(C.POINTER(C.c_float)), len(z))
+
+
+def libstdcxx_normal_triples(seed, n):
+    """the (nx, ny, nz) / stddev sequence libstdc++ produces for the reference's three distributions over one engine"""
+    out = np.zeros((n, 3), np.float32)
+    load().lib.orc_libstdcxx_normal_triples(C.c_ulong(int(seed)), int(n), out.ctypes.data_as(C.POINTER(C.c_float)))
+    return out
+
+
 def _p(a, t):
     return a.ctypes.data_as(C.POINTER(t))
 

@@ -315,3 +315,17 @@ def collect(m, case):
         out["inf_t"] = m.inflate_query(case["q_pos"], case["q_t"])
         out["inf_dt"] = m.inflate_query(case["q_pos"], case["q_dt_in"])
     return out
+
+
+def resample_case(seed):
+    """Two-agent swarm whose peer is in flight at the map time (replan_risk_rate > 0 scenes; the same inputs feed the
+    live reference comparison and the GPU test)."""
+    from pred_occ_planner_b200 import worldgen
+    rng = np.random.default_rng(seed)
+    ego = seed % 2
+    t_map = 50.0
+    ts = [t_map + rng.uniform(-1.5, -0.2), t_map + rng.uniform(-1.5, -0.2)]
+    recs = curved_trajs(rng, 2, ts, int(rng.integers(3, 7)), 0.4)
+    offs, counts = worldgen.body_table(2, BODY_SIZE, ego_id=ego)
+    pose = rng.uniform([-1, -1, 0.8], [1, 1, 1.3])
+    return dict(ego=ego, t_map=t_map, recs=recs, offs=offs, counts=counts, pose=pose)

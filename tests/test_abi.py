@@ -50,10 +50,16 @@ def test_invalid_config_rejected(pop):
         pop.PopEngine(cfg)
     assert e.value.code == -1
     cfg = pop.default_config()
-    cfg.replan_risk_rate = 0.1  # Gaussian resampling of peers is not reproducible → refused
+    cfg.replan_risk_rate = 0.1  # resampled peer particles carry fractional risks: u8 cells are refused
+    cfg.cell_dtype = pop.POP_CELL_U8
     with pytest.raises(pop.PopError) as e:
         pop.PopEngine(cfg)
     assert e.value.code == -6
+    cfg.cell_dtype = pop.POP_CELL_F32
+    cfg.num_resample = 17
+    with pytest.raises(pop.PopError) as e:
+        pop.PopEngine(cfg)
+    assert e.value.code == -1
 
 
 def test_product_does_not_import_oracle():

@@ -61,3 +61,44 @@ def test_map_path_equals_reference_outputs(name, cell):
         assert np.array_equal(am.getInflateOccupancy(case["q_pos"], case["q_t"]), gold[f"{name}.inf_t"])
         assert np.array_equal(am.getInflateOccupancy(case["q_pos"], case["q_dt_in"]), gold[f"{name}.inf_dt"])
     eng.close()
+
+
+def test_peer_resampling_equals_oracle_and_reference_noise():
+    """swarm/replan_risk_rate > 0: the Gaussian copies of a peer's body particles (particles.cpp:365-408) deposited by
+    k_peer_scatter, fed the noise sequence libstdc++ hands the reference for a given clock value.  The oracle this is
+    compared with is pinned bit for bit against the compiled reference (tests/test_ref_map_pins.py::
+    test_peer_resampling_live).  Support identical; weights to 1e-6 relative (the device rounds exp once from double,
+    glibc's expf is correctly rounded in all but rare cases; deposits into one cell are summed by atomics)."""
+    from tests import cases, oracle_lib
+    orc = oracle_lib.load()
+    cfg = cases.cfg_c1(p.POP_CELL_F32)
+    cfg.n_agents_local, cfg.n_agents_total, cfg.replan_risk_rate, cfg.num_resample = 1, 2, 0.1, 10
+    cells = exact = 0
+    try:
+        for seed in range(6):
+            z = oracle_lib.libstdcxx_normal_triples(1000 + 77 * seed, 64 * cfg.num_resample)
+            oracle_lib.set_resample_noise(z)
+            case = rml.resample_case(seed)
+            cfg.agent_id_base = case["ego"]
+            eng = p.PopEngine(cfg)
+            eng.set_resample_noise(z)
+            eng.set_body_particles(case["offs"], case["counts"])
+            eng.set_trajectories(case["recs"])
+            eng.set_world_cloud(np.zeros((0, 3), np.float32))
+            eng.set_cylinders(np.zeros(0, p.CYL_DTYPE))
+            eng.set_poses(case["pose"].astype(np.float32)[None])
+            eng.map_update_gt(case["t_map"])
+            got = eng.agent_map(0).risk_maps()
+            om = orc.map(cfg)
+            om.set_pose(case["pose"].astype(np.float32))
+            om.update_gt(np.zeros((0, 3), np.float32), np.zeros(0, p.CYL_DTYPE), case["t_map"])
+            om.add_other_agents(case["offs"], case["counts"], case["recs"], case["ego"])
+            want = om.risk_maps()
+            assert np.array_equal(got != 0, want != 0), seed
+            assert np.allclose(got, want, rtol=1e-6, atol=1e-7), (seed, float(np.abs(got - want).max()))
+            cells += np.count_nonzero(want)
+            exact += int(np.count_nonzero(got == want))
+            eng.close()
+    finally:
+        oracle_lib.set_resample_noise(np.zeros((0, 3), np.float32))
+    assert cells > 2000

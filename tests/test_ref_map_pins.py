@@ -217,3 +217,40 @@ def test_device_ownership_source_equals_reference_vectors(gold):
         ok = inr & (idx >= 0) & (idx < V)
         cells.update((idx[ok] * T + k).tolist())
     assert cells == set(nz.tolist())
+
+
+def test_peer_resampling_live(oracle):
+    """swarm/replan_risk_rate > 0 (particles.cpp:365-408): num_resample Gaussian copies per peer particle with
+    density weights normalised per particle.  The reference seeds its generator with time(NULL) in every call; the
+    reference library answers time() itself, and the oracle is fed the sequence libstdc++ produces for that value
+    (three distributions over one engine).  Deposited grid identical, cell for cell."""
+    import ctypes as C
+    from tests import oracle_lib
+    lib = rml.load("fake_c1")
+    if lib is None:
+        pytest.skip("reference map libraries not present")
+    cfg = cases.cfg_c1(p.POP_CELL_F32)
+    cfg.n_agents_total, cfg.replan_risk_rate, cfg.num_resample = 2, 0.1, 10
+    cells = 0
+    try:
+        for seed in range(6):
+            clock = 1000 + 77 * seed
+            lib.refmap_set_time_seed(C.c_long(clock))
+            oracle_lib.set_resample_noise(oracle_lib.libstdcxx_normal_triples(clock, 64 * cfg.num_resample))
+            case = rml.resample_case(seed)
+            rm = rml.RefMap(lib, cfg)
+            rm.set_pose(case["pose"])
+            rm.set_swarm(2, case["ego"], rml.BODY_SIZE, case["offs"], case["counts"], case["recs"], case["t_map"],
+                         replan_risk_rate=cfg.replan_risk_rate, num_resample=cfg.num_resample)
+            rm.set_cylinders(np.zeros(0, p.CYL_DTYPE))
+            rm.update(np.zeros((0, 3), np.float32), case["t_map"])
+            om = oracle.map(cfg)
+            om.set_pose(case["pose"].astype(np.float32))
+            om.update_gt(np.zeros((0, 3), np.float32), np.zeros(0, p.CYL_DTYPE), case["t_map"])
+            om.add_other_agents(case["offs"], case["counts"], case["recs"], case["ego"])
+            a, b = rm.risk_maps(), om.risk_maps()
+            assert np.array_equal(a, b), seed
+            cells += np.count_nonzero(a)
+    finally:
+        oracle_lib.set_resample_noise(np.zeros((0, 3), np.float32))
+    assert cells > 2000

@@ -448,6 +448,22 @@ int pop_traj_sample_batch(pop_handle* h, int all_agents, const double* t_abs, in
  * local agent's resident state (the `start` of the next pop_replan_cycle_resident) and map centre become its
  * commanded state at t_next; past the end of its trajectory it holds the end point, without one it stays. Async. */
 int pop_swarm_advance(pop_handle* h, double t_next);
+/* The FSM's bookkeeping after a cycle (FiniteStateMachineFake::FSMCallback, plan_manager/src/fake_plan_manager.cpp:85-234):
+ * per local agent, from the status of the last cycle — a success resets the failure counter and executes the new
+ * trajectory; a failed replan from a trajectory keeps flying the old one and counts; once the count exceeds
+ * fsm/replan_max_failures (:187-197), or when a fresh plan fails (:124-131), the agent publishes the reference's "empty"
+ * trajectory (publishEmptyTrajectory :389-408: one piece of hover_duration = 1.5 s whose five control points are its
+ * current position, traj_id + 1, start = t_now) into the send buffer — it hovers, pop_swarm_advance holds it there and
+ * its peers project a stationary body — and plans afresh next time; an executing agent within fsm/goal_tolerance of its
+ * goal is done (:149-152) and is left alone afterwards.  out_state / out_failures (n_local, may be NULL). */
+enum { POP_FSM_NEW_PLAN = 0, POP_FSM_EXEC_TRAJ = 1, POP_FSM_REPLAN = 2, POP_FSM_GOAL_REACHED = 3 };
+typedef struct pop_fsm_params {
+  int32_t replan_max_failures;   /* fsm/replan_max_failures, 3 */
+  int32_t _pad;
+  double  goal_tolerance;        /* fsm/goal_tolerance, 1.0 m */
+  double  hover_duration;        /* 1.5 s (fake_plan_manager.cpp:399) */
+} pop_fsm_params;
+int pop_fsm_update(pop_handle* h, double t_now, const pop_fsm_params* prm, int32_t* out_state, int32_t* out_failures);
 /* the resident agent states: out_start n_local x 9 */
 int pop_swarm_states(pop_handle* h, double* out_start);
 /* MultiAgentLogger::getMinObsDist / getMinUAVDist (eval_helper/include/eval_helper/multi_eval.hpp:240-275) for

@@ -60,6 +60,11 @@ assert CYL_DTYPE.itemsize == C.sizeof(PopCylinder)
 os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 
 
+class PopFsmParams(C.Structure):
+    _fields_ = [("replan_max_failures", C.c_int32), ("_pad", C.c_int32), ("goal_tolerance", C.c_double),
+                ("hover_duration", C.c_double)]
+
+
 class PopConfig(C.Structure):
     _fields_ = [
         ("abi_version", C.c_int32),
@@ -173,6 +178,7 @@ SYMBOLS = [
     ("pop_set_world_cloud_dev", _I, [_VP, _VP, _I]),
     ("pop_set_cylinders_dev", _I, [_VP, _VP, _I, _D]),
     ("pop_get_trajectories", _I, [_VP, C.POINTER(PopTrajRecord)]),
+    ("pop_fsm_update", _I, [_VP, _D, C.POINTER(PopFsmParams), _PI32, _PI32]),
     ("pop_set_resample_noise", _I, [_VP, _PF, _I]),
     ("pop_comm_unique_id", _I, [_VP]),
     ("pop_comm_init", _I, [_VP, _VP, _I, _I]),

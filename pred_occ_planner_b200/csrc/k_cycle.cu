@@ -58,6 +58,29 @@ __global__ void __launch_bounds__(128) k_separate(int a0, int w0, int n_local, i
     bool far = false;
     for (int q = 0; q < 3; q++) if (bmin[q] - amax[q] > 1e-2 || amin[q] - bmax[q] > 1e-2) far = true;
     if (far) continue;
+    // Certificate before the LP: along u = centroid(A) - centroid(B), n = 2 (1 + 1e-9) u / gap and d halfway between the
+    // two sets.  If this (n, d) satisfies every row of the LP below — checked row by row, in double, with the box —
+    // the LP is feasible and the pair is safe; the solver is only needed for pairs that nearly touch or interpenetrate.
+    {
+      double ca[3] = {0, 0, 0}, cb[3] = {0, 0, 0};
+      for (int k = 0; k < na; k++) for (int q = 0; q < 3; q++) ca[q] += A[k * 3 + q];
+      for (int k = 0; k < nb; k++) for (int q = 0; q < 3; q++) cb[q] += B[k * 3 + q];
+      double u[3];
+      for (int q = 0; q < 3; q++) u[q] = ca[q] / na - cb[q] / nb;
+      double lo_a = 1e300, hi_b = -1e300;
+      for (int k = 0; k < na; k++) lo_a = fmin(lo_a, u[0] * A[k * 3] + u[1] * A[k * 3 + 1] + u[2] * A[k * 3 + 2]);
+      for (int k = 0; k < nb; k++) hi_b = fmax(hi_b, u[0] * B[k * 3] + u[1] * B[k * 3 + 1] + u[2] * B[k * 3 + 2]);
+      const double gap = lo_a - hi_b;
+      if (gap > 0.0) {
+        const double sc = 2.0 * (1.0 + 1e-9) / gap;
+        const double nn[3] = {sc * u[0], sc * u[1], sc * u[2]};
+        const double dd = -0.5 * sc * (lo_a + hi_b);
+        bool ok = fabs(nn[0]) <= 9.99e3 && fabs(nn[1]) <= 9.99e3 && fabs(nn[2]) <= 9.99e3 && fabs(dd) <= 9.99e3;
+        for (int k = 0; ok && k < na; k++) ok = nn[0] * A[k * 3] + nn[1] * A[k * 3 + 1] + nn[2] * A[k * 3 + 2] + dd >= 1.0;
+        for (int k = 0; ok && k < nb; k++) ok = nn[0] * B[k * 3] + nn[1] * B[k * 3 + 1] + nn[2] * B[k * 3 + 2] + dd <= -1.0;
+        if (ok) continue;
+      }
+    }
     int rr = 0;
     for (int k = 0; k < na; k++) { for (int q = 0; q < 3; q++) rowsM[rr * 4 + q] = -A[k * 3 + q]; rowsM[rr * 4 + 3] = -1.0; rhs[rr] = -1.0; rr++; }
     for (int k = 0; k < nb; k++) { for (int q = 0; q < 3; q++) rowsM[rr * 4 + q] = B[k * 3 + q]; rowsM[rr * 4 + 3] = 1.0; rhs[rr] = -1.0; rr++; }
@@ -122,6 +145,52 @@ __global__ void k_finalize(int a0, int n, int id_base, double t_plan, double tau
   for (int k = 0; k < POP_MAX_PIECES * 15; k++) r.cpts[k] = k < 15 * M ? c[k] : 0.0;
 }
 
+// FiniteStateMachineFake::FSMCallback, the branches that follow a replan (plan_manager/src/fake_plan_manager.cpp):
+//   REPLAN (:157-197): success -> num_replan_failures_ = 0, EXEC_TRAJ; failure -> counter + 1, and once it exceeds
+//     fsm/replan_max_failures -> NEW_PLAN + publishEmptyTrajectory (the counter is only ever reset by a success);
+//   NEW_PLAN (:117-138): success -> EXEC_TRAJ; failure -> publishEmptyTrajectory;
+//   EXEC_TRAJ (:149-152): |odom - goal| < fsm/goal_tolerance -> GOAL_REACHED.
+// publishEmptyTrajectory (:389-408): traj_id + 1, start = now, one piece of 1.5 s whose five control points are the
+// current position — the drone hovers, and its peers project a stationary body.
+__global__ void k_fsm_update(int n, int id_base, double t_now, int max_failures, double goal_tol, double hover_dur,
+                             const int* __restrict__ status, const double* __restrict__ start,
+                             const double* __restrict__ goal, pop_traj_record* __restrict__ send,
+                             int* __restrict__ traj_ids, int* __restrict__ fsm_state, int* __restrict__ fsm_fail) {
+  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= n) return;
+  int st = fsm_state[a], fails = fsm_fail[a];
+  if (st == POP_FSM_GOAL_REACHED) return;
+  const bool ok = status[a] == POP_REPLAN_OK;
+  bool hover = false;
+  if (st == POP_FSM_NEW_PLAN) {
+    if (ok) st = POP_FSM_EXEC_TRAJ; else hover = true;
+  } else {   // EXEC_TRAJ / REPLAN: a replan from the current trajectory
+    if (ok) { fails = 0; st = POP_FSM_EXEC_TRAJ; }
+    else {
+      fails++;
+      st = POP_FSM_REPLAN;
+      if (fails > max_failures) { st = POP_FSM_NEW_PLAN; hover = true; }
+    }
+  }
+  const double* p = start + 9 * a;
+  if (hover) {
+    pop_traj_record& r = send[a];
+    r.drone_id = id_base + a;
+    r.traj_id = ++traj_ids[a];
+    r.n_pieces = 1;
+    r.valid = 1;
+    r.start_time = t_now;
+    for (int k = 0; k < POP_MAX_PIECES; k++) r.duration[k] = k == 0 ? static_cast<float>(hover_dur) : 0.f;
+    for (int k = 0; k < POP_MAX_PIECES * 15; k++) r.cpts[k] = k < 15 ? p[k % 3] : 0.0;
+  }
+  if (st == POP_FSM_EXEC_TRAJ) {
+    const double dx = p[0] - goal[3 * a], dy = p[1] - goal[3 * a + 1], dz = p[2] - goal[3 * a + 2];
+    if (sqrt(dx * dx + dy * dy + dz * dz) < goal_tol) st = POP_FSM_GOAL_REACHED;
+  }
+  fsm_state[a] = st;
+  fsm_fail[a] = fails;
+}
+
 }  // namespace
 
 struct PlanDev {
@@ -130,6 +199,8 @@ struct PlanDev {
   int* safe = nullptr;      // [n_local]
   int* status = nullptr;    // [n_local]
   int* traj_ids = nullptr;  // [n_local]
+  int* fsm_state = nullptr; // [n_local] POP_FSM_*
+  int* fsm_fail = nullptr;  // [n_local] num_replan_failures_
   int* sep_np = nullptr;    // staging for pop_separation_check_batch
   int* sep_st = nullptr;
   double* sep_cpts = nullptr;
@@ -146,18 +217,22 @@ static int plan_alloc(pop_handle* h) {
   ok &= cudaMalloc(&d->safe, sizeof(int) * nl) == cudaSuccess;
   ok &= cudaMalloc(&d->status, sizeof(int) * nl) == cudaSuccess;
   ok &= cudaMalloc(&d->traj_ids, sizeof(int) * nl) == cudaSuccess;
+  ok &= cudaMalloc(&d->fsm_state, sizeof(int) * nl) == cudaSuccess;
+  ok &= cudaMalloc(&d->fsm_fail, sizeof(int) * nl) == cudaSuccess;
   ok &= cudaMalloc(&d->sep_np, sizeof(int) * nl) == cudaSuccess;
   ok &= cudaMalloc(&d->sep_st, sizeof(int) * nl) == cudaSuccess;
   ok &= cudaMalloc(&d->sep_cpts, sizeof(double) * POP_MAX_PIECES * 15 * nl) == cudaSuccess;
   auto finish = [&]() -> int {
     if (!ok) { cudaGetLastError(); return pop_fail(h, POP_E_CUDA, "cycle workspace allocation failed"); }
     POP_CUDA(h, cudaMemsetAsync(d->traj_ids, 0, sizeof(int) * nl, h->stream));
+    POP_CUDA(h, cudaMemsetAsync(d->fsm_state, 0, sizeof(int) * nl, h->stream));   // POP_FSM_NEW_PLAN
+    POP_CUDA(h, cudaMemsetAsync(d->fsm_fail, 0, sizeof(int) * nl, h->stream));
     POP_CUDA(h, cudaMemsetAsync(d->status, 0, sizeof(int) * nl, h->stream));
     return POP_OK;
   };
   const int rc = finish();
   if (rc != POP_OK) {   // leave no half-built workspace behind: the next call allocates again
-    void* ptrs[] = {d->sep_wd, d->sep_wi, d->safe, d->status, d->traj_ids, d->sep_np, d->sep_st, d->sep_cpts};
+    void* ptrs[] = {d->sep_wd, d->sep_wi, d->safe, d->status, d->traj_ids, d->fsm_state, d->fsm_fail, d->sep_np, d->sep_st, d->sep_cpts};
     for (void* q : ptrs) if (q) cudaFree(q);
     delete d;
     h->plan = nullptr;
@@ -171,7 +246,7 @@ void pop_plan_free(pop_handle* h) {
   popk_qp_free(h);
   PlanDev* d = h->plan;
   if (!d) return;
-  void* ptrs[] = {d->sep_wd, d->sep_wi, d->safe, d->status, d->traj_ids, d->sep_np, d->sep_st, d->sep_cpts};
+  void* ptrs[] = {d->sep_wd, d->sep_wi, d->safe, d->status, d->traj_ids, d->fsm_state, d->fsm_fail, d->sep_np, d->sep_st, d->sep_cpts};
   for (void* p : ptrs) if (p) cudaFree(p);
   delete d;
   h->plan = nullptr;
@@ -306,6 +381,23 @@ int pop_separation_check_batch(pop_handle* h, const int32_t* n_pieces, const dou
   POP_CUDA(h, cudaMemcpyAsync(safe.data(), d->safe, sizeof(int) * nl, cudaMemcpyDeviceToHost, h->stream));
   POP_CUDA(h, cudaStreamSynchronize(h->stream));
   for (int i = 0; i < nl; i++) out_safe[i] = static_cast<int8_t>(safe[i]);
+  return POP_OK;
+}
+
+int pop_fsm_update(pop_handle* h, double t_now, const pop_fsm_params* prm, int32_t* out_state, int32_t* out_failures) {
+  if (!h || !prm || prm->replan_max_failures < 0 || !(prm->goal_tolerance >= 0.0) || !(prm->hover_duration > 0.0)) return POP_E_INVALID;
+  PopDeviceGuard guard(h);
+  if (!h->plan || !h->astar) return pop_fail(h, POP_E_STATE, "no cycle has run yet");
+  PlanDev* d = h->plan;
+  const int nl = h->cfg.n_agents_local;
+  k_fsm_update<<<(nl + 127) / 128, 128, 0, h->stream>>>(nl, h->cfg.agent_id_base, t_now, prm->replan_max_failures, prm->goal_tolerance,
+                                                       prm->hover_duration, d->status, popk_astar_start_dev(h), popk_astar_goal_dev(h),
+                                                       h->d_traj_send, d->traj_ids, d->fsm_state, d->fsm_fail);
+  POP_LAUNCH_CHECK(h);
+  h->n_launches++;
+  if (out_state) POP_CUDA(h, cudaMemcpyAsync(out_state, d->fsm_state, sizeof(int) * nl, cudaMemcpyDeviceToHost, h->stream));
+  if (out_failures) POP_CUDA(h, cudaMemcpyAsync(out_failures, d->fsm_fail, sizeof(int) * nl, cudaMemcpyDeviceToHost, h->stream));
+  if (out_state || out_failures) POP_CUDA(h, cudaStreamSynchronize(h->stream));
   return POP_OK;
 }
 

@@ -227,6 +227,14 @@ class PopEngine:
         """Every local agent moves to its commanded state at t_next (perfect tracking); resident, async."""
         self._check(self.lib.pop_swarm_advance(self._h, float(t_next)))
 
+    def fsm_update(self, t_now: float, replan_max_failures: int = 3, goal_tolerance: float = 1.0, hover_duration: float = 1.5):
+        """FSM bookkeeping after a cycle (failure counters, hover trajectory, goal check): (states, failure counts)."""
+        prm = _lib.PopFsmParams(int(replan_max_failures), 0, float(goal_tolerance), float(hover_duration))
+        st = np.zeros(self.n_local, np.int32)
+        fl = np.zeros(self.n_local, np.int32)
+        self._check(self.lib.pop_fsm_update(self._h, float(t_now), C.byref(prm), as_ptr(st, C.c_int32), as_ptr(fl, C.c_int32)))
+        return st, fl
+
     def swarm_states(self):
         out = np.zeros((self.n_local, 9))
         self._check(self.lib.pop_swarm_states(self._h, as_ptr(out, C.c_double)))

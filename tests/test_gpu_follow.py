@@ -84,3 +84,39 @@ def test_closed_loop_flight(oracle):
     mo, mu = eng.eval_metrics(t0 + 1.02)
     assert mu.min() > 0.2 and mo.min() > 0.0              # no agent inside an obstacle or on top of a peer
     eng.close()
+
+
+def test_is_traj_safe(oracle):
+    """pop_traj_safe_batch = BaselinePlanner::isTrajSafe (baseline.cpp:45-68): after a cycle, the world moves on and
+    every agent's own trajectory is re-checked against the new map from several wall-clock times and horizons —
+    booleans and the time of the first occupied sample identical to the oracle (itself pinned against the compiled
+    reference planners, tests/test_ref_pins.py)."""
+    n = 10
+    cfg, eng, cloud, cyl = _engine(n)
+    start, goal = p.worldgen.circle_agents(n, 5.5)
+    poses = start[:, :3].astype(np.float32)
+    st, tr = eng.replan_cycle(start, goal, poses, 40.0, 40.02)
+    assert (st == 0).sum() >= n // 2
+    unsafe = 0
+    for t_map, drift in ((40.0, 0.0), (40.5, 0.25), (41.0, 0.6)):
+        # later map stamps seen from drifted map centres: some samples have become occupied
+        poses2 = (poses + np.float32([drift, -0.5 * drift, 0.0])).astype(np.float32)
+        eng.set_poses(poses2)
+        eng.map_update_gt(t_map)
+        oms = []
+        for a in range(n):
+            m = oracle.map(cfg)
+            m.set_pose(poses2[a])
+            m.update_gt(cloud, cyl, t_map)
+            oms.append(m)
+        for now, T in ((39.9, 2.0), (40.02, 2.0), (40.33, 1.0), (40.7, 5.0), (41.4, 0.5), (43.0, 2.0)):
+            safe, tu = eng.is_traj_safe(now, T)
+            for a in range(n):
+                if st[a] != 0:
+                    assert safe[a] == 1 and tu[a] == -1.0      # no trajectory: nothing to sample
+                    continue
+                want, wt = oms[a].traj_safe(tr[a], cfg.corridor_tau, [now], T)
+                assert safe[a] == want[0] and tu[a] == wt[0], (t_map, now, T, a, safe[a], want[0], tu[a], wt[0])
+                unsafe += int(want[0] == 0)
+    assert unsafe > 0
+    eng.close()

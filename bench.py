@@ -61,6 +61,17 @@ CONFIGS = {
 }
 
 
+def arena_origin(rank: int, world: int, pitch: float):
+    """Centre of rank `rank`'s arena: slot `rank` of a side x side tiling (side = ceil(sqrt(world))) centred on the
+    origin, row-major.  POP_BENCH_ARENA_SHIFT (diagnosis) moves every arena further out along x by that many pitches."""
+    side = 1
+    while side * side < world:
+        side += 1
+    ix, iy = rank % side, rank // side
+    shift = int(os.environ.get("POP_BENCH_ARENA_SHIFT", "0"))
+    return ((ix - 0.5 * (side - 1) + shift) * pitch, (iy - 0.5 * (side - 1)) * pitch)
+
+
 class Scenario:
     """One rank's share of a config: configuration, world script, initial agent states."""
 
@@ -81,14 +92,20 @@ class Scenario:
         c.max_cloud_points = 1 << 19
         self.cfg = c
         world = n_total // n_local
-        rank = id_base // n_local + int(os.environ.get("POP_BENCH_ARENA_SHIFT", "0"))   # diagnosis: fly in a later rank's arena
-        self.shift = rank * k["pitch"]
+        rank = id_base // n_local
         cloud, cyl, owner = p.worldgen.make_world(k["seed"], arena=k["arena"], n_static=k["n_static"], n_moving=k["n_moving"],
                                                   return_owner=True)
-        # every rank flies its own copy of the arena, translated along x (weak scaling as BASELINE config 4 words it:
-        # "arena per GPU"); all trajectories are still exchanged and every rank's peer projection scans all records
-        cloud[:, 0] += np.float32(self.shift)
-        cyl["x"] += self.shift
+        # every rank flies its own copy of the arena (weak scaling as BASELINE config 4 words it: "arena per GPU"),
+        # translated to its slot of a square tiling centred on the origin; all trajectories are still exchanged and
+        # every rank's peer projection scans all records.  The tiling is kept compact on purpose: the reference sets
+        # OSQP's eps_rel = 1e-3 on an unscaled termination test in WORLD coordinates (iosqp.hpp:87-89), so the corridor
+        # rows may be violated by 1e-3 x |coordinate| — 1.5 cm in the reference's own +-15 m arenas, 22 cm for an arena
+        # 224 m out, where planned trajectories then touch their neighbours' and the separation test rejects them.
+        self.origin = arena_origin(rank, world, k["pitch"])
+        cloud[:, 0] += np.float32(self.origin[0])
+        cloud[:, 1] += np.float32(self.origin[1])
+        cyl["x"] += self.origin[0]
+        cyl["y"] += self.origin[1]
         self.cloud0, self.cyl0, self.owner = cloud, cyl, owner
         self.max_abs_vy = float(np.abs(cyl["vy"]).max()) if len(cyl) else 0.0
         if k["layout"] == "circle":
@@ -98,9 +115,10 @@ class Scenario:
         start = np.tile(s0, (world, 1))
         goal = np.tile(g0, (world, 1))
         for r in range(world):
-            off = (r + int(os.environ.get("POP_BENCH_ARENA_SHIFT", "0"))) * k["pitch"]
-            start[r * n_local:(r + 1) * n_local, 0] += off
-            goal[r * n_local:(r + 1) * n_local, 0] += off
+            ox, oy = arena_origin(r, world, k["pitch"])
+            for arr in (start, goal):
+                arr[r * n_local:(r + 1) * n_local, 0] += ox
+                arr[r * n_local:(r + 1) * n_local, 1] += oy
         self.start_all, self.goal_all = start, goal
         self.body = p.worldgen.body_table(n_total, [0.4, 0.4, 0.45])
 

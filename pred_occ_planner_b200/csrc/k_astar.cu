@@ -19,7 +19,8 @@
 
 namespace {
 
-constexpr int kThreads = 128;
+constexpr int kRoleThreads = 96;            // three warps cover the 75 primitives
+constexpr int kThreads = 3 * kRoleThreads;  // lookup, gather and heuristic roles
 constexpr int kMaxPrim = 75;
 constexpr int kSmemNodes = 16384;  // f (double) + heap (int) = 12 B per node in shared memory
 
@@ -68,14 +69,20 @@ __device__ __forceinline__ unsigned hash_slot(unsigned long long k, unsigned mas
   k ^= k >> 23; k *= 0x2127599bf4325c37ull; k ^= k >> 29;
   return static_cast<unsigned>(k) & mask;
 }
+// Linear probing, two slots per round: keys and values of both are loaded before any is looked at, so the usual
+// lookup (hit or miss within two slots) costs one memory round trip instead of two or three dependent ones.
 __device__ int hash_find(const unsigned long long* hkey, const int* hval, unsigned mask, unsigned gen,
                          unsigned long long key) {
   unsigned pos = hash_slot(key, mask);
-  for (unsigned probe = 0; probe <= mask; probe++) {
-    const unsigned long long k = hkey[pos];
-    if ((k >> 48) != (gen & 0xffffu)) return -1;
-    if (k == key) return hval[pos];
-    pos = (pos + 1) & mask;
+  for (unsigned probe = 0; probe <= mask; probe += 2) {
+    const unsigned pos1 = (pos + 1) & mask;
+    const unsigned long long k0 = hkey[pos], k1 = hkey[pos1];
+    const int v0 = hval[pos], v1 = hval[pos1];
+    if ((k0 >> 48) != (gen & 0xffffu)) return -1;
+    if (k0 == key) return v0;
+    if ((k1 >> 48) != (gen & 0xffffu)) return -1;
+    if (k1 == key) return v1;
+    pos = (pos + 2) & mask;
   }
   return -1;
 }
@@ -166,11 +173,18 @@ __device__ double heuristic(const AstarParams& P, const double* x1, const double
   const double t_bar = linf / v_max;
   ts[n++] = t_bar;
   double cost = 100000000, t_d = t_bar;
-  for (int i = 0; i < n; i++) {
-    const double t = ts[i];
-    if (t < t_bar) continue;
-    const double c = -c1 / (3 * t * t * t) - c2 / (2 * t * t) - c3 / t + P.w_time * t;
-    if (c < cost) { cost = c; t_d = t; }
+  // at most 4 roots + t_bar; the candidates' costs do not depend on one another, so they are evaluated side by side
+  // (three divisions each, the long pole of this function) and only the selection walks them in order
+  double cs[5];
+#pragma unroll
+  for (int i = 0; i < 5; i++) {
+    const double t = i < n ? ts[i] : 1.0;
+    cs[i] = -c1 / (3 * t * t * t) - c2 / (2 * t * t) - c3 / t + P.w_time * t;
+  }
+#pragma unroll
+  for (int i = 0; i < 5; i++) {
+    if (i >= n || ts[i] < t_bar) continue;
+    if (cs[i] < cost) { cost = cs[i]; t_d = ts[i]; }
   }
   if (opt_t) *opt_t = t_d;
   return 1.0 * (1 + P.tie_breaker) * cost;
@@ -225,12 +239,13 @@ __device__ void heap_pop(int* heap, const double* f, int& size) {
 
 struct Prim {  // per-primitive scratch in shared memory
   double state[6];
-  double g, f;
   int id[3];
+  double node_g; // g of the existing node
   int node;      // existing node found in the hash (-1 none)
   int nstate;    // its state
   int valid;
 };
+enum { EV_NONE = 0, EV_NEW, EV_LOWER, EV_UPD, EV_ERR };
 
 template <typename C>
 __global__ void __launch_bounds__(kThreads) k_astar(PopGeom g, AstarParams P, AstarDev D,
@@ -240,9 +255,11 @@ __global__ void __launch_bounds__(kThreads) k_astar(PopGeom g, AstarParams P, As
   double* f = reinterpret_cast<double*>(smem_raw);            // [cap]
   int* heap = reinterpret_cast<int*>(f + P.cap);              // [cap]
   __shared__ Prim prim[kMaxPrim];
-  __shared__ int s_tmp_node[kMaxPrim], s_tmp_owner[kMaxPrim], s_tmp_src[kMaxPrim];
-  __shared__ int s_leader[kMaxPrim], s_slot[kMaxPrim];
-  __shared__ int s_ntmp, s_heap_size, s_use, s_iter, s_ret, s_done, s_cur, s_init, s_shot, s_term;
+  __shared__ unsigned long long s_key[kMaxPrim];
+  __shared__ double s_score[kMaxPrim], s_pg[kMaxPrim], s_pf[kMaxPrim];
+  __shared__ int s_leader[kMaxPrim], s_newid[kMaxPrim], s_ev[kMaxPrim], s_owns[kMaxPrim], s_bad[kMaxPrim];
+  __shared__ unsigned s_evmask[3];
+  __shared__ int s_heap_size, s_use, s_iter, s_ret, s_done, s_cur, s_init, s_shot, s_term;
   __shared__ double s_cur_state[6], s_cur_time, s_cur_g, s_end[6], s_start[9], s_time_origin, s_center[3];
   __shared__ int s_cur_index[3], s_cur_tidx, s_end_index[3];
   __shared__ unsigned s_gen;
@@ -273,6 +290,14 @@ __global__ void __launch_bounds__(kThreads) k_astar(PopGeom g, AstarParams P, As
     return static_cast<int>(floor(__dmul_rn(__dsub_rn(t, s_time_origin), P.inv_tres)));
   };
 
+#ifdef POP_ASTAR_PROF   // cycles per section of an expansion, thread 0's clock (scripts/gpu_astar_phase.sh)
+  long long prof_acc[6] = {0, 0, 0, 0, 0, 0}, prof_t = clock64();
+  __shared__ long long s_prof_role[3];
+  if (tid < 3) s_prof_role[tid] = 0;
+#define POP_ASTAR_TICK(k) do { if (tid == 0) { const long long c_ = clock64(); prof_acc[k] += c_ - prof_t; prof_t = c_; } } while (0)
+#else
+#define POP_ASTAR_TICK(k) do { } while (0)
+#endif
   int total_iter = 0, retried = 0;
   for (int attempt = 0; attempt < 2; attempt++) {
     // ---- reset() + search() prologue (:85-107, :122-165) ----
@@ -314,15 +339,24 @@ __global__ void __launch_bounds__(kThreads) k_astar(PopGeom g, AstarParams P, As
 
     while (true) {
       // ---- pop / termination (:167-225) ----
-      if (tid == 0) {
-        if (s_heap_size == 0) {
+      // The sift-down of pop() needs only the heap; the termination tests need only the top node's payload.  Two
+      // threads of different warps do one each: if the node turns out to be terminal the search ends and the popped
+      // heap is never looked at again.
+      POP_ASTAR_TICK(0);
+      const int top_node = s_heap_size > 0 ? heap[0] : -1;
+      __syncthreads();
+      if (tid == 0 && top_node >= 0) heap_pop(heap, f, s_heap_size);
+      if (tid == 32) {
+        if (top_node < 0) {
           s_done = 1; s_ret = POP_ASTAR_NO_PATH; s_term = -1;
         } else {
-          const int cur = heap[0];
+          const int cur = top_node;
           double cs[6];
           for (int i = 0; i < 6; i++) cs[i] = n_state[cur * 6 + i];
           const double ctime = n_time[cur];
           int cidx[3] = {n_index[cur * 3], n_index[cur * 3 + 1], n_index[cur * 3 + 2]};
+          const double cg = n_g[cur];
+          const int ctidx = n_tidx[cur];
           const double dx = cs[0] - s_start[0], dy = cs[1] - s_start[1], dz = cs[2] - s_start[2];
           const bool reach_horizon = sqrt(dx * dx + dy * dy + dz * dz) >= P.horizon;
           const bool near_end = abs(cidx[0] - s_end_index[0]) <= P.tolerance &&
@@ -362,170 +396,218 @@ __global__ void __launch_bounds__(kThreads) k_astar(PopGeom g, AstarParams P, As
             else if (near_end) s_ret = s_shot ? POP_ASTAR_REACH_END : (n_parent[cur] >= 0 ? POP_ASTAR_NEAR_END : POP_ASTAR_NO_PATH);
             else s_ret = POP_ASTAR_REACH_HORIZON;
           } else {
-            heap_pop(heap, f, s_heap_size);
             n_nstate[cur] = IN_CLOSE_SET;
             s_iter++;
             s_cur = cur;
             for (int i = 0; i < 6; i++) s_cur_state[i] = cs[i];
             s_cur_time = ctime;
-            s_cur_g = n_g[cur];
-            s_cur_tidx = n_tidx[cur];
+            s_cur_g = cg;
+            s_cur_tidx = ctidx;
             for (int i = 0; i < 3; i++) s_cur_index[i] = cidx[i];
-            s_ntmp = 0;
           }
         }
       }
+      __threadfence_block();
       __syncthreads();
       if (s_done) break;
+      POP_ASTAR_TICK(1);
 
-      // ---- phase 1: evaluate primitives in parallel (:229-343) ----
+      // ---- evaluate the primitives in parallel (:229-343) ----
+      // Three roles, one warp group each, all starting from the popped node's state: the lookups (closed set /
+      // velocity / same voxel pruning), the SOGM region-risk gathers and the quartic heuristics do not need one
+      // another's results, only the commit needs all three.  Gathers and heuristics of primitives the lookup prunes
+      // are wasted work on otherwise idle warps; the expansion's latency is that of the slowest role, not their sum.
       const int n_inputs = s_init ? 1 : kMaxPrim;
-      if (tid < n_inputs) {
-        Prim& pr = prim[tid];
-        double um[3];
-        if (s_init) {
+      auto prim_input = [&](int i, double* um) {
+        if (n_inputs == 1) {
           um[0] = s_start[6]; um[1] = s_start[7]; um[2] = s_start[8];
         } else {
           // ax, ay in {-A, -A/2, 0, A/2, A}, az in {-A/2, 0, A/2}; loop order ax -> ay -> az,
           // values accumulated like `ax += max_acc_ * res`
           const double step = __dmul_rn(P.max_acc, 0.5);
-          const int ia = tid / 15, ib = (tid / 3) % 5, ic = tid % 3;
+          const int ia = i / 15, ib = (i / 3) % 5, ic = i % 3;
           double ax = -P.max_acc, ay = -P.max_acc, az = __dmul_rn(-0.5, P.max_acc);
           for (int q = 0; q < ia; q++) ax = __dadd_rn(ax, step);
           for (int q = 0; q < ib; q++) ay = __dadd_rn(ay, step);
           for (int q = 0; q < ic; q++) az = __dadd_rn(az, step);
           um[0] = ax; um[1] = ay; um[2] = az;
         }
-        const double tau = P.tau;
-        double ps[6];
-        transit(s_cur_state, ps, um, tau);
-        const double pro_t = __dadd_rn(s_cur_time, tau);
-        int pid[3];
-        pos_to_index(ps, pid);
-        const int pro_t_id = time_to_index(pro_t);
-        int valid = 1;
-        const int node = hash_find(hkey, hval, mask, s_gen, pack_key(s_gen, pid[0], pid[1], pid[2], pro_t_id));
-        int nst = NOT_EXPAND;
-        if (node >= 0) {
-          nst = n_nstate[node];
-          if (nst == IN_CLOSE_SET) valid = 0;
-        }
-        if (valid && (fabs(ps[3]) > P.max_vel || fabs(ps[4]) > P.max_vel || fabs(ps[5]) > P.max_vel)) valid = 0;
-        if (valid && pid[0] == s_cur_index[0] && pid[1] == s_cur_index[1] && pid[2] == s_cur_index[2] &&
-            pro_t_id - s_cur_tidx == 0)
-          valid = 0;
-        if (valid) {
-          for (int k = 1; k <= P.check_num; ++k) {
-            const double dt = __ddiv_rn(__dmul_rn(tau, static_cast<double>(k)), static_cast<double>(P.check_num));
-            double xt[6];
-            transit(s_cur_state, xt, um, dt);
-            const double t = __dadd_rn(s_cur_time, dt);
-            if (query_dt<C>(g, ag, pose, xt, t) != 0) { valid = 0; break; }
+      };
+      const int role = tid / kRoleThreads, ri = tid % kRoleThreads;
+#ifdef POP_ASTAR_PROF
+      const long long role_t0 = clock64();
+#endif
+      if (ri < n_inputs) {
+        double um[3], ps[6];
+        prim_input(ri, um);
+        transit(s_cur_state, ps, um, P.tau);
+        const bool vel_ok = !(fabs(ps[3]) > P.max_vel || fabs(ps[4]) > P.max_vel || fabs(ps[5]) > P.max_vel);
+        if (role == 0) {
+          Prim& pr = prim[ri];
+          const double pro_t = __dadd_rn(s_cur_time, P.tau);
+          int pid[3];
+          pos_to_index(ps, pid);
+          const int pro_t_id = time_to_index(pro_t);
+          int valid = 1;
+          const int node = hash_find(hkey, hval, mask, s_gen, pack_key(s_gen, pid[0], pid[1], pid[2], pro_t_id));
+          int nst = NOT_EXPAND;
+          double node_g = 0.0;
+          if (node >= 0) {
+            nst = n_nstate[node];
+            node_g = n_g[node];
+            if (nst == IN_CLOSE_SET) valid = 0;
           }
-        }
-        if (valid) {
-          const double usq = um[0] * um[0] + um[1] * um[1] + um[2] * um[2];
-          pr.g = (usq + P.w_time) * tau + s_cur_g;
-          pr.f = pr.g + P.lambda_heu * heuristic(P, ps, s_end, nullptr);
-        }
-        for (int i = 0; i < 6; i++) pr.state[i] = ps[i];
-        for (int i = 0; i < 3; i++) pr.id[i] = pid[i];
-        pr.node = node;
-        pr.nstate = nst;
-        pr.valid = valid;
-      }
-      __syncthreads();
-      // same-voxel duplicates among this expansion's new nodes (:345-360): the reference scans the list of nodes
-      // created so far for every primitive; here every primitive finds, in parallel, the first earlier valid
-      // primitive of its voxel (the one that will have created the node), so the ordered commit below is O(n)
-      if (tid < n_inputs) {
-        int leader = tid;
-        const Prim& pr = prim[tid];
-        if (pr.valid && pr.node < 0) {
-          for (int j = 0; j < tid; j++) {
-            const Prim& q = prim[j];
-            if (q.valid && q.id[0] == pr.id[0] && q.id[1] == pr.id[1] && q.id[2] == pr.id[2]) { leader = j; break; }
-          }
-        }
-        s_leader[tid] = leader;
-      }
-      __syncthreads();
-
-      // ---- phase 2: ordered commit (:345-419) ----
-      if (tid == 0) {
-        const int pro_t_id = time_to_index(__dadd_rn(s_cur_time, P.tau));
-        for (int i = 0; i < n_inputs; i++) {
-          Prim& pr = prim[i];
-          if (!pr.valid) continue;
-          if (pr.node < 0 && s_leader[i] != i) {   // an earlier primitive of this expansion created the node
-            const int j = s_slot[s_leader[i]];
-            const int en = s_tmp_node[j];
-            if (pr.f < f[en]) { f[en] = pr.f; s_tmp_owner[j] = i; }
-            continue;
-          }
-          if (pr.node < 0) {
-            const int id = s_use;
-            f[id] = pr.f;
-            heap_push(heap, f, s_heap_size, id);
-            s_tmp_node[s_ntmp] = id; s_tmp_owner[s_ntmp] = i; s_tmp_src[s_ntmp] = i;
-            s_slot[i] = s_ntmp;
-            s_ntmp++;
-            s_use++;
-            if (s_use == P.cap) { s_done = 1; s_ret = POP_ASTAR_NO_PATH; s_term = -1; break; }
-          } else if (n_nstate[pr.node] == IN_OPEN_SET) {
-            const int nd = pr.node;
-            if (pr.g < n_g[nd]) {
-              for (int q = 0; q < 6; q++) n_state[nd * 6 + q] = pr.state[q];
-              f[nd] = pr.f;
-              n_g[nd] = pr.g;
-              const double step = __dmul_rn(P.max_acc, 0.5);
-              double ax = -P.max_acc, ay = -P.max_acc, az = __dmul_rn(-0.5, P.max_acc);
-              if (s_init) { ax = s_start[6]; ay = s_start[7]; az = s_start[8]; }
-              else {
-                for (int q = 0; q < i / 15; q++) ax = __dadd_rn(ax, step);
-                for (int q = 0; q < (i / 3) % 5; q++) ay = __dadd_rn(ay, step);
-                for (int q = 0; q < i % 3; q++) az = __dadd_rn(az, step);
-              }
-              n_input[nd * 3] = ax; n_input[nd * 3 + 1] = ay; n_input[nd * 3 + 2] = az;
-              n_parent[nd] = s_cur;
-              n_time[nd] = __dadd_rn(s_cur_time, P.tau);
+          if (valid && !vel_ok) valid = 0;
+          if (valid && pid[0] == s_cur_index[0] && pid[1] == s_cur_index[1] && pid[2] == s_cur_index[2] &&
+              pro_t_id - s_cur_tidx == 0)
+            valid = 0;
+          for (int i = 0; i < 6; i++) pr.state[i] = ps[i];
+          for (int i = 0; i < 3; i++) pr.id[i] = pid[i];
+          pr.node = node;
+          pr.nstate = nst;
+          pr.node_g = node_g;
+          pr.valid = valid;
+          s_newid[ri] = -1;
+        } else if (role == 1) {
+          int bad = 0;
+          if (vel_ok) {
+            for (int k = 1; k <= P.check_num && !bad; ++k) {
+              const double dt = __ddiv_rn(__dmul_rn(P.tau, static_cast<double>(k)), static_cast<double>(P.check_num));
+              double xt[6];
+              transit(s_cur_state, xt, um, dt);
+              bad = query_dt<C>(g, ag, pose, xt, __dadd_rn(s_cur_time, dt)) != 0;
             }
+          }
+          s_bad[ri] = bad;
+        } else if (vel_ok) {
+          const double usq = um[0] * um[0] + um[1] * um[1] + um[2] * um[2];
+          const double gg = (usq + P.w_time) * P.tau + s_cur_g;
+          s_pg[ri] = gg;
+          s_pf[ri] = gg + P.lambda_heu * heuristic(P, ps, s_end, nullptr);
+        }
+      }
+#ifdef POP_ASTAR_PROF
+      if (ri == 37) s_prof_role[role] += clock64() - role_t0;   // a middle primitive of each role
+#endif
+      __syncthreads();
+      POP_ASTAR_TICK(2);
+      // ---- ordered commit (:345-419), resolved in parallel ----
+      // All valid primitives that land in one voxel address one node (the time index is the same for all of them):
+      // a new one, created by the first of them ("leader", the same-voxel scan of :345-360), or one already open.  The
+      // reference walks the primitives in order; what that walk does to a node depends only on the primitives of
+      // its voxel, so every primitive finds out by itself, from the others' voxel and score, whether the walk
+      //   NEW    creates the node with its f (it is the leader),
+      //   LOWER  lowers the new node's f in place (its f is below that of every earlier primitive of the voxel),
+      //   UPD    re-parents the open node (its g is below the node's and every earlier primitive's of the voxel),
+      // and whether it ends up owning the node's payload (lowest score of the voxel, first among equals).  Only the
+      // heap order still needs the walk: thread 0 replays those events, in primitive order, on f[] and the heap.
+      if (tid < kMaxPrim) {   // slots past n_inputs (the first expansion has one input) get a key nothing matches
+        Prim& pr = prim[tid];
+        const int valid = tid < n_inputs && pr.valid && !s_bad[tid];
+        pr.valid = valid;
+        s_key[tid] = valid ? pack_key(0, pr.id[0], pr.id[1], pr.id[2], 0) : (~0ull - static_cast<unsigned long long>(tid));
+        s_score[tid] = pr.node < 0 ? s_pf[tid] : s_pg[tid];
+      }
+      __syncthreads();
+      int ev = EV_NONE;
+      if (tid < n_inputs) {
+        const Prim& pr = prim[tid];
+        int owns = 0;
+        if (pr.valid) {
+          const unsigned long long key = s_key[tid];
+          const double mine = s_score[tid];
+          int leader = tid, beaten = 0;
+          double prev_min = pr.node < 0 ? INFINITY : pr.node_g;
+          // the key compares are branch-free and unrolled (their loads do not wait for one another); only the few
+          // primitives that share the voxel are then looked at
+#pragma unroll
+          for (int c = 0; c < 3; c++) {
+            unsigned m = 0u;
+#pragma unroll
+            for (int k = 0; k < 25; k++) m |= (s_key[c * 25 + k] == key ? 1u : 0u) << k;
+            if (tid / 25 == c) m &= ~(1u << (tid % 25));
+            while (m) {
+              const int j = c * 25 + __ffs(m) - 1;
+              m &= m - 1;
+              const double sj = s_score[j];
+              if (j < tid) { leader = min(leader, j); prev_min = fmin(prev_min, sj); }
+              if (sj < mine || (sj == mine && j < tid)) beaten = 1;
+            }
+          }
+          s_leader[tid] = leader;
+          if (pr.node < 0) {
+            ev = leader == tid ? EV_NEW : (mine < prev_min ? EV_LOWER : EV_NONE);
+            owns = !beaten;
+          } else if (pr.nstate == IN_OPEN_SET) {
+            ev = mine < prev_min ? EV_UPD : EV_NONE;
+            owns = !beaten && mine < pr.node_g;
           } else {
-            s_done = 1; s_ret = POP_ASTAR_SEARCH_ERR; s_term = -1; break;
+            ev = EV_ERR;
           }
         }
-        (void)pro_t_id;
+        s_owns[tid] = owns;
+        s_ev[tid] = ev;
+      }
+      if (tid < 96) {   // warps 0..2 cover the 75 primitives
+        const unsigned m = __ballot_sync(0xffffffffu, ev != EV_NONE);
+        if ((tid & 31) == 0) s_evmask[tid >> 5] = m;
+      }
+      __syncthreads();
+      POP_ASTAR_TICK(3);
+      if (tid == 0) {
+        bool stop = false;
+        for (int w = 0; w < 3 && !stop; w++) {
+          unsigned m = s_evmask[w];
+          while (m) {
+            const int i = w * 32 + __ffs(m) - 1;
+            m &= m - 1;
+            const int e = s_ev[i];
+            if (e == EV_NEW) {
+              const int id = s_use;
+              f[id] = s_pf[i];
+              heap_push(heap, f, s_heap_size, id);
+              s_newid[i] = id;
+              s_use++;
+              if (s_use == P.cap) { s_done = 1; s_ret = POP_ASTAR_NO_PATH; s_term = -1; stop = true; break; }
+            } else if (e == EV_LOWER) {
+              f[s_newid[s_leader[i]]] = s_pf[i];
+            } else if (e == EV_UPD) {
+              f[prim[i].node] = s_pf[i];
+            } else {
+              s_done = 1; s_ret = POP_ASTAR_SEARCH_ERR; s_term = -1; stop = true; break;
+            }
+          }
+        }
         if (s_init) s_init = 0;
       }
       __syncthreads();
+      POP_ASTAR_TICK(4);
 
-      // ---- phase 3: publish new nodes (payload + hash) in parallel ----
-      if (tid < s_ntmp) {
-        const int id = s_tmp_node[tid], owner = s_tmp_owner[tid], src = s_tmp_src[tid];
-        const Prim& pr = prim[owner];
-        for (int q = 0; q < 6; q++) n_state[id * 6 + q] = pr.state[q];
-        double um[3];
-        if (n_inputs == 1) { um[0] = s_start[6]; um[1] = s_start[7]; um[2] = s_start[8]; }
-        else {
-          const double step = __dmul_rn(P.max_acc, 0.5);
-          um[0] = -P.max_acc; um[1] = -P.max_acc; um[2] = __dmul_rn(-0.5, P.max_acc);
-          for (int q = 0; q < owner / 15; q++) um[0] = __dadd_rn(um[0], step);
-          for (int q = 0; q < (owner / 3) % 5; q++) um[1] = __dadd_rn(um[1], step);
-          for (int q = 0; q < owner % 3; q++) um[2] = __dadd_rn(um[2], step);
+      // ---- publish the payloads (new nodes and re-parented open nodes) and the hash entries in parallel ----
+      if (tid < n_inputs && s_owns[tid]) {
+        const Prim& pr = prim[tid];
+        const int id = pr.node < 0 ? s_newid[s_leader[tid]] : pr.node;
+        if (id >= 0) {   // -1: the walk stopped (pool exhausted) before the leader's turn
+          for (int q = 0; q < 6; q++) n_state[id * 6 + q] = pr.state[q];
+          double um[3];
+          prim_input(tid, um);
+          for (int q = 0; q < 3; q++) n_input[id * 3 + q] = um[q];
+          const double t = __dadd_rn(s_cur_time, P.tau);
+          n_time[id] = t;
+          n_g[id] = s_pg[tid];
+          n_parent[id] = s_cur;
+          if (pr.node < 0) {
+            for (int q = 0; q < 3; q++) n_index[id * 3 + q] = pr.id[q];
+            n_tidx[id] = time_to_index(t);
+            n_nstate[id] = IN_OPEN_SET;
+            // expanded_nodes_.insert(pro_id, pro_node->time, ...): the double time is truncated to int
+            hash_insert(hkey, hval, mask, s_gen, pack_key(s_gen, pr.id[0], pr.id[1], pr.id[2], static_cast<int>(t)), id);
+          }
         }
-        for (int q = 0; q < 3; q++) { n_input[id * 3 + q] = um[q]; n_index[id * 3 + q] = prim[src].id[q]; }
-        const double t = __dadd_rn(s_cur_time, P.tau);
-        n_time[id] = t;
-        n_tidx[id] = time_to_index(t);
-        n_g[id] = pr.g;
-        n_parent[id] = s_cur;
-        n_nstate[id] = IN_OPEN_SET;
-        // expanded_nodes_.insert(pro_id, pro_node->time, ...): the double time is truncated to int
-        hash_insert(hkey, hval, mask, s_gen,
-                    pack_key(s_gen, prim[src].id[0], prim[src].id[1], prim[src].id[2], static_cast<int>(t)), id);
       }
       __threadfence_block();
       __syncthreads();
+      POP_ASTAR_TICK(5);
       if (s_done) break;
     }
     total_iter += s_iter;
@@ -535,6 +617,12 @@ __global__ void __launch_bounds__(kThreads) k_astar(PopGeom g, AstarParams P, As
     __syncthreads();
   }
 
+#ifdef POP_ASTAR_PROF
+  if (tid == 0 && total_iter >= 100)
+    printf("astar_prof agent %d expansions %d nodes %d cycles/expansion: pop %lld evaluate %lld (lookup %lld gather %lld heuristic %lld) resolve %lld commit %lld publish %lld\n", a,
+           total_iter, s_use, prof_acc[1] / total_iter, prof_acc[2] / total_iter, s_prof_role[0] / total_iter, s_prof_role[1] / total_iter, s_prof_role[2] / total_iter, prof_acc[3] / total_iter,
+           prof_acc[4] / total_iter, prof_acc[5] / total_iter);
+#endif
   // ---- retrievePath + getPathWithVel(corridor_tau) (:826-836, :663-694) ----
   if (tid == 0) {
     int len = 0;

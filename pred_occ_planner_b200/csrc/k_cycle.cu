@@ -58,32 +58,35 @@ __global__ void __launch_bounds__(128) k_separate(int a0, int w0, int n_local, i
     bool far = false;
     for (int q = 0; q < 3; q++) if (bmin[q] - amax[q] > 1e-2 || amin[q] - bmax[q] > 1e-2) far = true;
     if (far) continue;
+    // GLPK's variables are free, so the reference's answer does not depend on where the pair sits; inside the box
+    // below that only holds with the points taken relative to one of them (A's first), which keeps d small.
+    const double o[3] = {A[0], A[1], A[2]};
     // Certificate before the LP: along u = centroid(A) - centroid(B), n = 2 (1 + 1e-9) u / gap and d halfway between the
     // two sets.  If this (n, d) satisfies every row of the LP below — checked row by row, in double, with the box —
     // the LP is feasible and the pair is safe; the solver is only needed for pairs that nearly touch or interpenetrate.
     {
       double ca[3] = {0, 0, 0}, cb[3] = {0, 0, 0};
-      for (int k = 0; k < na; k++) for (int q = 0; q < 3; q++) ca[q] += A[k * 3 + q];
-      for (int k = 0; k < nb; k++) for (int q = 0; q < 3; q++) cb[q] += B[k * 3 + q];
+      for (int k = 0; k < na; k++) for (int q = 0; q < 3; q++) ca[q] += A[k * 3 + q] - o[q];
+      for (int k = 0; k < nb; k++) for (int q = 0; q < 3; q++) cb[q] += B[k * 3 + q] - o[q];
       double u[3];
       for (int q = 0; q < 3; q++) u[q] = ca[q] / na - cb[q] / nb;
       double lo_a = 1e300, hi_b = -1e300;
-      for (int k = 0; k < na; k++) lo_a = fmin(lo_a, u[0] * A[k * 3] + u[1] * A[k * 3 + 1] + u[2] * A[k * 3 + 2]);
-      for (int k = 0; k < nb; k++) hi_b = fmax(hi_b, u[0] * B[k * 3] + u[1] * B[k * 3 + 1] + u[2] * B[k * 3 + 2]);
+      for (int k = 0; k < na; k++) lo_a = fmin(lo_a, u[0] * (A[k * 3] - o[0]) + u[1] * (A[k * 3 + 1] - o[1]) + u[2] * (A[k * 3 + 2] - o[2]));
+      for (int k = 0; k < nb; k++) hi_b = fmax(hi_b, u[0] * (B[k * 3] - o[0]) + u[1] * (B[k * 3 + 1] - o[1]) + u[2] * (B[k * 3 + 2] - o[2]));
       const double gap = lo_a - hi_b;
       if (gap > 0.0) {
         const double sc = 2.0 * (1.0 + 1e-9) / gap;
         const double nn[3] = {sc * u[0], sc * u[1], sc * u[2]};
         const double dd = -0.5 * sc * (lo_a + hi_b);
         bool ok = fabs(nn[0]) <= 9.99e3 && fabs(nn[1]) <= 9.99e3 && fabs(nn[2]) <= 9.99e3 && fabs(dd) <= 9.99e3;
-        for (int k = 0; ok && k < na; k++) ok = nn[0] * A[k * 3] + nn[1] * A[k * 3 + 1] + nn[2] * A[k * 3 + 2] + dd >= 1.0;
-        for (int k = 0; ok && k < nb; k++) ok = nn[0] * B[k * 3] + nn[1] * B[k * 3 + 1] + nn[2] * B[k * 3 + 2] + dd <= -1.0;
+        for (int k = 0; ok && k < na; k++) ok = nn[0] * (A[k * 3] - o[0]) + nn[1] * (A[k * 3 + 1] - o[1]) + nn[2] * (A[k * 3 + 2] - o[2]) + dd >= 1.0;
+        for (int k = 0; ok && k < nb; k++) ok = nn[0] * (B[k * 3] - o[0]) + nn[1] * (B[k * 3 + 1] - o[1]) + nn[2] * (B[k * 3 + 2] - o[2]) + dd <= -1.0;
         if (ok) continue;
       }
     }
     int rr = 0;
-    for (int k = 0; k < na; k++) { for (int q = 0; q < 3; q++) rowsM[rr * 4 + q] = -A[k * 3 + q]; rowsM[rr * 4 + 3] = -1.0; rhs[rr] = -1.0; rr++; }
-    for (int k = 0; k < nb; k++) { for (int q = 0; q < 3; q++) rowsM[rr * 4 + q] = B[k * 3 + q]; rowsM[rr * 4 + 3] = 1.0; rhs[rr] = -1.0; rr++; }
+    for (int k = 0; k < na; k++) { for (int q = 0; q < 3; q++) rowsM[rr * 4 + q] = -(A[k * 3 + q] - o[q]); rowsM[rr * 4 + 3] = -1.0; rhs[rr] = -1.0; rr++; }
+    for (int k = 0; k < nb; k++) { for (int q = 0; q < 3; q++) rowsM[rr * 4 + q] = B[k * 3 + q] - o[q]; rowsM[rr * 4 + 3] = 1.0; rhs[rr] = -1.0; rr++; }
     for (int k = 0; k < 4; k++) {
       for (int q = 0; q < 4; q++) { rowsM[rr * 4 + q] = q == k ? 1.0 : 0.0; rowsM[(rr + 1) * 4 + q] = q == k ? -1.0 : 0.0; }
       rhs[rr] = 1e4; rhs[rr + 1] = 1e4;

@@ -169,8 +169,9 @@ template <> struct Cell<float> {
   }
 };
 
-// Sum of the (2S+1) x (2S+1) x (2SZ+1) collision footprint in the reference's order (x outer, y, z inner), one
-// x-plane at a time: the plane's cells are loaded together, then added in order; see geom_query.
+// Sum of the (2S+1) x (2S+1) x (2SZ+1) collision footprint in the reference's order (x outer, y, z inner), compared
+// with the threshold once at the end; see geom_query for why that equals the reference's early exit.  Without an
+// exit between them, all loads of the footprint are independent and go out together.
 template <typename C, int S, int SZ>
 __device__ __forceinline__ int geom_region_sum(const PopGeom& g, const uint8_t* grid, size_t slice, int ix, int iy,
                                                int iz, float thr) {
@@ -194,9 +195,53 @@ __device__ __forceinline__ int geom_region_sum(const PopGeom& g, const uint8_t* 
     }
 #pragma unroll
     for (int k = 0; k < NY * NZ; k++) sum = __fadd_rn(sum, v[k]);
-    if (sum > thr) return 1;
   }
-  return 0;
+  return sum > thr ? 1 : 0;
+}
+
+// Byte cells hold small integers (saturating unit risks), so the footprint's float sum is exact in any order and the
+// 2S+1 <= 9 x-contiguous cells of a row can be read as three aligned words instead of nine byte loads: the window is
+// shifted into place with funnel shifts and its bytes are added with dp4a.  Only for footprints that lie inside the
+// map in x (the clipped ones keep the per-cell path); rows outside in y or z contribute nothing, as in the reference.
+template <int S, int SZ>
+__device__ __forceinline__ int geom_region_sum_u8_rows(const PopGeom& g, const uint8_t* grid, size_t slice, int ix,
+                                                       int iy, int iz, float thr) {
+  constexpr int W = 2 * S + 1;
+  static_assert(W <= 9, "window of at most 9 cells: 12 bytes cover it at any alignment");
+  unsigned sum = 0u;
+#pragma unroll
+  for (int dz = -SZ; dz <= SZ; dz++) {
+    const int z = iz + dz;
+#pragma unroll
+    for (int dy = -S; dy <= S; dy++) {
+      const int y = iy + dy;
+      if (y < 0 || y >= g.ny || z < 0 || z >= g.nz) continue;
+      const uint8_t* row = grid + slice + static_cast<size_t>(z) * g.nx * g.ny + static_cast<size_t>(y) * g.nx + (ix - S);
+      const unsigned* w = reinterpret_cast<const unsigned*>(reinterpret_cast<uintptr_t>(row) & ~uintptr_t(3));
+      const unsigned sh = 8u * static_cast<unsigned>(reinterpret_cast<uintptr_t>(row) & 3u);
+      const unsigned w0 = w[0], w1 = w[1], w2 = W + 3 > 8 ? w[2] : 0u;
+      unsigned b0 = __funnelshift_r(w0, w1, sh);           // window bytes 0..3
+      unsigned b1 = __funnelshift_r(w1, w2, sh);           // window bytes 4..7
+      unsigned b2 = w2 >> sh;                              // window byte 8
+      if (W < 4) b0 &= (1u << (8 * (W & 3))) - 1u;
+      if (W <= 4) b1 = 0u;
+      else if (W < 8) b1 &= (1u << (8 * (W & 3))) - 1u;
+      b2 = W > 8 ? (b2 & 0xffu) : 0u;
+      sum = __dp4a(b0, 0x01010101u, sum);
+      sum = __dp4a(b1, 0x01010101u, sum);
+      sum += b2;
+    }
+  }
+  return static_cast<float>(sum) > thr ? 1 : 0;
+}
+
+template <typename C, int S, int SZ>
+__device__ __forceinline__ int geom_region(const PopGeom& g, const uint8_t* grid, size_t slice, int ix, int iy, int iz,
+                                           float thr) {
+  if constexpr (sizeof(C) == 1) {
+    if (ix - S >= 0 && ix + S < g.nx) return geom_region_sum_u8_rows<S, SZ>(g, grid, slice, ix, iy, iz, thr);
+  }
+  return geom_region_sum<C, S, SZ>(g, grid, slice, ix, iy, iz, thr);
 }
 
 // getClearOcccupancy(pos, int t): fake_particle_risk_voxel.cpp:309-330 / risk_base.cpp:228-250.
@@ -225,17 +270,17 @@ __device__ __forceinline__ int geom_query(const PopGeom& g, const uint8_t* grid,
   const size_t slice = static_cast<size_t>(t) * g.V;
   const int s = g.inf_step;
   const int sz = g.kernel_shape == POP_KERNEL_DISC_Z0 ? 0 : s;
-  // Cells are non-negative, so the running sum never decreases and the reference's early exit ("return 1 as soon
-  // as the sum exceeds the threshold") equals comparing the sum of each x-plane, taken in the same order, once per
-  // plane.  That lets the loads of a plane be issued together instead of one dependent load per cell (the A*
-  // inner loop is bound by exactly this latency).  Out-of-range cells contribute 0, which changes neither the sum
-  // nor the comparison.
-  if (s == 2 && sz == 0) return geom_region_sum<C, 2, 0>(g, grid, slice, ix, iy, iz, thr);
-  if (s == 1 && sz == 1) return geom_region_sum<C, 1, 1>(g, grid, slice, ix, iy, iz, thr);
-  if (s == 2 && sz == 2) return geom_region_sum<C, 2, 2>(g, grid, slice, ix, iy, iz, thr);
-  if (s == 1 && sz == 0) return geom_region_sum<C, 1, 0>(g, grid, slice, ix, iy, iz, thr);
-  if (s == 3 && sz == 0) return geom_region_sum<C, 3, 0>(g, grid, slice, ix, iy, iz, thr);
-  if (s == 4 && sz == 0) return geom_region_sum<C, 4, 0>(g, grid, slice, ix, iy, iz, thr);   // 0.45 m clearance at 0.1 m
+  // Cells are non-negative and round-to-nearest addition is monotone, so the running sum never decreases and the
+  // reference's early exit ("return 1 as soon as the sum exceeds the threshold") equals comparing the sum of the
+  // whole footprint, taken in the same order, once.  That lets all its loads be issued together instead of one
+  // dependent load per cell (the A* inner loop is bound by exactly this latency).  Out-of-range cells contribute 0,
+  // which changes neither the sum nor the comparison.
+  if (s == 2 && sz == 0) return geom_region<C, 2, 0>(g, grid, slice, ix, iy, iz, thr);
+  if (s == 1 && sz == 1) return geom_region<C, 1, 1>(g, grid, slice, ix, iy, iz, thr);
+  if (s == 2 && sz == 2) return geom_region<C, 2, 2>(g, grid, slice, ix, iy, iz, thr);
+  if (s == 1 && sz == 0) return geom_region<C, 1, 0>(g, grid, slice, ix, iy, iz, thr);
+  if (s == 3 && sz == 0) return geom_region<C, 3, 0>(g, grid, slice, ix, iy, iz, thr);
+  if (s == 4 && sz == 0) return geom_region<C, 4, 0>(g, grid, slice, ix, iy, iz, thr);   // 0.45 m clearance at 0.1 m
   float sum = 0.0f;
   for (int dx = -s; dx <= s; dx++) {
     const int x = ix + dx;

@@ -5,6 +5,8 @@
 // path does not use them).
 #include <cmath>
 #include <cstdint>
+#include <cstring>
+#include <vector>
 #include <cuda_runtime.h>
 
 static inline float __fadd_rn(float a, float b) { return a + b; }
@@ -16,6 +18,13 @@ static inline unsigned atomicOr(unsigned* p, unsigned v) { unsigned o = *p; *p |
 static inline unsigned atomicCAS(unsigned* p, unsigned c, unsigned v) { unsigned o = *p; if (o == c) *p = v; return o; }
 static inline float atomicExch(float* p, float v) { float o = *p; *p = v; return o; }
 static inline float atomicAdd(float* p, float v) { float o = *p; *p += v; return o; }
+static inline unsigned __funnelshift_r(unsigned lo, unsigned hi, unsigned sh) {
+  return static_cast<unsigned>(((static_cast<unsigned long long>(hi) << 32) | lo) >> (sh & 31u));
+}
+static inline unsigned __dp4a(unsigned a, unsigned b, unsigned c) {
+  for (int k = 0; k < 4; k++) c += ((a >> (8 * k)) & 0xffu) * ((b >> (8 * k)) & 0xffu);
+  return c;
+}
 
 #include "../../pred_occ_planner_b200/csrc/pop_geom.cuh"
 
@@ -47,7 +56,15 @@ extern "C" {
 void dev_query(const pop_config* cfg, const void* grid, const float* pose, const double* pos, const int32_t* t, int n,
                int8_t* out) {
   const PopGeom g = geom_of(*cfg);
+  // the byte-cell query reads whole aligned words around a row (the device grid is allocated with slack for that)
+  std::vector<uint32_t> padded;
   const uint8_t* base = static_cast<const uint8_t*>(grid);
+  if (cfg->cell_dtype == POP_CELL_U8) {
+    const size_t bytes = static_cast<size_t>(g.nt) * g.V;
+    padded.assign(bytes / 4 + 8, 0u);
+    memcpy(padded.data(), grid, bytes);
+    base = reinterpret_cast<const uint8_t*>(padded.data());
+  }
   for (int i = 0; i < n; i++)
     out[i] = static_cast<int8_t>(cfg->cell_dtype == POP_CELL_U8
                                      ? geom_query<uint8_t>(g, base, pose[0], pose[1], pose[2], pos[3 * i], pos[3 * i + 1], pos[3 * i + 2], t[i])

@@ -9,6 +9,29 @@
 // driven by a caller-owned 64-bit LCG so CPU and GPU agree call by call.
 // PINNED against the reference's own sdlp.hpp compiled into oracle/_ref/libref.so: optimum and minimiser within
 // 1e-9 / 1e-7 on bounded problems, same infeasible / unbounded classification (tests/test_ref_pins.py).
+//
+// The algorithm and its structure are those of sdlp.hpp, whose notices are preserved here as they ask:
+//
+//   Copyright (c) 1990 Michael E. Hohmeyer,
+//         hohmeyer@icemcfd.com
+//   Permission is granted to modify and re-distribute this code in any manner
+//   as long as this notice is preserved.  All standard disclaimers apply.
+//
+//   R. Seidel's algorithm for solving LPs (linear programs.)
+//
+//   Copyright (c) 2021 Zhepei Wang,
+//         wangzhepei@live.com
+//   1. Bug fix in "move_to_front" function that "prev[m]" is illegally accessed
+//      while "prev" originally has only m ints. It is fixed by allocating a
+//      "prev" with m + 1 ints.
+//   2. Add Eigen interface.
+//   3. Resursive template.
+//   Permission is granted to modify and re-distribute this code in any manner
+//   as long as this notice is preserved.  All standard disclaimers apply.
+//
+//   Ref: Seidel, R. (1991), "Small-dimensional linear programming and convex
+//        hulls made easy", Discrete & Computational Geometry 6 (1): 423-434,
+//        doi:10.1007/BF02574699
 #include <cmath>
 #include <limits>
 #include <vector>

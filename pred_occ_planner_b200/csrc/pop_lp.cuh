@@ -4,6 +4,29 @@
 // (traj_utils/include/traj_utils/sdlp.hpp:25-785 of the reference).  Constraint order comes
 // from a Fisher-Yates shuffle driven by a caller-provided 64-bit LCG state (the reference
 // shuffles with a function-static mt19937_64 whose state depends on global call history).
+//
+// The algorithm and its structure are those of sdlp.hpp, whose notices are preserved here as they ask:
+//
+//   Copyright (c) 1990 Michael E. Hohmeyer,
+//         hohmeyer@icemcfd.com
+//   Permission is granted to modify and re-distribute this code in any manner
+//   as long as this notice is preserved.  All standard disclaimers apply.
+//
+//   R. Seidel's algorithm for solving LPs (linear programs.)
+//
+//   Copyright (c) 2021 Zhepei Wang,
+//         wangzhepei@live.com
+//   1. Bug fix in "move_to_front" function that "prev[m]" is illegally accessed
+//      while "prev" originally has only m ints. It is fixed by allocating a
+//      "prev" with m + 1 ints.
+//   2. Add Eigen interface.
+//   3. Resursive template.
+//   Permission is granted to modify and re-distribute this code in any manner
+//   as long as this notice is preserved.  All standard disclaimers apply.
+//
+//   Ref: Seidel, R. (1991), "Small-dimensional linear programming and convex
+//        hulls made easy", Discrete & Computational Geometry 6 (1): 423-434,
+//        doi:10.1007/BF02574699
 #pragma once
 #include <cuda_runtime.h>
 #include <math.h>

@@ -42,6 +42,9 @@ METRIC = "agent-replans/s (SOGM+A*+corridor+QP cycle)"
 UNIT = "agent-replans/s"
 DT = 0.1          # replan period (10 Hz)
 LOOKAHEAD = 0.02  # traj_start_time - map stamp
+# N > 1: the allgather of cycle s overlaps cycle s+1 and is consumed by cycle s+2 — a broadcast one replan period in
+# flight, as the reference's "/broadcast_traj" messages are; POP_BENCH_EXCHANGE=strict makes every cycle wait for it
+PIPELINED = os.environ.get("POP_BENCH_EXCHANGE", "pipelined") == "pipelined"
 T0 = 100.0
 PREROLL = 2
 
@@ -304,7 +307,9 @@ def config_dict(sc, world, cloud_points, rec_bytes):
             "loop": "closed: obstacles move, agents track their planned trajectories, trajectories exchanged every step",
             "parallelism": f"agents sharded x{world}, one arena per GPU",
             "l2": "inputs larger than L2 (per-step SOGM writes %.2f GB per GPU)" % (c.n_agents_local * V * c.nt / 1e9),
-            "collective": "1 allgather of 1536 B trajectory records per cycle" if world > 1
+            "collective": ("1 allgather of 1536 B trajectory records per cycle"
+                           + (", pipelined: own records at once, the other ranks' arrive one cycle later "
+                              "(pop_exchange_trajs_pipelined)" if PIPELINED else ", consumed by the next cycle")) if world > 1
             else "single rank: device-to-device publish"}
 
 
@@ -420,7 +425,7 @@ def run_b200(args, rank, world, local_rank):
         eng.set_trajectories(np.zeros(n_total, p.TRAJ_DTYPE))
         # '/broadcast_traj': one allgather of fixed-size trajectory records per cycle, issued on the
         # current torch stream (= the engine's) straight between libpop's device buffers
-        xchg = p.swarm.TrajExchange(n_total, world, rank, engine=eng, device=local_rank)
+        xchg = p.swarm.TrajExchange(n_total, world, rank, engine=eng, device=local_rank, pipelined=PIPELINED)
         exchange = xchg.step
         if os.environ.get("POP_BENCH_EXCHANGE") == "local":   # diagnosis only: no collective
             exchange = eng.traj_publish_local
@@ -493,13 +498,21 @@ def run_b200(args, rank, world, local_rank):
     # ================= device-resident: the same script, nothing crosses PCIe =================
     eng, exchange = new_engine()
 
-    def resident_step(s):
+    marks = []   # (before the exchange, after it) per timed step: what a rank spends waiting for the others
+
+    def resident_step(s, mark=False):
         if s > 0:
             eng.swarm_advance(sc.t(s))
         eng.set_world_cloud_dev(d_clouds[s].data_ptr(), n_cloud)
         eng.set_cylinders_dev(d_cyls[s].data_ptr(), len(sc.cyl0), sc.max_abs_vy)
         eng.replan_cycle_resident(sc.t(s), sc.t(s) + LOOKAHEAD)
+        if mark:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
         exchange()
+        if mark:
+            e1.record(stream)
+            marks.append((e0, e1))
 
     # step 0 places the agents (host states once); afterwards everything stays on the device
     eng.set_world_cloud(h_clouds[0])
@@ -523,7 +536,7 @@ def run_b200(args, rank, world, local_rank):
     ev0.record(stream)
     host_t0 = time.perf_counter()
     for s in range(PREROLL + W, n_steps):
-        resident_step(s)
+        resident_step(s, mark=world > 1)
     host_enqueue_ms = 1e3 * (time.perf_counter() - host_t0) / K   # host time to enqueue one cycle
     ev1.record(stream)
     torch.cuda.synchronize()
@@ -535,6 +548,14 @@ def run_b200(args, rank, world, local_rank):
         tt = torch.tensor([ms_total], device="cuda", dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         ms_total = float(tt.item())
+        # own work per step = the step minus the time spent inside the exchange (waiting for the slowest rank)
+        own = ev0.elapsed_time(ev1) - sum(a.elapsed_time(b) for a, b in marks)
+        allown = torch.zeros(world, device="cuda", dtype=torch.float64)
+        allown[rank] = own / K
+        dist.all_reduce(allown)
+        own_ms_by_rank = [round(float(v), 3) for v in allown.tolist()]
+    else:
+        own_ms_by_rank = None
     stage_ms, stage_launches = eng.profile_read(True)
     launches = eng.kernel_launches() - launches0
     status, _ = eng.cycle_results()
@@ -577,6 +598,7 @@ def run_b200(args, rank, world, local_rank):
                          "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                          "algorithmic_bytes_per_step": int(alg_bytes), "ms_per_step": vox_ms},
             "stage_ms_serialised": {k: v / n_serial for k, v in serial_ms.items()},
+            "own_ms_per_step_by_rank": own_ms_by_rank,
             "stage_note": "untimed extra pass with the planning stages run one after the other over the whole batch; "
                           "in the timed region they are pipelined over agent groups on side streams",
             "replans_ok_frac": ok_frac,

@@ -325,12 +325,21 @@ int pop_traj_publish_local(pop_handle* h);
  *   pop_exchange_trajs   after a cycle: allgather of the records the cycle published (send buffer) into the table the
  *                        next map update projects (receive buffer), on the handle's stream, asynchronous.  Without a
  *                        communicator (single GPU) it is the device-to-device publish of pop_traj_publish_local.
+ *   pop_exchange_trajs_pipelined   the same allgather, one call behind: this rank's own records enter its table at
+ *                        once, the other ranks' records are those of the PREVIOUS call, whose allgather ran on a
+ *                        stream of its own while this rank planned the cycle in between.  A rank then waits for the
+ *                        slowest rank of the cycle before last instead of the last one — a broadcast in flight for one
+ *                        replan period, as "/broadcast_traj" messages are in the reference (the subscriber's callback
+ *                        runs whenever the message arrives, fake_plan_manager.cpp:364-399; records carry their own
+ *                        start time and are evaluated at absolute time, particles.cpp:131-191).  Every rank must use
+ *                        the same variant for every call.  Falls back to pop_exchange_trajs without a communicator.
  * NCCL is loaded at run time (libnccl.so.2); POP_E_UNSUPPORTED if it is not there. */
 #define POP_COMM_ID_BYTES 128
 int pop_comm_unique_id(void* id_out /* POP_COMM_ID_BYTES */);
 int pop_comm_init(pop_handle* h, const void* nccl_unique_id, int rank, int world);
 int pop_comm_info(const pop_handle* h, int* rank, int* world, int* nccl_version);
 int pop_exchange_trajs(pop_handle* h);
+int pop_exchange_trajs_pipelined(pop_handle* h);
 /* Device buffers for the per-cycle trajectory allgather ("/broadcast_traj",
  * plan_manager/src/fake_plan_manager.cpp:364-399 → particles.cpp:131-191):
  * *send_dev = n_agents_local records produced by the last cycle,

@@ -184,6 +184,7 @@ SYMBOLS = [
     ("pop_comm_init", _I, [_VP, _VP, _I, _I]),
     ("pop_comm_info", _I, [_VP, C.POINTER(_I), C.POINTER(_I), C.POINTER(_I)]),
     ("pop_exchange_trajs", _I, [_VP]),
+    ("pop_exchange_trajs_pipelined", _I, [_VP]),
     ("pop_set_poses", _I, [_VP, _PF]),
     ("pop_set_body_particles", _I, [_VP, _PD, _PI32]),
     ("pop_set_trajectories", _I, [_VP, C.POINTER(PopTrajRecord)]),

@@ -50,13 +50,50 @@ NcclApi& nccl() {
 struct CommDev {
   ncclComm_t comm = nullptr;
   int rank = 0, world = 1;
+  // pipelined exchange (pop_exchange_trajs_pipelined): the allgather runs on its own stream between private
+  // buffers, one call behind the cycle that consumes it
+  cudaStream_t cs = nullptr;
+  cudaEvent_t ev_send = nullptr, ev_snap = nullptr, ev_done[2] = {nullptr, nullptr};
+  pop_traj_record* snap[2] = {nullptr, nullptr};    // this rank's records as sent, per parity of the call
+  pop_traj_record* stage[2] = {nullptr, nullptr};   // all ranks' records as received
+  bool pending[2] = {false, false};
+  unsigned long long seq = 0;
 };
 
 void pop_comm_free(pop_handle* h) {
-  if (!h->comm) return;
-  if (h->comm->comm && nccl().ok) nccl().CommDestroy(h->comm->comm);
-  delete h->comm;
+  CommDev* c = h->comm;
+  if (!c) return;
+  if (c->cs) cudaStreamSynchronize(c->cs);   // an allgather in flight finishes before its communicator goes
+  if (c->comm && nccl().ok) nccl().CommDestroy(c->comm);
+  for (int k = 0; k < 2; k++) {
+    if (c->snap[k]) cudaFree(c->snap[k]);
+    if (c->stage[k]) cudaFree(c->stage[k]);
+    if (c->ev_done[k]) cudaEventDestroy(c->ev_done[k]);
+  }
+  if (c->ev_send) cudaEventDestroy(c->ev_send);
+  if (c->ev_snap) cudaEventDestroy(c->ev_snap);
+  if (c->cs) cudaStreamDestroy(c->cs);
+  delete c;
   h->comm = nullptr;
+}
+
+static int comm_pipeline_alloc(pop_handle* h) {
+  CommDev* c = h->comm;
+  if (c->cs) return POP_OK;
+  const pop_config& cfg = h->cfg;
+  bool ok = cudaStreamCreateWithFlags(&c->cs, cudaStreamNonBlocking) == cudaSuccess;
+  ok = ok && cudaEventCreateWithFlags(&c->ev_send, cudaEventDisableTiming) == cudaSuccess;
+  ok = ok && cudaEventCreateWithFlags(&c->ev_snap, cudaEventDisableTiming) == cudaSuccess;
+  for (int k = 0; k < 2 && ok; k++) {
+    ok = ok && cudaEventCreateWithFlags(&c->ev_done[k], cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaMalloc(&c->snap[k], sizeof(pop_traj_record) * cfg.n_agents_local) == cudaSuccess;
+    ok = ok && cudaMalloc(&c->stage[k], sizeof(pop_traj_record) * cfg.n_agents_total) == cudaSuccess;
+  }
+  if (!ok) {
+    cudaGetLastError();
+    return pop_fail(h, POP_E_CUDA, "pipelined exchange: stream / event / buffer allocation failed");
+  }
+  return POP_OK;
 }
 
 extern "C" {
@@ -119,6 +156,44 @@ int pop_exchange_trajs(pop_handle* h) {
   const ncclResult_t r = nccl().AllGather(h->d_traj_send, h->d_traj_all, sizeof(pop_traj_record) * c.n_agents_local, ncclUint8,
                                           h->comm->comm, h->stream);
   if (r != ncclSuccess) return pop_fail(h, POP_E_CUDA, "ncclAllGather failed: %s", nccl().GetErrorString(r));
+  h->have_traj = true;
+  return POP_OK;
+}
+
+int pop_exchange_trajs_pipelined(pop_handle* h) {
+  if (!h) return POP_E_INVALID;
+  PopDeviceGuard guard(h);
+  const pop_config& c = h->cfg;
+  if (!h->comm || h->comm->world == 1 || !h->comm->comm) return pop_exchange_trajs(h);
+  CommDev* cd = h->comm;
+  int rc = comm_pipeline_alloc(h);
+  if (rc) return rc;
+  const int nl = c.n_agents_local, nt = c.n_agents_total, base = c.agent_id_base;
+  const int cur = static_cast<int>(cd->seq & 1), prev = cur ^ 1;
+  // 1. this rank's own records are visible to its next map update at once
+  if ((rc = pop_traj_publish_local(h))) return rc;
+  // 2. the other ranks' records of the previous call (its allgather has had a whole cycle to complete)
+  if (cd->pending[prev]) {
+    POP_CUDA(h, cudaStreamWaitEvent(h->stream, cd->ev_done[prev], 0));
+    if (base > 0)
+      POP_CUDA(h, cudaMemcpyAsync(h->d_traj_all, cd->stage[prev], sizeof(pop_traj_record) * base, cudaMemcpyDeviceToDevice, h->stream));
+    if (base + nl < nt)
+      POP_CUDA(h, cudaMemcpyAsync(h->d_traj_all + base + nl, cd->stage[prev] + base + nl,
+                                  sizeof(pop_traj_record) * (nt - base - nl), cudaMemcpyDeviceToDevice, h->stream));
+    cd->pending[prev] = false;
+  }
+  // 3. snapshot what this cycle published (the next cycle overwrites the send buffer long before every rank has
+  //    arrived at this allgather) and start the allgather on the exchange stream
+  POP_CUDA(h, cudaEventRecord(cd->ev_send, h->stream));
+  POP_CUDA(h, cudaStreamWaitEvent(cd->cs, cd->ev_send, 0));
+  POP_CUDA(h, cudaMemcpyAsync(cd->snap[cur], h->d_traj_send, sizeof(pop_traj_record) * nl, cudaMemcpyDeviceToDevice, cd->cs));
+  POP_CUDA(h, cudaEventRecord(cd->ev_snap, cd->cs));
+  POP_CUDA(h, cudaStreamWaitEvent(h->stream, cd->ev_snap, 0));
+  const ncclResult_t r = nccl().AllGather(cd->snap[cur], cd->stage[cur], sizeof(pop_traj_record) * nl, ncclUint8, cd->comm, cd->cs);
+  if (r != ncclSuccess) return pop_fail(h, POP_E_CUDA, "ncclAllGather failed: %s", nccl().GetErrorString(r));
+  POP_CUDA(h, cudaEventRecord(cd->ev_done[cur], cd->cs));
+  cd->pending[cur] = true;
+  cd->seq++;
   h->have_traj = true;
   return POP_OK;
 }

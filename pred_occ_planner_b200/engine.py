@@ -277,9 +277,11 @@ class PopEngine:
         self._check(self.lib.pop_comm_info(self._h, C.byref(r), C.byref(w), C.byref(v)))
         return r.value, w.value, v.value
 
-    def exchange_trajs(self):
-        """one ncclAllGather of this cycle's trajectory records (or the local publish on a single GPU); async"""
-        self._check(self.lib.pop_exchange_trajs(self._h))
+    def exchange_trajs(self, pipelined: bool = False):
+        """one ncclAllGather of this cycle's trajectory records (or the local publish on a single GPU); async.
+        pipelined: own records at once, the other ranks' one call later (pop_exchange_trajs_pipelined)"""
+        fn = self.lib.pop_exchange_trajs_pipelined if pipelined else self.lib.pop_exchange_trajs
+        self._check(fn(self._h))
 
     def traj_buffers(self):
         s, r = C.c_void_p(), C.c_void_p()

@@ -49,8 +49,10 @@ class TrajExchange:
     (gloo) — the path the CPU tests exercise.
     """
 
-    def __init__(self, n_total: int, world: int, rank: int, engine=None, device: int | None = None, unique_id: bytes | None = None):
+    def __init__(self, n_total: int, world: int, rank: int, engine=None, device: int | None = None, unique_id: bytes | None = None,
+                 pipelined: bool = False):
         self.world, self.rank, self.n_total = world, rank, n_total
+        self.pipelined = pipelined   # device mode: pop_exchange_trajs_pipelined (remote records one cycle in flight)
         self.id_base, self.n_local = shard(n_total, world, rank)
         self.engine = engine
         self.bytes_per_cycle = self.n_local * RECORD_BYTES
@@ -75,7 +77,7 @@ class TrajExchange:
 
     def step(self, local_records: np.ndarray | None = None) -> np.ndarray | None:
         if self.engine is not None:
-            self.engine.exchange_trajs()
+            self.engine.exchange_trajs(self.pipelined)
             return None
         import torch
         import torch.distributed as dist

@@ -49,8 +49,18 @@ def main():
         tables.append(eng.get_trajectories())
         own.append(tr)
         assert (st == 0).all(), st
+    # three more cycles through the pipelined variant: own block fresh, the other rank's block one call behind
+    ptables, pown = [], []
+    for k in range(2, 5):
+        st, tr = eng.replan_cycle(start[sl], goal[sl], start[sl, :3].astype(np.float32), 10.0 + 0.1 * k, 10.02 + 0.1 * k)
+        eng.exchange_trajs(pipelined=True)
+        eng.sync()
+        ptables.append(eng.get_trajectories())
+        pown.append(tr)
     np.savez(os.path.join(d, f"rank{rank}.npz"), table0=tables[0].view(np.uint8), table1=tables[1].view(np.uint8),
-             own0=own[0].view(np.uint8), own1=own[1].view(np.uint8))
+             own0=own[0].view(np.uint8), own1=own[1].view(np.uint8),
+             **{f"ptable{k}": t.view(np.uint8) for k, t in enumerate(ptables)},
+             **{f"pown{k}": t.view(np.uint8) for k, t in enumerate(pown)})
     eng.close()
 
 

@@ -62,3 +62,15 @@ def test_two_rank_allgather(tmp_path):
         assert np.array_equal(tab[:3 * rec], r0[f"own{k}"]) and np.array_equal(tab[3 * rec:], r1[f"own{k}"])
     t1 = r0["table1"].view(p.TRAJ_DTYPE)
     assert (t1["n_pieces"] > 0).all() and sorted(t1["drone_id"].tolist()) == list(range(6))
+    # pipelined variant (pop_exchange_trajs_pipelined): a rank's own block is the cycle it just planned, the other
+    # rank's block is what that rank planned one call earlier (before the first pipelined call: the last strict table)
+    ranks = (r0, r1)
+    for me in (0, 1):
+        other = 1 - me
+        mine = slice(me * 3 * rec, (me + 1) * 3 * rec)
+        theirs = slice(other * 3 * rec, (other + 1) * 3 * rec)
+        for k in range(3):
+            tab = ranks[me][f"ptable{k}"]
+            assert np.array_equal(tab[mine], ranks[me][f"pown{k}"])
+            expect = ranks[other][f"pown{k - 1}"] if k > 0 else ranks[other]["own1"]
+            assert np.array_equal(tab[theirs], expect), (me, k)

@@ -22,7 +22,11 @@ namespace {
 constexpr int kRoleThreads = 96;            // three warps cover the 75 primitives
 constexpr int kThreads = 3 * kRoleThreads;  // lookup, gather and heuristic roles
 constexpr int kMaxPrim = 75;
-constexpr int kSmemNodes = 16384;  // f (double) + heap (int) = 12 B per node in shared memory
+constexpr int kSmemNodes = 16384;  // f (double) + heap slot (16-bit node id) = 10 B per node in shared memory: two
+                                   // searches of the default 10 000-node pool share an SM
+using HeapIdx = unsigned short;
+constexpr int kSmemBytesPerNode = 8 + sizeof(HeapIdx);
+static_assert(kSmemNodes <= 65536, "node ids must fit the heap slot");
 
 enum { IN_CLOSE_SET = 1, IN_OPEN_SET = 2, NOT_EXPAND = 3 };
 
@@ -199,7 +203,7 @@ __device__ __forceinline__ int query_dt(const PopGeom& g, const uint8_t* ag, con
 }
 
 // ---- open set: std::priority_queue<Node*, vector, NodeComparator{f1 > f2}> (libstdc++) --------
-__device__ __forceinline__ void heap_push_up(int* heap, const double* f, int hole, int top, int value) {
+__device__ __forceinline__ void heap_push_up(HeapIdx* heap, const double* f, int hole, int top, int value) {
   const double fv = f[value];
   int parent = (hole - 1) / 2;
   while (hole > top && f[heap[parent]] > fv) {
@@ -207,14 +211,14 @@ __device__ __forceinline__ void heap_push_up(int* heap, const double* f, int hol
     hole = parent;
     parent = (hole - 1) / 2;
   }
-  heap[hole] = value;
+  heap[hole] = static_cast<HeapIdx>(value);
 }
-__device__ void heap_push(int* heap, const double* f, int& size, int value) {
-  heap[size] = value;
+__device__ void heap_push(HeapIdx* heap, const double* f, int& size, int value) {
+  heap[size] = static_cast<HeapIdx>(value);
   size++;
   heap_push_up(heap, f, size - 1, 0, value);
 }
-__device__ void heap_pop(int* heap, const double* f, int& size) {
+__device__ void heap_pop(HeapIdx* heap, const double* f, int& size) {
   if (size > 1) {
     const int last = size - 1;
     const int value = heap[last];
@@ -253,7 +257,7 @@ __global__ void __launch_bounds__(kThreads) k_astar(PopGeom g, AstarParams P, As
                                                     const float* __restrict__ poses, int a0) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* f = reinterpret_cast<double*>(smem_raw);            // [cap]
-  int* heap = reinterpret_cast<int*>(f + P.cap);              // [cap]
+  HeapIdx* heap = reinterpret_cast<HeapIdx*>(f + P.cap);      // [cap]
   __shared__ Prim prim[kMaxPrim];
   __shared__ unsigned long long s_key[kMaxPrim];
   __shared__ double s_score[kMaxPrim], s_pg[kMaxPrim], s_pf[kMaxPrim];
@@ -715,7 +719,7 @@ int popk_astar_alloc(pop_handle* h) {
     POP_CUDA(h, cudaMemsetAsync(d->hkey, 0, nh * sizeof(unsigned long long), h->stream));
     POP_CUDA(h, cudaMemsetAsync(d->gen, 0, d->n_agents * sizeof(unsigned), h->stream));
     POP_CUDA(h, cudaMemsetAsync(d->d_path, 0, static_cast<size_t>(d->n_agents) * POP_MAX_PATH * 6 * sizeof(double), h->stream));
-    const size_t smem = static_cast<size_t>(d->cap) * 12 + 16;
+    const size_t smem = static_cast<size_t>(d->cap) * kSmemBytesPerNode + 16;
     POP_CUDA(h, cudaFuncSetAttribute(k_astar<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     POP_CUDA(h, cudaFuncSetAttribute(k_astar<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     return POP_OK;
@@ -748,7 +752,7 @@ int popk_astar_run(pop_handle* h, cudaStream_t st, int a0, int na) {
   P.tie_breaker = 1.0 + 1.0 / 10000;
   P.corridor_tau = c.corridor_tau;
   P.cap = d->cap; P.check_num = c.check_num; P.tolerance = c.tolerance; P.hash_mask = d->hash_cap - 1;
-  const size_t smem = static_cast<size_t>(d->cap) * 12 + 16;
+  const size_t smem = static_cast<size_t>(d->cap) * kSmemBytesPerNode + 16;
   pop_prof_begin(h, POP_STAGE_ASTAR);
   if (c.cell_dtype == POP_CELL_U8)
     k_astar<uint8_t><<<na, kThreads, smem, st>>>(h->geom, P, *d, h->d_grid, h->d_poses, a0);

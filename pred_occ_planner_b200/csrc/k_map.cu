@@ -425,20 +425,20 @@ __device__ __forceinline__ int vox_future_layer(const PopGeom& g, int iz, float 
   return (l >= 0 && l < g.nz) ? l : -1;
 }
 
-__global__ void __launch_bounds__(256) k_vox_count(PopGeom g, int H, int nbands, const float* __restrict__ cloud,
+__global__ void __launch_bounds__(256) k_vox_count(PopGeom g, int S, int nstrips, const float* __restrict__ cloud,
                                                    int n_cloud, const float* __restrict__ poses,
                                                    int* __restrict__ cnt) {
   const int a = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_cloud) return;
   const float posez = poses[3 * a + 2];
-  const int nkeys = g.nz * nbands;
+  const int nkeys = g.nz * nstrips;
   int ix, iy, iz;
   if (!vox_point(g, cloud, i, poses[3 * a], poses[3 * a + 1], posez, &ix, &iy, &iz)) return;
-  const int band = iy / H;
-  atomicAdd(&cnt[(a * 2 + 0) * nkeys + iz * nbands + band], 1);
+  const int strip = iy / S;
+  atomicAdd(&cnt[(a * 2 + 0) * nkeys + iz * nstrips + strip], 1);
   if (1.0f > g.risk_threshold) {   // tmp[i][0] > risk_threshold_ (fake_particle_risk_voxel.cpp:121)
     const int lf = vox_future_layer(g, iz, posez);
-    if (lf >= 0) atomicAdd(&cnt[(a * 2 + 1) * nkeys + lf * nbands + band], 1);
+    if (lf >= 0) atomicAdd(&cnt[(a * 2 + 1) * nkeys + lf * nstrips + strip], 1);
   }
 }
 
@@ -467,7 +467,7 @@ __global__ void __launch_bounds__(256) k_vox_scan(int nkeys, int cap, const int*
   }
 }
 
-__global__ void __launch_bounds__(256) k_vox_fill(PopGeom g, int H, int nbands, const float* __restrict__ cloud,
+__global__ void __launch_bounds__(256) k_vox_fill(PopGeom g, int S, int nstrips, const float* __restrict__ cloud,
                                                   int n_cloud, const float* __restrict__ poses,
                                                   const PopCylDev* __restrict__ cyl, int n_cyl,
                                                   const int* __restrict__ off, int* __restrict__ cur,
@@ -479,12 +479,12 @@ __global__ void __launch_bounds__(256) k_vox_fill(PopGeom g, int H, int nbands, 
   const int a = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_cloud) return;
   const float posex = poses[3 * a], posey = poses[3 * a + 1], posez = poses[3 * a + 2];
-  const int nkeys = g.nz * nbands;
+  const int nkeys = g.nz * nstrips;
   int ix, iy, iz;
   if (!vox_point(g, cloud, i, posex, posey, posez, &ix, &iy, &iz)) return;
-  const int band = iy / H;
+  const int strip = iy / S;
   {
-    const int l = a * 2 + 0, key = iz * nbands + band;
+    const int l = a * 2 + 0, key = iz * nstrips + strip;
     const int pos = off[l * (nkeys + 1) + key] + atomicAdd(&cur[l * nkeys + key], 1);
     if (pos < cap) ent0[static_cast<size_t>(a) * cap + pos] = static_cast<unsigned>(iy * g.nx + ix);
   }
@@ -497,7 +497,7 @@ __global__ void __launch_bounds__(256) k_vox_fill(PopGeom g, int H, int nbands, 
   const float ptz = geom_axis_position(iz, g.rz, g.res, posez);
   const int own = geom_gt_owner(g, scyl, n_cyl, ptx, pty, ptz);
   const unsigned owner = own >= 0 ? static_cast<unsigned>(own) : 0xffffu;
-  const int l = a * 2 + 1, key = lf * nbands + band;
+  const int l = a * 2 + 1, key = lf * nstrips + strip;
   const int pos = off[l * (nkeys + 1) + key] + atomicAdd(&cur[l * nkeys + key], 1);
   if (pos < cap)
     entf[static_cast<size_t>(a) * cap + pos] = static_cast<unsigned long long>(ix) |
@@ -519,7 +519,8 @@ static int tile_max_bytes() {
   return v;
 }
 
-__global__ void __launch_bounds__(kTileThreads) k_vox_tiles(PopGeom g, int H, int nbands, float reach_per_slice,
+__global__ void __launch_bounds__(kTileThreads) k_vox_tiles(PopGeom g, int H, int nbands, int S, int nstrips,
+                                                               float reach_per_slice,
                                                                uint8_t* __restrict__ grid, int n_agents,
                                                                const float* __restrict__ poses,
                                                                const PopCylDev* __restrict__ cyl, int n_cyl,
@@ -532,13 +533,13 @@ __global__ void __launch_bounds__(kTileThreads) k_vox_tiles(PopGeom g, int H, in
   float2* svel = reinterpret_cast<float2*>(tile + tile_max);   // cylinder velocities
   for (int c = threadIdx.x; c < n_cyl; c += blockDim.x) svel[c] = make_float2(cyl[c].vx, cyl[c].vy);
   const unsigned smem = static_cast<unsigned>(__cvta_generic_to_shared(tile));
-  const int nkeys = g.nz * nbands;
-  const long long units = static_cast<long long>(n_agents) * g.nt * nkeys;
+  const int nkeys = g.nz * nstrips, nunits = g.nz * nbands, spb = H / S;   // strips per band (S divides H)
+  const long long units = static_cast<long long>(n_agents) * g.nt * nunits;
   for (long long u = blockIdx.x; u < units; u += gridDim.x) {
     const int band = static_cast<int>(u % nbands);
     const int iz = static_cast<int>((u / nbands) % g.nz);
-    const int k = static_cast<int>((u / nkeys) % g.nt);
-    const int a = static_cast<int>(u / (static_cast<long long>(nkeys) * g.nt));
+    const int k = static_cast<int>((u / nunits) % g.nt);
+    const int a = static_cast<int>(u / (static_cast<long long>(nunits) * g.nt));
     const int y0 = band * H, rows = min(H, g.ny - y0), bytes = rows * g.nx;
     // the previous unit's bulk stores must have finished READING the tile before it is rebuilt
     if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
@@ -547,21 +548,20 @@ __global__ void __launch_bounds__(kTileThreads) k_vox_tiles(PopGeom g, int H, in
       *reinterpret_cast<uint4*>(tile + i) = make_uint4(0, 0, 0, 0);
     __syncthreads();
     if (k == 0) {
-      const int* o = off + (a * 2 + 0) * (nkeys + 1) + iz * nbands + band;
+      const int* o = off + (a * 2 + 0) * (nkeys + 1) + iz * nstrips;   // the strips of one layer are consecutive keys
       const unsigned* e = ent0 + static_cast<size_t>(a) * cap;
-      const int e1 = o[1], base = y0 * g.nx;
-      for (int q = o[0] + threadIdx.x; q < e1; q += kTileThreads) tile[e[q] - base] = 1;
+      const int e1 = o[min(nstrips, (band + 1) * spb)], base = y0 * g.nx;
+      for (int q = o[band * spb] + threadIdx.x; q < e1; q += kTileThreads) tile[e[q] - base] = 1;
     } else {
-      // source bands whose voxels can land in this band after k slices
-      const int r = static_cast<int>((reach_per_slice * static_cast<float>(k) + 2.0f) / static_cast<float>(H)) + 1;
-      const int b0 = max(0, band - r), b1 = min(nbands - 1, band + r);
-      const int* o = off + (a * 2 + 1) * (nkeys + 1) + iz * nbands;
-      const int e0 = o[b0], e1 = o[b1 + 1];   // the keys of one layer are consecutive
+      // source strips whose voxels can land in this band after k slices: |dy| <= reach*k rows (+2 for rounding)
+      const int dr = static_cast<int>(reach_per_slice * static_cast<float>(k) + 2.0f) + 1;
+      const int s0 = max(0, (y0 - dr) / S), s1 = min(nstrips - 1, (y0 + rows - 1 + dr) / S);
+      const int* o = off + (a * 2 + 1) * (nkeys + 1) + iz * nstrips;
+      const int e0 = o[s0], e1 = o[s1 + 1];   // the keys of one layer are consecutive
       const unsigned long long* e = entf + static_cast<size_t>(a) * cap;
       const float posex = poses[3 * a], posey = poses[3 * a + 1];
       const float kf = static_cast<float>(k);
-      for (int q = e0 + threadIdx.x; q < e1; q += kTileThreads) {
-        const unsigned long long v = e[q];
+      auto place = [&](unsigned long long v) {
         const int ix = static_cast<int>(v & 0xffffu), iy = static_cast<int>((v >> 16) & 0xffffu);
         const unsigned owner = static_cast<unsigned>(v >> 32) & 0xffffu;
         float vx = 0.f, vy = 0.f;
@@ -570,11 +570,19 @@ __global__ void __launch_bounds__(kTileThreads) k_vox_tiles(PopGeom g, int H, in
         const float pty = geom_axis_position(iy, g.ry, g.res, posey);
         const float qx = __fsub_rn(__fadd_rn(ptx, __fmul_rn(__fmul_rn(vx, g.dt), kf)), posex);
         const float qy = __fsub_rn(__fadd_rn(pty, __fmul_rn(__fmul_rn(vy, g.dt), kf)), posey);
-        if (!(qx > -g.rx && qx < g.rx && qy > -g.ry && qy < g.ry)) continue;
+        if (!(qx > -g.rx && qx < g.rx && qy > -g.ry && qy < g.ry)) return;
         const int jx = geom_axis_index(qx, g.rx, g.res), jy = geom_axis_index(qy, g.ry, g.res) - y0;
-        if (jx < 0 || jx >= g.nx || jy < 0 || jy >= rows) continue;
+        if (jx < 0 || jx >= g.nx || jy < 0 || jy >= rows) return;
         tile[jy * g.nx + jx] = 1;
+      };
+      // four entries in flight per thread: the list comes from L2/HBM and one dependent load per iteration
+      // left the tile build, not the bulk store, as the longer half of a unit on dense clouds (config 3)
+      int q = e0 + threadIdx.x;
+      for (; q + 3 * kTileThreads < e1; q += 4 * kTileThreads) {
+        const unsigned long long v0 = e[q], v1 = e[q + kTileThreads], v2 = e[q + 2 * kTileThreads], v3 = e[q + 3 * kTileThreads];
+        place(v0); place(v1); place(v2); place(v3);
       }
+      for (; q < e1; q += kTileThreads) place(e[q]);
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
@@ -625,7 +633,12 @@ static bool vox_tiles_ok(const pop_handle* h) {
 static int vox_update_tiles(pop_handle* h, int sms, int* launches) {
   const PopGeom& g = h->geom;
   const int nl = h->cfg.n_agents_local, cap = h->cfg.max_cloud_points;
-  const int H = vox_band_rows(g), nbands = (g.ny + H - 1) / H, nkeys = g.nz * nbands;
+  const int H = vox_band_rows(g), nbands = (g.ny + H - 1) / H;
+  // the entry lists are keyed by (layer, strip of S rows); S divides H so a band is a whole number of strips, and a
+  // band's unit reads only the strips within reach of its rows instead of whole neighbouring bands
+  int S = H;
+  if (nbands > 1) for (int c = 32; c >= 1; c--) if (H % c == 0) { S = c; break; }
+  const int nstrips = (g.ny + S - 1) / S, nkeys = g.nz * nstrips;
   const int smem = ((g.nx * H + 127) & ~127) + static_cast<int>(sizeof(float2)) * (h->cfg.max_cylinders + 1);
   if (!h->vox) {
     VoxDev* d = new VoxDev();
@@ -644,7 +657,7 @@ static int vox_update_tiles(pop_handle* h, int sms, int* launches) {
   POP_CUDA(h, cudaMemsetAsync(d->cnt, 0, sizeof(int) * nl * 2 * nkeys, h->stream));
   if (h->n_cloud > 0) {
     dim3 grid((h->n_cloud + 255) / 256, nl);
-    k_vox_count<<<grid, 256, 0, h->stream>>>(g, H, nbands, h->d_cloud, h->n_cloud, h->d_poses, d->cnt);
+    k_vox_count<<<grid, 256, 0, h->stream>>>(g, S, nstrips, h->d_cloud, h->n_cloud, h->d_poses, d->cnt);
     POP_LAUNCH_CHECK(h);
     (*launches)++;
   }
@@ -654,7 +667,7 @@ static int vox_update_tiles(pop_handle* h, int sms, int* launches) {
   if (h->n_cloud > 0) {
     dim3 grid((h->n_cloud + 255) / 256, nl);
     const size_t sm = sizeof(PopCylDev) * (h->n_cyl > 0 ? h->n_cyl : 1);
-    k_vox_fill<<<grid, 256, sm, h->stream>>>(g, H, nbands, h->d_cloud, h->n_cloud, h->d_poses, h->d_cyl, h->n_cyl,
+    k_vox_fill<<<grid, 256, sm, h->stream>>>(g, S, nstrips, h->d_cloud, h->n_cloud, h->d_poses, h->d_cyl, h->n_cyl,
                                              d->off, d->cur, d->ent0, d->entf, cap);
     POP_LAUNCH_CHECK(h);
     (*launches)++;
@@ -667,7 +680,7 @@ static int vox_update_tiles(pop_handle* h, int sms, int* launches) {
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_vox_tiles, kTileThreads, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
     if (per_sm > 8) per_sm = 8;
   }
-  k_vox_tiles<<<per_sm * sms, kTileThreads, smem, h->stream>>>(g, H, nbands, reach, h->d_grid, nl, h->d_poses, h->d_cyl,
+  k_vox_tiles<<<per_sm * sms, kTileThreads, smem, h->stream>>>(g, H, nbands, S, nstrips, reach, h->d_grid, nl, h->d_poses, h->d_cyl,
                                                          h->n_cyl, d->off, d->ent0, d->entf, cap);
   POP_LAUNCH_CHECK(h);
   (*launches)++;

@@ -66,7 +66,8 @@ CONFIGS = {
 
 def arena_origin(rank: int, world: int, pitch: float):
     """Centre of rank `rank`'s arena: slot `rank` of a side x side tiling (side = ceil(sqrt(world))) centred on the
-    origin, row-major.  POP_BENCH_ARENA_SHIFT (diagnosis) moves every arena further out along x by that many pitches."""
+    origin, row-major.  Stacking arenas in z would keep them closer to the origin, but the reference's corridor stage
+    clamps its boxes to z in [0, 4] m (baseline_fake.cpp:324-325), so every arena has to stay on the ground floor.  POP_BENCH_ARENA_SHIFT (diagnosis) moves every arena further out along x by that many pitches."""
     side = 1
     while side * side < world:
         side += 1

@@ -85,6 +85,21 @@ class Engine {
   }
   void publishLocal() { check(pop_traj_publish_local(h_)); }
   void advance(double t_next) { check(pop_swarm_advance(h_, t_next)); }
+  // "/broadcast_traj" over several GPUs: one handle per GPU (a process or a host thread each), rank 0 makes the id
+  static std::vector<uint8_t> commUniqueId() {
+    std::vector<uint8_t> id(POP_COMM_ID_BYTES);
+    const int rc = pop_comm_unique_id(id.data());
+    if (rc != POP_OK) throw Error(rc, "pop_comm_unique_id failed (libnccl.so.2 not loadable?)");
+    return id;
+  }
+  void commInit(const std::vector<uint8_t>& id, int rank, int world) { check(pop_comm_init(h_, world > 1 ? id.data() : nullptr, rank, world)); }
+  // after a cycle: the allgather of its records; pipelined = the other ranks' records arrive one call later
+  void exchange(bool pipelined = false) { check(pipelined ? pop_exchange_trajs_pipelined(h_) : pop_exchange_trajs(h_)); }
+  std::vector<pop_traj_record> trajectories() {
+    std::vector<pop_traj_record> t(cfg_.n_agents_total);
+    check(pop_get_trajectories(h_, t.data()));
+    return t;
+  }
 
  private:
   pop_config cfg_;

@@ -333,10 +333,10 @@ static int cycle_enqueue(pop_handle* h, double t_map, double t_plan, bool update
     for (int gi = 0; gi < n_groups; gi++) POP_CUDA(h, cudaStreamWaitEvent(h->side[gi], h->fork_ev, 0));
   }
   const int per = (nl + n_groups - 1) / n_groups;
-  for (int gi = 0; gi < n_groups; gi++) {
-    const int a0 = gi * per, na = min(per, nl - a0);
-    if (na <= 0) break;
-    cudaStream_t st = n_groups > 1 ? h->side[gi] : h->stream;
+  // one group's chain on its stream; a failure part-way leaves work queued on the side streams, so the caller below
+  // joins every stream that was forked before reporting it (the handle's stream then still orders after all of it)
+  auto enqueue_group = [&](int gi, int a0, int na, cudaStream_t st) -> int {
+    int rc;
     if ((rc = popk_astar_run(h, st, a0, na))) return rc;
     if ((rc = popk_corridor_run(h, popk_astar_path_dev(h), popk_astar_len_dev(h), popk_astar_start_dev(h), st, a0, na))) return rc;
     k_prepare_qp<<<(na + 127) / 128, 128, 0, st>>>(a0, a0 + na, c.corridor_tau, popk_astar_start_dev(h),
@@ -353,11 +353,20 @@ static int cycle_enqueue(pop_handle* h, double t_map, double t_plan, bool update
                                                 popk_qp_cpts_dev(h), d->status, h->d_traj_send, d->traj_ids);
     POP_LAUNCH_CHECK(h);
     h->n_launches += 2;   // k_prepare_qp + k_finalize
-    if (n_groups > 1) {
-      POP_CUDA(h, cudaEventRecord(h->side_done[gi], st));
-      POP_CUDA(h, cudaStreamWaitEvent(h->stream, h->side_done[gi], 0));
+    return POP_OK;
+  };
+  int first_error = POP_OK;
+  for (int gi = 0; gi < n_groups; gi++) {
+    const int a0 = gi * per, na = min(per, nl - a0);
+    if (na <= 0) break;
+    cudaStream_t st = n_groups > 1 ? h->side[gi] : h->stream;
+    if (first_error == POP_OK) first_error = enqueue_group(gi, a0, na, st);
+    if (n_groups > 1) {   // also after an error: every forked stream is joined
+      cudaEventRecord(h->side_done[gi], st);
+      cudaStreamWaitEvent(h->stream, h->side_done[gi], 0);
     }
   }
+  if (first_error != POP_OK) return first_error;
   h->n_launches += 1;   // k_fill_times
   return POP_OK;
 }

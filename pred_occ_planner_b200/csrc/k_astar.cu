@@ -252,7 +252,7 @@ struct Prim {  // per-primitive scratch in shared memory
 enum { EV_NONE = 0, EV_NEW, EV_LOWER, EV_UPD, EV_ERR };
 
 template <typename C>
-__global__ void __launch_bounds__(kThreads) k_astar(PopGeom g, AstarParams P, AstarDev D,
+__global__ void __launch_bounds__(kThreads, 1) k_astar(PopGeom g, AstarParams P, AstarDev D,
                                                     const uint8_t* __restrict__ grid,
                                                     const float* __restrict__ poses, int a0) {
   extern __shared__ __align__(16) unsigned char smem_raw[];

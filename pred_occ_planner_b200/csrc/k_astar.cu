@@ -679,6 +679,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_astar(PopGeom g, AstarParams P,
 }  // namespace
 
 // ---- host side -----------------------------------------------------------------------------------
+#ifndef POP_ASTAR_DEVICE_ONLY   // scripts/ubench/heur_lat.cu includes the device code alone
 int popk_astar_alloc(pop_handle* h) {
   if (h->astar) return POP_OK;
   const pop_config& c = h->cfg;
@@ -794,3 +795,4 @@ extern "C" int pop_astar_search_batch(pop_handle* h, const double* start, const 
     if (out_len[i] < 0) return pop_fail(h, POP_E_CAPACITY, "agent %d: A* path longer than POP_MAX_PATH=%d samples", i, POP_MAX_PATH);
   return POP_OK;
 }
+#endif  // POP_ASTAR_DEVICE_ONLY

@@ -650,7 +650,7 @@ static int vox_update_tiles(pop_handle* h, int sms, int* launches) {
     ok &= cudaMalloc(&d->cur, sizeof(int) * nl * 2 * nkeys) == cudaSuccess;
     ok &= cudaMalloc(&d->ent0, sizeof(unsigned) * static_cast<size_t>(nl) * cap) == cudaSuccess;
     ok &= cudaMalloc(&d->entf, sizeof(unsigned long long) * static_cast<size_t>(nl) * cap) == cudaSuccess;
-    if (!ok) { cudaGetLastError(); return pop_fail(h, POP_E_CUDA, "voxel-update entry lists allocation failed"); }
+    if (!ok) { cudaGetLastError(); popk_vox_free(h); return pop_fail(h, POP_E_CUDA, "voxel-update entry lists allocation failed"); }
     POP_CUDA(h, cudaFuncSetAttribute(k_vox_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   }
   VoxDev* d = h->vox;

@@ -320,8 +320,7 @@ def dsp_leg(stream, device, with_cpu, n_agents=64, frames=20, warm=5):
     for 64 agents at the reference's own grid (66x66x20 @0.15 m, 6 future slices): one pop_dsp_update per frame
     with HOST camera clouds (host->device copies inside the timed region), the sequential oracle beside it."""
     import pred_occ_planner_b200 as p
-    from pred_occ_planner_b200 import dsp, worldgen
-    from tests import cases
+    from pred_occ_planner_b200 import dsp, worldgen, scenes as cases
     import torch
     cfg = cases.dsp_cfg_ref(n_local=n_agents, n_total=n_agents)
     d = cases.dsp_params(cfg)

@@ -6,6 +6,6 @@ from ._lib import (POP_CELL_F32, POP_CELL_U8, POP_KERNEL_CUBE, POP_KERNEL_DISC_Z
                    POP_MAX_FACES, POP_MAX_PATH, POP_MAX_PIECES, POP_QUERY_FAKE, POP_QUERY_RISKBASE,
                    CYL_DTYPE, TRAJ_DTYPE, PopConfig, PopDspConfig, PopGridmapConfig, PopError, default_config, load)
 from .engine import AgentMap, PopEngine
-from . import dsp, gridmap, swarm, wire, worldgen
+from . import dsp, gridmap, scenes, swarm, wire, worldgen
 
 __all__ = ["PopEngine", "AgentMap", "PopConfig", "PopError", "default_config", "load", "dsp", "gridmap", "swarm", "wire", "worldgen"]

@@ -16,13 +16,100 @@ constexpr int kSepDoubles = 5 * kSepRows + poplp::work_doubles(kSepRows, 4);
 constexpr int kSepInts = poplp::work_ints(kSepRows);
 constexpr int kSepWarps = 148 * 8;
 
-// one warp (lane 0) per (ego, peer) pair, grid-stride over pairs
-// Agents [a0, a0 + n_local) against every peer; warp w of this launch works in workspace slot w0 + w.
-__global__ void __launch_bounds__(128) k_separate(int a0, int w0, int n_local, int n_total, int id_base, double t0,
-                                                  const int* __restrict__ n_pieces, const int* __restrict__ qp_status,
-                                                  const double* __restrict__ cpts,
-                                                  const pop_traj_record* __restrict__ trajs, double* __restrict__ wd,
-                                                  int* __restrict__ wi, int* __restrict__ safe) {
+// The point sets of one (ego, peer) pair — the ego's new control points and the peer's from the piece that is current at
+// t0 on — or false when there is nothing to separate (no trajectory, failed QP, peer not active at t0).
+struct SepPair {
+  const double* A; const double* B;
+  int na, nb, a;
+};
+__device__ __forceinline__ bool sep_sets(int a0, int n_total, int id_base, double t0, long long pair,
+                                         const int* __restrict__ n_pieces, const int* __restrict__ qp_status,
+                                         const double* __restrict__ cpts, const pop_traj_record* __restrict__ trajs,
+                                         SepPair* out) {
+  const int a = a0 + static_cast<int>(pair / n_total), i = static_cast<int>(pair % n_total);
+  if (i == id_base + a) return false;
+  const int M = n_pieces[a];
+  const int st = qp_status[a];
+  if (M <= 0 || !(st == 1 || st == 2)) return false;
+  const pop_traj_record& r = trajs[i];
+  if (r.n_pieces <= 0 || r.n_pieces > POP_MAX_PIECES) return false;
+  double t_end = r.start_time;
+  for (int k = 0; k < r.n_pieces; k++) t_end += r.duration[k];
+  if (!(r.start_time < t0 && t0 < t_end)) return false;
+  double rem = t0 - r.start_time;  // Bezier::locatePiece
+  int piece = r.n_pieces - 1;
+  for (int k = 0; k < r.n_pieces; k++) {
+    rem -= static_cast<double>(r.duration[k]);
+    if (rem < 0) { piece = k; break; }
+  }
+  const double* A = cpts + static_cast<size_t>(a) * POP_MAX_PIECES * 15;
+  const int na = 5 * M, nb = (r.n_pieces - piece) * 5;
+  const double* B = r.cpts + piece * 15;
+  out->A = A; out->B = B; out->na = na; out->nb = nb; out->a = a;
+  return true;
+}
+// Screening of a pair's point sets: 0 = safe without the solver (an axis-aligned gap, or the centroid-direction
+// certificate holds), 1 = the LP has to decide.
+__device__ __forceinline__ int sep_screen(const SepPair& sp) {
+  const double* A = sp.A; const double* B = sp.B;
+  const int na = sp.na, nb = sp.nb;
+  // axis-aligned gap: an LP with margin 1 inside |n|,|d| <= 1e4 is feasible for any gap > 2e-4
+  double amin[3] = {1e300, 1e300, 1e300}, amax[3] = {-1e300, -1e300, -1e300};
+  double bmin[3] = {1e300, 1e300, 1e300}, bmax[3] = {-1e300, -1e300, -1e300};
+  for (int k = 0; k < na; k++) for (int q = 0; q < 3; q++) { amin[q] = fmin(amin[q], A[k * 3 + q]); amax[q] = fmax(amax[q], A[k * 3 + q]); }
+  for (int k = 0; k < nb; k++) for (int q = 0; q < 3; q++) { bmin[q] = fmin(bmin[q], B[k * 3 + q]); bmax[q] = fmax(bmax[q], B[k * 3 + q]); }
+  for (int q = 0; q < 3; q++) if (bmin[q] - amax[q] > 1e-2 || amin[q] - bmax[q] > 1e-2) return 0;
+  // GLPK's variables are free, so the reference's answer does not depend on where the pair sits; inside the box
+  // of the LP that only holds with the points taken relative to one of them (A's first), which keeps d small.
+  const double o[3] = {A[0], A[1], A[2]};
+  // Certificate before the LP: along u = centroid(A) - centroid(B), n = 2 (1 + 1e-9) u / gap and d halfway between the
+  // two sets.  If this (n, d) satisfies every row of the LP — checked row by row, in double, with the box — the LP is
+  // feasible and the pair is safe; the solver is only needed for pairs that nearly touch or interpenetrate.
+  double ca[3] = {0, 0, 0}, cb[3] = {0, 0, 0};
+  for (int k = 0; k < na; k++) for (int q = 0; q < 3; q++) ca[q] += A[k * 3 + q] - o[q];
+  for (int k = 0; k < nb; k++) for (int q = 0; q < 3; q++) cb[q] += B[k * 3 + q] - o[q];
+  double u[3];
+  for (int q = 0; q < 3; q++) u[q] = ca[q] / na - cb[q] / nb;
+  double lo_a = 1e300, hi_b = -1e300;
+  for (int k = 0; k < na; k++) lo_a = fmin(lo_a, u[0] * (A[k * 3] - o[0]) + u[1] * (A[k * 3 + 1] - o[1]) + u[2] * (A[k * 3 + 2] - o[2]));
+  for (int k = 0; k < nb; k++) hi_b = fmax(hi_b, u[0] * (B[k * 3] - o[0]) + u[1] * (B[k * 3 + 1] - o[1]) + u[2] * (B[k * 3 + 2] - o[2]));
+  const double gap = lo_a - hi_b;
+  if (gap > 0.0) {
+    const double sc = 2.0 * (1.0 + 1e-9) / gap;
+    const double nn[3] = {sc * u[0], sc * u[1], sc * u[2]};
+    const double dd = -0.5 * sc * (lo_a + hi_b);
+    bool ok = fabs(nn[0]) <= 9.99e3 && fabs(nn[1]) <= 9.99e3 && fabs(nn[2]) <= 9.99e3 && fabs(dd) <= 9.99e3;
+    for (int k = 0; ok && k < na; k++) ok = nn[0] * (A[k * 3] - o[0]) + nn[1] * (A[k * 3 + 1] - o[1]) + nn[2] * (A[k * 3 + 2] - o[2]) + dd >= 1.0;
+    for (int k = 0; ok && k < nb; k++) ok = nn[0] * (B[k * 3] - o[0]) + nn[1] * (B[k * 3 + 1] - o[1]) + nn[2] * (B[k * 3 + 2] - o[2]) + dd <= -1.0;
+    if (ok) return 0;
+  }
+  return 1;
+}
+
+// Separation in two launches.  k_sep_screen: one thread per (ego, peer) pair — almost every pair of a swarm is settled
+// there; the pairs that nearly touch are appended to the launch's list.  k_sep_lp: one warp (lane 0: Seidel's LP is a
+// sequential algorithm) per listed pair, so the few LPs of a cycle run side by side instead of behind one another.
+// Agents [a0, a0 + n_local) against every peer; list and counter of the launch are those of agent a0.
+__global__ void __launch_bounds__(128) k_sep_screen(int a0, int n_local, int n_total, int id_base, double t0,
+                                                    const int* __restrict__ n_pieces, const int* __restrict__ qp_status,
+                                                    const double* __restrict__ cpts,
+                                                    const pop_traj_record* __restrict__ trajs, int* __restrict__ list,
+                                                    int* __restrict__ count) {
+  const long long pair = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (pair >= static_cast<long long>(n_local) * n_total) return;
+  SepPair sp;
+  if (!sep_sets(a0, n_total, id_base, t0, pair, n_pieces, qp_status, cpts, trajs, &sp)) return;
+  if (!sep_screen(sp)) return;
+  list[static_cast<size_t>(a0) * n_total + atomicAdd(&count[a0], 1)] = static_cast<int>(pair);
+}
+
+// warp w of this launch works in workspace slot w0 + w
+__global__ void __launch_bounds__(128) k_sep_lp(int a0, int w0, int n_total, int id_base, double t0,
+                                                const int* __restrict__ n_pieces, const int* __restrict__ qp_status,
+                                                const double* __restrict__ cpts,
+                                                const pop_traj_record* __restrict__ trajs, const int* __restrict__ list,
+                                                const int* __restrict__ count, double* __restrict__ wd,
+                                                int* __restrict__ wi, int* __restrict__ safe) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if ((threadIdx.x & 31) != 0) return;
   const int total_warps = (gridDim.x * blockDim.x) >> 5;
@@ -30,60 +117,13 @@ __global__ void __launch_bounds__(128) k_separate(int a0, int w0, int n_local, i
   double* rhs = rowsM + 4 * kSepRows;
   double* lpw = rhs + kSepRows;
   int* lpi = wi + static_cast<size_t>(w0 + warp) * kSepInts;
-  for (long long pair = warp; pair < static_cast<long long>(n_local) * n_total; pair += total_warps) {
-    const int a = a0 + static_cast<int>(pair / n_total), i = static_cast<int>(pair % n_total);
-    if (i == id_base + a) continue;
-    const int M = n_pieces[a];
-    const int st = qp_status[a];
-    if (M <= 0 || !(st == 1 || st == 2)) continue;
-    const pop_traj_record& r = trajs[i];
-    if (r.n_pieces <= 0 || r.n_pieces > POP_MAX_PIECES) continue;
-    double t_end = r.start_time;
-    for (int k = 0; k < r.n_pieces; k++) t_end += r.duration[k];
-    if (!(r.start_time < t0 && t0 < t_end)) continue;
-    double rem = t0 - r.start_time;  // Bezier::locatePiece
-    int piece = r.n_pieces - 1;
-    for (int k = 0; k < r.n_pieces; k++) {
-      rem -= static_cast<double>(r.duration[k]);
-      if (rem < 0) { piece = k; break; }
-    }
-    const double* A = cpts + static_cast<size_t>(a) * POP_MAX_PIECES * 15;
-    const int na = 5 * M, nb = (r.n_pieces - piece) * 5;
-    const double* B = r.cpts + piece * 15;
-    // axis-aligned gap: an LP with margin 1 inside |n|,|d| <= 1e4 is feasible for any gap > 2e-4
-    double amin[3] = {1e300, 1e300, 1e300}, amax[3] = {-1e300, -1e300, -1e300};
-    double bmin[3] = {1e300, 1e300, 1e300}, bmax[3] = {-1e300, -1e300, -1e300};
-    for (int k = 0; k < na; k++) for (int q = 0; q < 3; q++) { amin[q] = fmin(amin[q], A[k * 3 + q]); amax[q] = fmax(amax[q], A[k * 3 + q]); }
-    for (int k = 0; k < nb; k++) for (int q = 0; q < 3; q++) { bmin[q] = fmin(bmin[q], B[k * 3 + q]); bmax[q] = fmax(bmax[q], B[k * 3 + q]); }
-    bool far = false;
-    for (int q = 0; q < 3; q++) if (bmin[q] - amax[q] > 1e-2 || amin[q] - bmax[q] > 1e-2) far = true;
-    if (far) continue;
-    // GLPK's variables are free, so the reference's answer does not depend on where the pair sits; inside the box
-    // below that only holds with the points taken relative to one of them (A's first), which keeps d small.
+  const int n = count[a0];
+  for (int e = warp; e < n; e += total_warps) {
+    SepPair sp;
+    if (!sep_sets(a0, n_total, id_base, t0, list[static_cast<size_t>(a0) * n_total + e], n_pieces, qp_status, cpts, trajs, &sp)) continue;
+    const double* A = sp.A; const double* B = sp.B;
+    const int na = sp.na, nb = sp.nb;
     const double o[3] = {A[0], A[1], A[2]};
-    // Certificate before the LP: along u = centroid(A) - centroid(B), n = 2 (1 + 1e-9) u / gap and d halfway between the
-    // two sets.  If this (n, d) satisfies every row of the LP below — checked row by row, in double, with the box —
-    // the LP is feasible and the pair is safe; the solver is only needed for pairs that nearly touch or interpenetrate.
-    {
-      double ca[3] = {0, 0, 0}, cb[3] = {0, 0, 0};
-      for (int k = 0; k < na; k++) for (int q = 0; q < 3; q++) ca[q] += A[k * 3 + q] - o[q];
-      for (int k = 0; k < nb; k++) for (int q = 0; q < 3; q++) cb[q] += B[k * 3 + q] - o[q];
-      double u[3];
-      for (int q = 0; q < 3; q++) u[q] = ca[q] / na - cb[q] / nb;
-      double lo_a = 1e300, hi_b = -1e300;
-      for (int k = 0; k < na; k++) lo_a = fmin(lo_a, u[0] * (A[k * 3] - o[0]) + u[1] * (A[k * 3 + 1] - o[1]) + u[2] * (A[k * 3 + 2] - o[2]));
-      for (int k = 0; k < nb; k++) hi_b = fmax(hi_b, u[0] * (B[k * 3] - o[0]) + u[1] * (B[k * 3 + 1] - o[1]) + u[2] * (B[k * 3 + 2] - o[2]));
-      const double gap = lo_a - hi_b;
-      if (gap > 0.0) {
-        const double sc = 2.0 * (1.0 + 1e-9) / gap;
-        const double nn[3] = {sc * u[0], sc * u[1], sc * u[2]};
-        const double dd = -0.5 * sc * (lo_a + hi_b);
-        bool ok = fabs(nn[0]) <= 9.99e3 && fabs(nn[1]) <= 9.99e3 && fabs(nn[2]) <= 9.99e3 && fabs(dd) <= 9.99e3;
-        for (int k = 0; ok && k < na; k++) ok = nn[0] * (A[k * 3] - o[0]) + nn[1] * (A[k * 3 + 1] - o[1]) + nn[2] * (A[k * 3 + 2] - o[2]) + dd >= 1.0;
-        for (int k = 0; ok && k < nb; k++) ok = nn[0] * (B[k * 3] - o[0]) + nn[1] * (B[k * 3 + 1] - o[1]) + nn[2] * (B[k * 3 + 2] - o[2]) + dd <= -1.0;
-        if (ok) continue;
-      }
-    }
     int rr = 0;
     for (int k = 0; k < na; k++) { for (int q = 0; q < 3; q++) rowsM[rr * 4 + q] = -(A[k * 3 + q] - o[q]); rowsM[rr * 4 + 3] = -1.0; rhs[rr] = -1.0; rr++; }
     for (int k = 0; k < nb; k++) { for (int q = 0; q < 3; q++) rowsM[rr * 4 + q] = B[k * 3 + q] - o[q]; rowsM[rr * 4 + 3] = 1.0; rhs[rr] = -1.0; rr++; }
@@ -96,16 +136,17 @@ __global__ void __launch_bounds__(128) k_separate(int a0, int w0, int n_local, i
     double x[4];
     unsigned long long rng = 0x5eed5eedull + static_cast<unsigned long long>(na) * 131 + nb;
     const double v = poplp::linprog<4>(c, rowsM, 4, rhs, 1, rr, x, &rng, lpw, lpi);
-    if (isinf(v)) atomicExch(&safe[a], 0);
+    if (isinf(v)) atomicExch(&safe[sp.a], 0);
   }
 }
 
-__global__ void k_fill_times(int n, double t_rel, double t_abs, double* tstart, double* tst, int* safe) {
+__global__ void k_fill_times(int n, double t_rel, double t_abs, double* tstart, double* tst, int* safe, int* sep_count) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   tstart[i] = t_rel;
   tst[i] = t_abs;
   safe[i] = 1;
+  sep_count[i] = 0;
 }
 
 // QP inputs from the A* / corridor outputs (baseline_fake.cpp:393-427)
@@ -207,6 +248,8 @@ struct PlanDev {
   int* sep_np = nullptr;    // staging for pop_separation_check_batch
   int* sep_st = nullptr;
   double* sep_cpts = nullptr;
+  int* sep_list = nullptr;  // [n_local][n_total] pairs the screening left to the LP, per launch from its first agent's row
+  int* sep_count = nullptr; // [n_local]
 };
 
 static int plan_alloc(pop_handle* h) {
@@ -225,6 +268,8 @@ static int plan_alloc(pop_handle* h) {
   ok &= cudaMalloc(&d->sep_np, sizeof(int) * nl) == cudaSuccess;
   ok &= cudaMalloc(&d->sep_st, sizeof(int) * nl) == cudaSuccess;
   ok &= cudaMalloc(&d->sep_cpts, sizeof(double) * POP_MAX_PIECES * 15 * nl) == cudaSuccess;
+  ok &= cudaMalloc(&d->sep_list, sizeof(int) * static_cast<size_t>(nl) * h->cfg.n_agents_total) == cudaSuccess;
+  ok &= cudaMalloc(&d->sep_count, sizeof(int) * nl) == cudaSuccess;
   auto finish = [&]() -> int {
     if (!ok) { cudaGetLastError(); return pop_fail(h, POP_E_CUDA, "cycle workspace allocation failed"); }
     POP_CUDA(h, cudaMemsetAsync(d->traj_ids, 0, sizeof(int) * nl, h->stream));
@@ -235,7 +280,7 @@ static int plan_alloc(pop_handle* h) {
   };
   const int rc = finish();
   if (rc != POP_OK) {   // leave no half-built workspace behind: the next call allocates again
-    void* ptrs[] = {d->sep_wd, d->sep_wi, d->safe, d->status, d->traj_ids, d->fsm_state, d->fsm_fail, d->sep_np, d->sep_st, d->sep_cpts};
+    void* ptrs[] = {d->sep_wd, d->sep_wi, d->safe, d->status, d->traj_ids, d->fsm_state, d->fsm_fail, d->sep_np, d->sep_st, d->sep_cpts, d->sep_list, d->sep_count};
     for (void* q : ptrs) if (q) cudaFree(q);
     delete d;
     h->plan = nullptr;
@@ -249,7 +294,7 @@ void pop_plan_free(pop_handle* h) {
   popk_qp_free(h);
   PlanDev* d = h->plan;
   if (!d) return;
-  void* ptrs[] = {d->sep_wd, d->sep_wi, d->safe, d->status, d->traj_ids, d->fsm_state, d->fsm_fail, d->sep_np, d->sep_st, d->sep_cpts};
+  void* ptrs[] = {d->sep_wd, d->sep_wi, d->safe, d->status, d->traj_ids, d->fsm_state, d->fsm_fail, d->sep_np, d->sep_st, d->sep_cpts, d->sep_list, d->sep_count};
   for (void* p : ptrs) if (p) cudaFree(p);
   delete d;
   h->plan = nullptr;
@@ -262,11 +307,16 @@ static int run_separation(pop_handle* h, double t_now, const int* d_np, const in
   if (timed) pop_prof_begin(h, POP_STAGE_SEPARATION);
   int launches = 0;
   if (h->have_traj && h->cfg.n_agents_total > 1) {
-    const int blocks = nw / 4 > 0 ? nw / 4 : 1;
-    k_separate<<<blocks, 128, 0, st>>>(a0, w0, na, h->cfg.n_agents_total, h->cfg.agent_id_base, t_now, d_np, d_st,
-                                       d_cpts, h->d_traj_all, d->sep_wd, d->sep_wi, d->safe);
+    const int nt = h->cfg.n_agents_total;
+    const long long pairs = static_cast<long long>(na) * nt;
+    k_sep_screen<<<static_cast<unsigned>((pairs + 127) / 128), 128, 0, st>>>(a0, na, nt, h->cfg.agent_id_base, t_now, d_np, d_st,
+                                                                             d_cpts, h->d_traj_all, d->sep_list, d->sep_count);
     POP_LAUNCH_CHECK(h);
-    launches = 1;
+    const int blocks = nw / 4 > 0 ? nw / 4 : 1;
+    k_sep_lp<<<blocks, 128, 0, st>>>(a0, w0, nt, h->cfg.agent_id_base, t_now, d_np, d_st, d_cpts, h->d_traj_all, d->sep_list,
+                                     d->sep_count, d->sep_wd, d->sep_wi, d->safe);
+    POP_LAUNCH_CHECK(h);
+    launches = 2;
   }
   if (timed) pop_prof_end(h, POP_STAGE_SEPARATION, launches);
   else h->n_launches += launches;
@@ -322,7 +372,7 @@ static int cycle_enqueue(pop_handle* h, double t_map, double t_plan, bool update
     t_map = h->t_map;   // the SOGM as the last map update (ground truth or particle map) left it
   }
   k_fill_times<<<(nl + 127) / 128, 128, 0, h->stream>>>(nl, t_plan - t_map, t_plan, popk_astar_tstart_dev(h),
-                                                       popk_corridor_tst_dev(h), d->safe);
+                                                       popk_corridor_tst_dev(h), d->safe, d->sep_count);
   POP_LAUNCH_CHECK(h);
   // A* → corridors → QP are independent per agent: unless every stage is being timed, run them as
   // chains over agent groups on side streams, so one agent's 4 000-iteration QP overlaps the other
@@ -386,6 +436,7 @@ int pop_separation_check_batch(pop_handle* h, const int32_t* n_pieces, const dou
   POP_CUDA(h, cudaMemcpyAsync(d->sep_np, n_pieces, sizeof(int) * nl, cudaMemcpyHostToDevice, h->stream));
   POP_CUDA(h, cudaMemcpyAsync(d->sep_st, ones.data(), sizeof(int) * nl, cudaMemcpyHostToDevice, h->stream));
   POP_CUDA(h, cudaMemcpyAsync(d->safe, ones.data(), sizeof(int) * nl, cudaMemcpyHostToDevice, h->stream));
+  POP_CUDA(h, cudaMemsetAsync(d->sep_count, 0, sizeof(int) * nl, h->stream));
   POP_CUDA(h, cudaMemcpyAsync(d->sep_cpts, cpts, sizeof(double) * POP_MAX_PIECES * 15 * nl, cudaMemcpyHostToDevice, h->stream));
   rc = run_separation(h, t_now, d->sep_np, d->sep_st, d->sep_cpts, h->stream, 0, nl, 0, kSepWarps, true);
   if (rc) return rc;

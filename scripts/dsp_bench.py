@@ -10,7 +10,7 @@ import numpy as np
 import torch
 import pred_occ_planner_b200 as p
 from pred_occ_planner_b200 import dsp, worldgen
-from tests import cases
+from pred_occ_planner_b200 import scenes as cases
 
 
 def run(cfg, d, n_agents, frames, warm, label, cpu=False):

@@ -210,31 +210,41 @@ __global__ void __launch_bounds__(256) k_gm_rays(GmGeo G, const GmMap* __restric
     }
     __syncthreads();
     if (prune) {
-      // commit in index order: warp 0, 32 path voxels per step
+      // commit in index order: warp 0, 32 path voxels per step.  Only the bitmap is order-dependent, so the walk
+      // touches shared memory alone and leaves, per ray, how many of its voxels count (up to and including the one
+      // that stops it); the counters in global memory are then updated by all threads at once — with the atomics
+      // inside the walk every step waited for a global round trip.
       if (tid < 32) {
         for (int r = 0; r < kChunk; r++) {
           const int len = plen[r];
+          int keep = len < 0 ? 0 : len;
           bool stop = false;
           for (int s0 = 0; s0 < len && !stop; s0 += 32) {
             const int s = s0 + tid;
-            unsigned pk = 0;
-            int bit = 0, a = -1, lin = 0;
+            int bit = 0, lin = 0;
             if (s < len) {
-              pk = paths[r * kMaxPath + s];
+              const unsigned pk = paths[r * kMaxPath + s];
               const int rx = pk & 1023, ry = (pk >> 10) & 1023, rz = pk >> 20;
               lin = (rx * G.B + ry) * G.B + rz;
               bit = (bitmap[lin >> 5] >> (lin & 31)) & 1;
-              a = ((rx + box0[0]) * G.n[1] + (ry + box0[1])) * G.n[2] + (rz + box0[2]);
             }
             const unsigned hit = __ballot_sync(0xffffffffu, bit);
             const int f = hit ? __ffs(hit) - 1 : 32;      // first already-traversed voxel of this step
-            if (s < len && tid <= f) {
-              gm_count(a, 0, M.cnt_hm, M.cnt_hit, M.touched, M.ntouched);   // a miss, also on the voxel that stops the ray
-              if (tid < f) atomicOr(&bitmap[lin >> 5], 1u << (lin & 31));
-            }
+            if (s < len && tid < f) atomicOr(&bitmap[lin >> 5], 1u << (lin & 31));
             __syncwarp();
-            stop = f < 32;
+            if (f < 32) { stop = true; keep = s0 + f + 1; }   // a miss also on the voxel that stops the ray
           }
+          if (tid == 0) plen[r] = keep;
+        }
+      }
+      __syncthreads();
+      for (int e = tid; e < kChunk * kMaxPath; e += blockDim.x) {
+        const int r = e / kMaxPath, s = e % kMaxPath;
+        if (s < plen[r]) {
+          const unsigned pk = paths[e];
+          const int rx = pk & 1023, ry = (pk >> 10) & 1023, rz = pk >> 20;
+          const int a = ((rx + box0[0]) * G.n[1] + (ry + box0[1])) * G.n[2] + (rz + box0[2]);
+          gm_count(a, 0, M.cnt_hm, M.cnt_hit, M.touched, M.ntouched);
         }
       }
     } else {

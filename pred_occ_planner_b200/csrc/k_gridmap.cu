@@ -74,6 +74,7 @@ struct GmMap {
   double* occ; signed char* inflate; int* cnt_hm; int* cnt_hit; int* first_end; int* touched; int* ntouched;
   double* pw; int* endv; unsigned long long* bbox;   // bbox: min xyz, max xyz as ordered keys
   int* lb;   // local_bound_min (3), local_bound_max (3)
+  int* cast; // indices of the points that cast a ray this frame, in order
 };
 
 // K1: clip every projected point, count its end voxel, elect the casting point per end voxel (:337-377)
@@ -163,7 +164,11 @@ __device__ int gm_trace(const GmGeo& G, const double* pw, const double* cam, con
     // the reference addresses linearly without range checks: take the voxel that address really is
     const int a = gm_addr(G, id);
     if (a >= 0 && a < G.N) {
-      const int rx = a / (G.n[1] * G.n[2]) - box0[0], ry = (a / G.n[2]) % G.n[1] - box0[1], rz = a % G.n[2] - box0[2];
+      // an index inside the map is its own address decomposition (no divisions on the common path)
+      const bool inside = id[0] >= 0 && id[0] < G.n[0] && id[1] >= 0 && id[1] < G.n[1] && id[2] >= 0 && id[2] < G.n[2];
+      const int rx = (inside ? id[0] : a / (G.n[1] * G.n[2])) - box0[0];
+      const int ry = (inside ? id[1] : (a / G.n[2]) % G.n[1]) - box0[1];
+      const int rz = (inside ? id[2] : a % G.n[2]) - box0[2];
       if (len >= cap || rx < 0 || ry < 0 || rz < 0 || rx >= G.B || ry >= G.B || rz >= G.B) { *bad = true; return len; }
       path[len++] = static_cast<unsigned>(rx) | (static_cast<unsigned>(ry) << 10) | (static_cast<unsigned>(rz) << 20);
     }
@@ -179,7 +184,7 @@ __device__ int gm_trace(const GmGeo& G, const double* pw, const double* cam, con
 // K2: rays in index order (one CTA per map)
 __global__ void __launch_bounds__(256) k_gm_rays(GmGeo G, const GmMap* __restrict__ maps, const int* __restrict__ counts,
                                                  const double* __restrict__ cam_all, const int* __restrict__ flags_work,
-                                                 int* __restrict__ err) {
+                                                 int* __restrict__ err, int chunk) {
   extern __shared__ unsigned smem[];
   const int m = blockIdx.x, tid = threadIdx.x;
   const int prune = flags_work[m];
@@ -192,16 +197,34 @@ __global__ void __launch_bounds__(256) k_gm_rays(GmGeo G, const GmMap* __restric
   for (int k = 0; k < 3; k++) box0[k] = camv[k] - G.R;
   const int nwords = (G.B * G.B * G.B + 31) / 32;
   unsigned* bitmap = smem;                       // nwords
-  unsigned* paths = smem + nwords;               // kChunk * kMaxPath
-  int* plen = reinterpret_cast<int*>(paths + kChunk * kMaxPath);   // kChunk
+  unsigned* paths = smem + nwords;               // chunk * kMaxPath
+  int* plen = reinterpret_cast<int*>(paths + chunk * kMaxPath);   // chunk
+  __shared__ int s_wsum[8], s_ncast;
   for (int i = tid; i < nwords; i += blockDim.x) bitmap[i] = 0u;
+  // the points that cast a ray (not clipped away; with pruning, only the first point of every end voxel), compacted
+  // in index order, so that every trace thread of a round below has a ray to walk
+  if (tid == 0) s_ncast = 0;
   __syncthreads();
-  for (int base = 0; base < np; base += kChunk) {
-    // trace: thread r < kChunk walks ray base + r if that point casts
-    if (tid < kChunk) {
-      const int i = base + tid;
+  for (int w0 = 0; w0 < np; w0 += blockDim.x) {
+    const int i = w0 + tid;
+    const bool casts = i < np && M.endv[i] != -2 && (!prune || M.endv[i] < 0 || M.first_end[M.endv[i]] == i);
+    const unsigned bal = __ballot_sync(0xffffffffu, casts);
+    if ((tid & 31) == 0) s_wsum[tid >> 5] = __popc(bal);
+    __syncthreads();
+    int off = s_ncast;
+    for (int w = 0; w < (tid >> 5); w++) off += s_wsum[w];
+    if (casts) M.cast[off + __popc(bal & ((1u << (tid & 31)) - 1u))] = i;
+    __syncthreads();
+    if (tid == 0) { int t = 0; for (int w = 0; w < 8; w++) t += s_wsum[w]; s_ncast += t; }
+    __syncthreads();
+  }
+  const int nc = s_ncast;
+  for (int base = 0; base < nc; base += chunk) {
+    // trace: thread r < chunk walks the r-th casting ray of this round
+    if (tid < chunk) {
       int len = -1;
-      if (i < np && M.endv[i] != -2 && (!prune || M.endv[i] < 0 || M.first_end[M.endv[i]] == i)) {
+      if (base + tid < nc) {
+        const int i = M.cast[base + tid];
         bool bad = false;
         len = gm_trace(G, M.pw + static_cast<size_t>(i) * 3, cam, box0, paths + tid * kMaxPath, kMaxPath, &bad);
         if (bad) atomicOr(err, 1);
@@ -215,7 +238,7 @@ __global__ void __launch_bounds__(256) k_gm_rays(GmGeo G, const GmMap* __restric
       // that stops it); the counters in global memory are then updated by all threads at once — with the atomics
       // inside the walk every step waited for a global round trip.
       if (tid < 32) {
-        for (int r = 0; r < kChunk; r++) {
+        for (int r = 0; r < chunk; r++) {
           const int len = plen[r];
           int keep = len < 0 ? 0 : len;
           bool stop = false;
@@ -238,7 +261,7 @@ __global__ void __launch_bounds__(256) k_gm_rays(GmGeo G, const GmMap* __restric
         }
       }
       __syncthreads();
-      for (int e = tid; e < kChunk * kMaxPath; e += blockDim.x) {
+      for (int e = tid; e < chunk * kMaxPath; e += blockDim.x) {
         const int r = e / kMaxPath, s = e % kMaxPath;
         if (s < plen[r]) {
           const unsigned pk = paths[e];
@@ -249,7 +272,7 @@ __global__ void __launch_bounds__(256) k_gm_rays(GmGeo G, const GmMap* __restric
       }
     } else {
       // frames >= 128: no pruning, every traced voxel is a miss
-      for (int e = tid; e < kChunk * kMaxPath; e += blockDim.x) {
+      for (int e = tid; e < chunk * kMaxPath; e += blockDim.x) {
         const int r = e / kMaxPath, s = e % kMaxPath;
         if (s < plen[r]) {
           const unsigned pk = paths[e];
@@ -473,6 +496,7 @@ struct pop_gridmap {
   void* d_q = nullptr; size_t d_q_bytes = 0;
   std::vector<void*> allocs;
   size_t rays_smem = 0;
+  int rays_chunk = 0;
 };
 
 // see PopDeviceGuard (pop_internal.h): the map's device is current inside every entry point, the caller's afterwards
@@ -581,7 +605,13 @@ int pop_gridmap_create(const pop_gridmap_config* c, int n_maps, int device, void
   G.B = 2 * G.R + 1;
   if (G.B > 1023 || 3 * G.R + 3 > kMaxPath) return fail(POP_E_UNSUPPORTED);
   const size_t nwords = (static_cast<size_t>(G.B) * G.B * G.B + 31) / 32;
-  g->rays_smem = sizeof(unsigned) * (nwords + kChunk * kMaxPath) + sizeof(int) * kChunk;
+  // rays traced per round: 128 when the bitmap leaves room for their paths, else 64
+  g->rays_chunk = 2 * kChunk;
+  g->rays_smem = sizeof(unsigned) * (nwords + g->rays_chunk * kMaxPath) + sizeof(int) * g->rays_chunk;
+  if (g->rays_smem > 227 * 1024) {
+    g->rays_chunk = kChunk;
+    g->rays_smem = sizeof(unsigned) * (nwords + kChunk * kMaxPath) + sizeof(int) * kChunk;
+  }
   if (g->rays_smem > 227 * 1024) return fail(POP_E_UNSUPPORTED);
   if (cudaFuncSetAttribute(k_gm_rays, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(g->rays_smem)) != cudaSuccess)
     return fail(POP_E_CUDA);
@@ -607,7 +637,8 @@ int pop_gridmap_create(const pop_gridmap_config* c, int n_maps, int device, void
     M.endv = static_cast<int*>(alloc(sizeof(int) * c->max_points));
     M.bbox = static_cast<unsigned long long*>(alloc(sizeof(unsigned long long) * 6));
     M.lb = static_cast<int*>(alloc(sizeof(int) * 6));
-    ok = M.occ && M.inflate && M.cnt_hm && M.cnt_hit && M.first_end && M.touched && M.ntouched && M.pw && M.endv && M.bbox && M.lb;
+    M.cast = static_cast<int*>(alloc(sizeof(int) * c->max_points));
+    ok = M.occ && M.inflate && M.cnt_hm && M.cnt_hit && M.first_end && M.touched && M.ntouched && M.pw && M.endv && M.bbox && M.lb && M.cast;
     if (ok) k_gm_fill<<<static_cast<unsigned>((N + 255) / 256), 256, 0, g->stream>>>(M.occ, N, G.unk, M.first_end);
   }
   g->d_maps = static_cast<GmMap*>(alloc(sizeof(GmMap) * n_maps));
@@ -642,7 +673,7 @@ static int gm_run(pop_gridmap* g, const int32_t* counts) {
   GM_CUDA(g, cudaStreamSynchronize(st));           // flags_work is stack-owned
   k_gm_frame_reset<<<(A + 63) / 64, 64, 0, st>>>(g->d_maps, A);
   k_gm_points<<<dim3((maxn + 255) / 256, A), 256, 0, st>>>(G, g->d_maps, g->d_pts, g->d_counts, g->d_cam, g->d_flags, g->d_err);
-  k_gm_rays<<<A, 256, g->rays_smem, st>>>(G, g->d_maps, g->d_counts, g->d_cam, g->d_flags, g->d_err);
+  k_gm_rays<<<A, 256, g->rays_smem, st>>>(G, g->d_maps, g->d_counts, g->d_cam, g->d_flags, g->d_err, g->rays_chunk);
   k_gm_update<<<dim3(64, A), 256, 0, st>>>(G, g->d_maps, g->d_counts, g->d_cam);
   k_gm_clear<<<dim3(128, A), 256, 0, st>>>(G, g->d_maps, g->d_counts);
   k_gm_inflate<<<dim3(128, A), 256, 0, st>>>(G, g->d_maps, g->d_counts);

@@ -739,25 +739,41 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_corridor_firi(
 // =================================================================================================
 // per-agent tail: cut at first invalid corridor, intersections, goal reachability
 // =================================================================================================
-__global__ void k_corridor_finish(const double* __restrict__ path, const int* __restrict__ len,
-                                  const double* __restrict__ start, int id_base, int variant,
-                                  const double* __restrict__ seg_h, const int* __restrict__ seg_rows,
-                                  const int* __restrict__ seg_valid, double* __restrict__ scr_all,
-                                  int* __restrict__ scri_all, int* __restrict__ out_npoly, double* __restrict__ out_goal,
-                                  int a0, int n_agents) {
-  const int a = a0 + blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);   // n_agents = end of the range
-  if (a >= n_agents || (threadIdx.x & 31) != 0) return;
+// One block per agent, one warp per corridor pair: warp w decides whether corridors w and w + 1 intersect (its own LP
+// in segment w's scratch), then warp 0 walks the sequential rules with those answers and solves the goal LPs.
+__global__ void __launch_bounds__(32 * POP_MAX_PIECES) k_corridor_finish(
+    const double* __restrict__ path, const int* __restrict__ len, const double* __restrict__ start, int id_base, int variant,
+    const double* __restrict__ seg_h, const int* __restrict__ seg_rows, const int* __restrict__ seg_valid,
+    double* __restrict__ scr_all, int* __restrict__ scri_all, int* __restrict__ out_npoly, double* __restrict__ out_goal,
+    int a0, int n_agents) {
+  __shared__ int s_inter[POP_MAX_PIECES];
+  const int a = a0 + blockIdx.x, w = threadIdx.x >> 5;   // n_agents = end of the range
+  if (a >= n_agents) return;
+  const double* H = seg_h + static_cast<size_t>(a) * POP_MAX_PIECES * POP_MAX_FACES * 4;
+  const int* rows = seg_rows + a * POP_MAX_PIECES;
+  const int* valid = seg_valid + a * POP_MAX_PIECES;
+  const unsigned long long seed_base = static_cast<unsigned long long>(id_base + a);
+  if ((threadIdx.x & 31) == 0) {
+    const int np = corridor_valid_prefix(len[a], valid);
+    int meets = 1;
+    if (w + 1 < np) {
+      double* scr = scr_all + (static_cast<size_t>(a) * POP_MAX_PIECES + w) * kScrDoubles;   // ab at its head (< kScrLp), LP work behind
+      int* scri = scri_all + (static_cast<size_t>(a) * POP_MAX_PIECES + w) * kScrInts;
+      meets = corridor_pair_intersects(H, rows, w, seed_base, scr, scr + kScrLp, scri) ? 1 : 0;
+    }
+    s_inter[w] = meets;
+  }
+  __syncthreads();
+  if (threadIdx.x != 0) return;
   // reuse segment 0's scratch of this agent: holds up to kLpRows rows of LP workspace
   double* scr = scr_all + static_cast<size_t>(a) * POP_MAX_PIECES * kScrDoubles;
   int* scri = scri_all + static_cast<size_t>(a) * POP_MAX_PIECES * kScrInts;
   double* lpw = scr + kScrLp;
   double* ab = scr + static_cast<size_t>(kScrDoubles);  // segment 1's scratch: 4 * kLpRows doubles fit
-  out_npoly[a] = corridor_finish_agent(variant, static_cast<unsigned long long>(id_base + a), len[a],
-                                       path + static_cast<size_t>(a) * POP_MAX_PATH * 6,
-                                       seg_h + static_cast<size_t>(a) * POP_MAX_PIECES * POP_MAX_FACES * 4,
-                                       seg_rows + a * POP_MAX_PIECES, seg_valid + a * POP_MAX_PIECES, start + a * 9, ab,
-                                       lpw, scri, out_goal + a * 6);
+  out_npoly[a] = corridor_finish_agent(variant, seed_base, len[a], path + static_cast<size_t>(a) * POP_MAX_PATH * 6, H, rows,
+                                       valid, start + a * 9, ab, lpw, scri, out_goal + a * 6, s_inter);
 }
+static_assert(4 * kLpRows <= kScrLp, "the intersection LP's rows must fit in front of its work array");
 
 }  // namespace
 
@@ -845,7 +861,7 @@ int popk_corridor_run(pop_handle* h, const double* d_path, const int* d_len, con
       h->geom, h->d_poses, d->segs, d->pts, d->cap, c.shrink_size, c.agent_id_base, d->distRs, d->tang, d->flags,
       d->scr, d->scri, d->seg_h, d->seg_rows, d->seg_valid, seg0, seg0 + ns, d->err);
   POP_LAUNCH_CHECK(h);
-  k_corridor_finish<<<(na + 3) / 4, 128, 0, st>>>(d_path, d_len, d_start, c.agent_id_base, c.query_variant, d->seg_h,
+  k_corridor_finish<<<na, 32 * POP_MAX_PIECES, 0, st>>>(d_path, d_len, d_start, c.agent_id_base, c.query_variant, d->seg_h,
                                                                  d->seg_rows, d->seg_valid, d->scr, d->scri, d->npoly,
                                                                  d->goal, a0, a0 + na);
   POP_LAUNCH_CHECK(h);

@@ -50,40 +50,56 @@ __device__ inline bool corridor_goal_reachable(const double* h, int m, const dou
   return false;
 }
 
+// Do corridors i and i + 1 intersect?  (the feasibility LP of baseline_fake.cpp:366-378 = baseline.cpp:363-375)
+__device__ inline bool corridor_pair_intersects(const double* H, const int* rows, int i, unsigned long long seed_base,
+                                                double* ab, double* lpw, int* scri) {
+  const int m0 = rows[i], m1 = rows[i + 1];
+  for (int k = 0; k < m0; k++) {
+    const double* h = H + (static_cast<size_t>(i) * POP_MAX_FACES + k) * 4;
+    for (int q = 0; q < 3; q++) ab[k * 4 + q] = h[q];
+    ab[k * 4 + 3] = -h[3];
+  }
+  for (int k = 0; k < m1; k++) {
+    const double* h = H + (static_cast<size_t>(i + 1) * POP_MAX_FACES + k) * 4;
+    for (int q = 0; q < 3; q++) ab[(m0 + k) * 4 + q] = h[q];
+    ab[(m0 + k) * 4 + 3] = -h[3];
+  }
+  const double c[3] = {0, 0, 0};
+  double x[3];
+  unsigned long long rng = lp_seed(seed_base, i, 2);
+  const double rst = poplp::linprog<3>(c, ab, 4, ab + 3, 4, m0 + m1, x, &rng, lpw, scri);
+  return !isinf(rst);
+}
+
+// number of leading corridors whose validity check passed
+__device__ inline int corridor_valid_prefix(int n, const int* valid) {
+  int np = 0;
+  for (int i = 0; i < n - 1 && i < POP_MAX_PIECES; i++) {
+    if (!valid[i]) break;
+    np++;
+  }
+  return np;
+}
+
 // Returns the number of corridors kept (0 = the replan fails here) and writes the local goal (pos, vel).
 //   n        samples of the A* path P (n x 6)
 //   H, rows  the agent's corridors, POP_MAX_PIECES x POP_MAX_FACES x 4 and their row counts
 //   valid    per-segment result of checkCorridorValidity
 //   sp       start state (position first)
 //   ab       4 * (2 * POP_MAX_FACES + 8) doubles, lpw / scri the LP work arrays
+//   inter    optional: inter[i] = corridor_pair_intersects(i) for every i + 1 < valid prefix, solved beforehand (the
+//            pairs do not depend on one another; the kernel gives each its own warp); nullptr = solve them here
 __device__ inline int corridor_finish_agent(int variant, unsigned long long seed_base, int n, const double* P,
                                             const double* H, const int* rows, const int* valid, const double* sp,
-                                            double* ab, double* lpw, int* scri, double* out_goal) {
+                                            double* ab, double* lpw, int* scri, double* out_goal,
+                                            const int* inter = nullptr) {
   const bool real = variant != POP_QUERY_FAKE;
-  int np = 0;
-  for (int i = 0; i < n - 1 && i < POP_MAX_PIECES; i++) {
-    if (!valid[i]) break;
-    np++;
-  }
+  int np = corridor_valid_prefix(n, valid);
   bool fail = false;
   // adjacent corridors must intersect (baseline_fake.cpp:366-378, baseline.cpp:363-375)
   for (int i = 0; i + 1 < np; i++) {
-    const int m0 = rows[i], m1 = rows[i + 1];
-    for (int k = 0; k < m0; k++) {
-      const double* h = H + (static_cast<size_t>(i) * POP_MAX_FACES + k) * 4;
-      for (int q = 0; q < 3; q++) ab[k * 4 + q] = h[q];
-      ab[k * 4 + 3] = -h[3];
-    }
-    for (int k = 0; k < m1; k++) {
-      const double* h = H + (static_cast<size_t>(i + 1) * POP_MAX_FACES + k) * 4;
-      for (int q = 0; q < 3; q++) ab[(m0 + k) * 4 + q] = h[q];
-      ab[(m0 + k) * 4 + 3] = -h[3];
-    }
-    const double c[3] = {0, 0, 0};
-    double x[3];
-    unsigned long long rng = lp_seed(seed_base, i, 2);
-    const double rst = poplp::linprog<3>(c, ab, 4, ab + 3, 4, m0 + m1, x, &rng, lpw, scri);
-    if (isinf(rst)) {
+    const bool meets = inter ? inter[i] != 0 : corridor_pair_intersects(H, rows, i, seed_base, ab, lpw, scri);
+    if (!meets) {
       if (i < 2) { fail = true; break; }
       np = real ? i : i + 1;
       break;

@@ -1,11 +1,33 @@
-"""Small end-to-end pass over the newer kernels (sensor, particle map, raycast map, trajectory sampling) meant to be
-run under `compute-sanitizer --tool memcheck` (development aid)."""
+"""Small end-to-end pass over the kernels (ground-truth SOGM with byte cells, A*, corridors, QP, separation, FSM,
+isTrajSafe; sensor, particle map, raycast map, trajectory sampling) meant to be run under
+`compute-sanitizer --tool memcheck` (development aid)."""
 import sys
 sys.path.insert(0, ".")
 import numpy as np
 import pred_occ_planner_b200 as p
 from pred_occ_planner_b200 import dsp, gridmap, worldgen
 from tests import cases
+
+# ---- ground-truth map + planning cycle, byte cells, agents near the map edge (clipped footprints) ----
+n = 6
+c2 = cases.cfg_small_c2(p.POP_CELL_U8, n_local=n, n_total=n)
+e2 = p.PopEngine(c2, device=0)
+cl, cy = cases.world_moving(5, (12.0, 12.0, 3.0), 4, 6)
+e2.set_world_cloud(cl); e2.set_cylinders(cy)
+e2.set_body_particles(*worldgen.body_table(n, [0.4, 0.4, 0.45]))
+e2.set_trajectories(np.zeros(n, p.TRAJ_DTYPE))
+s0, g0 = worldgen.circle_agents(n, 4.5)
+for k in range(3):
+    if k > 0:
+        e2.swarm_advance(10.0 + 0.1 * k); s0 = e2.swarm_states()
+    st, tr = e2.replan_cycle(s0, g0, s0[:, :3].astype(np.float32), 10.0 + 0.1 * k, 10.02 + 0.1 * k)
+    e2.traj_publish_local()
+    print("cycle", k, st.tolist())
+print("traj safe", e2.is_traj_safe(10.25, 1.0)[0].tolist())
+m0 = e2.agent_map(0)
+edge = np.array([[s0[0, 0] + 5.9, s0[0, 1], 1.0], [s0[0, 0] - 5.9, s0[0, 1] + 5.9, 1.0], [s0[0, 0], s0[0, 1], 1.0]])
+print("edge queries", m0.getClearOcccupancy(edge, 0).tolist(), m0.getInflateOccupancy(edge).tolist())
+e2.close()
 
 cfg = cases.dsp_cfg_ref(n_local=2, n_total=2)
 d = cases.dsp_params(cfg, n_randoms=1 << 16)

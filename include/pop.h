@@ -546,6 +546,13 @@ int pop_profile_read(pop_handle* h, float* ms /*[POP_STAGE_COUNT]*/,
  * factorisation, all factorisations, ADMM loop, number of factorisations, and (builds with
  * -DPOP_QP_PHASE_PROF only) gather, KKT solve, row update inside the loop, reserved}. */
 int pop_qp_profile(pop_handle* h, int n, int64_t* out);
+/* Diagnostic: the device's Seidel LP on its own — min c.x s.t. A x <= b, A row-major rows x d, d = 2..4 — what
+ * sdlp::linprog<d> is to the reference (traj_utils/include/traj_utils/sdlp.hpp:708-785), with the shuffle seeded by
+ * `seed`.  cooperative = 1 runs the warp-cooperative implementation the planner kernels use, 0 the single-thread one
+ * that the host-compiled tests share; both return the same bits.  out_value = the minimum (+inf infeasible, -inf
+ * unbounded), out_x = d doubles. */
+int pop_lp_solve(pop_handle* h, int d, int rows, const double* c, const double* A, const double* b, uint64_t seed,
+                 int cooperative, double* out_x, double* out_value);
 /* total kernels launched by this handle since creation */
 int64_t pop_kernel_launches(const pop_handle* h);
 

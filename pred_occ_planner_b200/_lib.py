@@ -210,6 +210,8 @@ SYMBOLS = [
     ("pop_profile_enable", _I, [_VP, _I]),
     ("pop_profile_read", _I, [_VP, _PF, C.POINTER(C.c_int64), _I]),
     ("pop_qp_profile", _I, [_VP, _I, C.POINTER(C.c_int64)]),
+    ("pop_lp_solve", _I, [_VP, _I, _I, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_uint64, _I,
+                      C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     ("pop_kernel_launches", C.c_int64, [_VP]),
     ("pop_dsp_default_config", None, [C.POINTER(PopConfig), C.POINTER(PopDspConfig)]),
     ("pop_dsp_attach", _I, [_VP, C.POINTER(PopDspConfig)]),

@@ -419,24 +419,28 @@ constexpr int kScrLp = kScrLm + 2 * N9 * kMem + 2 * kMem;
 constexpr int kScrDoubles = kScrLp + poplp::work_doubles(kLpRows, 4);
 constexpr int kScrInts = poplp::work_ints(kLpRows);
 
-// maxVolInsEllipsoid (firi.hpp:146-236); hPoly = M x 4.  Three steps: mvie_prepare (lane 0: deepest
-// point by LP, normalised faces A3, Cholesky start point), lbfgs9 (whole warp), mvie_finish (lane 0).
+// maxVolInsEllipsoid (firi.hpp:146-236); hPoly = M x 4.  Steps: mvie_prepare (whole warp: the deepest point by the
+// warp-cooperative LP; then lane 0: normalised faces A3, Cholesky start point), lbfgs9 (whole warp), mvie_finish (lane 0).
+// Returns to every lane whether the polytope has an interior.
 __device__ bool mvie_prepare(const double* hPoly, int M, const double* R, const double* p, const double* r,
                              unsigned long long* rng, double* scr, int* scri, double* x, double* interior) {
+  const int lane = static_cast<int>(threadIdx.x & 31u);
   double* Alp = scr + kScrAlp;
   double* blp = scr + kScrBlp;
   double* A3 = scr + kScrA3;
-  for (int i = 0; i < M; i++) {
+  for (int i = lane; i < M; i += 32) {
     const double* h = hPoly + i * 4;
     const double hn = sqrt((h[0] * h[0] + h[1] * h[1]) + h[2] * h[2]);
     for (int k = 0; k < 3; k++) Alp[i * 4 + k] = h[k] / hn;
     Alp[i * 4 + 3] = 1.0;
     blp[i] = -h[3] / hn;
   }
+  __syncwarp();
   const double clp[4] = {0, 0, 0, -1.0};
   double xlp[4];
-  const double maxdepth = -poplp::linprog<4>(clp, Alp, 4, blp, 1, M, xlp, rng, scr + kScrLp, scri);
+  const double maxdepth = -poplp::warp::linprog<4>(clp, Alp, 4, blp, 1, M, xlp, rng, scr + kScrLp, scri);
   if (!(maxdepth > 0.0) || isinf(maxdepth)) return false;
+  if (lane != 0) return true;
   for (int k = 0; k < 3; k++) interior[k] = xlp[k];
   for (int i = 0; i < M; i++) {
     const double* a = Alp + i * 4;
@@ -473,16 +477,18 @@ __device__ void mvie_finish(const double* x, const double* interior, double* R, 
   }
 }
 
-// checkCorridorValidity (baseline_fake.cpp:191-204) on m rows of (h0,h1,h2,h3)
+// checkCorridorValidity (baseline_fake.cpp:191-204) on m rows of (h0,h1,h2,h3); whole warp, same answer on every lane
 __device__ bool corridor_valid(const double* h, int m, unsigned long long* rng, double* lpw, int* lpi,
                                double* ab /* 4*m scratch */) {
-  for (int i = 0; i < m; i++) {
+  const int lane = static_cast<int>(threadIdx.x & 31u);
+  for (int i = lane; i < m; i += 32) {
     for (int k = 0; k < 3; k++) ab[i * 4 + k] = h[i * 4 + k];
     ab[i * 4 + 3] = -h[i * 4 + 3];
   }
+  __syncwarp();
   const double c[3] = {0, 0, 0};
   double x[3];
-  const double rst = poplp::linprog<3>(c, ab, 4, ab + 3, 4, m, x, rng, lpw, lpi);
+  const double rst = poplp::warp::linprog<3>(c, ab, 4, ab + 3, 4, m, x, rng, lpw, lpi);
   return !isinf(rst);
 }
 
@@ -693,9 +699,10 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_corridor_firi(
       }
       __syncwarp();
       if (loop == 1) break;
-      if (lane == 0) {
+      {
         unsigned long long rng = lp_seed(seed_base, si, 0);
-        W.mvie_ok = mvie_prepare(&W.hP[0][0], nH, W.R, W.p, W.r, &rng, scr, scri, W.x9, W.interior) ? 1 : 0;
+        const bool interior_found = mvie_prepare(&W.hP[0][0], nH, W.R, W.p, W.r, &rng, scr, scri, W.x9, W.interior);
+        if (lane == 0) W.mvie_ok = interior_found ? 1 : 0;
       }
       __syncwarp();
       if (W.mvie_ok) {   // uniform: the whole warp runs the 9-variable L-BFGS, lanes share the face loop
@@ -728,11 +735,14 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_corridor_firi(
   }
   __syncwarp();
   for (int i = lane; i < nH * 4; i += 32) oh[i] = (&W.hP[0][0])[i];
-  if (lane == 0) {
+  __syncwarp();
+  {
     unsigned long long rng = lp_seed(seed_base, si, 1);
     const bool ok = corridor_valid(&W.hP[0][0], nH, &rng, scr + kScrLp, scri, scr + kScrAlp);
-    out_rows[seg] = nH;
-    out_valid[seg] = ok ? 1 : 0;
+    if (lane == 0) {
+      out_rows[seg] = nH;
+      out_valid[seg] = ok ? 1 : 0;
+    }
   }
 }
 
@@ -753,15 +763,26 @@ __global__ void __launch_bounds__(32 * POP_MAX_PIECES) k_corridor_finish(
   const int* rows = seg_rows + a * POP_MAX_PIECES;
   const int* valid = seg_valid + a * POP_MAX_PIECES;
   const unsigned long long seed_base = static_cast<unsigned long long>(id_base + a);
-  if ((threadIdx.x & 31) == 0) {
+  {
+    const int lane = static_cast<int>(threadIdx.x & 31u);
     const int np = corridor_valid_prefix(len[a], valid);
     int meets = 1;
-    if (w + 1 < np) {
-      double* scr = scr_all + (static_cast<size_t>(a) * POP_MAX_PIECES + w) * kScrDoubles;   // ab at its head (< kScrLp), LP work behind
+    if (w + 1 < np) {   // warp-uniform: the pair's feasibility LP, rows of both corridors (corridor_pair_intersects)
+      double* ab = scr_all + (static_cast<size_t>(a) * POP_MAX_PIECES + w) * kScrDoubles;   // rows at the head (< kScrLp), LP work behind
       int* scri = scri_all + (static_cast<size_t>(a) * POP_MAX_PIECES + w) * kScrInts;
-      meets = corridor_pair_intersects(H, rows, w, seed_base, scr, scr + kScrLp, scri) ? 1 : 0;
+      const int m0 = rows[w], m1 = rows[w + 1];
+      for (int k = lane; k < m0 + m1; k += 32) {
+        const double* hh = H + (static_cast<size_t>(k < m0 ? w : w + 1) * POP_MAX_FACES + (k < m0 ? k : k - m0)) * 4;
+        for (int q = 0; q < 3; q++) ab[k * 4 + q] = hh[q];
+        ab[k * 4 + 3] = -hh[3];
+      }
+      __syncwarp();
+      const double c[3] = {0, 0, 0};
+      double x[3];
+      unsigned long long rng = lp_seed(seed_base, w, 2);
+      meets = isinf(poplp::warp::linprog<3>(c, ab, 4, ab + 3, 4, m0 + m1, x, &rng, ab + kScrLp, scri)) ? 0 : 1;
     }
-    s_inter[w] = meets;
+    if (lane == 0) s_inter[w] = meets;
   }
   __syncthreads();
   if (threadIdx.x != 0) return;

@@ -110,8 +110,7 @@ __global__ void __launch_bounds__(128) k_sep_lp(int a0, int w0, int n_total, int
                                                 const pop_traj_record* __restrict__ trajs, const int* __restrict__ list,
                                                 const int* __restrict__ count, double* __restrict__ wd,
                                                 int* __restrict__ wi, int* __restrict__ safe) {
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if ((threadIdx.x & 31) != 0) return;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   const int total_warps = (gridDim.x * blockDim.x) >> 5;
   double* rowsM = wd + static_cast<size_t>(w0 + warp) * kSepDoubles;
   double* rhs = rowsM + 4 * kSepRows;
@@ -124,19 +123,28 @@ __global__ void __launch_bounds__(128) k_sep_lp(int a0, int w0, int n_total, int
     const double* A = sp.A; const double* B = sp.B;
     const int na = sp.na, nb = sp.nb;
     const double o[3] = {A[0], A[1], A[2]};
-    int rr = 0;
-    for (int k = 0; k < na; k++) { for (int q = 0; q < 3; q++) rowsM[rr * 4 + q] = -(A[k * 3 + q] - o[q]); rowsM[rr * 4 + 3] = -1.0; rhs[rr] = -1.0; rr++; }
-    for (int k = 0; k < nb; k++) { for (int q = 0; q < 3; q++) rowsM[rr * 4 + q] = B[k * 3 + q] - o[q]; rowsM[rr * 4 + 3] = 1.0; rhs[rr] = -1.0; rr++; }
-    for (int k = 0; k < 4; k++) {
-      for (int q = 0; q < 4; q++) { rowsM[rr * 4 + q] = q == k ? 1.0 : 0.0; rowsM[(rr + 1) * 4 + q] = q == k ? -1.0 : 0.0; }
-      rhs[rr] = 1e4; rhs[rr + 1] = 1e4;
-      rr += 2;
+    __syncwarp();
+    for (int k = lane; k < na + nb + 8; k += 32) {
+      if (k < na) {
+        for (int q = 0; q < 3; q++) rowsM[k * 4 + q] = -(A[k * 3 + q] - o[q]);
+        rowsM[k * 4 + 3] = -1.0; rhs[k] = -1.0;
+      } else if (k < na + nb) {
+        const int kb = k - na;
+        for (int q = 0; q < 3; q++) rowsM[k * 4 + q] = B[kb * 3 + q] - o[q];
+        rowsM[k * 4 + 3] = 1.0; rhs[k] = -1.0;
+      } else {   // the box |n_i|, |d| <= 1e4, two rows per variable
+        const int kk = k - na - nb, var = kk >> 1;
+        for (int q = 0; q < 4; q++) rowsM[k * 4 + q] = q == var ? ((kk & 1) ? -1.0 : 1.0) : 0.0;
+        rhs[k] = 1e4;
+      }
     }
+    __syncwarp();
+    const int rr = na + nb + 8;
     const double c[4] = {0, 0, 0, 0};
     double x[4];
     unsigned long long rng = 0x5eed5eedull + static_cast<unsigned long long>(na) * 131 + nb;
-    const double v = poplp::linprog<4>(c, rowsM, 4, rhs, 1, rr, x, &rng, lpw, lpi);
-    if (isinf(v)) atomicExch(&safe[sp.a], 0);
+    const double v = poplp::warp::linprog<4>(c, rowsM, 4, rhs, 1, rr, x, &rng, lpw, lpi);
+    if (lane == 0 && isinf(v)) atomicExch(&safe[sp.a], 0);
   }
 }
 
@@ -522,5 +530,57 @@ extern "C" int pop_traj_publish_local(pop_handle* h) {
   POP_CUDA(h, cudaMemcpyAsync(h->d_traj_all + h->cfg.agent_id_base, h->d_traj_send,
                               sizeof(pop_traj_record) * h->cfg.n_agents_local, cudaMemcpyDeviceToDevice, h->stream));
   h->have_traj = true;
+  return POP_OK;
+}
+
+// ---- diagnostic: the device LP on its own (both implementations), for tests ---------------------------------------
+namespace {
+template <int d>
+__global__ void k_lp_solve(int rows, const double* __restrict__ c, const double* __restrict__ A, const double* __restrict__ b,
+                           unsigned long long seed, int cooperative, double* __restrict__ out, double* wd, int* wi) {
+  double x[d];
+  unsigned long long rng = seed;
+  double v;
+  if (cooperative) {
+    v = poplp::warp::linprog<d>(c, A, d, b, 1, rows, x, &rng, wd, wi);
+  } else {
+    if (threadIdx.x != 0) return;
+    v = poplp::linprog<d>(c, A, d, b, 1, rows, x, &rng, wd, wi);
+  }
+  if (threadIdx.x == 0) {
+    out[0] = v;
+    for (int k = 0; k < d; k++) out[1 + k] = x[k];
+  }
+}
+}  // namespace
+
+extern "C" int pop_lp_solve(pop_handle* h, int d, int rows, const double* c, const double* A, const double* b,
+                            uint64_t seed, int cooperative, double* out_x, double* out_value) {
+  if (!h || d < 2 || d > 4 || rows < 0 || rows > 4096 || !c || (rows > 0 && (!A || !b)) || !out_x || !out_value) return POP_E_INVALID;
+  PopDeviceGuard guard(h);
+  const size_t nwd = poplp::work_doubles(rows, 4) + 8, nwi = poplp::work_ints(rows) + 8;
+  double *dc = nullptr, *dA = nullptr, *db = nullptr, *dout = nullptr, *wd = nullptr;
+  int* wi = nullptr;
+  bool ok = cudaMalloc(&dc, sizeof(double) * 4) == cudaSuccess && cudaMalloc(&dA, sizeof(double) * (rows * d + 1)) == cudaSuccess &&
+            cudaMalloc(&db, sizeof(double) * (rows + 1)) == cudaSuccess && cudaMalloc(&dout, sizeof(double) * 5) == cudaSuccess &&
+            cudaMalloc(&wd, sizeof(double) * nwd) == cudaSuccess && cudaMalloc(&wi, sizeof(int) * nwi) == cudaSuccess;
+  double out[5] = {0, 0, 0, 0, 0};
+  if (ok) {
+    cudaMemcpyAsync(dc, c, sizeof(double) * d, cudaMemcpyHostToDevice, h->stream);
+    if (rows > 0) {
+      cudaMemcpyAsync(dA, A, sizeof(double) * rows * d, cudaMemcpyHostToDevice, h->stream);
+      cudaMemcpyAsync(db, b, sizeof(double) * rows, cudaMemcpyHostToDevice, h->stream);
+    }
+    if (d == 2) k_lp_solve<2><<<1, 32, 0, h->stream>>>(rows, dc, dA, db, seed, cooperative, dout, wd, wi);
+    else if (d == 3) k_lp_solve<3><<<1, 32, 0, h->stream>>>(rows, dc, dA, db, seed, cooperative, dout, wd, wi);
+    else k_lp_solve<4><<<1, 32, 0, h->stream>>>(rows, dc, dA, db, seed, cooperative, dout, wd, wi);
+    cudaMemcpyAsync(out, dout, sizeof(out), cudaMemcpyDeviceToHost, h->stream);
+    ok = cudaStreamSynchronize(h->stream) == cudaSuccess;
+  }
+  void* ptrs[] = {dc, dA, db, dout, wd, wi};
+  for (void* q : ptrs) if (q) cudaFree(q);
+  if (!ok) { cudaGetLastError(); return pop_fail(h, POP_E_CUDA, "pop_lp_solve: allocation or launch failed"); }
+  *out_value = out[0];
+  for (int k = 0; k < d; k++) out_x[k] = out[1 + k];
   return POP_OK;
 }

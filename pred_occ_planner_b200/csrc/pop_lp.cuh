@@ -338,4 +338,292 @@ __device__ double linprog(const double* c, const double* A, int lda, const doubl
   return minimum;
 }
 
+
+// =================================================================================================================
+// The same algorithm for a whole warp (device only).  Seidel's method walks the constraints in a fixed (shuffled,
+// move-to-front) order and almost all of them are no-ops: a constraint the current optimum already satisfies changes
+// nothing.  So the 32 lanes test the next 32 constraints of the order at once, the first one that is violated is
+// handled exactly as the sequential code handles it (all lanes carry the same optimum in registers and do the same
+// scalar arithmetic), and the walk resumes behind it.  The projection of the earlier constraints onto a violated
+// one and the move-to-front are done lane-parallel.  The order lives in an array (position -> constraint) instead
+// of a linked list, so "the constraints before position p" is a range.  Same arithmetic, same order of events, same
+// result bit for bit as linprog<d> (tests/test_gpu_lp.py compares them on the device).
+// Every lane of a converged warp must call it with the same arguments; the result is returned to every lane.
+// =================================================================================================================
+#ifdef __CUDACC__
+namespace warp {
+
+constexpr unsigned kFull = 0xffffffffu;
+__device__ __forceinline__ int lane_id() { return static_cast<int>(threadIdx.x & 31u); }
+
+// ord[1..p] rotated right by one: the constraint at position p goes to position 1 (to_front); p <= 1: nothing moves
+__device__ __forceinline__ void rotate_to_front(int* ord, int p) {
+  if (p <= 1) return;
+  const int lane = lane_id();
+  const int moved = ord[p];
+  __syncwarp();
+  for (int base = p; base > 1; base -= 32) {
+    const int k = base - lane;
+    const int v = k > 1 ? ord[k - 1] : 0;
+    __syncwarp();
+    if (k > 1) ord[k] = v;
+    __syncwarp();
+  }
+  if (lane == 0) ord[1] = moved;
+  __syncwarp();
+}
+
+// first position q in [from, to) for which pred(q) holds, or `to`
+template <typename Pred>
+__device__ __forceinline__ int first_where(int from, int to, Pred pred) {
+  const int lane = lane_id();
+  for (int base = from; base < to; base += 32) {
+    const int q = base + lane;
+    const unsigned hit = __ballot_sync(kFull, q < to && pred(q));
+    if (hit) return base + __ffs(hit) - 1;
+  }
+  return to;
+}
+
+// what feasible_arc's first loop does with constraint h given the current arc: 0 nothing, 1 cw update, 2 ccw update,
+// 3 infeasible, 4 degenerate
+__device__ __forceinline__ int arc_event(const double* cw, const double* ccw, const double* h) {
+  const double d_cw = d2(cw, h), d_ccw = d2(ccw, h);
+  if (d_ccw >= 2.0 * kEps) return d_cw <= -2.0 * kEps ? 1 : 0;
+  if (d_cw >= 2.0 * kEps) return d_ccw <= -2.0 * kEps ? 2 : 0;
+  if (d_ccw <= -2.0 * kEps && d_cw <= -2.0 * kEps) return 3;
+  if (d_cw <= -2.0 * kEps || d_ccw <= -2.0 * kEps || x2(cw, h) < 0.0) return 4;
+  return 0;
+}
+
+__device__ inline int feasible_arc(const double* hv /*[id][2]*/, int m, int* ord, double* cw, double* ccw, bool* degen) {
+  *degen = false;
+  int q = first_where(0, m, [&](int k) { double t[2]; return !norm2(hv + 2 * ord[k], t); });
+  if (q == m) return LP_UNBOUNDED;
+  norm2(hv + 2 * ord[q], ccw);
+  cw[0] = ccw[1]; cw[1] = -ccw[0];
+  ccw[0] = -cw[0]; ccw[1] = -cw[1];
+  q = 0;
+  while (true) {
+    q = first_where(q, m, [&](int k) { return arc_event(cw, ccw, hv + 2 * ord[k]) != 0; });
+    if (q == m) break;
+    const double* h = hv + 2 * ord[q];
+    const int ev = arc_event(cw, ccw, h);
+    if (ev == 3) return LP_INFEASIBLE;
+    if (ev == 1) {
+      cw[0] = h[1]; cw[1] = -h[0];
+      norm2(cw, cw);
+    } else if (ev == 2) {
+      ccw[0] = -h[1]; ccw[1] = h[0];
+      norm2(ccw, ccw);
+    } else {
+      const double d_cw = d2(cw, h), d_ccw = d2(ccw, h);
+      if (d_cw <= -2.0 * kEps) norm2(ccw, cw);
+      else if (d_ccw <= -2.0 * kEps) norm2(cw, ccw);
+      *degen = true;
+    }
+    rotate_to_front(ord, q);   // every event of this loop is "offensive"
+    q++;
+    if (*degen) break;
+  }
+  if (*degen) {
+    while (true) {
+      q = first_where(q, m, [&](int k) {
+        const double* g = hv + 2 * ord[k];
+        return d2(cw, g) < -2.0 * kEps || d2(ccw, g) < -2.0 * kEps;
+      });
+      if (q == m) break;
+      const double* h = hv + 2 * ord[q];
+      const double d_cw = d2(cw, h), d_ccw = d2(ccw, h);
+      if (d_cw < -2.0 * kEps) {
+        if (d_ccw < -2.0 * kEps) return LP_INFEASIBLE;
+        cw[0] = ccw[0]; cw[1] = ccw[1];
+      } else {
+        ccw[0] = cw[0]; ccw[1] = cw[1];
+      }
+      q++;
+    }
+  }
+  return LP_MINIMUM;
+}
+
+__device__ inline int solve_1d(const double* hv, int m, const double* nv, const double* dv, double* opt, int* ord) {
+  double cw[2], ccw[2];
+  bool degen;
+  int status = feasible_arc(hv, m, ord, cw, ccw, &degen);
+  if (status == LP_INFEASIBLE) return status;
+  if (status == LP_UNBOUNDED) return free_optimum<1>(nv, dv, opt);
+  if (fabs(x2(nv, dv)) < 2.0 * kEps * kEps) {
+    if (d2(nv, nv) < 2.0 * kEps * kEps || d2(dv, dv) > 2.0 * kEps * kEps) {
+      opt[0] = cw[0]; opt[1] = cw[1];
+      status = LP_AMBIGUOUS;
+    } else {
+      if (!degen && x2(cw, nv) <= 0.0 && x2(nv, ccw) <= 0.0) {
+        opt[0] = -nv[0]; opt[1] = -nv[1];
+      } else if (d2(nv, cw) > d2(nv, ccw)) {
+        opt[0] = ccw[0]; opt[1] = ccw[1];
+      } else {
+        opt[0] = cw[0]; opt[1] = cw[1];
+      }
+      status = LP_MINIMUM;
+    }
+  } else {
+    rational_min(degen, cw, ccw, nv, dv, opt);
+    status = LP_MINIMUM;
+  }
+  return status;
+}
+
+// m = number of order positions in play (the constraints before the one the caller is handling)
+template <int d>
+__device__ int solve_nd(const double* hv, int max_size, int m, const double* nv, const double* dv, double* opt,
+                        double* work, int* ord) {
+  if constexpr (d == 1) {
+    if (m > 0) return solve_1d(hv, m, nv, dv, opt, ord);
+    return free_optimum<1>(nv, dv, opt);
+  } else {
+    const int lane = lane_id();
+    double val = 0.0;
+    for (int j = 0; j <= d; j++) val += dv[j] * dv[j];
+    const bool dv_zero = val < (d + 1) * kEps * kEps;
+    int status = free_optimum<d>(nv, dv, opt);
+    if (m <= 0) return status;
+    double* sub_h = work;                       // [constraint id][d]
+    double* sub_work = sub_h + max_size * d;
+    int p = 0;
+    while (true) {
+      p = first_where(p, m, [&](int k) {
+        const double* pl = hv + ord[k] * (d + 1);
+        double v = 0.0;
+        for (int j = 0; j <= d; j++) v += opt[j] * pl[j];
+        return v < -(d + 1) * kEps;
+      });
+      if (p == m) break;
+      const int i = ord[p];
+      const double* pl = hv + i * (d + 1);
+      int imax = 0;
+      double rmax = fabs(pl[0]);
+      for (int j = 1; j <= d; j++) {
+        const double ab = fabs(pl[j]);
+        if (ab > rmax) { imax = j; rmax = ab; }
+      }
+      if (p != 0) {
+        const double fac = 1.0 / pl[imax];
+        for (int q = lane; q < p; q += 32) {
+          const int j = ord[q];
+          const double* op = hv + j * (d + 1);
+          const double crit = op[imax] * fac;
+          double* np = sub_h + j * d;
+          for (int k = 0; k <= d; k++) {
+            const int l = k < imax ? k : k - 1;
+            if (k != imax) np[l] = op[k] - pl[k] * crit;
+          }
+        }
+      }
+      double sub_n[d], sub_d[d], sub_opt[d];
+      if (dv_zero) {
+        double ve = 0.0, ee = 0.0;
+        for (int j = 0; j <= d; j++) { ve += nv[j] * pl[j]; ee += pl[j] * pl[j]; }
+        const double fac = ve / ee;
+        for (int j = 0; j <= d; j++)
+          if (j != imax) sub_n[j < imax ? j : j - 1] = nv[j] - pl[j] * fac;
+        for (int j = 0; j < d; j++) sub_d[j] = 0.0;
+      } else {
+        const double cn = nv[imax] / pl[imax], cd = dv[imax] / pl[imax];
+        for (int j = 0; j <= d; j++)
+          if (j != imax) {
+            sub_n[j < imax ? j : j - 1] = nv[j] - pl[j] * cn;
+            sub_d[j < imax ? j : j - 1] = dv[j] - pl[j] * cd;
+          }
+      }
+      __syncwarp();   // the projected constraints are read by every lane below
+      status = solve_nd<d - 1>(sub_h, max_size, p, sub_n, sub_d, sub_opt, sub_work, ord);
+      if (status == LP_INFEASIBLE) return status;
+      opt[imax] = 0.0;
+      for (int j = 0; j <= d; j++)
+        if (j != imax) {
+          const int l = j < imax ? j : j - 1;
+          opt[j] = sub_opt[l];
+          opt[imax] -= pl[j] * sub_opt[l];
+        }
+      opt[imax] /= pl[imax];
+      double mag = 0.0;
+      for (int j = 0; j <= d; j++) mag += opt[j] * opt[j];
+      mag = 1.0 / sqrt(mag);
+      for (int j = 0; j <= d; j++) opt[j] *= mag;
+      rotate_to_front(ord, p);
+      p++;
+    }
+    return status;
+  }
+}
+
+// workspace for `rows` constraints in dimension d (the linked-list version's sizes cover it)
+template <int d>
+__device__ double linprog(const double* c, const double* A, int lda, const double* b, int ldb, int rows, double* x,
+                          unsigned long long* rng, double* wd, int* wi) {
+  const int lane = lane_id();
+  const int m = rows + 1;
+  for (int i = 0; i < d; i++) x[i] = 0.0;
+  if (m <= 1) {
+    double mx = 0.0;
+    for (int i = 0; i < d; i++) mx = fmax(mx, fabs(c[i]));
+    return mx > 0.0 ? -INFINITY : 0.0;
+  }
+  double* hv = wd;
+  double* work = hv + (d + 1) * m;
+  int* perm = wi;
+  int* ord = perm + m;
+  double nv[d + 1], dv[d + 1], opt[d + 1];
+  __syncwarp();
+  if (lane == 0) {
+    for (int j = 0; j < d; j++) hv[j] = 0.0;
+    hv[d] = 1.0;
+  }
+  for (int i = lane; i < rows; i += 32) {
+    double* h = hv + (i + 1) * (d + 1);
+    double sq = 0.0;
+    for (int j = 0; j < d; j++) { h[j] = -A[i * lda + j]; sq += h[j] * h[j]; }
+    h[d] = b[i * ldb];
+    sq += h[d] * h[d];
+    const double nrm = sqrt(sq);
+    if (nrm > 0.0)
+      for (int j = 0; j <= d; j++) h[j] /= nrm;
+  }
+  for (int j = 0; j < d; j++) { nv[j] = c[j]; dv[j] = 0.0; }
+  nv[d] = 0.0;
+  dv[d] = 1.0;
+  unsigned long long state = *rng;
+  if (lane == 0) {   // the shuffle is a sequential recurrence; it is a few hundred integer operations
+    for (int i = 0; i < m - 1; i++) perm[i] = i;
+    for (int i = 0; i < m - 1; i++) {
+      const int j = static_cast<int>(lcg_next(&state) % static_cast<unsigned>(m - 1 - i)) + i;
+      const int t = perm[i]; perm[i] = perm[j]; perm[j] = t;
+    }
+  }
+  state = __shfl_sync(kFull, state, 0);
+  *rng = state;
+  __syncwarp();
+  for (int i = lane; i < m; i += 32) ord[i] = i == 0 ? 0 : perm[i - 1] + 1;
+  __syncwarp();
+  const int status = solve_nd<d>(hv, m, m, nv, dv, opt, work, ord);
+  double minimum = INFINITY;
+  if (status != LP_INFEASIBLE) {
+    if (opt[d] != 0.0 && status != LP_UNBOUNDED) {
+      minimum = 0.0;
+      for (int j = 0; j < d; j++) x[j] = opt[j] / opt[d];
+      for (int j = 0; j < d; j++) minimum += c[j] * x[j];
+    }
+    if (opt[d] == 0.0 || status == LP_UNBOUNDED) {
+      for (int j = 0; j < d; j++) x[j] = opt[j];
+      minimum = -INFINITY;
+    }
+  }
+  __syncwarp();
+  return minimum;
+}
+
+}  // namespace warp
+#endif  // __CUDACC__
+
 }  // namespace poplp

@@ -306,6 +306,19 @@ class PopEngine:
         self._check(self.lib.pop_qp_profile(self._h, n, as_ptr(out, C.c_int64)))
         return out
 
+    def lp_solve(self, c, A, b, seed: int = 1, cooperative: bool = True):
+        """the device LP on its own (diagnostic): min c.x s.t. A x <= b; returns (value, x)"""
+        c = _f64(c)
+        d = len(c)
+        A = _f64(A).reshape(-1, d) if len(b) else np.zeros((0, d))
+        b = _f64(b)
+        x = np.zeros(d)
+        v = C.c_double(0.0)
+        self._check(self.lib.pop_lp_solve(self._h, d, len(b), as_ptr(c, C.c_double), as_ptr(A, C.c_double) if len(b) else None,
+                                          as_ptr(b, C.c_double) if len(b) else None, int(seed), int(bool(cooperative)),
+                                          as_ptr(x, C.c_double), C.byref(v)))
+        return float(v.value), x
+
     def kernel_launches(self) -> int:
         return int(self.lib.pop_kernel_launches(self._h))
 

@@ -3,12 +3,15 @@
 //   :458-475 (closetPointInMap), :477-583 (clearAndInflateLocalMap)
 //   plan_env/src/raycast.cpp:17-31, 242-335 (RayCaster::setInput / step)
 //   plan_env/include/plan_env/grid_map.h:261-420 (index helpers, occupancy getters)
-// The DDA (RayDda below) is PINNED against the reference's own raycast.cpp compiled into oracle/_ref/libref.so:
-// identical voxel sequences on 25 000 rays (tests/test_ref_pins.py).  The rest (grid_map.cpp needs ROS, PCL and
-// OpenCV) is PARITY UNPINNED by the reference's tests (none exist for GridMap); every step is integer counting or a
-// fixed sequence of IEEE double operations.  Quirk kept: flag_rayend_ / flag_traverse_ are vector<char>
-// compared with the int frame counter raycast_num_, so ray-end de-duplication and the early break on voxels
-// traversed by an earlier ray of the same frame only work for the first 127 frames.
+// PINNED against the reference's own sources: the DDA (RayDda below) against raycast.cpp in oracle/_ref/libref.so
+// (identical voxel sequences on 25 000 rays, tests/test_ref_pins.py) and everything else — projectDepthImage, the
+// log-odds update, the shell reset, inflation, the virtual ceiling, both queries — against grid_map.cpp compiled
+// unmodified into oracle/_ref/libref_gridmap.so (ROS, PCL, cv_bridge and Eigen replaced by stand-ins): projected
+// points, occupancy_buffer_ doubles, inflated map and bounds bit for bit over hundreds of frames, live and through
+// committed vectors (tests/test_ref_gridmap_pins.py).  Quirk kept: the frame counter raycast_num_ is a `char`
+// (grid_map.h:140) like the flags it is compared with, so it wraps 127 -> -128 and a flag written 256 frames ago — or
+// the initial -1 of a never-touched voxel, at frame 255 — reads as "already done in this frame".  (Round 1 restated
+// the counter as an int, i.e. no de-duplication after frame 127; the pin against the compiled reference found it.)
 #include <algorithm>
 #include <cmath>
 #include <queue>
@@ -25,8 +28,8 @@ struct GridMapO {
   std::vector<double> occ;
   std::vector<char> inflate;
   std::vector<short> cnt_hm, cnt_hit;
-  std::vector<char> flag_traverse, flag_rayend;
-  int raycast_num = 0;
+  std::vector<signed char> flag_traverse, flag_rayend;
+  signed char raycast_num = 0;   // `char raycast_num_` (grid_map.h:140), signed on the reference's platforms
   int lb_min[3] = {0, 0, 0}, lb_max[3] = {0, 0, 0};
   std::queue<int> cache;   // addresses (the reference queues index triples)
 
@@ -130,7 +133,7 @@ struct RayDda {
 
 void GridMapO::raycast(const double* pts, int np, const double* cam) {
   if (np == 0) return;
-  raycast_num += 1;
+  raycast_num = static_cast<signed char>(raycast_num + 1);   // wraps 127 -> -128
   double mn[3] = {bmax[0], bmax[1], bmax[2]}, mx[3] = {bmin[0], bmin[1], bmin[2]};
   for (int i = 0; i < np; ++i) {
     double pw[3] = {pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]};
@@ -155,8 +158,8 @@ void GridMapO::raycast(const double* pts, int np, const double* cam) {
     }
     for (int k = 0; k < 3; k++) { mx[k] = std::max(mx[k], pw[k]); mn[k] = std::min(mn[k], pw[k]); }
     if (vox >= 0) {
-      if (flag_rayend[vox] == raycast_num) continue;         // char vs int: true only while raycast_num <= 127
-      flag_rayend[vox] = static_cast<char>(raycast_num);
+      if (flag_rayend[vox] == raycast_num) continue;
+      flag_rayend[vox] = raycast_num;
     }
     // RayCaster::setInput(pt_w / res, camera / res) + step loop (:379-395)
     double s[3], e[3], ray[3];
@@ -168,7 +171,7 @@ void GridMapO::raycast(const double* pts, int np, const double* cam) {
       const int v = set_cache(tmp, 0);
       if (v < 0) continue;
       if (flag_traverse[v] == raycast_num) break;
-      flag_traverse[v] = static_cast<char>(raycast_num);
+      flag_traverse[v] = raycast_num;
     }
   }
   for (int k = 0; k < 3; k++) { mn[k] = std::min(mn[k], cam[k]); mx[k] = std::max(mx[k], cam[k]); }

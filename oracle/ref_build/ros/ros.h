@@ -9,6 +9,7 @@
 #include <stdlib.h>   // double — with libstdc++'s <stdlib.h>/<math.h> wrappers visible that is std::abs(double), not abs(int)
 #include <map>
 #include <string>
+#include <type_traits>
 
 namespace ros {
 // time: now() is whatever the test set (ros::Time::set_now), so the reference's wall-clock reads are inputs
@@ -18,6 +19,7 @@ class Time {
   Time() {}
   explicit Time(double s) : sec_(s) {}
   double toSec() const { return sec_; }
+  Time& fromSec(double s) { sec_ = s; return *this; }
   static double& now_value() { static double v = 0.0; return v; }
   static void set_now(double s) { now_value() = s; }
   static Time now() { return Time(now_value()); }
@@ -38,6 +40,7 @@ class Timer {};
 class Publisher {
  public:
   template <class M> void publish(const M&) const {}
+  int getNumSubscribers() const { return 0; }
 };
 
 class NodeHandle {
@@ -54,7 +57,8 @@ class NodeHandle {
       it = global_values().find(name);
       if (it == global_values().end()) { var = dflt; return false; }
     }
-    var = static_cast<T>(it->second);
+    if constexpr (std::is_arithmetic<T>::value) var = static_cast<T>(it->second);
+    else var = dflt;   // strings (frame ids) are not numbers: the default stands
     return true;
   }
   template <class T>
@@ -66,6 +70,9 @@ class NodeHandle {
   }
   // topics and timers are never driven: the tests call the callbacks directly
   template <class... A> Subscriber subscribe(const std::string&, int, A&&...) { return Subscriber(); }
+  // node.subscribe<Msg>(topic, queue, &Class::callback, this): the message type is given, the rest deduced
+  template <class M, class C, class Arg> Subscriber subscribe(const std::string&, int, void (C::*)(Arg), C*,
+                                                               const TransportHints& = TransportHints()) { return Subscriber(); }
   template <class M> Publisher advertise(const std::string&, int, bool = false) { return Publisher(); }
   template <class... A> Timer createTimer(Duration, A&&...) { return Timer(); }
 };

@@ -9,5 +9,6 @@ struct Vector3 { double x = 0, y = 0, z = 0; };
 struct Pose { Point position; Quaternion orientation; };
 struct PoseWithCovariance { Pose pose; };
 struct PoseStamped { Header header; Pose pose; typedef std::shared_ptr<const PoseStamped> ConstPtr; };
+typedef std::shared_ptr<const PoseStamped> PoseStampedConstPtr;
 }  // namespace geometry_msgs
 #endif

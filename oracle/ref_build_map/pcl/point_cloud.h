@@ -4,12 +4,14 @@
 #define POP_PCL_POINT_CLOUD_STANDIN_H
 #include <pcl/point_types.h>
 #include <memory>
+#include <string>
 #include <vector>
 namespace pcl {
 template <class P> struct PointCloud {
   std::vector<P> points;
   uint32_t width = 0, height = 0;
   bool is_dense = true;
+  struct Header { std::string frame_id; uint64_t stamp = 0; uint32_t seq = 0; } header;
   typedef std::shared_ptr<PointCloud<P>> Ptr;
   typedef std::shared_ptr<const PointCloud<P>> ConstPtr;
   void push_back(const P& p) { points.push_back(p); }

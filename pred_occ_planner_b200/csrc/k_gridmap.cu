@@ -8,13 +8,16 @@
 // (flag_rayend_), and a ray stops at the first voxel an EARLIER ray of the same frame traversed
 // (flag_traverse_) — after counting a miss there.  Both are reproduced exactly:
 //   * ray ends: atomicMin of the point index per end voxel;
-//   * traversal: one CTA per map walks the rays in index order.  64 rays at a time are traced in parallel
+//   * traversal: one CTA per map walks the rays in index order.  The casting points are compacted in order and 128
+//     rays at a time are traced in parallel
 //     (Amanatides-Woo DDA in the reference's double arithmetic) into shared-memory path buffers; one warp
 //     then commits them in order against a shared-memory bitmap of the voxels traversed so far (the rays of a
 //     frame live inside a (2R+1)^3 box around the camera, R = max_ray_length / resolution), 32 path voxels
 //     per step with a ballot for the first already-traversed one.
-//   * the reference keeps both flags in vector<char> and compares them with the int frame counter, so from
-//     frame 128 on neither mechanism fires: every point casts a full ray.  Kept (fully parallel path).
+//   * the reference keeps both flags in vector<char> and its frame counter raycast_num_ is a char as well
+//     (grid_map.h:139-140): the counter wraps 127 -> -128, and a stamp written 256 frames ago — or the initial -1 of a
+//     never-touched voxel, at frame 255 — reads as "already done in this frame".  Kept: persistent per-voxel stamps
+//     are preloaded into the bitmap when such a match is possible and written back after every frame.
 // Hit/miss counters are integer atomics; every touched voxel receives exactly one log-odds update per frame,
 // so occupancy_buffer_ is bit-identical to the sequential result.
 #include <cfloat>
@@ -75,6 +78,8 @@ struct GmMap {
   double* pw; int* endv; unsigned long long* bbox;   // bbox: min xyz, max xyz as ordered keys
   int* lb;   // local_bound_min (3), local_bound_max (3)
   int* cast; // indices of the points that cast a ray this frame, in order
+  signed char* flag_rayend;    // the reference's per-voxel frame stamps (grid_map.h:139), persistent, initial -1
+  signed char* flag_traverse;
 };
 
 // K1: clip every projected point, count its end voxel, elect the casting point per end voxel (:337-377)
@@ -82,7 +87,6 @@ __global__ void __launch_bounds__(256) k_gm_points(GmGeo G, const GmMap* __restr
                                                    const int* __restrict__ counts, const double* __restrict__ cam_all,
                                                    const int* __restrict__ flags_work, int* __restrict__ err) {
   const int m = blockIdx.y;
-  const int dedupe = flags_work[m];
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= counts[m]) return;
   const GmMap M = maps[m];
@@ -135,7 +139,7 @@ __global__ void __launch_bounds__(256) k_gm_points(GmGeo G, const GmMap* __restr
     atomicMax(&M.bbox[3 + k], d2ord(pw[k]));
   }
   M.endv[i] = a;
-  if (dedupe && a >= 0) atomicMin(&M.first_end[a], i);
+  if (a >= 0) atomicMin(&M.first_end[a], i);   // the first point of an end voxel is the one that may cast (:370-377)
 }
 
 // DDA of one ray into a path of voxel coordinates relative to the bitmap box (packed 3 x 10 bits); returns length
@@ -187,7 +191,12 @@ __global__ void __launch_bounds__(256) k_gm_rays(GmGeo G, const GmMap* __restric
                                                  int* __restrict__ err, int chunk) {
   extern __shared__ unsigned smem[];
   const int m = blockIdx.x, tid = threadIdx.x;
-  const int prune = flags_work[m];
+  // `char raycast_num_` (grid_map.h:140): the frame counter wraps 127 -> -128, and the per-voxel stamps it is compared
+  // with are chars too, so a stamp written 256 frames ago — or the initial -1 of a never-touched voxel, at frame 255 —
+  // reads as "already done in this frame".  Within a frame the stamps are the bitmap below; the persistent copies are
+  // consulted when such a stale match is possible (frame >= 255) and updated at the end of every frame.
+  const int frame = flags_work[m];
+  const signed char num = static_cast<signed char>(static_cast<unsigned char>(frame & 0xff));
   const GmMap M = maps[m];
   const int np = counts[m];
   if (np == 0) return;
@@ -201,13 +210,34 @@ __global__ void __launch_bounds__(256) k_gm_rays(GmGeo G, const GmMap* __restric
   int* plen = reinterpret_cast<int*>(paths + chunk * kMaxPath);   // chunk
   __shared__ int s_wsum[8], s_ncast;
   for (int i = tid; i < nwords; i += blockDim.x) bitmap[i] = 0u;
-  // the points that cast a ray (not clipped away; with pruning, only the first point of every end voxel), compacted
+  __syncthreads();
+  if (frame >= 255) {   // stale traverse stamps inside the box count as traversed
+    for (int q = tid; q < G.B * G.B; q += blockDim.x) {
+      const int rx = q / G.B, ry = q % G.B, x = rx + box0[0], y = ry + box0[1];
+      if (x < 0 || x >= G.n[0] || y < 0 || y >= G.n[1]) continue;
+      for (int rz = 0; rz < G.B; rz++) {
+        const int z = rz + box0[2];
+        if (z < 0 || z >= G.n[2]) continue;
+        if (M.flag_traverse[(x * G.n[1] + y) * G.n[2] + z] == num) {
+          const int lin = (rx * G.B + ry) * G.B + rz;
+          atomicOr(&bitmap[lin >> 5], 1u << (lin & 31));
+        }
+      }
+    }
+  }
+  // the points that cast a ray (not clipped away; only the first point of every end voxel, and none if the voxel's
+  // ray-end stamp already equals this frame's number), compacted
   // in index order, so that every trace thread of a round below has a ray to walk
   if (tid == 0) s_ncast = 0;
   __syncthreads();
   for (int w0 = 0; w0 < np; w0 += blockDim.x) {
     const int i = w0 + tid;
-    const bool casts = i < np && M.endv[i] != -2 && (!prune || M.endv[i] < 0 || M.first_end[M.endv[i]] == i);
+    bool casts = i < np && M.endv[i] != -2;
+    if (casts && M.endv[i] >= 0) {
+      const int a = M.endv[i];
+      casts = M.first_end[a] == i && M.flag_rayend[a] != num;
+      if (casts) M.flag_rayend[a] = num;   // only the elected point of a voxel reads and writes its stamp
+    }
     const unsigned bal = __ballot_sync(0xffffffffu, casts);
     if ((tid & 31) == 0) s_wsum[tid >> 5] = __popc(bal);
     __syncthreads();
@@ -232,7 +262,7 @@ __global__ void __launch_bounds__(256) k_gm_rays(GmGeo G, const GmMap* __restric
       plen[tid] = len;
     }
     __syncthreads();
-    if (prune) {
+    {
       // commit in index order: warp 0, 32 path voxels per step.  Only the bitmap is order-dependent, so the walk
       // touches shared memory alone and leaves, per ray, how many of its voxels count (up to and including the one
       // that stops it); the counters in global memory are then updated by all threads at once — with the atomics
@@ -270,19 +300,18 @@ __global__ void __launch_bounds__(256) k_gm_rays(GmGeo G, const GmMap* __restric
           gm_count(a, 0, M.cnt_hm, M.cnt_hit, M.touched, M.ntouched);
         }
       }
-    } else {
-      // frames >= 128: no pruning, every traced voxel is a miss
-      for (int e = tid; e < chunk * kMaxPath; e += blockDim.x) {
-        const int r = e / kMaxPath, s = e % kMaxPath;
-        if (s < plen[r]) {
-          const unsigned pk = paths[e];
-          const int rx = pk & 1023, ry = (pk >> 10) & 1023, rz = pk >> 20;
-          const int a = ((rx + box0[0]) * G.n[1] + (ry + box0[1])) * G.n[2] + (rz + box0[2]);
-          gm_count(a, 0, M.cnt_hm, M.cnt_hit, M.touched, M.ntouched);
-        }
-      }
     }
     __syncthreads();
+  }
+  // every voxel traversed in this frame carries the frame's number from now on
+  for (int w = tid; w < nwords; w += blockDim.x) {
+    unsigned bits = bitmap[w];
+    while (bits) {
+      const int lin = w * 32 + __ffs(bits) - 1;
+      bits &= bits - 1;
+      const int rz = lin % G.B, ry = (lin / G.B) % G.B, rx = lin / (G.B * G.B);
+      M.flag_traverse[((rx + box0[0]) * G.n[1] + (ry + box0[1])) * G.n[2] + (rz + box0[2])] = num;
+    }
   }
 }
 
@@ -638,7 +667,13 @@ int pop_gridmap_create(const pop_gridmap_config* c, int n_maps, int device, void
     M.bbox = static_cast<unsigned long long*>(alloc(sizeof(unsigned long long) * 6));
     M.lb = static_cast<int*>(alloc(sizeof(int) * 6));
     M.cast = static_cast<int*>(alloc(sizeof(int) * c->max_points));
-    ok = M.occ && M.inflate && M.cnt_hm && M.cnt_hit && M.first_end && M.touched && M.ntouched && M.pw && M.endv && M.bbox && M.lb && M.cast;
+    M.flag_rayend = static_cast<signed char*>(alloc(N));
+    M.flag_traverse = static_cast<signed char*>(alloc(N));
+    if (M.flag_rayend && M.flag_traverse) {
+      cudaMemsetAsync(M.flag_rayend, 0xff, N, g->stream);
+      cudaMemsetAsync(M.flag_traverse, 0xff, N, g->stream);
+    }
+    ok = M.occ && M.inflate && M.cnt_hm && M.cnt_hit && M.first_end && M.touched && M.ntouched && M.pw && M.endv && M.bbox && M.lb && M.cast && M.flag_rayend && M.flag_traverse;
     if (ok) k_gm_fill<<<static_cast<unsigned>((N + 255) / 256), 256, 0, g->stream>>>(M.occ, N, G.unk, M.first_end);
   }
   g->d_maps = static_cast<GmMap*>(alloc(sizeof(GmMap) * n_maps));
@@ -667,7 +702,7 @@ static int gm_run(pop_gridmap* g, const int32_t* counts) {
   std::vector<int> flags_work(A);
   for (int m = 0; m < A; m++) {
     if (counts[m] > 0) g->frame[m] += 1;           // md_.raycast_num_
-    flags_work[m] = g->frame[m] <= 127;            // vector<char> flags vs the int counter
+    flags_work[m] = g->frame[m];                   // the kernels take the char it wraps to
   }
   GM_CUDA(g, cudaMemcpyAsync(g->d_flags, flags_work.data(), sizeof(int) * A, cudaMemcpyHostToDevice, st));
   GM_CUDA(g, cudaStreamSynchronize(st));           // flags_work is stack-owned

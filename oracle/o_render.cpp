@@ -2,8 +2,10 @@
 //   uav_simulator/local_sensing/src/depth_render.cu:2-58   (render / depth_initial kernels, restated on the CPU)
 //   uav_simulator/local_sensing/src/pcl_render_node.cpp:108-136 (cam2world from the odometry), :219-254
 //   (render_pcl_world: depth image -> points, sensing horizon), :263-285 (render_currentpose: mm -> metres)
-// PARITY UNPINNED by the reference's tests (it has none for the sensor); every step is integer or a fixed
-// sequence of IEEE operations, so the restatement is deterministic.  Deviations, documented: the camera pose
+// render_depth is PINNED against the reference's own kernel: depth_render.cu compiled unmodified by nvcc into
+// oracle/_ref/libref_depth.so and run on the GPU gives the same depth images, pixel for pixel
+// (tests/test_gpu_zz_reference_depth.py).  The node around it (pose handling, image -> cloud) is restated without a
+// pin; every step is integer or a fixed sequence of IEEE operations, so the restatement is deterministic.  Deviations, documented: the camera pose
 // is inverted as a rigid transform (Rᵀ, −Rᵀt) instead of Eigen's general 4x4 inverse; points are returned in
 // the CAMERA frame (what filterPointCloud consumes) as well as in the world frame the node publishes.
 #include <algorithm>

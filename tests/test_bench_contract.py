@@ -5,6 +5,8 @@ import os
 import subprocess
 import sys
 
+import numpy as np
+
 from tests.conftest import ROOT
 
 
@@ -42,3 +44,21 @@ def test_reference_arm_does_not_load_libpop():
             "maps = open('/proc/self/maps').read(); assert 'liboracle.so' in maps; assert 'libpop.so' not in maps" % os.path.join(ROOT, "bench.py"))
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stderr[-2000:]
+
+
+def test_arenas_are_tiled_compactly_around_the_origin():
+    """Weak scaling flies one arena per rank; the reference's OSQP tolerance grows with |coordinate|,
+    so the arenas are packed around the origin: distinct slots one pitch apart, centred, and every coordinate of the
+    8-rank layout within 1.5 pitches + half an arena."""
+    import bench
+    for world in (1, 2, 4, 8):
+        slots = [bench.arena_origin(r, world, 32.0) for r in range(world)]
+        assert len(set(slots)) == world
+        xs, ys = np.array([s[0] for s in slots]), np.array([s[1] for s in slots])
+        assert max(abs(xs).max(), abs(ys).max()) <= 32.0 * (1.0 if world > 4 else 0.5) + 1e-9
+        for i in range(world):
+            for j in range(i):
+                assert max(abs(xs[i] - xs[j]), abs(ys[i] - ys[j])) >= 32.0 - 1e-9     # arenas (30 m) do not overlap
+    sc = bench.Scenario("c2", 64, 128, 64)          # rank 1 of 2
+    assert np.allclose(sc.start_all[64:, :2].mean(axis=0), sc.origin[:2], atol=1e-6)   # its agents circle its own arena
+    assert np.allclose(sc.cyl0["x"].mean(), sc.origin[0], atol=3.0)
